@@ -1,0 +1,215 @@
+/*
+ * lol_b200.h -- C ABI of libctensor_b200.so, the B200 (sm_100a) back end for
+ * Lol's cyclotomic `Tensor` hot path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) DROP-IN SYMBOLS.  The 29 `extern "C"` functions that
+ *      lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Backend.hs:304-337 imports with
+ *      `foreign import ccall unsafe`, with the reference's exact names and C
+ *      signatures (crt.cpp:562-598, l.cpp:109-180, g.cpp:125-273,
+ *      norm.cpp:39,61, random.cpp:61, mul.cpp:27,32).  Host pointers, one ring
+ *      element per call, in place, the caller keeps ownership, nothing is
+ *      retained after return.  Each call stages the element to the GPU, runs
+ *      the same CUDA kernels as group (2) and copies the result back.  There is
+ *      no CPU implementation behind them: without a usable CUDA device they
+ *      print a diagnostic and abort(), as the reference's ASSERT does
+ *      (types.h:36-41).
+ *
+ *  (2) BATCHED, DEVICE-RESIDENT ENTRY POINTS (`lolb_*`).  What a
+ *      `Crypto.Lol.Cyclotomic.Tensor.CUDA` instance binds in place of the
+ *      per-element calls: a plan holds the per-(m, moduli) tables on the
+ *      device; every operator takes a device pointer to `batch` ring elements
+ *      laid out back to back in the reference's element layout and a CUDA
+ *      stream, launches asynchronously and returns a status.
+ *
+ * Element layout (both groups; reference: tensor.h:69,91 and the tuple
+ * `Storable` instance at Backend.hs:80-90): coefficient j of RNS limb t of
+ * element b is  y[(b*totm + j)*tupSize + t];  Zq coefficients are int64 in
+ * [0, q_t) on entry and exit (zq.cpp:57-67), complex coefficients are
+ * {double re, double im} (types.h:122-126).  The tensor index is
+ * j = i_1 + phi_1*(i_2 + phi_2*(...)) with prime powers in increasing prime
+ * order, the first one fastest (tensor.h:44-73; FactoredDefs.hs:92-94).
+ */
+#ifndef LOL_B200_H_
+#define LOL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ types */
+
+typedef int64_t hInt_t;   /* reference: types.h:21 */
+typedef int32_t hDim_t;   /* reference: types.h:22 (Haskell passes Int64; the low 32 bits are read) */
+typedef int16_t hShort_t; /* reference: types.h:23 */
+
+/* reference: types.h:27-31; Haskell side `type CPP = (Int16, Int16)` (Backend.hs:78) */
+typedef struct { hShort_t prime; hShort_t exponent; } PrimeExponent;
+
+/* reference: types.h:122-126 (class Complex is {double real; double imag;}) */
+typedef struct { double real; double imag; } lolb_complex;
+
+/* ------------------------------------------------- (1) drop-in symbols ---- */
+
+/* replaces crt.cpp:562-566 */
+void tensorCRTRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t** ru, hInt_t* qs);
+/* replaces crt.cpp:569-581 */
+void tensorCRTInvRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t** ruinv, hInt_t* mhatInv, hInt_t* qs);
+/* replaces crt.cpp:583-586 */
+void tensorCRTC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, lolb_complex** ru);
+/* replaces crt.cpp:589-598 */
+void tensorCRTInvC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, lolb_complex** ruinv, lolb_complex* mhatInv);
+
+/* replace l.cpp:109-115, 125-139, 150-156, 166-180 */
+void tensorLRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs);
+void tensorLInvRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs);
+void tensorLR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorLInvR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorLDouble(hShort_t tupSize, double* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorLInvDouble(hShort_t tupSize, double* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorLC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorLInvC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+
+/* replace norm.cpp:39-59, 61-80: result in y[0 .. tupSize); the rest of y is
+ * left untouched (the reference leaves its scratch transform there; the
+ * Haskell caller reads index 0 only, CPP.hs:344-346) */
+void tensorNormSqR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorNormSqD(hShort_t tupSize, double* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+
+/* replace g.cpp:125-155 */
+void tensorGPowR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorGPowRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs);
+void tensorGPowC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorGDecR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+void tensorGDecRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs);
+void tensorGDecC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+
+/* replace g.cpp:169-273.  Return 1 = ok, 0 = not divisible by g (R), or
+ * rad_odd(m) not invertible mod some q (Rq) -> Haskell `Nothing`
+ * (CPP.hs:309-323).  The R and C variants implement the documented intent
+ * (exact / real division by rad_odd(m)), not the defects at g.cpp:175-182 and
+ * g.cpp:213-218; see DESIGN.md "reference quirks". */
+hShort_t tensorGInvPowR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+hShort_t tensorGInvPowRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs);
+hShort_t tensorGInvPowC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+hShort_t tensorGInvDecR(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+hShort_t tensorGInvDecRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs);
+hShort_t tensorGInvDecC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE);
+
+/* replaces random.cpp:61-64 */
+void tensorGaussianDec(hShort_t tupSize, double* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, lolb_complex** ru);
+
+/* replace mul.cpp:27-30, 32-35 */
+void mulRq(hShort_t tupSize, hInt_t* a, hInt_t* b, hDim_t totm, hInt_t* qs);
+void mulC(hShort_t tupSize, lolb_complex* a, lolb_complex* b, hDim_t totm);
+
+/* ------------------------------------- (2) batched, device-resident API --- */
+
+typedef struct lolb_plan lolb_plan;
+
+/* status codes of every lolb_* function returning int */
+#define LOLB_OK            0
+#define LOLB_ERR_ARG       1   /* bad argument (NULL, totm mismatch, q out of range ...) */
+#define LOLB_ERR_NO_CRT    2   /* some q is not prime or m does not divide q-1 (ZqBasic.hs:159-165) */
+#define LOLB_ERR_CUDA      3   /* CUDA runtime error; lolb_last_error() has the text */
+#define LOLB_ERR_NOT_INVERTIBLE 4 /* rad_odd(m) not invertible mod some q (g.cpp:193-199): Haskell `Nothing` */
+
+/* text of the last error on the calling thread ("" if none) */
+const char* lolb_last_error(void);
+/* number of CUDA kernels launched by this library in this process so far */
+int64_t lolb_kernel_launch_count(void);
+/* 1 if a CUDA device is usable, else 0 (never falls back to the CPU) */
+int lolb_device_available(void);
+
+/*
+ * Plan over Z_q1 x ... x Z_qk for index m = prod peArr (prime powers in
+ * increasing prime order, as `ppsFact` gives them).  Root tables:
+ *   ru / ruinv / mhatInv  as the drop-in symbols take them (host pointers,
+ *   ru[i][j*tupSize + t] = w_t^{+-j*m/p_i^e_i}, CPP.hs:422-442), or all NULL to
+ *   let the library derive them exactly as the Haskell side does
+ *   (smallest generator of Z_q^*, ZqBasic.hs:144-171).  With NULL tables and a
+ *   modulus without a CRT the plan is still created and serves L / G / mul;
+ *   the CRT entry points then return LOLB_ERR_NO_CRT.
+ */
+int lolb_plan_create_rq(lolb_plan** out, const PrimeExponent* peArr, hShort_t sizeOfPE, hShort_t tupSize,
+                        const hInt_t* qs, hInt_t* const* ru, hInt_t* const* ruinv, const hInt_t* mhatInv);
+/* Plan for the modulus-free rings (int64 "R", double, complex): roots are cis(2 pi j / p^e) (CRTrans.hs:88-95). */
+int lolb_plan_create_c(lolb_plan** out, const PrimeExponent* peArr, hShort_t sizeOfPE, hShort_t tupSize);
+void lolb_plan_destroy(lolb_plan* plan);
+
+int32_t lolb_plan_totient(const lolb_plan* plan);   /* n = phi(m) */
+int32_t lolb_plan_tupsize(const lolb_plan* plan);
+/* copy the plan's own tables out (host buffers sized like the drop-in arguments); for cross-checking */
+int lolb_plan_get_ru_rq(const lolb_plan* plan, int inverse, int pp_index, hInt_t* out /* p^e * tupSize */);
+int lolb_plan_get_mhatinv_rq(const lolb_plan* plan, hInt_t* out /* tupSize */);
+/* gCRT / gInvCRT vectors (Tensor.hs:290-337; CPP.hs:451-454) resident on the device: [totm][tupSize] int64 */
+const hInt_t* lolb_plan_gcrt_dev(const lolb_plan* plan, int inverse);
+/* force the generic pass engine instead of a fused kernel (testing / profiling) */
+void lolb_plan_set_force_generic(lolb_plan* plan, int on);
+/* name of the kernel family an operator will use: "fused_a", "pow2", "generic", ... */
+const char* lolb_plan_kernel_name(const lolb_plan* plan, const char* op);
+
+/*
+ * Batched operators.  `y` is a DEVICE pointer to batch*totm*tupSize
+ * coefficients, transformed in place.  `stream` is a cudaStream_t (NULL =
+ * legacy default stream).  Asynchronous: the call returns after the launch.
+ * Same operator, same result bit for bit, as `batch` calls of the drop-in
+ * symbol of the same name.
+ */
+int lolb_tensorCRTRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorCRTInvRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorLRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorLInvRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorGPowRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorGDecRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorGInvPowRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);   /* LOLB_ERR_NOT_INVERTIBLE = reference's 0 */
+int lolb_tensorGInvDecRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+/* a[i] <- a[i] * b[i]; b holds `b_batch` elements (1 = broadcast one element, e.g. gCRT; else == batch) */
+int lolb_mulRq(const lolb_plan* plan, hInt_t* a, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream);
+
+/* modulus-free rings; plan from lolb_plan_create_c */
+int lolb_tensorLR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorLInvR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorGPowR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+int lolb_tensorGDecR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
+/* ok[b] (device, int16) <- 1 if element b was divisible by g and has been divided, else 0 (element then holds the undivided transform) */
+int lolb_tensorGInvPowR(const lolb_plan* plan, hInt_t* y, hShort_t* ok, int64_t batch, void* stream);
+int lolb_tensorGInvDecR(const lolb_plan* plan, hInt_t* y, hShort_t* ok, int64_t batch, void* stream);
+int lolb_tensorLDouble(const lolb_plan* plan, double* y, int64_t batch, void* stream);
+int lolb_tensorLInvDouble(const lolb_plan* plan, double* y, int64_t batch, void* stream);
+int lolb_tensorLC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorLInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorGPowC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorGDecC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorGInvPowC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorGInvDecC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorCRTC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_tensorCRTInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream);
+int lolb_mulC(const lolb_plan* plan, lolb_complex* a, const lolb_complex* b, int64_t batch, int64_t b_batch, void* stream);
+/* y: batch elements of totm*tupSize doubles, i.i.d. Gaussians in, decoding-basis coefficients out (random.cpp:61-64) */
+int lolb_tensorGaussianDec(const lolb_plan* plan, double* y, int64_t batch, void* stream);
+/* out[b*tupSize + t] (device) <- the value the drop-in symbol leaves in y[t]; y is not modified */
+int lolb_tensorNormSqR(const lolb_plan* plan, const hInt_t* y, hInt_t* out, int64_t batch, void* stream);
+int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double* out, int64_t batch, void* stream);
+
+/*
+ * Host-buffer batched calls (what an FFI caller with Haskell-owned vectors
+ * uses): `y` is a HOST pointer to batch elements; the call pipelines
+ * host->device copy, kernel(s) and device->host copy over chunks on internal
+ * streams and returns when the result is back in `y`.  `ops` is a
+ * NUL-terminated list of operator names separated by ',' applied in order,
+ * e.g. "CRT", "CRT,CRTInv", "L,GPow" (names as in the drop-in symbols, without
+ * the `tensor` prefix and ring suffix).
+ */
+int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t* y, int64_t batch);
+/* pinned host memory for the above (cudaHostAlloc / cudaFreeHost) */
+void* lolb_host_alloc(uint64_t bytes);
+void lolb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOL_B200_H_ */

@@ -1,0 +1,298 @@
+"""ctypes binding of libctensor_b200.so (include/lol_b200.h).
+
+Plain pointers and sizes only: device buffers are passed as integer addresses
+(`tensor.data_ptr()`), streams as `cudaStream_t` handles.  Loading the library
+needs no GPU; every operator call does and raises `LolB200Error` otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import library_path
+
+_i16, _i32, _i64, _p = C.c_int16, C.c_int32, C.c_int64, C.c_void_p
+
+LOLB_OK = 0
+LOLB_ERR_ARG = 1
+LOLB_ERR_NO_CRT = 2
+LOLB_ERR_CUDA = 3
+LOLB_ERR_NOT_INVERTIBLE = 4
+
+
+class LolB200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libctensor_b200 status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The shared library.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it with `python -m lol_b200.build` "
+                "(libctensor_b200 has no CPU or pure-Python fallback)")
+        _lib = C.CDLL(path)
+        _lib.lolb_last_error.restype = C.c_char_p
+        _lib.lolb_kernel_launch_count.restype = _i64
+        _lib.lolb_plan_gcrt_dev.restype = _p
+        _lib.lolb_plan_kernel_name.restype = C.c_char_p
+        _lib.lolb_host_alloc.restype = _p
+        _lib.lolb_host_alloc.argtypes = [C.c_uint64]
+        _lib.lolb_host_free.argtypes = [_p]
+    return _lib
+
+
+def last_error() -> str:
+    return lib().lolb_last_error().decode()
+
+
+def kernel_launch_count() -> int:
+    return int(lib().lolb_kernel_launch_count())
+
+
+def device_available() -> bool:
+    return bool(lib().lolb_device_available())
+
+
+def check(status: int) -> None:
+    if status != LOLB_OK:
+        raise LolB200Error(status, last_error())
+
+
+def pe_array(pps) -> np.ndarray:
+    """[(p, e), ...] -> PrimeExponent[] (int16 pairs)."""
+    return np.ascontiguousarray(np.array(list(pps), dtype=np.int16).reshape(-1, 2))
+
+
+def _ptr_array(tables):
+    return (_p * len(tables))(*[t.ctypes.data for t in tables])
+
+
+class PlanRq:
+    """lolb_plan over Z_q1 x ... x Z_qk (lolb_plan_create_rq)."""
+
+    def __init__(self, pps, qs, ru=None, ruinv=None, mhatinv=None):
+        self.pps = [(int(p), int(e)) for p, e in pps]
+        self.qs = [int(q) for q in qs]
+        self.k = len(self.qs)
+        pe = pe_array(self.pps)
+        qarr = np.ascontiguousarray(self.qs, dtype=np.int64)
+        keep = []
+        ru_p = ruinv_p = mh_p = None
+        if ru is not None:
+            ru = [np.ascontiguousarray(t, dtype=np.int64) for t in ru]
+            keep.append(ru)
+            ru_p = _ptr_array(ru)
+        if ruinv is not None:
+            ruinv = [np.ascontiguousarray(t, dtype=np.int64) for t in ruinv]
+            mh = np.ascontiguousarray(mhatinv, dtype=np.int64)
+            keep += [ruinv, mh]
+            ruinv_p, mh_p = _ptr_array(ruinv), mh.ctypes.data_as(_p)
+        self._h = _p()
+        check(lib().lolb_plan_create_rq(C.byref(self._h), pe.ctypes.data_as(_p), _i16(len(self.pps)), _i16(self.k),
+                                        qarr.ctypes.data_as(_p), ru_p, ruinv_p, mh_p))
+        self.n = int(lib().lolb_plan_totient(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().lolb_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def force_generic(self, on: bool = True) -> None:
+        lib().lolb_plan_set_force_generic(self._h, int(on))
+
+    def kernel_name(self, op: str) -> str:
+        return lib().lolb_plan_kernel_name(self._h, op.encode()).decode()
+
+    def ru_table(self, pp_index: int, inverse: bool = False) -> np.ndarray:
+        p, e = self.pps[pp_index]
+        out = np.empty((p ** e, self.k), dtype=np.int64)
+        check(lib().lolb_plan_get_ru_rq(self._h, int(inverse), pp_index, out.ctypes.data_as(_p)))
+        return out
+
+    def mhatinv(self) -> np.ndarray:
+        out = np.empty(self.k, dtype=np.int64)
+        check(lib().lolb_plan_get_mhatinv_rq(self._h, out.ctypes.data_as(_p)))
+        return out
+
+    def gcrt_dev(self, inverse: bool = False) -> int:
+        return int(lib().lolb_plan_gcrt_dev(self._h, int(inverse)) or 0)
+
+    # device-pointer operators: `ptr` an integer device address, `stream` a cudaStream_t handle (int)
+    def op(self, name: str, ptr: int, batch: int, stream: int = 0) -> int:
+        f = getattr(lib(), "lolb_tensor" + name + "Rq")
+        return int(f(self._h, _p(ptr), _i64(batch), _p(stream)))
+
+    def mul(self, a_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_mulRq(self._h, _p(a_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
+
+    def apply_host(self, ops: str, host_ptr: int, batch: int) -> int:
+        return int(lib().lolb_rq_apply_host(self._h, ops.encode(), _p(host_ptr), _i64(batch)))
+
+
+class PlanC:
+    """lolb_plan for the modulus-free rings: int64 'R', double, complex (lolb_plan_create_c)."""
+
+    def __init__(self, pps, k: int = 1):
+        self.pps = [(int(p), int(e)) for p, e in pps]
+        self.k = int(k)
+        pe = pe_array(self.pps)
+        self._h = _p()
+        check(lib().lolb_plan_create_c(C.byref(self._h), pe.ctypes.data_as(_p), _i16(len(self.pps)), _i16(self.k)))
+        self.n = int(lib().lolb_plan_totient(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().lolb_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def op(self, name: str, ptr: int, batch: int, stream: int = 0) -> int:
+        """name: 'LR', 'LInvDouble', 'GPowC', 'CRTC', 'CRTInvC', 'GaussianDec', 'GInvPowC', ..."""
+        f = getattr(lib(), "lolb_tensor" + name)
+        return int(f(self._h, _p(ptr), _i64(batch), _p(stream)))
+
+    def ginv_r(self, name: str, ptr: int, ok_ptr: int, batch: int, stream: int = 0) -> int:
+        f = getattr(lib(), "lolb_tensor" + name + "R")
+        return int(f(self._h, _p(ptr), _p(ok_ptr), _i64(batch), _p(stream)))
+
+    def normsq(self, tag: str, ptr: int, out_ptr: int, batch: int, stream: int = 0) -> int:
+        f = getattr(lib(), "lolb_tensorNormSq" + tag)
+        return int(f(self._h, _p(ptr), _p(out_ptr), _i64(batch), _p(stream)))
+
+    def mul(self, a_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_mulC(self._h, _p(a_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
+
+
+# ------------------------------------------------------------------ drop-in symbols over numpy (host pointers)
+class DropIn:
+    """The 29 reference symbols exactly as Backend.hs imports them, driven with numpy host
+    arrays (one element per call, in place on a copy)."""
+
+    def _basic(self, name, y, pe, k, dtype, qs=None, status=False):
+        y = np.array(y, dtype=dtype, order="C", copy=True)
+        pe = pe_array(pe)
+        totm = y.size // k
+        f = getattr(lib(), name)
+        f.restype = _i16 if status else None
+        args = [_i16(k), y.ctypes.data_as(_p), _i32(totm), pe.ctypes.data_as(_p), _i16(len(pe))]
+        if qs is not None:
+            qarr = np.ascontiguousarray(qs, dtype=np.int64)
+            args.append(qarr.ctypes.data_as(_p))
+        ret = f(*args)
+        return (y, int(ret)) if status else y
+
+    def tensorCRTRq(self, y, pe, ru, qs):
+        k = len(qs)
+        y = np.array(y, dtype=np.int64, order="C", copy=True)
+        pe = pe_array(pe)
+        ru = [np.ascontiguousarray(t, dtype=np.int64) for t in ru]
+        qarr = np.ascontiguousarray(qs, dtype=np.int64)
+        f = lib().tensorCRTRq
+        f.restype = None
+        f(_i16(k), y.ctypes.data_as(_p), _i32(y.size // k), pe.ctypes.data_as(_p), _i16(len(pe)), _ptr_array(ru), qarr.ctypes.data_as(_p))
+        return y
+
+    def tensorCRTInvRq(self, y, pe, ruinv, mhatinv, qs):
+        k = len(qs)
+        y = np.array(y, dtype=np.int64, order="C", copy=True)
+        pe = pe_array(pe)
+        ruinv = [np.ascontiguousarray(t, dtype=np.int64) for t in ruinv]
+        mh = np.ascontiguousarray(mhatinv, dtype=np.int64)
+        qarr = np.ascontiguousarray(qs, dtype=np.int64)
+        f = lib().tensorCRTInvRq
+        f.restype = None
+        f(_i16(k), y.ctypes.data_as(_p), _i32(y.size // k), pe.ctypes.data_as(_p), _i16(len(pe)), _ptr_array(ruinv),
+          mh.ctypes.data_as(_p), qarr.ctypes.data_as(_p))
+        return y
+
+    def tensorCRTC(self, y, pe, ru, k=1):
+        y = np.array(y, dtype=np.complex128, order="C", copy=True)
+        pe = pe_array(pe)
+        ru = [np.ascontiguousarray(t, dtype=np.complex128) for t in ru]
+        f = lib().tensorCRTC
+        f.restype = None
+        f(_i16(k), y.ctypes.data_as(_p), _i32(y.size // k), pe.ctypes.data_as(_p), _i16(len(pe)), _ptr_array(ru))
+        return y
+
+    def tensorCRTInvC(self, y, pe, ruinv, mhatinv, k=1):
+        y = np.array(y, dtype=np.complex128, order="C", copy=True)
+        pe = pe_array(pe)
+        ruinv = [np.ascontiguousarray(t, dtype=np.complex128) for t in ruinv]
+        mh = np.ascontiguousarray(mhatinv, dtype=np.complex128)
+        f = lib().tensorCRTInvC
+        f.restype = None
+        f(_i16(k), y.ctypes.data_as(_p), _i32(y.size // k), pe.ctypes.data_as(_p), _i16(len(pe)), _ptr_array(ruinv), mh.ctypes.data_as(_p))
+        return y
+
+    def tensorGaussianDec(self, y, pe, ru, k=1):
+        y = np.array(y, dtype=np.float64, order="C", copy=True)
+        pe = pe_array(pe)
+        ru = [np.ascontiguousarray(t, dtype=np.complex128) for t in ru]
+        f = lib().tensorGaussianDec
+        f.restype = None
+        f(_i16(k), y.ctypes.data_as(_p), _i32(y.size // k), pe.ctypes.data_as(_p), _i16(len(pe)), _ptr_array(ru))
+        return y
+
+    def tensorLRq(self, y, pe, qs): return self._basic("tensorLRq", y, pe, len(qs), np.int64, qs)
+    def tensorLInvRq(self, y, pe, qs): return self._basic("tensorLInvRq", y, pe, len(qs), np.int64, qs)
+    def tensorGPowRq(self, y, pe, qs): return self._basic("tensorGPowRq", y, pe, len(qs), np.int64, qs)
+    def tensorGDecRq(self, y, pe, qs): return self._basic("tensorGDecRq", y, pe, len(qs), np.int64, qs)
+    def tensorGInvPowRq(self, y, pe, qs): return self._basic("tensorGInvPowRq", y, pe, len(qs), np.int64, qs, status=True)
+    def tensorGInvDecRq(self, y, pe, qs): return self._basic("tensorGInvDecRq", y, pe, len(qs), np.int64, qs, status=True)
+    def tensorLR(self, y, pe, k=1): return self._basic("tensorLR", y, pe, k, np.int64)
+    def tensorLInvR(self, y, pe, k=1): return self._basic("tensorLInvR", y, pe, k, np.int64)
+    def tensorGPowR(self, y, pe, k=1): return self._basic("tensorGPowR", y, pe, k, np.int64)
+    def tensorGDecR(self, y, pe, k=1): return self._basic("tensorGDecR", y, pe, k, np.int64)
+    def tensorGInvPowR(self, y, pe, k=1): return self._basic("tensorGInvPowR", y, pe, k, np.int64, status=True)
+    def tensorGInvDecR(self, y, pe, k=1): return self._basic("tensorGInvDecR", y, pe, k, np.int64, status=True)
+    def tensorNormSqR(self, y, pe, k=1): return self._basic("tensorNormSqR", y, pe, k, np.int64)
+    def tensorLDouble(self, y, pe, k=1): return self._basic("tensorLDouble", y, pe, k, np.float64)
+    def tensorLInvDouble(self, y, pe, k=1): return self._basic("tensorLInvDouble", y, pe, k, np.float64)
+    def tensorNormSqD(self, y, pe, k=1): return self._basic("tensorNormSqD", y, pe, k, np.float64)
+    def tensorLC(self, y, pe, k=1): return self._basic("tensorLC", y, pe, k, np.complex128)
+    def tensorLInvC(self, y, pe, k=1): return self._basic("tensorLInvC", y, pe, k, np.complex128)
+    def tensorGPowC(self, y, pe, k=1): return self._basic("tensorGPowC", y, pe, k, np.complex128)
+    def tensorGDecC(self, y, pe, k=1): return self._basic("tensorGDecC", y, pe, k, np.complex128)
+    def tensorGInvPowC(self, y, pe, k=1): return self._basic("tensorGInvPowC", y, pe, k, np.complex128, status=True)
+    def tensorGInvDecC(self, y, pe, k=1): return self._basic("tensorGInvDecC", y, pe, k, np.complex128, status=True)
+
+    def mulRq(self, a, b, qs):
+        k = len(qs)
+        a = np.array(a, dtype=np.int64, order="C", copy=True)
+        b = np.ascontiguousarray(b, dtype=np.int64)
+        qarr = np.ascontiguousarray(qs, dtype=np.int64)
+        f = lib().mulRq
+        f.restype = None
+        f(_i16(k), a.ctypes.data_as(_p), b.ctypes.data_as(_p), _i32(a.size // k), qarr.ctypes.data_as(_p))
+        return a
+
+    def mulC(self, a, b, k=1):
+        a = np.array(a, dtype=np.complex128, order="C", copy=True)
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        f = lib().mulC
+        f.restype = None
+        f(_i16(k), a.ctypes.data_as(_p), b.ctypes.data_as(_p), _i32(a.size // k))
+        return a

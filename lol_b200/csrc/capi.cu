@@ -1,0 +1,710 @@
+// capi.cu -- the C ABI of libctensor_b200.so (include/lol_b200.h): plan management, the batched
+// device-resident operators, the host-batched pipeline and the 29 drop-in symbols of
+// lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Backend.hs:304-337.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "fused.cuh"
+#include "lolb_internal.cuh"
+#include "numtheory.h"
+
+using namespace lolb;
+
+// ------------------------------------------------------------------ errors / counters
+namespace lolb {
+
+static thread_local std::string t_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+  t_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return LOLB_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace lolb
+
+extern "C" const char* lolb_last_error(void) { return t_last_error.c_str(); }
+extern "C" int64_t lolb_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int lolb_device_available(void)
+{
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count > 0 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ plans
+
+static void fill_zq_consts(lolb_plan* pl)
+{
+  for (int t = 0; t < pl->k; t++) {
+    const uint64_t q = (uint64_t)pl->qs[t];
+    const uint64_t mu = (uint64_t)((((u128)1) << 64) / q);
+    ZqConsts* all[3] = {&pl->zq_plain, &pl->zq_mhat, &pl->zq_radinv};
+    for (ZqConsts* c : all) { c->q[t] = (uint32_t)q; c->mu[t] = mu; c->scale[t] = 1u % (uint32_t)q; }
+  }
+  pl->ginv_ok = true;
+  for (int t = 0; t < pl->k; t++) {
+    const int64_t inv = mod_inverse(pl->qs[t], pl->odd_rad % pl->qs[t]);   // g.cpp:193-199
+    if (inv == 0) pl->ginv_ok = false;
+    pl->zq_radinv.scale[t] = (uint32_t)inv;
+  }
+}
+
+static int copy_tables(const lolb_plan* pl, hInt_t* const* src, std::vector<std::vector<int64_t>>* dst)
+{
+  const int npe = (int)pl->pe.size();
+  dst->assign(npe, {});
+  for (int i = 0; i < npe; i++) {
+    if (!src[i]) { set_error("plan: NULL root table"); return LOLB_ERR_ARG; }
+    const size_t cnt = (size_t)ipow64(pl->pe[i].prime, pl->pe[i].exponent) * pl->k;
+    (*dst)[i].assign(src[i], src[i] + cnt);
+  }
+  return LOLB_OK;
+}
+
+static uint64_t hash_tables(const lolb_plan* pl, const void* const* tabs, size_t elem_bytes, const void* extra, size_t extra_bytes)
+{
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < pl->pe.size(); i++)
+    h = hash_bytes(tabs[i], (size_t)ipow64(pl->pe[i].prime, pl->pe[i].exponent) * pl->k * elem_bytes, h);
+  if (extra) h = hash_bytes(extra, extra_bytes, h);
+  return h;
+}
+
+extern "C" int lolb_plan_create_rq(lolb_plan** out, const PrimeExponent* peArr, hShort_t sizeOfPE, hShort_t tupSize,
+                                   const hInt_t* qs, hInt_t* const* ru, hInt_t* const* ruinv, const hInt_t* mhatInv)
+{
+  if (!out || !qs) { set_error("lolb_plan_create_rq: NULL argument"); return LOLB_ERR_ARG; }
+  *out = nullptr;
+  lolb_plan* pl = new lolb_plan();
+  pl->kind = PLAN_RQ;
+  int rc = plan_build_common(pl, peArr, sizeOfPE, tupSize);
+  if (rc) { delete pl; return rc; }
+  pl->qs.assign(qs, qs + tupSize);
+  for (int t = 0; t < tupSize; t++)
+    if (qs[t] < 2 || qs[t] >= ((int64_t)1 << 32)) { set_error("lolb_plan_create_rq: modulus out of range [2, 2^32)"); delete pl; return LOLB_ERR_ARG; }
+  fill_zq_consts(pl);
+  if (ru || ruinv) {
+    if (ru) { rc = copy_tables(pl, ru, &pl->ru); if (!rc) rc = plan_upload_rq_dir(pl, false); }
+    if (!rc && ruinv) {
+      if (!mhatInv) { set_error("lolb_plan_create_rq: ruinv without mhatInv"); rc = LOLB_ERR_ARG; }
+      if (!rc) rc = copy_tables(pl, ruinv, &pl->ruinv);
+      if (!rc) { pl->mhatinv.assign(mhatInv, mhatInv + tupSize); rc = plan_upload_rq_dir(pl, true); }
+    }
+    if (!rc && ru) rc = plan_upload_rq_gcrt(pl);
+  } else {
+    rc = plan_derive_rq_roots(pl);
+    if (rc == LOLB_OK) {
+      rc = plan_upload_rq_dir(pl, false);
+      if (!rc) rc = plan_upload_rq_dir(pl, true);
+      if (!rc) rc = plan_upload_rq_gcrt(pl);
+    } else if (rc == LOLB_ERR_NO_CRT) {
+      rc = LOLB_OK;   // still serves L / G / mul
+    }
+  }
+  if (!rc) rc = fused_select(pl);
+  if (rc) { lolb_plan_destroy(pl); return rc; }
+  *out = pl;
+  return LOLB_OK;
+}
+
+static int plan_set_c_tables(lolb_plan* pl, lolb_complex* const* ru, lolb_complex* const* ruinv, const lolb_complex* mhatInv)
+{
+  const int npe = (int)pl->pe.size();
+  int rc = LOLB_OK;
+  if (ru) {
+    pl->cru.assign(npe, {});
+    for (int i = 0; i < npe; i++) {
+      const size_t cnt = (size_t)ipow64(pl->pe[i].prime, pl->pe[i].exponent) * pl->k;
+      pl->cru[i].assign(ru[i], ru[i] + cnt);
+    }
+    rc = plan_upload_c_dir(pl, false);
+  }
+  if (!rc && ruinv) {
+    pl->cruinv.assign(npe, {});
+    for (int i = 0; i < npe; i++) {
+      const size_t cnt = (size_t)ipow64(pl->pe[i].prime, pl->pe[i].exponent) * pl->k;
+      pl->cruinv[i].assign(ruinv[i], ruinv[i] + cnt);
+    }
+    if (mhatInv) for (int t = 0; t < pl->k; t++) pl->c_mhatinv[t] = make_double2(mhatInv[t].real, mhatInv[t].imag);
+    rc = plan_upload_c_dir(pl, true);
+  }
+  return rc;
+}
+
+extern "C" int lolb_plan_create_c(lolb_plan** out, const PrimeExponent* peArr, hShort_t sizeOfPE, hShort_t tupSize)
+{
+  if (!out) { set_error("lolb_plan_create_c: NULL argument"); return LOLB_ERR_ARG; }
+  *out = nullptr;
+  lolb_plan* pl = new lolb_plan();
+  pl->kind = PLAN_C;
+  int rc = plan_build_common(pl, peArr, sizeOfPE, tupSize);
+  if (!rc) {
+    plan_derive_c_roots(pl);
+    rc = plan_upload_c_dir(pl, false);
+    if (!rc) rc = plan_upload_c_dir(pl, true);
+  }
+  if (rc) { lolb_plan_destroy(pl); return rc; }
+  *out = pl;
+  return LOLB_OK;
+}
+
+extern "C" void lolb_plan_destroy(lolb_plan* pl)
+{
+  if (!pl) return;
+  fused_release(pl);
+  void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_ws, pl->d_stage};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& s : pl->streams) if (s) cudaStreamDestroy(s);
+  for (auto& e : pl->events) if (e) cudaEventDestroy(e);
+  delete pl;
+}
+
+extern "C" int32_t lolb_plan_totient(const lolb_plan* pl) { return pl ? pl->n : 0; }
+extern "C" int32_t lolb_plan_tupsize(const lolb_plan* pl) { return pl ? pl->k : 0; }
+
+extern "C" int lolb_plan_get_ru_rq(const lolb_plan* pl, int inverse, int pp_index, hInt_t* out)
+{
+  if (!pl || pl->kind != PLAN_RQ || !out) { set_error("lolb_plan_get_ru_rq: bad argument"); return LOLB_ERR_ARG; }
+  const auto& tabs = inverse ? pl->ruinv : pl->ru;
+  if (pp_index < 0 || pp_index >= (int)tabs.size()) return LOLB_ERR_NO_CRT;
+  memcpy(out, tabs[pp_index].data(), tabs[pp_index].size() * sizeof(int64_t));
+  return LOLB_OK;
+}
+
+extern "C" int lolb_plan_get_mhatinv_rq(const lolb_plan* pl, hInt_t* out)
+{
+  if (!pl || pl->kind != PLAN_RQ || !out) { set_error("lolb_plan_get_mhatinv_rq: bad argument"); return LOLB_ERR_ARG; }
+  if ((int)pl->mhatinv.size() != pl->k) return LOLB_ERR_NO_CRT;
+  memcpy(out, pl->mhatinv.data(), sizeof(int64_t) * pl->k);
+  return LOLB_OK;
+}
+
+extern "C" const hInt_t* lolb_plan_gcrt_dev(const lolb_plan* pl, int inverse)
+{
+  if (!pl) return nullptr;
+  return inverse ? pl->d_gcrtinv : pl->d_gcrt;
+}
+
+extern "C" void lolb_plan_set_force_generic(lolb_plan* pl, int on) { if (pl) pl->force_generic = on != 0; }
+
+extern "C" const char* lolb_plan_kernel_name(const lolb_plan* pl, const char* op)
+{
+  if (!pl || !op) return "none";
+  if (pl->force_generic) return "generic";
+  return fused_kernel_name(pl, op);
+}
+
+// ------------------------------------------------------------------ batched operators
+
+#define REQUIRE_PLAN(KIND)                                                                 \
+  if (!plan || plan->kind != (KIND)) { set_error(std::string(__func__) + ": wrong or NULL plan"); return LOLB_ERR_ARG; } \
+  if (batch < 0 || (batch > 0 && !y)) { set_error(std::string(__func__) + ": bad batch / NULL data"); return LOLB_ERR_ARG; }
+
+static int crt_rq(const lolb_plan* plan, bool inverse, hInt_t* y, int64_t batch, void* stream)
+{
+  if (!(inverse ? plan->has_inv : plan->has_fwd)) {
+    set_error("no CRT over this modulus / index (ZqBasic.hs:159-165) or tables not supplied");
+    return LOLB_ERR_NO_CRT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!plan->force_generic) {
+    int rc = fused_crt_rq(plan, inverse, y, batch, st);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  return engine_crt_zq(plan, inverse, y, batch, st);
+}
+
+static int line_rq(const lolb_plan* plan, int kind, bool ginv, hInt_t* y, int64_t batch, void* stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ginv && !plan->ginv_ok) return LOLB_ERR_NOT_INVERTIBLE;
+  const ZqConsts& zc = ginv ? plan->zq_radinv : plan->zq_plain;
+  if (!plan->force_generic) {
+    int rc = fused_line_rq(plan, kind, zc, ginv, y, batch, st);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  return engine_line_zq(plan, kind, zc, ginv, y, batch, st);
+}
+
+extern "C" int lolb_tensorCRTRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return crt_rq(plan, false, y, batch, stream); }
+extern "C" int lolb_tensorCRTInvRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return crt_rq(plan, true, y, batch, stream); }
+extern "C" int lolb_tensorLRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return line_rq(plan, PASS_L, false, y, batch, stream); }
+extern "C" int lolb_tensorLInvRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return line_rq(plan, PASS_LINV, false, y, batch, stream); }
+extern "C" int lolb_tensorGPowRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return line_rq(plan, PASS_GPOW, false, y, batch, stream); }
+extern "C" int lolb_tensorGDecRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return line_rq(plan, PASS_GDEC, false, y, batch, stream); }
+extern "C" int lolb_tensorGInvPowRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return line_rq(plan, PASS_GINVPOW, true, y, batch, stream); }
+extern "C" int lolb_tensorGInvDecRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_RQ); return line_rq(plan, PASS_GINVDEC, true, y, batch, stream); }
+
+extern "C" int lolb_mulRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_RQ);
+  if (!b || (b_batch != 1 && b_batch != batch)) { set_error("lolb_mulRq: b_batch must be 1 or batch"); return LOLB_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!plan->force_generic) {
+    int rc = fused_mul_rq(plan, y, b, batch, b_batch, st);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  return engine_mul_zq(plan, y, b, batch, b_batch, st);
+}
+
+extern "C" int lolb_tensorLR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_L, 0, nullptr, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorLInvR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_LINV, 0, nullptr, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGPowR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GPOW, 0, nullptr, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGDecR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GDEC, 0, nullptr, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGInvPowR(const lolb_plan* plan, hInt_t* y, hShort_t* ok, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GINVPOW, plan->odd_rad, ok, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGInvDecR(const lolb_plan* plan, hInt_t* y, hShort_t* ok, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GINVDEC, plan->odd_rad, ok, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorLDouble(const lolb_plan* plan, double* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_f64(plan, PASS_L, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorLInvDouble(const lolb_plan* plan, double* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_f64(plan, PASS_LINV, y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorLC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_L, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorLInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_LINV, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGPowC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GPOW, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGDecC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GDEC, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGInvPowC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GINVPOW, 1.0 / (double)plan->odd_rad, (double2*)y, batch, (cudaStream_t)stream); }
+extern "C" int lolb_tensorGInvDecC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GINVDEC, 1.0 / (double)plan->odd_rad, (double2*)y, batch, (cudaStream_t)stream); }
+
+extern "C" int lolb_tensorCRTC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (!plan->has_fwd) return LOLB_ERR_NO_CRT;
+  return engine_crt_c(plan, false, (double2*)y, batch, (cudaStream_t)stream);
+}
+extern "C" int lolb_tensorCRTInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (!plan->has_inv) return LOLB_ERR_NO_CRT;
+  return engine_crt_c(plan, true, (double2*)y, batch, (cudaStream_t)stream);
+}
+extern "C" int lolb_mulC(const lolb_plan* plan, lolb_complex* y, const lolb_complex* b, int64_t batch, int64_t b_batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (!b || (b_batch != 1 && b_batch != batch)) { set_error("lolb_mulC: b_batch must be 1 or batch"); return LOLB_ERR_ARG; }
+  return engine_mul_c(plan, (double2*)y, (const double2*)b, batch, b_batch, (cudaStream_t)stream);
+}
+extern "C" int lolb_tensorGaussianDec(const lolb_plan* plan, double* y, int64_t batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (!plan->has_fwd) return LOLB_ERR_NO_CRT;
+  return engine_gauss(plan, y, batch, (cudaStream_t)stream);
+}
+extern "C" int lolb_tensorNormSqR(const lolb_plan* plan, const hInt_t* y, hInt_t* out, int64_t batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (batch > 0 && !out) { set_error("lolb_tensorNormSqR: NULL out"); return LOLB_ERR_ARG; }
+  return engine_normsq_i64(plan, y, out, batch, (cudaStream_t)stream);
+}
+extern "C" int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double* out, int64_t batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (batch > 0 && !out) { set_error("lolb_tensorNormSqD: NULL out"); return LOLB_ERR_ARG; }
+  return engine_normsq_f64(plan, y, out, batch, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-batched pipeline
+
+extern "C" void* lolb_host_alloc(uint64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void lolb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int apply_named_rq(const lolb_plan* plan, const std::string& op, hInt_t* y, int64_t batch, cudaStream_t st)
+{
+  if (op == "CRT") return lolb_tensorCRTRq(plan, y, batch, st);
+  if (op == "CRTInv") return lolb_tensorCRTInvRq(plan, y, batch, st);
+  if (op == "L") return lolb_tensorLRq(plan, y, batch, st);
+  if (op == "LInv") return lolb_tensorLInvRq(plan, y, batch, st);
+  if (op == "GPow") return lolb_tensorGPowRq(plan, y, batch, st);
+  if (op == "GDec") return lolb_tensorGDecRq(plan, y, batch, st);
+  if (op == "GInvPow") return lolb_tensorGInvPowRq(plan, y, batch, st);
+  if (op == "GInvDec") return lolb_tensorGInvDecRq(plan, y, batch, st);
+  if (op == "MulGCRT") return lolb_mulRq(plan, y, plan->d_gcrt, batch, 1, st);
+  if (op == "DivGCRT") return lolb_mulRq(plan, y, plan->d_gcrtinv, batch, 1, st);
+  set_error("lolb_rq_apply_host: unknown operator '" + op + "'");
+  return LOLB_ERR_ARG;
+}
+
+// Three-slot ring: slot s carries chunk c = s (mod 3) through  H2D -> kernels -> D2H  on its own stream, so
+// the copy engines (one per direction) and the SMs all stay busy.
+extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t* y, int64_t batch)
+{
+  if (!plan || plan->kind != PLAN_RQ || !ops || batch < 0 || (batch > 0 && !y)) { set_error("lolb_rq_apply_host: bad argument"); return LOLB_ERR_ARG; }
+  if (batch == 0) return LOLB_OK;
+  std::vector<std::string> names;
+  {
+    std::string cur;
+    for (const char* c = ops;; c++) {
+      if (*c == ',' || *c == 0) { if (!cur.empty()) names.push_back(cur); cur.clear(); if (*c == 0) break; }
+      else if (*c != ' ') cur.push_back(*c);
+    }
+  }
+  const size_t elem_bytes = (size_t)plan->n * plan->k * sizeof(int64_t);
+  const int slots = 3;
+  int64_t chunk = (int64_t)((size_t)(96u << 20) / elem_bytes);        // ~96 MiB per slot
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  int rc = plan_reserve_stage(plan, (size_t)slots * chunk * elem_bytes);
+  if (rc) return rc;
+  for (int s = 0; s < slots; s++)
+    if (!plan->streams[s]) LOLB_CUDA(cudaStreamCreateWithFlags(&plan->streams[s], cudaStreamNonBlocking));
+  int64_t done = 0;
+  for (int c = 0; done < batch; c++) {
+    const int s = c % slots;
+    const int64_t cnt = (batch - done < chunk) ? batch - done : chunk;
+    hInt_t* dev = (hInt_t*)((char*)plan->d_stage + (size_t)s * chunk * elem_bytes);
+    hInt_t* host = y + (size_t)done * plan->n * plan->k;
+    cudaStream_t st = plan->streams[s];       // stream order makes slot reuse safe
+    LOLB_CUDA(cudaMemcpyAsync(dev, host, (size_t)cnt * elem_bytes, cudaMemcpyHostToDevice, st));
+    for (const std::string& op : names) {
+      rc = apply_named_rq(plan, op, dev, cnt, st);
+      if (rc) { cudaDeviceSynchronize(); return rc; }
+    }
+    LOLB_CUDA(cudaMemcpyAsync(host, dev, (size_t)cnt * elem_bytes, cudaMemcpyDeviceToHost, st));
+    done += cnt;
+  }
+  for (int s = 0; s < slots; s++) LOLB_CUDA(cudaStreamSynchronize(plan->streams[s]));
+  return LOLB_OK;
+}
+
+// ------------------------------------------------------------------ drop-in symbols (host pointers, one element)
+
+namespace {
+
+std::mutex g_mutex;
+std::map<std::string, lolb_plan*> g_plans;
+
+[[noreturn]] void die(const char* sym, int rc)
+{
+  fprintf(stderr, "libctensor_b200: %s failed (status %d): %s\n", sym, rc, lolb_last_error());
+  fprintf(stderr, "libctensor_b200 has no CPU path; a CUDA device (sm_100a) is required.\n");
+  abort();
+}
+
+std::string plan_key(int kind, hShort_t k, const PrimeExponent* pe, hShort_t npe, const hInt_t* qs)
+{
+  std::string key((const char*)&kind, sizeof(kind));
+  key.append((const char*)&k, sizeof(k));
+  if (npe > 0) key.append((const char*)pe, sizeof(PrimeExponent) * (size_t)npe);
+  if (qs) key.append((const char*)qs, sizeof(hInt_t) * (size_t)k);
+  return key;
+}
+
+void check_totm(const char* sym, const lolb_plan* pl, hDim_t totm)
+{
+  if (pl->n != totm) {
+    set_error("totm does not match the totient of the prime powers");
+    die(sym, LOLB_ERR_ARG);
+  }
+}
+
+// plan without CRT tables (L, G, mul need none); tables are attached lazily by the CRT symbols
+lolb_plan* legacy_plan_rq(const char* sym, hShort_t k, const PrimeExponent* pe, hShort_t npe, const hInt_t* qs, hDim_t totm)
+{
+  const std::string key = plan_key(PLAN_RQ, k, pe, npe, qs);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) { check_totm(sym, it->second, totm); return it->second; }
+  lolb_plan* pl = new lolb_plan();
+  pl->kind = PLAN_RQ;
+  int rc = plan_build_common(pl, pe, npe, k);
+  if (rc) die(sym, rc);
+  pl->qs.assign(qs, qs + k);
+  for (int t = 0; t < k; t++)
+    if (qs[t] < 2 || qs[t] >= ((int64_t)1 << 32)) { set_error("modulus out of range [2, 2^32)"); die(sym, LOLB_ERR_ARG); }
+  fill_zq_consts(pl);
+  rc = fused_select(pl);
+  if (rc) die(sym, rc);
+  check_totm(sym, pl, totm);
+  g_plans[key] = pl;
+  return pl;
+}
+
+lolb_plan* legacy_plan_c(const char* sym, hShort_t k, const PrimeExponent* pe, hShort_t npe, hDim_t totm)
+{
+  const std::string key = plan_key(PLAN_C, k, pe, npe, nullptr);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) { check_totm(sym, it->second, totm); return it->second; }
+  lolb_plan* pl = nullptr;
+  int rc = lolb_plan_create_c(&pl, pe, npe, k);
+  if (rc) die(sym, rc);
+  check_totm(sym, pl, totm);
+  g_plans[key] = pl;
+  return pl;
+}
+
+// stage `bytes` of host data on the device, run `body(dev)`, copy back `back_bytes`
+template <class Body>
+void with_staged(const char* sym, const lolb_plan* pl, void* host, size_t bytes, size_t back_bytes, Body body)
+{
+  int rc = plan_reserve_stage(pl, bytes);
+  if (rc) die(sym, rc);
+  cudaError_t e = cudaMemcpy(pl->d_stage, host, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) die(sym, cuda_fail(e, "cudaMemcpy H2D"));
+  rc = body(pl->d_stage);
+  if (rc) { cudaDeviceSynchronize(); die(sym, rc); }
+  e = cudaMemcpy(host, pl->d_stage, back_bytes, cudaMemcpyDeviceToHost);   // synchronises with the null stream
+  if (e != cudaSuccess) die(sym, cuda_fail(e, "cudaMemcpy D2H"));
+}
+
+}  // namespace
+
+#define LEGACY_LOCK std::lock_guard<std::mutex> lock__(g_mutex)
+
+extern "C" void tensorCRTRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t** ru, hInt_t* qs)
+{
+  LEGACY_LOCK;
+  lolb_plan* pl = legacy_plan_rq(__func__, tupSize, peArr, sizeOfPE, qs, totm);
+  const uint64_t h = hash_tables(pl, (const void* const*)ru, sizeof(hInt_t), nullptr, 0);
+  if (!pl->has_fwd || pl->fwd_hash != h) {
+    int rc = copy_tables(pl, ru, &pl->ru);
+    if (!rc) rc = plan_upload_rq_dir(pl, false);
+    if (!rc) rc = fused_select(pl);
+    if (rc) die(__func__, rc);
+    pl->fwd_hash = h;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(hInt_t);
+  with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensorCRTRq(pl, (hInt_t*)d, 1, nullptr); });
+}
+
+extern "C" void tensorCRTInvRq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t** ruinv, hInt_t* mhatInv, hInt_t* qs)
+{
+  LEGACY_LOCK;
+  lolb_plan* pl = legacy_plan_rq(__func__, tupSize, peArr, sizeOfPE, qs, totm);
+  const uint64_t h = hash_tables(pl, (const void* const*)ruinv, sizeof(hInt_t), mhatInv, sizeof(hInt_t) * (size_t)tupSize);
+  if (!pl->has_inv || pl->inv_hash != h) {
+    int rc = copy_tables(pl, ruinv, &pl->ruinv);
+    pl->mhatinv.assign(mhatInv, mhatInv + tupSize);
+    if (!rc) rc = plan_upload_rq_dir(pl, true);
+    if (!rc) rc = fused_select(pl);
+    if (rc) die(__func__, rc);
+    pl->inv_hash = h;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(hInt_t);
+  with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensorCRTInvRq(pl, (hInt_t*)d, 1, nullptr); });
+}
+
+extern "C" void tensorCRTC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, lolb_complex** ru)
+{
+  LEGACY_LOCK;
+  lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);
+  const uint64_t h = hash_tables(pl, (const void* const*)ru, sizeof(lolb_complex), nullptr, 0);
+  if (pl->fwd_hash != h) {
+    int rc = plan_set_c_tables(pl, ru, nullptr, nullptr);
+    if (rc) die(__func__, rc);
+    pl->fwd_hash = h;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(lolb_complex);
+  with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensorCRTC(pl, (lolb_complex*)d, 1, nullptr); });
+}
+
+extern "C" void tensorCRTInvC(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, lolb_complex** ruinv, lolb_complex* mhatInv)
+{
+  LEGACY_LOCK;
+  lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);
+  const uint64_t h = hash_tables(pl, (const void* const*)ruinv, sizeof(lolb_complex), mhatInv, sizeof(lolb_complex) * (size_t)tupSize);
+  if (pl->inv_hash != h) {
+    int rc = plan_set_c_tables(pl, nullptr, ruinv, mhatInv);
+    if (rc) die(__func__, rc);
+    pl->inv_hash = h;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(lolb_complex);
+  with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensorCRTInvC(pl, (lolb_complex*)d, 1, nullptr); });
+}
+
+extern "C" void tensorGaussianDec(hShort_t tupSize, double* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, lolb_complex** ru)
+{
+  LEGACY_LOCK;
+  lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);
+  const uint64_t h = hash_tables(pl, (const void* const*)ru, sizeof(lolb_complex), nullptr, 0);
+  if (pl->fwd_hash != h) {
+    int rc = plan_set_c_tables(pl, ru, nullptr, nullptr);
+    if (rc) die(__func__, rc);
+    pl->fwd_hash = h;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(double);
+  with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensorGaussianDec(pl, (double*)d, 1, nullptr); });
+}
+
+#define LEGACY_RQ(NAME)                                                                                               \
+  extern "C" void tensor##NAME##Rq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs) \
+  {                                                                                                                   \
+    LEGACY_LOCK;                                                                                                      \
+    lolb_plan* pl = legacy_plan_rq(__func__, tupSize, peArr, sizeOfPE, qs, totm);                                     \
+    const size_t bytes = (size_t)totm * tupSize * sizeof(hInt_t);                                                     \
+    with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensor##NAME##Rq(pl, (hInt_t*)d, 1, nullptr); }); \
+  }
+LEGACY_RQ(L)
+LEGACY_RQ(LInv)
+LEGACY_RQ(GPow)
+LEGACY_RQ(GDec)
+
+#define LEGACY_GINV_RQ(NAME)                                                                                          \
+  extern "C" hShort_t tensor##NAME##Rq(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE, hInt_t* qs) \
+  {                                                                                                                   \
+    LEGACY_LOCK;                                                                                                      \
+    lolb_plan* pl = legacy_plan_rq(__func__, tupSize, peArr, sizeOfPE, qs, totm);                                     \
+    if (!pl->ginv_ok) return 0;   /* g.cpp:196-198: reciprocal == 0 */                                               \
+    const size_t bytes = (size_t)totm * tupSize * sizeof(hInt_t);                                                     \
+    with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensor##NAME##Rq(pl, (hInt_t*)d, 1, nullptr); }); \
+    return 1;                                                                                                         \
+  }
+LEGACY_GINV_RQ(GInvPow)
+LEGACY_GINV_RQ(GInvDec)
+
+#define LEGACY_PLAIN(NAME, TAG, T, CALLT)                                                                             \
+  extern "C" void tensor##NAME##TAG(hShort_t tupSize, T* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE)     \
+  {                                                                                                                   \
+    LEGACY_LOCK;                                                                                                      \
+    lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);                                          \
+    const size_t bytes = (size_t)totm * tupSize * sizeof(T);                                                          \
+    with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensor##NAME##TAG(pl, (CALLT*)d, 1, nullptr); }); \
+  }
+LEGACY_PLAIN(L, R, hInt_t, hInt_t)
+LEGACY_PLAIN(LInv, R, hInt_t, hInt_t)
+LEGACY_PLAIN(GPow, R, hInt_t, hInt_t)
+LEGACY_PLAIN(GDec, R, hInt_t, hInt_t)
+LEGACY_PLAIN(L, Double, double, double)
+LEGACY_PLAIN(LInv, Double, double, double)
+LEGACY_PLAIN(L, C, lolb_complex, lolb_complex)
+LEGACY_PLAIN(LInv, C, lolb_complex, lolb_complex)
+LEGACY_PLAIN(GPow, C, lolb_complex, lolb_complex)
+LEGACY_PLAIN(GDec, C, lolb_complex, lolb_complex)
+
+#define LEGACY_GINV_C(NAME)                                                                                           \
+  extern "C" hShort_t tensor##NAME##C(hShort_t tupSize, lolb_complex* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE) \
+  {                                                                                                                   \
+    LEGACY_LOCK;                                                                                                      \
+    lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);                                          \
+    const size_t bytes = (size_t)totm * tupSize * sizeof(lolb_complex);                                               \
+    with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensor##NAME##C(pl, (lolb_complex*)d, 1, nullptr); }); \
+    return 1;                                                                                                         \
+  }
+LEGACY_GINV_C(GInvPow)
+LEGACY_GINV_C(GInvDec)
+
+// element at [0, bytes), one int16 status right behind it (8-byte aligned)
+#define LEGACY_GINV_R(NAME)                                                                                           \
+  extern "C" hShort_t tensor##NAME##R(hShort_t tupSize, hInt_t* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE) \
+  {                                                                                                                   \
+    LEGACY_LOCK;                                                                                                      \
+    lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);                                          \
+    const size_t bytes = (size_t)totm * tupSize * sizeof(hInt_t);                                                     \
+    int rc = plan_reserve_stage(pl, bytes + 8);                                                                       \
+    if (rc) die(__func__, rc);                                                                                        \
+    hShort_t* ok_dev = (hShort_t*)((char*)pl->d_stage + bytes);                                                       \
+    hShort_t ok = 0;                                                                                                  \
+    with_staged(__func__, pl, y, bytes, bytes, [&](void* d) { return lolb_tensor##NAME##R(pl, (hInt_t*)d, ok_dev, 1, nullptr); }); \
+    cudaError_t e = cudaMemcpy(&ok, ok_dev, sizeof(ok), cudaMemcpyDeviceToHost);                                      \
+    if (e != cudaSuccess) die(__func__, cuda_fail(e, "cudaMemcpy status"));                                           \
+    return ok;                                                                                                        \
+  }
+LEGACY_GINV_R(GInvPow)
+LEGACY_GINV_R(GInvDec)
+
+#define LEGACY_NORM(TAG, T)                                                                                           \
+  extern "C" void tensorNormSq##TAG(hShort_t tupSize, T* y, hDim_t totm, PrimeExponent* peArr, hShort_t sizeOfPE)     \
+  {                                                                                                                   \
+    LEGACY_LOCK;                                                                                                      \
+    lolb_plan* pl = legacy_plan_c(__func__, tupSize, peArr, sizeOfPE, totm);                                          \
+    const size_t bytes = (size_t)totm * tupSize * sizeof(T);                                                          \
+    const size_t out_bytes = (size_t)tupSize * sizeof(T);                                                             \
+    int rc = plan_reserve_stage(pl, bytes + out_bytes);                                                               \
+    if (rc) die(__func__, rc);                                                                                        \
+    cudaError_t e = cudaMemcpy(pl->d_stage, y, bytes, cudaMemcpyHostToDevice);                                        \
+    if (e != cudaSuccess) die(__func__, cuda_fail(e, "cudaMemcpy H2D"));                                              \
+    T* out_dev = (T*)((char*)pl->d_stage + bytes);                                                                    \
+    rc = lolb_tensorNormSq##TAG(pl, (const T*)pl->d_stage, out_dev, 1, nullptr);                                      \
+    if (rc) die(__func__, rc);                                                                                        \
+    e = cudaMemcpy(y, out_dev, out_bytes, cudaMemcpyDeviceToHost);                                                    \
+    if (e != cudaSuccess) die(__func__, cuda_fail(e, "cudaMemcpy D2H"));                                              \
+  }
+LEGACY_NORM(R, hInt_t)
+LEGACY_NORM(D, double)
+
+extern "C" void mulRq(hShort_t tupSize, hInt_t* a, hInt_t* b, hDim_t totm, hInt_t* qs)
+{
+  LEGACY_LOCK;
+  // mul.cpp:27-30 takes no prime powers: a one-factor "plan" keyed on (totm, qs) carries the moduli
+  const std::string key = plan_key(-PLAN_RQ, tupSize, nullptr, 0, qs) + std::string((const char*)&totm, sizeof(totm));
+  lolb_plan* pl;
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) pl = it->second;
+  else {
+    pl = new lolb_plan();
+    pl->kind = PLAN_RQ;
+    int rc = plan_build_common(pl, nullptr, 0, tupSize);
+    if (rc) die(__func__, rc);
+    pl->n = totm;
+    pl->qs.assign(qs, qs + tupSize);
+    for (int t = 0; t < tupSize; t++)
+      if (qs[t] < 2 || qs[t] >= ((int64_t)1 << 32)) { set_error("modulus out of range [2, 2^32)"); die(__func__, LOLB_ERR_ARG); }
+    fill_zq_consts(pl);
+    g_plans[key] = pl;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(hInt_t);
+  int rc = plan_reserve_stage(pl, 2 * bytes);
+  if (rc) die(__func__, rc);
+  hInt_t* bdev = (hInt_t*)((char*)pl->d_stage + bytes);
+  cudaError_t e = cudaMemcpy(bdev, b, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) die(__func__, cuda_fail(e, "cudaMemcpy H2D"));
+  with_staged(__func__, pl, a, bytes, bytes, [&](void* d) { return lolb_mulRq(pl, (hInt_t*)d, bdev, 1, 1, nullptr); });
+}
+
+extern "C" void mulC(hShort_t tupSize, lolb_complex* a, lolb_complex* b, hDim_t totm)
+{
+  LEGACY_LOCK;
+  const std::string key = plan_key(-PLAN_C, tupSize, nullptr, 0, nullptr) + std::string((const char*)&totm, sizeof(totm));
+  lolb_plan* pl;
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) pl = it->second;
+  else {
+    pl = new lolb_plan();
+    pl->kind = PLAN_C;
+    int rc = plan_build_common(pl, nullptr, 0, tupSize);
+    if (rc) die(__func__, rc);
+    pl->n = totm;
+    g_plans[key] = pl;
+  }
+  const size_t bytes = (size_t)totm * tupSize * sizeof(lolb_complex);
+  int rc = plan_reserve_stage(pl, 2 * bytes);
+  if (rc) die(__func__, rc);
+  lolb_complex* bdev = (lolb_complex*)((char*)pl->d_stage + bytes);
+  cudaError_t e = cudaMemcpy(bdev, b, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) die(__func__, cuda_fail(e, "cudaMemcpy H2D"));
+  with_staged(__func__, pl, a, bytes, bytes, [&](void* d) { return lolb_mulC(pl, (lolb_complex*)d, bdev, 1, 1, nullptr); });
+}

@@ -1,0 +1,18 @@
+// fused.cuh -- interface of the fused (single HBM round trip, shape-specialised) kernels.
+// Every entry returns LOLB_FUSED_UNAVAILABLE when the plan's shape has no fused kernel; the caller then
+// runs the generic pass engine (engine.cu).  Both paths are CUDA; neither is a CPU fallback.
+#pragma once
+#include "lolb_internal.cuh"
+
+namespace lolb {
+
+constexpr int LOLB_FUSED_UNAVAILABLE = -1;
+
+int fused_select(lolb_plan* pl);          // (re)build fused-kernel tables after the plan's root tables changed
+void fused_release(lolb_plan* pl);
+const char* fused_kernel_name(const lolb_plan* pl, const char* op);
+int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_mul_rq(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st);
+
+}  // namespace lolb

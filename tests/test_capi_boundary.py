@@ -1,0 +1,115 @@
+"""CPU suite: the C-ABI library loads without a GPU, exports every symbol include/lol_b200.h
+declares (and the 29 names Backend.hs:304-337 imports), and fails loudly -- not silently on a CPU
+path -- when asked to compute without a device."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lol_b200.h")
+
+# foreign imports of lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Backend.hs:304-337
+BACKEND_HS_IMPORTS = [
+    "tensorLR", "tensorLInvR", "tensorLRq", "tensorLInvRq", "tensorLDouble", "tensorLInvDouble", "tensorLC", "tensorLInvC",
+    "tensorNormSqR", "tensorNormSqD",
+    "tensorGPowR", "tensorGPowRq", "tensorGPowC", "tensorGDecR", "tensorGDecRq", "tensorGDecC",
+    "tensorGInvPowR", "tensorGInvPowRq", "tensorGInvPowC", "tensorGInvDecR", "tensorGInvDecRq", "tensorGInvDecC",
+    "tensorCRTRq", "tensorCRTC", "tensorCRTInvRq", "tensorCRTInvC",
+    "tensorGaussianDec", "mulRq", "mulC",
+]
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from lol_b200 import build_library
+    return build_library()
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)
+    skip = {"defined", "sizeof"}
+    return sorted({n for n in names if n not in skip and (n.startswith("lolb_") or n.startswith("tensor") or n in ("mulRq", "mulC"))})
+
+
+def test_header_declares_all_backend_imports():
+    assert len(BACKEND_HS_IMPORTS) == 29
+    decl = set(declared_functions())
+    assert set(BACKEND_HS_IMPORTS) <= decl
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [n for n in declared_functions() if n not in exported]
+    assert not missing, missing
+
+
+def test_library_is_sm100a_only(libpath):
+    out = subprocess.run(["cuobjdump", "-lelf", libpath], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_library_does_not_link_oracle(libpath):
+    out = subprocess.run(["nm", "-D", libpath], capture_output=True, text=True, check=True).stdout
+    assert "lo_tensor" not in out and "lo_mul" not in out
+    src = os.path.join(ROOT, "lol_b200")
+    for dirpath, _, files in os.walk(src):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                body = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in body, os.path.join(dirpath, f)
+
+
+def test_loads_and_reports_without_gpu(libpath):
+    from lol_b200 import capi
+    assert capi.kernel_launch_count() >= 0
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device behaviour is not observable here")
+    assert not capi.device_available()
+    with pytest.raises(capi.LolB200Error) as ei:
+        capi.PlanRq([(2, 6), (3, 2), (5, 2)], [14401])
+    assert ei.value.status == capi.LOLB_ERR_CUDA
+
+
+def test_dropin_aborts_without_gpu(libpath):
+    """The drop-in symbols are `void`: with no device they must die loudly (types.h:36-41 ASSERT style),
+    never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from lol_b200 import capi\n"
+        "y = capi.DropIn().tensorLRq(np.arange(6, dtype=np.int64), [(7, 1)], [29])\n"
+        "print('SURVIVED', y)\n" % ROOT)
+    r = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "SURVIVED" not in r.stdout
+    assert "no CPU path" in r.stderr
+
+
+def test_bad_arguments_rejected(libpath):
+    from lol_b200 import capi
+    with pytest.raises(capi.LolB200Error) as ei:
+        capi.PlanRq([(3, 1), (2, 2)], [13])           # primes must be increasing (ppsFact order)
+    assert ei.value.status == capi.LOLB_ERR_ARG
+    with pytest.raises(capi.LolB200Error) as ei:
+        capi.PlanRq([(2, 2)], [1 << 33])              # modulus beyond what int64 products allow (types.h:79-84)
+    assert ei.value.status == capi.LOLB_ERR_ARG
+
+
+def test_factored_matches_oracle_tables():
+    from lol_b200 import factored
+    from oracle import tables as T
+    for m in (1, 2, 3, 4, 6, 7, 8, 12, 21, 42, 89, 1024, 1728, 5184, 14400, 65536, 7 * 13 * 4):
+        assert factored.pps_fact(m) == T.factor_pps(m)
+        assert factored.totient_fact(m) == T.totient_pps(T.factor_pps(m))
+        assert factored.value_hat(m) == T.value_hat(m)
+        assert factored.radical_fact(m) == T.radical(m)
+        assert factored.odd_radical_fact(m) == T.odd_radical(m)

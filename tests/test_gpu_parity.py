@@ -1,0 +1,327 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+  * every one of the 29 drop-in symbols vs the oracle on the reference's own test parameters
+    (bit-exact for Zq / int64, 1e-9 relative for double / complex: BASELINE.json north_star);
+  * the batched device-resident entry points vs the oracle, element by element;
+  * the committed golden fixtures (outputs of the compiled reference), incl. config B digests;
+  * the library's own root tables (ZqBasic.hs restated in C++) vs the oracle's table builder;
+  * at BASELINE.json's full sizes: the reference's algebraic properties (TensorTests.hs:80-131)
+    -- crtInv.crt = id, linearity, mulGCRT = crt.mulGPow.crtInv -- as size-independent checks.
+
+Nothing here reads /root/reference.
+"""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (CONFIG_A, CONFIG_B, CONFIG_C, NON_CRT_PARAMS, PAPER_PARAMS, REFERENCE_TEST_PARAMS, rel_err,
+                      zq_input)
+from oracle import tables as T
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_TOL = 1e-9      # BASELINE.json: "within a stated relative tolerance (e.g. 1e-9)"
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+SMALL_GOLDEN = [g for g in GOLDEN if "cfgB" not in g]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU suite needs a CUDA device: libctensor_b200 has no CPU path")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def dropin(torch_cuda):
+    from lol_b200 import build_library, capi
+    build_library()
+    assert capi.device_available()
+    return capi.DropIn()
+
+
+def _tables(m, qs):
+    return (T.pe_array(m), T.totient_pps(T.factor_pps(m)), T.ru_tables_zq(m, qs), T.ru_tables_zq(m, qs, inverse=True),
+            [T.mhat_inv(m, q) for q in qs])
+
+
+# ------------------------------------------------------------------ drop-in symbols
+@pytest.mark.parametrize("m,qs", REFERENCE_TEST_PARAMS + PAPER_PARAMS + [CONFIG_C], ids=lambda v: str(v))
+def test_dropin_zq_symbols_bit_exact(dropin, oracle, m, qs):
+    from lol_b200 import capi
+    before = capi.kernel_launch_count()
+    rng = np.random.default_rng(m * 31 + len(qs))
+    pe, n, ru, rui, mh = _tables(m, qs)
+    y, y2 = zq_input(rng, n, qs), zq_input(rng, n, qs)
+    assert np.array_equal(dropin.tensorCRTRq(y, pe, ru, qs), oracle.tensorCRTRq(y, pe, ru, qs))
+    assert np.array_equal(dropin.tensorCRTInvRq(y, pe, rui, mh, qs), oracle.tensorCRTInvRq(y, pe, rui, mh, qs))
+    for nm in ("tensorLRq", "tensorLInvRq", "tensorGPowRq", "tensorGDecRq"):
+        assert np.array_equal(getattr(dropin, nm)(y, pe, qs), getattr(oracle, nm)(y, pe, qs)), nm
+    for nm in ("tensorGInvPowRq", "tensorGInvDecRq"):
+        (a, sa), (b, sb) = getattr(dropin, nm)(y, pe, qs), getattr(oracle, nm)(y, pe, qs)
+        assert sa == sb == 1 and np.array_equal(a, b), nm
+    assert np.array_equal(dropin.mulRq(y, y2, qs), oracle.mulRq(y, y2, qs))
+    assert capi.kernel_launch_count() >= before + 9      # the CUDA path ran
+
+
+@pytest.mark.parametrize("m,qs", NON_CRT_PARAMS, ids=lambda v: str(v))
+def test_dropin_line_ops_composite_modulus(dropin, oracle, m, qs):
+    rng = np.random.default_rng(m)
+    pe = T.pe_array(m)
+    n = T.totient_pps(T.factor_pps(m))
+    y = zq_input(rng, n, qs)
+    for nm in ("tensorLRq", "tensorLInvRq", "tensorGPowRq", "tensorGDecRq"):
+        assert np.array_equal(getattr(dropin, nm)(y, pe, qs), getattr(oracle, nm)(y, pe, qs)), nm
+    for nm in ("tensorGInvPowRq", "tensorGInvDecRq"):
+        (a, sa), (b, sb) = getattr(dropin, nm)(y, pe, qs), getattr(oracle, nm)(y, pe, qs)
+        assert sa == sb, nm                      # 0 when rad_odd(m) is not a unit mod q (g.cpp:196-198)
+        if sa:
+            assert np.array_equal(a, b), nm
+
+
+@pytest.mark.parametrize("m", [1, 2, 7, 8, 12, 21, 42, 89, 1728, 14400], ids=str)
+def test_dropin_int64_symbols_bit_exact(dropin, oracle, m):
+    rng = np.random.default_rng(m + 5)
+    pe = T.pe_array(m)
+    n = T.totient_pps(T.factor_pps(m))
+    z = rng.integers(-(2 ** 62), 2 ** 62, size=(n, 1)).astype(np.int64)      # exercises wrap-around
+    for nm in ("tensorLR", "tensorLInvR", "tensorGPowR", "tensorGDecR"):
+        assert np.array_equal(getattr(dropin, nm)(z, pe), getattr(oracle, nm)(z, pe)), nm
+    zs = rng.integers(-8, 9, size=(n, 1)).astype(np.int64)
+    assert dropin.tensorNormSqR(zs, pe).flat[0] == oracle.tensorNormSqR(zs, pe).flat[0]
+    assert dropin.tensorNormSqR(z, pe).flat[0] == oracle.tensorNormSqR(z, pe).flat[0]
+    # divG . mulG = id over Z (TensorTests.hs:87-101), and non-multiples are refused
+    for mul, div in (("tensorGPowR", "tensorGInvPowR"), ("tensorGDecR", "tensorGInvDecR")):
+        g = getattr(dropin, mul)(zs, pe)
+        out, st = getattr(dropin, div)(g, pe)
+        ref, rst = getattr(oracle, div)(g, pe)
+        assert st == rst == 1 and np.array_equal(out, zs) and np.array_equal(ref, zs)
+        if T.odd_radical(m) > 1:
+            bad = np.zeros((n, 1), dtype=np.int64)
+            bad[0, 0] = 1
+            _, st = getattr(dropin, div)(bad, pe)
+            _, rst = getattr(oracle, div)(bad, pe)
+            assert st == rst == 0
+
+
+@pytest.mark.parametrize("m", [1, 4, 7, 12, 21, 42, 89, 1728, 14400], ids=str)
+def test_dropin_double_and_complex_symbols(dropin, oracle, m):
+    rng = np.random.default_rng(m + 11)
+    pe = T.pe_array(m)
+    n = T.totient_pps(T.factor_pps(m))
+    d = rng.normal(size=(n, 1))
+    c = rng.normal(size=(n, 1)) + 1j * rng.normal(size=(n, 1))
+    c2 = rng.normal(size=(n, 1)) + 1j * rng.normal(size=(n, 1))
+    ruc, ruci = T.ru_tables_c(m), T.ru_tables_c(m, inverse=True)
+    assert rel_err(dropin.tensorCRTC(c, pe, ruc), oracle.tensorCRTC(c, pe, ruc)) <= FLOAT_TOL
+    assert rel_err(dropin.tensorCRTInvC(c, pe, ruci, T.mhat_inv_c(m)), oracle.tensorCRTInvC(c, pe, ruci, T.mhat_inv_c(m))) <= FLOAT_TOL
+    assert rel_err(dropin.tensorGaussianDec(d, pe, ruc), oracle.tensorGaussianDec(d, pe, ruc)) <= FLOAT_TOL
+    assert rel_err(dropin.tensorNormSqD(d, pe).flat[0], oracle.tensorNormSqD(d, pe).flat[0]) <= FLOAT_TOL
+    for nm in ("tensorLDouble", "tensorLInvDouble"):
+        assert rel_err(getattr(dropin, nm)(d, pe), getattr(oracle, nm)(d, pe)) <= FLOAT_TOL, nm
+    for nm in ("tensorLC", "tensorLInvC", "tensorGPowC", "tensorGDecC"):
+        assert rel_err(getattr(dropin, nm)(c, pe), getattr(oracle, nm)(c, pe)) <= FLOAT_TOL, nm
+    for nm in ("tensorGInvPowC", "tensorGInvDecC"):
+        (a, sa), (b, sb) = getattr(dropin, nm)(c, pe), getattr(oracle, nm)(c, pe)
+        assert sa == sb == 1 and rel_err(a, b) <= FLOAT_TOL, nm
+    assert rel_err(dropin.mulC(c, c2), oracle.mulC(c, c2)) <= FLOAT_TOL
+    # crtInv . crt = id over C (TensorTests.hs:115-119)
+    assert rel_err(dropin.tensorCRTInvC(dropin.tensorCRTC(c, pe, ruc), pe, ruci, T.mhat_inv_c(m)), c) <= FLOAT_TOL
+
+
+def test_dropin_tuple_layout_complex_k2(dropin, oracle):
+    m, k = 21, 2
+    rng = np.random.default_rng(3)
+    pe = T.pe_array(m)
+    n = T.totient_pps(T.factor_pps(m))
+    c = rng.normal(size=(n, k)) + 1j * rng.normal(size=(n, k))
+    d = rng.normal(size=(n, k))
+    ruc = T.ru_tables_c(m, k)
+    assert rel_err(dropin.tensorCRTC(c, pe, ruc, k), oracle.tensorCRTC(c, pe, ruc, k)) <= FLOAT_TOL
+    assert rel_err(dropin.tensorGaussianDec(d, pe, ruc, k), oracle.tensorGaussianDec(d, pe, ruc, k)) <= FLOAT_TOL
+    assert rel_err(dropin.tensorNormSqD(d, pe, k).flat[:k], oracle.tensorNormSqD(d, pe, k).flat[:k]) <= FLOAT_TOL
+    assert rel_err(dropin.tensorLC(c, pe, k), oracle.tensorLC(c, pe, k)) <= FLOAT_TOL
+    z = rng.integers(-100, 100, size=(n, k)).astype(np.int64)
+    assert np.array_equal(dropin.tensorGPowR(z, pe, k), oracle.tensorGPowR(z, pe, k))
+
+
+# ------------------------------------------------------------------ golden fixtures (outputs of the compiled reference)
+@pytest.mark.parametrize("path", SMALL_GOLDEN, ids=[os.path.basename(p)[:-4] for p in SMALL_GOLDEN])
+def test_dropin_matches_reference_golden(dropin, path):
+    g = np.load(path)
+    m, qs = int(g["m"]), [int(q) for q in g["qs"]]
+    pe, n, ru, rui, mh = _tables(m, qs)
+    y, y2 = g["rq_in"], g["rq_in2"]
+    assert np.array_equal(dropin.tensorCRTRq(y, pe, ru, qs), g["CRTRq"])
+    assert np.array_equal(dropin.tensorCRTInvRq(y, pe, rui, mh, qs), g["CRTInvRq"])
+    for nm in ("LRq", "LInvRq", "GPowRq", "GDecRq"):
+        assert np.array_equal(getattr(dropin, "tensor" + nm)(y, pe, qs), g[nm]), nm
+    for nm in ("GInvPowRq", "GInvDecRq"):
+        arr, st = getattr(dropin, "tensor" + nm)(y, pe, qs)
+        assert st == int(g[nm + "_status"]) and np.array_equal(arr, g[nm]), nm
+    assert np.array_equal(dropin.mulRq(y, y2, qs), g["mulRq"])
+    for nm in ("LR", "LInvR", "GPowR", "GDecR"):
+        assert np.array_equal(getattr(dropin, "tensor" + nm)(g["r_in"], pe), g[nm]), nm
+    assert dropin.tensorNormSqR(g["norm_in"], pe).flat[0] == g["NormSqR"][0]
+    ruc, ruci = T.ru_tables_c(m), T.ru_tables_c(m, inverse=True)
+    assert rel_err(dropin.tensorGaussianDec(g["d_in"], pe, ruc), g["GaussianDec"]) <= FLOAT_TOL
+    assert rel_err(dropin.tensorNormSqD(g["d_in"], pe).flat[0], g["NormSqD"][0]) <= FLOAT_TOL
+    assert rel_err(dropin.tensorCRTC(g["c_in"], pe, ruc), g["CRTC"]) <= FLOAT_TOL
+    assert rel_err(dropin.tensorCRTInvC(g["c_in"], pe, ruci, T.mhat_inv_c(m)), g["CRTInvC"]) <= FLOAT_TOL
+    for nm in ("LDouble", "LInvDouble"):
+        assert rel_err(getattr(dropin, "tensor" + nm)(g["d_in"], pe), g[nm]) <= FLOAT_TOL
+    for nm in ("LC", "LInvC", "GPowC", "GDecC"):
+        assert rel_err(getattr(dropin, "tensor" + nm)(g["c_in"], pe), g[nm]) <= FLOAT_TOL
+    assert rel_err(dropin.mulC(g["c_in"], g["c_in2"]), g["mulC"]) <= FLOAT_TOL
+
+
+def test_config_b_matches_reference_digests(dropin):
+    g = np.load([p for p in GOLDEN if "cfgB" in p][0])
+    m, qs = int(g["m"]), [int(q) for q in g["qs"]]
+    rng = np.random.default_rng(int(g["seed"]))
+    pe, n, ru, rui, mh = _tables(m, qs)
+    y, y2 = zq_input(rng, n, qs), zq_input(rng, n, qs)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(y) == str(g["in_digest"])
+    crt = dropin.tensorCRTRq(y, pe, ru, qs)
+    assert np.array_equal(crt[:8], g["CRTRq_head"])
+    assert sha(crt) == str(g["CRTRq_digest"])
+    assert sha(dropin.tensorCRTInvRq(y, pe, rui, mh, qs)) == str(g["CRTInvRq_digest"])
+    assert sha(dropin.mulRq(y, y2, qs)) == str(g["mulRq_digest"])
+
+
+# ------------------------------------------------------------------ batched device API
+BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
+                (1024, [12289]), (64 * 27, [3457]), CONFIG_A, CONFIG_C]
+
+
+@pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
+@pytest.mark.parametrize("m,qs", BATCH_PARAMS, ids=lambda v: str(v))
+def test_batched_rq_matches_oracle(torch_cuda, oracle, m, qs, force_generic):
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    B = 37                                   # ragged: not a multiple of any tile size
+    rng = np.random.default_rng(m + 99)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)                  # tables derived inside the library
+    t.plan.force_generic(force_generic)
+    for i in range(len(pe)):
+        assert np.array_equal(t.plan.ru_table(i), ru[i]) and np.array_equal(t.plan.ru_table(i, True), rui[i])
+    assert list(t.plan.mhatinv()) == mh
+    y = zq_input(rng, n, qs, batch=B)
+    y2 = zq_input(rng, n, qs, batch=B)
+    x, x2 = torch.from_numpy(y).cuda(), torch.from_numpy(y2).cuda()
+    per_elem = lambda f: np.stack([f(y[b]) for b in range(B)])
+    assert np.array_equal(t.crt(x).cpu().numpy(), per_elem(lambda v: oracle.tensorCRTRq(v, pe, ru, qs)))
+    assert np.array_equal(t.crtInv(x).cpu().numpy(), per_elem(lambda v: oracle.tensorCRTInvRq(v, pe, rui, mh, qs)))
+    for meth, nm in (("l", "tensorLRq"), ("lInv", "tensorLInvRq"), ("mulGPow", "tensorGPowRq"), ("mulGDec", "tensorGDecRq")):
+        assert np.array_equal(getattr(t, meth)(x).cpu().numpy(), per_elem(lambda v: getattr(oracle, nm)(v, pe, qs))), nm
+    for meth, nm in (("divGPow", "tensorGInvPowRq"), ("divGDec", "tensorGInvDecRq")):
+        assert np.array_equal(getattr(t, meth)(x).cpu().numpy(), per_elem(lambda v: getattr(oracle, nm)(v, pe, qs)[0])), nm
+    assert np.array_equal(t.mul(x, x2).cpu().numpy(), np.stack([oracle.mulRq(y[b], y2[b], qs) for b in range(B)]))
+    g, gi = T.g_crt_vectors(m, qs)
+    assert np.array_equal(t.mulGCRT(x).cpu().numpy(), per_elem(lambda v: oracle.mulRq(v, g, qs)))
+    assert np.array_equal(t.divGCRT(x).cpu().numpy(), per_elem(lambda v: oracle.mulRq(v, gi, qs)))
+    assert torch.equal(x, torch.from_numpy(y).cuda())      # pure: inputs untouched
+    # empty batch is a no-op
+    e = torch.empty(0, n, len(qs), dtype=torch.int64, device="cuda")
+    assert t.crt(e).shape[0] == 0
+
+
+def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
+    m, B = 14400, 5
+    rng = np.random.default_rng(77)
+    pe = T.pe_array(m)
+    n = T.totient_pps(T.factor_pps(m))
+    ruc, ruci = T.ru_tables_c(m), T.ru_tables_c(m, inverse=True)
+    ti, tr, tc = CudaTensorInt(m), CudaTensorReal(m), CudaTensorComplex(m)
+    z = rng.integers(-8, 9, size=(B, n, 1)).astype(np.int64)
+    d = rng.normal(size=(B, n, 1))
+    c = rng.normal(size=(B, n, 1)) + 1j * rng.normal(size=(B, n, 1))
+    zx, dx, cx = torch.from_numpy(z).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda()
+    per = lambda f, arr: np.stack([f(arr[b]) for b in range(B)])
+    assert np.array_equal(ti.l(zx).cpu().numpy(), per(lambda v: oracle.tensorLR(v, pe), z))
+    assert np.array_equal(ti.mulGDec(zx).cpu().numpy(), per(lambda v: oracle.tensorGDecR(v, pe), z))
+    assert np.array_equal(ti.gSqNormDec(zx).cpu().numpy().reshape(-1), np.array([oracle.tensorNormSqR(z[b], pe).flat[0] for b in range(B)]))
+    gz = ti.mulGPow(zx)
+    back, ok = ti.divGPow(gz)
+    assert ok.cpu().tolist() == [1] * B and torch.equal(back, zx)
+    assert rel_err(tr.gSqNormDec(dx).cpu().numpy().reshape(-1), np.array([oracle.tensorNormSqD(d[b], pe).flat[0] for b in range(B)])) <= FLOAT_TOL
+    assert rel_err(tr.gaussianDecTransform(dx).cpu().numpy(), per(lambda v: oracle.tensorGaussianDec(v, pe, ruc), d)) <= FLOAT_TOL
+    assert rel_err(tc.crt(cx).cpu().numpy(), per(lambda v: oracle.tensorCRTC(v, pe, ruc), c)) <= FLOAT_TOL
+    assert rel_err(tc.crtInv(cx).cpu().numpy(), per(lambda v: oracle.tensorCRTInvC(v, pe, ruci, T.mhat_inv_c(m)), c)) <= FLOAT_TOL
+    assert rel_err(tc.mulGPow(cx).cpu().numpy(), per(lambda v: oracle.tensorGPowC(v, pe), c)) <= FLOAT_TOL
+    # tGaussianDec: right shape, finite, and gSqNormDec of it is positive (RLWE/Discrete.hs:42-59 usage)
+    smp = tr.tGaussianDec(0.1, 8)
+    assert smp.shape == (8, n, 1) and torch.isfinite(smp).all()
+    assert (tr.gSqNormDec(smp) > 0).all()
+
+
+def test_host_pipeline_matches_device_path(torch_cuda, oracle):
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    m, qs = CONFIG_A
+    t = CudaTensorRq(m, qs)
+    B = 300
+    rng = np.random.default_rng(5)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    y = zq_input(rng, n, qs, batch=B)
+    h = torch.from_numpy(y.copy()).pin_memory()
+    t.apply_host("CRT", h)
+    assert np.array_equal(h[3].numpy(), oracle.tensorCRTRq(y[3], pe, ru, qs))
+    assert torch.equal(h.cuda(), t.crt(torch.from_numpy(y).cuda()))
+    t.apply_host("CRTInv", h)
+    assert np.array_equal(h.numpy(), y)
+    h2 = torch.from_numpy(y.copy())          # pageable memory works too
+    t.apply_host("CRT,CRTInv", h2)
+    assert np.array_equal(h2.numpy(), y)
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE.json configs)
+def _device_uniform(torch, B, n, qs, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    cols = [torch.randint(0, q, (B, n, 1), dtype=torch.int64, device="cuda", generator=g) for q in qs]
+    return torch.cat(cols, dim=2).contiguous()
+
+
+@pytest.mark.parametrize("cfg,B", [(CONFIG_A, 65536), (CONFIG_C, 8192), (CONFIG_B, 256)], ids=["A", "C", "B"])
+def test_full_size_properties(torch_cuda, oracle, cfg, B):
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    m, qs = cfg
+    t = CudaTensorRq(m, qs)
+    n, k = t.n, t.k
+    x = _device_uniform(torch, B, n, qs, seed=0)
+    q = torch.tensor(qs, dtype=torch.int64, device="cuda")
+    f = t.crt(x)
+    assert int(f.min()) >= 0 and bool((f < q).all())                       # canonical output (zq.cpp:57-67)
+    assert torch.equal(t.crtInv(f), x)                                      # crtInv . crt = id
+    # linearity: crt(x + x') = crt(x) + crt(x') mod q
+    x2 = _device_uniform(torch, B, n, qs, seed=1)
+    assert torch.equal(t.crt((x + x2) % q), (f + t.crt(x2)) % q)
+    # mulGCRT = crt . mulGPow . crtInv ; divGCRT . mulGCRT = id ; lInv . l = id ; mulGDec = lInv . mulGPow . l
+    assert torch.equal(t.mulGCRT(f), t.crt(t.mulGPow(x)))
+    assert torch.equal(t.divGCRT(t.mulGCRT(f)), f)
+    assert torch.equal(t.lInv(t.l(x)), x)
+    assert torch.equal(t.mulGDec(x), t.lInv(t.mulGPow(t.l(x))))
+    assert torch.equal(t.divGPow(t.mulGPow(x)), x) and torch.equal(t.divGDec(t.mulGDec(x)), x)
+    # scalarCRT = crt . scalarPow
+    assert torch.equal(t.crt(t.scalarPow(5, batch=3)), t.scalarCRT(5, batch=3))
+    # spot parity against the oracle: first, middle, last element of the batch
+    pe, _, ru, rui, mh = _tables(m, qs)
+    for b in (0, B // 2, B - 1):
+        assert np.array_equal(f[b].cpu().numpy(), oracle.tensorCRTRq(x[b].cpu().numpy(), pe, ru, qs))
+    # ring product through the CRT basis: commutes and matches the oracle composition on one element
+    prod = t.crtInv(t.mul(f, t.crt(x2)))
+    assert torch.equal(prod, t.crtInv(t.mul(t.crt(x2), f)))
+    b = B // 3
+    ref = oracle.tensorCRTInvRq(oracle.mulRq(oracle.tensorCRTRq(x[b].cpu().numpy(), pe, ru, qs),
+                                             oracle.tensorCRTRq(x2[b].cpu().numpy(), pe, ru, qs), qs), pe, rui, mh, qs)
+    assert np.array_equal(prod[b].cpu().numpy(), ref)
