@@ -1,0 +1,377 @@
+// fused_a.cu -- fused Z_q CRT / CRT^-1 for m = 2^6 * 3^2 * 5^2 = 14400 (n = 3840 = 32 * 6 * 20), the index of
+// BASELINE.json's headline metric: one HBM read and one HBM write per ring element, everything else on chip.
+//
+// The operator is the reference's (crt.cpp:518-581 on tensor.h:76-95): CRT_m = CRT_64 (x) CRT_9 (x) CRT_25 with the
+// first factor on the fastest axis, CRT_{p^e} = (DFT_{p^(e-1)} (x) I_{p-1}) . That . (I_{p^(e-1)} (x) CRT_p).
+// Factors on different axes commute, and over Z_q any exact evaluation order gives the same residues, so the
+// schedule is chosen for the machine, not copied from the reference:
+//
+//   element X[i3][i2][i1], i1 < 32 (2^6 axis), i2 < 6 (3^2 axis), i3 < 20 (5^2 axis), flat j = i1 + 32*i2 + 192*i3
+//
+//   phase 1  thread (i1,i2) loads its 20 coefficients along i3 straight from HBM (each warp instruction reads
+//            256 contiguous bytes), applies CRT_25 in registers, writes u32 to shared memory
+//   phase 2  warp <-> i3: lane i1 reads 6 coefficients along i2 (conflict-free), applies CRT_9 in registers, then
+//            CRT_64 across the 32 lanes with a register-exchange butterfly network (one shuffle per two
+//            coefficients per radix-2 round), and stores int64 to HBM (128-byte contiguous runs)
+//
+// Diagonal twiddles (crtTwiddle) and the final mhat^-1 are folded into the small dense matrices on the host.
+// Arithmetic (q*q*8 + 2q < 2^32, e.g. q = 14401): residues stay lazily in [0, 2q) as u32; a row of a dense
+// stage is a plain 32-bit multiply-accumulate followed by ONE Barrett reduction; canonical [0,q) only at the store.
+#include "fused.cuh"
+#include "numtheory.h"
+
+namespace lolb {
+
+namespace {
+
+struct FusedAConsts {
+  uint32_t q, q2, mu;       // mu = floor(2^32 / q)
+  uint32_t m5[5][4][4];     // fwd: (twiddle . CRT_5) per block i0;      inv: (CRT_5^-1' . twiddle) * mhat^-1
+  uint32_t d5[5][5];        // DFT_5 over the block index (fwd or inverse roots)
+  uint32_t m3[3][2][2];
+  uint32_t d3[3][3];
+  const uint32_t* lane_tw;  // device [8][32] per-lane twiddles of the 2^6 axis (see build_lane_tw)
+};
+
+struct ArithS {
+  uint32_t q, q2, mu;
+  __device__ __forceinline__ uint32_t red(uint32_t x) const { return x - __umulhi(x, mu) * q; }        // any x -> [0,2q)
+  __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }                 // [0,4q) -> [0,2q)
+  __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }                 // [0,2q) -> [0,q)
+};
+
+constexpr int kN = 3840, kD1 = 32, kD2 = 6, kD3 = 20;
+constexpr int kThreadsA = 192;
+
+// CRT_25 / CRT_25^-1 on the 20 values of one (i1,i2) column, v[4*i0 + c]
+template <bool INV>
+__device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, const ArithS& A)
+{
+  if (!INV) {
+#pragma unroll
+    for (int i0 = 0; i0 < 5; i0++) {
+      uint32_t o[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        uint32_t acc = C.m5[i0][r][0] * v[4 * i0];
+#pragma unroll
+        for (int c = 1; c < 4; c++) acc += C.m5[i0][r][c] * v[4 * i0 + c];
+        o[r] = A.red(acc);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) v[4 * i0 + r] = o[r];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) {            // DFT_5 across the block index for residue column c
+    uint32_t o[5];
+    o[0] = A.red(v[c] + v[4 + c] + v[8 + c] + v[12 + c] + v[16 + c]);
+#pragma unroll
+    for (int row = 1; row < 5; row++) {
+      uint32_t acc = v[c];
+#pragma unroll
+      for (int col = 1; col < 5; col++) acc += C.d5[row][col] * v[4 * col + c];
+      o[row] = A.red(acc);
+    }
+#pragma unroll
+    for (int row = 0; row < 5; row++) v[4 * row + c] = o[row];
+  }
+  if (INV) {
+#pragma unroll
+    for (int i0 = 0; i0 < 5; i0++) {
+      uint32_t o[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        uint32_t acc = C.m5[i0][r][0] * v[4 * i0];
+#pragma unroll
+        for (int c = 1; c < 4; c++) acc += C.m5[i0][r][c] * v[4 * i0 + c];
+        o[r] = A.red(acc);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) v[4 * i0 + r] = o[r];
+    }
+  }
+}
+
+// CRT_9 / CRT_9^-1 on the 6 values x[2*i0 + c] of one (i3, i1)
+template <bool INV>
+__device__ __forceinline__ void axis3(uint32_t (&x)[6], const FusedAConsts& C, const ArithS& A)
+{
+  if (!INV) {
+#pragma unroll
+    for (int i0 = 0; i0 < 3; i0++) {
+      uint32_t a = x[2 * i0], b = x[2 * i0 + 1];
+      x[2 * i0] = A.red(C.m3[i0][0][0] * a + C.m3[i0][0][1] * b);
+      x[2 * i0 + 1] = A.red(C.m3[i0][1][0] * a + C.m3[i0][1][1] * b);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    uint32_t a = x[c], b = x[2 + c], d = x[4 + c];
+    x[c] = A.red(a + b + d);
+    x[2 + c] = A.red(a + C.d3[1][1] * b + C.d3[1][2] * d);
+    x[4 + c] = A.red(a + C.d3[2][1] * b + C.d3[2][2] * d);
+  }
+  if (INV) {
+#pragma unroll
+    for (int i0 = 0; i0 < 3; i0++) {
+      uint32_t a = x[2 * i0], b = x[2 * i0 + 1];
+      x[2 * i0] = A.red(C.m3[i0][0][0] * a + C.m3[i0][0][1] * b);
+      x[2 * i0 + 1] = A.red(C.m3[i0][1][0] * a + C.m3[i0][1][1] * b);
+    }
+  }
+}
+
+// One radix-2 round of the exchange network on lane bit `bit`.  Before: the lane owns (c0[j], c1[j]) for three
+// rows; after: the two columns of one butterfly.  Forward: (u,t) -> (u+t, (u-t)*tw).  Inverse: (u,t) -> (u+t*tw, u-t*tw).
+template <bool INV>
+__device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)[3], int lane, int bit, uint32_t tw, const ArithS& A)
+{
+  const bool hi = (lane >> bit) & 1;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const uint32_t send = hi ? c0[j] : c1[j];
+    const uint32_t keep = hi ? c1[j] : c0[j];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+    const uint32_t u = hi ? recv : keep;
+    uint32_t t = hi ? keep : recv;
+    if (!INV) {
+      c0[j] = A.fold(u + t);
+      c1[j] = A.red((u + A.q2 - t) * tw);
+    } else {
+      t = A.red(t * tw);
+      c0[j] = A.fold(u + t);
+      c1[j] = A.fold(u + A.q2 - t);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t load_coeff(const int64_t* p, uint32_t q)
+{
+  const int64_t x = *p;
+  if ((uint64_t)x < (uint64_t)q) return (uint32_t)x;          // canonical input (the contract)
+  int64_t r = x % (int64_t)q;
+  return (uint32_t)(r < 0 ? r + q : r);
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(kThreadsA, 5)
+k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_constant__ FusedAConsts C)
+{
+  __shared__ uint32_t sm[2][kN];
+  const ArithS A{C.q, C.q2, C.mu};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // per-lane twiddles of the 2^6 axis, loaded once
+  uint32_t ltw[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
+
+  int buf = 0;
+  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x, buf ^= 1) {
+    int64_t* base = y + ((size_t)e * kN) * k + limb;
+    // ---------------- phase 1: 5^2 axis
+    {
+      uint32_t v[20];
+#pragma unroll
+      for (int a = 0; a < 20; a++) v[a] = load_coeff(base + (size_t)(a * 192 + tid) * k, C.q);
+      axis5<INV>(v, C, A);
+#pragma unroll
+      for (int a = 0; a < 20; a++) sm[buf][a * 192 + tid] = v[a];
+    }
+    __syncthreads();
+    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp
+    for (int i3 = warp; i3 < kD3; i3 += kThreadsA / 32) {
+      uint32_t x[6];
+#pragma unroll
+      for (int i2 = 0; i2 < 6; i2++) x[i2] = sm[buf][i3 * 192 + i2 * 32 + lane];
+      axis3<INV>(x, C, A);
+      uint32_t c0[3], c1[3];
+      if (!INV) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {          // crtTwiddle of 2^6 (crt.cpp:43-58), column = lane
+          c0[j] = A.red(x[2 * j] * ltw[0]);
+          c1[j] = A.red(x[2 * j + 1] * ltw[0]);
+        }
+#pragma unroll
+        for (int r = 0; r < 5; r++) exchange_round<false>(c0, c1, lane, r, ltw[1 + r], A);
+        // lane owns rows 2j + (lane&1), columns (lane>>1) and (lane>>1)+16
+        int64_t* out = base + (size_t)(i3 * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          out[(size_t)(j * 64) * k] = (int64_t)A.canon(c0[j]);
+          out[(size_t)(j * 64 + 16) * k] = (int64_t)A.canon(c1[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+#pragma unroll
+        for (int r = 4; r >= 0; r--) exchange_round<true>(c0, c1, lane, r, ltw[r], A);
+        // lane owns rows 2j + (lane>>4), columns 2*(lane&15) and 2*(lane&15)+1; crtTwiddle with inverse roots last
+        int64_t* out = base + (size_t)(i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int64_t a = (int64_t)A.canon(A.red(c0[j] * ltw[5]));
+          const int64_t b = (int64_t)A.canon(A.red(c1[j] * ltw[6]));
+          if (k == 1) {
+            *reinterpret_cast<longlong2*>(out + j * 64) = make_longlong2(a, b);
+          } else {
+            out[(size_t)(j * 64) * k] = a;
+            out[(size_t)(j * 64 + 1) * k] = b;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host: constants from the plan's root tables
+
+struct FusedA {
+  bool ok_fwd = false, ok_inv = false;
+  std::vector<FusedAConsts> fwd, inv;      // per limb
+  uint32_t* d_lane_tw = nullptr;           // [k][2][8][32]
+};
+
+inline uint64_t rd(const std::vector<int64_t>& tab, int64_t j, int k, int limb, uint64_t q)
+{
+  int64_t v = tab[(size_t)j * k + limb] % (int64_t)q;
+  if (v < 0) v += q;
+  return (uint64_t)v;
+}
+
+void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, uint32_t* lane_tw /* [8][32] */)
+{
+  const int k = pl->k;
+  const uint64_t q = (uint64_t)pl->qs[limb];
+  const auto& T = inverse ? pl->ruinv : pl->ru;
+  auto r64 = [&](int64_t j) { return rd(T[0], j % 64, k, limb, q); };
+  auto r9 = [&](int64_t j) { return rd(T[1], j % 9, k, limb, q); };
+  auto r25 = [&](int64_t j) { return rd(T[2], j % 25, k, limb, q); };
+  C->q = (uint32_t)q; C->q2 = (uint32_t)(2 * q); C->mu = (uint32_t)((((uint64_t)1) << 32) / q);
+  const uint64_t scale = inverse ? (uint64_t)(((pl->mhatinv[limb] % (int64_t)q) + (int64_t)q) % (int64_t)q) : 1;
+  for (int row = 0; row < 5; row++) for (int col = 0; col < 5; col++) C->d5[row][col] = (uint32_t)r25(5 * ((row * col) % 5));
+  for (int row = 0; row < 3; row++) for (int col = 0; col < 3; col++) C->d3[row][col] = (uint32_t)r9(3 * ((row * col) % 3));
+  for (int i0 = 0; i0 < 5; i0++)
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) {
+        uint64_t v;
+        if (!inverse) {   // crtTwiddle(i0, r) * CRT_5[r][c]   (crt.cpp:60-79, 272-295)
+          const uint64_t tw = i0 ? r25((int64_t)i0 * (r + 1)) : 1;
+          v = mulmod64(tw, r25(5 * (((r + 1) * c) % 5)), q);
+        } else {          // (w^-r(c+1) - w^(c+1)) * crtTwiddle(i0, c) * mhat^-1   (crt.cpp:376-399)
+          const uint64_t tw = i0 ? r25((int64_t)i0 * (c + 1)) : 1;
+          const uint64_t mat = (r25(5 * ((r * (c + 1)) % 5)) + q - r25(5 * (5 - c - 1))) % q;
+          v = mulmod64(mulmod64(tw, mat, q), scale, q);
+        }
+        C->m5[i0][r][c] = (uint32_t)v;
+      }
+  for (int i0 = 0; i0 < 3; i0++)
+    for (int r = 0; r < 2; r++)
+      for (int c = 0; c < 2; c++) {
+        uint64_t v;
+        if (!inverse) {
+          const uint64_t tw = i0 ? r9((int64_t)i0 * (r + 1)) : 1;
+          v = mulmod64(tw, r9(3 * (((r + 1) * c) % 3)), q);
+        } else {
+          const uint64_t tw = i0 ? r9((int64_t)i0 * (c + 1)) : 1;
+          const uint64_t mat = (r9(3 * ((r * (c + 1)) % 3)) + q - r9(3 * (3 - c - 1))) % q;
+          v = mulmod64(tw, mat, q);
+        }
+        C->m3[i0][r][c] = (uint32_t)v;
+      }
+  // 2^6 axis.  Forward rows: [0] crtTwiddle by column = lane; [1+r] round r, i0 = lane >> (r+1).
+  // Inverse rows: [r] round r, i0 = (lane >> r) & (2^(4-r) - 1); [5],[6] crtTwiddle of columns 2*(lane&15) + {0,1}.
+  for (int i = 0; i < 8 * 32; i++) lane_tw[i] = 1;
+  for (int lane = 0; lane < 32; lane++) {
+    if (!inverse) {
+      lane_tw[0 * 32 + lane] = lane ? (uint32_t)r64(digit_rev(2, 5, lane)) : 1;
+      for (int r = 0; r < 5; r++) {
+        const int i0 = lane >> (r + 1);
+        lane_tw[(1 + r) * 32 + lane] = i0 ? (uint32_t)r64(digit_rev(2, 4 - r, i0) * (2 << r)) : 1;
+      }
+    } else {
+      for (int r = 0; r < 5; r++) {
+        const int i0 = (lane >> r) & ((1 << (4 - r)) - 1);
+        lane_tw[r * 32 + lane] = i0 ? (uint32_t)r64(digit_rev(2, 4 - r, i0) * (2 << r)) : 1;
+      }
+      for (int s = 0; s < 2; s++) {
+        const int col = 2 * (lane & 15) + s;
+        lane_tw[(5 + s) * 32 + lane] = col ? (uint32_t)r64(digit_rev(2, 5, col)) : 1;
+      }
+    }
+  }
+}
+
+bool shape_is_a(const lolb_plan* pl)
+{
+  if (pl->kind != PLAN_RQ || pl->pe.size() != 3) return false;
+  const PrimeExponent want[3] = {{2, 6}, {3, 2}, {5, 2}};
+  for (int i = 0; i < 3; i++) if (pl->pe[i].prime != want[i].prime || pl->pe[i].exponent != want[i].exponent) return false;
+  for (int64_t q : pl->qs) {
+    const uint64_t uq = (uint64_t)q;
+    if (8 * uq * uq + 2 * uq >= ((uint64_t)1 << 32)) return false;      // lazy 32-bit accumulation bound
+  }
+  return true;
+}
+
+}  // namespace
+
+int fused_a_select(lolb_plan* pl, void** slot)
+{
+  FusedA* F = (FusedA*)*slot;
+  if (!shape_is_a(pl)) { return LOLB_OK; }
+  if (!F) { F = new FusedA(); *slot = F; }
+  const int k = pl->k;
+  std::vector<uint32_t> lt((size_t)k * 2 * 8 * 32, 1u);
+  F->fwd.assign(k, FusedAConsts{});
+  F->inv.assign(k, FusedAConsts{});
+  F->ok_fwd = pl->has_fwd && pl->ru.size() == 3;
+  F->ok_inv = pl->has_inv && pl->ruinv.size() == 3 && (int)pl->mhatinv.size() == k;
+  for (int t = 0; t < k; t++) {
+    if (F->ok_fwd) build_consts(pl, false, t, &F->fwd[t], lt.data() + ((size_t)t * 2 + 0) * 256);
+    if (F->ok_inv) build_consts(pl, true, t, &F->inv[t], lt.data() + ((size_t)t * 2 + 1) * 256);
+  }
+  if (F->d_lane_tw) { cudaFree(F->d_lane_tw); F->d_lane_tw = nullptr; }
+  LOLB_CUDA(cudaMalloc((void**)&F->d_lane_tw, lt.size() * sizeof(uint32_t)));
+  LOLB_CUDA(cudaMemcpy(F->d_lane_tw, lt.data(), lt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  for (int t = 0; t < k; t++) {
+    F->fwd[t].lane_tw = F->d_lane_tw + ((size_t)t * 2 + 0) * 256;
+    F->inv[t].lane_tw = F->d_lane_tw + ((size_t)t * 2 + 1) * 256;
+  }
+  return LOLB_OK;
+}
+
+void fused_a_release(void* slot)
+{
+  FusedA* F = (FusedA*)slot;
+  if (!F) return;
+  if (F->d_lane_tw) cudaFree(F->d_lane_tw);
+  delete F;
+}
+
+bool fused_a_available(const void* slot, bool inverse)
+{
+  const FusedA* F = (const FusedA*)slot;
+  return F && (inverse ? F->ok_inv : F->ok_fwd);
+}
+
+int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const FusedA* F = (const FusedA*)slot;
+  if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
+  if (batch <= 0) return LOLB_OK;
+  int per_sm = 5;
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > batch) grid = batch;
+  for (int t = 0; t < pl->k; t++) {
+    if (inverse) k_fused_a<true><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->inv[t]);
+    else k_fused_a<false><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->fwd[t]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_fused_a");
+    count_launch();
+  }
+  return LOLB_OK;
+}
+
+}  // namespace lolb
