@@ -146,10 +146,9 @@ __device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)
   }
 }
 
-__device__ __forceinline__ uint32_t load_coeff(const int64_t* p, uint32_t q)
+// slow path for non-canonical input (outside the Haskell contract, tolerated like `c % q`, types.h:62-66)
+__device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
 {
-  const int64_t x = *p;
-  if ((uint64_t)x < (uint64_t)q) return (uint32_t)x;          // canonical input (the contract)
   int64_t r = x % (int64_t)q;
   return (uint32_t)(r < 0 ? r + q : r);
 }
@@ -172,9 +171,19 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_
     int64_t* base = y + ((size_t)e * kN) * k + limb;
     // ---------------- phase 1: 5^2 axis
     {
+      // all 20 loads are issued before the first use; the canonical-range check is one OR-reduction
       uint32_t v[20];
+      bool odd_input = false;
 #pragma unroll
-      for (int a = 0; a < 20; a++) v[a] = load_coeff(base + (size_t)(a * 192 + tid) * k, C.q);
+      for (int a = 0; a < 20; a++) {
+        const int64_t raw = __ldcs(base + (size_t)(a * 192 + tid) * k);
+        v[a] = (uint32_t)raw;
+        odd_input |= (uint64_t)raw >= (uint64_t)C.q;
+      }
+      if (odd_input) {
+#pragma unroll 1
+        for (int a = 0; a < 20; a++) v[a] = reduce_any(base[(size_t)(a * 192 + tid) * k], C.q);
+      }
       axis5<INV>(v, C, A);
 #pragma unroll
       for (int a = 0; a < 20; a++) sm[buf][a * 192 + tid] = v[a];
@@ -199,8 +208,8 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_
         int64_t* out = base + (size_t)(i3 * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          out[(size_t)(j * 64) * k] = (int64_t)A.canon(c0[j]);
-          out[(size_t)(j * 64 + 16) * k] = (int64_t)A.canon(c1[j]);
+          __stcs(out + (size_t)(j * 64) * k, (int64_t)A.canon(c0[j]));
+          __stcs(out + (size_t)(j * 64 + 16) * k, (int64_t)A.canon(c1[j]));
         }
       } else {
 #pragma unroll
@@ -214,10 +223,10 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_
           const int64_t a = (int64_t)A.canon(A.red(c0[j] * ltw[5]));
           const int64_t b = (int64_t)A.canon(A.red(c1[j] * ltw[6]));
           if (k == 1) {
-            *reinterpret_cast<longlong2*>(out + j * 64) = make_longlong2(a, b);
+            __stcs(reinterpret_cast<longlong2*>(out + j * 64), make_longlong2(a, b));
           } else {
-            out[(size_t)(j * 64) * k] = a;
-            out[(size_t)(j * 64 + 1) * k] = b;
+            __stcs(out + (size_t)(j * 64) * k, a);
+            __stcs(out + (size_t)(j * 64 + 1) * k, b);
           }
         }
       }
