@@ -133,13 +133,13 @@ __device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)
     const uint32_t send = hi ? c0[j] : c1[j];
     const uint32_t keep = hi ? c1[j] : c0[j];
     const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
-    const uint32_t u = hi ? recv : keep;
-    uint32_t t = hi ? keep : recv;
     if (!INV) {
-      c0[j] = A.fold(u + t);
-      c1[j] = A.red((u + A.q2 - t) * tw);
+      // u + t is symmetric; (u - t) = +-(keep - recv) and the sign lives in the lane's twiddle (host: q - tw for hi lanes)
+      c0[j] = A.fold(keep + recv);
+      c1[j] = A.red((keep + A.q2 - recv) * tw);
     } else {
-      t = A.red(t * tw);
+      const uint32_t t = A.red((hi ? keep : recv) * tw);
+      const uint32_t u = hi ? recv : keep;
       c0[j] = A.fold(u + t);
       c1[j] = A.fold(u + A.q2 - t);
     }
@@ -153,10 +153,12 @@ __device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
   return (uint32_t)(r < 0 ? r + q : r);
 }
 
-template <bool INV>
+// K = compile-time tupSize (1: immediate address offsets, 128-bit stores) or 0 for a run-time k
+template <bool INV, int K>
 __global__ void __launch_bounds__(kThreadsA, 5)
-k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_constant__ FusedAConsts C)
+k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __grid_constant__ FusedAConsts C)
 {
+  const int k = K ? K : k_rt;
   __shared__ uint32_t sm[2][kN];
   const ArithS A{C.q, C.q2, C.mu};
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,18 +173,20 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_
     int64_t* base = y + ((size_t)e * kN) * k + limb;
     // ---------------- phase 1: 5^2 axis
     {
-      // all 20 loads are issued before the first use; the canonical-range check is one OR-reduction
+      // all 20 loads are issued before the first use; the canonical-range check is two OR/max reductions
       uint32_t v[20];
-      bool odd_input = false;
+      uint32_t hi_or = 0, lo_max = 0;
+      const int64_t* src = base + (size_t)tid * k;
 #pragma unroll
       for (int a = 0; a < 20; a++) {
-        const int64_t raw = __ldcs(base + (size_t)(a * 192 + tid) * k);
+        const int64_t raw = __ldcs(src + (size_t)(a * 192) * k);
         v[a] = (uint32_t)raw;
-        odd_input |= (uint64_t)raw >= (uint64_t)C.q;
+        hi_or |= (uint32_t)((uint64_t)raw >> 32);
+        lo_max = max(lo_max, v[a]);
       }
-      if (odd_input) {
+      if (hi_or != 0 || lo_max >= C.q) {
 #pragma unroll 1
-        for (int a = 0; a < 20; a++) v[a] = reduce_any(base[(size_t)(a * 192 + tid) * k], C.q);
+        for (int a = 0; a < 20; a++) v[a] = reduce_any(src[(size_t)(a * 192) * k], C.q);
       }
       axis5<INV>(v, C, A);
 #pragma unroll
@@ -222,7 +226,7 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k, int limb, const __grid_
         for (int j = 0; j < 3; j++) {
           const int64_t a = (int64_t)A.canon(A.red(c0[j] * ltw[5]));
           const int64_t b = (int64_t)A.canon(A.red(c1[j] * ltw[6]));
-          if (k == 1) {
+          if (K == 1) {
             __stcs(reinterpret_cast<longlong2*>(out + j * 64), make_longlong2(a, b));
           } else {
             __stcs(out + (size_t)(j * 64) * k, a);
@@ -297,7 +301,9 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
       lane_tw[0 * 32 + lane] = lane ? (uint32_t)r64(digit_rev(2, 5, lane)) : 1;
       for (int r = 0; r < 5; r++) {
         const int i0 = lane >> (r + 1);
-        lane_tw[(1 + r) * 32 + lane] = i0 ? (uint32_t)r64(digit_rev(2, 4 - r, i0) * (2 << r)) : 1;
+        const uint64_t tw = i0 ? r64(digit_rev(2, 4 - r, i0) * (2 << r)) : 1;
+        // lanes whose bit r is set hold (t, u) instead of (u, t): they multiply (t - u) by -tw
+        lane_tw[(1 + r) * 32 + lane] = (uint32_t)(((lane >> r) & 1) ? (q - tw) % q : tw);
       }
     } else {
       for (int r = 0; r < 5; r++) {
@@ -374,8 +380,13 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   int64_t grid = (int64_t)pl->num_sms * per_sm;
   if (grid > batch) grid = batch;
   for (int t = 0; t < pl->k; t++) {
-    if (inverse) k_fused_a<true><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->inv[t]);
-    else k_fused_a<false><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->fwd[t]);
+    if (pl->k == 1) {
+      if (inverse) k_fused_a<true, 1><<<(int)grid, kThreadsA, 0, st>>>(y, batch, 1, t, F->inv[t]);
+      else k_fused_a<false, 1><<<(int)grid, kThreadsA, 0, st>>>(y, batch, 1, t, F->fwd[t]);
+    } else {
+      if (inverse) k_fused_a<true, 0><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->inv[t]);
+      else k_fused_a<false, 0><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->fwd[t]);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_fused_a");
     count_launch();
