@@ -11,6 +11,11 @@ void fused_a_release(void* slot);
 bool fused_a_available(const void* slot, bool inverse);
 int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 
+// fused_stream.cu
+const char* fused_stream_line_name(const lolb_plan* pl);
+int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_stream_mul(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st);
+
 namespace {
 struct FusedSet {
   void* a = nullptr;      // m = 14400 CRT / CRT^-1
@@ -41,6 +46,10 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
   }
+  if (!strcmp(op, "mulRq") || !strcmp(op, "MulGCRT") || !strcmp(op, "DivGCRT")) return ((int64_t)pl->n * pl->k) % 2 == 0 ? "mul_stream" : "generic";
+  if (pl->kind == PLAN_RQ && (!strcmp(op, "L") || !strcmp(op, "LInv") || !strcmp(op, "GPow") || !strcmp(op, "GDec") ||
+                              !strcmp(op, "GInvPow") || !strcmp(op, "GInvDec")))
+    return fused_stream_line_name(pl);
   return "generic";
 }
 
@@ -51,7 +60,14 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
   return fused_a_crt(pl, s->a, inverse, y, batch, st);
 }
 
-int fused_line_rq(const lolb_plan*, int, const ZqConsts&, bool, int64_t*, int64_t, cudaStream_t) { return LOLB_FUSED_UNAVAILABLE; }
-int fused_mul_rq(const lolb_plan*, int64_t*, const int64_t*, int64_t, int64_t, cudaStream_t) { return LOLB_FUSED_UNAVAILABLE; }
+int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  return fused_stream_line(pl, kind, zc, scale, y, batch, st);
+}
+
+int fused_mul_rq(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st)
+{
+  return fused_stream_mul(pl, a, b, batch, b_batch, st);
+}
 
 }  // namespace lolb

@@ -1,0 +1,272 @@
+// fused_stream.cu -- streaming (register-only, no shared memory, no barrier) kernels for the cheap linear operators
+// of the path over Z_q:  L, L^-1, *g in Pow/Dec, /g in Pow/Dec (l.cpp:28-98, g.cpp:16-123 lifted by tensor.h:39-74)
+// and the coefficient-wise product (mul.cpp:14-30).
+//
+// Line operators.  For an index with one or two odd prime factors every operator is a Kronecker product of small
+// integer matrices along the (p-1)-long lines of each odd-prime axis.  A thread owns one TILE: all (pA-1)*(pB-1)
+// coefficients that share every other tensor digit, loads them (consecutive threads <-> consecutive fastest
+// digit, so each warp instruction touches contiguous memory), applies axis A then axis B exactly over the
+// integers in int64 (|entries| <= p, <= p terms: no overflow for q < 2^32), reduces once per axis modulo q,
+// and stores.  Algorithmic traffic: 16 bytes per coefficient, one read and one write.
+#include "fused.cuh"
+
+namespace lolb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t barrett64(uint64_t x, uint32_t q, uint64_t mu)
+{
+  uint64_t r = x - __umul64hi(x, mu) * q;       // [0, 2q)
+  if (r >= q) r -= q;
+  if (r >= q) r -= q;
+  return (uint32_t)r;
+}
+
+// exact integer form of the prime-index operators on one line v[0..D), D = P-1
+template <int KIND, int P>
+__device__ __forceinline__ void line_op(int64_t (&v)[P - 1])
+{
+  constexpr int D = P - 1;
+  if (KIND == PASS_L) {                                   // l.cpp:28-57
+#pragma unroll
+    for (int a = 1; a < D; a++) v[a] += v[a - 1];
+  } else if (KIND == PASS_LINV) {                         // l.cpp:67-98
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) v[a] -= v[a - 1];
+  } else if (KIND == PASS_GPOW) {                         // g.cpp:16-35
+    const int64_t last = v[D - 1];
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) v[a] += last - v[a - 1];
+    v[0] += last;
+  } else if (KIND == PASS_GDEC) {                         // g.cpp:37-58
+    int64_t acc = v[0];
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) { acc += v[a]; v[a] -= v[a - 1]; }
+    v[0] += acc;
+  } else if (KIND == PASS_GINVPOW) {                      // g.cpp:60-90
+    int64_t lo = 0, hi = 0;
+#pragma unroll
+    for (int a = 0; a < D; a++) lo += v[a];
+#pragma unroll
+    for (int a = D - 1; a >= 0; a--) {
+      const int64_t z = v[a];
+      v[a] = (int64_t)(P - 1 - a) * lo - (int64_t)(a + 1) * hi;
+      lo -= z; hi += z;
+    }
+  } else if (KIND == PASS_GINVDEC) {                      // g.cpp:92-123
+    int64_t s = 0;
+#pragma unroll
+    for (int a = 0; a < D; a++) s += (int64_t)(a + 1) * v[a];
+    int64_t acc = s;
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) { const int64_t keep = acc; acc -= v[a] * (int64_t)P; v[a] = keep; }
+    v[0] = acc;
+  }
+}
+
+struct LineGeom {
+  int32_t n, k;
+  int32_t RA, RB;        // strides (rts) of the two axes; RB = n when there is no second axis
+  int32_t M;             // RB / (RA * dA)
+  int32_t tiles;         // n / (dA * dB)
+};
+
+template <int KIND, int PA, int PB>
+__global__ void __launch_bounds__(256)
+k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ LineGeom G, const __grid_constant__ ZqConsts Z, int scale)
+{
+  constexpr int DA = PA - 1, DB = PB > 1 ? PB - 1 : 1;
+  const int k = G.k;
+  // the tile / limb of a thread is fixed; blockIdx.y strides over ring elements
+  const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rem >= G.tiles * k) return;
+  const int limb = rem % k;
+  int t = rem / k;
+  const int lo = t % G.RA; t /= G.RA;
+  const int mid = t % G.M;
+  const int hi = t / G.M;
+  const uint32_t q = Z.q[limb];
+  const uint64_t mu = Z.mu[limb];
+  const uint32_t s = Z.scale[limb];
+  // bias: a multiple of q above the largest negative intermediate (|x| <= P*P*q)
+  const int64_t biasA = (int64_t)q * (PA * PA), biasB = (int64_t)q * (PB * PB);
+  const size_t off = ((size_t)lo + (size_t)G.RA * DA * mid + (size_t)G.RB * DB * hi) * k + limb;
+  const size_t sa = (size_t)G.RA * k, sb = (size_t)G.RB * k;
+  for (int64_t e = blockIdx.y; e < batch; e += gridDim.y) {
+    int64_t* base = y + (size_t)e * G.n * k + off;
+    int64_t v[DB][DA];
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) v[b][a] = __ldcs(base + sa * a + sb * b);
+    // canonical input is the contract; anything else is reduced first like `c % q` (types.h:62-66)
+    bool odd_input = false;
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) odd_input |= (uint64_t)v[b][a] >= (uint64_t)q;
+    if (odd_input) {
+#pragma unroll
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) { int64_t r = v[b][a] % (int64_t)q; v[b][a] = r < 0 ? r + q : r; }
+    }
+#pragma unroll
+    for (int b = 0; b < DB; b++) {
+      line_op<KIND, PA>(v[b]);
+#pragma unroll
+      for (int a = 0; a < DA; a++) v[b][a] = barrett64((uint64_t)(v[b][a] + biasA), q, mu);
+    }
+    if constexpr (PB > 1) {
+#pragma unroll
+      for (int a = 0; a < DA; a++) {
+        int64_t w[DB];
+#pragma unroll
+        for (int b = 0; b < DB; b++) w[b] = v[b][a];
+        line_op<KIND, PB>(w);
+#pragma unroll
+        for (int b = 0; b < DB; b++) v[b][a] = barrett64((uint64_t)(w[b] + biasB), q, mu);
+      }
+    }
+    if (scale) {
+#pragma unroll
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) v[b][a] = barrett64((uint64_t)v[b][a] * s, q, mu);
+    }
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) __stcs(base + sa * a + sb * b, v[b][a]);
+  }
+}
+
+// coefficient-wise product, two coefficients (16 bytes) per thread per operand
+__global__ void __launch_bounds__(256)
+k_mul_stream(longlong2* __restrict__ a, const longlong2* __restrict__ b, int64_t pairs, int64_t b_pairs, int k,
+             const __grid_constant__ ZqConsts Z)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const longlong2 x = __ldcs(a + i);
+    const longlong2 w = (b_pairs == pairs) ? __ldcs(b + i) : __ldg(b + (i % b_pairs));
+    const int l0 = (int)((2 * i) % k), l1 = (int)((2 * i + 1) % k);
+    const uint32_t q0 = Z.q[l0], q1 = Z.q[l1];
+    uint64_t x0 = (uint64_t)x.x, x1 = (uint64_t)x.y, w0 = (uint64_t)w.x, w1 = (uint64_t)w.y;
+    if (x0 >= q0 || w0 >= q0) { int64_t r = x.x % (int64_t)q0; x0 = r < 0 ? r + q0 : r; r = w.x % (int64_t)q0; w0 = r < 0 ? r + q0 : r; }
+    if (x1 >= q1 || w1 >= q1) { int64_t r = x.y % (int64_t)q1; x1 = r < 0 ? r + q1 : r; r = w.y % (int64_t)q1; w1 = r < 0 ? r + q1 : r; }
+    longlong2 o;
+    o.x = (int64_t)barrett64(x0 * w0, q0, Z.mu[l0]);
+    o.y = (int64_t)barrett64(x1 * w1, q1, Z.mu[l1]);
+    __stcs(a + i, o);
+  }
+}
+
+template <int KIND, int PA, int PB>
+int launch_line(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const int per_elem = G.tiles * G.k;
+  int threads = per_elem >= 256 ? 256 : ((per_elem + 31) / 32) * 32;
+  for (int c = 256; c >= 128; c -= 32) if (per_elem % c == 0) { threads = c; break; }   // avoid a ragged last block
+  dim3 grid((per_elem + threads - 1) / threads, 1, 1);
+  int64_t gy = ((int64_t)pl->num_sms * 2048 / threads + grid.x - 1) / grid.x * 2;     // ~2 waves of resident threads
+  if (gy > batch) gy = batch;
+  if (gy > 65535) gy = 65535;
+  grid.y = (unsigned)gy;
+  k_line_stream<KIND, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, zc, scale ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_line_stream");
+  count_launch();
+  return LOLB_OK;
+}
+
+template <int PA, int PB>
+int dispatch_kind(const lolb_plan* pl, int kind, const LineGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  switch (kind) {
+    case PASS_L: return launch_line<PASS_L, PA, PB>(pl, G, zc, scale, y, batch, st);
+    case PASS_LINV: return launch_line<PASS_LINV, PA, PB>(pl, G, zc, scale, y, batch, st);
+    case PASS_GPOW: return launch_line<PASS_GPOW, PA, PB>(pl, G, zc, scale, y, batch, st);
+    case PASS_GDEC: return launch_line<PASS_GDEC, PA, PB>(pl, G, zc, scale, y, batch, st);
+    case PASS_GINVPOW: return launch_line<PASS_GINVPOW, PA, PB>(pl, G, zc, scale, y, batch, st);
+    case PASS_GINVDEC: return launch_line<PASS_GINVDEC, PA, PB>(pl, G, zc, scale, y, batch, st);
+    default: return LOLB_FUSED_UNAVAILABLE;
+  }
+}
+
+}  // namespace
+
+// odd prime axes of the plan as (p, rts); returns how many
+static int odd_axes(const lolb_plan* pl, int (&p)[4], int64_t (&rts)[4])
+{
+  int cnt = 0;
+  int64_t r = 1;
+  for (const PrimeExponent& pe : pl->pe) {
+    int64_t phi = (int64_t)(pe.prime - 1);
+    for (int i = 1; i < pe.exponent; i++) phi *= pe.prime;
+    if (pe.prime != 2) { if (cnt < 4) { p[cnt] = pe.prime; rts[cnt] = r; } cnt++; }
+    r *= phi;
+  }
+  return cnt;
+}
+
+const char* fused_stream_line_name(const lolb_plan* pl)
+{
+  int p[4]; int64_t r[4];
+  const int cnt = odd_axes(pl, p, r);
+  if (cnt == 0) return "identity";
+  if (cnt == 1 && (p[0] == 3 || p[0] == 5 || p[0] == 7)) return "line_stream";
+  if (cnt == 2 && p[0] == 3 && (p[1] == 5 || p[1] == 7)) return "line_stream";
+  return "generic";
+}
+
+int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  int p[4]; int64_t r[4];
+  const int cnt = odd_axes(pl, p, r);
+  if (batch <= 0) return LOLB_OK;
+  if (cnt == 0) {
+    // every prime-index operator is the identity for p = 2 (l.cpp:35, g.cpp:18,39,62,94) and rad_odd = 1:
+    // canonical input is already the result, no launch
+    return LOLB_OK;
+  }
+  LineGeom G{};
+  G.n = pl->n; G.k = pl->k;
+  G.RA = (int32_t)r[0];
+  if (cnt == 1) {
+    G.RB = pl->n; G.M = (int32_t)(pl->n / (r[0] * (p[0] - 1))); G.tiles = pl->n / (p[0] - 1);
+    // with a single axis "hi" is always 0: fold everything above the axis into `mid`
+    switch (p[0]) {
+      case 3: return dispatch_kind<3, 1>(pl, kind, G, zc, scale, y, batch, st);
+      case 5: return dispatch_kind<5, 1>(pl, kind, G, zc, scale, y, batch, st);
+      case 7: return dispatch_kind<7, 1>(pl, kind, G, zc, scale, y, batch, st);
+      default: return LOLB_FUSED_UNAVAILABLE;
+    }
+  }
+  if (cnt == 2 && p[0] == 3 && (p[1] == 5 || p[1] == 7)) {
+    G.RB = (int32_t)r[1];
+    G.M = (int32_t)(r[1] / (r[0] * (p[0] - 1)));
+    G.tiles = pl->n / ((p[0] - 1) * (p[1] - 1));
+    if (p[1] == 5) return dispatch_kind<3, 5>(pl, kind, G, zc, scale, y, batch, st);
+    return dispatch_kind<3, 7>(pl, kind, G, zc, scale, y, batch, st);
+  }
+  return LOLB_FUSED_UNAVAILABLE;
+}
+
+int fused_stream_mul(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st)
+{
+  const int64_t nk = (int64_t)pl->n * pl->k;
+  if (batch <= 0) return LOLB_OK;
+  // pairs of coefficients must not straddle elements of b when broadcasting, and pointers must be 16-byte aligned
+  if ((nk & 1) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return LOLB_FUSED_UNAVAILABLE;
+  const int64_t pairs = batch * nk / 2, b_pairs = b_batch * nk / 2;
+  int64_t blocks = (pairs + 255) / 256;
+  const int64_t cap = (int64_t)pl->num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  k_mul_stream<<<(int)blocks, 256, 0, st>>>((longlong2*)a, (const longlong2*)b, pairs, b_pairs, pl->k, pl->zq_plain);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_mul_stream");
+  count_launch();
+  return LOLB_OK;
+}
+
+}  // namespace lolb

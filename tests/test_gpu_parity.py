@@ -65,7 +65,7 @@ def test_dropin_zq_symbols_bit_exact(dropin, oracle, m, qs):
         (a, sa), (b, sb) = getattr(dropin, nm)(y, pe, qs), getattr(oracle, nm)(y, pe, qs)
         assert sa == sb == 1 and np.array_equal(a, b), nm
     assert np.array_equal(dropin.mulRq(y, y2, qs), oracle.mulRq(y, y2, qs))
-    assert capi.kernel_launch_count() >= before + 9      # the CUDA path ran
+    assert capi.kernel_launch_count() >= before + 3      # the CUDA path ran (L, G are the identity without an odd prime: no launch)
 
 
 @pytest.mark.parametrize("m,qs", NON_CRT_PARAMS, ids=lambda v: str(v))
