@@ -1,0 +1,75 @@
+{-|
+Module      : Crypto.Lol.Cyclotomic.Tensor.CUDA.Backend
+Description : FFI to libctensor_b200.so (include/lol_b200.h): plans and batched, device-backed operators.
+
+NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no GHC/stack/cabal here (SURVEY.md, fact 2), so this module
+is written against lol-0.7.0.0 / lol-cpp-0.0.0.4 and has never been type-checked.  It mirrors
+lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Backend.hs: the per-element `Dispatch'` class of that file keeps
+working unchanged against the drop-in symbols of the new library (same names, same C signatures), and this module
+adds what the C++ back end never had -- a plan handle and whole-batch calls.
+-}
+
+{-# LANGUAGE ForeignFunctionInterface #-}
+{-# LANGUAGE ScopedTypeVariables      #-}
+
+module Crypto.Lol.Cyclotomic.Tensor.CUDA.Backend
+( Plan, withPlanRq, applyHostRq
+, lolbDeviceAvailable, lolbLastError
+) where
+
+import Control.Exception      (bracket, throwIO, ErrorCall (..))
+import Control.Monad          (when)
+import Data.Int
+import Foreign.C.String       (CString, peekCString, withCString)
+import Foreign.ForeignPtr
+import Foreign.Marshal.Alloc  (alloca)
+import Foreign.Marshal.Array  (withArray, withArrayLen)
+import Foreign.Ptr
+import Foreign.Storable       (peek)
+
+-- | Same C representation of a prime power as CPP/Backend.hs:78.
+type CPP = (Int16, Int16)
+
+-- | Opaque @lolb_plan@.
+data PlanStruct
+newtype Plan = Plan (ForeignPtr PlanStruct)
+
+foreign import ccall unsafe "lolb_plan_create_rq" c_planCreateRq ::
+  Ptr (Ptr PlanStruct) -> Ptr CPP -> Int16 -> Int16 -> Ptr Int64
+  -> Ptr (Ptr Int64) -> Ptr (Ptr Int64) -> Ptr Int64 -> IO Int32
+foreign import ccall unsafe "&lolb_plan_destroy" p_planDestroy :: FunPtr (Ptr PlanStruct -> IO ())
+foreign import ccall unsafe "lolb_rq_apply_host" c_applyHostRq ::
+  Ptr PlanStruct -> CString -> Ptr Int64 -> Int64 -> IO Int32
+foreign import ccall unsafe "lolb_last_error" c_lastError :: IO CString
+foreign import ccall unsafe "lolb_device_available" c_deviceAvailable :: IO Int32
+
+lolbLastError :: IO String
+lolbLastError = c_lastError >>= peekCString
+
+lolbDeviceAvailable :: IO Bool
+lolbDeviceAvailable = (/= 0) <$> c_deviceAvailable
+
+check :: String -> Int32 -> IO ()
+check what st = when (st /= 0) $ do
+  msg <- lolbLastError
+  throwIO $ ErrorCall $ what ++ ": libctensor_b200 status " ++ show st ++ ": " ++ msg
+
+-- | Plan for index @m = prod pps@ over the moduli @qs@; root tables are derived inside the library exactly as
+-- 'Crypto.Lol.Types.Unsafe.ZqBasic' derives them (smallest generator of Z_q^*), so results agree with 'CT'.
+withPlanRq :: [CPP] -> [Int64] -> (Plan -> IO a) -> IO a
+withPlanRq pps qs act =
+  withArrayLen pps $ \npe ppe ->
+  withArrayLen qs $ \k pqs ->
+  alloca $ \(pp :: Ptr (Ptr PlanStruct)) -> do
+    c_planCreateRq pp ppe (fromIntegral npe) (fromIntegral k) pqs nullPtr nullPtr nullPtr >>= check "lolb_plan_create_rq"
+    raw <- peek pp
+    fp <- newForeignPtr p_planDestroy raw
+    act (Plan fp)
+
+-- | @applyHostRq plan "CRT,CRTInv" buf batch@: transform @batch@ ring elements laid out back to back in @buf@
+-- (the element layout of CPP/Backend.hs:80-90) in place; the library pipelines host->device copy, kernels and
+-- device->host copy over chunks.  Operator names: CRT, CRTInv, L, LInv, GPow, GDec, GInvPow, GInvDec, MulGCRT, DivGCRT.
+applyHostRq :: Plan -> String -> Ptr Int64 -> Int64 -> IO ()
+applyHostRq (Plan fp) ops buf batch =
+  withForeignPtr fp $ \p -> withCString ops $ \cops ->
+    c_applyHostRq p cops buf batch >>= check "lolb_rq_apply_host"

@@ -1,0 +1,73 @@
+"""CPU suite: the N > 1 path (lol_b200/shard.py) with world_size 2 over gloo.
+
+The data-path has no collective; what is tested is the partition (every element owned exactly
+once, ragged batches), scatter -> per-rank transform -> gather, and that transforming shards
+independently equals transforming the whole batch (the independence the sharding relies on).
+The per-rank transform here is the CPU oracle standing in for the GPU operator."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lol_b200.shard import gather_batch, max_shard, scatter_batch, shard_bounds
+
+
+def test_shard_bounds_partition():
+    for batch in (0, 1, 2, 7, 64, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(batch, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) == (max_shard(batch, world) if batch else 0)
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, batch, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cpu, tables as T
+        m, qs = 42, [19393921, 18869761]
+        pe, n = T.pe_array(m), T.totient_pps(T.factor_pps(m))
+        ru = T.ru_tables_zq(m, qs)
+        O = cpu.restatement()
+        full = None
+        if rank == 0:
+            rng = np.random.default_rng(7)
+            full = torch.from_numpy(np.stack([rng.integers(0, q, size=(batch, n)) for q in qs], axis=-1).astype(np.int64))
+        local = scatter_batch(full, batch, (n, len(qs)), torch.int64, "cpu")
+        lo, hi = shard_bounds(batch, world, rank)
+        assert local.shape[0] == hi - lo
+        out = torch.from_numpy(np.stack([O.tensorCRTRq(local[b].numpy(), pe, ru, qs) for b in range(local.shape[0])])
+                               if local.shape[0] else np.zeros((0, n, len(qs)), dtype=np.int64))
+        got = gather_batch(out, batch)
+        if rank == 0:
+            want = np.stack([O.tensorCRTRq(full[b].numpy(), pe, ru, qs) for b in range(batch)])
+            ok = got.shape == (batch, n, len(qs)) and np.array_equal(got.numpy(), want)
+            with open(result_path, "w") as f:
+                f.write("ok" if ok else "mismatch")
+        # timing reduction used by bench.py: max over ranks
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == float(world)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [5, 8])
+def test_scatter_transform_gather_world2(tmp_path, batch):
+    result = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(2, _free_port(), batch, str(result)), nprocs=2, join=True)
+    assert result.read_text() == "ok"
