@@ -17,6 +17,8 @@
 // Diagonal twiddles (crtTwiddle) and the final mhat^-1 are folded into the small dense matrices on the host.
 // Arithmetic (q*q*8 + 2q < 2^32, e.g. q = 14401): residues stay lazily in [0, 2q) as u32; a row of a dense
 // stage is a plain 32-bit multiply-accumulate followed by ONE Barrett reduction; canonical [0,q) only at the store.
+#include <cstdlib>
+
 #include "fused.cuh"
 #include "numtheory.h"
 
@@ -41,7 +43,6 @@ struct ArithS {
 };
 
 constexpr int kN = 3840, kD1 = 32, kD2 = 6, kD3 = 20;
-constexpr int kThreadsA = 192;
 
 // CRT_25 / CRT_25^-1 on the 20 values of one (i1,i2) column, v[4*i0 + c]
 template <bool INV>
@@ -153,15 +154,18 @@ __device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
   return (uint32_t)(r < 0 ? r + q : r);
 }
 
-// K = compile-time tupSize (1: immediate address offsets, 128-bit stores) or 0 for a run-time k
-template <bool INV, int K>
-__global__ void __launch_bounds__(kThreadsA, 5)
+// K = compile-time tupSize (1: immediate address offsets, 128-bit stores) or 0 for a run-time k.
+// EPB ring elements per CTA iteration on WARPS warps: phase 1 has 6*EPB warp-tasks (32 columns each), phase 2 has
+// 20*EPB; (EPB, WARPS) = (5, 10) balances both exactly (3 and 10 tasks per warp).  EPB == 1 double-buffers the
+// shared tile (one barrier per element), EPB > 1 uses a single tile and two barriers per EPB elements.
+template <bool INV, int K, int EPB, int WARPS, int MINB, int NBUF>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __grid_constant__ FusedAConsts C)
 {
   const int k = K ? K : k_rt;
-  __shared__ uint32_t sm[2][kN];
+  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [NBUF][EPB][kN]
   const ArithS A{C.q, C.q2, C.mu};
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // per-lane twiddles of the 2^6 axis, loaded once
   uint32_t ltw[7];
@@ -169,14 +173,19 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
   for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
 
   int buf = 0;
-  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x, buf ^= 1) {
-    int64_t* base = y + ((size_t)e * kN) * k + limb;
-    // ---------------- phase 1: 5^2 axis
-    {
+  const int64_t groups = (batch + EPB - 1) / EPB;
+  for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int64_t e0 = g * EPB;
+    const int cnt = (int)(batch - e0 < EPB ? batch - e0 : EPB);
+    uint32_t* tile = sm_dyn + (size_t)buf * EPB * kN;
+    // ---------------- phase 1: 5^2 axis; warp-task = (element slot, i2), lane = i1
+    for (int t = warp; t < 6 * EPB; t += WARPS) {
+      const int slot = t / 6, col = (t - slot * 6) * 32 + lane;
+      if (slot >= cnt) break;
+      const int64_t* src = y + ((size_t)(e0 + slot) * kN + col) * k + limb;
       // all 20 loads are issued before the first use; the canonical-range check is two OR/max reductions
       uint32_t v[20];
       uint32_t hi_or = 0, lo_max = 0;
-      const int64_t* src = base + (size_t)tid * k;
 #pragma unroll
       for (int a = 0; a < 20; a++) {
         const int64_t raw = __ldcs(src + (size_t)(a * 192) * k);
@@ -189,52 +198,83 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
         for (int a = 0; a < 20; a++) v[a] = reduce_any(src[(size_t)(a * 192) * k], C.q);
       }
       axis5<INV>(v, C, A);
+      uint32_t* dst = tile + slot * kN + col;
 #pragma unroll
-      for (int a = 0; a < 20; a++) sm[buf][a * 192 + tid] = v[a];
+      for (int a = 0; a < 20; a++) dst[a * 192] = v[a];
     }
     __syncthreads();
-    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp
-    for (int i3 = warp; i3 < kD3; i3 += kThreadsA / 32) {
-      uint32_t x[6];
+    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp; warp-task = (element slot, i3).
+    // Two tasks are processed together (U = 2) so that two independent dependency chains interleave.
+    constexpr int U = 1;      // U = 2 measured slower (ragged pairs recompute a dead task)
+    for (int t0 = warp; t0 < kD3 * EPB; t0 += U * WARPS) {
+      int64_t* out[U];
+      uint32_t x[U][6], c0[U][3], c1[U][3];
+      bool live[U];
 #pragma unroll
-      for (int i2 = 0; i2 < 6; i2++) x[i2] = sm[buf][i3 * 192 + i2 * 32 + lane];
-      axis3<INV>(x, C, A);
-      uint32_t c0[3], c1[3];
+      for (int u = 0; u < U; u++) {
+        const int t = t0 + u * WARPS;
+        const int slot = t / kD3, i3 = t - slot * kD3;
+        live[u] = t < kD3 * EPB && slot < cnt;
+        const int ts = live[u] ? slot : 0, ti = live[u] ? i3 : 0;     // dead lanes of the pair recompute task (0,0), never store
+        const uint32_t* srow = tile + ts * kN + ti * 192 + lane;
+#pragma unroll
+        for (int i2 = 0; i2 < 6; i2++) x[u][i2] = srow[i2 * 32];
+        int64_t* base = y + ((size_t)(e0 + ts) * kN) * k + limb;
+        out[u] = INV ? base + (size_t)(ti * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k
+                     : base + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) axis3<INV>(x[u], C, A);
       if (!INV) {
 #pragma unroll
-        for (int j = 0; j < 3; j++) {          // crtTwiddle of 2^6 (crt.cpp:43-58), column = lane
-          c0[j] = A.red(x[2 * j] * ltw[0]);
-          c1[j] = A.red(x[2 * j + 1] * ltw[0]);
-        }
+        for (int u = 0; u < U; u++)
 #pragma unroll
-        for (int r = 0; r < 5; r++) exchange_round<false>(c0, c1, lane, r, ltw[1 + r], A);
+          for (int j = 0; j < 3; j++) {          // crtTwiddle of 2^6 (crt.cpp:43-58), column = lane
+            c0[u][j] = A.red(x[u][2 * j] * ltw[0]);
+            c1[u][j] = A.red(x[u][2 * j + 1] * ltw[0]);
+          }
+#pragma unroll
+        for (int r = 0; r < 5; r++)
+#pragma unroll
+          for (int u = 0; u < U; u++) exchange_round<false>(c0[u], c1[u], lane, r, ltw[1 + r], A);
         // lane owns rows 2j + (lane&1), columns (lane>>1) and (lane>>1)+16
-        int64_t* out = base + (size_t)(i3 * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          __stcs(out + (size_t)(j * 64) * k, (int64_t)A.canon(c0[j]));
-          __stcs(out + (size_t)(j * 64 + 16) * k, (int64_t)A.canon(c1[j]));
-        }
+        for (int u = 0; u < U; u++)
+          if (live[u]) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              __stcs(out[u] + (size_t)(j * 64) * k, (int64_t)A.canon(c0[u][j]));
+              __stcs(out[u] + (size_t)(j * 64 + 16) * k, (int64_t)A.canon(c1[u][j]));
+            }
+          }
       } else {
 #pragma unroll
-        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+        for (int u = 0; u < U; u++)
 #pragma unroll
-        for (int r = 4; r >= 0; r--) exchange_round<true>(c0, c1, lane, r, ltw[r], A);
+          for (int j = 0; j < 3; j++) { c0[u][j] = x[u][2 * j]; c1[u][j] = x[u][2 * j + 1]; }
+#pragma unroll
+        for (int r = 4; r >= 0; r--)
+#pragma unroll
+          for (int u = 0; u < U; u++) exchange_round<true>(c0[u], c1[u], lane, r, ltw[r], A);
         // lane owns rows 2j + (lane>>4), columns 2*(lane&15) and 2*(lane&15)+1; crtTwiddle with inverse roots last
-        int64_t* out = base + (size_t)(i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k;
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const int64_t a = (int64_t)A.canon(A.red(c0[j] * ltw[5]));
-          const int64_t b = (int64_t)A.canon(A.red(c1[j] * ltw[6]));
-          if (K == 1) {
-            __stcs(reinterpret_cast<longlong2*>(out + j * 64), make_longlong2(a, b));
-          } else {
-            __stcs(out + (size_t)(j * 64) * k, a);
-            __stcs(out + (size_t)(j * 64 + 1) * k, b);
+        for (int u = 0; u < U; u++)
+          if (live[u]) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const int64_t a = (int64_t)A.canon(A.red(c0[u][j] * ltw[5]));
+              const int64_t b = (int64_t)A.canon(A.red(c1[u][j] * ltw[6]));
+              if (K == 1) {
+                __stcs(reinterpret_cast<longlong2*>(out[u] + j * 64), make_longlong2(a, b));
+              } else {
+                __stcs(out[u] + (size_t)(j * 64) * k, a);
+                __stcs(out[u] + (size_t)(j * 64 + 1) * k, b);
+              }
+            }
           }
-        }
       }
     }
+    if (NBUF == 1) __syncthreads(); else buf ^= 1;
   }
 }
 
@@ -371,25 +411,53 @@ bool fused_a_available(const void* slot, bool inverse)
   return F && (inverse ? F->ok_inv : F->ok_fwd);
 }
 
+template <bool INV, int K, int EPB, int WARPS, int MINB, int NBUF>
+static int launch_a(const lolb_plan* pl, int64_t* y, int64_t batch, int limb, const FusedAConsts& C, cudaStream_t st)
+{
+  const size_t smem = (size_t)NBUF * EPB * kN * sizeof(uint32_t);
+  auto kern = k_fused_a<INV, K, EPB, WARPS, MINB, NBUF>;
+  static bool attr_done = false;
+  if (smem > 48 * 1024 && !attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fused_a)");
+    attr_done = true;
+  }
+  const int64_t groups = (batch + EPB - 1) / EPB;
+  int64_t grid = (int64_t)pl->num_sms * MINB;
+  if (grid > groups) grid = groups;
+  kern<<<(int)grid, WARPS * 32, smem, st>>>(y, batch, pl->k, limb, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_fused_a");
+  count_launch();
+  return LOLB_OK;
+}
+
+static int g_variant = -1;      // LOLB_FUSED_A_VARIANT selects (EPB, WARPS, CTAs/SM, buffers) for tuning runs
+
 int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
 {
   const FusedA* F = (const FusedA*)slot;
   if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  int per_sm = 5;
-  int64_t grid = (int64_t)pl->num_sms * per_sm;
-  if (grid > batch) grid = batch;
+  if (g_variant < 0) { const char* v = getenv("LOLB_FUSED_A_VARIANT"); g_variant = v ? atoi(v) : 2; }
   for (int t = 0; t < pl->k; t++) {
+    const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];
+    int rc;
+#define LA(...) (inverse ? launch_a<true, __VA_ARGS__>(pl, y, batch, t, C, st) : launch_a<false, __VA_ARGS__>(pl, y, batch, t, C, st))
     if (pl->k == 1) {
-      if (inverse) k_fused_a<true, 1><<<(int)grid, kThreadsA, 0, st>>>(y, batch, 1, t, F->inv[t]);
-      else k_fused_a<false, 1><<<(int)grid, kThreadsA, 0, st>>>(y, batch, 1, t, F->fwd[t]);
+      switch (g_variant) {
+        case 1: rc = LA(1, 5, 10, 3, 1); break;
+        case 2: rc = LA(1, 1, 3, 10, 1); break;
+        case 3: rc = LA(1, 1, 2, 14, 1); break;
+        case 4: rc = LA(1, 1, 6, 5, 1); break;
+        case 5: rc = LA(1, 1, 3, 7, 2); break;
+        default: rc = LA(1, 1, 6, 5, 2); break;
+      }
     } else {
-      if (inverse) k_fused_a<true, 0><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->inv[t]);
-      else k_fused_a<false, 0><<<(int)grid, kThreadsA, 0, st>>>(y, batch, pl->k, t, F->fwd[t]);
+      rc = LA(0, 1, 6, 5, 2);
     }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "k_fused_a");
-    count_launch();
+#undef LA
+    if (rc) return rc;
   }
   return LOLB_OK;
 }
