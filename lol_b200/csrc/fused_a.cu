@@ -27,26 +27,56 @@ namespace lolb {
 namespace {
 
 struct FusedAConsts {
-  uint32_t q, q2, mu;       // mu = floor(2^32 / q)
+  uint32_t q, q2;
+  uint32_t r0;              // ArithS: mu = floor(2^32 / q);  ArithM: -q^-1 mod 2^32
+  uint32_t one;             // ArithS: 1;                     ArithM: 2^32 mod q (Montgomery form of 1)
   uint32_t m5[5][4][4];     // fwd: (twiddle . CRT_5) per block i0;      inv: (CRT_5^-1' . twiddle) * mhat^-1
   uint32_t d5[5][5];        // DFT_5 over the block index (fwd or inverse roots)
   uint32_t m3[3][2][2];
   uint32_t d3[3][3];
-  const uint32_t* lane_tw;  // device [8][32] per-lane twiddles of the 2^6 axis (see build_lane_tw)
+  const uint32_t* lane_tw;  // device [8][32] per-lane twiddles of the 2^6 axis (see build_consts)
 };
 
+// Two arithmetic policies with one interface.  Residues are lazy u32 in [0,2q); `Acc` accumulates a row of a dense
+// stage without intermediate reduction; red() brings an accumulator back to [0,2q).
+//
+// ArithS (8q^2 + 2q < 2^32, e.g. q = 14401): 32-bit multiply-accumulate, Barrett reduction, constants as plain residues.
 struct ArithS {
+  typedef uint32_t Acc;
   uint32_t q, q2, mu;
-  __device__ __forceinline__ uint32_t red(uint32_t x) const { return x - __umulhi(x, mu) * q; }        // any x -> [0,2q)
+  __device__ __forceinline__ ArithS(const FusedAConsts& C) : q(C.q), q2(C.q2), mu(C.r0) {}
+  __device__ __forceinline__ Acc mul(uint32_t c, uint32_t v) const { return c * v; }
+  __device__ __forceinline__ Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + c * v; }
+  __device__ __forceinline__ Acc unit(uint32_t v) const { return v; }                                   // the "1 * v" term
+  __device__ __forceinline__ uint32_t red(Acc x) const { return x - __umulhi(x, mu) * q; }              // any x -> [0,2q)
   __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }                 // [0,4q) -> [0,2q)
   __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }                 // [0,2q) -> [0,q)
+};
+
+// ArithM (10q < 2^32, e.g. the 20-bit SymmSHE moduli 1008001, 1065601): 64-bit multiply-accumulate, ONE Montgomery
+// reduction per row; constants are stored in Montgomery form c * 2^32 mod q, data stays in plain form, so
+// REDC(sum c~_i v_i) = sum c_i v_i mod q.  acc < 10 q^2 and 10q < 2^32 give REDC(acc) < 2q.
+struct ArithM {
+  typedef uint64_t Acc;
+  uint32_t q, q2, qinv, one;
+  __device__ __forceinline__ ArithM(const FusedAConsts& C) : q(C.q), q2(C.q2), qinv(C.r0), one(C.one) {}
+  __device__ __forceinline__ Acc mul(uint32_t c, uint32_t v) const { return (uint64_t)c * v; }
+  __device__ __forceinline__ Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + (uint64_t)c * v; }
+  __device__ __forceinline__ Acc unit(uint32_t v) const { return (uint64_t)one * v; }
+  __device__ __forceinline__ uint32_t red(Acc x) const
+  {
+    const uint32_t m = (uint32_t)x * qinv;
+    return (uint32_t)((x + (uint64_t)m * q) >> 32);
+  }
+  __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }
+  __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }
 };
 
 constexpr int kN = 3840, kD1 = 32, kD2 = 6, kD3 = 20;
 
 // CRT_25 / CRT_25^-1 on the 20 values of one (i1,i2) column, v[4*i0 + c]
-template <bool INV>
-__device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, const ArithS& A)
+template <bool INV, class AR>
+__device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, const AR& A)
 {
   if (!INV) {
 #pragma unroll
@@ -54,9 +84,9 @@ __device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, 
       uint32_t o[4];
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        uint32_t acc = C.m5[i0][r][0] * v[4 * i0];
+        typename AR::Acc acc = A.mul(C.m5[i0][r][0], v[4 * i0]);
 #pragma unroll
-        for (int c = 1; c < 4; c++) acc += C.m5[i0][r][c] * v[4 * i0 + c];
+        for (int c = 1; c < 4; c++) acc = A.mad(acc, C.m5[i0][r][c], v[4 * i0 + c]);
         o[r] = A.red(acc);
       }
 #pragma unroll
@@ -66,12 +96,12 @@ __device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, 
 #pragma unroll
   for (int c = 0; c < 4; c++) {            // DFT_5 across the block index for residue column c
     uint32_t o[5];
-    o[0] = A.red(v[c] + v[4 + c] + v[8 + c] + v[12 + c] + v[16 + c]);
+    o[0] = A.red(A.unit(v[c] + v[4 + c] + v[8 + c] + v[12 + c] + v[16 + c]));
 #pragma unroll
     for (int row = 1; row < 5; row++) {
-      uint32_t acc = v[c];
+      typename AR::Acc acc = A.unit(v[c]);
 #pragma unroll
-      for (int col = 1; col < 5; col++) acc += C.d5[row][col] * v[4 * col + c];
+      for (int col = 1; col < 5; col++) acc = A.mad(acc, C.d5[row][col], v[4 * col + c]);
       o[row] = A.red(acc);
     }
 #pragma unroll
@@ -83,9 +113,9 @@ __device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, 
       uint32_t o[4];
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        uint32_t acc = C.m5[i0][r][0] * v[4 * i0];
+        typename AR::Acc acc = A.mul(C.m5[i0][r][0], v[4 * i0]);
 #pragma unroll
-        for (int c = 1; c < 4; c++) acc += C.m5[i0][r][c] * v[4 * i0 + c];
+        for (int c = 1; c < 4; c++) acc = A.mad(acc, C.m5[i0][r][c], v[4 * i0 + c]);
         o[r] = A.red(acc);
       }
 #pragma unroll
@@ -95,38 +125,38 @@ __device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, 
 }
 
 // CRT_9 / CRT_9^-1 on the 6 values x[2*i0 + c] of one (i3, i1)
-template <bool INV>
-__device__ __forceinline__ void axis3(uint32_t (&x)[6], const FusedAConsts& C, const ArithS& A)
+template <bool INV, class AR>
+__device__ __forceinline__ void axis3(uint32_t (&x)[6], const FusedAConsts& C, const AR& A)
 {
   if (!INV) {
 #pragma unroll
     for (int i0 = 0; i0 < 3; i0++) {
       uint32_t a = x[2 * i0], b = x[2 * i0 + 1];
-      x[2 * i0] = A.red(C.m3[i0][0][0] * a + C.m3[i0][0][1] * b);
-      x[2 * i0 + 1] = A.red(C.m3[i0][1][0] * a + C.m3[i0][1][1] * b);
+      x[2 * i0] = A.red(A.mad(A.mul(C.m3[i0][0][0], a), C.m3[i0][0][1], b));
+      x[2 * i0 + 1] = A.red(A.mad(A.mul(C.m3[i0][1][0], a), C.m3[i0][1][1], b));
     }
   }
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     uint32_t a = x[c], b = x[2 + c], d = x[4 + c];
-    x[c] = A.red(a + b + d);
-    x[2 + c] = A.red(a + C.d3[1][1] * b + C.d3[1][2] * d);
-    x[4 + c] = A.red(a + C.d3[2][1] * b + C.d3[2][2] * d);
+    x[c] = A.red(A.unit(a + b + d));
+    x[2 + c] = A.red(A.mad(A.mad(A.unit(a), C.d3[1][1], b), C.d3[1][2], d));
+    x[4 + c] = A.red(A.mad(A.mad(A.unit(a), C.d3[2][1], b), C.d3[2][2], d));
   }
   if (INV) {
 #pragma unroll
     for (int i0 = 0; i0 < 3; i0++) {
       uint32_t a = x[2 * i0], b = x[2 * i0 + 1];
-      x[2 * i0] = A.red(C.m3[i0][0][0] * a + C.m3[i0][0][1] * b);
-      x[2 * i0 + 1] = A.red(C.m3[i0][1][0] * a + C.m3[i0][1][1] * b);
+      x[2 * i0] = A.red(A.mad(A.mul(C.m3[i0][0][0], a), C.m3[i0][0][1], b));
+      x[2 * i0 + 1] = A.red(A.mad(A.mul(C.m3[i0][1][0], a), C.m3[i0][1][1], b));
     }
   }
 }
 
 // One radix-2 round of the exchange network on lane bit `bit`.  Before: the lane owns (c0[j], c1[j]) for three
 // rows; after: the two columns of one butterfly.  Forward: (u,t) -> (u+t, (u-t)*tw).  Inverse: (u,t) -> (u+t*tw, u-t*tw).
-template <bool INV>
-__device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)[3], int lane, int bit, uint32_t tw, const ArithS& A)
+template <bool INV, class AR>
+__device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)[3], int lane, int bit, uint32_t tw, const AR& A)
 {
   const bool hi = (lane >> bit) & 1;
 #pragma unroll
@@ -137,9 +167,9 @@ __device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)
     if (!INV) {
       // u + t is symmetric; (u - t) = +-(keep - recv) and the sign lives in the lane's twiddle (host: q - tw for hi lanes)
       c0[j] = A.fold(keep + recv);
-      c1[j] = A.red((keep + A.q2 - recv) * tw);
+      c1[j] = A.red(A.mul(tw, keep + A.q2 - recv));
     } else {
-      const uint32_t t = A.red((hi ? keep : recv) * tw);
+      const uint32_t t = A.red(A.mul(tw, hi ? keep : recv));
       const uint32_t u = hi ? recv : keep;
       c0[j] = A.fold(u + t);
       c1[j] = A.fold(u + A.q2 - t);
@@ -158,13 +188,13 @@ __device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
 // EPB ring elements per CTA iteration on WARPS warps: phase 1 has 6*EPB warp-tasks (32 columns each), phase 2 has
 // 20*EPB; (EPB, WARPS) = (5, 10) balances both exactly (3 and 10 tasks per warp).  EPB == 1 double-buffers the
 // shared tile (one barrier per element), EPB > 1 uses a single tile and two barriers per EPB elements.
-template <bool INV, int K, int EPB, int WARPS, int MINB, int NBUF>
+template <bool INV, class AR, int K, int EPB, int WARPS, int MINB, int NBUF>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __grid_constant__ FusedAConsts C)
 {
   const int k = K ? K : k_rt;
   extern __shared__ __align__(16) uint32_t sm_dyn[];       // [NBUF][EPB][kN]
-  const ArithS A{C.q, C.q2, C.mu};
+  const AR A(C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // per-lane twiddles of the 2^6 axis, loaded once
@@ -197,7 +227,7 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll 1
         for (int a = 0; a < 20; a++) v[a] = reduce_any(src[(size_t)(a * 192) * k], C.q);
       }
-      axis5<INV>(v, C, A);
+      axis5<INV, AR>(v, C, A);
       uint32_t* dst = tile + slot * kN + col;
 #pragma unroll
       for (int a = 0; a < 20; a++) dst[a * 192] = v[a];
@@ -224,19 +254,19 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
                      : base + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
       }
 #pragma unroll
-      for (int u = 0; u < U; u++) axis3<INV>(x[u], C, A);
+      for (int u = 0; u < U; u++) axis3<INV, AR>(x[u], C, A);
       if (!INV) {
 #pragma unroll
         for (int u = 0; u < U; u++)
 #pragma unroll
           for (int j = 0; j < 3; j++) {          // crtTwiddle of 2^6 (crt.cpp:43-58), column = lane
-            c0[u][j] = A.red(x[u][2 * j] * ltw[0]);
-            c1[u][j] = A.red(x[u][2 * j + 1] * ltw[0]);
+            c0[u][j] = A.red(A.mul(ltw[0], x[u][2 * j]));
+            c1[u][j] = A.red(A.mul(ltw[0], x[u][2 * j + 1]));
           }
 #pragma unroll
         for (int r = 0; r < 5; r++)
 #pragma unroll
-          for (int u = 0; u < U; u++) exchange_round<false>(c0[u], c1[u], lane, r, ltw[1 + r], A);
+          for (int u = 0; u < U; u++) exchange_round<false, AR>(c0[u], c1[u], lane, r, ltw[1 + r], A);
         // lane owns rows 2j + (lane&1), columns (lane>>1) and (lane>>1)+16
 #pragma unroll
         for (int u = 0; u < U; u++)
@@ -255,15 +285,15 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll
         for (int r = 4; r >= 0; r--)
 #pragma unroll
-          for (int u = 0; u < U; u++) exchange_round<true>(c0[u], c1[u], lane, r, ltw[r], A);
+          for (int u = 0; u < U; u++) exchange_round<true, AR>(c0[u], c1[u], lane, r, ltw[r], A);
         // lane owns rows 2j + (lane>>4), columns 2*(lane&15) and 2*(lane&15)+1; crtTwiddle with inverse roots last
 #pragma unroll
         for (int u = 0; u < U; u++)
           if (live[u]) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-              const int64_t a = (int64_t)A.canon(A.red(c0[u][j] * ltw[5]));
-              const int64_t b = (int64_t)A.canon(A.red(c1[u][j] * ltw[6]));
+              const int64_t a = (int64_t)A.canon(A.red(A.mul(ltw[5], c0[u][j])));
+              const int64_t b = (int64_t)A.canon(A.red(A.mul(ltw[6], c1[u][j])));
               if (K == 1) {
                 __stcs(reinterpret_cast<longlong2*>(out[u] + j * 64), make_longlong2(a, b));
               } else {
@@ -280,8 +310,19 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 
 // ------------------------------------------------------------------ host: constants from the plan's root tables
 
+enum ArithClass { ARITH_NONE = 0, ARITH_S, ARITH_M };
+
+// which policy a modulus admits (see ArithS / ArithM)
+inline ArithClass arith_class(uint64_t q)
+{
+  if (8 * q * q + 2 * q < ((uint64_t)1 << 32)) return ARITH_S;
+  if (10 * q < ((uint64_t)1 << 32) && (q & 1)) return ARITH_M;      // Montgomery needs odd q
+  return ARITH_NONE;
+}
+
 struct FusedA {
   bool ok_fwd = false, ok_inv = false;
+  std::vector<int> cls;                    // ArithClass per limb
   std::vector<FusedAConsts> fwd, inv;      // per limb
   uint32_t* d_lane_tw = nullptr;           // [k][2][8][32]
 };
@@ -301,7 +342,7 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
   auto r64 = [&](int64_t j) { return rd(T[0], j % 64, k, limb, q); };
   auto r9 = [&](int64_t j) { return rd(T[1], j % 9, k, limb, q); };
   auto r25 = [&](int64_t j) { return rd(T[2], j % 25, k, limb, q); };
-  C->q = (uint32_t)q; C->q2 = (uint32_t)(2 * q); C->mu = (uint32_t)((((uint64_t)1) << 32) / q);
+  C->q = (uint32_t)q; C->q2 = (uint32_t)(2 * q); C->r0 = (uint32_t)((((uint64_t)1) << 32) / q); C->one = 1;
   const uint64_t scale = inverse ? (uint64_t)(((pl->mhatinv[limb] % (int64_t)q) + (int64_t)q) % (int64_t)q) : 1;
   for (int row = 0; row < 5; row++) for (int col = 0; col < 5; col++) C->d5[row][col] = (uint32_t)r25(5 * ((row * col) % 5));
   for (int row = 0; row < 3; row++) for (int col = 0; col < 3; col++) C->d3[row][col] = (uint32_t)r9(3 * ((row * col) % 3));
@@ -356,6 +397,19 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
       }
     }
   }
+  if (arith_class(q) == ARITH_M) {
+    // constants to Montgomery form c * 2^32 mod q; r0 = -q^-1 mod 2^32 (Newton iteration on the odd q)
+    auto mont = [&](uint32_t c) { return (uint32_t)((((uint64_t)c) << 32) % q); };
+    uint32_t inv = (uint32_t)q;                       // q * inv == 1 mod 2^3 initially
+    for (int i = 0; i < 5; i++) inv *= 2u - (uint32_t)q * inv;
+    C->r0 = 0u - inv;
+    C->one = mont(1);
+    for (auto& a : C->m5) for (auto& b : a) for (auto& c : b) c = mont(c);
+    for (auto& a : C->d5) for (auto& c : a) c = mont(c);
+    for (auto& a : C->m3) for (auto& b : a) for (auto& c : b) c = mont(c);
+    for (auto& a : C->d3) for (auto& c : a) c = mont(c);
+    for (int i = 0; i < 8 * 32; i++) lane_tw[i] = mont(lane_tw[i]);
+  }
 }
 
 bool shape_is_a(const lolb_plan* pl)
@@ -363,10 +417,8 @@ bool shape_is_a(const lolb_plan* pl)
   if (pl->kind != PLAN_RQ || pl->pe.size() != 3) return false;
   const PrimeExponent want[3] = {{2, 6}, {3, 2}, {5, 2}};
   for (int i = 0; i < 3; i++) if (pl->pe[i].prime != want[i].prime || pl->pe[i].exponent != want[i].exponent) return false;
-  for (int64_t q : pl->qs) {
-    const uint64_t uq = (uint64_t)q;
-    if (8 * uq * uq + 2 * uq >= ((uint64_t)1 << 32)) return false;      // lazy 32-bit accumulation bound
-  }
+  for (int64_t q : pl->qs)
+    if (arith_class((uint64_t)q) == ARITH_NONE) return false;
   return true;
 }
 
@@ -379,6 +431,8 @@ int fused_a_select(lolb_plan* pl, void** slot)
   if (!F) { F = new FusedA(); *slot = F; }
   const int k = pl->k;
   std::vector<uint32_t> lt((size_t)k * 2 * 8 * 32, 1u);
+  F->cls.assign(k, ARITH_NONE);
+  for (int t = 0; t < k; t++) F->cls[t] = arith_class((uint64_t)pl->qs[t]);
   F->fwd.assign(k, FusedAConsts{});
   F->inv.assign(k, FusedAConsts{});
   F->ok_fwd = pl->has_fwd && pl->ru.size() == 3;
@@ -411,11 +465,11 @@ bool fused_a_available(const void* slot, bool inverse)
   return F && (inverse ? F->ok_inv : F->ok_fwd);
 }
 
-template <bool INV, int K, int EPB, int WARPS, int MINB, int NBUF>
+template <bool INV, class AR, int K, int EPB, int WARPS, int MINB, int NBUF>
 static int launch_a(const lolb_plan* pl, int64_t* y, int64_t batch, int limb, const FusedAConsts& C, cudaStream_t st)
 {
   const size_t smem = (size_t)NBUF * EPB * kN * sizeof(uint32_t);
-  auto kern = k_fused_a<INV, K, EPB, WARPS, MINB, NBUF>;
+  auto kern = k_fused_a<INV, AR, K, EPB, WARPS, MINB, NBUF>;
   static bool attr_done = false;
   if (smem > 48 * 1024 && !attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -443,18 +497,17 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   for (int t = 0; t < pl->k; t++) {
     const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];
     int rc;
-#define LA(...) (inverse ? launch_a<true, __VA_ARGS__>(pl, y, batch, t, C, st) : launch_a<false, __VA_ARGS__>(pl, y, batch, t, C, st))
-    if (pl->k == 1) {
+#define LA(AR, ...) (inverse ? launch_a<true, AR, __VA_ARGS__>(pl, y, batch, t, C, st) : launch_a<false, AR, __VA_ARGS__>(pl, y, batch, t, C, st))
+    if (F->cls[t] == ARITH_M) {
+      rc = pl->k == 1 ? LA(ArithM, 1, 1, 3, 8, 1) : LA(ArithM, 0, 1, 3, 8, 1);
+    } else if (pl->k == 1) {
       switch (g_variant) {
-        case 1: rc = LA(1, 5, 10, 3, 1); break;
-        case 2: rc = LA(1, 1, 3, 10, 1); break;
-        case 3: rc = LA(1, 1, 2, 14, 1); break;
-        case 4: rc = LA(1, 1, 6, 5, 1); break;
-        case 5: rc = LA(1, 1, 3, 7, 2); break;
-        default: rc = LA(1, 1, 6, 5, 2); break;
+        case 0: rc = LA(ArithS, 1, 1, 6, 5, 2); break;
+        case 1: rc = LA(ArithS, 1, 5, 10, 3, 1); break;
+        default: rc = LA(ArithS, 1, 1, 3, 10, 1); break;
       }
     } else {
-      rc = LA(0, 1, 6, 5, 2);
+      rc = LA(ArithS, 0, 1, 3, 10, 1);
     }
 #undef LA
     if (rc) return rc;
