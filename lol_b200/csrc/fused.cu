@@ -11,6 +11,12 @@ void fused_a_release(void* slot);
 bool fused_a_available(const void* slot, bool inverse);
 int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 
+// fused_pow2.cu
+int fused_pow2_select(lolb_plan* pl, void** slot);
+void fused_pow2_release(void* slot);
+bool fused_pow2_available(const void* slot, bool inverse);
+int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+
 // fused_stream.cu
 const char* fused_stream_line_name(const lolb_plan* pl);
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
@@ -19,6 +25,7 @@ int fused_stream_mul(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t 
 namespace {
 struct FusedSet {
   void* a = nullptr;      // m = 14400 CRT / CRT^-1
+  void* pow2 = nullptr;   // m = 2^e CRT / CRT^-1
 };
 FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
 }  // namespace
@@ -27,7 +34,9 @@ int fused_select(lolb_plan* pl)
 {
   if (pl->kind != PLAN_RQ) return LOLB_OK;
   if (!pl->fused) pl->fused = new FusedSet();
-  return fused_a_select(pl, &set_of(pl)->a);
+  int rc = fused_a_select(pl, &set_of(pl)->a);
+  if (!rc) rc = fused_pow2_select(pl, &set_of(pl)->pow2);
+  return rc;
 }
 
 void fused_release(lolb_plan* pl)
@@ -35,6 +44,7 @@ void fused_release(lolb_plan* pl)
   FusedSet* s = set_of(pl);
   if (!s) return;
   fused_a_release(s->a);
+  fused_pow2_release(s->pow2);
   delete s;
   pl->fused = nullptr;
 }
@@ -45,6 +55,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
   if (s) {
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
+    if (!strcmp(op, "CRT") && fused_pow2_available(s->pow2, false)) return "fused_pow2";
+    if (!strcmp(op, "CRTInv") && fused_pow2_available(s->pow2, true)) return "fused_pow2";
   }
   if (!strcmp(op, "mulRq") || !strcmp(op, "MulGCRT") || !strcmp(op, "DivGCRT")) return ((int64_t)pl->n * pl->k) % 2 == 0 ? "mul_stream" : "generic";
   if (pl->kind == PLAN_RQ && (!strcmp(op, "L") || !strcmp(op, "LInv") || !strcmp(op, "GPow") || !strcmp(op, "GDec") ||
@@ -57,7 +69,9 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
 {
   const FusedSet* s = set_of(pl);
   if (!s) return LOLB_FUSED_UNAVAILABLE;
-  return fused_a_crt(pl, s->a, inverse, y, batch, st);
+  int rc = fused_a_crt(pl, s->a, inverse, y, batch, st);
+  if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_crt(pl, s->pow2, inverse, y, batch, st);
+  return rc;
 }
 
 int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)

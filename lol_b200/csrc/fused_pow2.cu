@@ -1,0 +1,330 @@
+// fused_pow2.cu -- fused Z_q CRT / CRT^-1 for power-of-two index m = 2^e (n = 2^(e-1) <= 32768), the shape of
+// BASELINE.json config B (m = 2^16 over four ~30-bit primes).  One CTA per (ring element, RNS limb): the limb lives
+// in shared memory as u32 (128 KB at n = 32768), one HBM read and one HBM write per coefficient.
+//
+// Operator (crt.cpp:518-538 with p = 2): y[i] *= w^{rev(i)} (crtTwiddle, crt.cpp:43-58), then e-1 radix-2 rounds
+// r = 0 .. e-2 of { butterfly at stride 2^r (crt.cpp:137-149) ; positions with bit r set *= w^{rev(i0) 2^(r+1)},
+// i0 = pos >> (r+1) (dftTwiddle, crt.cpp:92-106) }.  The inverse runs the rounds backwards with inverse roots
+// (crt.cpp:488-516), then the inverse crtTwiddle and mhat^-1 (crt.cpp:573-579), folded into one table here.
+//
+// Schedule: rounds are grouped into passes of S <= 5; in a pass a thread owns the 2^S coefficients that differ in
+// bits [r, r+S) and runs S rounds in registers.  Shared memory is XOR-swizzled (word ^ ((word >> 5) & 31)) so the
+// stride-1, stride-32 and stride-1024 accesses of the three passes are all bank-conflict free.  The last forward
+// pass stores straight to HBM, the first inverse pass loads straight from HBM.
+//
+// Arithmetic (4q < 2^32): lazy residues in [0,2q); twiddles in Montgomery form w * 2^32 mod q, so one
+// multiplication is IMAD.WIDE, IMAD, IMAD.WIDE with no companion table; canonical [0,q) only at the store.
+#include <cstdlib>
+
+#include "fused.cuh"
+#include "numtheory.h"
+
+namespace lolb {
+
+namespace {
+
+struct Pow2Limb {
+  uint32_t q, q2, qinv;          // qinv = -q^-1 mod 2^32
+  const uint32_t* crt_tw;        // [n]  fwd: mont(w^rev(i));  inv: mont(w^-rev(i) * mhat^-1)
+  const uint32_t* round_tw;      // rounds 0 .. e-2 back to back: round r has 2^(e-2-r) entries mont(w^{+-rev(i0) 2^(r+1)})
+};
+
+struct Pow2Params {
+  int32_t e, n, k;
+  int32_t npass;
+  int32_t pass_r[8], pass_s[8];  // forward order; the inverse walks it backwards
+  int32_t round_off[32];         // offset of round r inside round_tw
+  Pow2Limb limb[kMaxLimbs];
+};
+
+struct Mont {
+  uint32_t q, q2, qinv;
+  // x any u32, w < q  ->  x*w*2^-32 mod q  in [0, 2q)
+  __device__ __forceinline__ uint32_t mul(uint32_t x, uint32_t w) const
+  {
+    const uint64_t p = (uint64_t)x * w;
+    const uint32_t m = (uint32_t)p * qinv;
+    return (uint32_t)((p + (uint64_t)m * q) >> 32);
+  }
+  __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }
+  __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }
+};
+
+__device__ __forceinline__ int swz(int pos) { return pos ^ ((pos >> 5) & 31); }
+
+__device__ __noinline__ uint32_t reduce_any64(int64_t x, uint32_t q)
+{
+  int64_t r = x % (int64_t)q;
+  return (uint32_t)(r < 0 ? r + q : r);
+}
+
+// S rounds on the 2^S registers of one block.  Twiddle of the pair (j0, j0 | 2^a) in round r + a:
+// index (j0 >> (a+1)) + (H << (S-1-a)) of that round's table.
+template <int S, bool INV>
+__device__ __forceinline__ void rounds_in_regs(uint32_t (&v)[1 << S], const Mont& M, const uint32_t* __restrict__ round_tw,
+                                               const int32_t* round_off, int r, int H)
+{
+  if (!INV) {
+#pragma unroll
+    for (int a = 0; a < S; a++) {
+      const uint32_t* tw = round_tw + round_off[r + a] + (H << (S - 1 - a));
+#pragma unroll
+      for (int j0 = 0; j0 < (1 << S); j0++) {
+        if (j0 & (1 << a)) continue;
+        const int j1 = j0 | (1 << a);
+        const uint32_t w = __ldg(tw + (j0 >> (a + 1)));
+        const uint32_t u = v[j0], t = v[j1];
+        v[j0] = M.fold(u + t);
+        v[j1] = M.mul(u + M.q2 - t, w);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int a = S - 1; a >= 0; a--) {
+      const uint32_t* tw = round_tw + round_off[r + a] + (H << (S - 1 - a));
+#pragma unroll
+      for (int j0 = 0; j0 < (1 << S); j0++) {
+        if (j0 & (1 << a)) continue;
+        const int j1 = j0 | (1 << a);
+        const uint32_t w = __ldg(tw + (j0 >> (a + 1)));
+        const uint32_t u = v[j0], t = M.mul(v[j1], w);
+        v[j0] = M.fold(u + t);
+        v[j1] = M.fold(u + M.q2 - t);
+      }
+    }
+  }
+}
+
+// one pass over the whole limb held in shared memory.  FROM_GLOBAL / TO_GLOBAL fuse the HBM load (inverse, first
+// pass) or store (forward, last pass): those passes have r + S = e - 1, so pos(j) = low + (j << r) with `low` = block
+// index and consecutive threads touch consecutive coefficients.
+template <int S, bool INV, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void run_pass(uint32_t* sm, int64_t* gbase, int k, const Pow2Params& P, const Pow2Limb& L, const Mont& M, int r)
+{
+  const int n = P.n;
+  const int blocks = n >> S;
+  for (int b = threadIdx.x; b < blocks; b += blockDim.x) {
+    const int low = b & ((1 << r) - 1), H = b >> r;
+    const int base = low + (H << (r + S));
+    uint32_t v[1 << S];
+    if (FROM_GLOBAL) {
+      uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+      for (int j = 0; j < (1 << S); j++) {
+        const int64_t raw = __ldcs(gbase + (size_t)(base + (j << r)) * k);
+        v[j] = (uint32_t)raw;
+        hi_or |= (uint32_t)((uint64_t)raw >> 32);
+        lo_max = max(lo_max, v[j]);
+      }
+      if (hi_or != 0 || lo_max >= L.q) {
+#pragma unroll 1
+        for (int j = 0; j < (1 << S); j++) v[j] = reduce_any64(gbase[(size_t)(base + (j << r)) * k], L.q);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << S); j++) v[j] = sm[swz(base + (j << r))];
+    }
+    rounds_in_regs<S, INV>(v, M, L.round_tw, P.round_off, r, H);
+    if (TO_GLOBAL) {
+#pragma unroll
+      for (int j = 0; j < (1 << S); j++) __stcs(gbase + (size_t)(base + (j << r)) * k, (int64_t)M.canon(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < (1 << S); j++) sm[swz(base + (j << r))] = v[j];
+    }
+  }
+}
+
+template <bool INV, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void run_pass_s(int S, uint32_t* sm, int64_t* gbase, int k, const Pow2Params& P, const Pow2Limb& L, const Mont& M, int r)
+{
+  switch (S) {
+    case 5: run_pass<5, INV, FROM_GLOBAL, TO_GLOBAL>(sm, gbase, k, P, L, M, r); break;
+    case 4: run_pass<4, INV, FROM_GLOBAL, TO_GLOBAL>(sm, gbase, k, P, L, M, r); break;
+    default: run_pass<3, INV, FROM_GLOBAL, TO_GLOBAL>(sm, gbase, k, P, L, M, r); break;
+  }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(1024, 1)
+k_pow2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2Params P)
+{
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int n = P.n, k = P.k;
+  const int64_t items = batch * k;
+  for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+    const int64_t el = w / k;
+    const int limb = (int)(w - el * k);
+    const Pow2Limb& L = P.limb[limb];
+    const Mont M{L.q, L.q2, L.qinv};
+    int64_t* gbase = y + (size_t)el * n * k + limb;
+    if (!INV) {
+      // load + crtTwiddle, coalesced, 8 loads in flight per thread
+      for (int i0 = threadIdx.x; i0 < n; i0 += blockDim.x * 8) {
+        int64_t raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int pos = i0 + u * blockDim.x;
+          raw[u] = pos < n ? __ldcs(gbase + (size_t)pos * k) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int pos = i0 + u * blockDim.x;
+          if (pos < n) {
+            uint32_t x = (uint64_t)raw[u] < (uint64_t)L.q ? (uint32_t)raw[u] : reduce_any64(raw[u], L.q);
+            sm[swz(pos)] = M.mul(x, __ldg(L.crt_tw + pos));
+          }
+        }
+      }
+      __syncthreads();
+      for (int p = 0; p < P.npass; p++) {
+        if (p == P.npass - 1) run_pass_s<false, false, true>(P.pass_s[p], sm, gbase, k, P, L, M, P.pass_r[p]);
+        else run_pass_s<false, false, false>(P.pass_s[p], sm, gbase, k, P, L, M, P.pass_r[p]);
+        __syncthreads();
+      }
+    } else {
+      for (int p = P.npass - 1; p >= 0; p--) {
+        if (p == P.npass - 1) run_pass_s<true, true, false>(P.pass_s[p], sm, gbase, k, P, L, M, P.pass_r[p]);
+        else run_pass_s<true, false, false>(P.pass_s[p], sm, gbase, k, P, L, M, P.pass_r[p]);
+        __syncthreads();
+      }
+      // inverse crtTwiddle * mhat^-1, canonical store, coalesced
+      for (int pos = threadIdx.x; pos < n; pos += blockDim.x)
+        __stcs(gbase + (size_t)pos * k, (int64_t)M.canon(M.mul(sm[swz(pos)], __ldg(L.crt_tw + pos))));
+      __syncthreads();
+    }
+  }
+}
+
+struct FusedPow2 {
+  bool ok_fwd = false, ok_inv = false;
+  Pow2Params fwd{}, inv{};
+  uint32_t* d_tab = nullptr;       // all tables of all limbs, both directions
+  int threads = 1024;
+};
+
+bool shape_is_pow2(const lolb_plan* pl)
+{
+  if (pl->kind != PLAN_RQ || pl->pe.size() != 1 || pl->pe[0].prime != 2) return false;
+  const int e = pl->pe[0].exponent;
+  if (e < 7 || e > 16) return false;                    // n = 64 .. 32768 (<= 128 KB of shared memory)
+  for (int64_t q : pl->qs) if (!(q & 1) || 4 * (uint64_t)q >= ((uint64_t)1 << 32)) return false;
+  return true;
+}
+
+uint32_t neg_inv32(uint32_t q)
+{
+  uint32_t inv = q;
+  for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
+  return 0u - inv;
+}
+
+}  // namespace
+
+int fused_pow2_select(lolb_plan* pl, void** slot)
+{
+  if (!shape_is_pow2(pl)) return LOLB_OK;
+  FusedPow2* F = (FusedPow2*)*slot;
+  if (!F) { F = new FusedPow2(); *slot = F; }
+  const int e = pl->pe[0].exponent, n = pl->n, k = pl->k, rounds = e - 1;
+  F->ok_fwd = pl->has_fwd && pl->ru.size() == 1;
+  F->ok_inv = pl->has_inv && pl->ruinv.size() == 1 && (int)pl->mhatinv.size() == k;
+  Pow2Params P{};
+  P.e = e; P.n = n; P.k = k;
+  // passes of at most 5 rounds, as even as possible, at least 3 rounds each (template instances 3, 4, 5)
+  int npass = (rounds + 4) / 5;
+  if (rounds / npass < 3 && npass > 1) npass--;
+  P.npass = npass;
+  for (int p = 0, r = 0; p < npass; p++) {
+    int s = rounds / npass + (p < rounds % npass ? 1 : 0);
+    P.pass_r[p] = r; P.pass_s[p] = s; r += s;
+  }
+  if (rounds < 3 || P.pass_s[npass - 1] < 3 || P.pass_s[0] > 5) { F->ok_fwd = F->ok_inv = false; return LOLB_OK; }
+  int32_t off = 0;
+  for (int r = 0; r < rounds; r++) { P.round_off[r] = off; off += 1 << (e - 2 - r); }
+  const size_t per_dir = (size_t)n + (size_t)off;           // crt table + round tables
+  std::vector<uint32_t> host((size_t)k * 2 * per_dir, 0u);
+  const int64_t m = pl->m;
+  for (int t = 0; t < k; t++) {
+    const uint64_t q = (uint64_t)pl->qs[t];
+    auto mont = [&](uint64_t c) { return (uint32_t)(((c % q) << 32) % q); };
+    for (int dir = 0; dir < 2; dir++) {
+      if (dir == 0 ? !F->ok_fwd : !F->ok_inv) continue;
+      const std::vector<int64_t>& T = dir == 0 ? pl->ru[0] : pl->ruinv[0];
+      auto root = [&](int64_t j) { int64_t v = T[(size_t)(j % m) * k + t] % (int64_t)q; return (uint64_t)(v < 0 ? v + (int64_t)q : v); };
+      uint32_t* crt = host.data() + ((size_t)t * 2 + dir) * per_dir;
+      uint32_t* rnd = crt + n;
+      const uint64_t scale = dir == 1 ? (uint64_t)(((pl->mhatinv[t] % (int64_t)q) + (int64_t)q) % (int64_t)q) : 1;
+      for (int i = 0; i < n; i++) {
+        const uint64_t w = i ? root(digit_rev(2, e - 1, i)) : 1;          // crt.cpp:43-58
+        crt[i] = mont(mulmod64(w, scale, q));
+      }
+      for (int r = 0; r < rounds; r++)
+        for (int i0 = 0; i0 < (1 << (e - 2 - r)); i0++)                   // crt.cpp:92-106, twidRuStride = 2^(r+1)
+          rnd[P.round_off[r] + i0] = mont(i0 ? root(digit_rev(2, e - 2 - r, i0) * ((int64_t)2 << r)) : 1);
+    }
+  }
+  if (F->d_tab) { cudaFree(F->d_tab); F->d_tab = nullptr; }
+  LOLB_CUDA(cudaMalloc((void**)&F->d_tab, host.size() * sizeof(uint32_t)));
+  LOLB_CUDA(cudaMemcpy(F->d_tab, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  F->fwd = P; F->inv = P;
+  for (int t = 0; t < k; t++) {
+    const uint32_t q = (uint32_t)pl->qs[t];
+    for (int dir = 0; dir < 2; dir++) {
+      Pow2Limb& L = (dir == 0 ? F->fwd : F->inv).limb[t];
+      L.q = q; L.q2 = 2 * q; L.qinv = neg_inv32(q);
+      L.crt_tw = F->d_tab + ((size_t)t * 2 + dir) * per_dir;
+      L.round_tw = L.crt_tw + n;
+    }
+  }
+  // one block of 2^S coefficients per thread in the widest pass, at most 1024 threads
+  int blocks = n >> 5;
+  for (int p = 0; p < npass; p++) if ((n >> P.pass_s[p]) > blocks) blocks = n >> P.pass_s[p];
+  F->threads = blocks > 1024 ? 1024 : (blocks < 32 ? 32 : blocks);
+  return LOLB_OK;
+}
+
+void fused_pow2_release(void* slot)
+{
+  FusedPow2* F = (FusedPow2*)slot;
+  if (!F) return;
+  if (F->d_tab) cudaFree(F->d_tab);
+  delete F;
+}
+
+bool fused_pow2_available(const void* slot, bool inverse)
+{
+  const FusedPow2* F = (const FusedPow2*)slot;
+  return F && (inverse ? F->ok_inv : F->ok_fwd);
+}
+
+int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const FusedPow2* F = (const FusedPow2*)slot;
+  if (!fused_pow2_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
+  if (batch <= 0) return LOLB_OK;
+  const size_t smem = (size_t)pl->n * sizeof(uint32_t);
+  static bool attr_done[2] = {false, false};
+  if (smem > 48 * 1024 && !attr_done[inverse]) {
+    cudaError_t e = inverse ? cudaFuncSetAttribute(k_pow2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                            : cudaFuncSetAttribute(k_pow2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_pow2)");
+    attr_done[inverse] = true;
+  }
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  const int by_threads = 2048 / F->threads;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 16) per_sm = 16;
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  const int64_t items = batch * pl->k;
+  if (grid > items) grid = items;
+  if (inverse) k_pow2<true><<<(int)grid, F->threads, smem, st>>>(y, batch, F->inv);
+  else k_pow2<false><<<(int)grid, F->threads, smem, st>>>(y, batch, F->fwd);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_pow2");
+  count_launch();
+  return LOLB_OK;
+}
+
+}  // namespace lolb

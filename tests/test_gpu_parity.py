@@ -235,6 +235,27 @@ def test_batched_rq_matches_oracle(torch_cuda, oracle, m, qs, force_generic):
     assert t.crt(e).shape[0] == 0
 
 
+@pytest.mark.parametrize("e", list(range(5, 17)), ids=lambda e: f"m=2^{e}")
+def test_power_of_two_indices(torch_cuda, oracle, e):
+    """Every power-of-two index up to config B's 2^16 (fused NTT from 2^7 on, generic below), RNS pair with a
+    20-bit and a 30-bit prime, ragged batch; crtInv . crt = id and element-wise parity with the oracle."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    m, qs = 2 ** e, [786433, 537133057]
+    B = 3 if e >= 14 else 11
+    rng = np.random.default_rng(e)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    y = zq_input(rng, n, qs, batch=B)
+    x = torch.from_numpy(y).cuda()
+    f = t.crt(x)
+    assert np.array_equal(f.cpu().numpy(), np.stack([oracle.tensorCRTRq(y[b], pe, ru, qs) for b in range(B)]))
+    assert np.array_equal(t.crtInv(x).cpu().numpy(), np.stack([oracle.tensorCRTInvRq(y[b], pe, rui, mh, qs) for b in range(B)]))
+    assert torch.equal(t.crtInv(f), x)
+    t.plan.force_generic(True)
+    assert torch.equal(t.crt(x), f)
+
+
 def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
