@@ -196,6 +196,158 @@ k_pow2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2Param
   }
 }
 
+// ---- compile-time specialisation for E = 16 (n = 32768, passes (0,5) (5,5) (10,5)): pass geometry, swizzle and
+// table offsets fold into immediates; 512 threads x 2 blocks per pass keeps 2 x 32 coefficients in 128 registers.
+constexpr int kE16 = 16, kN16 = 1 << 15, kT16 = 512;
+__host__ __device__ constexpr int round_off16(int r) { return (1 << 14) * 2 - (1 << (15 - r)); }   // sum_{r'<r} 2^(14-r')
+
+// the 31 twiddles of one block: round R+a needs entries [H << (4-a), (H+1) << (4-a)) of its table -- contiguous, so
+// they are fetched with 128/64/32-bit loads up front (9 instructions) instead of one dependent load per butterfly
+__device__ __forceinline__ void load_tw16(uint32_t (&tw)[31], const uint32_t* __restrict__ round_tw, int R, int H)
+{
+  const uint32_t* t0 = round_tw + round_off16(R) + (H << 4);
+  const uint32_t* t1 = round_tw + round_off16(R + 1) + (H << 3);
+  const uint32_t* t2 = round_tw + round_off16(R + 2) + (H << 2);
+  const uint32_t* t3 = round_tw + round_off16(R + 3) + (H << 1);
+  const uint32_t* t4 = round_tw + round_off16(R + 4) + H;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(t0) + i);
+    tw[4 * i] = x.x; tw[4 * i + 1] = x.y; tw[4 * i + 2] = x.z; tw[4 * i + 3] = x.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(t1) + i);
+    tw[16 + 4 * i] = x.x; tw[16 + 4 * i + 1] = x.y; tw[16 + 4 * i + 2] = x.z; tw[16 + 4 * i + 3] = x.w;
+  }
+  {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(t2));
+    tw[24] = x.x; tw[25] = x.y; tw[26] = x.z; tw[27] = x.w;
+    const uint2 z = __ldg(reinterpret_cast<const uint2*>(t3));
+    tw[28] = z.x; tw[29] = z.y;
+    tw[30] = __ldg(t4);
+  }
+}
+
+template <bool INV>
+__device__ __forceinline__ void rounds16(uint32_t (&v)[32], const Mont& M, const uint32_t (&tw)[31])
+{
+#pragma unroll
+  for (int aa = 0; aa < 5; aa++) {
+    const int a = INV ? 4 - aa : aa;
+    const int toff = 32 - (32 >> a);          // 0, 16, 24, 28, 30
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0++) {
+      if (j0 & (1 << a)) continue;
+      const int j1 = j0 | (1 << a);
+      const uint32_t w = tw[toff + (j0 >> (a + 1))];
+      if (!INV) {
+        const uint32_t u = v[j0], t = v[j1];
+        v[j0] = M.fold(u + t);
+        v[j1] = M.mul(u + M.q2 - t, w);
+      } else {
+        const uint32_t u = v[j0], t = M.mul(v[j1], w);
+        v[j0] = M.fold(u + t);
+        v[j1] = M.fold(u + M.q2 - t);
+      }
+    }
+  }
+}
+
+// physical (swizzled) shared-memory word of coefficient j of block (low, H) in the pass starting at bit R
+template <int R>
+__device__ __forceinline__ int phys16(int low, int H, int j)
+{
+  if (R == 0) return (j ^ (H & 31)) + (H << 5);                       // pos = j + 32 H
+  if (R == 5) return (low ^ j) + (j << 5) + (H << 10);                // pos = low + 32 j + 1024 H
+  return (low ^ ((low >> 5) & 31)) + (j << 10);                       // pos = low + 1024 j
+}
+
+template <int R, bool INV, bool FROM_GLOBAL, bool TO_GLOBAL, int K>
+__device__ __forceinline__ void pass16(uint32_t* sm, int64_t* gbase, int k_rt, const Pow2Limb& L, const Mont& M)
+{
+  const int k = K ? K : k_rt;
+#pragma unroll 1
+  for (int b = threadIdx.x; b < (kN16 >> 5); b += kT16) {
+    const int low = b & ((1 << R) - 1), H = b >> R;
+    uint32_t v[32], tw[31];
+    load_tw16(tw, L.round_tw, R, H);
+    if (FROM_GLOBAL) {          // R = 10: pos = b + 1024 j
+      uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int64_t raw = __ldcs(gbase + (size_t)(b + (j << 10)) * k);
+        v[j] = (uint32_t)raw;
+        hi_or |= (uint32_t)((uint64_t)raw >> 32);
+        lo_max = max(lo_max, v[j]);
+      }
+      if (hi_or != 0 || lo_max >= L.q) {
+#pragma unroll 1
+        for (int j = 0; j < 32; j++) v[j] = reduce_any64(gbase[(size_t)(b + (j << 10)) * k], L.q);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = sm[phys16<R>(low, H, j)];
+    }
+    rounds16<INV>(v, M, tw);
+    if (TO_GLOBAL) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) __stcs(gbase + (size_t)(b + (j << 10)) * k, (int64_t)M.canon(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j++) sm[phys16<R>(low, H, j)] = v[j];
+    }
+  }
+}
+
+template <bool INV, int K>
+__global__ void __launch_bounds__(kT16, 1)
+k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2Params P)
+{
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int k = K ? K : P.k;
+  const int64_t items = batch * k;
+  for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+    const int64_t el = w / k;
+    const int limb = (int)(w - el * k);
+    const Pow2Limb& L = P.limb[limb];
+    const Mont M{L.q, L.q2, L.qinv};
+    int64_t* gbase = y + (size_t)el * kN16 * k + limb;
+    if (!INV) {
+#pragma unroll 1
+      for (int i0 = threadIdx.x; i0 < kN16; i0 += kT16 * 8) {
+        int64_t raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) raw[u] = __ldcs(gbase + (size_t)(i0 + u * kT16) * k);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int pos = i0 + u * kT16;
+          const uint32_t x = (uint64_t)raw[u] < (uint64_t)L.q ? (uint32_t)raw[u] : reduce_any64(raw[u], L.q);
+          sm[swz(pos)] = M.mul(x, __ldg(L.crt_tw + pos));
+        }
+      }
+      __syncthreads();
+      pass16<0, false, false, false, K>(sm, gbase, k, L, M);
+      __syncthreads();
+      pass16<5, false, false, false, K>(sm, gbase, k, L, M);
+      __syncthreads();
+      pass16<10, false, false, true, K>(sm, gbase, k, L, M);
+      __syncthreads();
+    } else {
+      pass16<10, true, true, false, K>(sm, gbase, k, L, M);
+      __syncthreads();
+      pass16<5, true, false, false, K>(sm, gbase, k, L, M);
+      __syncthreads();
+      pass16<0, true, false, false, K>(sm, gbase, k, L, M);
+      __syncthreads();
+#pragma unroll 4
+      for (int pos = threadIdx.x; pos < kN16; pos += kT16)
+        __stcs(gbase + (size_t)pos * k, (int64_t)M.canon(M.mul(sm[swz(pos)], __ldg(L.crt_tw + pos))));
+      __syncthreads();
+    }
+  }
+}
+
 struct FusedPow2 {
   bool ok_fwd = false, ok_inv = false;
   Pow2Params fwd{}, inv{};
@@ -242,7 +394,7 @@ int fused_pow2_select(lolb_plan* pl, void** slot)
   if (rounds < 3 || P.pass_s[npass - 1] < 3 || P.pass_s[0] > 5) { F->ok_fwd = F->ok_inv = false; return LOLB_OK; }
   int32_t off = 0;
   for (int r = 0; r < rounds; r++) { P.round_off[r] = off; off += 1 << (e - 2 - r); }
-  const size_t per_dir = (size_t)n + (size_t)off;           // crt table + round tables
+  const size_t per_dir = (((size_t)n + (size_t)off) + 3) & ~(size_t)3;   // crt table + round tables, 16-byte multiple
   std::vector<uint32_t> host((size_t)k * 2 * per_dir, 0u);
   const int64_t m = pl->m;
   for (int t = 0; t < k; t++) {
@@ -319,7 +471,23 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
   int64_t grid = (int64_t)pl->num_sms * per_sm;
   const int64_t items = batch * pl->k;
   if (grid > items) grid = items;
-  if (inverse) k_pow2<true><<<(int)grid, F->threads, smem, st>>>(y, batch, F->inv);
+  if (pl->pe[0].exponent == kE16 && !getenv("LOLB_POW2_GENERIC")) {
+    static bool attr16 = false;
+    if (!attr16) {
+      cudaFuncSetAttribute(k_pow2_e16<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr16 = true;
+    }
+    if (pl->k == 1) {
+      if (inverse) k_pow2_e16<true, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
+      else k_pow2_e16<false, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
+    } else {
+      if (inverse) k_pow2_e16<true, 0><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
+      else k_pow2_e16<false, 0><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
+    }
+  } else if (inverse) k_pow2<true><<<(int)grid, F->threads, smem, st>>>(y, batch, F->inv);
   else k_pow2<false><<<(int)grid, F->threads, smem, st>>>(y, batch, F->fwd);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_pow2");

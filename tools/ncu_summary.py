@@ -1,0 +1,26 @@
+"""Summarise an .ncu-rep (raw page) : python tools/ncu_summary.py file.ncu-rep"""
+import csv, subprocess, sys, io
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'smsp__warps_eligible.avg.per_cycle_active', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'lts__t_sector_hit_rate.pct', 'sm__cycles_elapsed.max',
+        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum']
+for r in rows[2:]:
+    print('----', r[hdr.index('Kernel Name')][:70])
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w); print(f'  {w} [{units[i]}] = {r[i]}')
+    items = []
+    for i, h in enumerate(hdr):
+        if 'pcsamp_warps_issue_stalled' in h and 'not_issued' not in h:
+            try: items.append((float(r[i]), h.replace('smsp__pcsamp_warps_issue_stalled_', '')))
+            except ValueError: pass
+    items.sort(reverse=True); tot = sum(v for v, _ in items) or 1
+    print('  stalls:', ', '.join(f'{h} {100*v/tot:.0f}%' for v, h in items[:9]))
