@@ -263,49 +263,31 @@ __device__ __forceinline__ int phys16(int low, int H, int j)
   return (low ^ ((low >> 5) & 31)) + (j << 10);                       // pos = low + 1024 j
 }
 
-template <int R, bool INV, bool FROM_GLOBAL, bool TO_GLOBAL, int K>
-__device__ __forceinline__ void pass16(uint32_t* sm, int64_t* gbase, int k_rt, const Pow2Limb& L, const Mont& M)
+// one block (32 coefficients) of the pass starting at bit R, shared memory -> registers -> shared memory
+template <int R, bool INV>
+__device__ __forceinline__ void block16_smem(uint32_t* sm, const Pow2Limb& L, const Mont& M, int low, int H)
 {
-  const int k = K ? K : k_rt;
-#pragma unroll 1
-  for (int b = threadIdx.x; b < (kN16 >> 5); b += kT16) {
-    const int low = b & ((1 << R) - 1), H = b >> R;
-    uint32_t v[32], tw[31];
-    load_tw16(tw, L.round_tw, R, H);
-    if (FROM_GLOBAL) {          // R = 10: pos = b + 1024 j
-      uint32_t hi_or = 0, lo_max = 0;
+  uint32_t v[32], tw[31];
+  load_tw16(tw, L.round_tw, R, H);
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int64_t raw = __ldcs(gbase + (size_t)(b + (j << 10)) * k);
-        v[j] = (uint32_t)raw;
-        hi_or |= (uint32_t)((uint64_t)raw >> 32);
-        lo_max = max(lo_max, v[j]);
-      }
-      if (hi_or != 0 || lo_max >= L.q) {
-#pragma unroll 1
-        for (int j = 0; j < 32; j++) v[j] = reduce_any64(gbase[(size_t)(b + (j << 10)) * k], L.q);
-      }
-    } else {
+  for (int j = 0; j < 32; j++) v[j] = sm[phys16<R>(low, H, j)];
+  rounds16<INV>(v, M, tw);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = sm[phys16<R>(low, H, j)];
-    }
-    rounds16<INV>(v, M, tw);
-    if (TO_GLOBAL) {
-#pragma unroll
-      for (int j = 0; j < 32; j++) __stcs(gbase + (size_t)(b + (j << 10)) * k, (int64_t)M.canon(v[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j++) sm[phys16<R>(low, H, j)] = v[j];
-    }
-  }
+  for (int j = 0; j < 32; j++) sm[phys16<R>(low, H, j)] = v[j];
 }
 
+// Dependency structure used below: the pass on bits [0,5) works inside aligned 32-blocks and the pass on bits
+// [5,10) inside aligned 1024-chunks, so a warp that owns whole 1024-chunks (load/store, pass 0 and pass 1 of that
+// chunk) needs only __syncwarp between them.  Only the pass on bits [10,15) couples all chunks: two CTA barriers
+// per ring element, and warps drift apart so that one warp's HBM traffic overlaps another warp's arithmetic.
 template <bool INV, int K>
 __global__ void __launch_bounds__(kT16, 1)
 k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2Params P)
 {
   extern __shared__ __align__(16) uint32_t sm[];
   const int k = K ? K : P.k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kT16 / 32, kChunks = kN16 >> 10;
   const int64_t items = batch * k;
   for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
     const int64_t el = w / k;
@@ -315,34 +297,73 @@ k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2P
     int64_t* gbase = y + (size_t)el * kN16 * k + limb;
     if (!INV) {
 #pragma unroll 1
-      for (int i0 = threadIdx.x; i0 < kN16; i0 += kT16 * 8) {
-        int64_t raw[8];
+      for (int H = warp; H < kChunks; H += kWarps) {
+        // load chunk H (coalesced) with crtTwiddle
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          int64_t raw[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) raw[u] = __ldcs(gbase + (size_t)(i0 + u * kT16) * k);
+          for (int u = 0; u < 8; u++) raw[u] = __ldcs(gbase + (size_t)((H << 10) + ((i0 + u) << 5) + lane) * k);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int pos = i0 + u * kT16;
-          const uint32_t x = (uint64_t)raw[u] < (uint64_t)L.q ? (uint32_t)raw[u] : reduce_any64(raw[u], L.q);
-          sm[swz(pos)] = M.mul(x, __ldg(L.crt_tw + pos));
+          for (int u = 0; u < 8; u++) {
+            const int pos = (H << 10) + ((i0 + u) << 5) + lane;
+            const uint32_t x = (uint64_t)raw[u] < (uint64_t)L.q ? (uint32_t)raw[u] : reduce_any64(raw[u], L.q);
+            sm[swz(pos)] = M.mul(x, __ldg(L.crt_tw + pos));
+          }
         }
+        __syncwarp();
+        block16_smem<0, false>(sm, L, M, 0, (H << 5) + lane);
+        __syncwarp();
+        block16_smem<5, false>(sm, L, M, lane, H);
       }
       __syncthreads();
-      pass16<0, false, false, false, K>(sm, gbase, k, L, M);
-      __syncthreads();
-      pass16<5, false, false, false, K>(sm, gbase, k, L, M);
-      __syncthreads();
-      pass16<10, false, false, true, K>(sm, gbase, k, L, M);
+      // bits [10,15): block b = coefficients b + 1024 j, straight to HBM
+#pragma unroll 1
+      for (int b = threadIdx.x; b < 1024; b += kT16) {
+        uint32_t v[32], tw[31];
+        load_tw16(tw, L.round_tw, 10, 0);
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = sm[phys16<10>(b, 0, j)];
+        rounds16<false>(v, M, tw);
+#pragma unroll
+        for (int j = 0; j < 32; j++) __stcs(gbase + (size_t)(b + (j << 10)) * k, (int64_t)M.canon(v[j]));
+      }
       __syncthreads();
     } else {
-      pass16<10, true, true, false, K>(sm, gbase, k, L, M);
+#pragma unroll 1
+      for (int b = threadIdx.x; b < 1024; b += kT16) {
+        uint32_t v[32], tw[31];
+        load_tw16(tw, L.round_tw, 10, 0);
+        uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int64_t raw = __ldcs(gbase + (size_t)(b + (j << 10)) * k);
+          v[j] = (uint32_t)raw;
+          hi_or |= (uint32_t)((uint64_t)raw >> 32);
+          lo_max = max(lo_max, v[j]);
+        }
+        if (hi_or != 0 || lo_max >= L.q) {
+#pragma unroll 1
+          for (int j = 0; j < 32; j++) v[j] = reduce_any64(gbase[(size_t)(b + (j << 10)) * k], L.q);
+        }
+        rounds16<true>(v, M, tw);
+#pragma unroll
+        for (int j = 0; j < 32; j++) sm[phys16<10>(b, 0, j)] = v[j];
+      }
       __syncthreads();
-      pass16<5, true, false, false, K>(sm, gbase, k, L, M);
-      __syncthreads();
-      pass16<0, true, false, false, K>(sm, gbase, k, L, M);
-      __syncthreads();
-#pragma unroll 4
-      for (int pos = threadIdx.x; pos < kN16; pos += kT16)
-        __stcs(gbase + (size_t)pos * k, (int64_t)M.canon(M.mul(sm[swz(pos)], __ldg(L.crt_tw + pos))));
+#pragma unroll 1
+      for (int H = warp; H < kChunks; H += kWarps) {
+        block16_smem<5, true>(sm, L, M, lane, H);
+        __syncwarp();
+        block16_smem<0, true>(sm, L, M, 0, (H << 5) + lane);
+        __syncwarp();
+        // inverse crtTwiddle * mhat^-1, canonical store of chunk H
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+          const int pos = (H << 10) + (i << 5) + lane;
+          __stcs(gbase + (size_t)pos * k, (int64_t)M.canon(M.mul(sm[swz(pos)], __ldg(L.crt_tw + pos))));
+        }
+      }
       __syncthreads();
     }
   }
