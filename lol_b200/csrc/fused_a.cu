@@ -43,12 +43,12 @@ struct FusedAConsts {
 // ArithS (8q^2 + 2q < 2^32, e.g. q = 14401): 32-bit multiply-accumulate, Barrett reduction, constants as plain residues.
 struct ArithS {
   typedef uint32_t Acc;
-  uint32_t q, q2, mu;
-  __device__ __forceinline__ ArithS(const FusedAConsts& C) : q(C.q), q2(C.q2), mu(C.r0) {}
+  uint32_t q, q2, mu, nq;    // nq = 2^32 - q: "x - t*q" as one multiply-add without a negation
+  __device__ __forceinline__ ArithS(const FusedAConsts& C) : q(C.q), q2(C.q2), mu(C.r0), nq(0u - C.q) {}
   __device__ __forceinline__ Acc mul(uint32_t c, uint32_t v) const { return c * v; }
   __device__ __forceinline__ Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + c * v; }
   __device__ __forceinline__ Acc unit(uint32_t v) const { return v; }                                   // the "1 * v" term
-  __device__ __forceinline__ uint32_t red(Acc x) const { return x - __umulhi(x, mu) * q; }              // any x -> [0,2q)
+  __device__ __forceinline__ uint32_t red(Acc x) const { return __umulhi(x, mu) * nq + x; }             // any x -> [0,2q)
   __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }                 // [0,4q) -> [0,2q)
   __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }                 // [0,2q) -> [0,q)
 };
