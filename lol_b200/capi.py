@@ -169,6 +169,9 @@ class PlanC:
     def handle(self):
         return self._h
 
+    def force_generic(self, on: bool = True) -> None:
+        lib().lolb_plan_set_force_generic(self._h, int(on))
+
     def op(self, name: str, ptr: int, batch: int, stream: int = 0) -> int:
         """name: 'LR', 'LInvDouble', 'GPowC', 'CRTC', 'CRTInvC', 'GaussianDec', 'GInvPowC', ..."""
         f = getattr(lib(), "lolb_tensor" + name)

@@ -268,34 +268,47 @@ extern "C" int lolb_mulRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int
   return engine_mul_zq(plan, y, b, batch, b_batch, st);
 }
 
+// modulus-free rings: streaming kernel when the index has one or two small odd primes, generic engine otherwise
+static int plain_line(const lolb_plan* plan, int ring, int kind, void* y, int64_t batch, double rscale, void* stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!plan->force_generic) {
+    int rc = fused_plain_line(plan, ring, kind, y, batch, rscale, st);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  if (ring == RING_I64) return engine_line_i64(plan, kind, 0, nullptr, (int64_t*)y, batch, st);
+  if (ring == RING_F64) return engine_line_f64(plan, kind, (double*)y, batch, st);
+  return engine_line_c64(plan, kind, rscale, (double2*)y, batch, st);
+}
+
 extern "C" int lolb_tensorLR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_L, 0, nullptr, y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_I64, PASS_L, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorLInvR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_LINV, 0, nullptr, y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_I64, PASS_LINV, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorGPowR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GPOW, 0, nullptr, y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_I64, PASS_GPOW, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorGDecR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GDEC, 0, nullptr, y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_I64, PASS_GDEC, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorGInvPowR(const lolb_plan* plan, hInt_t* y, hShort_t* ok, int64_t batch, void* stream)
 { REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GINVPOW, plan->odd_rad, ok, y, batch, (cudaStream_t)stream); }
 extern "C" int lolb_tensorGInvDecR(const lolb_plan* plan, hInt_t* y, hShort_t* ok, int64_t batch, void* stream)
 { REQUIRE_PLAN(PLAN_C); return engine_line_i64(plan, PASS_GINVDEC, plan->odd_rad, ok, y, batch, (cudaStream_t)stream); }
 extern "C" int lolb_tensorLDouble(const lolb_plan* plan, double* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_f64(plan, PASS_L, y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_F64, PASS_L, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorLInvDouble(const lolb_plan* plan, double* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_f64(plan, PASS_LINV, y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_F64, PASS_LINV, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorLC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_L, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_C64, PASS_L, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorLInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_LINV, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_C64, PASS_LINV, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorGPowC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GPOW, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_C64, PASS_GPOW, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorGDecC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GDEC, 0.0, (double2*)y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_C64, PASS_GDEC, y, batch, 0.0, stream); }
 extern "C" int lolb_tensorGInvPowC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GINVPOW, 1.0 / (double)plan->odd_rad, (double2*)y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_C64, PASS_GINVPOW, y, batch, 1.0 / (double)plan->odd_rad, stream); }
 extern "C" int lolb_tensorGInvDecC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
-{ REQUIRE_PLAN(PLAN_C); return engine_line_c64(plan, PASS_GINVDEC, 1.0 / (double)plan->odd_rad, (double2*)y, batch, (cudaStream_t)stream); }
+{ REQUIRE_PLAN(PLAN_C); return plain_line(plan, RING_C64, PASS_GINVDEC, y, batch, 1.0 / (double)plan->odd_rad, stream); }
 
 extern "C" int lolb_tensorCRTC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
 {
@@ -319,18 +332,30 @@ extern "C" int lolb_tensorGaussianDec(const lolb_plan* plan, double* y, int64_t 
 {
   REQUIRE_PLAN(PLAN_C);
   if (!plan->has_fwd) return LOLB_ERR_NO_CRT;
+  if (!plan->force_generic) {
+    int rc = fused_plain_gauss(plan, y, batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   return engine_gauss(plan, y, batch, (cudaStream_t)stream);
 }
 extern "C" int lolb_tensorNormSqR(const lolb_plan* plan, const hInt_t* y, hInt_t* out, int64_t batch, void* stream)
 {
   REQUIRE_PLAN(PLAN_C);
   if (batch > 0 && !out) { set_error("lolb_tensorNormSqR: NULL out"); return LOLB_ERR_ARG; }
+  if (!plan->force_generic) {
+    int rc = fused_plain_normsq_i64(plan, y, out, batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   return engine_normsq_i64(plan, y, out, batch, (cudaStream_t)stream);
 }
 extern "C" int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double* out, int64_t batch, void* stream)
 {
   REQUIRE_PLAN(PLAN_C);
   if (batch > 0 && !out) { set_error("lolb_tensorNormSqD: NULL out"); return LOLB_ERR_ARG; }
+  if (!plan->force_generic) {
+    int rc = fused_plain_normsq_f64(plan, y, out, batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   return engine_normsq_f64(plan, y, out, batch, (cudaStream_t)stream);
 }
 

@@ -14,5 +14,10 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op);
 int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
 int fused_mul_rq(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st);
+// modulus-free rings (fused_plain.cu); ring = RING_I64 / RING_F64 / RING_C64
+int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t batch, double rscale, cudaStream_t st);
+int fused_plain_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st);
+int fused_plain_normsq_i64(const lolb_plan* pl, const int64_t* y, int64_t* out, int64_t batch, cudaStream_t st);
+int fused_plain_normsq_f64(const lolb_plan* pl, const double* y, double* out, int64_t batch, cudaStream_t st);
 
 }  // namespace lolb

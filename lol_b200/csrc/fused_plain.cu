@@ -1,0 +1,417 @@
+// fused_plain.cu -- streaming kernels for the modulus-free rings (wrapping int64 "R", double, complex double):
+// L, L^-1, *g (l.cpp:28-98, g.cpp:16-58), the Gaussian E_m transform (random.cpp:19-64) and g-norm (norm.cpp:15-80)
+// for indices with one or two small odd primes.  Same tile scheme as fused_stream.cu: a thread owns the
+// (pA-1)*(pB-1) coefficients that share all other tensor digits, applies axis A then axis B in registers, one HBM
+// read and one HBM write per coefficient, no shared memory.  tupSize > 1 is folded into the strides for the
+// element-wise operators (I (x) A (x) I_{R*k}); Gaussian and norm are per-limb and take tupSize = 1 here.
+#include "fused.cuh"
+#include "rings.cuh"
+
+namespace lolb {
+
+namespace {
+
+struct PlainGeom {
+  int32_t n;             // coefficients per element (tupSize folded in)
+  int32_t RA, RB;        // strides of the two axes (tupSize folded in); RB = n without a second axis
+  int32_t M;             // RB / (RA * dA)
+  int32_t tiles;         // n / (dA * dB)
+};
+
+// ring-generic prime-index operators on one line, operation order of the reference
+template <int KIND, int P, class R>
+__device__ __forceinline__ void line_ring(const R& ring, typename R::T (&v)[P - 1])
+{
+  typedef typename R::T T;
+  constexpr int D = P - 1;
+  if (KIND == PASS_L) {
+#pragma unroll
+    for (int a = 1; a < D; a++) v[a] = ring.add(v[a], v[a - 1]);
+  } else if (KIND == PASS_LINV) {
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) v[a] = ring.sub(v[a], v[a - 1]);
+  } else if (KIND == PASS_GPOW) {
+    const T last = v[D - 1];
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) v[a] = ring.add(v[a], ring.sub(last, v[a - 1]));
+    v[0] = ring.add(v[0], last);
+  } else if (KIND == PASS_GDEC) {
+    T acc = v[0];
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) { acc = ring.add(acc, v[a]); v[a] = ring.sub(v[a], v[a - 1]); }
+    v[0] = ring.add(v[0], acc);
+  } else if (KIND == PASS_GINVPOW) {
+    T lo = ring.zero(), hi = ring.zero();
+#pragma unroll
+    for (int a = 0; a < D; a++) lo = ring.add(lo, v[a]);
+#pragma unroll
+    for (int a = D - 1; a >= 0; a--) {
+      const T z = v[a];
+      v[a] = ring.sub(ring.mul(ring.from_int(P - 1 - a), lo), ring.mul(ring.from_int(a + 1), hi));
+      lo = ring.sub(lo, z); hi = ring.add(hi, z);
+    }
+  } else if (KIND == PASS_GINVDEC) {
+    T s = ring.zero();
+#pragma unroll
+    for (int a = 0; a < D; a++) s = ring.add(s, ring.mul(ring.from_int(a + 1), v[a]));
+    T acc = s;
+    const T pp = ring.from_int(P);
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) { const T keep = acc; acc = ring.sub(acc, ring.mul(v[a], pp)); v[a] = keep; }
+    v[0] = acc;
+  } else if (KIND == PASS_NORMSQ) {
+    T s = ring.zero();
+#pragma unroll
+    for (int a = 0; a < D; a++) s = ring.add(s, v[a]);
+#pragma unroll
+    for (int a = 0; a < D; a++) v[a] = ring.add(v[a], s);
+  }
+}
+
+struct TileIndex {
+  size_t off, sa, sb;
+  __device__ __forceinline__ TileIndex(const PlainGeom& G, int t, int DA, int DB)
+  {
+    const int lo = t % G.RA; t /= G.RA;
+    const int mid = t % G.M;
+    const int hi = t / G.M;
+    off = (size_t)lo + (size_t)G.RA * DA * mid + (size_t)G.RB * DB * hi;
+    sa = (size_t)G.RA; sb = (size_t)G.RB;
+  }
+};
+
+template <class R, int KIND, int PA, int PB>
+__global__ void __launch_bounds__(256)
+k_line_plain(typename R::IO* __restrict__ y, int64_t batch, const __grid_constant__ PlainGeom G, double rscale)
+{
+  typedef typename R::T T;
+  constexpr int DA = PA - 1, DB = PB > 1 ? PB - 1 : 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G.tiles) return;
+  const TileIndex ix(G, t, DA, DB);
+  const R ring{};
+  for (int64_t e = blockIdx.y; e < batch; e += gridDim.y) {
+    typename R::IO* base = y + (size_t)e * G.n + ix.off;
+    T v[DB][DA];
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) v[b][a] = __ldcs(base + ix.sa * a + ix.sb * b);
+#pragma unroll
+    for (int b = 0; b < DB; b++) line_ring<KIND, PA, R>(ring, v[b]);
+    if constexpr (PB > 1) {
+#pragma unroll
+      for (int a = 0; a < DA; a++) {
+        T w[DB];
+#pragma unroll
+        for (int b = 0; b < DB; b++) w[b] = v[b][a];
+        line_ring<KIND, PB, R>(ring, w);
+#pragma unroll
+        for (int b = 0; b < DB; b++) v[b][a] = w[b];
+      }
+    }
+    if constexpr (sizeof(T) == 16) {          // complex: optional real scale (g.cpp:209-220 intent)
+      if (rscale != 0.0) {
+#pragma unroll
+        for (int b = 0; b < DB; b++)
+#pragma unroll
+          for (int a = 0; a < DA; a++) v[b][a] = make_double2(__dmul_rn(v[b][a].x, rscale), __dmul_rn(v[b][a].y, rscale));
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) __stcs(base + ix.sa * a + ix.sb * b, v[b][a]);
+  }
+}
+
+// E_p as a dense (p-1) x (p-1) real matrix per odd prime, row-major; built on the host from the complex roots
+struct GaussMats {
+  double a[6][6];
+  double b[6][6];
+};
+
+// out[row] = (sum_col (2 * E[row][col]) * in[col]) / sqrt(2), accumulation order of random.cpp:33-40
+template <int P>
+__device__ __forceinline__ void gauss_line(double (&v)[P - 1], const double (&E)[6][6])
+{
+  constexpr int D = P - 1;
+  double o[D];
+  const double sqrt2 = sqrt(2.0);
+#pragma unroll
+  for (int row = 0; row < D; row++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int col = 0; col < D; col++) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(2.0, E[row][col]), v[col]));
+    o[row] = __ddiv_rn(acc, sqrt2);
+  }
+#pragma unroll
+  for (int row = 0; row < D; row++) v[row] = o[row];
+}
+
+template <int PA, int PB>
+__global__ void __launch_bounds__(256)
+k_gauss_stream(double* __restrict__ y, int64_t batch, const __grid_constant__ PlainGeom G, const __grid_constant__ GaussMats E)
+{
+  constexpr int DA = PA - 1, DB = PB > 1 ? PB - 1 : 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G.tiles) return;
+  const TileIndex ix(G, t, DA, DB);
+  for (int64_t e = blockIdx.y; e < batch; e += gridDim.y) {
+    double* base = y + (size_t)e * G.n + ix.off;
+    double v[DB][DA];
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) v[b][a] = __ldcs(base + ix.sa * a + ix.sb * b);
+#pragma unroll
+    for (int b = 0; b < DB; b++) gauss_line<PA>(v[b], E.a);
+    if constexpr (PB > 1) {
+#pragma unroll
+      for (int a = 0; a < DA; a++) {
+        double w[DB];
+#pragma unroll
+        for (int b = 0; b < DB; b++) w[b] = v[b][a];
+        gauss_line<PB>(w, E.b);
+#pragma unroll
+        for (int b = 0; b < DB; b++) v[b][a] = w[b];
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) __stcs(base + ix.sa * a + ix.sb * b, v[b][a]);
+  }
+}
+
+__device__ __forceinline__ int64_t wsum(int64_t v)
+{
+  for (int o = 16; o > 0; o >>= 1) v = (int64_t)((uint64_t)v + (uint64_t)__shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double wsum(double v)
+{
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one CTA per ring element (grid-stride): out[e] = sum_j y[j] * ((x)(I+J) y)[j]; fixed reduction tree => deterministic
+template <class R, int PA, int PB>
+__global__ void __launch_bounds__(512)
+k_normsq_stream(const typename R::IO* __restrict__ y, typename R::IO* __restrict__ out, int64_t batch, const __grid_constant__ PlainGeom G)
+{
+  typedef typename R::T T;
+  constexpr int DA = PA - 1, DB = PB > 1 ? PB - 1 : 1;
+  __shared__ T red[32];
+  const R ring{};
+  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
+    T acc = ring.zero();
+    for (int t = threadIdx.x; t < G.tiles; t += blockDim.x) {
+      const TileIndex ix(G, t, DA, DB);
+      const typename R::IO* base = y + (size_t)e * G.n + ix.off;
+      T v[DB][DA], o[DB][DA];
+#pragma unroll
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) { v[b][a] = __ldcs(base + ix.sa * a + ix.sb * b); o[b][a] = v[b][a]; }
+#pragma unroll
+      for (int b = 0; b < DB; b++) line_ring<PASS_NORMSQ, PA, R>(ring, v[b]);
+      if constexpr (PB > 1) {
+#pragma unroll
+        for (int a = 0; a < DA; a++) {
+          T w[DB];
+#pragma unroll
+          for (int b = 0; b < DB; b++) w[b] = v[b][a];
+          line_ring<PASS_NORMSQ, PB, R>(ring, w);
+#pragma unroll
+          for (int b = 0; b < DB; b++) v[b][a] = w[b];
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) acc = ring.add(acc, ring.mul(o[b][a], v[b][a]));
+    }
+    acc = wsum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      T v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : ring.zero();
+      v = wsum(v);
+      if (threadIdx.x == 0) out[e] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// odd prime axes of the plan as (p, rts, p^(e-1)); returns how many
+int odd_axes(const lolb_plan* pl, int (&p)[4], int64_t (&rts)[4], int (&ppi)[4], int64_t (&mprime)[4])
+{
+  int cnt = 0;
+  int64_t r = 1;
+  for (size_t i = 0; i < pl->pe.size(); i++) {
+    const PrimeExponent& pe = pl->pe[i];
+    int64_t mp = 1;
+    for (int j = 1; j < pe.exponent; j++) mp *= pe.prime;
+    if (pe.prime != 2) { if (cnt < 4) { p[cnt] = pe.prime; rts[cnt] = r; ppi[cnt] = (int)i; mprime[cnt] = mp; } cnt++; }
+    r *= (int64_t)(pe.prime - 1) * mp;
+  }
+  return cnt;
+}
+
+// supported (pA, pB) combinations; 1 = no second axis
+bool combo_ok(int cnt, const int (&p)[4])
+{
+  if (cnt == 1) return p[0] == 3 || p[0] == 5 || p[0] == 7;
+  if (cnt == 2) return p[0] == 3 && (p[1] == 5 || p[1] == 7);
+  return false;
+}
+
+bool make_geom(const lolb_plan* pl, int fold_k, PlainGeom* G, int (&p)[4], int (&ppi)[4], int64_t (&mprime)[4], int* cnt_out)
+{
+  int64_t r[4];
+  const int cnt = odd_axes(pl, p, r, ppi, mprime);
+  *cnt_out = cnt;
+  if (!combo_ok(cnt, p)) return false;
+  const int64_t n = (int64_t)pl->n * fold_k;
+  G->n = (int32_t)n;
+  G->RA = (int32_t)(r[0] * fold_k);
+  if (cnt == 1) {
+    G->RB = (int32_t)n;
+    G->M = (int32_t)(n / ((int64_t)G->RA * (p[0] - 1)));
+    G->tiles = (int32_t)(n / (p[0] - 1));
+  } else {
+    G->RB = (int32_t)(r[1] * fold_k);
+    G->M = (int32_t)((int64_t)G->RB / ((int64_t)G->RA * (p[0] - 1)));
+    G->tiles = (int32_t)(n / ((p[0] - 1) * (p[1] - 1)));
+  }
+  return true;
+}
+
+dim3 tile_grid(const lolb_plan* pl, const PlainGeom& G, int64_t batch, int* threads_out)
+{
+  int threads = G.tiles >= 256 ? 256 : ((G.tiles + 31) / 32) * 32;
+  for (int c = 256; c >= 128; c -= 32) if (G.tiles % c == 0) { threads = c; break; }
+  dim3 grid((G.tiles + threads - 1) / threads, 1, 1);
+  int64_t gy = ((int64_t)pl->num_sms * 2048 / threads + grid.x - 1) / grid.x * 2;
+  if (gy > batch) gy = batch;
+  if (gy > 65535) gy = 65535;
+  grid.y = (unsigned)gy;
+  *threads_out = threads;
+  return grid;
+}
+
+int launched(const char* what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  count_launch();
+  return LOLB_OK;
+}
+
+template <class R, int PA, int PB>
+int line_kind(const lolb_plan* pl, int kind, const PlainGeom& G, typename R::IO* y, int64_t batch, double rscale, cudaStream_t st)
+{
+  int threads;
+  const dim3 grid = tile_grid(pl, G, batch, &threads);
+  switch (kind) {
+    case PASS_L: k_line_plain<R, PASS_L, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, rscale); break;
+    case PASS_LINV: k_line_plain<R, PASS_LINV, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, rscale); break;
+    case PASS_GPOW: k_line_plain<R, PASS_GPOW, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, rscale); break;
+    case PASS_GDEC: k_line_plain<R, PASS_GDEC, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, rscale); break;
+    case PASS_GINVPOW: k_line_plain<R, PASS_GINVPOW, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, rscale); break;
+    case PASS_GINVDEC: k_line_plain<R, PASS_GINVDEC, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, rscale); break;
+    default: return LOLB_FUSED_UNAVAILABLE;
+  }
+  return launched("k_line_plain");
+}
+
+template <class R>
+int line_combo(const lolb_plan* pl, int kind, const PlainGeom& G, int cnt, const int (&p)[4], typename R::IO* y, int64_t batch, double rscale, cudaStream_t st)
+{
+  if (cnt == 1) {
+    if (p[0] == 3) return line_kind<R, 3, 1>(pl, kind, G, y, batch, rscale, st);
+    if (p[0] == 5) return line_kind<R, 5, 1>(pl, kind, G, y, batch, rscale, st);
+    return line_kind<R, 7, 1>(pl, kind, G, y, batch, rscale, st);
+  }
+  if (p[1] == 5) return line_kind<R, 3, 5>(pl, kind, G, y, batch, rscale, st);
+  return line_kind<R, 3, 7>(pl, kind, G, y, batch, rscale, st);
+}
+
+}  // namespace
+
+// ring: RING_I64 / RING_F64 / RING_C64.  GInv on int64 needs the per-element divisibility verdict: generic engine.
+int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t batch, double rscale, cudaStream_t st)
+{
+  if (batch <= 0) return LOLB_OK;
+  PlainGeom G{};
+  int p[4], ppi[4], cnt; int64_t mp[4];
+  if (!make_geom(pl, pl->k, &G, p, ppi, mp, &cnt)) {
+    if (cnt == 0 && !(ring == RING_C64 && rscale != 0.0 && rscale != 1.0)) return LOLB_OK;     // identity for p = 2
+    return LOLB_FUSED_UNAVAILABLE;
+  }
+  if (ring == RING_I64) {
+    if (kind == PASS_GINVPOW || kind == PASS_GINVDEC) return LOLB_FUSED_UNAVAILABLE;
+    return line_combo<I64Ring>(pl, kind, G, cnt, p, (int64_t*)y, batch, 0.0, st);
+  }
+  if (ring == RING_F64) return line_combo<F64Ring>(pl, kind, G, cnt, p, (double*)y, batch, 0.0, st);
+  return line_combo<C64Ring>(pl, kind, G, cnt, p, (double2*)y, batch, rscale, st);
+}
+
+int fused_plain_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st)
+{
+  if (batch <= 0) return LOLB_OK;
+  if (pl->k != 1) return LOLB_FUSED_UNAVAILABLE;
+  PlainGeom G{};
+  int p[4], ppi[4], cnt; int64_t mp[4];
+  if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) return cnt == 0 ? LOLB_OK : LOLB_FUSED_UNAVAILABLE;
+  // E_p[row][col-1] = Re or Im of ru[(row*col mod p) * p^(e-1)]  (random.cpp:33-40)
+  GaussMats E{};
+  for (int ax = 0; ax < cnt; ax++) {
+    const int P = p[ax];
+    double (*M)[6] = ax == 0 ? E.a : E.b;
+    const std::vector<lolb_complex>& T = pl->cru[ppi[ax]];
+    for (int row = 0; row < P - 1; row++)
+      for (int col = 1; col <= P - 1; col++) {
+        const lolb_complex w = T[(size_t)(((int64_t)row * col) % P) * mp[ax]];
+        M[row][col - 1] = col <= (P >> 1) ? w.real : w.imag;
+      }
+  }
+  int threads;
+  const dim3 grid = tile_grid(pl, G, batch, &threads);
+  if (cnt == 1) {
+    if (p[0] == 3) k_gauss_stream<3, 1><<<grid, threads, 0, st>>>(y, batch, G, E);
+    else if (p[0] == 5) k_gauss_stream<5, 1><<<grid, threads, 0, st>>>(y, batch, G, E);
+    else k_gauss_stream<7, 1><<<grid, threads, 0, st>>>(y, batch, G, E);
+  } else if (p[1] == 5) k_gauss_stream<3, 5><<<grid, threads, 0, st>>>(y, batch, G, E);
+  else k_gauss_stream<3, 7><<<grid, threads, 0, st>>>(y, batch, G, E);
+  return launched("k_gauss_stream");
+}
+
+template <class R>
+static int normsq_combo(const lolb_plan* pl, const typename R::IO* y, typename R::IO* out, int64_t batch, cudaStream_t st)
+{
+  if (batch <= 0) return LOLB_OK;
+  if (pl->k != 1) return LOLB_FUSED_UNAVAILABLE;
+  PlainGeom G{};
+  int p[4], ppi[4], cnt; int64_t mp[4];
+  if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) return LOLB_FUSED_UNAVAILABLE;
+  int threads = G.tiles >= 512 ? 512 : ((G.tiles + 31) / 32) * 32;
+  for (int c = 512; c >= 128; c -= 32) if (G.tiles % c == 0) { threads = c; break; }
+  int64_t grid = (int64_t)pl->num_sms * (2048 / threads);
+  if (grid > batch) grid = batch;
+  if (cnt == 1) {
+    if (p[0] == 3) k_normsq_stream<R, 3, 1><<<(int)grid, threads, 0, st>>>(y, out, batch, G);
+    else if (p[0] == 5) k_normsq_stream<R, 5, 1><<<(int)grid, threads, 0, st>>>(y, out, batch, G);
+    else k_normsq_stream<R, 7, 1><<<(int)grid, threads, 0, st>>>(y, out, batch, G);
+  } else if (p[1] == 5) k_normsq_stream<R, 3, 5><<<(int)grid, threads, 0, st>>>(y, out, batch, G);
+  else k_normsq_stream<R, 3, 7><<<(int)grid, threads, 0, st>>>(y, out, batch, G);
+  return launched("k_normsq_stream");
+}
+
+int fused_plain_normsq_i64(const lolb_plan* pl, const int64_t* y, int64_t* out, int64_t batch, cudaStream_t st)
+{ return normsq_combo<I64Ring>(pl, y, out, batch, st); }
+int fused_plain_normsq_f64(const lolb_plan* pl, const double* y, double* out, int64_t batch, cudaStream_t st)
+{ return normsq_combo<F64Ring>(pl, y, out, batch, st); }
+
+}  // namespace lolb

@@ -287,6 +287,49 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
     assert (tr.gSqNormDec(smp) > 0).all()
 
 
+@pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89], ids=str)
+def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
+    """The streaming kernels of the modulus-free rings (one or two small odd primes) against the generic pass
+    engine on the same batch: bit-identical for int64, <= 1e-12 for double / complex (same operation order)."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
+    B = 9
+    rng = np.random.default_rng(m)
+    ti, tr, tc = CudaTensorInt(m), CudaTensorReal(m), CudaTensorComplex(m)
+    n = ti.n
+    z = torch.from_numpy(rng.integers(-(2 ** 62), 2 ** 62, size=(B, n, 1)).astype(np.int64)).cuda()
+    d = torch.from_numpy(rng.normal(size=(B, n, 1))).cuda()
+    c = torch.from_numpy(rng.normal(size=(B, n, 1)) + 1j * rng.normal(size=(B, n, 1))).cuda()
+
+    def both(t, fn):
+        t.plan.force_generic(False)
+        a = fn()
+        t.plan.force_generic(True)
+        b = fn()
+        t.plan.force_generic(False)
+        return a, b
+
+    for meth in ("l", "lInv", "mulGPow", "mulGDec"):
+        a, b = both(ti, lambda: getattr(ti, meth)(z))
+        assert torch.equal(a, b), meth
+        a, b = both(tc, lambda: getattr(tc, meth)(c))
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-12, meth
+    for meth in ("divGPow", "divGDec"):
+        a, b = both(tc, lambda: getattr(tc, meth)(c))
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-12, meth
+    for meth in ("l", "lInv", "gaussianDecTransform"):
+        a, b = both(tr, lambda: getattr(tr, meth)(d))
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-12, meth
+    a, b = both(ti, lambda: ti.gSqNormDec(z))
+    assert torch.equal(a, b)
+    a, b = both(tr, lambda: tr.gSqNormDec(d))
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-12
+    # and against the oracle for one element
+    pe = T.pe_array(m)
+    assert oracle.tensorNormSqR(z[2].cpu().numpy(), pe).flat[0] == int(ti.gSqNormDec(z)[2, 0])
+    assert rel_err(tr.gaussianDecTransform(d)[1].cpu().numpy(), oracle.tensorGaussianDec(d[1].cpu().numpy(), pe, T.ru_tables_c(m))) <= FLOAT_TOL
+
+
 def test_host_pipeline_matches_device_path(torch_cuda, oracle):
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorRq
