@@ -8,6 +8,8 @@
 // digit, so each warp instruction touches contiguous memory), applies axis A then axis B exactly over the
 // integers in int64 (|entries| <= p, <= p terms: no overflow for q < 2^32), reduces once per axis modulo q,
 // and stores.  Algorithmic traffic: 16 bytes per coefficient, one read and one write.
+#include <type_traits>
+
 #include "fused.cuh"
 
 namespace lolb {
@@ -23,8 +25,8 @@ __device__ __forceinline__ uint32_t barrett64(uint64_t x, uint32_t q, uint64_t m
 }
 
 // exact integer form of the prime-index operators on one line v[0..D), D = P-1
-template <int KIND, int P>
-__device__ __forceinline__ void line_op(int64_t (&v)[P - 1])
+template <int KIND, int P, typename I>
+__device__ __forceinline__ void line_op(I (&v)[P - 1])
 {
   constexpr int D = P - 1;
   if (KIND == PASS_L) {                                   // l.cpp:28-57
@@ -34,32 +36,32 @@ __device__ __forceinline__ void line_op(int64_t (&v)[P - 1])
 #pragma unroll
     for (int a = D - 1; a >= 1; a--) v[a] -= v[a - 1];
   } else if (KIND == PASS_GPOW) {                         // g.cpp:16-35
-    const int64_t last = v[D - 1];
+    const I last = v[D - 1];
 #pragma unroll
     for (int a = D - 1; a >= 1; a--) v[a] += last - v[a - 1];
     v[0] += last;
   } else if (KIND == PASS_GDEC) {                         // g.cpp:37-58
-    int64_t acc = v[0];
+    I acc = v[0];
 #pragma unroll
     for (int a = D - 1; a >= 1; a--) { acc += v[a]; v[a] -= v[a - 1]; }
     v[0] += acc;
   } else if (KIND == PASS_GINVPOW) {                      // g.cpp:60-90
-    int64_t lo = 0, hi = 0;
+    I lo = 0, hi = 0;
 #pragma unroll
     for (int a = 0; a < D; a++) lo += v[a];
 #pragma unroll
     for (int a = D - 1; a >= 0; a--) {
-      const int64_t z = v[a];
-      v[a] = (int64_t)(P - 1 - a) * lo - (int64_t)(a + 1) * hi;
+      const I z = v[a];
+      v[a] = (I)(P - 1 - a) * lo - (I)(a + 1) * hi;
       lo -= z; hi += z;
     }
   } else if (KIND == PASS_GINVDEC) {                      // g.cpp:92-123
-    int64_t s = 0;
+    I s = 0;
 #pragma unroll
-    for (int a = 0; a < D; a++) s += (int64_t)(a + 1) * v[a];
-    int64_t acc = s;
+    for (int a = 0; a < D; a++) s += (I)(a + 1) * v[a];
+    I acc = s;
 #pragma unroll
-    for (int a = D - 1; a >= 1; a--) { const int64_t keep = acc; acc -= v[a] * (int64_t)P; v[a] = keep; }
+    for (int a = D - 1; a >= 1; a--) { const I keep = acc; acc -= v[a] * (I)P; v[a] = keep; }
     v[0] = acc;
   }
 }
@@ -71,7 +73,19 @@ struct LineGeom {
   int32_t tiles;         // n / (dA * dB)
 };
 
-template <int KIND, int PA, int PB>
+__device__ __forceinline__ uint32_t barrett32(uint32_t x, uint32_t q, uint32_t mu32)
+{
+  uint32_t r = x - __umulhi(x, mu32) * q;       // [0, 2q)
+  return min(r, r - q);
+}
+
+__device__ __forceinline__ int32_t reduce_biased(int32_t x, int64_t bias, uint32_t q, uint64_t mu)
+{ return (int32_t)barrett32((uint32_t)x + (uint32_t)bias, q, (uint32_t)(mu >> 32)); }
+__device__ __forceinline__ int64_t reduce_biased(int64_t x, int64_t bias, uint32_t q, uint64_t mu)
+{ return (int64_t)barrett64((uint64_t)(x + bias), q, mu); }
+
+// NARROW: P*P*q < 2^31 on both axes, so the exact integer intermediates fit int32 and one 32-bit Barrett step reduces
+template <int KIND, int PA, int PB, bool NARROW>
 __global__ void __launch_bounds__(256)
 k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ LineGeom G, const __grid_constant__ ZqConsts Z, int scale)
 {
@@ -92,52 +106,60 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
   const int64_t biasA = (int64_t)q * (PA * PA), biasB = (int64_t)q * (PB * PB);
   const size_t off = ((size_t)lo + (size_t)G.RA * DA * mid + (size_t)G.RB * DB * hi) * k + limb;
   const size_t sa = (size_t)G.RA * k, sb = (size_t)G.RB * k;
+  typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
   for (int64_t e = blockIdx.y; e < batch; e += gridDim.y) {
     int64_t* base = y + (size_t)e * G.n * k + off;
-    int64_t v[DB][DA];
+    int64_t raw[DB][DA];
 #pragma unroll
     for (int b = 0; b < DB; b++)
 #pragma unroll
-      for (int a = 0; a < DA; a++) v[b][a] = __ldcs(base + sa * a + sb * b);
+      for (int a = 0; a < DA; a++) raw[b][a] = __ldcs(base + sa * a + sb * b);
     // canonical input is the contract; anything else is reduced first like `c % q` (types.h:62-66)
     bool odd_input = false;
 #pragma unroll
     for (int b = 0; b < DB; b++)
 #pragma unroll
-      for (int a = 0; a < DA; a++) odd_input |= (uint64_t)v[b][a] >= (uint64_t)q;
+      for (int a = 0; a < DA; a++) odd_input |= (uint64_t)raw[b][a] >= (uint64_t)q;
     if (odd_input) {
 #pragma unroll
       for (int b = 0; b < DB; b++)
 #pragma unroll
-        for (int a = 0; a < DA; a++) { int64_t r = v[b][a] % (int64_t)q; v[b][a] = r < 0 ? r + q : r; }
+        for (int a = 0; a < DA; a++) { int64_t r = raw[b][a] % (int64_t)q; raw[b][a] = r < 0 ? r + q : r; }
     }
+    I v[DB][DA];
+#pragma unroll
+    for (int b = 0; b < DB; b++)
+#pragma unroll
+      for (int a = 0; a < DA; a++) v[b][a] = (I)raw[b][a];
 #pragma unroll
     for (int b = 0; b < DB; b++) {
-      line_op<KIND, PA>(v[b]);
+      line_op<KIND, PA, I>(v[b]);
 #pragma unroll
-      for (int a = 0; a < DA; a++) v[b][a] = barrett64((uint64_t)(v[b][a] + biasA), q, mu);
+      for (int a = 0; a < DA; a++)
+        v[b][a] = reduce_biased(v[b][a], biasA, q, mu);
     }
     if constexpr (PB > 1) {
 #pragma unroll
       for (int a = 0; a < DA; a++) {
-        int64_t w[DB];
+        I w[DB];
 #pragma unroll
         for (int b = 0; b < DB; b++) w[b] = v[b][a];
-        line_op<KIND, PB>(w);
+        line_op<KIND, PB, I>(w);
 #pragma unroll
-        for (int b = 0; b < DB; b++) v[b][a] = barrett64((uint64_t)(w[b] + biasB), q, mu);
+        for (int b = 0; b < DB; b++)
+          v[b][a] = reduce_biased(w[b], biasB, q, mu);
       }
     }
     if (scale) {
 #pragma unroll
       for (int b = 0; b < DB; b++)
 #pragma unroll
-        for (int a = 0; a < DA; a++) v[b][a] = barrett64((uint64_t)v[b][a] * s, q, mu);
+        for (int a = 0; a < DA; a++) v[b][a] = (I)barrett64((uint64_t)(uint32_t)v[b][a] * s, q, mu);
     }
 #pragma unroll
     for (int b = 0; b < DB; b++)
 #pragma unroll
-      for (int a = 0; a < DA; a++) __stcs(base + sa * a + sb * b, v[b][a]);
+      for (int a = 0; a < DA; a++) __stcs(base + sa * a + sb * b, (int64_t)(uint32_t)v[b][a]);
   }
 }
 
@@ -161,8 +183,8 @@ k_mul_stream(longlong2* __restrict__ a, const longlong2* __restrict__ b, int64_t
   }
 }
 
-template <int KIND, int PA, int PB>
-int launch_line(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+template <int KIND, int PA, int PB, bool NARROW>
+int launch_line_n(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
 {
   const int per_elem = G.tiles * G.k;
   int threads = per_elem >= 256 ? 256 : ((per_elem + 31) / 32) * 32;
@@ -172,11 +194,21 @@ int launch_line(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bool
   if (gy > batch) gy = batch;
   if (gy > 65535) gy = 65535;
   grid.y = (unsigned)gy;
-  k_line_stream<KIND, PA, PB><<<grid, threads, 0, st>>>(y, batch, G, zc, scale ? 1 : 0);
+  k_line_stream<KIND, PA, PB, NARROW><<<grid, threads, 0, st>>>(y, batch, G, zc, scale ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_line_stream");
   count_launch();
   return LOLB_OK;
+}
+
+template <int KIND, int PA, int PB>
+int launch_line(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  constexpr int64_t PM = (PA > PB ? PA : PB);
+  bool narrow = true;
+  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * PM * PM < ((int64_t)1 << 31);
+  return narrow ? launch_line_n<KIND, PA, PB, true>(pl, G, zc, scale, y, batch, st)
+                : launch_line_n<KIND, PA, PB, false>(pl, G, zc, scale, y, batch, st);
 }
 
 template <int PA, int PB>
