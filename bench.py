@@ -288,6 +288,47 @@ def run_gpu_arm(args):
             per_op[name] = {"ms": ms, "elems_per_s": B / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak, "kernel": t.plan.kernel_name(name)}
         del y2
 
+    # ---- the other BASELINE.json configurations, device-resident (informational; parity for each is in tests/)
+    other = {}
+    if not args.no_per_op and world == 1:
+        def timed(fn, iters=5):
+            fn(); fn()
+            return time_op(torch, fn, iters)
+
+        def rq_config(m, qs, Bc, label):
+            tc = CudaTensorRq(m, qs)
+            kc = len(qs)
+            xc = torch.cat([torch.randint(0, q, (Bc, tc.n, 1), dtype=torch.int64, device="cuda", generator=gen) for q in qs], dim=2).contiguous()
+            res = {"m": m, "qs": qs, "batch": Bc, "bytes_per_elem_per_transform": 16 * tc.n * kc}
+            for name in ("CRT", "CRTInv"):
+                ms = timed(lambda: capi.check(tc.plan.op(name, xc.data_ptr(), Bc, stream)))
+                gbs = 16 * tc.n * kc * Bc / (ms * 1e-3) / 1e9
+                res[name] = {"ms": ms, "elems_per_s": Bc / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak, "kernel": tc.plan.kernel_name(name)}
+            xb = xc.clone()
+            ms = timed(lambda: capi.check(tc.plan.mul(xc.data_ptr(), xb.data_ptr(), Bc, Bc, stream)))
+            gbs = 24 * tc.n * kc * Bc / (ms * 1e-3) / 1e9
+            res["mulRq"] = {"ms": ms, "elems_per_s": Bc / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak, "kernel": tc.plan.kernel_name("mulRq")}
+            other[label] = res
+
+        del x
+        torch.cuda.empty_cache()
+        rq_config(65536, [537133057, 537591809, 537722881, 538116097], 1024, "configs[2]: m=2^16, four ~30-bit primes")
+        rq_config(14400, [1008001, 1065601], 32768, "configs[3] moduli: m=14400, q=(1008001,1065601) (SymmSHE key-switch modulus)")
+        from lol_b200.tensor import CudaTensorInt, CudaTensorReal
+        Bg = 32768
+        tr, ti = CudaTensorReal(M), CudaTensorInt(M)
+        dg = torch.randn(Bg, tr.n, 1, dtype=torch.float64, device="cuda", generator=gen)
+        zg = torch.randint(-8, 9, (Bg, tr.n, 1), dtype=torch.int64, device="cuda", generator=gen)
+        og = torch.empty(Bg, 1, dtype=torch.int64, device="cuda")
+        res = {"m": M, "batch": Bg}
+        ms = timed(lambda: capi.check(tr.plan.op("GaussianDec", dg.data_ptr(), Bg, stream)))
+        res["tensorGaussianDec"] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 16 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak}
+        ms = timed(lambda: capi.check(ti.plan.normsq("R", zg.data_ptr(), og.data_ptr(), Bg, stream)))
+        res["tensorNormSqR"] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 8 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak}
+        other["configs[4]: m=14400 tensorGaussianDec + tensorNormSqR (double / int64)"] = res
+        del dg, zg
+        x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
     if not args.no_e2e and world == 1:
@@ -321,7 +362,7 @@ def run_gpu_arm(args):
                    "batch_per_gpu": B, "l2": "inputs (1.9 GB per GPU) larger than the 126 MB L2; no flush needed",
                    "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
         "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clk.summary(), "per_op": per_op,
+        "clocks": clk.summary(), "per_op": per_op, "other_configs": other,
     }
     print(json.dumps(line))
     if world > 1:

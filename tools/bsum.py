@@ -9,3 +9,7 @@ if d.get("cpu_baseline"): print("  cpu %.1f (%d cores, %s)" % (d["cpu_baseline"]
 print("  clocks", d.get("clocks"), "launches", d.get("gpu_launches"))
 for k, v in (d.get("per_op") or {}).items():
     print("  %-8s %.3f ms  frac %.3f  [%s]" % (k, v["ms"], v["frac"], v["kernel"]))
+for label, res in (d.get("other_configs") or {}).items():
+    print("  ==", label)
+    for k, v in res.items():
+        if isinstance(v, dict): print("     %-18s %.3f ms  %.3gM elems/s  frac %.3f  %s" % (k, v["ms"], v["elems_per_s"] / 1e6, v["frac"], v.get("kernel", "")))
