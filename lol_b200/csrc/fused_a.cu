@@ -308,6 +308,112 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
   }
 }
 
+// tupSize = 2 (e.g. the SymmSHE key-switch modulus q = 1008001 * 1065601): both RNS limbs of a coefficient are one
+// 16-byte unit in the ABI layout, so a thread loads and stores them together (128-bit accesses, every sector fully
+// used) and runs the two limbs as independent instruction streams with their own constants.
+struct FusedAConsts2 { FusedAConsts c[2]; };
+
+template <bool INV, class AR, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts2 CC)
+{
+  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN]
+  const AR A0(CC.c[0]), A1(CC.c[1]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t ltw[2][7];
+#pragma unroll
+  for (int l = 0; l < 2; l++)
+#pragma unroll
+    for (int i = 0; i < 7; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
+
+  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
+    longlong2* ebase = reinterpret_cast<longlong2*>(y + (size_t)e * kN * 2);
+    // ---------------- phase 1: 5^2 axis, both limbs of column (i2, lane)
+    for (int i2 = warp; i2 < kD2; i2 += WARPS) {
+      const int col = i2 * 32 + lane;
+      const longlong2* src = ebase + col;
+      uint32_t v0[20], v1[20];
+      uint32_t hi_or = 0, max0 = 0, max1 = 0;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {         // two batches of ten 128-bit loads bound the registers in flight
+        longlong2 raw[10];
+#pragma unroll
+        for (int a = 0; a < 10; a++) raw[a] = __ldcs(src + (half * 10 + a) * 192);
+#pragma unroll
+        for (int a = 0; a < 10; a++) {
+          v0[half * 10 + a] = (uint32_t)raw[a].x;
+          v1[half * 10 + a] = (uint32_t)raw[a].y;
+          hi_or |= (uint32_t)((uint64_t)raw[a].x >> 32) | (uint32_t)((uint64_t)raw[a].y >> 32);
+          max0 = max(max0, (uint32_t)raw[a].x);
+          max1 = max(max1, (uint32_t)raw[a].y);
+        }
+      }
+      if (hi_or != 0 || max0 >= CC.c[0].q || max1 >= CC.c[1].q) {
+#pragma unroll 1
+        for (int a = 0; a < 20; a++) {
+          const longlong2 raw = src[a * 192];
+          v0[a] = reduce_any(raw.x, CC.c[0].q);
+          v1[a] = reduce_any(raw.y, CC.c[1].q);
+        }
+      }
+      axis5<INV, AR>(v0, CC.c[0], A0);
+#pragma unroll
+      for (int a = 0; a < 20; a++) sm_dyn[a * 192 + col] = v0[a];
+      axis5<INV, AR>(v1, CC.c[1], A1);
+#pragma unroll
+      for (int a = 0; a < 20; a++) sm_dyn[kN + a * 192 + col] = v1[a];
+    }
+    __syncthreads();
+    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp, both limbs of row block i3
+    for (int i3 = warp; i3 < kD3; i3 += WARPS) {
+      uint32_t x[2][6], c0[2][3], c1[2][3];
+#pragma unroll
+      for (int l = 0; l < 2; l++)
+#pragma unroll
+        for (int i2 = 0; i2 < 6; i2++) x[l][i2] = sm_dyn[l * kN + i3 * 192 + i2 * 32 + lane];
+      axis3<INV, AR>(x[0], CC.c[0], A0);
+      axis3<INV, AR>(x[1], CC.c[1], A1);
+      if (!INV) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          c0[0][j] = A0.red(A0.mul(ltw[0][0], x[0][2 * j]));     c1[0][j] = A0.red(A0.mul(ltw[0][0], x[0][2 * j + 1]));
+          c0[1][j] = A1.red(A1.mul(ltw[1][0], x[1][2 * j]));     c1[1][j] = A1.red(A1.mul(ltw[1][0], x[1][2 * j + 1]));
+        }
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          exchange_round<false, AR>(c0[0], c1[0], lane, r, ltw[0][1 + r], A0);
+          exchange_round<false, AR>(c0[1], c1[1], lane, r, ltw[1][1 + r], A1);
+        }
+        longlong2* out = ebase + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          __stcs(out + j * 64, make_longlong2((int64_t)A0.canon(c0[0][j]), (int64_t)A1.canon(c0[1][j])));
+          __stcs(out + j * 64 + 16, make_longlong2((int64_t)A0.canon(c1[0][j]), (int64_t)A1.canon(c1[1][j])));
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < 2; l++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) { c0[l][j] = x[l][2 * j]; c1[l][j] = x[l][2 * j + 1]; }
+#pragma unroll
+        for (int r = 4; r >= 0; r--) {
+          exchange_round<true, AR>(c0[0], c1[0], lane, r, ltw[0][r], A0);
+          exchange_round<true, AR>(c0[1], c1[1], lane, r, ltw[1][r], A1);
+        }
+        longlong2* out = ebase + i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          __stcs(out + j * 64, make_longlong2((int64_t)A0.canon(A0.red(A0.mul(ltw[0][5], c0[0][j]))),
+                                              (int64_t)A1.canon(A1.red(A1.mul(ltw[1][5], c0[1][j])))));
+          __stcs(out + j * 64 + 1, make_longlong2((int64_t)A0.canon(A0.red(A0.mul(ltw[0][6], c1[0][j]))),
+                                                  (int64_t)A1.canon(A1.red(A1.mul(ltw[1][6], c1[1][j])))));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ host: constants from the plan's root tables
 
 enum ArithClass { ARITH_NONE = 0, ARITH_S, ARITH_M };
@@ -494,6 +600,26 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
   if (g_variant < 0) { const char* v = getenv("LOLB_FUSED_A_VARIANT"); g_variant = v ? atoi(v) : 2; }
+  if (pl->k == 2 && F->cls[0] == F->cls[1] && !getenv("LOLB_FUSED_A_PER_LIMB")) {
+    FusedAConsts2 CC;
+    CC.c[0] = inverse ? F->inv[0] : F->fwd[0];
+    CC.c[1] = inverse ? F->inv[1] : F->fwd[1];
+    constexpr int W = 3, MB = 5;
+    const size_t smem = 2 * kN * sizeof(uint32_t);
+    int64_t grid = (int64_t)pl->num_sms * MB;
+    if (grid > batch) grid = batch;
+    if (F->cls[0] == ARITH_M) {
+      if (inverse) k_fused_a_k2<true, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
+      else k_fused_a_k2<false, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
+    } else {
+      if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
+      else k_fused_a_k2<false, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_k2");
+    count_launch();
+    return LOLB_OK;
+  }
   for (int t = 0; t < pl->k; t++) {
     const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];
     int rc;
