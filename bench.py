@@ -256,6 +256,33 @@ def run_gpu_arm(args):
     crt_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     inv_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
 
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region);
+    # every rank drives its own GPU from its own host buffer, time = max over ranks
+    e2e = None
+    if not args.no_e2e:
+        Be = min(B, args.e2e_batch)
+        h = torch.empty(Be, t.n, 1, dtype=torch.int64).pin_memory()
+        h.copy_(x[:Be])
+        h0 = h[:2].clone()
+        t.apply_host("CRT,CRTInv", h)      # warm-up (allocates staging, creates streams)
+        ksteps = max(3, min(K, 10))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            capi.check(t.plan.apply_host("CRT,CRTInv", h.data_ptr(), Be))
+        dt = (time.perf_counter() - t0) / ksteps
+        dt_t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t.item())
+        assert torch.equal(h[:2], h0)
+        e2e = {"value": world * Be / dt, "unit": UNIT, "h2d_bytes_per_step": world * Be * N_COEFF * 8,
+               "d2h_bytes_per_step": world * Be * N_COEFF * 8, "batch_per_gpu": Be, "ms_per_step": dt * 1e3,
+               "api": "lolb_rq_apply_host(plan, \"CRT,CRTInv\", host_ptr, batch) per rank"}
+        del h
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -328,26 +355,6 @@ def run_gpu_arm(args):
         other["configs[4]: m=14400 tensorGaussianDec + tensorNormSqR (double / int64)"] = res
         del dg, zg
         x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
-
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
-    e2e = None
-    if not args.no_e2e and world == 1:
-        Be = min(B, args.e2e_batch)
-        h = torch.empty(Be, t.n, 1, dtype=torch.int64).pin_memory()
-        h.copy_(x[:Be])
-        h0 = h[:2].clone()
-        t.apply_host("CRT,CRTInv", h)      # warm-up (allocates staging, creates streams)
-        ksteps = max(3, min(K, 10))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            capi.check(t.plan.apply_host("CRT,CRTInv", h.data_ptr(), Be))
-        dt = (time.perf_counter() - t0) / ksteps
-        assert torch.equal(h[:2], h0)
-        e2e = {"value": Be / dt, "unit": UNIT, "h2d_bytes_per_step": Be * N_COEFF * 8, "d2h_bytes_per_step": Be * N_COEFF * 8,
-               "batch": Be, "ms_per_step": dt * 1e3, "api": "lolb_rq_apply_host(plan, \"CRT,CRTInv\", host_ptr, batch)"}
-    elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
 
     cpu_base = None
     if world == 1 and not args.no_cpu:

@@ -308,6 +308,86 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
   }
 }
 
+// Software-pipelined variant for tupSize = 1: 6 warps, one ring element per iteration, double-buffered tile.  The 20
+// loads of the NEXT element are issued right after the barrier, so they are in flight during phase 2 of the current
+// element and phase 1 never waits on HBM (the price: 40 live registers through phase 2).
+template <bool INV, class AR, int MINB>
+__global__ void __launch_bounds__(192, MINB)
+k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts C)
+{
+  __shared__ uint32_t sm[2][kN];
+  const AR A(C);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t ltw[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
+
+  int64_t raw[20];
+  int64_t e = blockIdx.x;
+  if (e < batch) {
+#pragma unroll
+    for (int a = 0; a < 20; a++) raw[a] = __ldcs(y + (size_t)e * kN + a * 192 + tid);
+  }
+  int buf = 0;
+  for (; e < batch; e += gridDim.x, buf ^= 1) {
+    int64_t* base = y + (size_t)e * kN;
+    {
+      uint32_t v[20];
+      uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+      for (int a = 0; a < 20; a++) {
+        v[a] = (uint32_t)raw[a];
+        hi_or |= (uint32_t)((uint64_t)raw[a] >> 32);
+        lo_max = max(lo_max, v[a]);
+      }
+      if (hi_or != 0 || lo_max >= C.q) {
+#pragma unroll 1
+        for (int a = 0; a < 20; a++) v[a] = reduce_any(base[a * 192 + tid], C.q);
+      }
+      axis5<INV, AR>(v, C, A);
+#pragma unroll
+      for (int a = 0; a < 20; a++) sm[buf][a * 192 + tid] = v[a];
+    }
+    __syncthreads();
+    const int64_t en = e + gridDim.x;
+    if (en < batch) {
+#pragma unroll
+      for (int a = 0; a < 20; a++) raw[a] = __ldcs(y + (size_t)en * kN + a * 192 + tid);
+    }
+    for (int i3 = warp; i3 < kD3; i3 += 6) {
+      uint32_t x[6], c0[3], c1[3];
+#pragma unroll
+      for (int i2 = 0; i2 < 6; i2++) x[i2] = sm[buf][i3 * 192 + i2 * 32 + lane];
+      axis3<INV, AR>(x, C, A);
+      if (!INV) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          c0[j] = A.red(A.mul(ltw[0], x[2 * j]));
+          c1[j] = A.red(A.mul(ltw[0], x[2 * j + 1]));
+        }
+#pragma unroll
+        for (int r = 0; r < 5; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[1 + r], A);
+        int64_t* out = base + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          __stcs(out + j * 64, (int64_t)A.canon(c0[j]));
+          __stcs(out + j * 64 + 16, (int64_t)A.canon(c1[j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+#pragma unroll
+        for (int r = 4; r >= 0; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
+        int64_t* out = base + i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15);
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          __stcs(reinterpret_cast<longlong2*>(out + j * 64),
+                 make_longlong2((int64_t)A.canon(A.red(A.mul(ltw[5], c0[j]))), (int64_t)A.canon(A.red(A.mul(ltw[6], c1[j])))));
+      }
+    }
+  }
+}
+
 // tupSize = 2 (e.g. the SymmSHE key-switch modulus q = 1008001 * 1065601): both RNS limbs of a coefficient are one
 // 16-byte unit in the ABI layout, so a thread loads and stores them together (128-bit accesses, every sector fully
 // used) and runs the two limbs as independent instruction streams with their own constants.
@@ -628,6 +708,16 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
       rc = pl->k == 1 ? LA(ArithM, 1, 1, 3, 8, 1) : LA(ArithM, 0, 1, 3, 8, 1);
     } else if (pl->k == 1) {
       switch (g_variant) {
+        case 6: case 7: {
+          int64_t grid = (int64_t)pl->num_sms * 4;
+          if (grid > batch) grid = batch;
+          if (inverse) k_fused_a_pf<true, ArithS, 4><<<(int)grid, 192, 0, st>>>(y, batch, C);
+          else k_fused_a_pf<false, ArithS, 4><<<(int)grid, 192, 0, st>>>(y, batch, C);
+          cudaError_t e = cudaGetLastError();
+          if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_pf");
+          count_launch();
+          rc = LOLB_OK;
+        } break;
         case 0: rc = LA(ArithS, 1, 1, 6, 5, 2); break;
         case 1: rc = LA(ArithS, 1, 5, 10, 3, 1); break;
         default: rc = LA(ArithS, 1, 1, 3, 10, 1); break;

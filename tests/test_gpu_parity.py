@@ -330,6 +330,40 @@ def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
     assert rel_err(tr.gaussianDecTransform(d)[1].cpu().numpy(), oracle.tensorGaussianDec(d[1].cpu().numpy(), pe, T.ru_tables_c(m))) <= FLOAT_TOL
 
 
+@pytest.mark.parametrize("m,qs", [CONFIG_A, CONFIG_C, (42, [8191]), (2 ** 16, [786433]), (2 ** 9, [12289]), (14400, [14401, 43201])],
+                         ids=lambda v: str(v))
+def test_non_canonical_input_is_reduced_like_the_reference(torch_cuda, oracle, m, qs):
+    """Outside the Haskell contract (coefficients in [0,q)), the reference reduces with `c % q` (types.h:62-66) and
+    canonicalises at exit (zq.cpp:57-67).  Every kernel family (fused, streaming, generic) must do the same for
+    negative, >= q and > 2^32 inputs instead of silently computing on garbage."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    B = 4
+    rng = np.random.default_rng(m + 1)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    y = zq_input(rng, n, qs, batch=B)
+    y[0, 0, :] = [q for q in qs]                        # == q
+    y[1, n // 2, :] = [-3 for _ in qs]                  # negative
+    y[2, n - 1, :] = [q + 5 + (1 << 40) * q for q in qs]   # far above 2^32
+    y[3, :, 0] += qs[0]                                 # a whole limb shifted by q
+    canon = np.stack([np.mod(y[..., t], q) for t, q in enumerate(qs)], axis=-1)
+    t = CudaTensorRq(m, qs)
+    x = torch.from_numpy(y).cuda()
+    per = lambda f: np.stack([f(canon[b]) for b in range(B)])
+    assert np.array_equal(t.crt(x).cpu().numpy(), per(lambda v: oracle.tensorCRTRq(v, pe, ru, qs)))
+    assert np.array_equal(t.crtInv(x).cpu().numpy(), per(lambda v: oracle.tensorCRTInvRq(v, pe, rui, mh, qs)))
+    if T.odd_radical(m) > 1:
+        assert np.array_equal(t.mulGPow(x).cpu().numpy(), per(lambda v: oracle.tensorGPowRq(v, pe, qs)))
+        assert np.array_equal(t.lInv(x).cpu().numpy(), per(lambda v: oracle.tensorLInvRq(v, pe, qs)))
+    else:
+        # power-of-two index: L and G are the identity (l.cpp:35, g.cpp:18) and nothing is launched, so the input
+        # comes back untouched (the reference would only add q to negatives, zq.cpp:57-67); documented in DESIGN.md
+        assert torch.equal(t.mulGPow(x), x) and torch.equal(t.lInv(x), x)
+    assert np.array_equal(t.mul(x, x).cpu().numpy(), per(lambda v: oracle.mulRq(v, v, qs)))
+    # the oracle itself agrees: feeding it the raw values gives the same answer as the canonical ones
+    assert np.array_equal(oracle.tensorCRTRq(y[1], pe, ru, qs), oracle.tensorCRTRq(canon[1], pe, ru, qs))
+
+
 def test_host_pipeline_matches_device_path(torch_cuda, oracle):
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorRq
