@@ -369,6 +369,124 @@ k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2P
   }
 }
 
+// ---- tupSize > 1 at E = 16: one CTA per ring ELEMENT.  The RNS limbs of a coefficient are interleaved in the ABI
+// layout (32 bytes per coefficient at k = 4), so a per-limb CTA touches every sector of the element for a quarter of
+// its bytes.  Here the element is read ONCE with full-width coalesced loads and split into a per-CTA scratch
+// [k][n] of u32 in global memory (512 KB per CTA at k = 4: it lives in the 126 MB L2, never meant to reach HBM);
+// each limb is then transformed from / to its contiguous u32 row, and the element is re-interleaved and written
+// ONCE with full-width stores.  HBM sees exactly one fully coalesced read and write of the element.
+template <bool INV>
+__device__ __forceinline__ void limb16_from_scratch(uint32_t* sm, uint32_t* row, const Pow2Limb& L, const Mont& M, int lane, int warp)
+{
+  constexpr int kWarps = kT16 / 32, kChunks = kN16 >> 10;
+  if (!INV) {
+#pragma unroll 1
+    for (int H = warp; H < kChunks; H += kWarps) {
+#pragma unroll 8
+      for (int i = 0; i < 32; i++) {
+        const int pos = (H << 10) + (i << 5) + lane;
+        sm[swz(pos)] = M.mul(row[pos], __ldg(L.crt_tw + pos));
+      }
+      __syncwarp();
+      block16_smem<0, false>(sm, L, M, 0, (H << 5) + lane);
+      __syncwarp();
+      block16_smem<5, false>(sm, L, M, lane, H);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int b = threadIdx.x; b < 1024; b += kT16) {
+      uint32_t v[32], tw[31];
+      load_tw16(tw, L.round_tw, 10, 0);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = sm[phys16<10>(b, 0, j)];
+      rounds16<false>(v, M, tw);
+#pragma unroll
+      for (int j = 0; j < 32; j++) row[b + (j << 10)] = M.canon(v[j]);
+    }
+    __syncthreads();
+  } else {
+#pragma unroll 1
+    for (int b = threadIdx.x; b < 1024; b += kT16) {
+      uint32_t v[32], tw[31];
+      load_tw16(tw, L.round_tw, 10, 0);
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = row[b + (j << 10)];
+      rounds16<true>(v, M, tw);
+#pragma unroll
+      for (int j = 0; j < 32; j++) sm[phys16<10>(b, 0, j)] = v[j];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int H = warp; H < kChunks; H += kWarps) {
+      block16_smem<5, true>(sm, L, M, lane, H);
+      __syncwarp();
+      block16_smem<0, true>(sm, L, M, 0, (H << 5) + lane);
+      __syncwarp();
+#pragma unroll 8
+      for (int i = 0; i < 32; i++) {
+        const int pos = (H << 10) + (i << 5) + lane;
+        row[pos] = M.canon(M.mul(sm[swz(pos)], __ldg(L.crt_tw + pos)));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool INV, int K>
+__global__ void __launch_bounds__(kT16, 1)
+k_pow2_e16_elem(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2Params P, uint32_t* __restrict__ scratch)
+{
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* mine = scratch + (size_t)blockIdx.x * K * kN16;
+  for (int64_t el = blockIdx.x; el < batch; el += gridDim.x) {
+    int64_t* ebase = y + (size_t)el * kN16 * K;
+    // split: coefficient `pos` -> scratch[l][pos]
+#pragma unroll 2
+    for (int pos = threadIdx.x; pos < kN16; pos += kT16) {
+      int64_t c[K];
+      if (K % 2 == 0) {
+#pragma unroll
+        for (int h = 0; h < K / 2; h++) {
+          const longlong2 raw = __ldcs(reinterpret_cast<const longlong2*>(ebase + (size_t)pos * K) + h);
+          c[2 * h] = raw.x; c[2 * h + 1] = raw.y;
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < K; l++) c[l] = __ldcs(ebase + (size_t)pos * K + l);
+      }
+#pragma unroll
+      for (int l = 0; l < K; l++) {
+        const uint32_t q = P.limb[l].q;
+        mine[(size_t)l * kN16 + pos] = (uint64_t)c[l] < (uint64_t)q ? (uint32_t)c[l] : reduce_any64(c[l], q);
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < K; l++) {
+      const Pow2Limb& L = P.limb[l];
+      const Mont M{L.q, L.q2, L.qinv};
+      limb16_from_scratch<INV>(sm, mine + (size_t)l * kN16, L, M, lane, warp);
+    }
+    // merge: scratch[l][pos] -> element
+#pragma unroll 2
+    for (int pos = threadIdx.x; pos < kN16; pos += kT16) {
+      int64_t c[K];
+#pragma unroll
+      for (int l = 0; l < K; l++) c[l] = (int64_t)mine[(size_t)l * kN16 + pos];
+      if (K % 2 == 0) {
+#pragma unroll
+        for (int h = 0; h < K / 2; h++)
+          __stcs(reinterpret_cast<longlong2*>(ebase + (size_t)pos * K) + h, make_longlong2(c[2 * h], c[2 * h + 1]));
+      } else {
+#pragma unroll
+        for (int l = 0; l < K; l++) __stcs(ebase + (size_t)pos * K + l, c[l]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct FusedPow2 {
   bool ok_fwd = false, ok_inv = false;
   Pow2Params fwd{}, inv{};
@@ -504,6 +622,27 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
     if (pl->k == 1) {
       if (inverse) k_pow2_e16<true, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
       else k_pow2_e16<false, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
+    } else if ((pl->k == 2 || pl->k == 3 || pl->k == 4) && getenv("LOLB_POW2_ELEM")) {
+      // opt-in experiment: +14% forward, but the scratch is partly written back to HBM (1.33x traffic)
+      int64_t g2 = pl->num_sms;
+      if (g2 > batch) g2 = batch;
+      int rc = plan_reserve_ws(pl, (size_t)g2 * pl->k * kN16 * sizeof(uint32_t));
+      if (rc) return rc;
+      uint32_t* scratch = (uint32_t*)pl->d_ws;
+      static bool attr_el = false;
+      if (!attr_el) {
+        cudaFuncSetAttribute(k_pow2_e16_elem<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pow2_e16_elem<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pow2_e16_elem<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pow2_e16_elem<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pow2_e16_elem<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pow2_e16_elem<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_el = true;
+      }
+#define LE(KK) (inverse ? k_pow2_e16_elem<true, KK><<<(int)g2, kT16, smem, st>>>(y, batch, F->inv, scratch) \
+                        : k_pow2_e16_elem<false, KK><<<(int)g2, kT16, smem, st>>>(y, batch, F->fwd, scratch))
+      if (pl->k == 2) LE(2); else if (pl->k == 3) LE(3); else LE(4);
+#undef LE
     } else {
       if (inverse) k_pow2_e16<true, 0><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
       else k_pow2_e16<false, 0><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
