@@ -34,7 +34,7 @@ struct FusedAConsts {
   uint32_t d5[5][5];        // DFT_5 over the block index (fwd or inverse roots)
   uint32_t m3[3][2][2];
   uint32_t d3[3][3];
-  const uint32_t* lane_tw;  // device [8][32] per-lane twiddles of the 2^6 axis (see build_consts)
+  const uint32_t* lane_tw;  // device [kLaneRows][32] per-lane constants: 2^6-axis twiddles and folded m3 (see build_consts)
 };
 
 // Two arithmetic policies with one interface.  Residues are lazy u32 in [0,2q); `Acc` accumulates a row of a dense
@@ -72,6 +72,7 @@ struct ArithM {
   __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }
 };
 
+constexpr int kLaneRows = 20;      // rows 0-7: 2^6-axis twiddles; rows 8-19: forward m3[i0][r][c] * crtTwiddle_64(lane)
 constexpr int kN = 3840, kD1 = 32, kD2 = 6, kD3 = 20;
 
 // CRT_25 / CRT_25^-1 on the 20 values of one (i1,i2) column, v[4*i0 + c]
@@ -125,15 +126,17 @@ __device__ __forceinline__ void axis5(uint32_t (&v)[20], const FusedAConsts& C, 
 }
 
 // CRT_9 / CRT_9^-1 on the 6 values x[2*i0 + c] of one (i3, i1)
+// Forward: the 2x2 blocks use the PER-LANE constants m3l = m3 * crtTwiddle_64(column = lane): the diagonal twiddle of
+// the 2^6 axis is a scalar per lane, commutes with the 3^2 axis and costs nothing once folded in here.
 template <bool INV, class AR>
-__device__ __forceinline__ void axis3(uint32_t (&x)[6], const FusedAConsts& C, const AR& A)
+__device__ __forceinline__ void axis3(uint32_t (&x)[6], const FusedAConsts& C, const AR& A, const uint32_t (&m3l)[12])
 {
   if (!INV) {
 #pragma unroll
     for (int i0 = 0; i0 < 3; i0++) {
       uint32_t a = x[2 * i0], b = x[2 * i0 + 1];
-      x[2 * i0] = A.red(A.mad(A.mul(C.m3[i0][0][0], a), C.m3[i0][0][1], b));
-      x[2 * i0 + 1] = A.red(A.mad(A.mul(C.m3[i0][1][0], a), C.m3[i0][1][1], b));
+      x[2 * i0] = A.red(A.mad(A.mul(m3l[4 * i0], a), m3l[4 * i0 + 1], b));
+      x[2 * i0 + 1] = A.red(A.mad(A.mul(m3l[4 * i0 + 2], a), m3l[4 * i0 + 3], b));
     }
   }
 #pragma unroll
@@ -198,9 +201,11 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // per-lane twiddles of the 2^6 axis, loaded once
-  uint32_t ltw[7];
+  uint32_t ltw[7], m3l[12];
 #pragma unroll
   for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
+#pragma unroll
+  for (int i = 0; i < 12; i++) m3l[i] = C.lane_tw[(8 + i) * 32 + lane];
 
   int buf = 0;
   const int64_t groups = (batch + EPB - 1) / EPB;
@@ -254,15 +259,12 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
                      : base + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
       }
 #pragma unroll
-      for (int u = 0; u < U; u++) axis3<INV, AR>(x[u], C, A);
+      for (int u = 0; u < U; u++) axis3<INV, AR>(x[u], C, A, m3l);
       if (!INV) {
 #pragma unroll
         for (int u = 0; u < U; u++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) {          // crtTwiddle of 2^6 (crt.cpp:43-58), column = lane
-            c0[u][j] = A.red(A.mul(ltw[0], x[u][2 * j]));
-            c1[u][j] = A.red(A.mul(ltw[0], x[u][2 * j + 1]));
-          }
+          for (int j = 0; j < 3; j++) { c0[u][j] = x[u][2 * j]; c1[u][j] = x[u][2 * j + 1]; }   // crtTwiddle of 2^6 already in m3l
 #pragma unroll
         for (int r = 0; r < 5; r++)
 #pragma unroll
@@ -318,9 +320,11 @@ k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
   __shared__ uint32_t sm[2][kN];
   const AR A(C);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t ltw[7];
+  uint32_t ltw[7], m3l[12];
 #pragma unroll
   for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
+#pragma unroll
+  for (int i = 0; i < 12; i++) m3l[i] = C.lane_tw[(8 + i) * 32 + lane];
 
   int64_t raw[20];
   int64_t e = blockIdx.x;
@@ -358,13 +362,10 @@ k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
       uint32_t x[6], c0[3], c1[3];
 #pragma unroll
       for (int i2 = 0; i2 < 6; i2++) x[i2] = sm[buf][i3 * 192 + i2 * 32 + lane];
-      axis3<INV, AR>(x, C, A);
+      axis3<INV, AR>(x, C, A, m3l);
       if (!INV) {
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          c0[j] = A.red(A.mul(ltw[0], x[2 * j]));
-          c1[j] = A.red(A.mul(ltw[0], x[2 * j + 1]));
-        }
+        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
 #pragma unroll
         for (int r = 0; r < 5; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[1 + r], A);
         int64_t* out = base + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
@@ -400,11 +401,14 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
   extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN]
   const AR A0(CC.c[0]), A1(CC.c[1]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t ltw[2][7];
+  uint32_t ltw[2][7], m3l[2][12];
 #pragma unroll
-  for (int l = 0; l < 2; l++)
+  for (int l = 0; l < 2; l++) {
 #pragma unroll
     for (int i = 0; i < 7; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < 12; i++) m3l[l][i] = CC.c[l].lane_tw[(8 + i) * 32 + lane];
+  }
 
   for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
     longlong2* ebase = reinterpret_cast<longlong2*>(y + (size_t)e * kN * 2);
@@ -451,14 +455,13 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
       for (int l = 0; l < 2; l++)
 #pragma unroll
         for (int i2 = 0; i2 < 6; i2++) x[l][i2] = sm_dyn[l * kN + i3 * 192 + i2 * 32 + lane];
-      axis3<INV, AR>(x[0], CC.c[0], A0);
-      axis3<INV, AR>(x[1], CC.c[1], A1);
+      axis3<INV, AR>(x[0], CC.c[0], A0, m3l[0]);
+      axis3<INV, AR>(x[1], CC.c[1], A1, m3l[1]);
       if (!INV) {
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          c0[0][j] = A0.red(A0.mul(ltw[0][0], x[0][2 * j]));     c1[0][j] = A0.red(A0.mul(ltw[0][0], x[0][2 * j + 1]));
-          c0[1][j] = A1.red(A1.mul(ltw[1][0], x[1][2 * j]));     c1[1][j] = A1.red(A1.mul(ltw[1][0], x[1][2 * j + 1]));
-        }
+        for (int l = 0; l < 2; l++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) { c0[l][j] = x[l][2 * j]; c1[l][j] = x[l][2 * j + 1]; }
 #pragma unroll
         for (int r = 0; r < 5; r++) {
           exchange_round<false, AR>(c0[0], c1[0], lane, r, ltw[0][1 + r], A0);
@@ -510,7 +513,7 @@ struct FusedA {
   bool ok_fwd = false, ok_inv = false;
   std::vector<int> cls;                    // ArithClass per limb
   std::vector<FusedAConsts> fwd, inv;      // per limb
-  uint32_t* d_lane_tw = nullptr;           // [k][2][8][32]
+  uint32_t* d_lane_tw = nullptr;           // [k][2][kLaneRows][32]
 };
 
 inline uint64_t rd(const std::vector<int64_t>& tab, int64_t j, int k, int limb, uint64_t q)
@@ -520,7 +523,7 @@ inline uint64_t rd(const std::vector<int64_t>& tab, int64_t j, int k, int limb, 
   return (uint64_t)v;
 }
 
-void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, uint32_t* lane_tw /* [8][32] */)
+void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, uint32_t* lane_tw /* [kLaneRows][32] */)
 {
   const int k = pl->k;
   const uint64_t q = (uint64_t)pl->qs[limb];
@@ -562,10 +565,15 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
       }
   // 2^6 axis.  Forward rows: [0] crtTwiddle by column = lane; [1+r] round r, i0 = lane >> (r+1).
   // Inverse rows: [r] round r, i0 = (lane >> r) & (2^(4-r) - 1); [5],[6] crtTwiddle of columns 2*(lane&15) + {0,1}.
-  for (int i = 0; i < 8 * 32; i++) lane_tw[i] = 1;
+  for (int i = 0; i < kLaneRows * 32; i++) lane_tw[i] = 1;
   for (int lane = 0; lane < 32; lane++) {
     if (!inverse) {
-      lane_tw[0 * 32 + lane] = lane ? (uint32_t)r64(digit_rev(2, 5, lane)) : 1;
+      const uint64_t tw0 = lane ? r64(digit_rev(2, 5, lane)) : 1;           // crtTwiddle of 2^6 (crt.cpp:43-58), column = lane
+      lane_tw[0 * 32 + lane] = (uint32_t)tw0;
+      for (int i0 = 0; i0 < 3; i0++)
+        for (int r = 0; r < 2; r++)
+          for (int c = 0; c < 2; c++)
+            lane_tw[(8 + 4 * i0 + 2 * r + c) * 32 + lane] = (uint32_t)mulmod64(C->m3[i0][r][c], tw0, q);
       for (int r = 0; r < 5; r++) {
         const int i0 = lane >> (r + 1);
         const uint64_t tw = i0 ? r64(digit_rev(2, 4 - r, i0) * (2 << r)) : 1;
@@ -594,7 +602,7 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
     for (auto& a : C->d5) for (auto& c : a) c = mont(c);
     for (auto& a : C->m3) for (auto& b : a) for (auto& c : b) c = mont(c);
     for (auto& a : C->d3) for (auto& c : a) c = mont(c);
-    for (int i = 0; i < 8 * 32; i++) lane_tw[i] = mont(lane_tw[i]);
+    for (int i = 0; i < kLaneRows * 32; i++) lane_tw[i] = mont(lane_tw[i]);
   }
 }
 
@@ -616,7 +624,7 @@ int fused_a_select(lolb_plan* pl, void** slot)
   if (!shape_is_a(pl)) { return LOLB_OK; }
   if (!F) { F = new FusedA(); *slot = F; }
   const int k = pl->k;
-  std::vector<uint32_t> lt((size_t)k * 2 * 8 * 32, 1u);
+  std::vector<uint32_t> lt((size_t)k * 2 * kLaneRows * 32, 1u);
   F->cls.assign(k, ARITH_NONE);
   for (int t = 0; t < k; t++) F->cls[t] = arith_class((uint64_t)pl->qs[t]);
   F->fwd.assign(k, FusedAConsts{});
@@ -624,15 +632,15 @@ int fused_a_select(lolb_plan* pl, void** slot)
   F->ok_fwd = pl->has_fwd && pl->ru.size() == 3;
   F->ok_inv = pl->has_inv && pl->ruinv.size() == 3 && (int)pl->mhatinv.size() == k;
   for (int t = 0; t < k; t++) {
-    if (F->ok_fwd) build_consts(pl, false, t, &F->fwd[t], lt.data() + ((size_t)t * 2 + 0) * 256);
-    if (F->ok_inv) build_consts(pl, true, t, &F->inv[t], lt.data() + ((size_t)t * 2 + 1) * 256);
+    if (F->ok_fwd) build_consts(pl, false, t, &F->fwd[t], lt.data() + ((size_t)t * 2 + 0) * kLaneRows * 32);
+    if (F->ok_inv) build_consts(pl, true, t, &F->inv[t], lt.data() + ((size_t)t * 2 + 1) * kLaneRows * 32);
   }
   if (F->d_lane_tw) { cudaFree(F->d_lane_tw); F->d_lane_tw = nullptr; }
   LOLB_CUDA(cudaMalloc((void**)&F->d_lane_tw, lt.size() * sizeof(uint32_t)));
   LOLB_CUDA(cudaMemcpy(F->d_lane_tw, lt.data(), lt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   for (int t = 0; t < k; t++) {
-    F->fwd[t].lane_tw = F->d_lane_tw + ((size_t)t * 2 + 0) * 256;
-    F->inv[t].lane_tw = F->d_lane_tw + ((size_t)t * 2 + 1) * 256;
+    F->fwd[t].lane_tw = F->d_lane_tw + ((size_t)t * 2 + 0) * kLaneRows * 32;
+    F->inv[t].lane_tw = F->d_lane_tw + ((size_t)t * 2 + 1) * kLaneRows * 32;
   }
   return LOLB_OK;
 }
