@@ -158,7 +158,9 @@ __device__ __forceinline__ void axis3(uint32_t (&x)[6], const FusedAConsts& C, c
 
 // One radix-2 round of the exchange network on lane bit `bit`.  Before: the lane owns (c0[j], c1[j]) for three
 // rows; after: the two columns of one butterfly.  Forward: (u,t) -> (u+t, (u-t)*tw).  Inverse: (u,t) -> (u+t*tw, u-t*tw).
-template <bool INV, class AR>
+// TRIVIAL: every twiddle of the round is 1 (bit 4: i0 = column >> 5 = 0, crt.cpp:92-106 skips i0 = 0), so the
+// multiplication and its reduction are dropped.
+template <bool INV, class AR, bool TRIVIAL = false>
 __device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)[3], int lane, int bit, uint32_t tw, const AR& A)
 {
   const bool hi = (lane >> bit) & 1;
@@ -167,7 +169,11 @@ __device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)
     const uint32_t send = hi ? c0[j] : c1[j];
     const uint32_t keep = hi ? c1[j] : c0[j];
     const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
-    if (!INV) {
+    if (TRIVIAL) {
+      const uint32_t u = hi ? recv : keep, t = hi ? keep : recv;
+      c0[j] = A.fold(u + t);
+      c1[j] = A.fold(u + A.q2 - t);
+    } else if (!INV) {
       // u + t is symmetric; (u - t) = +-(keep - recv) and the sign lives in the lane's twiddle (host: q - tw for hi lanes)
       c0[j] = A.fold(keep + recv);
       c1[j] = A.red(A.mul(tw, keep + A.q2 - recv));
@@ -266,9 +272,11 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll
           for (int j = 0; j < 3; j++) { c0[u][j] = x[u][2 * j]; c1[u][j] = x[u][2 * j + 1]; }   // crtTwiddle of 2^6 already in m3l
 #pragma unroll
-        for (int r = 0; r < 5; r++)
+        for (int r = 0; r < 4; r++)
 #pragma unroll
           for (int u = 0; u < U; u++) exchange_round<false, AR>(c0[u], c1[u], lane, r, ltw[1 + r], A);
+#pragma unroll
+        for (int u = 0; u < U; u++) exchange_round<false, AR, true>(c0[u], c1[u], lane, 4, 0u, A);
         // lane owns rows 2j + (lane&1), columns (lane>>1) and (lane>>1)+16
 #pragma unroll
         for (int u = 0; u < U; u++)
@@ -285,7 +293,9 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll
           for (int j = 0; j < 3; j++) { c0[u][j] = x[u][2 * j]; c1[u][j] = x[u][2 * j + 1]; }
 #pragma unroll
-        for (int r = 4; r >= 0; r--)
+        for (int u = 0; u < U; u++) exchange_round<true, AR, true>(c0[u], c1[u], lane, 4, 0u, A);
+#pragma unroll
+        for (int r = 3; r >= 0; r--)
 #pragma unroll
           for (int u = 0; u < U; u++) exchange_round<true, AR>(c0[u], c1[u], lane, r, ltw[r], A);
         // lane owns rows 2j + (lane>>4), columns 2*(lane&15) and 2*(lane&15)+1; crtTwiddle with inverse roots last
@@ -367,7 +377,8 @@ k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 #pragma unroll
         for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
 #pragma unroll
-        for (int r = 0; r < 5; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[1 + r], A);
+        for (int r = 0; r < 4; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[1 + r], A);
+        exchange_round<false, AR, true>(c0, c1, lane, 4, 0u, A);
         int64_t* out = base + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -378,7 +389,9 @@ k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 #pragma unroll
         for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
 #pragma unroll
-        for (int r = 4; r >= 0; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
+        exchange_round<true, AR, true>(c0, c1, lane, 4, 0u, A);
+#pragma unroll
+        for (int r = 3; r >= 0; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
         int64_t* out = base + i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15);
 #pragma unroll
         for (int j = 0; j < 3; j++)
@@ -463,10 +476,12 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 #pragma unroll
           for (int j = 0; j < 3; j++) { c0[l][j] = x[l][2 * j]; c1[l][j] = x[l][2 * j + 1]; }
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
+        for (int r = 0; r < 4; r++) {
           exchange_round<false, AR>(c0[0], c1[0], lane, r, ltw[0][1 + r], A0);
           exchange_round<false, AR>(c0[1], c1[1], lane, r, ltw[1][1 + r], A1);
         }
+        exchange_round<false, AR, true>(c0[0], c1[0], lane, 4, 0u, A0);
+        exchange_round<false, AR, true>(c0[1], c1[1], lane, 4, 0u, A1);
         longlong2* out = ebase + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -479,7 +494,10 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 #pragma unroll
           for (int j = 0; j < 3; j++) { c0[l][j] = x[l][2 * j]; c1[l][j] = x[l][2 * j + 1]; }
 #pragma unroll
-        for (int r = 4; r >= 0; r--) {
+        exchange_round<true, AR, true>(c0[0], c1[0], lane, 4, 0u, A0);
+        exchange_round<true, AR, true>(c0[1], c1[1], lane, 4, 0u, A1);
+#pragma unroll
+        for (int r = 3; r >= 0; r--) {
           exchange_round<true, AR>(c0[0], c1[0], lane, r, ltw[0][r], A0);
           exchange_round<true, AR>(c0[1], c1[1], lane, r, ltw[1][r], A1);
         }
