@@ -229,7 +229,9 @@ __device__ __forceinline__ void load_tw16(uint32_t (&tw)[31], const uint32_t* __
   }
 }
 
-template <bool INV>
+// H0: the block has H = 0 (the pass on bits [10,15)), so the twiddle index of a pair is just j0 >> (a+1), known at
+// compile time; index 0 is the twiddle 1 (crt.cpp:92-106 starts at i0 = 1) and those 31 of 80 multiplications are dropped.
+template <bool INV, bool H0 = false>
 __device__ __forceinline__ void rounds16(uint32_t (&v)[32], const Mont& M, const uint32_t (&tw)[31])
 {
 #pragma unroll
@@ -241,7 +243,12 @@ __device__ __forceinline__ void rounds16(uint32_t (&v)[32], const Mont& M, const
       if (j0 & (1 << a)) continue;
       const int j1 = j0 | (1 << a);
       const uint32_t w = tw[toff + (j0 >> (a + 1))];
-      if (!INV) {
+      const bool trivial = H0 && (j0 >> (a + 1)) == 0;
+      if (trivial) {
+        const uint32_t u = v[j0], t = v[j1];
+        v[j0] = M.fold(u + t);
+        v[j1] = M.fold(u + M.q2 - t);
+      } else if (!INV) {
         const uint32_t u = v[j0], t = v[j1];
         v[j0] = M.fold(u + t);
         v[j1] = M.mul(u + M.q2 - t, w);
@@ -299,15 +306,19 @@ k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2P
 #pragma unroll 1
       for (int H = warp; H < kChunks; H += kWarps) {
         // load chunk H (coalesced) with crtTwiddle
-#pragma unroll 1
-        for (int i0 = 0; i0 < 32; i0 += 8) {
-          int64_t raw[8];
+        {
+          // all 32 loads of the chunk in flight at once (one HBM latency per chunk instead of four)
+          int64_t raw[32];
+          uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
-          for (int u = 0; u < 8; u++) raw[u] = __ldcs(gbase + (size_t)((H << 10) + ((i0 + u) << 5) + lane) * k);
+          for (int u = 0; u < 32; u++) raw[u] = __ldcs(gbase + (size_t)((H << 10) + (u << 5) + lane) * k);
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int pos = (H << 10) + ((i0 + u) << 5) + lane;
-            const uint32_t x = (uint64_t)raw[u] < (uint64_t)L.q ? (uint32_t)raw[u] : reduce_any64(raw[u], L.q);
+          for (int u = 0; u < 32; u++) { hi_or |= (uint32_t)((uint64_t)raw[u] >> 32); lo_max = max(lo_max, (uint32_t)raw[u]); }
+          const bool odd_input = hi_or != 0 || lo_max >= L.q;
+#pragma unroll
+          for (int u = 0; u < 32; u++) {
+            const int pos = (H << 10) + (u << 5) + lane;
+            const uint32_t x = odd_input ? reduce_any64(raw[u], L.q) : (uint32_t)raw[u];
             sm[swz(pos)] = M.mul(x, __ldg(L.crt_tw + pos));
           }
         }
@@ -324,7 +335,7 @@ k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2P
         load_tw16(tw, L.round_tw, 10, 0);
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = sm[phys16<10>(b, 0, j)];
-        rounds16<false>(v, M, tw);
+        rounds16<false, true>(v, M, tw);
 #pragma unroll
         for (int j = 0; j < 32; j++) __stcs(gbase + (size_t)(b + (j << 10)) * k, (int64_t)M.canon(v[j]));
       }
@@ -346,7 +357,7 @@ k_pow2_e16(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Pow2P
 #pragma unroll 1
           for (int j = 0; j < 32; j++) v[j] = reduce_any64(gbase[(size_t)(b + (j << 10)) * k], L.q);
         }
-        rounds16<true>(v, M, tw);
+        rounds16<true, true>(v, M, tw);
 #pragma unroll
         for (int j = 0; j < 32; j++) sm[phys16<10>(b, 0, j)] = v[j];
       }
@@ -399,7 +410,7 @@ __device__ __forceinline__ void limb16_from_scratch(uint32_t* sm, uint32_t* row,
       load_tw16(tw, L.round_tw, 10, 0);
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = sm[phys16<10>(b, 0, j)];
-      rounds16<false>(v, M, tw);
+      rounds16<false, true>(v, M, tw);
 #pragma unroll
       for (int j = 0; j < 32; j++) row[b + (j << 10)] = M.canon(v[j]);
     }
@@ -411,7 +422,7 @@ __device__ __forceinline__ void limb16_from_scratch(uint32_t* sm, uint32_t* row,
       load_tw16(tw, L.round_tw, 10, 0);
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = row[b + (j << 10)];
-      rounds16<true>(v, M, tw);
+      rounds16<true, true>(v, M, tw);
 #pragma unroll
       for (int j = 0; j < 32; j++) sm[phys16<10>(b, 0, j)] = v[j];
     }
