@@ -628,13 +628,18 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
       cudaFuncSetAttribute(k_pow2_e16<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_pow2_e16<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_pow2_e16<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_pow2_e16<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr16 = true;
     }
     if (pl->k == 1) {
       if (inverse) k_pow2_e16<true, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
       else k_pow2_e16<false, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
-    } else if ((pl->k == 2 || pl->k == 3 || pl->k == 4) && getenv("LOLB_POW2_ELEM")) {
-      // opt-in experiment: +14% forward, but the scratch is partly written back to HBM (1.33x traffic)
+    } else if (!getenv("LOLB_POW2_PER_LIMB") && ((pl->k == 4 && !inverse) || ((pl->k == 2 || pl->k == 3 || pl->k == 4) && getenv("LOLB_POW2_ELEM")))) {
+      // element-per-CTA with an L2 scratch: measured faster only for the forward transform at tupSize 4
+      // (28.7 % vs 24.8 % of HBM peak; inverse 28.3 % vs 30.8 %); part of the scratch is written back to HBM
       int64_t g2 = pl->num_sms;
       if (g2 > batch) g2 = batch;
       int rc = plan_reserve_ws(pl, (size_t)g2 * pl->k * kN16 * sizeof(uint32_t));
@@ -654,6 +659,12 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
                         : k_pow2_e16_elem<false, KK><<<(int)g2, kT16, smem, st>>>(y, batch, F->fwd, scratch))
       if (pl->k == 2) LE(2); else if (pl->k == 3) LE(3); else LE(4);
 #undef LE
+    } else if (pl->k == 2) {
+      if (inverse) k_pow2_e16<true, 2><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
+      else k_pow2_e16<false, 2><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
+    } else if (pl->k == 4) {
+      if (inverse) k_pow2_e16<true, 4><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
+      else k_pow2_e16<false, 4><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
     } else {
       if (inverse) k_pow2_e16<true, 0><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
       else k_pow2_e16<false, 0><<<(int)grid, kT16, smem, st>>>(y, batch, F->fwd);
