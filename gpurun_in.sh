@@ -1,0 +1,9 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "dataflow or power_of_two or config_b or non_canonical or full_size" 2>&1 | tail -15
+Q4=537133057,537591809,537722881,538116097
+for op in CRT CRTInv; do
+  timeout 120 python tools/run_op.py 65536 $Q4 1024 $op 20
+  timeout 120 python tools/run_op.py 65536 537133057,537591809 2048 $op 20
+  timeout 120 python tools/run_op.py 65536 537133057 4096 $op 20
+done
+LOLB_POW2_NO_DF=1 timeout 120 python tools/run_op.py 65536 $Q4 1024 CRT 20

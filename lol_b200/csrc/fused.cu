@@ -17,6 +17,12 @@ void fused_pow2_release(void* slot);
 bool fused_pow2_available(const void* slot, bool inverse);
 int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 
+// fused_pow2_df.cu
+int fused_pow2_df_select(lolb_plan* pl, void** slot);
+void fused_pow2_df_release(void* slot);
+bool fused_pow2_df_available(const void* slot, bool inverse);
+int fused_pow2_df_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+
 // fused_stream.cu
 const char* fused_stream_line_name(const lolb_plan* pl);
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
@@ -25,7 +31,8 @@ int fused_stream_mul(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t 
 namespace {
 struct FusedSet {
   void* a = nullptr;      // m = 14400 CRT / CRT^-1
-  void* pow2 = nullptr;   // m = 2^e CRT / CRT^-1
+  void* pow2 = nullptr;   // m = 2^e CRT / CRT^-1, limb resident in shared memory (e <= 12, tupSize 3, ...)
+  void* pow2_df = nullptr;  // m = 2^e CRT / CRT^-1, dataflow kernel with an L2 exchange ring (13 <= e <= 16)
 };
 FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
 }  // namespace
@@ -36,6 +43,7 @@ int fused_select(lolb_plan* pl)
   if (!pl->fused) pl->fused = new FusedSet();
   int rc = fused_a_select(pl, &set_of(pl)->a);
   if (!rc) rc = fused_pow2_select(pl, &set_of(pl)->pow2);
+  if (!rc) rc = fused_pow2_df_select(pl, &set_of(pl)->pow2_df);
   return rc;
 }
 
@@ -45,6 +53,7 @@ void fused_release(lolb_plan* pl)
   if (!s) return;
   fused_a_release(s->a);
   fused_pow2_release(s->pow2);
+  fused_pow2_df_release(s->pow2_df);
   delete s;
   pl->fused = nullptr;
 }
@@ -55,6 +64,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
   if (s) {
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
+    if (!strcmp(op, "CRT") && fused_pow2_df_available(s->pow2_df, false)) return "fused_pow2_df";
+    if (!strcmp(op, "CRTInv") && fused_pow2_df_available(s->pow2_df, true)) return "fused_pow2_df";
     if (!strcmp(op, "CRT") && fused_pow2_available(s->pow2, false)) return "fused_pow2";
     if (!strcmp(op, "CRTInv") && fused_pow2_available(s->pow2, true)) return "fused_pow2";
   }
@@ -70,6 +81,7 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
   const FusedSet* s = set_of(pl);
   if (!s) return LOLB_FUSED_UNAVAILABLE;
   int rc = fused_a_crt(pl, s->a, inverse, y, batch, st);
+  if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_df_crt(pl, s->pow2_df, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_crt(pl, s->pow2, inverse, y, batch, st);
   return rc;
 }

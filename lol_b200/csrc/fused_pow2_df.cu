@@ -1,0 +1,478 @@
+// fused_pow2_df.cu -- Z_q CRT / CRT^-1 for power-of-two index m = 2^e, 12 <= e <= 16, as ONE persistent
+// dataflow kernel with an L2-resident exchange ring (BASELINE.json config B: m = 2^16, four ~30-bit primes).
+//
+// Operator.  For p = 2 the reference's  crtTwiddle ; {dftp ; dftTwiddle} x (e-1)  (crt.cpp:43-58, 137-149, 92-106,
+// 459-486, 518-538) evaluates  f(x) = sum_i y[i] x^rev(i)  at  psi^(2 pos + 1),  pos = 0 .. n-1, psi = ru[0][1]
+// (oracle-checked: tests/test_oracle_pinning.py::test_pow2_crt_is_negacyclic_evaluation).  Over Z_q every exact
+// evaluation order gives the same residues, so the kernel uses the twist-free Cooley-Tukey form of the same map:
+//   round r = 0 .. e-2, pairs (pos, pos + 2^r) with bit r of pos clear, p = pos mod 2^r:
+//     forward   (u, t) -> (u + T t, u - T t),      T = psi^((2p+1) n / 2^(r+1))          rounds ascending
+//     inverse   (u, t) -> (u + t, (u - t) / T),    rounds descending, then * mhat^-1      (crt.cpp:488-516, 573-579)
+// No crtTwiddle table, no separate scaling pass; the twiddle of round r depends on the LOW r bits of pos only, so
+// rounds 0-4 use 31 per-limb constants (kernel-parameter bank), rounds 5-9 a 4 KB L1-resident table.
+//
+// Schedule.  The limb (n <= 32768 coefficients, 128 KB as u32) is never resident in one SM.  Position bits [0,10)
+// ("chunk" rounds) and bits [10, e-1) ("column" rounds) are two task kinds of 128 threads each:
+//   chunk task   one contiguous 32 KB piece of the element (1024 coefficients x K limbs x 4/K chunks): coalesced
+//                128-bit loads, limbs de-interleaved through 17 KB of shared memory, rounds 0-4 by the thread
+//                that owns 32 consecutive coefficients, rounds 5-9 by the lane that owns stride-32 coefficients
+//   column task  128 consecutive (coefficient, limb) pairs x all 2^(e-11) chunks: rounds 10 .. e-2 in registers,
+//                no shared memory; every int64 store / load of the element is part of a fully used 32-byte sector
+// The two kinds exchange u32 residues through a ring of `ring` element slots in global memory that is sized to stay
+// in the 126 MB L2 (default 48 slots = 24 MB at config B), so HBM sees one read and one write of the element.
+// CTAs are persistent and take tasks from an atomic counter; per-element counters order  first kind -> second kind
+// -> slot reuse.  A task only waits for tasks with a smaller index, which are already running: no deadlock.
+//
+// Arithmetic (odd q, 4q < 2^32): lazy residues in [0,4q) (forward) / [0,2q) (inverse), twiddles in Montgomery form
+// (IMAD.WIDE, IMAD, IMAD.HI), fold = one VIADDMNMX, canonical [0,q) only at the final store.
+#include <cstdlib>
+
+#include "fused.cuh"
+#include "numtheory.h"
+
+namespace lolb {
+
+namespace {
+
+constexpr int kDfThreads = 128;
+constexpr int kDfUnit = 1024 + 32 + 8;   // words per (chunk, limb) unit in shared memory: +1 per 32 (padding), +8 (bank shift per unit)
+constexpr int kDfMaxK = 4;
+constexpr int kDfCtrHead = 16;           // ctr[0] = task counter; per-element counters start here
+
+struct DfLimb {
+  uint32_t q, q2, qinv;
+  uint32_t sA, sB;         // inverse: mont(mhat^-1), mont(mhat^-1 / T_0)
+  uint32_t c0[31];         // Montgomery twiddles of rounds 0..4: entry (2^a - 1) + p
+  const uint32_t* tw;      // all rounds: entry (2^r - 1) + p, p < 2^r, Montgomery form
+};
+
+struct DfParams {
+  int32_t n, k;
+  int32_t ring, lag;       // exchange-ring slots; distance (in elements) between the two task kinds in the queue
+  DfLimb limb[kDfMaxK];
+};
+
+struct Mont {
+  uint32_t q, q2, qinv;    // qinv = -q^-1 mod 2^32
+  // x any u32, w < q in Montgomery form  ->  x * w mod q  in [0, 2q)
+  __device__ __forceinline__ uint32_t mul(uint32_t x, uint32_t w) const
+  {
+    const uint64_t p = (uint64_t)x * w;
+    const uint32_t m = (uint32_t)p * qinv;
+    return (uint32_t)((p + (uint64_t)m * q) >> 32);
+  }
+  __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }    // [0,4q) -> [0,2q)
+  __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }    // [0,2q) -> [0,q)
+};
+
+__device__ __noinline__ uint32_t df_reduce_any64(int64_t x, uint32_t q)
+{
+  int64_t r = x % (int64_t)q;
+  return (uint32_t)(r < 0 ? r + q : r);
+}
+
+// S forward rounds on the 2^S registers of one block; tw(a, jj) = twiddle of the pairs with j0 mod 2^a = jj
+template <int S, bool CANON_IN, class TW>
+__device__ __forceinline__ void ct_rounds(uint32_t (&v)[1 << S], const Mont& M, TW tw)
+{
+#pragma unroll
+  for (int a = 0; a < S; a++) {
+#pragma unroll
+    for (int j0 = 0; j0 < (1 << S); j0++) {
+      if (j0 & (1 << a)) continue;
+      const int j1 = j0 | (1 << a);
+      const uint32_t w = tw(a, j0 & ((1 << a) - 1));
+      const uint32_t u = (CANON_IN && a == 0) ? v[j0] : M.fold(v[j0]);
+      const uint32_t t = M.mul(v[j1], w);
+      v[j0] = u + t;
+      v[j1] = u + M.q2 - t;
+    }
+  }
+}
+
+// inverse rounds S-1 .. LOW on residues in [0,2q)
+template <int S, int LOW, class TW>
+__device__ __forceinline__ void gs_rounds(uint32_t (&v)[1 << S], const Mont& M, TW tw)
+{
+#pragma unroll
+  for (int a = S - 1; a >= LOW; a--) {
+#pragma unroll
+    for (int j0 = 0; j0 < (1 << S); j0++) {
+      if (j0 & (1 << a)) continue;
+      const int j1 = j0 | (1 << a);
+      const uint32_t w = tw(a, j0 & ((1 << a) - 1));
+      const uint32_t u = v[j0], t = v[j1];
+      v[j0] = M.fold(u + t);
+      v[j1] = M.mul(u + M.q2 - t, w);
+    }
+  }
+}
+
+// rounds 0-4 of one unit: lane owns coefficients 32*lane .. 32*lane+31 (padded word 33*lane + j, conflict free).
+// LIMB is a template parameter so the 31 twiddles and q, q', 2q are constant-bank operands, not registers.
+template <bool INV, int LIMB>
+__device__ __forceinline__ void unit_rounds_0_4(uint32_t* Uu, const DfParams& P, int lane)
+{
+  const DfLimb& L = P.limb[LIMB];
+  const Mont M{L.q, L.q2, L.qinv};
+  uint32_t* base = Uu + 33 * lane;
+  uint32_t v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = base[j];
+  if (!INV) {
+    ct_rounds<5, true>(v, M, [&](int a, int jj) { return L.c0[(1 << a) - 1 + jj]; });
+  } else {
+    gs_rounds<5, 1>(v, M, [&](int a, int jj) { return L.c0[(1 << a) - 1 + jj]; });
+    // round 0 with mhat^-1 folded in (crt.cpp:573-579), then canonical
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 2) {
+      const uint32_t u = v[j0], t = v[j0 + 1];
+      v[j0] = M.canon(M.mul(u + t, L.sA));
+      v[j0 + 1] = M.canon(M.mul(u + M.q2 - t, L.sB));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) base[j] = v[j];
+}
+
+template <bool INV>
+__device__ __forceinline__ void unit_rounds_0_4_any(int limb, uint32_t* Uu, const DfParams& P, int lane)
+{
+  switch (limb) {
+    case 0: unit_rounds_0_4<INV, 0>(Uu, P, lane); break;
+    case 1: unit_rounds_0_4<INV, 1>(Uu, P, lane); break;
+    case 2: unit_rounds_0_4<INV, 2>(Uu, P, lane); break;
+    default: unit_rounds_0_4<INV, 3>(Uu, P, lane); break;
+  }
+}
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target)
+{
+  if (threadIdx.x == 0) {
+    while (ld_acquire(p) < target) __nanosleep(100);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void signal_counter(unsigned* p)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(p, 1u);
+  }
+}
+
+// K = tupSize (1, 2 or 4); TOP = e - 11 = rounds above bit 10 (1..5)
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kDfThreads, 4)
+k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring,
+          unsigned* __restrict__ ctr)
+{
+  constexpr int NCH = 1 << TOP;                 // chunks per limb
+  constexpr int N = 1024 << TOP;                // coefficients per limb
+  constexpr int G = 4 / K;                      // chunks per chunk task (4 units of 1024 residues)
+  constexpr int NT_CHUNK = NCH / G;             // chunk tasks per element
+  constexpr int NT_COL = (1024 * K) / kDfThreads;   // column tasks per element
+  constexpr int NT_A = INV ? NT_COL : NT_CHUNK;     // first kind
+  constexpr int NT_B = INV ? NT_CHUNK : NT_COL;     // second kind
+  constexpr int NV = 1 << TOP;                  // residues per thread in a column task
+  static_assert(NCH % G == 0, "chunk tasks must tile the element");
+
+  __shared__ __align__(16) uint32_t U[4 * kDfUnit];
+  __shared__ unsigned s_task;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned* cnt_a = ctr + kDfCtrHead;           // finished first-kind tasks per element
+  unsigned* cnt_b = cnt_a + batch;              // finished second-kind tasks per element
+  const int64_t groups = batch + P.lag;
+  const unsigned total = (unsigned)(groups * (NT_A + NT_B));
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_task = atomicAdd(ctr, 1u);
+    __syncthreads();
+    const unsigned t = s_task;
+    if (t >= total) break;
+    const int64_t grp = t / (NT_A + NT_B);
+    const int r = (int)(t - grp * (NT_A + NT_B));
+    const bool first = r < NT_A;
+    const int64_t el = first ? grp : grp - P.lag;
+    if (el < 0 || el >= batch) continue;
+    const int task = first ? r : r - NT_A;
+    const bool chunk_task = (first != INV);
+    uint32_t* slot = ring + (size_t)(el % P.ring) * ((size_t)K * N);
+    int64_t* ebase = y + (size_t)el * ((size_t)K * N);
+
+    if (first) {
+      if (el >= P.ring) wait_counter(cnt_b + (el - P.ring), NT_B);     // slot free: its previous element is consumed
+    } else {
+      wait_counter(cnt_a + el, NT_A);                                    // all first-kind tasks of this element done
+    }
+
+    if (chunk_task) {
+      // ---------------------------------------------------------------- chunk task: bits [0,10)
+      const int chunk0 = task * G;
+      int64_t* gpiece = ebase + (size_t)chunk0 * 1024 * K;              // 4096 contiguous int64
+      const int unit = warp;                                             // (chunk_in_task, limb) of this warp
+      const int uch = unit / K, limb = unit % K;
+      uint32_t* Uu = U + unit * kDfUnit;
+      const DfLimb& L = P.limb[limb];
+      const Mont M{L.q, L.q2, L.qinv};
+      uint32_t* srow = slot + (size_t)limb * N + (size_t)(chunk0 + uch) * 1024 + lane;
+      if (!INV) {
+        // coalesced load of the piece, limbs de-interleaved into the 4 units
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          longlong2 raw[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) raw[i] = __ldcs(reinterpret_cast<const longlong2*>(gpiece) + tid + kDfThreads * (half * 8 + i));
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int v0 = 2 * (tid + kDfThreads * (half * 8 + i));      // index of the first int64 of the pair
+            const int c = v0 / K, l0 = v0 % K;
+            const int cc = c & 1023, u0 = (c >> 10) * K + l0;
+            const uint32_t q0 = P.limb[l0].q;
+            const uint32_t x0 = (uint64_t)raw[i].x < (uint64_t)q0 ? (uint32_t)raw[i].x : df_reduce_any64(raw[i].x, q0);
+            U[u0 * kDfUnit + cc + (cc >> 5)] = x0;
+            if (K == 1) {
+              const uint32_t x1 = (uint64_t)raw[i].y < (uint64_t)q0 ? (uint32_t)raw[i].y : df_reduce_any64(raw[i].y, q0);
+              U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] = x1;
+            } else {
+              const uint32_t q1 = P.limb[l0 + 1].q;
+              const uint32_t x1 = (uint64_t)raw[i].y < (uint64_t)q1 ? (uint32_t)raw[i].y : df_reduce_any64(raw[i].y, q1);
+              U[(u0 + 1) * kDfUnit + cc + (cc >> 5)] = x1;
+            }
+          }
+        }
+        __syncthreads();
+        unit_rounds_0_4_any<false>(limb, Uu, P, lane);
+        __syncwarp();
+        // rounds 5-9: lane owns coefficients lane + 32 j
+        {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
+          const uint32_t* twl = L.tw + lane;
+          ct_rounds<5, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+          for (int j = 0; j < 32; j++) srow[32 * j] = v[j];
+        }
+        signal_counter(cnt_a + el);
+      } else {
+        {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = __ldcg(srow + 32 * j);
+          const uint32_t* twl = L.tw + lane;
+          gs_rounds<5, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+          for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
+        }
+        __syncwarp();
+        unit_rounds_0_4_any<true>(limb, Uu, P, lane);
+        __syncthreads();
+        // canonical residues -> interleaved int64, coalesced 128-bit stores
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int v0 = 2 * (tid + kDfThreads * i);
+          const int c = v0 / K, l0 = v0 % K;
+          const int cc = c & 1023, u0 = (c >> 10) * K + l0;
+          const uint32_t x0 = U[u0 * kDfUnit + cc + (cc >> 5)];
+          const uint32_t x1 = K == 1 ? U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] : U[(u0 + 1) * kDfUnit + cc + (cc >> 5)];
+          __stcs(reinterpret_cast<longlong2*>(gpiece) + tid + kDfThreads * i, make_longlong2((int64_t)x0, (int64_t)x1));
+        }
+        signal_counter(cnt_b + el);
+      }
+    } else {
+      // ---------------------------------------------------------------- column task: bits [10, 10 + TOP)
+      const int f = task * kDfThreads + tid;                             // (coefficient b, limb) pair, ABI order
+      const int b = f / K, limb = f % K;
+      const DfLimb& L = P.limb[limb];
+      const Mont M{L.q, L.q2, L.qinv};
+      uint32_t* scol = slot + (size_t)limb * N + b;
+      int64_t* gcol = ebase + f;
+      const uint32_t* twb = L.tw + b;
+      uint32_t v[NV];
+      if (!INV) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) v[j] = __ldcg(scol + 1024 * j);
+        ct_rounds<TOP, false>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
+#pragma unroll
+        for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
+        signal_counter(cnt_b + el);
+      } else {
+        uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          const int64_t raw = __ldcs(gcol + (size_t)1024 * K * j);
+          v[j] = (uint32_t)raw;
+          hi_or |= (uint32_t)((uint64_t)raw >> 32);
+          lo_max = max(lo_max, v[j]);
+        }
+        if (hi_or != 0 || lo_max >= L.q) {      // outside the Haskell contract: reduce like the reference's c % q
+#pragma unroll
+          for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(gcol[(size_t)1024 * K * j], L.q);
+        }
+        gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
+#pragma unroll
+        for (int j = 0; j < NV; j++) scol[1024 * j] = v[j];
+        signal_counter(cnt_a + el);
+      }
+    }
+  }
+}
+
+struct FusedPow2Df {
+  bool ok_fwd = false, ok_inv = false;
+  DfParams fwd{}, inv{};
+  uint32_t* d_tab = nullptr;
+  int top = 0;
+};
+
+uint32_t neg_inv32(uint32_t q)
+{
+  uint32_t inv = q;
+  for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
+  return 0u - inv;
+}
+
+bool shape_ok(const lolb_plan* pl)
+{
+  if (pl->kind != PLAN_RQ || pl->pe.size() != 1 || pl->pe[0].prime != 2) return false;
+  const int e = pl->pe[0].exponent;
+  if (e < 13 || e > 16) return false;
+  if (pl->k != 1 && pl->k != 2 && pl->k != 4) return false;
+  for (int64_t q : pl->qs) if (!(q & 1) || 4 * (uint64_t)q >= ((uint64_t)1 << 32)) return false;
+  return true;
+}
+
+template <bool INV, int K, int TOP>
+int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  static int per_sm = 0;
+  if (!per_sm) {
+    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_df<INV, K, TOP>, kDfThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  DfParams P = INV ? F->inv : F->fwd;
+  const char* s;
+  if ((s = getenv("LOLB_DF_RING")) != nullptr && atoi(s) > 0) P.ring = atoi(s);
+  if ((s = getenv("LOLB_DF_LAG")) != nullptr && atoi(s) > 0) P.lag = atoi(s);
+  if (P.lag >= P.ring) P.lag = P.ring - 1;
+  const size_t slot_bytes = (size_t)K * pl->n * sizeof(uint32_t);
+  const size_t ring_bytes = (size_t)P.ring * slot_bytes;
+  const size_t ctr_bytes = ((size_t)kDfCtrHead + 2 * (size_t)batch) * sizeof(unsigned);
+  int rc = plan_reserve_ws(pl, ring_bytes + ctr_bytes);
+  if (rc) return rc;
+  uint32_t* ring = (uint32_t*)pl->d_ws;
+  unsigned* ctr = (unsigned*)((char*)pl->d_ws + ring_bytes);
+  LOLB_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
+  const int64_t tasks_per_el = (int64_t)(((1 << TOP) * K) / 4 + (1024 * K) / kDfThreads);
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > batch * tasks_per_el) grid = batch * tasks_per_el;
+  k_pow2_df<INV, K, TOP><<<(int)grid, kDfThreads, 0, st>>>(y, batch, P, ring, ctr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_pow2_df");
+  count_launch();
+  return LOLB_OK;
+}
+
+template <bool INV, int K>
+int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  switch (F->top) {
+    case 2: return launch_df<INV, K, 2>(pl, F, y, batch, st);
+    case 3: return launch_df<INV, K, 3>(pl, F, y, batch, st);
+    case 4: return launch_df<INV, K, 4>(pl, F, y, batch, st);
+    case 5: return launch_df<INV, K, 5>(pl, F, y, batch, st);
+  }
+  return LOLB_FUSED_UNAVAILABLE;
+}
+
+}  // namespace
+
+int fused_pow2_df_select(lolb_plan* pl, void** slot)
+{
+  if (!shape_ok(pl)) return LOLB_OK;
+  FusedPow2Df* F = (FusedPow2Df*)*slot;
+  if (!F) { F = new FusedPow2Df(); *slot = F; }
+  const int e = pl->pe[0].exponent, n = pl->n, k = pl->k, rounds = e - 1;
+  F->top = e - 11;
+  F->ok_fwd = pl->has_fwd && pl->ru.size() == 1;
+  F->ok_inv = pl->has_inv && pl->ruinv.size() == 1 && (int)pl->mhatinv.size() == k;
+  const size_t per_dir = ((size_t)n + 3) & ~(size_t)3;      // n - 1 entries, padded
+  std::vector<uint32_t> host((size_t)k * 2 * per_dir, 0u);
+  const int64_t m = pl->m;
+  DfParams P[2]{};
+  for (int dir = 0; dir < 2; dir++) {
+    P[dir].n = n; P[dir].k = k;
+    P[dir].ring = 48; P[dir].lag = 12;
+  }
+  for (int t = 0; t < k; t++) {
+    const uint64_t q = (uint64_t)pl->qs[t];
+    auto mont = [&](uint64_t c) { return (uint32_t)(((c % q) << 32) % q); };
+    for (int dir = 0; dir < 2; dir++) {
+      if (dir == 0 ? !F->ok_fwd : !F->ok_inv) continue;
+      const std::vector<int64_t>& T = dir == 0 ? pl->ru[0] : pl->ruinv[0];
+      auto root = [&](int64_t j) { int64_t v = T[(size_t)(j % m) * k + t] % (int64_t)q; return (uint64_t)(v < 0 ? v + (int64_t)q : v); };
+      uint32_t* tw = host.data() + ((size_t)t * 2 + dir) * per_dir;
+      for (int r = 0; r < rounds; r++)
+        for (int64_t p = 0; p < ((int64_t)1 << r); p++)
+          tw[((size_t)1 << r) - 1 + p] = mont(root((2 * p + 1) * (n >> (r + 1))));
+      DfLimb& L = P[dir].limb[t];
+      L.q = (uint32_t)q; L.q2 = 2 * (uint32_t)q; L.qinv = neg_inv32((uint32_t)q);
+      for (int i = 0; i < 31; i++) L.c0[i] = tw[i];
+      if (dir == 1) {
+        const uint64_t s = (uint64_t)(((pl->mhatinv[t] % (int64_t)q) + (int64_t)q) % (int64_t)q);
+        L.sA = mont(s);
+        L.sB = mont(mulmod64(s, root(n >> 1), q));
+      }
+    }
+  }
+  if (F->d_tab) { cudaFree(F->d_tab); F->d_tab = nullptr; }
+  LOLB_CUDA(cudaMalloc((void**)&F->d_tab, host.size() * sizeof(uint32_t)));
+  LOLB_CUDA(cudaMemcpy(F->d_tab, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  for (int t = 0; t < k; t++)
+    for (int dir = 0; dir < 2; dir++) P[dir].limb[t].tw = F->d_tab + ((size_t)t * 2 + dir) * per_dir;
+  F->fwd = P[0]; F->inv = P[1];
+  return LOLB_OK;
+}
+
+void fused_pow2_df_release(void* slot)
+{
+  FusedPow2Df* F = (FusedPow2Df*)slot;
+  if (!F) return;
+  if (F->d_tab) cudaFree(F->d_tab);
+  delete F;
+}
+
+bool fused_pow2_df_available(const void* slot, bool inverse)
+{
+  const FusedPow2Df* F = (const FusedPow2Df*)slot;
+  if (!F || getenv("LOLB_POW2_NO_DF")) return false;
+  return inverse ? F->ok_inv : F->ok_fwd;
+}
+
+int fused_pow2_df_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const FusedPow2Df* F = (const FusedPow2Df*)slot;
+  if (!fused_pow2_df_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
+  if (batch <= 0) return LOLB_OK;
+  if ((uint64_t)batch >= ((uint64_t)1 << 25)) return LOLB_FUSED_UNAVAILABLE;      // 32-bit task counter
+  switch (pl->k) {
+    case 1: return inverse ? launch_df_top<true, 1>(pl, F, y, batch, st) : launch_df_top<false, 1>(pl, F, y, batch, st);
+    case 2: return inverse ? launch_df_top<true, 2>(pl, F, y, batch, st) : launch_df_top<false, 2>(pl, F, y, batch, st);
+    case 4: return inverse ? launch_df_top<true, 4>(pl, F, y, batch, st) : launch_df_top<false, 4>(pl, F, y, batch, st);
+  }
+  return LOLB_FUSED_UNAVAILABLE;
+}
+
+}  // namespace lolb

@@ -287,6 +287,33 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
     assert (tr.gSqNormDec(smp) > 0).all()
 
 
+@pytest.mark.parametrize("ring,lag", [(3, 1), (5, 4), (48, 12)], ids=lambda v: str(v))
+@pytest.mark.parametrize("e,k", [(13, 1), (13, 2), (13, 4), (14, 4), (15, 2), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
+def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, ring, lag):
+    """fused_pow2_df (persistent dataflow kernel, L2 exchange ring) for tupSize 1, 2, 4: batches larger than the
+    ring so slots are reused, tiny rings so the per-element counters are exercised; oracle parity on a sample of
+    elements, the generic engine on all of them, and crtInv . crt = id."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    monkeypatch.setenv("LOLB_DF_RING", str(ring))
+    monkeypatch.setenv("LOLB_DF_LAG", str(lag))
+    m, qs = 2 ** e, CONFIG_B[1][:k]
+    B = 23 if ring < 48 else 61
+    rng = np.random.default_rng(e * 10 + k)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    assert t.plan.kernel_name("CRT") == "fused_pow2_df" and t.plan.kernel_name("CRTInv") == "fused_pow2_df"
+    y = zq_input(rng, n, qs, batch=B)
+    x = torch.from_numpy(y).cuda()
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, 1, B // 2, B - 1):
+        assert np.array_equal(f[b].cpu().numpy(), oracle.tensorCRTRq(y[b], pe, ru, qs)), b
+        assert np.array_equal(g[b].cpu().numpy(), oracle.tensorCRTInvRq(y[b], pe, rui, mh, qs)), b
+    assert torch.equal(t.crtInv(f), x) and torch.equal(t.crt(g), x)
+    t.plan.force_generic(True)
+    assert torch.equal(t.crt(x), f) and torch.equal(t.crtInv(x), g)
+
+
 @pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89], ids=str)
 def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
     """The streaming kernels of the modulus-free rings (one or two small odd primes) against the generic pass

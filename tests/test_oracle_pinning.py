@@ -156,3 +156,42 @@ def test_table_anchors():
     assert T.smallest_generator(14401) == 11 and T.omega(14400, 14401) == 11 and T.mhat_inv(14400, 14401) == 14399
     assert T.smallest_generator(786433) == 10 and T.omega(65536, 786433) == 108788
     assert [q for q, _ in zip(T.good_qs(65536, 2 ** 29), range(4))] == CONFIG_B[1]
+
+
+@pytest.mark.parametrize("e,q", [(5, 97), (8, 257), (11, 12289), (13, 40961)], ids=lambda v: str(v))
+def test_pow2_crt_is_negacyclic_evaluation(oracle, e, q):
+    """What lol_b200/csrc/fused_pow2_df.cu relies on: for m = 2^e the reference's crtTwiddle + DFT rounds
+    (crt.cpp:43-58, 459-486) evaluate f(x) = sum_i y[i] x^rev(i) at psi^(2 pos + 1), psi = ru[0][1], so the
+    twist-free Cooley-Tukey rounds with T_r[p] = psi^((2p+1) n / 2^(r+1)) give the same residues."""
+    m, n = 1 << e, 1 << (e - 1)
+    pe = T.pe_array(m)
+    ru, rui = T.ru_tables_zq(m, [q]), T.ru_tables_zq(m, [q], inverse=True)
+    y = zq_input(np.random.default_rng(e), n, [q])
+    want = oracle.tensorCRTRq(y, pe, ru, [q])
+    root = [int(v) for v in ru[0].reshape(-1)]
+    v = [int(c) for c in y.reshape(-1)]
+    for r in range(e - 1):
+        st = 1 << r
+        tw = [root[(2 * p + 1) * (n >> (r + 1))] for p in range(st)]
+        for pos in range(n):
+            if not pos & st:
+                u, t = v[pos], v[pos + st] * tw[pos & (st - 1)] % q
+                v[pos], v[pos + st] = (u + t) % q, (u - t) % q
+    assert v == [int(c) for c in want.reshape(-1)]
+    if e <= 8:        # direct evaluation
+        rev = lambda i: int(format(i, f"0{e - 1}b")[::-1], 2)
+        for pos in (0, 1, n // 2, n - 1):
+            x = pow(root[1], 2 * pos + 1, q)
+            assert sum(int(y[i, 0]) * pow(x, rev(i), q) for i in range(n)) % q == int(want[pos, 0])
+    # inverse: rounds descending with inverse twiddles, then mhat^-1
+    rooti = [int(c) for c in rui[0].reshape(-1)]
+    w = [int(c) for c in want.reshape(-1)]
+    for r in range(e - 2, -1, -1):
+        st = 1 << r
+        tw = [rooti[(2 * p + 1) * (n >> (r + 1))] for p in range(st)]
+        for pos in range(n):
+            if not pos & st:
+                u, t = w[pos], w[pos + st]
+                w[pos], w[pos + st] = (u + t) % q, (u - t) * tw[pos & (st - 1)] % q
+    s = T.mhat_inv(m, q)
+    assert [c * s % q for c in w] == [int(c) for c in y.reshape(-1)]
