@@ -35,7 +35,7 @@ def lib() -> C.CDLL:
     """The shared library.  Raises if it has not been built: there is no fallback."""
     global _lib
     if _lib is None:
-        path = library_path()
+        path = os.environ.get("LOLB_LIBRARY") or library_path()      # override: kernel-tuning builds (tools/build_variant.py)
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} is missing: build it with `python -m lol_b200.build` "

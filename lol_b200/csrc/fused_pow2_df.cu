@@ -34,7 +34,6 @@ namespace lolb {
 
 namespace {
 
-constexpr int kDfThreads = 128;
 constexpr int kDfUnit = 1024 + 32 + 8;   // words per (chunk, limb) unit in shared memory: +1 per 32 (padding), +8 (bank shift per unit)
 constexpr int kDfMaxK = 4;
 constexpr int kDfCtrHead = 16;           // ctr[0] = task counter; per-element counters start here
@@ -146,6 +145,41 @@ __device__ __forceinline__ void unit_rounds_0_4_any(int limb, uint32_t* Uu, cons
   }
 }
 
+#ifndef LOLB_DF_NW
+#define LOLB_DF_NW 4            // warps per CTA = (chunk, limb) units per chunk task
+#endif
+#ifndef LOLB_DF_SWITCH
+#define LOLB_DF_SWITCH 0        // 1: rounds 0-4 specialised per limb (twiddles as constant-bank operands); 0: one copy, LDC
+#endif
+constexpr int kDfWarps = LOLB_DF_NW;
+constexpr int kDfThreads = 32 * kDfWarps;
+
+// rounds 0-4 with a run-time limb: one copy of the code, twiddles fetched with LDC
+template <bool INV>
+__device__ __forceinline__ void unit_rounds_0_4_rt(int limb, uint32_t* Uu, const DfParams& P, int lane)
+{
+  const DfLimb& L = P.limb[limb];
+  const Mont M{L.q, L.q2, L.qinv};
+  uint32_t* base = Uu + 33 * lane;
+  uint32_t v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = base[j];
+  if (!INV) {
+    ct_rounds<5, true>(v, M, [&](int a, int jj) { return L.c0[(1 << a) - 1 + jj]; });
+  } else {
+    gs_rounds<5, 1>(v, M, [&](int a, int jj) { return L.c0[(1 << a) - 1 + jj]; });
+    const uint32_t sA = L.sA, sB = L.sB;
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 2) {
+      const uint32_t u = v[j0], t = v[j0 + 1];
+      v[j0] = M.canon(M.mul(u + t, sA));
+      v[j0 + 1] = M.canon(M.mul(u + M.q2 - t, sB));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) base[j] = v[j];
+}
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
 {
   unsigned v;
@@ -153,107 +187,150 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
   return v;
 }
 
-__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target)
-{
-  if (threadIdx.x == 0) {
-    while (ld_acquire(p) < target) __nanosleep(100);
+// task index -> (element, kind, index inside the element); the queue interleaves, per element e, the first-kind
+// tasks of e with the second-kind tasks of e - lag
+template <int NT_A, int NT_B>
+struct TaskId {
+  int64_t el;
+  int task;
+  bool first, valid;
+  __device__ __forceinline__ TaskId(unsigned t, int64_t batch, int lag)
+  {
+    const int64_t grp = t / (unsigned)(NT_A + NT_B);
+    const int r = (int)(t - (unsigned)grp * (unsigned)(NT_A + NT_B));
+    first = r < NT_A;
+    el = first ? grp : grp - lag;
+    task = first ? r : r - NT_A;
+    valid = el >= 0 && el < batch;
   }
-  __syncthreads();
-}
+};
 
-__device__ __forceinline__ void signal_counter(unsigned* p)
-{
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p, 1u);
-  }
-}
-
-// K = tupSize (1, 2 or 4); TOP = e - 11 = rounds above bit 10 (1..5)
+// K = tupSize (1, 2 or 4); TOP = e - 11 = rounds above bit 10 (2..5)
 template <bool INV, int K, int TOP>
-__global__ void __launch_bounds__(kDfThreads, 4)
+__global__ void __launch_bounds__(kDfThreads, 512 / kDfThreads)
 k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring,
           unsigned* __restrict__ ctr)
 {
   constexpr int NCH = 1 << TOP;                 // chunks per limb
   constexpr int N = 1024 << TOP;                // coefficients per limb
-  constexpr int G = 4 / K;                      // chunks per chunk task (4 units of 1024 residues)
+  constexpr int G = kDfWarps / K;               // chunks per chunk task (kDfWarps units of 1024 residues)
   constexpr int NT_CHUNK = NCH / G;             // chunk tasks per element
   constexpr int NT_COL = (1024 * K) / kDfThreads;   // column tasks per element
   constexpr int NT_A = INV ? NT_COL : NT_CHUNK;     // first kind
   constexpr int NT_B = INV ? NT_CHUNK : NT_COL;     // second kind
   constexpr int NV = 1 << TOP;                  // residues per thread in a column task
-  static_assert(NCH % G == 0, "chunk tasks must tile the element");
+  constexpr int PIECES = (kDfWarps * 1024) / (2 * kDfThreads);   // 16-byte pieces per thread in a chunk task (= 16)
+  static_assert(G >= 1 && NCH % G == 0, "chunk tasks must tile the element");
 
-  __shared__ __align__(16) uint32_t U[4 * kDfUnit];
+  __shared__ __align__(16) uint32_t U[kDfWarps * kDfUnit];
   __shared__ unsigned s_task;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned* cnt_a = ctr + kDfCtrHead;           // finished first-kind tasks per element
   unsigned* cnt_b = cnt_a + batch;              // finished second-kind tasks per element
-  const int64_t groups = batch + P.lag;
-  const unsigned total = (unsigned)(groups * (NT_A + NT_B));
+  const unsigned total = (unsigned)((batch + P.lag) * (NT_A + NT_B));
+  typedef TaskId<NT_A, NT_B> Tid;
+
+  // what a task waits for: first kind -> its ring slot is free (the element `ring` before it is consumed);
+  // second kind -> every first-kind task of its element is done.  Counters only grow, so a value read early
+  // that already satisfies the condition stays valid.
+  auto dep_ptr = [&](const Tid& id) -> const unsigned* {
+    if (!id.valid) return nullptr;
+    if (id.first) return id.el >= P.ring ? cnt_b + (id.el - P.ring) : nullptr;
+    return cnt_a + id.el;
+  };
+
+  // thread 0 runs two tasks ahead: the atomic that hands out task i+2 and the counter read for task i+1 are in
+  // flight while task i is computed
+  unsigned t_cur = 0, t_next = 0, dep_val = 0;
+  if (tid == 0) {
+    t_cur = atomicAdd(ctr, 1u);
+    t_next = atomicAdd(ctr, 1u);
+    if (t_cur < total) {
+      const Tid id(t_cur, batch, P.lag);
+      const unsigned* dp = dep_ptr(id);
+      dep_val = dp ? ld_acquire(dp) : 0u;
+    }
+  }
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_task = atomicAdd(ctr, 1u);
+    unsigned t_after = 0, dep_next = 0;
+    if (tid == 0) {
+      if (t_cur < total) {
+        const Tid id(t_cur, batch, P.lag);
+        const unsigned* dp = dep_ptr(id);
+        if (dp) {
+          const unsigned target = id.first ? NT_B : NT_A;
+          while (dep_val < target) { __nanosleep(64); dep_val = ld_acquire(dp); }
+        }
+      }
+      s_task = t_cur;
+    }
     __syncthreads();
     const unsigned t = s_task;
     if (t >= total) break;
-    const int64_t grp = t / (NT_A + NT_B);
-    const int r = (int)(t - grp * (NT_A + NT_B));
-    const bool first = r < NT_A;
-    const int64_t el = first ? grp : grp - P.lag;
-    if (el < 0 || el >= batch) continue;
-    const int task = first ? r : r - NT_A;
-    const bool chunk_task = (first != INV);
+    if (tid == 0) {
+      t_after = atomicAdd(ctr, 1u);
+      if (t_next < total) {
+        const Tid idn(t_next, batch, P.lag);
+        const unsigned* dp = dep_ptr(idn);
+        dep_next = dp ? ld_acquire(dp) : 0u;
+      }
+    }
+    const Tid id(t, batch, P.lag);
+    if (id.valid) {
+    const int64_t el = id.el;
+    const int task = id.task;
+    const bool chunk_task = (id.first != INV);
     uint32_t* slot = ring + (size_t)(el % P.ring) * ((size_t)K * N);
     int64_t* ebase = y + (size_t)el * ((size_t)K * N);
-
-    if (first) {
-      if (el >= P.ring) wait_counter(cnt_b + (el - P.ring), NT_B);     // slot free: its previous element is consumed
-    } else {
-      wait_counter(cnt_a + el, NT_A);                                    // all first-kind tasks of this element done
-    }
+    unsigned* done = id.first ? cnt_a + el : cnt_b + el;
 
     if (chunk_task) {
       // ---------------------------------------------------------------- chunk task: bits [0,10)
       const int chunk0 = task * G;
-      int64_t* gpiece = ebase + (size_t)chunk0 * 1024 * K;              // 4096 contiguous int64
+      int64_t* gpiece = ebase + (size_t)chunk0 * 1024 * K;              // kDfWarps * 1024 contiguous int64
       const int unit = warp;                                             // (chunk_in_task, limb) of this warp
       const int uch = unit / K, limb = unit % K;
       uint32_t* Uu = U + unit * kDfUnit;
       const DfLimb& L = P.limb[limb];
       const Mont M{L.q, L.q2, L.qinv};
       uint32_t* srow = slot + (size_t)limb * N + (size_t)(chunk0 + uch) * 1024 + lane;
+      // the pieces of this thread: int64 pair (2 tid + 2 kDfThreads i, +1); the limb of each half is fixed per thread
+      const int l0 = (2 * tid) % K, l1 = K == 1 ? 0 : l0 + 1;
       if (!INV) {
-        // coalesced load of the piece, limbs de-interleaved into the 4 units
+        const uint32_t q0 = P.limb[l0].q, q1 = P.limb[l1].q;
+        // coalesced load of the piece, limbs de-interleaved into the units
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-          longlong2 raw[8];
+          longlong2 raw[PIECES / 2];
+          uint32_t hi_or = 0, max0 = 0, max1 = 0;
 #pragma unroll
-          for (int i = 0; i < 8; i++) raw[i] = __ldcs(reinterpret_cast<const longlong2*>(gpiece) + tid + kDfThreads * (half * 8 + i));
+          for (int i = 0; i < PIECES / 2; i++) {
+            raw[i] = __ldcs(reinterpret_cast<const longlong2*>(gpiece) + tid + kDfThreads * (half * (PIECES / 2) + i));
+            hi_or |= (uint32_t)((uint64_t)raw[i].x >> 32) | (uint32_t)((uint64_t)raw[i].y >> 32);
+            max0 = max(max0, (uint32_t)raw[i].x);
+            max1 = max(max1, (uint32_t)raw[i].y);
+          }
+          const bool odd_input = hi_or != 0 || max0 >= q0 || max1 >= q1;   // outside the Haskell contract
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int v0 = 2 * (tid + kDfThreads * (half * 8 + i));      // index of the first int64 of the pair
-            const int c = v0 / K, l0 = v0 % K;
+          for (int i = 0; i < PIECES / 2; i++) {
+            const int v0 = 2 * (tid + kDfThreads * (half * (PIECES / 2) + i));
+            const int c = v0 / K;
             const int cc = c & 1023, u0 = (c >> 10) * K + l0;
-            const uint32_t q0 = P.limb[l0].q;
-            const uint32_t x0 = (uint64_t)raw[i].x < (uint64_t)q0 ? (uint32_t)raw[i].x : df_reduce_any64(raw[i].x, q0);
+            uint32_t x0 = (uint32_t)raw[i].x, x1 = (uint32_t)raw[i].y;
+            if (odd_input) { x0 = df_reduce_any64(raw[i].x, q0); x1 = df_reduce_any64(raw[i].y, q1); }
             U[u0 * kDfUnit + cc + (cc >> 5)] = x0;
-            if (K == 1) {
-              const uint32_t x1 = (uint64_t)raw[i].y < (uint64_t)q0 ? (uint32_t)raw[i].y : df_reduce_any64(raw[i].y, q0);
-              U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] = x1;
-            } else {
-              const uint32_t q1 = P.limb[l0 + 1].q;
-              const uint32_t x1 = (uint64_t)raw[i].y < (uint64_t)q1 ? (uint32_t)raw[i].y : df_reduce_any64(raw[i].y, q1);
-              U[(u0 + 1) * kDfUnit + cc + (cc >> 5)] = x1;
-            }
+            if (K == 1) U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] = x1;
+            else U[(u0 + 1) * kDfUnit + cc + (cc >> 5)] = x1;
           }
         }
         __syncthreads();
+#if LOLB_DF_SWITCH
         unit_rounds_0_4_any<false>(limb, Uu, P, lane);
+#else
+        unit_rounds_0_4_rt<false>(limb, Uu, P, lane);
+#endif
         __syncwarp();
         // rounds 5-9: lane owns coefficients lane + 32 j
         {
@@ -265,7 +342,6 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
 #pragma unroll
           for (int j = 0; j < 32; j++) srow[32 * j] = v[j];
         }
-        signal_counter(cnt_a + el);
       } else {
         {
           uint32_t v[32];
@@ -277,19 +353,22 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
           for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
         }
         __syncwarp();
+#if LOLB_DF_SWITCH
         unit_rounds_0_4_any<true>(limb, Uu, P, lane);
+#else
+        unit_rounds_0_4_rt<true>(limb, Uu, P, lane);
+#endif
         __syncthreads();
         // canonical residues -> interleaved int64, coalesced 128-bit stores
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < PIECES; i++) {
           const int v0 = 2 * (tid + kDfThreads * i);
-          const int c = v0 / K, l0 = v0 % K;
+          const int c = v0 / K;
           const int cc = c & 1023, u0 = (c >> 10) * K + l0;
           const uint32_t x0 = U[u0 * kDfUnit + cc + (cc >> 5)];
           const uint32_t x1 = K == 1 ? U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] : U[(u0 + 1) * kDfUnit + cc + (cc >> 5)];
           __stcs(reinterpret_cast<longlong2*>(gpiece) + tid + kDfThreads * i, make_longlong2((int64_t)x0, (int64_t)x1));
         }
-        signal_counter(cnt_b + el);
       }
     } else {
       // ---------------------------------------------------------------- column task: bits [10, 10 + TOP)
@@ -307,7 +386,6 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
         ct_rounds<TOP, false>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
 #pragma unroll
         for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
-        signal_counter(cnt_b + el);
       } else {
         uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
@@ -324,9 +402,17 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
         gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
 #pragma unroll
         for (int j = 0; j < NV; j++) scol[1024 * j] = v[j];
-        signal_counter(cnt_a + el);
       }
     }
+    __syncthreads();                             // the task's stores are done (and U may be overwritten)
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(done, 1u);
+    }
+    } else {
+      __syncthreads();
+    }
+    t_cur = t_next; t_next = t_after; dep_val = dep_next;
   }
 }
 
@@ -350,6 +436,7 @@ bool shape_ok(const lolb_plan* pl)
   const int e = pl->pe[0].exponent;
   if (e < 13 || e > 16) return false;
   if (pl->k != 1 && pl->k != 2 && pl->k != 4) return false;
+  if (((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // chunk tasks of kDfWarps units must tile the element
   for (int64_t q : pl->qs) if (!(q & 1) || 4 * (uint64_t)q >= ((uint64_t)1 << 32)) return false;
   return true;
 }
@@ -357,15 +444,27 @@ bool shape_ok(const lolb_plan* pl)
 template <bool INV, int K, int TOP>
 int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
+  if constexpr (((1 << TOP) * K) % kDfWarps != 0) return LOLB_FUSED_UNAVAILABLE;
+  else {
   static int per_sm = 0;
   if (!per_sm) {
     LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_df<INV, K, TOP>, kDfThreads, 0));
     if (per_sm < 1) per_sm = 1;
   }
   DfParams P = INV ? F->inv : F->fwd;
+  const int64_t tasks_per_el = (int64_t)(((1 << TOP) * K) / kDfWarps + (1024 * K) / kDfThreads);
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > batch * tasks_per_el) grid = batch * tasks_per_el;
+  // every CTA holds up to 3 tasks (one running, two claimed ahead): the second kind must trail the first by more
+  // than that window or it would wait for tasks that have not started, and a slot is reused a window after that
+  const int64_t window = (3 * grid + tasks_per_el - 1) / tasks_per_el;
+  P.lag = (int32_t)(window + 2);
+  P.ring = 2 * P.lag + 2;
   const char* s;
   if ((s = getenv("LOLB_DF_RING")) != nullptr && atoi(s) > 0) P.ring = atoi(s);
   if ((s = getenv("LOLB_DF_LAG")) != nullptr && atoi(s) > 0) P.lag = atoi(s);
+  if (P.ring > batch) P.ring = (int32_t)batch;
+  if (P.ring < 2) P.ring = 2;
   if (P.lag >= P.ring) P.lag = P.ring - 1;
   const size_t slot_bytes = (size_t)K * pl->n * sizeof(uint32_t);
   const size_t ring_bytes = (size_t)P.ring * slot_bytes;
@@ -375,14 +474,12 @@ int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t bat
   uint32_t* ring = (uint32_t*)pl->d_ws;
   unsigned* ctr = (unsigned*)((char*)pl->d_ws + ring_bytes);
   LOLB_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
-  const int64_t tasks_per_el = (int64_t)(((1 << TOP) * K) / 4 + (1024 * K) / kDfThreads);
-  int64_t grid = (int64_t)pl->num_sms * per_sm;
-  if (grid > batch * tasks_per_el) grid = batch * tasks_per_el;
   k_pow2_df<INV, K, TOP><<<(int)grid, kDfThreads, 0, st>>>(y, batch, P, ring, ctr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_pow2_df");
   count_launch();
   return LOLB_OK;
+  }
 }
 
 template <bool INV, int K>
