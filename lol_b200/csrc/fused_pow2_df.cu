@@ -148,6 +148,12 @@ __device__ __forceinline__ void unit_rounds_0_4_any(int limb, uint32_t* Uu, cons
 #ifndef LOLB_DF_NW
 #define LOLB_DF_NW 4            // warps per CTA = (chunk, limb) units per chunk task
 #endif
+#ifndef LOLB_DF_MINB
+#define LOLB_DF_MINB (640 / (32 * LOLB_DF_NW))   // CTAs per SM the register allocation must allow
+#endif
+#ifndef LOLB_DF_PREFETCH
+#define LOLB_DF_PREFETCH 1
+#endif
 #ifndef LOLB_DF_SWITCH
 #define LOLB_DF_SWITCH 0        // 1: rounds 0-4 specialised per limb (twiddles as constant-bank operands); 0: one copy, LDC
 #endif
@@ -207,7 +213,7 @@ struct TaskId {
 
 // K = tupSize (1, 2 or 4); TOP = e - 11 = rounds above bit 10 (2..5)
 template <bool INV, int K, int TOP>
-__global__ void __launch_bounds__(kDfThreads, 512 / kDfThreads)
+__global__ void __launch_bounds__(kDfThreads, LOLB_DF_MINB)
 k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring,
           unsigned* __restrict__ ctr)
 {
@@ -223,7 +229,6 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
   static_assert(G >= 1 && NCH % G == 0, "chunk tasks must tile the element");
 
   __shared__ __align__(16) uint32_t U[kDfWarps * kDfUnit];
-  __shared__ unsigned s_task;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned* cnt_a = ctr + kDfCtrHead;           // finished first-kind tasks per element
@@ -240,44 +245,69 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
     return cnt_a + id.el;
   };
 
-  // thread 0 runs two tasks ahead: the atomic that hands out task i+2 and the counter read for task i+1 are in
-  // flight while task i is computed
-  unsigned t_cur = 0, t_next = 0, dep_val = 0;
-  if (tid == 0) {
-    t_cur = atomicAdd(ctr, 1u);
-    t_next = atomicAdd(ctr, 1u);
-    if (t_cur < total) {
-      const Tid id(t_cur, batch, P.lag);
-      const unsigned* dp = dep_ptr(id);
-      dep_val = dp ? ld_acquire(dp) : 0u;
-    }
-  }
-
-  for (;;) {
-    unsigned t_after = 0, dep_next = 0;
-    if (tid == 0) {
-      if (t_cur < total) {
-        const Tid id(t_cur, batch, P.lag);
-        const unsigned* dp = dep_ptr(id);
-        if (dp) {
-          const unsigned target = id.first ? NT_B : NT_A;
-          while (dep_val < target) { __nanosleep(64); dep_val = ld_acquire(dp); }
-        }
+  // Thread 0 runs two tasks ahead: the atomic that hands out task i+2, the counter read for task i+1 and the L2
+  // prefetch of task i+1's input are in flight while task i is computed.  One CTA barrier per task hands over
+  // (task, ready) through a double-buffered mailbox; the completion signal of task i (fence + atomic) is issued by
+  // thread 0 AFTER that barrier, while the other threads already load task i+1.  `ready` = the dependency was
+  // already satisfied when it was read ahead (the normal case: counters only grow); otherwise thread 0 signals
+  // first (so it never waits while holding back its own completion) and then spins.
+  __shared__ unsigned s_task[2], s_ready[2];
+  auto dep_target = [&](const Tid& id) -> unsigned { return id.first ? NT_B : NT_A; };
+  // L2 prefetch of a task's HBM input, issued by warp 0 one task ahead (lane j takes row j of a column task)
+  auto prefetch_input = [&](const Tid& id) {
+    if (!LOLB_DF_PREFETCH || INV || !id.valid) return;      // measured: +1 % forward, -3 % inverse (strided rows)
+    const int64_t* eb = y + (size_t)id.el * ((size_t)K * N);
+    if (id.first != INV) {
+      if (!INV && lane == 0) {       // forward chunk task: one contiguous piece
+        const int64_t* g = eb + (size_t)(id.task * G) * 1024 * K;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(g), "r"(kDfWarps * 1024 * 8) : "memory");
       }
-      s_task = t_cur;
+    } else if (INV && lane < NV) {   // inverse column task: NV rows of kDfThreads int64
+      const int64_t* g = eb + (size_t)id.task * kDfThreads + (size_t)1024 * K * lane;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(g), "r"(kDfThreads * 8) : "memory");
     }
-    __syncthreads();
-    const unsigned t = s_task;
+  };
+  unsigned t_next = 0;
+  unsigned* pending = nullptr;                  // thread 0: completion counter of the task that just ended
+  if (tid == 0) {
+    const unsigned t0 = atomicAdd(ctr, 1u);
+    t_next = atomicAdd(ctr, 1u);
+    s_task[0] = t0;
+    s_ready[0] = 0u;
+  }
+  __syncthreads();
+
+  for (int it = 0;; it++) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    const unsigned t = s_task[cur];
     if (t >= total) break;
+    const Tid id(t, batch, P.lag);
+    if (tid == 0 && pending) {
+      __threadfence();
+      atomicAdd(pending, 1u);
+      pending = nullptr;
+    }
+    if (!s_ready[cur]) {
+      if (tid == 0) {
+        const unsigned* dp = dep_ptr(id);
+        if (dp) while (ld_acquire(dp) < dep_target(id)) __nanosleep(64);
+      }
+      __syncthreads();
+    }
+    unsigned t_after = 0, dep_next = 0, dep_need = 0;
     if (tid == 0) {
       t_after = atomicAdd(ctr, 1u);
+      s_task[nxt] = t_next;
       if (t_next < total) {
         const Tid idn(t_next, batch, P.lag);
         const unsigned* dp = dep_ptr(idn);
-        dep_next = dp ? ld_acquire(dp) : 0u;
+        if (dp) { dep_next = ld_acquire(dp); dep_need = dep_target(idn); }
       }
     }
-    const Tid id(t, batch, P.lag);
+    if (LOLB_DF_PREFETCH && !INV && warp == 0) {
+      const unsigned tn = __shfl_sync(0xffffffffu, t_next, 0);
+      if (tn < total) prefetch_input(Tid(tn, batch, P.lag));
+    }
     if (id.valid) {
     const int64_t el = id.el;
     const int task = id.task;
@@ -404,15 +434,17 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
         for (int j = 0; j < NV; j++) scol[1024 * j] = v[j];
       }
     }
-    __syncthreads();                             // the task's stores are done (and U may be overwritten)
+    if (tid == 0) pending = done;
+    }
     if (tid == 0) {
-      __threadfence();
-      atomicAdd(done, 1u);
+      s_ready[nxt] = dep_next >= dep_need ? 1u : 0u;
+      t_next = t_after;
     }
-    } else {
-      __syncthreads();
-    }
-    t_cur = t_next; t_next = t_after; dep_val = dep_next;
+    __syncthreads();      // the task's stores are issued, U may be overwritten, the mailbox of the next task is visible
+  }
+  if (tid == 0 && pending) {
+    __threadfence();
+    atomicAdd(pending, 1u);
   }
 }
 
