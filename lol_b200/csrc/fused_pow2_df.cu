@@ -148,11 +148,11 @@ __device__ __forceinline__ void unit_rounds_0_4_any(int limb, uint32_t* Uu, cons
 #ifndef LOLB_DF_NW
 #define LOLB_DF_NW 4            // warps per CTA = (chunk, limb) units per chunk task
 #endif
-#ifndef LOLB_DF_MINB
-#define LOLB_DF_MINB (640 / (32 * LOLB_DF_NW))   // CTAs per SM the register allocation must allow
+#ifndef LOLB_DF_STAGE
+#define LOLB_DF_STAGE 0           // 1: first-kind tasks read their HBM input through a TMA-filled staging buffer (measured slower: 4 CTAs/SM instead of 5, copy only one 1.5 us task ahead)
 #endif
-#ifndef LOLB_DF_PREFETCH
-#define LOLB_DF_PREFETCH 1
+#ifndef LOLB_DF_MINB
+#define LOLB_DF_MINB ((LOLB_DF_STAGE ? 512 : 640) / (32 * LOLB_DF_NW))   // CTAs per SM the register allocation must allow
 #endif
 #ifndef LOLB_DF_SWITCH
 #define LOLB_DF_SWITCH 0        // 1: rounds 0-4 specialised per limb (twiddles as constant-bank operands); 0: one copy, LDC
@@ -193,47 +193,94 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
   return v;
 }
 
+// ---- mbarrier + bulk-copy (TMA, 1-D) primitives: the HBM input of a task is copied into a staging buffer by the
+// copy engine one task ahead, so no thread waits on HBM latency
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // task index -> (element, kind, index inside the element); the queue interleaves, per element e, the first-kind
 // tasks of e with the second-kind tasks of e - lag
 template <int NT_A, int NT_B>
 struct TaskId {
-  int64_t el;
-  int task;
+  int el, task;
   bool first, valid;
-  __device__ __forceinline__ TaskId(unsigned t, int64_t batch, int lag)
+  __device__ __forceinline__ TaskId(unsigned t, int batch, int lag)
   {
-    const int64_t grp = t / (unsigned)(NT_A + NT_B);
-    const int r = (int)(t - (unsigned)grp * (unsigned)(NT_A + NT_B));
+    const unsigned grp = t / (unsigned)(NT_A + NT_B);
+    const int r = (int)(t - grp * (unsigned)(NT_A + NT_B));
     first = r < NT_A;
-    el = first ? grp : grp - lag;
+    el = first ? (int)grp : (int)grp - lag;
     task = first ? r : r - NT_A;
     valid = el >= 0 && el < batch;
+  }
+};
+
+template <int K, int TOP>
+struct DfGeom {
+  static constexpr int NCH = 1 << TOP;                 // chunks per limb
+  static constexpr int N = 1024 << TOP;                // coefficients per limb
+  static constexpr int G = kDfWarps / K;               // chunks per chunk task (kDfWarps units of 1024 residues)
+  static constexpr int NT_CHUNK = NCH / G;             // chunk tasks per element
+  static constexpr int NT_COL = (1024 * K) / kDfThreads;   // column tasks per element
+  static constexpr int NV = 1 << TOP;                  // residues per thread in a column task
+  static constexpr int PIECES = (kDfWarps * 1024) / (2 * kDfThreads);   // 16-byte pieces per thread in a chunk task
+  static constexpr int STEP = (2 * kDfThreads) / K;    // coefficients between consecutive pieces of a thread
+  static constexpr int CHUNK_BYTES = kDfWarps * 1024 * 8;
+  static constexpr int COL_BYTES = NV * kDfThreads * 8;
+  static constexpr int STAGE_BYTES = LOLB_DF_STAGE ? (CHUNK_BYTES > COL_BYTES ? CHUNK_BYTES : COL_BYTES) : 0;
+  static constexpr int SMEM_BYTES = STAGE_BYTES + kDfWarps * kDfUnit * 4 + 64;
+  // shared-memory word of piece ii of a thread, relative to  U + l0 * kDfUnit + c0 + (c0 >> 5),  c0 = 2 tid / K
+  static __host__ __device__ constexpr int piece_off(int ii)
+  {
+    return ((STEP * ii) >> 10) * K * kDfUnit + ((STEP * ii) & 1023) + (((STEP * ii) & 1023) >> 5);
   }
 };
 
 // K = tupSize (1, 2 or 4); TOP = e - 11 = rounds above bit 10 (2..5)
 template <bool INV, int K, int TOP>
 __global__ void __launch_bounds__(kDfThreads, LOLB_DF_MINB)
-k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring,
+k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring,
           unsigned* __restrict__ ctr)
 {
-  constexpr int NCH = 1 << TOP;                 // chunks per limb
-  constexpr int N = 1024 << TOP;                // coefficients per limb
-  constexpr int G = kDfWarps / K;               // chunks per chunk task (kDfWarps units of 1024 residues)
-  constexpr int NT_CHUNK = NCH / G;             // chunk tasks per element
-  constexpr int NT_COL = (1024 * K) / kDfThreads;   // column tasks per element
-  constexpr int NT_A = INV ? NT_COL : NT_CHUNK;     // first kind
-  constexpr int NT_B = INV ? NT_CHUNK : NT_COL;     // second kind
-  constexpr int NV = 1 << TOP;                  // residues per thread in a column task
-  constexpr int PIECES = (kDfWarps * 1024) / (2 * kDfThreads);   // 16-byte pieces per thread in a chunk task (= 16)
-  static_assert(G >= 1 && NCH % G == 0, "chunk tasks must tile the element");
+  typedef DfGeom<K, TOP> Geo;
+  constexpr int N = Geo::N, G = Geo::G, NV = Geo::NV, PIECES = Geo::PIECES;
+  constexpr int NT_A = INV ? Geo::NT_COL : Geo::NT_CHUNK;     // first kind (reads the element from HBM)
+  constexpr int NT_B = INV ? Geo::NT_CHUNK : Geo::NT_COL;     // second kind (writes the element to HBM)
+  constexpr bool STAGE = LOLB_DF_STAGE != 0;
+  static_assert(G >= 1 && Geo::NCH % G == 0, "chunk tasks must tile the element");
+  static_assert(Geo::STEP % 32 == 0 && 1024 % Geo::STEP == 0, "piece addressing");
 
-  __shared__ __align__(16) uint32_t U[kDfWarps * kDfUnit];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* stage = smem_raw;                                       // HBM input of the current first-kind task
+  uint32_t* U = reinterpret_cast<uint32_t*>(smem_raw + Geo::STAGE_BYTES);   // kDfWarps units of u32 residues
+  unsigned* mail = U + kDfWarps * kDfUnit;                               // [2][4]: task, ready, element, ring slot
+  uint64_t* bar = reinterpret_cast<uint64_t*>(mail + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned* cnt_a = ctr + kDfCtrHead;           // finished first-kind tasks per element
   unsigned* cnt_b = cnt_a + batch;              // finished second-kind tasks per element
-  const unsigned total = (unsigned)((batch + P.lag) * (NT_A + NT_B));
+  const unsigned total = (unsigned)(batch + P.lag) * (unsigned)(NT_A + NT_B);
   typedef TaskId<NT_A, NT_B> Tid;
 
   // what a task waits for: first kind -> its ring slot is free (the element `ring` before it is consumed);
@@ -244,42 +291,50 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
     if (id.first) return id.el >= P.ring ? cnt_b + (id.el - P.ring) : nullptr;
     return cnt_a + id.el;
   };
-
-  // Thread 0 runs two tasks ahead: the atomic that hands out task i+2, the counter read for task i+1 and the L2
-  // prefetch of task i+1's input are in flight while task i is computed.  One CTA barrier per task hands over
-  // (task, ready) through a double-buffered mailbox; the completion signal of task i (fence + atomic) is issued by
-  // thread 0 AFTER that barrier, while the other threads already load task i+1.  `ready` = the dependency was
-  // already satisfied when it was read ahead (the normal case: counters only grow); otherwise thread 0 signals
-  // first (so it never waits while holding back its own completion) and then spins.
-  __shared__ unsigned s_task[2], s_ready[2];
   auto dep_target = [&](const Tid& id) -> unsigned { return id.first ? NT_B : NT_A; };
-  // L2 prefetch of a task's HBM input, issued by warp 0 one task ahead (lane j takes row j of a column task)
-  auto prefetch_input = [&](const Tid& id) {
-    if (!LOLB_DF_PREFETCH || INV || !id.valid) return;      // measured: +1 % forward, -3 % inverse (strided rows)
-    const int64_t* eb = y + (size_t)id.el * ((size_t)K * N);
-    if (id.first != INV) {
-      if (!INV && lane == 0) {       // forward chunk task: one contiguous piece
-        const int64_t* g = eb + (size_t)(id.task * G) * 1024 * K;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(g), "r"(kDfWarps * 1024 * 8) : "memory");
+
+  // warp 0: start the copy of task tn's HBM input into `stage` (first-kind tasks only; their input is never
+  // written before all of them are done, so it can be fetched before the task's own dependency is met)
+  auto stage_issue = [&](unsigned tn) {
+    if (!STAGE || tn >= total) return;
+    const Tid idn(tn, batch, P.lag);
+    if (!idn.valid || !idn.first) return;
+    const int64_t* eb = y + (size_t)idn.el * ((size_t)K * N);
+    if (!INV) {
+      if (lane == 0) {
+        mbar_expect_tx(bar, Geo::CHUNK_BYTES);
+        bulk_g2s(stage, eb + (size_t)(idn.task * G) * 1024 * K, Geo::CHUNK_BYTES, bar);
       }
-    } else if (INV && lane < NV) {   // inverse column task: NV rows of kDfThreads int64
-      const int64_t* g = eb + (size_t)id.task * kDfThreads + (size_t)1024 * K * lane;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(g), "r"(kDfThreads * 8) : "memory");
+    } else {
+      if (lane == 0) mbar_expect_tx(bar, Geo::COL_BYTES);
+      __syncwarp();
+      if (lane < NV) bulk_g2s(stage + lane * (kDfThreads * 8), eb + (size_t)idn.task * kDfThreads + (size_t)1024 * K * lane, kDfThreads * 8, bar);
     }
   };
+
+  // Thread 0 runs two tasks ahead: the atomic that hands out task i+2, the counter read for task i+1 and the copy
+  // of task i+1's input are in flight while task i is computed.  One CTA barrier per task hands over the decoded
+  // task through a double-buffered mailbox; the completion signal of task i (fence + atomic) is issued by thread 0
+  // AFTER that barrier, while the other threads already work on task i+1.  `ready` = the dependency was already
+  // satisfied when it was read ahead (the normal case); otherwise thread 0 signals first (so it never waits while
+  // holding back its own completion) and then spins.
   unsigned t_next = 0;
   unsigned* pending = nullptr;                  // thread 0: completion counter of the task that just ended
+  unsigned stage_phase = 0;
   if (tid == 0) {
     const unsigned t0 = atomicAdd(ctr, 1u);
     t_next = atomicAdd(ctr, 1u);
-    s_task[0] = t0;
-    s_ready[0] = 0u;
+    const Tid id0(t0, batch, P.lag);
+    mail[0] = t0; mail[1] = 0u; mail[2] = (unsigned)id0.el; mail[3] = id0.valid ? (unsigned)id0.el % (unsigned)P.ring : 0u;
+    if (STAGE) mbar_init(bar, 1);
   }
   __syncthreads();
+  if (warp == 0) stage_issue(__shfl_sync(0xffffffffu, mail[0], 0));
 
   for (int it = 0;; it++) {
-    const int cur = it & 1, nxt = cur ^ 1;
-    const unsigned t = s_task[cur];
+    const unsigned* mc = mail + 4 * (it & 1);
+    unsigned* mn = mail + 4 * ((it & 1) ^ 1);
+    const unsigned t = mc[0];
     if (t >= total) break;
     const Tid id(t, batch, P.lag);
     if (tid == 0 && pending) {
@@ -287,7 +342,7 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
       atomicAdd(pending, 1u);
       pending = nullptr;
     }
-    if (!s_ready[cur]) {
+    if (!mc[1]) {
       if (tid == 0) {
         const unsigned* dp = dep_ptr(id);
         if (dp) while (ld_acquire(dp) < dep_target(id)) __nanosleep(64);
@@ -297,22 +352,24 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
     unsigned t_after = 0, dep_next = 0, dep_need = 0;
     if (tid == 0) {
       t_after = atomicAdd(ctr, 1u);
-      s_task[nxt] = t_next;
+      mn[0] = t_next;
       if (t_next < total) {
         const Tid idn(t_next, batch, P.lag);
+        mn[2] = (unsigned)idn.el;
+        mn[3] = idn.valid ? (unsigned)idn.el % (unsigned)P.ring : 0u;
         const unsigned* dp = dep_ptr(idn);
         if (dp) { dep_next = ld_acquire(dp); dep_need = dep_target(idn); }
       }
     }
-    if (LOLB_DF_PREFETCH && !INV && warp == 0) {
-      const unsigned tn = __shfl_sync(0xffffffffu, t_next, 0);
-      if (tn < total) prefetch_input(Tid(tn, batch, P.lag));
-    }
+    const bool staged = STAGE && id.valid && id.first;
+    // the staging buffer is idle during a second-kind task: fetch the next task's input right away
+    if (!staged && warp == 0) stage_issue(__shfl_sync(0xffffffffu, t_next, 0));
+
     if (id.valid) {
-    const int64_t el = id.el;
+    const int el = id.el;
     const int task = id.task;
     const bool chunk_task = (id.first != INV);
-    uint32_t* slot = ring + (size_t)(el % P.ring) * ((size_t)K * N);
+    uint32_t* slot = ring + (size_t)mc[3] * ((size_t)K * N);
     int64_t* ebase = y + (size_t)el * ((size_t)K * N);
     unsigned* done = id.first ? cnt_a + el : cnt_b + el;
 
@@ -326,18 +383,24 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
       const DfLimb& L = P.limb[limb];
       const Mont M{L.q, L.q2, L.qinv};
       uint32_t* srow = slot + (size_t)limb * N + (size_t)(chunk0 + uch) * 1024 + lane;
-      // the pieces of this thread: int64 pair (2 tid + 2 kDfThreads i, +1); the limb of each half is fixed per thread
-      const int l0 = (2 * tid) % K, l1 = K == 1 ? 0 : l0 + 1;
+      // the pieces of this thread: int64 pairs (2 tid + 2 kDfThreads ii, +1); the limb of each half is fixed per
+      // thread and the shared-memory word of piece ii is a compile-time offset from `ubase`
+      const int l0 = (2 * tid) % K, c0 = (2 * tid) / K;
+      uint32_t* ubase = U + l0 * kDfUnit + c0 + (c0 >> 5);
+      constexpr int second = K == 1 ? 1 : kDfUnit;                      // the other half: next coefficient / next limb
       if (!INV) {
-        const uint32_t q0 = P.limb[l0].q, q1 = P.limb[l1].q;
-        // coalesced load of the piece, limbs de-interleaved into the units
+        const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
+        const longlong2* src = STAGE ? reinterpret_cast<const longlong2*>(stage) + tid : reinterpret_cast<const longlong2*>(gpiece) + tid;
+        if (STAGE) { mbar_wait(bar, stage_phase); stage_phase ^= 1u; }
+        // coalesced read of the piece, limbs de-interleaved into the units
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           longlong2 raw[PIECES / 2];
           uint32_t hi_or = 0, max0 = 0, max1 = 0;
 #pragma unroll
           for (int i = 0; i < PIECES / 2; i++) {
-            raw[i] = __ldcs(reinterpret_cast<const longlong2*>(gpiece) + tid + kDfThreads * (half * (PIECES / 2) + i));
+            const int ii = half * (PIECES / 2) + i;
+            raw[i] = STAGE ? src[kDfThreads * ii] : __ldcs(src + kDfThreads * ii);
             hi_or |= (uint32_t)((uint64_t)raw[i].x >> 32) | (uint32_t)((uint64_t)raw[i].y >> 32);
             max0 = max(max0, (uint32_t)raw[i].x);
             max1 = max(max1, (uint32_t)raw[i].y);
@@ -345,17 +408,15 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
           const bool odd_input = hi_or != 0 || max0 >= q0 || max1 >= q1;   // outside the Haskell contract
 #pragma unroll
           for (int i = 0; i < PIECES / 2; i++) {
-            const int v0 = 2 * (tid + kDfThreads * (half * (PIECES / 2) + i));
-            const int c = v0 / K;
-            const int cc = c & 1023, u0 = (c >> 10) * K + l0;
+            const int ii = half * (PIECES / 2) + i;
             uint32_t x0 = (uint32_t)raw[i].x, x1 = (uint32_t)raw[i].y;
             if (odd_input) { x0 = df_reduce_any64(raw[i].x, q0); x1 = df_reduce_any64(raw[i].y, q1); }
-            U[u0 * kDfUnit + cc + (cc >> 5)] = x0;
-            if (K == 1) U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] = x1;
-            else U[(u0 + 1) * kDfUnit + cc + (cc >> 5)] = x1;
+            ubase[Geo::piece_off(ii)] = x0;
+            ubase[Geo::piece_off(ii) + second] = x1;
           }
         }
         __syncthreads();
+        if (STAGE && warp == 0) stage_issue(__shfl_sync(0xffffffffu, t_next, 0));      // staging buffer is free again
 #if LOLB_DF_SWITCH
         unit_rounds_0_4_any<false>(limb, Uu, P, lane);
 #else
@@ -391,13 +452,9 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
         __syncthreads();
         // canonical residues -> interleaved int64, coalesced 128-bit stores
 #pragma unroll
-        for (int i = 0; i < PIECES; i++) {
-          const int v0 = 2 * (tid + kDfThreads * i);
-          const int c = v0 / K;
-          const int cc = c & 1023, u0 = (c >> 10) * K + l0;
-          const uint32_t x0 = U[u0 * kDfUnit + cc + (cc >> 5)];
-          const uint32_t x1 = K == 1 ? U[u0 * kDfUnit + (cc + 1) + ((cc + 1) >> 5)] : U[(u0 + 1) * kDfUnit + cc + (cc >> 5)];
-          __stcs(reinterpret_cast<longlong2*>(gpiece) + tid + kDfThreads * i, make_longlong2((int64_t)x0, (int64_t)x1));
+        for (int ii = 0; ii < PIECES; ii++) {
+          const uint32_t x0 = ubase[Geo::piece_off(ii)], x1 = ubase[Geo::piece_off(ii) + second];
+          __stcs(reinterpret_cast<longlong2*>(gpiece) + tid + kDfThreads * ii, make_longlong2((int64_t)x0, (int64_t)x1));
         }
       }
     } else {
@@ -417,17 +474,23 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
 #pragma unroll
         for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
       } else {
+        const int64_t* srcw = reinterpret_cast<const int64_t*>(stage) + tid;
+        if (STAGE) { mbar_wait(bar, stage_phase); stage_phase ^= 1u; }
         uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-          const int64_t raw = __ldcs(gcol + (size_t)1024 * K * j);
+          const int64_t raw = STAGE ? srcw[kDfThreads * j] : __ldcs(gcol + (size_t)1024 * K * j);
           v[j] = (uint32_t)raw;
           hi_or |= (uint32_t)((uint64_t)raw >> 32);
           lo_max = max(lo_max, v[j]);
         }
         if (hi_or != 0 || lo_max >= L.q) {      // outside the Haskell contract: reduce like the reference's c % q
 #pragma unroll
-          for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(gcol[(size_t)1024 * K * j], L.q);
+          for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(STAGE ? srcw[kDfThreads * j] : gcol[(size_t)1024 * K * j], L.q);
+        }
+        if (STAGE) {
+          __syncthreads();
+          if (warp == 0) stage_issue(__shfl_sync(0xffffffffu, t_next, 0));             // staging buffer is free again
         }
         gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
 #pragma unroll
@@ -437,7 +500,7 @@ k_pow2_df(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPara
     if (tid == 0) pending = done;
     }
     if (tid == 0) {
-      s_ready[nxt] = dep_next >= dep_need ? 1u : 0u;
+      mn[1] = dep_next >= dep_need ? 1u : 0u;
       t_next = t_after;
     }
     __syncthreads();      // the task's stores are issued, U may be overwritten, the mailbox of the next task is visible
@@ -478,9 +541,11 @@ int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t bat
 {
   if constexpr (((1 << TOP) * K) % kDfWarps != 0) return LOLB_FUSED_UNAVAILABLE;
   else {
+  typedef DfGeom<K, TOP> Geo;
   static int per_sm = 0;
   if (!per_sm) {
-    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_df<INV, K, TOP>, kDfThreads, 0));
+    LOLB_CUDA(cudaFuncSetAttribute(k_pow2_df<INV, K, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo::SMEM_BYTES));
+    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_df<INV, K, TOP>, kDfThreads, Geo::SMEM_BYTES));
     if (per_sm < 1) per_sm = 1;
   }
   DfParams P = INV ? F->inv : F->fwd;
@@ -506,7 +571,7 @@ int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t bat
   uint32_t* ring = (uint32_t*)pl->d_ws;
   unsigned* ctr = (unsigned*)((char*)pl->d_ws + ring_bytes);
   LOLB_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
-  k_pow2_df<INV, K, TOP><<<(int)grid, kDfThreads, 0, st>>>(y, batch, P, ring, ctr);
+  k_pow2_df<INV, K, TOP><<<(int)grid, kDfThreads, Geo::SMEM_BYTES, st>>>(y, (int)batch, P, ring, ctr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_pow2_df");
   count_launch();
