@@ -392,27 +392,29 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
         const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
         const longlong2* src = STAGE ? reinterpret_cast<const longlong2*>(stage) + tid : reinterpret_cast<const longlong2*>(gpiece) + tid;
         if (STAGE) { mbar_wait(bar, stage_phase); stage_phase ^= 1u; }
-        // coalesced read of the piece, limbs de-interleaved into the units
+        // coalesced read of the piece (all 16-byte loads in flight at once), limbs de-interleaved into the units
+        {
+          longlong2 raw[PIECES];
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          longlong2 raw[PIECES / 2];
+          for (int ii = 0; ii < PIECES; ii++) raw[ii] = STAGE ? src[kDfThreads * ii] : __ldcs(src + kDfThreads * ii);
           uint32_t hi_or = 0, max0 = 0, max1 = 0;
 #pragma unroll
-          for (int i = 0; i < PIECES / 2; i++) {
-            const int ii = half * (PIECES / 2) + i;
-            raw[i] = STAGE ? src[kDfThreads * ii] : __ldcs(src + kDfThreads * ii);
-            hi_or |= (uint32_t)((uint64_t)raw[i].x >> 32) | (uint32_t)((uint64_t)raw[i].y >> 32);
-            max0 = max(max0, (uint32_t)raw[i].x);
-            max1 = max(max1, (uint32_t)raw[i].y);
+          for (int ii = 0; ii < PIECES; ii++) {
+            hi_or |= (uint32_t)((uint64_t)raw[ii].x >> 32) | (uint32_t)((uint64_t)raw[ii].y >> 32);
+            max0 = max(max0, (uint32_t)raw[ii].x);
+            max1 = max(max1, (uint32_t)raw[ii].y);
+            ubase[Geo::piece_off(ii)] = (uint32_t)raw[ii].x;
+            ubase[Geo::piece_off(ii) + second] = (uint32_t)raw[ii].y;
           }
-          const bool odd_input = hi_or != 0 || max0 >= q0 || max1 >= q1;   // outside the Haskell contract
-#pragma unroll
-          for (int i = 0; i < PIECES / 2; i++) {
-            const int ii = half * (PIECES / 2) + i;
-            uint32_t x0 = (uint32_t)raw[i].x, x1 = (uint32_t)raw[i].y;
-            if (odd_input) { x0 = df_reduce_any64(raw[i].x, q0); x1 = df_reduce_any64(raw[i].y, q1); }
-            ubase[Geo::piece_off(ii)] = x0;
-            ubase[Geo::piece_off(ii) + second] = x1;
+          if (hi_or != 0 || max0 >= q0 || max1 >= q1) {
+            // outside the Haskell contract (values not in [0,q)): redo this thread's pieces like the reference's c % q
+#pragma unroll 1
+            for (int ii = 0; ii < PIECES; ii++) {
+              const longlong2 r = src[kDfThreads * ii];
+              const int off = Geo::piece_off(ii);
+              ubase[off] = df_reduce_any64(r.x, q0);
+              ubase[off + second] = df_reduce_any64(r.y, q1);
+            }
           }
         }
         __syncthreads();
