@@ -219,6 +219,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// exchange-ring accesses: L2 only (the reader is another SM), optionally tagged evict_last so the ring stays in L2
+// while the streamed element data (ld.cs / st.cs) passes through
+#ifndef LOLB_DF_L2HINT
+#define LOLB_DF_L2HINT 0      // measured: evict_last on the ring does not reduce DRAM write-back, and costs reads
+#endif
+__device__ __forceinline__ uint64_t ring_policy()
+{
+  uint64_t pol = 0;
+#if LOLB_DF_L2HINT
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+__device__ __forceinline__ uint32_t ring_ld(const uint32_t* p, uint64_t pol)
+{
+#if LOLB_DF_L2HINT
+  uint32_t v;
+  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void ring_st(uint32_t* p, uint32_t v, uint64_t pol)
+{
+#if LOLB_DF_L2HINT
+  asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+
 // task index -> (element, kind, index inside the element); the queue interleaves, per element e, the first-kind
 // tasks of e with the second-kind tasks of e - lag
 template <int NT_A, int NT_B>
@@ -278,6 +310,7 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
   uint64_t* bar = reinterpret_cast<uint64_t*>(mail + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t pol = ring_policy();
   unsigned* cnt_a = ctr + kDfCtrHead;           // finished first-kind tasks per element
   unsigned* cnt_b = cnt_a + batch;              // finished second-kind tasks per element
   const unsigned total = (unsigned)(batch + P.lag) * (unsigned)(NT_A + NT_B);
@@ -433,13 +466,13 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
           const uint32_t* twl = L.tw + lane;
           ct_rounds<5, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
 #pragma unroll
-          for (int j = 0; j < 32; j++) srow[32 * j] = v[j];
+          for (int j = 0; j < 32; j++) ring_st(srow + 32 * j, v[j], pol);
         }
       } else {
         {
           uint32_t v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = __ldcg(srow + 32 * j);
+          for (int j = 0; j < 32; j++) v[j] = ring_ld(srow + 32 * j, pol);
           const uint32_t* twl = L.tw + lane;
           gs_rounds<5, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
 #pragma unroll
@@ -471,7 +504,7 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
       uint32_t v[NV];
       if (!INV) {
 #pragma unroll
-        for (int j = 0; j < NV; j++) v[j] = __ldcg(scol + 1024 * j);
+        for (int j = 0; j < NV; j++) v[j] = ring_ld(scol + 1024 * j, pol);
         ct_rounds<TOP, false>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
 #pragma unroll
         for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
@@ -496,7 +529,7 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
         }
         gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
 #pragma unroll
-        for (int j = 0; j < NV; j++) scol[1024 * j] = v[j];
+        for (int j = 0; j < NV; j++) ring_st(scol + 1024 * j, v[j], pol);
       }
     }
     if (tid == 0) pending = done;
@@ -511,6 +544,233 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
     __threadfence();
     atomicAdd(pending, 1u);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Paired schedule (default): one queue entry = one chunk task of element e PLUS the matching column task(s) of
+// element e - lag, executed back to back by the same CTA.  Per entry there is ONE CTA barrier (after the
+// de-interleave, forward; before the interleaved store, inverse); it also publishes the next entry, claimed by
+// thread 0 at the top of the current one.  Shared memory U is double buffered by entry parity, so a warp that is
+// done moves on without waiting for the others.  Every warp signals its own part (fence + atomic by lane 0,
+// issued after the loads of its next part, so the fence waits together with them) and reads the counters it
+// depends on one part ahead.  Counters count warp-parts: NT * kDfWarps per element and kind.
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kDfThreads, LOLB_DF_MINB)
+k_pow2_dfm(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring,
+           unsigned* __restrict__ ctr)
+{
+  typedef DfGeom<K, TOP> Geo;
+  constexpr int N = Geo::N, G = Geo::G, NV = Geo::NV, PIECES = Geo::PIECES;
+  constexpr int NT = Geo::NT_CHUNK;                     // queue entries per element
+  constexpr int CPI = Geo::NT_COL / Geo::NT_CHUNK;      // column tasks per entry (1 at e = 16)
+  constexpr unsigned FULL = (unsigned)NT * kDfWarps;    // warp-parts per element and kind
+  static_assert(G >= 1 && Geo::NCH % G == 0 && Geo::NT_COL % Geo::NT_CHUNK == 0 && CPI >= 1, "entry geometry");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* U2 = reinterpret_cast<uint32_t*>(smem_raw);                 // [2][kDfWarps units]
+  unsigned* mail = U2 + 2 * kDfWarps * kDfUnit;                         // [2] queue entry
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t pol = ring_policy();
+  unsigned* cnt_a = ctr + kDfCtrHead;           // finished first-kind warp-parts per element
+  unsigned* cnt_b = cnt_a + batch;              // finished second-kind warp-parts per element
+  const unsigned total = (unsigned)(batch + P.lag) * (unsigned)NT;
+
+  // Completion signal of the part this warp finished last (warp-uniform pointer).  EVERY lane fences its own ring /
+  // element stores before lane 0 bumps the counter: a fence by lane 0 alone does not order the other lanes' stores.
+  unsigned* pend = nullptr;
+  auto flush = [&]() {
+    if (pend) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(pend, 1u);
+      pend = nullptr;
+    }
+  };
+  // seen: value read ahead by lane 0.  A warp never waits while it holds back its own completion signal (the
+  // counter it waits for may, through a chain of other CTAs, depend on it), so the slow path signals first.
+  auto wait_dep = [&](const unsigned* dp, unsigned seen) {
+    if (dp != nullptr) {
+      const bool slow = __shfl_sync(0xffffffffu, (int)(seen < FULL), 0) != 0;
+      if (slow) {
+        flush();
+        if (lane == 0) do { __nanosleep(64); seen = ld_acquire(dp); } while (seen < FULL);
+        __syncwarp();
+      }
+    }
+  };
+
+  if (tid == 0) mail[0] = atomicAdd(ctr, 1u);
+  __syncthreads();
+
+  // the unit of this warp in a chunk task, and this thread's pieces in the (de)interleave
+  const int unit = warp, uch = unit / K, limb_u = unit % K;
+  const int l0 = (2 * tid) % K, c0 = (2 * tid) / K;
+  constexpr int second = K == 1 ? 1 : kDfUnit;
+
+  for (int it = 0;; it++) {
+    const unsigned c = mail[it & 1];
+    if (c >= total) break;
+    uint32_t* U = U2 + (it & 1) * (kDfWarps * kDfUnit);
+    uint32_t* Uu = U + unit * kDfUnit;
+    uint32_t* ubase = U + l0 * kDfUnit + c0 + (c0 >> 5);
+    const int el1 = (int)(c / (unsigned)NT), task = (int)(c % (unsigned)NT), el2 = el1 - P.lag;
+    const bool v1 = el1 < batch, v2 = el2 >= 0 && el2 < batch;
+    unsigned c_new = 0;
+    if (tid == 0) c_new = atomicAdd(ctr, 1u);
+    // counters this warp depends on, read ahead by lane 0: first kind -> ring slot free, second kind -> element ready
+    const unsigned* dp1 = (v1 && el1 >= P.ring) ? cnt_b + (el1 - P.ring) : nullptr;
+    const unsigned* dp2 = v2 ? cnt_a + el2 : nullptr;
+    unsigned seen1 = FULL, seen2 = FULL;
+    if (lane == 0) {
+      if (dp1) seen1 = ld_acquire(dp1);
+      if (dp2) seen2 = ld_acquire(dp2);
+    }
+    uint32_t* slot1 = ring + (size_t)((unsigned)el1 % (unsigned)P.ring) * ((size_t)K * N);
+    uint32_t* slot2 = ring + (size_t)((unsigned)(v2 ? el2 : 0) % (unsigned)P.ring) * ((size_t)K * N);
+    int64_t* ebase1 = y + (size_t)el1 * ((size_t)K * N);
+    int64_t* ebase2 = y + (size_t)(v2 ? el2 : 0) * ((size_t)K * N);
+    const DfLimb& Lu = P.limb[limb_u];
+    const Mont Mu{Lu.q, Lu.q2, Lu.qinv};
+
+    if (!INV) {
+      // ================================================================ forward
+      // ---- chunk task of element el1: bits [0,10)
+      const int chunk0 = task * G;
+      if (v1) {
+        const longlong2* src = reinterpret_cast<const longlong2*>(ebase1 + (size_t)chunk0 * 1024 * K) + tid;
+        const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
+        longlong2 raw[PIECES];
+#pragma unroll
+        for (int ii = 0; ii < PIECES; ii++) raw[ii] = __ldcs(src + kDfThreads * ii);
+        flush();
+        uint32_t hi_or = 0, max0 = 0, max1 = 0;
+#pragma unroll
+        for (int ii = 0; ii < PIECES; ii++) {
+          hi_or |= (uint32_t)((uint64_t)raw[ii].x >> 32) | (uint32_t)((uint64_t)raw[ii].y >> 32);
+          max0 = max(max0, (uint32_t)raw[ii].x);
+          max1 = max(max1, (uint32_t)raw[ii].y);
+          ubase[Geo::piece_off(ii)] = (uint32_t)raw[ii].x;
+          ubase[Geo::piece_off(ii) + second] = (uint32_t)raw[ii].y;
+        }
+        if (hi_or != 0 || max0 >= q0 || max1 >= q1) {
+          // outside the Haskell contract (values not in [0,q)): redo this thread's pieces like the reference's c % q
+#pragma unroll 1
+          for (int ii = 0; ii < PIECES; ii++) {
+            const longlong2 r = src[kDfThreads * ii];
+            const int off = Geo::piece_off(ii);
+            ubase[off] = df_reduce_any64(r.x, q0);
+            ubase[off + second] = df_reduce_any64(r.y, q1);
+          }
+        }
+      } else {
+        flush();
+      }
+      if (tid == 0) mail[(it & 1) ^ 1] = c_new;
+      __syncthreads();
+      if (v1) {
+        unit_rounds_0_4_rt<false>(limb_u, Uu, P, lane);
+        __syncwarp();
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
+        const uint32_t* twl = Lu.tw + lane;
+        ct_rounds<5, false>(v, Mu, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+        wait_dep(dp1, seen1);
+        uint32_t* srow = slot1 + (size_t)limb_u * N + (size_t)(chunk0 + uch) * 1024 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; j++) ring_st(srow + 32 * j, v[j], pol);
+        pend = cnt_a + el1;
+      }
+      // ---- column task(s) of element el2: bits [10, 10 + TOP)
+      if (v2) {
+        wait_dep(dp2, seen2);
+#pragma unroll 1
+        for (int sub = 0; sub < CPI; sub++) {
+          const int f = (task * CPI + sub) * kDfThreads + tid;           // (coefficient b, limb) pair, ABI order
+          const int b = f / K, limb = f % K;
+          const DfLimb& L = P.limb[limb];
+          const Mont M{L.q, L.q2, L.qinv};
+          const uint32_t* scol = slot2 + (size_t)limb * N + b;
+          int64_t* gcol = ebase2 + f;
+          const uint32_t* twb = L.tw + b;
+          uint32_t v[NV];
+#pragma unroll
+          for (int j = 0; j < NV; j++) v[j] = ring_ld(scol + 1024 * j, pol);
+          if (sub == 0) flush();
+          ct_rounds<TOP, false>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
+#pragma unroll
+          for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
+        }
+        pend = cnt_b + el2;
+      }
+    } else {
+      // ================================================================ inverse
+      // ---- column task(s) of element el1: bits [10, 10 + TOP), reads the element
+      if (v1) {
+#pragma unroll 1
+        for (int sub = 0; sub < CPI; sub++) {
+          const int f = (task * CPI + sub) * kDfThreads + tid;
+          const int b = f / K, limb = f % K;
+          const DfLimb& L = P.limb[limb];
+          const Mont M{L.q, L.q2, L.qinv};
+          uint32_t* scol = slot1 + (size_t)limb * N + b;
+          const int64_t* gcol = ebase1 + f;
+          const uint32_t* twb = L.tw + b;
+          uint32_t v[NV];
+          uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+          for (int j = 0; j < NV; j++) {
+            const int64_t raw = __ldcs(gcol + (size_t)1024 * K * j);
+            v[j] = (uint32_t)raw;
+            hi_or |= (uint32_t)((uint64_t)raw >> 32);
+          }
+          if (sub == 0) flush();
+#pragma unroll
+          for (int j = 0; j < NV; j++) lo_max = max(lo_max, v[j]);
+          if (hi_or != 0 || lo_max >= L.q) {      // outside the Haskell contract: reduce like the reference's c % q
+#pragma unroll
+            for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(gcol[(size_t)1024 * K * j], L.q);
+          }
+          gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
+          if (sub == 0) wait_dep(dp1, seen1);
+#pragma unroll
+          for (int j = 0; j < NV; j++) ring_st(scol + 1024 * j, v[j], pol);
+        }
+        pend = cnt_a + el1;
+      }
+      // ---- chunk task of element el2: bits [0,10), writes the element
+      const int chunk0 = task * G;
+      if (v2) {
+        wait_dep(dp2, seen2);
+        const uint32_t* srow = slot2 + (size_t)limb_u * N + (size_t)(chunk0 + uch) * 1024 + lane;
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = ring_ld(srow + 32 * j, pol);
+        flush();
+        const uint32_t* twl = Lu.tw + lane;
+        gs_rounds<5, 0>(v, Mu, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+        for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
+        __syncwarp();
+        unit_rounds_0_4_rt<true>(limb_u, Uu, P, lane);
+      } else {
+        flush();
+      }
+      if (tid == 0) mail[(it & 1) ^ 1] = c_new;
+      __syncthreads();
+      if (v2) {
+        longlong2* dst = reinterpret_cast<longlong2*>(ebase2 + (size_t)chunk0 * 1024 * K) + tid;
+#pragma unroll
+        for (int ii = 0; ii < PIECES; ii++) {
+          const uint32_t x0 = ubase[Geo::piece_off(ii)], x1 = ubase[Geo::piece_off(ii) + second];
+          __stcs(dst + kDfThreads * ii, make_longlong2((int64_t)x0, (int64_t)x1));
+        }
+        pend = cnt_b + el2;
+      }
+    }
+  }
+  flush();
 }
 
 struct FusedPow2Df {
@@ -581,9 +841,61 @@ int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t bat
   }
 }
 
+template <bool INV, int K, int TOP>
+int launch_dfm(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  if constexpr (((1 << TOP) * K) % kDfWarps != 0) return LOLB_FUSED_UNAVAILABLE;
+  else {
+  typedef DfGeom<K, TOP> Geo;
+  constexpr int smem = 2 * kDfWarps * kDfUnit * 4 + 64;
+  static int per_sm = 0;
+  if (!per_sm) {
+    LOLB_CUDA(cudaFuncSetAttribute(k_pow2_dfm<INV, K, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_dfm<INV, K, TOP>, kDfThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  DfParams P = INV ? F->inv : F->fwd;
+  const int64_t nt = Geo::NT_CHUNK;
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > batch * nt) grid = batch * nt;
+  // a CTA holds two queue entries (one running, one claimed): the second kind trails the first by more than that
+  // window, and a ring slot is reused one more window later
+  const int64_t window = (2 * grid + nt - 1) / nt;
+  P.lag = (int32_t)(window + 2);
+  P.ring = 2 * P.lag + 2;
+  const char* s;
+  if ((s = getenv("LOLB_DF_RING")) != nullptr && atoi(s) > 0) P.ring = atoi(s);
+  if ((s = getenv("LOLB_DF_LAG")) != nullptr && atoi(s) > 0) P.lag = atoi(s);
+  if (P.ring > batch) P.ring = (int32_t)batch;
+  if (P.ring < 2) P.ring = 2;
+  if (P.lag >= P.ring) P.lag = P.ring - 1;
+  const size_t ring_bytes = (size_t)P.ring * K * pl->n * sizeof(uint32_t);
+  const size_t ctr_bytes = ((size_t)kDfCtrHead + 2 * (size_t)batch) * sizeof(unsigned);
+  int rc = plan_reserve_ws(pl, ring_bytes + ctr_bytes);
+  if (rc) return rc;
+  uint32_t* ring = (uint32_t*)pl->d_ws;
+  unsigned* ctr = (unsigned*)((char*)pl->d_ws + ring_bytes);
+  LOLB_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
+  k_pow2_dfm<INV, K, TOP><<<(int)grid, kDfThreads, smem, st>>>(y, (int)batch, P, ring, ctr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_pow2_dfm");
+  count_launch();
+  return LOLB_OK;
+  }
+}
+
 template <bool INV, int K>
 int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
+  if (!getenv("LOLB_DF_UNPAIRED")) {
+    switch (F->top) {
+      case 2: return launch_dfm<INV, K, 2>(pl, F, y, batch, st);
+      case 3: return launch_dfm<INV, K, 3>(pl, F, y, batch, st);
+      case 4: return launch_dfm<INV, K, 4>(pl, F, y, batch, st);
+      case 5: return launch_dfm<INV, K, 5>(pl, F, y, batch, st);
+    }
+    return LOLB_FUSED_UNAVAILABLE;
+  }
   switch (F->top) {
     case 2: return launch_df<INV, K, 2>(pl, F, y, batch, st);
     case 3: return launch_df<INV, K, 3>(pl, F, y, batch, st);
