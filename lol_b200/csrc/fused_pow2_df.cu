@@ -887,7 +887,12 @@ int launch_dfm(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t ba
 template <bool INV, int K>
 int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
-  if (!getenv("LOLB_DF_UNPAIRED")) {
+  // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2
+  // paired (63 % / 59 %, 60 % / 58 % vs 61 % / 59 %, 58 % / 57 %).  Keeping the rounds 5-9 twiddles in shared memory
+  // instead of L1 was measured too: no gain, and it costs the paired kernel a CTA per SM.
+  const char* sched = getenv("LOLB_DF_SCHEDULE");      // "paired" / "unpaired" override
+  const bool paired = sched ? sched[0] == 'p' : K != 4;
+  if (paired) {
     switch (F->top) {
       case 2: return launch_dfm<INV, K, 2>(pl, F, y, batch, st);
       case 3: return launch_dfm<INV, K, 3>(pl, F, y, batch, st);

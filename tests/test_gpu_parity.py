@@ -287,16 +287,20 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
     assert (tr.gSqNormDec(smp) > 0).all()
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("schedule", ["paired", "unpaired"])
 @pytest.mark.parametrize("ring,lag", [(3, 1), (5, 4), (48, 12)], ids=lambda v: str(v))
 @pytest.mark.parametrize("e,k", [(13, 1), (13, 2), (13, 4), (14, 4), (15, 2), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
-def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, ring, lag):
-    """fused_pow2_df (persistent dataflow kernel, L2 exchange ring) for tupSize 1, 2, 4: batches larger than the
-    ring so slots are reused, tiny rings so the per-element counters are exercised; oracle parity on a sample of
-    elements, the generic engine on all of them, and crtInv . crt = id."""
+def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, ring, lag, schedule):
+    """fused_pow2_df (persistent dataflow kernels, L2 exchange ring) for tupSize 1, 2, 4, both schedules: batches
+    larger than the ring so slots are reused, tiny rings so the per-element counters and the slot-reuse ordering are
+    exercised (this is the test that caught a lane-0-only fence); oracle parity on a sample of elements, the generic
+    engine on all of them, and crtInv . crt = id."""
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorRq
     monkeypatch.setenv("LOLB_DF_RING", str(ring))
     monkeypatch.setenv("LOLB_DF_LAG", str(lag))
+    monkeypatch.setenv("LOLB_DF_SCHEDULE", schedule)
     m, qs = 2 ** e, CONFIG_B[1][:k]
     B = 23 if ring < 48 else 61
     rng = np.random.default_rng(e * 10 + k)
