@@ -3,7 +3,7 @@
 //
 // Operator.  For p = 2 the reference's  crtTwiddle ; {dftp ; dftTwiddle} x (e-1)  (crt.cpp:43-58, 137-149, 92-106,
 // 459-486, 518-538) evaluates  f(x) = sum_i y[i] x^rev(i)  at  psi^(2 pos + 1),  pos = 0 .. n-1, psi = ru[0][1]
-// (oracle-checked: tests/test_oracle_pinning.py::test_pow2_crt_is_negacyclic_evaluation).  Over Z_q every exact
+// (pinned on the CPU by tests/test_*_pinning.py::test_pow2_crt_is_negacyclic_evaluation).  Over Z_q every exact
 // evaluation order gives the same residues, so the kernel uses the twist-free Cooley-Tukey form of the same map:
 //   round r = 0 .. e-2, pairs (pos, pos + 2^r) with bit r of pos clear, p = pos mod 2^r:
 //     forward   (u, t) -> (u + T t, u - T t),      T = psi^((2p+1) n / 2^(r+1))          rounds ascending
