@@ -125,25 +125,28 @@ k_line_plain(typename R::IO* __restrict__ y, int64_t batch, const __grid_constan
   }
 }
 
-// E_p as a dense (p-1) x (p-1) real matrix per odd prime, row-major; built on the host from the complex roots
+// 2 * E_p as a dense (p-1) x (p-1) real matrix per odd prime, row-major; built on the host from the complex roots
 struct GaussMats {
   double a[6][6];
   double b[6][6];
 };
 
-// out[row] = (sum_col (2 * E[row][col]) * in[col]) / sqrt(2), accumulation order of random.cpp:33-40
+// out[row] = (sum_col (2 * E[row][col]) * in[col]) / sqrt(2), accumulation order of random.cpp:33-40.  The matrices
+// arrive as 2*E (exact), and the final division is a multiplication by the correctly rounded 1/sqrt(2): at most one
+// ulp away from the reference's quotient (the Gaussian path is specified to 1e-9 relative; the generic engine keeps
+// the division and is the cross-check), and it removes a ~25-instruction double division per coefficient and axis.
 template <int P>
 __device__ __forceinline__ void gauss_line(double (&v)[P - 1], const double (&E)[6][6])
 {
   constexpr int D = P - 1;
   double o[D];
-  const double sqrt2 = sqrt(2.0);
+  const double inv_sqrt2 = 0.70710678118654752440;
 #pragma unroll
   for (int row = 0; row < D; row++) {
     double acc = 0.0;
 #pragma unroll
-    for (int col = 0; col < D; col++) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(2.0, E[row][col]), v[col]));
-    o[row] = __ddiv_rn(acc, sqrt2);
+    for (int col = 0; col < D; col++) acc = __dadd_rn(acc, __dmul_rn(E[row][col], v[col]));
+    o[row] = __dmul_rn(acc, inv_sqrt2);
   }
 #pragma unroll
   for (int row = 0; row < D; row++) v[row] = o[row];
@@ -374,7 +377,7 @@ int fused_plain_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_
     for (int row = 0; row < P - 1; row++)
       for (int col = 1; col <= P - 1; col++) {
         const lolb_complex w = T[(size_t)(((int64_t)row * col) % P) * mp[ax]];
-        M[row][col - 1] = col <= (P >> 1) ? w.real : w.imag;
+        M[row][col - 1] = 2.0 * (col <= (P >> 1) ? w.real : w.imag);
       }
   }
   int threads;
