@@ -1,2 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "plain or double or golden" 2>&1 | tail -3
-timeout 120 python tools/run_plain.py 14400 65536 2>&1 | tail -9
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "complex or double_and or plain or golden" 2>&1 | tail -3

@@ -172,6 +172,9 @@ class PlanC:
     def force_generic(self, on: bool = True) -> None:
         lib().lolb_plan_set_force_generic(self._h, int(on))
 
+    def kernel_name(self, op: str) -> str:
+        return lib().lolb_plan_kernel_name(self._h, op.encode()).decode()
+
     def op(self, name: str, ptr: int, batch: int, stream: int = 0) -> int:
         """name: 'LR', 'LInvDouble', 'GPowC', 'CRTC', 'CRTInvC', 'GaussianDec', 'GInvPowC', ..."""
         f = getattr(lib(), "lolb_tensor" + name)

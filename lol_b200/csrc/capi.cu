@@ -141,6 +141,7 @@ static int plan_set_c_tables(lolb_plan* pl, lolb_complex* const* ru, lolb_comple
     if (mhatInv) for (int t = 0; t < pl->k; t++) pl->c_mhatinv[t] = make_double2(mhatInv[t].real, mhatInv[t].imag);
     rc = plan_upload_c_dir(pl, true);
   }
+  if (!rc) rc = fused_select(pl);
   return rc;
 }
 
@@ -155,6 +156,7 @@ extern "C" int lolb_plan_create_c(lolb_plan** out, const PrimeExponent* peArr, h
     plan_derive_c_roots(pl);
     rc = plan_upload_c_dir(pl, false);
     if (!rc) rc = plan_upload_c_dir(pl, true);
+    if (!rc) rc = fused_select(pl);
   }
   if (rc) { lolb_plan_destroy(pl); return rc; }
   *out = pl;
@@ -314,12 +316,20 @@ extern "C" int lolb_tensorCRTC(const lolb_plan* plan, lolb_complex* y, int64_t b
 {
   REQUIRE_PLAN(PLAN_C);
   if (!plan->has_fwd) return LOLB_ERR_NO_CRT;
+  if (!plan->force_generic) {
+    int rc = fused_crt_c(plan, false, (double2*)y, batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   return engine_crt_c(plan, false, (double2*)y, batch, (cudaStream_t)stream);
 }
 extern "C" int lolb_tensorCRTInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, void* stream)
 {
   REQUIRE_PLAN(PLAN_C);
   if (!plan->has_inv) return LOLB_ERR_NO_CRT;
+  if (!plan->force_generic) {
+    int rc = fused_crt_c(plan, true, (double2*)y, batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   return engine_crt_c(plan, true, (double2*)y, batch, (cudaStream_t)stream);
 }
 extern "C" int lolb_mulC(const lolb_plan* plan, lolb_complex* y, const lolb_complex* b, int64_t batch, int64_t b_batch, void* stream)

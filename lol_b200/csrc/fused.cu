@@ -23,6 +23,12 @@ void fused_pow2_df_release(void* slot);
 bool fused_pow2_df_available(const void* slot, bool inverse);
 int fused_pow2_df_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 
+// fused_ac.cu
+int fused_ac_select(lolb_plan* pl, void** slot);
+void fused_ac_release(void* slot);
+bool fused_ac_available(const void* slot, bool inverse);
+int fused_ac_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st);
+
 // fused_stream.cu
 const char* fused_stream_line_name(const lolb_plan* pl);
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
@@ -32,6 +38,7 @@ namespace {
 struct FusedSet {
   void* a = nullptr;      // m = 14400 CRT / CRT^-1
   void* pow2 = nullptr;   // m = 2^e CRT / CRT^-1, limb resident in shared memory (e <= 12, tupSize 3, ...)
+  void* ac = nullptr;       // m = 14400 complex CRT / CRT^-1
   void* pow2_df = nullptr;  // m = 2^e CRT / CRT^-1, dataflow kernel with an L2 exchange ring (13 <= e <= 16)
 };
 FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
@@ -39,6 +46,10 @@ FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
 
 int fused_select(lolb_plan* pl)
 {
+  if (pl->kind == PLAN_C) {
+    if (!pl->fused) pl->fused = new FusedSet();
+    return fused_ac_select(pl, &set_of(pl)->ac);
+  }
   if (pl->kind != PLAN_RQ) return LOLB_OK;
   if (!pl->fused) pl->fused = new FusedSet();
   int rc = fused_a_select(pl, &set_of(pl)->a);
@@ -54,6 +65,7 @@ void fused_release(lolb_plan* pl)
   fused_a_release(s->a);
   fused_pow2_release(s->pow2);
   fused_pow2_df_release(s->pow2_df);
+  fused_ac_release(s->ac);
   delete s;
   pl->fused = nullptr;
 }
@@ -62,6 +74,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
 {
   const FusedSet* s = set_of(pl);
   if (s) {
+    if (!strcmp(op, "CRTC") && fused_ac_available(s->ac, false)) return "fused_ac";
+    if (!strcmp(op, "CRTInvC") && fused_ac_available(s->ac, true)) return "fused_ac";
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
     if (!strcmp(op, "CRT") && fused_pow2_df_available(s->pow2_df, false)) return "fused_pow2_df";
@@ -84,6 +98,13 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_df_crt(pl, s->pow2_df, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_crt(pl, s->pow2, inverse, y, batch, st);
   return rc;
+}
+
+int fused_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cudaStream_t st)
+{
+  const FusedSet* s = set_of(pl);
+  if (!s) return LOLB_FUSED_UNAVAILABLE;
+  return fused_ac_crt(pl, s->ac, inverse, y, batch, st);
 }
 
 int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)

@@ -318,6 +318,32 @@ def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, rin
     assert torch.equal(t.crt(x), f) and torch.equal(t.crtInv(x), g)
 
 
+@pytest.mark.parametrize("k", [1, 2], ids=lambda k: f"k={k}")
+def test_complex_crt_fused_kernel_m14400(torch_cuda, oracle, k):
+    """tensorCRTC / tensorCRTInvC at m = 14400 run on fused_ac (one HBM round trip, FP64): against the oracle per
+    element (1e-9 relative, BASELINE.json), against the generic pass engine on the whole ragged batch, and
+    crtInv . crt = id; also through the drop-in symbols with caller-supplied root tables."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorComplex
+    m, B = 14400, 19
+    rng = np.random.default_rng(41 + k)
+    pe = T.pe_array(m)
+    t = CudaTensorComplex(m, k)
+    assert t.plan.kernel_name("CRTC") == "fused_ac" and t.plan.kernel_name("CRTInvC") == "fused_ac"
+    c = rng.normal(size=(B, t.n, k)) + 1j * rng.normal(size=(B, t.n, k))
+    x = torch.from_numpy(c).cuda()
+    ruc, ruci = T.ru_tables_c(m, k), T.ru_tables_c(m, k, inverse=True)
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, 7, B - 1):
+        assert rel_err(f[b].cpu().numpy(), oracle.tensorCRTC(c[b], pe, ruc, k)) <= FLOAT_TOL
+        assert rel_err(g[b].cpu().numpy(), oracle.tensorCRTInvC(c[b], pe, ruci, T.mhat_inv_c(m, k), k)) <= FLOAT_TOL
+    assert rel_err(t.crtInv(f).cpu().numpy(), c) <= 1e-12
+    t.plan.force_generic(True)
+    assert t.plan.kernel_name("CRTC") == "generic"
+    assert rel_err(t.crt(x).cpu().numpy(), f.cpu().numpy()) <= 1e-12
+    assert rel_err(t.crtInv(x).cpu().numpy(), g.cpu().numpy()) <= 1e-12
+
+
 @pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89], ids=str)
 def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
     """The streaming kernels of the modulus-free rings (one or two small odd primes) against the generic pass
