@@ -341,9 +341,9 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         rq_config(65536, [537133057, 537591809, 537722881, 538116097], 1024, "configs[2]: m=2^16, four ~30-bit primes")
         rq_config(14400, [1008001, 1065601], 32768, "configs[3] moduli: m=14400, q=(1008001,1065601) (SymmSHE key-switch modulus)")
-        from lol_b200.tensor import CudaTensorInt, CudaTensorReal
+        from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
         Bg = 32768
-        tr, ti = CudaTensorReal(M), CudaTensorInt(M)
+        tr, ti, tcx = CudaTensorReal(M), CudaTensorInt(M), CudaTensorComplex(M)
         dg = torch.randn(Bg, tr.n, 1, dtype=torch.float64, device="cuda", generator=gen)
         zg = torch.randint(-8, 9, (Bg, tr.n, 1), dtype=torch.int64, device="cuda", generator=gen)
         og = torch.empty(Bg, 1, dtype=torch.int64, device="cuda")
@@ -352,8 +352,13 @@ def run_gpu_arm(args):
         res["tensorGaussianDec"] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 16 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak}
         ms = timed(lambda: capi.check(ti.plan.normsq("R", zg.data_ptr(), og.data_ptr(), Bg, stream)))
         res["tensorNormSqR"] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 8 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak}
-        other["configs[4]: m=14400 tensorGaussianDec + tensorNormSqR (double / int64)"] = res
-        del dg, zg
+        cg = torch.randn(Bg, tr.n, 1, dtype=torch.complex128, device="cuda")
+        for name in ("CRTC", "CRTInvC"):
+            ms = timed(lambda: capi.check(tcx.plan.op(name, cg.data_ptr(), Bg, stream)))
+            res["tensor" + name] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 32 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak,
+                                    "kernel": tcx.plan.kernel_name(name)}
+        other["configs[4]: m=14400 tensorGaussianDec + tensorNormSqR (double / int64), complex CRT"] = res
+        del dg, zg, cg
         x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
 
     cpu_base = None
