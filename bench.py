@@ -307,7 +307,9 @@ def run_gpu_arm(args):
         ops = {"L": (lambda: t.plan.op("L", ptr, B, stream), 16), "LInv": (lambda: t.plan.op("LInv", ptr, B, stream), 16),
                "GPow": (lambda: t.plan.op("GPow", ptr, B, stream), 16), "GDec": (lambda: t.plan.op("GDec", ptr, B, stream), 16),
                "GInvPow": (lambda: t.plan.op("GInvPow", ptr, B, stream), 16), "GInvDec": (lambda: t.plan.op("GInvDec", ptr, B, stream), 16),
-               "mulRq": (lambda: t.plan.mul(ptr, y2.data_ptr(), B, B, stream), 24)}
+               "mulRq": (lambda: t.plan.mul(ptr, y2.data_ptr(), B, B, stream), 24),
+               "CRTMul": (lambda: t.plan.crt_mul(ptr, y2.data_ptr(), B, B, stream), 24),          # y <- CRT(y) . b, one pass
+               "MulCRTInv": (lambda: t.plan.mul_crt_inv(ptr, y2.data_ptr(), B, B, stream), 24)}   # y <- CRTInv(y . b), one pass
         for name, (fn, bpc) in ops.items():
             fn(); fn()
             ms = time_op(torch, fn, 10)

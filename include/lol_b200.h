@@ -169,6 +169,14 @@ int lolb_tensorGInvPowRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* 
 int lolb_tensorGInvDecRq(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
 /* a[i] <- a[i] * b[i]; b holds `b_batch` elements (1 = broadcast one element, e.g. gCRT; else == batch) */
 int lolb_mulRq(const lolb_plan* plan, hInt_t* a, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream);
+/* Fused pairs around the CRT (the callers either side of the path: the ring product of lol/Crypto/Lol/Cyclotomic/Cyc.hs:276-297
+ * = toCRT then zipWith (*) (UCyc.hs:232), and the CRT-basis products of key switching, lol-apps SymmSHE.hs:302-314):
+ *   lolb_crtMulRq     y <- tensorCRTRq(y) . b        (crt.cpp:562-566 then mul.cpp:27-30)
+ *   lolb_mulCrtInvRq  y <- tensorCRTInvRq(y . b)     (mul.cpp:27-30 then crt.cpp:569-581)
+ * b as in lolb_mulRq, must not alias y.  Results are those of the two calls in sequence; one HBM pass where a fused
+ * kernel exists (m = 14400), the two kernels back to back otherwise. */
+int lolb_crtMulRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream);
+int lolb_mulCrtInvRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream);
 
 /* modulus-free rings; plan from lolb_plan_create_c */
 int lolb_tensorLR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);

@@ -142,6 +142,12 @@ class PlanRq:
     def mul(self, a_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
         return int(lib().lolb_mulRq(self._h, _p(a_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
 
+    def crt_mul(self, y_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_crtMulRq(self._h, _p(y_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
+
+    def mul_crt_inv(self, y_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_mulCrtInvRq(self._h, _p(y_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
+
     def apply_host(self, ops: str, host_ptr: int, batch: int) -> int:
         return int(lib().lolb_rq_apply_host(self._h, ops.encode(), _p(host_ptr), _i64(batch)))
 

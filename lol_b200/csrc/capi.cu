@@ -270,6 +270,36 @@ extern "C" int lolb_mulRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int
   return engine_mul_zq(plan, y, b, batch, b_batch, st);
 }
 
+// Fused pair (the callers either side of the CRT).  Cyc's ring product converts a Pow/Dec
+// operand to the CRT basis and multiplies pointwise (Cyc.hs:276-297, UCyc.hs:232); key switching multiplies in the CRT
+// basis and converts back (SymmSHE.hs:302-314).  One HBM pass instead of two where a fused kernel exists (m = 14400);
+// otherwise the same two CUDA kernels back to back.
+extern "C" int lolb_crtMulRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_RQ);
+  if (!b || (b_batch != 1 && b_batch != batch)) { set_error("lolb_crtMulRq: b_batch must be 1 or batch"); return LOLB_ERR_ARG; }
+  if (!plan->has_fwd) { set_error("no CRT over this modulus / index (ZqBasic.hs:159-165) or tables not supplied"); return LOLB_ERR_NO_CRT; }
+  if (!plan->force_generic && b != y) {
+    int rc = fused_crt_mul_rq(plan, false, y, b, batch, b_batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  int rc = crt_rq(plan, false, y, batch, stream);
+  return rc ? rc : lolb_mulRq(plan, y, b, batch, b_batch, stream);
+}
+
+extern "C" int lolb_mulCrtInvRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_RQ);
+  if (!b || (b_batch != 1 && b_batch != batch)) { set_error("lolb_mulCrtInvRq: b_batch must be 1 or batch"); return LOLB_ERR_ARG; }
+  if (!plan->has_inv) { set_error("no CRT over this modulus / index (ZqBasic.hs:159-165) or tables not supplied"); return LOLB_ERR_NO_CRT; }
+  if (!plan->force_generic && b != y) {
+    int rc = fused_crt_mul_rq(plan, true, y, b, batch, b_batch, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  int rc = lolb_mulRq(plan, y, b, batch, b_batch, stream);
+  return rc ? rc : crt_rq(plan, true, y, batch, stream);
+}
+
 // modulus-free rings: streaming kernel when the index has one or two small odd primes, generic engine otherwise
 static int plain_line(const lolb_plan* plan, int ring, int kind, void* y, int64_t batch, double rscale, void* stream)
 {
@@ -411,7 +441,9 @@ extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t
   }
   const size_t elem_bytes = (size_t)plan->n * plan->k * sizeof(int64_t);
   const int slots = 3;
-  int64_t chunk = (int64_t)((size_t)(96u << 20) / elem_bytes);        // ~96 MiB per slot
+  static size_t slot_mib = 0;                                          // LOLB_STAGE_MIB: tuning override
+  if (!slot_mib) { const char* v = getenv("LOLB_STAGE_MIB"); slot_mib = v && atoi(v) > 0 ? (size_t)atoi(v) : 96; }
+  int64_t chunk = (int64_t)((slot_mib << 20) / elem_bytes);            // ~96 MiB per slot
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   int rc = plan_reserve_stage(plan, (size_t)slots * chunk * elem_bytes);

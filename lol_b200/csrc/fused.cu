@@ -10,6 +10,8 @@ int fused_a_select(lolb_plan* pl, void** slot);
 void fused_a_release(void* slot);
 bool fused_a_available(const void* slot, bool inverse);
 int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, const int64_t* b, int64_t batch,
+                    int64_t b_batch, cudaStream_t st);
 
 // fused_pow2.cu
 int fused_pow2_select(lolb_plan* pl, void** slot);
@@ -74,6 +76,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
 {
   const FusedSet* s = set_of(pl);
   if (s) {
+    if (!strcmp(op, "CRTMul") && fused_a_available(s->a, false) && pl->k != 2) return "fused_a+mul";
+    if (!strcmp(op, "MulCRTInv") && fused_a_available(s->a, true) && pl->k != 2) return "fused_a+mul";
     if (!strcmp(op, "CRTC") && fused_ac_available(s->ac, false)) return "fused_ac";
     if (!strcmp(op, "CRTInvC") && fused_ac_available(s->ac, true)) return "fused_ac";
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
@@ -98,6 +102,13 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_df_crt(pl, s->pow2_df, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_crt(pl, s->pow2, inverse, y, batch, st);
   return rc;
+}
+
+int fused_crt_mul_rq(const lolb_plan* pl, bool inverse, int64_t* y, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st)
+{
+  const FusedSet* s = set_of(pl);
+  if (!s) return LOLB_FUSED_UNAVAILABLE;
+  return fused_a_crt_mul(pl, s->a, inverse, y, b, batch, b_batch, st);
 }
 
 int fused_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cudaStream_t st)

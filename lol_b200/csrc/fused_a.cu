@@ -30,6 +30,7 @@ struct FusedAConsts {
   uint32_t q, q2;
   uint32_t r0;              // ArithS: mu = floor(2^32 / q);  ArithM: -q^-1 mod 2^32
   uint32_t one;             // ArithS: 1;                     ArithM: 2^32 mod q (Montgomery form of 1)
+  uint32_t r2;              // ArithS: unused;                ArithM: 2^64 mod q (data x data products, see mulv)
   uint32_t m5[5][4][4];     // fwd: (twiddle . CRT_5) per block i0;      inv: (CRT_5^-1' . twiddle) * mhat^-1
   uint32_t d5[5][5];        // DFT_5 over the block index (fwd or inverse roots)
   uint32_t m3[3][2][2];
@@ -49,6 +50,7 @@ struct ArithS {
   __device__ __forceinline__ Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + c * v; }
   __device__ __forceinline__ Acc unit(uint32_t v) const { return v; }                                   // the "1 * v" term
   __device__ __forceinline__ uint32_t red(Acc x) const { return __umulhi(x, mu) * nq + x; }             // any x -> [0,2q)
+  __device__ __forceinline__ uint32_t mulv(uint32_t x, uint32_t b) const { return red(x * b); }         // data x data, x < 2q, b < q
   __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }                 // [0,4q) -> [0,2q)
   __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }                 // [0,2q) -> [0,q)
 };
@@ -58,8 +60,8 @@ struct ArithS {
 // REDC(sum c~_i v_i) = sum c_i v_i mod q.  acc < 10 q^2 and 10q < 2^32 give REDC(acc) < 2q.
 struct ArithM {
   typedef uint64_t Acc;
-  uint32_t q, q2, qinv, one;
-  __device__ __forceinline__ ArithM(const FusedAConsts& C) : q(C.q), q2(C.q2), qinv(C.r0), one(C.one) {}
+  uint32_t q, q2, qinv, one, r2;
+  __device__ __forceinline__ ArithM(const FusedAConsts& C) : q(C.q), q2(C.q2), qinv(C.r0), one(C.one), r2(C.r2) {}
   __device__ __forceinline__ Acc mul(uint32_t c, uint32_t v) const { return (uint64_t)c * v; }
   __device__ __forceinline__ Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + (uint64_t)c * v; }
   __device__ __forceinline__ Acc unit(uint32_t v) const { return (uint64_t)one * v; }
@@ -68,6 +70,8 @@ struct ArithM {
     const uint32_t m = (uint32_t)x * qinv;
     return (uint32_t)((x + (uint64_t)m * q) >> 32);
   }
+  // data x data: both factors are in plain form, so REDC(x b) = x b 2^-32; a second REDC against 2^64 mod q restores it
+  __device__ __forceinline__ uint32_t mulv(uint32_t x, uint32_t b) const { return red((uint64_t)r2 * red((uint64_t)x * b)); }
   __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }
   __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }
 };
@@ -197,9 +201,12 @@ __device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
 // EPB ring elements per CTA iteration on WARPS warps: phase 1 has 6*EPB warp-tasks (32 columns each), phase 2 has
 // 20*EPB; (EPB, WARPS) = (5, 10) balances both exactly (3 and 10 tasks per warp).  EPB == 1 double-buffers the
 // shared tile (one barrier per element), EPB > 1 uses a single tile and two barriers per EPB elements.
-template <bool INV, class AR, int K, int EPB, int WARPS, int MINB, int NBUF>
+// MUL fuses the pointwise product with a second operand b (canonical residues, same layout; b_stride = 0 broadcasts one
+// element): forward  y <- CRT(y) . b  (multiplied at the store), inverse  y <- CRT^-1(y . b)  (multiplied at the load).
+template <bool INV, class AR, int K, int EPB, int WARPS, int MINB, int NBUF, bool MUL = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __grid_constant__ FusedAConsts C)
+k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __grid_constant__ FusedAConsts C,
+          const int64_t* __restrict__ bmul = nullptr, int64_t b_stride = 0)
 {
   const int k = K ? K : k_rt;
   extern __shared__ __align__(16) uint32_t sm_dyn[];       // [NBUF][EPB][kN]
@@ -238,6 +245,24 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll 1
         for (int a = 0; a < 20; a++) v[a] = reduce_any(src[(size_t)(a * 192) * k], C.q);
       }
+      if (MUL && INV) {
+        const int64_t* bsrc = bmul + (size_t)(e0 + slot) * b_stride + (size_t)col * k + limb;
+        uint32_t w[20];
+        uint32_t bh = 0, bm = 0;
+#pragma unroll
+        for (int a = 0; a < 20; a++) {
+          const int64_t raw = __ldg(bsrc + (size_t)(a * 192) * k);
+          w[a] = (uint32_t)raw;
+          bh |= (uint32_t)((uint64_t)raw >> 32);
+          bm = max(bm, w[a]);
+        }
+        if (bh != 0 || bm >= C.q) {
+#pragma unroll
+          for (int a = 0; a < 20; a++) w[a] = reduce_any(bsrc[(size_t)(a * 192) * k], C.q);
+        }
+#pragma unroll
+        for (int a = 0; a < 20; a++) v[a] = A.mulv(v[a], w[a]);
+      }
       axis5<INV, AR>(v, C, A);
       uint32_t* dst = tile + slot * kN + col;
 #pragma unroll
@@ -249,6 +274,7 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
     constexpr int U = 1;      // U = 2 measured slower (ragged pairs recompute a dead task)
     for (int t0 = warp; t0 < kD3 * EPB; t0 += U * WARPS) {
       int64_t* out[U];
+      const int64_t* bout[U];
       uint32_t x[U][6], c0[U][3], c1[U][3];
       bool live[U];
 #pragma unroll
@@ -263,6 +289,7 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
         int64_t* base = y + ((size_t)(e0 + ts) * kN) * k + limb;
         out[u] = INV ? base + (size_t)(ti * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k
                      : base + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
+        bout[u] = (MUL && !INV) ? bmul + (size_t)(e0 + ts) * b_stride + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k + limb : nullptr;
       }
 #pragma unroll
       for (int u = 0; u < U; u++) axis3<INV, AR>(x[u], C, A, m3l);
@@ -281,6 +308,17 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll
         for (int u = 0; u < U; u++)
           if (live[u]) {
+            if (MUL) {
+              const int64_t* bo = bout[u];
+              int64_t braw[6];
+#pragma unroll
+              for (int j = 0; j < 3; j++) { braw[2 * j] = __ldg(bo + (size_t)(j * 64) * k); braw[2 * j + 1] = __ldg(bo + (size_t)(j * 64 + 16) * k); }
+#pragma unroll
+              for (int j = 0; j < 6; j++) {
+                const uint32_t bw = (uint64_t)braw[j] < (uint64_t)C.q ? (uint32_t)braw[j] : reduce_any(braw[j], C.q);
+                if (j & 1) c1[u][j >> 1] = A.mulv(c1[u][j >> 1], bw); else c0[u][j >> 1] = A.mulv(c0[u][j >> 1], bw);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 3; j++) {
               __stcs(out[u] + (size_t)(j * 64) * k, (int64_t)A.canon(c0[u][j]));
@@ -616,6 +654,7 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
     for (int i = 0; i < 5; i++) inv *= 2u - (uint32_t)q * inv;
     C->r0 = 0u - inv;
     C->one = mont(1);
+    C->r2 = mont(mont(1));
     for (auto& a : C->m5) for (auto& b : a) for (auto& c : b) c = mont(c);
     for (auto& a : C->d5) for (auto& c : a) c = mont(c);
     for (auto& a : C->m3) for (auto& b : a) for (auto& c : b) c = mont(c);
@@ -691,10 +730,47 @@ static int launch_a(const lolb_plan* pl, int64_t* y, int64_t batch, int limb, co
   const int64_t groups = (batch + EPB - 1) / EPB;
   int64_t grid = (int64_t)pl->num_sms * MINB;
   if (grid > groups) grid = groups;
-  kern<<<(int)grid, WARPS * 32, smem, st>>>(y, batch, pl->k, limb, C);
+  kern<<<(int)grid, WARPS * 32, smem, st>>>(y, batch, pl->k, limb, C, nullptr, 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_fused_a");
   count_launch();
+  return LOLB_OK;
+}
+
+// y <- CRT(y) . b   /   y <- CRT^-1(y . b)   in one pass (b_batch = 1 broadcasts b)
+template <bool INV, class AR, int K, int MINB>
+static int launch_a_mul(const lolb_plan* pl, int64_t* y, const int64_t* b, int64_t batch, int64_t b_batch, int limb,
+                        const FusedAConsts& C, cudaStream_t st)
+{
+  int64_t grid = (int64_t)pl->num_sms * MINB;
+  if (grid > batch) grid = batch;
+  const int64_t b_stride = b_batch == 1 ? 0 : (int64_t)kN * pl->k;
+  k_fused_a<INV, AR, K, 1, 3, MINB, 1, true><<<(int)grid, 96, kN * sizeof(uint32_t), st>>>(y, batch, pl->k, limb, C, b, b_stride);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_fused_a<MUL>");
+  count_launch();
+  return LOLB_OK;
+}
+
+int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, const int64_t* b, int64_t batch,
+                    int64_t b_batch, cudaStream_t st)
+{
+  const FusedA* F = (const FusedA*)slot;
+  if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
+  // tupSize 2 has its own 128-bit kernel without the fused product: measured (config C moduli) the two kernels back to
+  // back take 2.09 ms against 2.39 ms for one strided fused launch per limb, so the pair stays unfused there
+  if (pl->k == 2 && F->cls[0] == F->cls[1]) return LOLB_FUSED_UNAVAILABLE;
+  if (batch <= 0) return LOLB_OK;
+  for (int t = 0; t < pl->k; t++) {
+    const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];
+    int rc;
+#define LM(AR, KK, MB) (inverse ? launch_a_mul<true, AR, KK, MB>(pl, y, b, batch, b_batch, t, C, st) \
+                                : launch_a_mul<false, AR, KK, MB>(pl, y, b, batch, b_batch, t, C, st))
+    if (F->cls[t] == ARITH_M) rc = pl->k == 1 ? LM(ArithM, 1, 8) : LM(ArithM, 0, 8);
+    else rc = pl->k == 1 ? LM(ArithS, 1, 10) : LM(ArithS, 0, 10);
+#undef LM
+    if (rc) return rc;
+  }
   return LOLB_OK;
 }
 

@@ -93,6 +93,24 @@ class CudaTensorRq:
         capi.check(self.plan.mul(y.data_ptr(), b.data_ptr(), ba, bb, _stream()))
         return y
 
+    def crtMul(self, a, b, inplace=False):
+        """crt a `zipWithT (*)` b in one pass: the ring product of a Pow-basis `a` with a CRT-basis `b`
+        (Cyc.hs:276-297; crt.cpp:562-566 then mul.cpp:27-30).  `b` may hold one element broadcast over the batch."""
+        ba = _require_cuda(a, torch.int64, self.n, self.k)
+        bb = _require_cuda(b, torch.int64, self.n, self.k)
+        y = a if inplace else a.clone()
+        capi.check(self.plan.crt_mul(y.data_ptr(), b.data_ptr(), ba, bb, _stream()))
+        return y
+
+    def mulCrtInv(self, a, b, inplace=False):
+        """crtInv (a `zipWithT (*)` b) in one pass (mul.cpp:27-30 then crt.cpp:569-581), e.g. the hint products of key
+        switching followed by the change back to the powerful basis (SymmSHE.hs:302-314)."""
+        ba = _require_cuda(a, torch.int64, self.n, self.k)
+        bb = _require_cuda(b, torch.int64, self.n, self.k)
+        y = a if inplace else a.clone()
+        capi.check(self.plan.mul_crt_inv(y.data_ptr(), b.data_ptr(), ba, bb, _stream()))
+        return y
+
     def _mul_by_plan_vector(self, x, inverse, inplace):
         b = _require_cuda(x, torch.int64, self.n, self.k)
         ptr = self.plan.gcrt_dev(inverse)

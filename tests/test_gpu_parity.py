@@ -235,6 +235,39 @@ def test_batched_rq_matches_oracle(torch_cuda, oracle, m, qs, force_generic):
     assert t.crt(e).shape[0] == 0
 
 
+@pytest.mark.parametrize("m,qs", [CONFIG_A, CONFIG_C, (14400, [14401, 1008001, 429336001]), (42, [8191]), (2 ** 13, [537133057])],
+                         ids=lambda v: str(v))
+def test_fused_crt_mul_pairs(torch_cuda, oracle, m, qs):
+    """lolb_crtMulRq / lolb_mulCrtInvRq (one pass at m = 14400, both arithmetic classes and tupSize 1/2/3; two kernels
+    back to back elsewhere) are bit-identical to the reference's two calls in sequence: tensorCRTRq then mulRq, mulRq then
+    tensorCRTInvRq; full-batch and broadcast second operand; and crtInv(crt(a) * crt(b)) is the negacyclic-style ring
+    product both ways round (commutativity as a size-independent check)."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    B = 13
+    rng = np.random.default_rng(m + 7)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    ya, yb = zq_input(rng, n, qs, batch=B), zq_input(rng, n, qs, batch=B)
+    a, b = torch.from_numpy(ya).cuda(), torch.from_numpy(yb).cuda()
+    b1 = b[:1].contiguous()
+    want = np.stack([oracle.mulRq(oracle.tensorCRTRq(ya[i], pe, ru, qs), yb[i], qs) for i in range(B)])
+    assert np.array_equal(t.crtMul(a, b).cpu().numpy(), want)
+    want1 = np.stack([oracle.mulRq(oracle.tensorCRTRq(ya[i], pe, ru, qs), yb[0], qs) for i in range(B)])
+    assert np.array_equal(t.crtMul(a, b1).cpu().numpy(), want1)
+    wanti = np.stack([oracle.tensorCRTInvRq(oracle.mulRq(ya[i], yb[i], qs), pe, rui, mh, qs) for i in range(B)])
+    assert np.array_equal(t.mulCrtInv(a, b).cpu().numpy(), wanti)
+    wanti1 = np.stack([oracle.tensorCRTInvRq(oracle.mulRq(ya[i], yb[0], qs), pe, rui, mh, qs) for i in range(B)])
+    assert np.array_equal(t.mulCrtInv(a, b1).cpu().numpy(), wanti1)
+    assert torch.equal(a, torch.from_numpy(ya).cuda()) and torch.equal(b, torch.from_numpy(yb).cuda())      # pure
+    # ring product a * b = crtInv(crt a . crt b), either way round
+    ab = t.mulCrtInv(t.crtMul(a, t.crt(b)), torch.ones_like(b1))
+    ba = t.mulCrtInv(t.crtMul(b, t.crt(a)), torch.ones_like(b1))
+    assert torch.equal(ab, ba) and torch.equal(ab, t.crtInv(t.mul(t.crt(a), t.crt(b))))
+    t.plan.force_generic(True)
+    assert np.array_equal(t.crtMul(a, b).cpu().numpy(), want) and np.array_equal(t.mulCrtInv(a, b).cpu().numpy(), wanti)
+
+
 @pytest.mark.parametrize("e", list(range(5, 17)), ids=lambda e: f"m=2^{e}")
 def test_power_of_two_indices(torch_cuda, oracle, e):
     """Every power-of-two index up to config B's 2^16 (fused NTT from 2^7 on, generic below), RNS pair with a
