@@ -1,10 +1,10 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "fused_crt_mul or batched_rq or full_size" 2>&1 | tail -5
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "fused_crt_mul" 2>&1 | tail -5
 python - <<'PY'
 import sys, torch
 sys.path.insert(0, ".")
 from lol_b200.tensor import CudaTensorRq
 from lol_b200 import capi
-for m, qs, B in ((14400, [14401], 65536), (14400, [1008001, 1065601], 32768)):
+for m, qs, B in ((14400, [1008001, 1065601], 32768),):
     t = CudaTensorRq(m, qs); k = len(qs)
     x = torch.cat([torch.randint(0, q, (B, t.n, 1), dtype=torch.int64, device="cuda") for q in qs], dim=2).contiguous()
     b = x.clone()

@@ -76,8 +76,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
 {
   const FusedSet* s = set_of(pl);
   if (s) {
-    if (!strcmp(op, "CRTMul") && fused_a_available(s->a, false) && pl->k != 2) return "fused_a+mul";
-    if (!strcmp(op, "MulCRTInv") && fused_a_available(s->a, true) && pl->k != 2) return "fused_a+mul";
+    if (!strcmp(op, "CRTMul") && fused_a_available(s->a, false)) return "fused_a+mul";
+    if (!strcmp(op, "MulCRTInv") && fused_a_available(s->a, true)) return "fused_a+mul";
     if (!strcmp(op, "CRTC") && fused_ac_available(s->ac, false)) return "fused_ac";
     if (!strcmp(op, "CRTInvC") && fused_ac_available(s->ac, true)) return "fused_ac";
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";

@@ -445,9 +445,10 @@ k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 // used) and runs the two limbs as independent instruction streams with their own constants.
 struct FusedAConsts2 { FusedAConsts c[2]; };
 
-template <bool INV, class AR, int WARPS, int MINB>
+template <bool INV, class AR, int WARPS, int MINB, bool MUL = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts2 CC)
+k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts2 CC,
+             const int64_t* __restrict__ bmul, int64_t b_stride)
 {
   extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN]
   const AR A0(CC.c[0]), A1(CC.c[1]);
@@ -491,6 +492,22 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
           v1[a] = reduce_any(raw.y, CC.c[1].q);
         }
       }
+      if (MUL && INV) {
+        const longlong2* bsrc = reinterpret_cast<const longlong2*>(bmul + (size_t)e * b_stride) + col;
+#pragma unroll
+        for (int part = 0; part < 4; part++) {       // four batches of five 128-bit loads
+          longlong2 braw[5];
+#pragma unroll
+          for (int a = 0; a < 5; a++) braw[a] = __ldg(bsrc + (part * 5 + a) * 192);
+#pragma unroll
+          for (int a = 0; a < 5; a++) {
+            const uint32_t w0 = (uint64_t)braw[a].x < (uint64_t)CC.c[0].q ? (uint32_t)braw[a].x : reduce_any(braw[a].x, CC.c[0].q);
+            const uint32_t w1 = (uint64_t)braw[a].y < (uint64_t)CC.c[1].q ? (uint32_t)braw[a].y : reduce_any(braw[a].y, CC.c[1].q);
+            v0[part * 5 + a] = A0.mulv(v0[part * 5 + a], w0);
+            v1[part * 5 + a] = A1.mulv(v1[part * 5 + a], w1);
+          }
+        }
+      }
       axis5<INV, AR>(v0, CC.c[0], A0);
 #pragma unroll
       for (int a = 0; a < 20; a++) sm_dyn[a * 192 + col] = v0[a];
@@ -521,6 +538,19 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
         exchange_round<false, AR, true>(c0[0], c1[0], lane, 4, 0u, A0);
         exchange_round<false, AR, true>(c0[1], c1[1], lane, 4, 0u, A1);
         longlong2* out = ebase + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
+        if (MUL) {
+          const longlong2* bo = reinterpret_cast<const longlong2*>(bmul + (size_t)e * b_stride) + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
+          longlong2 braw[6];
+#pragma unroll
+          for (int j = 0; j < 3; j++) { braw[2 * j] = __ldg(bo + j * 64); braw[2 * j + 1] = __ldg(bo + j * 64 + 16); }
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const uint32_t w0 = (uint64_t)braw[j].x < (uint64_t)CC.c[0].q ? (uint32_t)braw[j].x : reduce_any(braw[j].x, CC.c[0].q);
+            const uint32_t w1 = (uint64_t)braw[j].y < (uint64_t)CC.c[1].q ? (uint32_t)braw[j].y : reduce_any(braw[j].y, CC.c[1].q);
+            if (j & 1) { c1[0][j >> 1] = A0.mulv(c1[0][j >> 1], w0); c1[1][j >> 1] = A1.mulv(c1[1][j >> 1], w1); }
+            else { c0[0][j >> 1] = A0.mulv(c0[0][j >> 1], w0); c0[1][j >> 1] = A1.mulv(c0[1][j >> 1], w1); }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           __stcs(out + j * 64, make_longlong2((int64_t)A0.canon(c0[0][j]), (int64_t)A1.canon(c0[1][j])));
@@ -757,10 +787,28 @@ int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t
 {
   const FusedA* F = (const FusedA*)slot;
   if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
-  // tupSize 2 has its own 128-bit kernel without the fused product: measured (config C moduli) the two kernels back to
-  // back take 2.09 ms against 2.39 ms for one strided fused launch per limb, so the pair stays unfused there
-  if (pl->k == 2 && F->cls[0] == F->cls[1]) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
+  if (pl->k == 2 && F->cls[0] == F->cls[1]) {      // both limbs in one 128-bit kernel (one strided launch per limb was measured slower than the unfused pair)
+    FusedAConsts2 CC;
+    CC.c[0] = inverse ? F->inv[0] : F->fwd[0];
+    CC.c[1] = inverse ? F->inv[1] : F->fwd[1];
+    constexpr int W = 3, MB = 5;
+    const size_t smem = 2 * kN * sizeof(uint32_t);
+    int64_t grid = (int64_t)pl->num_sms * MB;
+    if (grid > batch) grid = batch;
+    const int64_t b_stride = b_batch == 1 ? 0 : (int64_t)kN * 2;
+    if (F->cls[0] == ARITH_M) {
+      if (inverse) k_fused_a_k2<true, ArithM, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+      else k_fused_a_k2<false, ArithM, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+    } else {
+      if (inverse) k_fused_a_k2<true, ArithS, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+      else k_fused_a_k2<false, ArithS, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_k2<MUL>");
+    count_launch();
+    return LOLB_OK;
+  }
   for (int t = 0; t < pl->k; t++) {
     const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];
     int rc;
@@ -791,11 +839,11 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
     int64_t grid = (int64_t)pl->num_sms * MB;
     if (grid > batch) grid = batch;
     if (F->cls[0] == ARITH_M) {
-      if (inverse) k_fused_a_k2<true, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
-      else k_fused_a_k2<false, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
+      if (inverse) k_fused_a_k2<true, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
+      else k_fused_a_k2<false, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
     } else {
-      if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
-      else k_fused_a_k2<false, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC);
+      if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
+      else k_fused_a_k2<false, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_k2");
