@@ -207,10 +207,12 @@ k_normsq_stream(const typename R::IO* __restrict__ y, typename R::IO* __restrict
   constexpr int DA = PA - 1, DB = PB > 1 ? PB - 1 : 1;
   __shared__ T red[32];
   const R ring{};
+  // a thread's first tile is the same for every element: its index arithmetic (two divisions) is done once
+  const TileIndex ix0(G, threadIdx.x < G.tiles ? threadIdx.x : 0, DA, DB);
   for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
     T acc = ring.zero();
     for (int t = threadIdx.x; t < G.tiles; t += blockDim.x) {
-      const TileIndex ix(G, t, DA, DB);
+      const TileIndex ix = t == (int)threadIdx.x ? ix0 : TileIndex(G, t, DA, DB);
       const typename R::IO* base = y + (size_t)e * G.n + ix.off;
       T v[DB][DA], o[DB][DA];
 #pragma unroll
