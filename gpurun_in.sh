@@ -1,2 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "plain or int64 or double_and" 2>&1 | tail -3
-timeout 120 python tools/run_plain.py 14400 65536 2>&1 | grep Norm
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "host_pipeline or dataflow or config_b" 2>&1 | tail -4

@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 
 #include "fused.cuh"
 #include "lolb_internal.cuh"
@@ -167,7 +168,8 @@ extern "C" void lolb_plan_destroy(lolb_plan* pl)
 {
   if (!pl) return;
   fused_release(pl);
-  void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_ws, pl->d_stage};
+  void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_ws, pl->d_stage,
+                  pl->ws_alt[0], pl->ws_alt[1], pl->ws_alt[2]};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : pl->streams) if (s) cudaStreamDestroy(s);
   for (auto& e : pl->events) if (e) cudaEventDestroy(e);
@@ -458,10 +460,15 @@ extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t
     hInt_t* host = y + (size_t)done * plan->n * plan->k;
     cudaStream_t st = plan->streams[s];       // stream order makes slot reuse safe
     LOLB_CUDA(cudaMemcpyAsync(dev, host, (size_t)cnt * elem_bytes, cudaMemcpyHostToDevice, st));
+    std::swap(plan->d_ws, plan->ws_alt[s]);                  // this slot's private kernel workspace
+    std::swap(plan->ws_bytes, plan->ws_alt_bytes[s]);
     for (const std::string& op : names) {
       rc = apply_named_rq(plan, op, dev, cnt, st);
-      if (rc) { cudaDeviceSynchronize(); return rc; }
+      if (rc) break;
     }
+    std::swap(plan->d_ws, plan->ws_alt[s]);
+    std::swap(plan->ws_bytes, plan->ws_alt_bytes[s]);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
     LOLB_CUDA(cudaMemcpyAsync(host, dev, (size_t)cnt * elem_bytes, cudaMemcpyDeviceToHost, st));
     done += cnt;
   }

@@ -979,13 +979,22 @@ int fused_pow2_df_crt(const lolb_plan* pl, const void* slot, bool inverse, int64
   const FusedPow2Df* F = (const FusedPow2Df*)slot;
   if (!fused_pow2_df_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  if ((uint64_t)batch >= ((uint64_t)1 << 25)) return LOLB_FUSED_UNAVAILABLE;      // 32-bit task counter
-  switch (pl->k) {
-    case 1: return inverse ? launch_df_top<true, 1>(pl, F, y, batch, st) : launch_df_top<false, 1>(pl, F, y, batch, st);
-    case 2: return inverse ? launch_df_top<true, 2>(pl, F, y, batch, st) : launch_df_top<false, 2>(pl, F, y, batch, st);
-    case 4: return inverse ? launch_df_top<true, 4>(pl, F, y, batch, st) : launch_df_top<false, 4>(pl, F, y, batch, st);
+  // one launch per slab of at most 2^16 elements: bounds the per-element counters (2 x 4 bytes per element) and the
+  // 32-bit task index; a slab is >= 2 GiB of data at the smallest supported shape, so the extra launches are noise
+  const int64_t slab = 65536;
+  for (int64_t off = 0; off < batch; off += slab) {
+    const int64_t cnt = batch - off < slab ? batch - off : slab;
+    int64_t* ys = y + (size_t)off * pl->n * pl->k;
+    int rc;
+    switch (pl->k) {
+      case 1: rc = inverse ? launch_df_top<true, 1>(pl, F, ys, cnt, st) : launch_df_top<false, 1>(pl, F, ys, cnt, st); break;
+      case 2: rc = inverse ? launch_df_top<true, 2>(pl, F, ys, cnt, st) : launch_df_top<false, 2>(pl, F, ys, cnt, st); break;
+      case 4: rc = inverse ? launch_df_top<true, 4>(pl, F, ys, cnt, st) : launch_df_top<false, 4>(pl, F, ys, cnt, st); break;
+      default: return LOLB_FUSED_UNAVAILABLE;
+    }
+    if (rc) return rc;
   }
-  return LOLB_FUSED_UNAVAILABLE;
+  return LOLB_OK;
 }
 
 }  // namespace lolb

@@ -102,6 +102,10 @@ struct lolb_plan {
   // ---- workspace for elements that do not fit in shared memory
   mutable void* d_ws = nullptr;
   mutable size_t ws_bytes = 0;
+  // one private workspace per stream slot of the host pipeline (kernels with a workspace -- exchange ring, counters,
+  // spilled elements -- must not share it across concurrently running streams); swapped into d_ws around a slot's launches
+  mutable void* ws_alt[3] = {nullptr, nullptr, nullptr};
+  mutable size_t ws_alt_bytes[3] = {0, 0, 0};
   // ---- staging for the drop-in (host pointer) entry points and host-batched calls
   mutable void* d_stage = nullptr;
   mutable size_t stage_bytes = 0;

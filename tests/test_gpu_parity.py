@@ -474,6 +474,30 @@ def test_host_pipeline_matches_device_path(torch_cuda, oracle):
     assert np.array_equal(h2.numpy(), y)
 
 
+def test_host_pipeline_private_workspaces_pow2(torch_cuda, oracle):
+    """The host pipeline runs three stream slots concurrently; kernels that need a workspace (the exchange ring and
+    counters of fused_pow2_df) get one per slot.  Config B shape, three chunks of the 96 MiB staging size."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    m, qs = CONFIG_B
+    t = CudaTensorRq(m, qs)
+    B = 200
+    g = torch.Generator()
+    g.manual_seed(11)
+    y = torch.cat([torch.randint(0, q, (B, t.n, 1), dtype=torch.int64, generator=g) for q in qs], dim=2).contiguous()
+    h = y.clone().pin_memory()
+    t.apply_host("CRT", h)
+    dev = t.crt(y.cuda())
+    assert torch.equal(h.cuda(), dev)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    for b in (0, 97, B - 1):
+        assert np.array_equal(h[b].numpy(), oracle.tensorCRTRq(y[b].numpy(), pe, ru, qs))
+    t.apply_host("CRTInv", h)
+    assert torch.equal(h, y)
+    t.apply_host("CRT,CRTInv", h)
+    assert torch.equal(h, y)
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE.json configs)
 def _device_uniform(torch, B, n, qs, seed):
     g = torch.Generator(device="cuda")
