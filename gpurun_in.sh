@@ -1,1 +1,13 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "host_pipeline or dataflow or config_b" 2>&1 | tail -4
+for cfg in "16 4 23 CRT 0 0" "16 4 23 CRTInv 0 0" "16 2 23 CRT 3 1" "16 2 23 CRTInv 3 1" "14 4 23 CRT 5 4" "14 4 23 CRTInv 5 4"; do
+  set -- $cfg
+  echo "== $cfg"
+  LOLB_DF_SCHEDULE=unpaired LOLB_DF_RING=$5 LOLB_DF_LAG=$6 timeout 40 python tools/df_probe.py $1 $2 $3 $4 2>&1 | tail -3
+done
+Q4=537133057,537591809,537722881,538116097
+V=lol_b200/csrc/build/variants
+for lib in "" $V/df_nocolt.so; do
+for op in CRT CRTInv; do
+  LOLB_LIBRARY=$lib timeout 120 python tools/run_op.py 65536 $Q4 1024 $op 20
+  LOLB_LIBRARY=$lib LOLB_DF_SCHEDULE=unpaired timeout 120 python tools/run_op.py 65536 537133057,537591809 2048 $op 20
+done
+done
