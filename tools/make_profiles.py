@@ -9,7 +9,7 @@ for r in rows[1:]:
     v = v / 1e3 if r[iu] == 'ns' else (v * 1e3 if r[iu] == 'ms' else v)
     agg.setdefault(r[ik], []).append(v)
 tot = sum(sum(v) for v in agg.values())
-head = [k for k in agg if 'k_fused_a<' in k]
+head = [k for k in agg if 'k_fused_a<' in k and ', 1, 0>(' in k]      # the MUL = 0 instances are the headline CRT / CRTInv
 head_tot = sum(sum(agg[k]) for k in head)
 with open('profiles/r01_launch_list.md', 'w') as f:
     f.write('# Round 1 -- ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e`\n\n')
