@@ -1,8 +1,12 @@
-set -x
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/bench_r01c.json 2> gpurun_out/bench_r01c.err; tail -c 300 gpurun_out/bench_r01c.err
-python tools/bsum.py gpurun_out/bench_r01c.json | tail -34
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused_a -s 6 -c 2 -o gpurun_out/prof_a_final -f python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-per-op > gpurun_out/ncu_full.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+export LOLB_DF_SCHEDULE=d16
+for cfg in "16 4 23 CRT 0 0" "16 4 23 CRTInv 0 0" "16 1 23 CRT 3 1" "16 2 23 CRTInv 3 1" "14 4 23 CRT 5 4" "13 2 23 CRTInv 5 4" "15 1 23 CRT 0 0"; do
+  set -- $cfg
+  echo "== $cfg"
+  LOLB_DF_RING=$5 LOLB_DF_LAG=$6 timeout 40 python tools/df_probe.py $1 $2 $3 $4 2>&1 | tail -4
+done
+Q4=537133057,537591809,537722881,538116097
+for op in CRT CRTInv; do
+  timeout 120 python tools/run_op.py 65536 $Q4 1024 $op 20
+  timeout 120 python tools/run_op.py 65536 537133057,537591809 2048 $op 20
+  timeout 120 python tools/run_op.py 65536 537133057 4096 $op 20
+done
