@@ -1,4 +1,4 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-tail -c 300 gpurun_out/bench_n2.err
-python tools/bsum.py gpurun_out/bench_n2.json | head -8
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -c 400
+V=lol_b200/csrc/build/variants
+for lib in "" $V/a_l2pf.so; do
+  for op in CRT CRTInv; do LOLB_LIBRARY=$lib timeout 120 python tools/run_op.py 14400 14401 65536 $op 30; done
+done
