@@ -773,6 +773,163 @@ k_pow2_dfm(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams 
   flush();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small indices m = 2^10, 2^11 (n = 512, 1024: the reference's own benchmark parameters, lol/.../Benchmarks/
+// Default.hs:41-46): a limb fits one warp -- 32 residues per lane -- so the whole transform is the two register passes
+// of a chunk task with a warp-private transposition through 4 KB of shared memory.  No queue, no ring, no counters.
+// tupSize 1: every warp is independent (own loads, __syncwarp only).  tupSize 2, 4: the CTA de-interleaves a 32 KB piece
+// cooperatively (three CTA barriers per piece).  n = 512: a warp holds two limbs (16 + 16 residues per lane in the
+// second pass).
+template <bool INV, int K, int E>
+__global__ void __launch_bounds__(128, 5)
+k_pow2_small(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P)
+{
+  constexpr int n = 1 << (E - 1);                       // 512 or 1024
+  constexpr int UPW = 1024 / n;                         // (element, limb) units per warp
+  constexpr int UW = n + n / 32 + (E == 11 ? 8 : 0);    // words per unit: 1064 / 528 (528 = 16 mod 32: the two units of a warp hit disjoint banks)
+  constexpr int S1 = E - 6;                             // rounds of the second pass: 5 or 4
+  constexpr int V1 = 1 << S1;                           // residues per lane and unit in the second pass
+  constexpr int LG = K == 1 ? 32 : 128;                 // threads that load one contiguous piece together
+  constexpr int UPG = K == 1 ? UPW : 4 * UPW;           // units per loader group
+  constexpr int EPG = UPG / K;                          // ring elements per loader group
+  constexpr int PIECES = (UPG * n) / (2 * LG);          // 16-byte pieces per thread (= 16)
+  constexpr int STEP = (2 * LG) / K;                    // coefficients between consecutive pieces of a thread
+  static_assert(EPG >= 1 && PIECES == 16 && n % STEP == 0 && STEP % 32 == 0, "geometry");
+  __shared__ __align__(16) uint32_t U[4 * UPW * UW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tg = K == 1 ? lane : tid;                   // index inside the loader group
+  const int grp = K == 1 ? warp : 0;                    // loader group inside the CTA
+  const int groups_per_cta = K == 1 ? 4 : 1;
+  const int l0 = (2 * tg) % K, c0 = (2 * tg) / K;
+  uint32_t* ubase = U + (grp * UPG + l0) * UW + c0 + (c0 >> 5);
+  constexpr int second = K == 1 ? 1 : UW;
+  auto piece_off = [](int ii) { return ((STEP * ii) / n) * K * UW + ((STEP * ii) % n) + (((STEP * ii) % n) >> 5); };
+  auto piece_el = [](int ii) { return (STEP * ii) / n; };                 // element (inside the group) of piece ii
+  auto sync_group = [&]() { if (K == 1) __syncwarp(); else __syncthreads(); };
+
+  const int64_t ngroups = (batch + EPG - 1) / EPG;
+  for (int64_t g = (int64_t)blockIdx.x * groups_per_cta + grp; g < ngroups; g += (int64_t)gridDim.x * groups_per_cta) {
+    const int64_t e0 = g * EPG;
+    const int cnt = (int)(batch - e0 < EPG ? batch - e0 : EPG);           // ring elements of this group that exist
+    longlong2* gp = reinterpret_cast<longlong2*>(y + (size_t)e0 * n * K) + tg;
+    // this warp's units: u = first + h, element u / K, limb u % K
+    const int ufirst = K == 1 ? 0 : warp * UPW;                           // inside the group
+    uint32_t* Uw = U + (grp * UPG + ufirst) * UW;                         // this warp's first unit
+
+    if (!INV || K > 1) {
+      // contiguous piece -> units, limbs de-interleaved
+      const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
+      longlong2 raw[PIECES];
+#pragma unroll
+      for (int ii = 0; ii < PIECES; ii++) raw[ii] = piece_el(ii) < cnt ? __ldcs(gp + LG * ii) : make_longlong2(0, 0);
+      uint32_t hi_or = 0, max0 = 0, max1 = 0;
+#pragma unroll
+      for (int ii = 0; ii < PIECES; ii++) {
+        hi_or |= (uint32_t)((uint64_t)raw[ii].x >> 32) | (uint32_t)((uint64_t)raw[ii].y >> 32);
+        max0 = max(max0, (uint32_t)raw[ii].x);
+        max1 = max(max1, (uint32_t)raw[ii].y);
+        ubase[piece_off(ii)] = (uint32_t)raw[ii].x;
+        ubase[piece_off(ii) + second] = (uint32_t)raw[ii].y;
+      }
+      if (hi_or != 0 || max0 >= q0 || max1 >= q1) {      // outside the Haskell contract: reduce like the reference's c % q
+#pragma unroll 1
+        for (int ii = 0; ii < PIECES; ii++) {
+          if (piece_el(ii) >= cnt) continue;
+          const longlong2 r = gp[LG * ii];
+          ubase[piece_off(ii)] = df_reduce_any64(r.x, q0);
+          ubase[piece_off(ii) + second] = df_reduce_any64(r.y, q1);
+        }
+      }
+      sync_group();
+    }
+
+    // ---- the two register passes on this warp's unit(s)
+    if (!INV) {
+      // rounds 0-4: lane owns 32 consecutive residues (n = 512: lanes 0-15 the first unit, 16-31 the second)
+      {
+        const int hu = UPW == 1 ? 0 : lane >> 4, blk = UPW == 1 ? lane : lane & 15;
+        const int limb = (ufirst + hu) % K;
+        unit_rounds_0_4_rt<false>(limb, Uw + hu * UW - 33 * lane + 33 * blk, P, lane);      // base + 33 * blk
+      }
+      __syncwarp();
+      // rounds 5 .. e-2: lane owns residues lane + 32 j of each unit
+#pragma unroll
+      for (int h = 0; h < UPW; h++) {
+        const int u = ufirst + h, limb = u % K, el = u / K;
+        const DfLimb& L = P.limb[limb];
+        const Mont M{L.q, L.q2, L.qinv};
+        uint32_t* ub = Uw + h * UW + lane;
+        uint32_t v[V1];
+#pragma unroll
+        for (int j = 0; j < V1; j++) v[j] = ub[33 * j];
+        const uint32_t* twl = L.tw + lane;
+        ct_rounds<S1, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+        if (K == 1) {
+          if (el < cnt) {
+            int64_t* out = y + (size_t)(e0 + el) * n + lane;
+#pragma unroll
+            for (int j = 0; j < V1; j++) __stcs(out + 32 * j, (int64_t)M.canon(M.fold(v[j])));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < V1; j++) ub[33 * j] = M.canon(M.fold(v[j]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < UPW; h++) {
+        const int u = ufirst + h, limb = u % K, el = u / K;
+        const DfLimb& L = P.limb[limb];
+        const Mont M{L.q, L.q2, L.qinv};
+        uint32_t* ub = Uw + h * UW + lane;
+        uint32_t v[V1];
+        if (K == 1) {
+          const int64_t* in = y + (size_t)(e0 + (el < cnt ? el : 0)) * n + lane;
+          uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+          for (int j = 0; j < V1; j++) {
+            const int64_t raw = __ldcs(in + 32 * j);
+            v[j] = (uint32_t)raw;
+            hi_or |= (uint32_t)((uint64_t)raw >> 32);
+            lo_max = max(lo_max, v[j]);
+          }
+          if (hi_or != 0 || lo_max >= L.q) {
+#pragma unroll
+            for (int j = 0; j < V1; j++) v[j] = df_reduce_any64(in[32 * j], L.q);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < V1; j++) v[j] = ub[33 * j];
+        }
+        const uint32_t* twl = L.tw + lane;
+        gs_rounds<S1, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+        for (int j = 0; j < V1; j++) ub[33 * j] = v[j];
+      }
+      __syncwarp();
+      {
+        const int hu = UPW == 1 ? 0 : lane >> 4, blk = UPW == 1 ? lane : lane & 15;
+        const int limb = (ufirst + hu) % K;
+        unit_rounds_0_4_rt<true>(limb, Uw + hu * UW - 33 * lane + 33 * blk, P, lane);
+      }
+    }
+
+    if (INV || K > 1) {
+      // units -> contiguous piece (canonical residues), coalesced 128-bit stores
+      sync_group();
+#pragma unroll
+      for (int ii = 0; ii < PIECES; ii++) {
+        if (piece_el(ii) < cnt) {
+          const uint32_t x0 = ubase[piece_off(ii)], x1 = ubase[piece_off(ii) + second];
+          __stcs(gp + LG * ii, make_longlong2((int64_t)x0, (int64_t)x1));
+        }
+      }
+    }
+    sync_group();      // U is reused by the next group
+  }
+}
+
 struct FusedPow2Df {
   bool ok_fwd = false, ok_inv = false;
   DfParams fwd{}, inv{};
@@ -791,9 +948,9 @@ bool shape_ok(const lolb_plan* pl)
 {
   if (pl->kind != PLAN_RQ || pl->pe.size() != 1 || pl->pe[0].prime != 2) return false;
   const int e = pl->pe[0].exponent;
-  if (e < 13 || e > 16) return false;
+  if (e != 10 && e != 11 && (e < 13 || e > 16)) return false;       // 2^12 stays on fused_pow2 (limb in shared memory)
   if (pl->k != 1 && pl->k != 2 && pl->k != 4) return false;
-  if (((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // chunk tasks of kDfWarps units must tile the element
+  if (e >= 13 && ((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // chunk tasks of kDfWarps units must tile the element
   for (int64_t q : pl->qs) if (!(q & 1) || 4 * (uint64_t)q >= ((uint64_t)1 << 32)) return false;
   return true;
 }
@@ -884,9 +1041,31 @@ int launch_dfm(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t ba
   }
 }
 
+template <bool INV, int K, int E>
+int launch_small(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  static int per_sm = 0;
+  if (!per_sm) {
+    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_small<INV, K, E>, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  constexpr int n = 1 << (E - 1), upw = 1024 / n;
+  const int64_t el_per_cta = K == 1 ? 4 * upw : (4 * upw) / K;      // ring elements one CTA iteration covers
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  const int64_t need = (batch + el_per_cta - 1) / el_per_cta;
+  if (grid > need) grid = need;
+  k_pow2_small<INV, K, E><<<(int)grid, 128, 0, st>>>(y, batch, INV ? F->inv : F->fwd);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_pow2_small");
+  count_launch();
+  return LOLB_OK;
+}
+
 template <bool INV, int K>
 int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
+  if (F->top == 0) return launch_small<INV, K, 11>(pl, F, y, batch, st);
+  if (F->top == -1) return launch_small<INV, K, 10>(pl, F, y, batch, st);
   // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2
   // paired (63 % / 59 %, 60 % / 58 % vs 61 % / 59 %, 58 % / 57 %).  Keeping the rounds 5-9 twiddles in shared memory
   // instead of L1 was measured too: no gain, and it costs the paired kernel a CTA per SM.

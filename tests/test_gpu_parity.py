@@ -323,9 +323,11 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("schedule", ["paired", "unpaired"])
 @pytest.mark.parametrize("ring,lag", [(3, 1), (5, 4), (48, 12)], ids=lambda v: str(v))
-@pytest.mark.parametrize("e,k", [(13, 1), (13, 2), (13, 4), (14, 4), (15, 2), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
+@pytest.mark.parametrize("e,k", [(10, 1), (10, 2), (10, 4), (11, 1), (11, 2), (11, 4), (13, 1), (13, 2), (13, 4), (14, 4), (15, 2), (16, 1), (16, 2),
+                                 (16, 4)], ids=lambda v: str(v))
 def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, ring, lag, schedule):
-    """fused_pow2_df (persistent dataflow kernels, L2 exchange ring) for tupSize 1, 2, 4, both schedules: batches
+    """fused_pow2_df for tupSize 1, 2, 4: the warp-resident kernel of m = 2^10, 2^11 (ragged groups) and the persistent
+    dataflow kernels with the L2 exchange ring from m = 2^13 on, both schedules: batches
     larger than the ring so slots are reused, tiny rings so the per-element counters and the slot-reuse ordering are
     exercised (this is the test that caught a lane-0-only fence); oracle parity on a sample of elements, the generic
     engine on all of them, and crtInv . crt = id."""
