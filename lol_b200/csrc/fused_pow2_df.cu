@@ -930,6 +930,184 @@ k_pow2_small(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfP
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Middle indices m = 2^12 (tupSize 1, 2, 4) and 2^13 (tupSize 1, 2): one ring element (all limbs, <= 34 KB as u32) is
+// resident in the shared memory of a 128-thread CTA.  The (chunk, limb) units of 1024 residues go through the two
+// register passes of a chunk task, one warp per unit; the remaining 1-2 rounds couple the chunks and run with a thread
+// per coefficient (2-4 residues at stride 1024, eight coefficients per thread in flight).  Four CTA barriers per
+// element, no queue and no ring; 5 CTAs per SM overlap each other's phases.
+template <bool INV, int K, int E>
+__global__ void __launch_bounds__(128, 5)
+k_pow2_mid(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P)
+{
+  constexpr int n = 1 << (E - 1);                       // 2048 or 4096
+  constexpr int NCH = n / 1024;                         // chunks per limb: 2 or 4
+  constexpr int T = E - 11;                             // top rounds: 1 or 2
+  constexpr int NV = 1 << T;
+  constexpr int UW = kDfUnit;
+  constexpr int EPC = NCH * K >= 4 ? 1 : 4 / (NCH * K);   // ring elements per CTA iteration: every warp gets a unit (2 at m = 2^12, tupSize 1)
+  constexpr int UNITS = NCH * K * EPC;
+  constexpr int PIECES = (n * K * EPC) / (2 * 128);     // 16-byte pieces per thread: 16 or 32
+  constexpr int STEP = 256 / K;
+  static_assert(UNITS * UW * 4 <= 40 * 1024 && 1024 % STEP == 0 && STEP % 32 == 0, "geometry");
+  extern __shared__ __align__(16) uint32_t U[];         // [UNITS][UW], unit = (element * NCH + chunk) * K + limb
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l0 = (2 * tid) % K, c0 = (2 * tid) / K;
+  uint32_t* ubase = U + l0 * UW + c0 + (c0 >> 5);
+  constexpr int second = K == 1 ? 1 : UW;
+  auto piece_off = [](int ii) { return ((STEP * ii) >> 10) * K * UW + ((STEP * ii) & 1023) + (((STEP * ii) & 1023) >> 5); };
+
+  // rounds 10 .. e-2 on the residues x + 1024 j of limb l, eight coefficients x = tid + 128 i per thread
+  auto top_pass = [&](int64_t* gbase, int cnt) {
+#pragma unroll 1
+    for (int el_l = 0; el_l < EPC * K; el_l++) {
+      const int l = el_l % K, eo = el_l / K;
+      if (eo >= cnt) break;
+      int64_t* ebase = gbase + (size_t)eo * n * K;
+      uint32_t* Ue = U + eo * NCH * K * UW;
+      const DfLimb& L = P.limb[l];
+      const Mont M{L.q, L.q2, L.qinv};
+      uint32_t v[8][NV];
+      if (INV && K == 1) {                              // straight from HBM: lanes are consecutive coefficients
+        uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < NV; j++) {
+            const int64_t raw = __ldcs(ebase + tid + 128 * i + 1024 * j);
+            v[i][j] = (uint32_t)raw;
+            hi_or |= (uint32_t)((uint64_t)raw >> 32);
+            lo_max = max(lo_max, v[i][j]);
+          }
+        if (hi_or != 0 || lo_max >= L.q) {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < NV; j++) v[i][j] = df_reduce_any64(ebase[tid + 128 * i + 1024 * j], L.q);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int x = tid + 128 * i;
+#pragma unroll
+          for (int j = 0; j < NV; j++) v[i][j] = Ue[(j * K + l) * UW + x + (x >> 5)];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const uint32_t* twx = L.tw + tid + 128 * i;
+        if (!INV) ct_rounds<T, false>(v[i], M, [&](int a, int jj) { return __ldg(twx + ((1024 << a) - 1 + 1024 * jj)); });
+        else gs_rounds<T, 0>(v[i], M, [&](int a, int jj) { return __ldg(twx + ((1024 << a) - 1 + 1024 * jj)); });
+      }
+      if (!INV && K == 1) {                             // straight to HBM
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < NV; j++) __stcs(ebase + tid + 128 * i + 1024 * j, (int64_t)M.canon(M.fold(v[i][j])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int x = tid + 128 * i;
+#pragma unroll
+          for (int j = 0; j < NV; j++) Ue[(j * K + l) * UW + x + (x >> 5)] = INV ? v[i][j] : M.canon(M.fold(v[i][j]));
+        }
+      }
+    }
+  };
+
+  // the two register passes of every (chunk, limb) unit, one warp per unit
+  auto unit_passes = [&]() {
+#pragma unroll 1
+    for (int u = warp; u < UNITS; u += 4) {
+      const int limb = u % K;
+      const DfLimb& L = P.limb[limb];
+      const Mont M{L.q, L.q2, L.qinv};
+      uint32_t* Uu = U + u * UW;
+      const uint32_t* twl = L.tw + lane;
+      if (!INV) {
+        unit_rounds_0_4_rt<false>(limb, Uu, P, lane);
+        __syncwarp();
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
+        ct_rounds<5, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+        for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
+      } else {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
+        gs_rounds<5, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+        for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
+        __syncwarp();
+        unit_rounds_0_4_rt<true>(limb, Uu, P, lane);
+      }
+    }
+  };
+
+  auto piece_el = [](int ii) { return (STEP * ii) / n; };                 // element (inside the CTA's group) of piece ii
+  const int64_t ngroups = (batch + EPC - 1) / EPC;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t e = g * EPC;
+    const int cnt = (int)(batch - e < EPC ? batch - e : EPC);
+    int64_t* ebase = y + (size_t)e * n * K;
+    longlong2* gp = reinterpret_cast<longlong2*>(ebase) + tid;
+    if (!(INV && K == 1)) {
+      // element -> units, limbs de-interleaved (at most 16 pieces in flight per thread)
+      const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
+#pragma unroll
+      for (int part = 0; part < (PIECES + 15) / 16; part++) {
+        constexpr int PP = PIECES < 16 ? PIECES : 16;
+        longlong2 raw[PP];
+#pragma unroll
+        for (int i = 0; i < PP; i++) raw[i] = piece_el(part * 16 + i) < cnt ? __ldcs(gp + 128 * (part * 16 + i)) : make_longlong2(0, 0);
+        uint32_t hi_or = 0, max0 = 0, max1 = 0;
+#pragma unroll
+        for (int i = 0; i < PP; i++) {
+          hi_or |= (uint32_t)((uint64_t)raw[i].x >> 32) | (uint32_t)((uint64_t)raw[i].y >> 32);
+          max0 = max(max0, (uint32_t)raw[i].x);
+          max1 = max(max1, (uint32_t)raw[i].y);
+          ubase[piece_off(part * 16 + i)] = (uint32_t)raw[i].x;
+          ubase[piece_off(part * 16 + i) + second] = (uint32_t)raw[i].y;
+        }
+        if (hi_or != 0 || max0 >= q0 || max1 >= q1) {      // outside the Haskell contract: reduce like the reference's c % q
+#pragma unroll 1
+          for (int i = 0; i < PP; i++) {
+            if (piece_el(part * 16 + i) >= cnt) continue;
+            const longlong2 r = gp[128 * (part * 16 + i)];
+            ubase[piece_off(part * 16 + i)] = df_reduce_any64(r.x, q0);
+            ubase[piece_off(part * 16 + i) + second] = df_reduce_any64(r.y, q1);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!INV) {
+      unit_passes();
+      __syncthreads();
+      top_pass(ebase, cnt);
+    } else {
+      top_pass(ebase, cnt);
+      __syncthreads();
+      unit_passes();
+    }
+    if (!(!INV && K == 1)) {
+      // units -> element (canonical residues), coalesced 128-bit stores
+      __syncthreads();
+#pragma unroll
+      for (int ii = 0; ii < PIECES; ii++) {
+        if (piece_el(ii) < cnt) {
+          const uint32_t x0 = ubase[piece_off(ii)], x1 = ubase[piece_off(ii) + second];
+          __stcs(gp + 128 * ii, make_longlong2((int64_t)x0, (int64_t)x1));
+        }
+      }
+    }
+    __syncthreads();      // U is reused by the next group
+  }
+}
+
 struct FusedPow2Df {
   bool ok_fwd = false, ok_inv = false;
   DfParams fwd{}, inv{};
@@ -948,9 +1126,9 @@ bool shape_ok(const lolb_plan* pl)
 {
   if (pl->kind != PLAN_RQ || pl->pe.size() != 1 || pl->pe[0].prime != 2) return false;
   const int e = pl->pe[0].exponent;
-  if (e != 10 && e != 11 && (e < 13 || e > 16)) return false;       // 2^12 stays on fused_pow2 (limb in shared memory)
+  if (e < 10 || e > 16) return false;
   if (pl->k != 1 && pl->k != 2 && pl->k != 4) return false;
-  if (e >= 13 && ((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // chunk tasks of kDfWarps units must tile the element
+  if (e >= 13 && !(e == 13 && pl->k <= 2) && ((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // chunk tasks of kDfWarps units must tile the element
   for (int64_t q : pl->qs) if (!(q & 1) || 4 * (uint64_t)q >= ((uint64_t)1 << 32)) return false;
   return true;
 }
@@ -1061,9 +1239,31 @@ int launch_small(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
   return LOLB_OK;
 }
 
+template <bool INV, int K, int E>
+int launch_mid(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  constexpr int units1 = ((1 << (E - 1)) / 1024) * K, epc = units1 >= 4 ? 1 : 4 / units1;
+  constexpr int smem = units1 * epc * kDfUnit * 4;
+  static int per_sm = 0;
+  if (!per_sm) {
+    LOLB_CUDA(cudaFuncSetAttribute(k_pow2_mid<INV, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_mid<INV, K, E>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > (batch + epc - 1) / epc) grid = (batch + epc - 1) / epc;
+  k_pow2_mid<INV, K, E><<<(int)grid, 128, smem, st>>>(y, batch, INV ? F->inv : F->fwd);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_pow2_mid");
+  count_launch();
+  return LOLB_OK;
+}
+
 template <bool INV, int K>
 int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
+  if (F->top == 1) return launch_mid<INV, K, 12>(pl, F, y, batch, st);
+  if constexpr (K <= 2) { if (F->top == 2 && !getenv("LOLB_POW2_MID_OFF")) return launch_mid<INV, K, 13>(pl, F, y, batch, st); }
   if (F->top == 0) return launch_small<INV, K, 11>(pl, F, y, batch, st);
   if (F->top == -1) return launch_small<INV, K, 10>(pl, F, y, batch, st);
   // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2
