@@ -931,25 +931,26 @@ k_pow2_small(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Middle indices m = 2^12 (tupSize 1, 2, 4) and 2^13 (tupSize 1, 2): one ring element (all limbs, <= 34 KB as u32) is
+// Middle indices m = 2^12, 2^13 (tupSize 1, 2, 4) and 2^14 (tupSize 1): one ring element (all limbs, 17-68 KB as u32) is
 // resident in the shared memory of a 128-thread CTA.  The (chunk, limb) units of 1024 residues go through the two
-// register passes of a chunk task, one warp per unit; the remaining 1-2 rounds couple the chunks and run with a thread
+// register passes of a chunk task, one warp per unit; the remaining 1-3 rounds couple the chunks and run with a thread
 // per coefficient (2-4 residues at stride 1024, eight coefficients per thread in flight).  Four CTA barriers per
 // element, no queue and no ring; 5 CTAs per SM overlap each other's phases.
 template <bool INV, int K, int E>
 __global__ void __launch_bounds__(128, 5)
 k_pow2_mid(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P)
 {
-  constexpr int n = 1 << (E - 1);                       // 2048 or 4096
-  constexpr int NCH = n / 1024;                         // chunks per limb: 2 or 4
-  constexpr int T = E - 11;                             // top rounds: 1 or 2
+  constexpr int n = 1 << (E - 1);                       // 2048 .. 8192
+  constexpr int NCH = n / 1024;                         // chunks per limb: 2, 4, 8
+  constexpr int T = E - 11;                             // top rounds: 1 .. 3
+  constexpr int XI = T <= 2 ? 8 : 4;                    // coefficients per thread in flight in the top pass (<= 32 residues)
   constexpr int NV = 1 << T;
   constexpr int UW = kDfUnit;
   constexpr int EPC = NCH * K >= 4 ? 1 : 4 / (NCH * K);   // ring elements per CTA iteration: every warp gets a unit (2 at m = 2^12, tupSize 1)
   constexpr int UNITS = NCH * K * EPC;
   constexpr int PIECES = (n * K * EPC) / (2 * 128);     // 16-byte pieces per thread: 16 or 32
   constexpr int STEP = 256 / K;
-  static_assert(UNITS * UW * 4 <= 40 * 1024 && 1024 % STEP == 0 && STEP % 32 == 0, "geometry");
+  static_assert(UNITS * UW * 4 <= 72 * 1024 && 1024 % STEP == 0 && STEP % 32 == 0, "geometry");
   extern __shared__ __align__(16) uint32_t U[];         // [UNITS][UW], unit = (element * NCH + chunk) * K + limb
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -968,50 +969,54 @@ k_pow2_mid(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfPar
       uint32_t* Ue = U + eo * NCH * K * UW;
       const DfLimb& L = P.limb[l];
       const Mont M{L.q, L.q2, L.qinv};
-      uint32_t v[8][NV];
+#pragma unroll 1
+      for (int ib = 0; ib < 8; ib += XI) {
+      uint32_t v[XI][NV];
+      const int xt = tid + 128 * ib;                      // first coefficient of this thread in this block
       if (INV && K == 1) {                              // straight from HBM: lanes are consecutive coefficients
         uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < XI; i++)
 #pragma unroll
           for (int j = 0; j < NV; j++) {
-            const int64_t raw = __ldcs(ebase + tid + 128 * i + 1024 * j);
+            const int64_t raw = __ldcs(ebase + xt + 128 * i + 1024 * j);
             v[i][j] = (uint32_t)raw;
             hi_or |= (uint32_t)((uint64_t)raw >> 32);
             lo_max = max(lo_max, v[i][j]);
           }
         if (hi_or != 0 || lo_max >= L.q) {
 #pragma unroll
-          for (int i = 0; i < 8; i++)
+          for (int i = 0; i < XI; i++)
 #pragma unroll
-            for (int j = 0; j < NV; j++) v[i][j] = df_reduce_any64(ebase[tid + 128 * i + 1024 * j], L.q);
+            for (int j = 0; j < NV; j++) v[i][j] = df_reduce_any64(ebase[xt + 128 * i + 1024 * j], L.q);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int x = tid + 128 * i;
+        for (int i = 0; i < XI; i++) {
+          const int x = xt + 128 * i;
 #pragma unroll
           for (int j = 0; j < NV; j++) v[i][j] = Ue[(j * K + l) * UW + x + (x >> 5)];
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const uint32_t* twx = L.tw + tid + 128 * i;
+      for (int i = 0; i < XI; i++) {
+        const uint32_t* twx = L.tw + xt + 128 * i;
         if (!INV) ct_rounds<T, false>(v[i], M, [&](int a, int jj) { return __ldg(twx + ((1024 << a) - 1 + 1024 * jj)); });
         else gs_rounds<T, 0>(v[i], M, [&](int a, int jj) { return __ldg(twx + ((1024 << a) - 1 + 1024 * jj)); });
       }
       if (!INV && K == 1) {                             // straight to HBM
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < XI; i++)
 #pragma unroll
-          for (int j = 0; j < NV; j++) __stcs(ebase + tid + 128 * i + 1024 * j, (int64_t)M.canon(M.fold(v[i][j])));
+          for (int j = 0; j < NV; j++) __stcs(ebase + xt + 128 * i + 1024 * j, (int64_t)M.canon(M.fold(v[i][j])));
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int x = tid + 128 * i;
+        for (int i = 0; i < XI; i++) {
+          const int x = xt + 128 * i;
 #pragma unroll
           for (int j = 0; j < NV; j++) Ue[(j * K + l) * UW + x + (x >> 5)] = INV ? v[i][j] : M.canon(M.fold(v[i][j]));
         }
+      }
       }
     }
   };
@@ -1128,7 +1133,7 @@ bool shape_ok(const lolb_plan* pl)
   const int e = pl->pe[0].exponent;
   if (e < 10 || e > 16) return false;
   if (pl->k != 1 && pl->k != 2 && pl->k != 4) return false;
-  if (e >= 13 && !(e == 13 && pl->k <= 2) && ((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // chunk tasks of kDfWarps units must tile the element
+  if (e >= 14 && ((1 << (e - 11)) * pl->k) % kDfWarps != 0) return false;      // dataflow: chunk tasks of kDfWarps units must tile the element
   for (int64_t q : pl->qs) if (!(q & 1) || 4 * (uint64_t)q >= ((uint64_t)1 << 32)) return false;
   return true;
 }
@@ -1263,7 +1268,13 @@ template <bool INV, int K>
 int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
   if (F->top == 1) return launch_mid<INV, K, 12>(pl, F, y, batch, st);
-  if constexpr (K <= 2) { if (F->top == 2 && !getenv("LOLB_POW2_MID_OFF")) return launch_mid<INV, K, 13>(pl, F, y, batch, st); }
+  // measured (B200, % of HBM peak forward / inverse, element-resident vs dataflow): m = 2^13: tupSize 1 82 / 78 vs 62 / 51,
+  // tupSize 2 69 / 67 vs 56 / -, tupSize 4 (68 KB, 3 CTAs/SM) 55 / 56 vs 30 / 27; m = 2^14: tupSize 1 70 / 58 vs 65 / 56,
+  // tupSize 2 (68 KB) 55 / 54 vs 63 / 54 -> dataflow from there on
+  if (!getenv("LOLB_POW2_MID_OFF")) {
+    if (F->top == 2) return launch_mid<INV, K, 13>(pl, F, y, batch, st);
+    if constexpr (K == 1) { if (F->top == 3) return launch_mid<INV, K, 14>(pl, F, y, batch, st); }
+  }
   if (F->top == 0) return launch_small<INV, K, 11>(pl, F, y, batch, st);
   if (F->top == -1) return launch_small<INV, K, 10>(pl, F, y, batch, st);
   // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2

@@ -323,8 +323,8 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("schedule", ["paired", "unpaired", "resident"])
 @pytest.mark.parametrize("ring,lag", [(3, 1), (5, 4), (48, 12)], ids=lambda v: str(v))
-@pytest.mark.parametrize("e,k", [(10, 1), (10, 2), (10, 4), (11, 1), (11, 2), (11, 4), (12, 1), (12, 2), (12, 4), (13, 1), (13, 2), (13, 4), (14, 4),
-                                 (15, 2), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
+@pytest.mark.parametrize("e,k", [(10, 1), (10, 2), (10, 4), (11, 1), (11, 2), (11, 4), (12, 1), (12, 2), (12, 4), (13, 1), (13, 2), (13, 4), (14, 1),
+                                 (14, 4), (15, 2), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
 def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, ring, lag, schedule):
     """fused_pow2_df for tupSize 1, 2, 4: the warp-resident kernel of m = 2^10, 2^11 (ragged groups) and the persistent
     kernel with the whole element in shared memory at m = 2^12, 2^13, and the persistent dataflow kernels with the L2
@@ -337,7 +337,7 @@ def test_power_of_two_dataflow_kernel(torch_cuda, oracle, monkeypatch, e, k, rin
     monkeypatch.setenv("LOLB_DF_RING", str(ring))
     monkeypatch.setenv("LOLB_DF_LAG", str(lag))
     if schedule == "resident":        # element-resident kernels where they exist (m <= 2^12, m = 2^13 with tupSize <= 2)
-        if e >= 14 or (e == 13 and k == 4) or ring != 48:
+        if e >= 15 or (e == 14 and k > 1) or ring != 48:
             pytest.skip("no element-resident kernel for this shape / ring size does not apply")
     else:
         if e <= 12 and ring != 48:
