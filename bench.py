@@ -343,6 +343,7 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         rq_config(65536, [537133057, 537591809, 537722881, 538116097], 1024, "configs[2]: m=2^16, four ~30-bit primes")
         rq_config(14400, [1008001, 1065601], 32768, "configs[3] moduli: m=14400, q=(1008001,1065601) (SymmSHE key-switch modulus)")
+        rq_config(2048, [12289], 131072, "the reference's own benchmark parameters (lol Benchmarks/Default.hs:41-46): m=2^11, q=12289")
         from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
         Bg = 32768
         tr, ti, tcx = CudaTensorReal(M), CudaTensorInt(M), CudaTensorComplex(M)
