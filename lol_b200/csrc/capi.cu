@@ -227,6 +227,8 @@ static int crt_rq(const lolb_plan* plan, bool inverse, hInt_t* y, int64_t batch,
   if (!plan->force_generic) {
     int rc = fused_crt_rq(plan, inverse, y, batch, st);
     if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+    rc = engine_axis_crt_zq(plan, inverse, y, batch, st);
+    if (rc != -1) return rc;
   }
   return engine_crt_zq(plan, inverse, y, batch, st);
 }
@@ -351,6 +353,8 @@ extern "C" int lolb_tensorCRTC(const lolb_plan* plan, lolb_complex* y, int64_t b
   if (!plan->force_generic) {
     int rc = fused_crt_c(plan, false, (double2*)y, batch, (cudaStream_t)stream);
     if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+    rc = engine_axis_crt_c(plan, false, (double2*)y, batch, (cudaStream_t)stream);
+    if (rc != -1) return rc;
   }
   return engine_crt_c(plan, false, (double2*)y, batch, (cudaStream_t)stream);
 }
@@ -361,6 +365,8 @@ extern "C" int lolb_tensorCRTInvC(const lolb_plan* plan, lolb_complex* y, int64_
   if (!plan->force_generic) {
     int rc = fused_crt_c(plan, true, (double2*)y, batch, (cudaStream_t)stream);
     if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+    rc = engine_axis_crt_c(plan, true, (double2*)y, batch, (cudaStream_t)stream);
+    if (rc != -1) return rc;
   }
   return engine_crt_c(plan, true, (double2*)y, batch, (cudaStream_t)stream);
 }

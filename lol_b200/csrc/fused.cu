@@ -87,6 +87,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
     if (!strcmp(op, "CRT") && fused_pow2_available(s->pow2, false)) return "fused_pow2";
     if (!strcmp(op, "CRTInv") && fused_pow2_available(s->pow2, true)) return "fused_pow2";
   }
+  if ((!strcmp(op, "CRT") || !strcmp(op, "CRTC")) && engine_axis_supported(pl, false)) return "engine_axis";
+  if ((!strcmp(op, "CRTInv") || !strcmp(op, "CRTInvC")) && engine_axis_supported(pl, true)) return "engine_axis";
   if (!strcmp(op, "mulRq") || !strcmp(op, "MulGCRT") || !strcmp(op, "DivGCRT")) return ((int64_t)pl->n * pl->k) % 2 == 0 ? "mul_stream" : "generic";
   if (pl->kind == PLAN_RQ && (!strcmp(op, "L") || !strcmp(op, "LInv") || !strcmp(op, "GPow") || !strcmp(op, "GDec") ||
                               !strcmp(op, "GInvPow") || !strcmp(op, "GInvDec")))

@@ -147,6 +147,10 @@ enum Finish : int32_t {
   FIN_REAL_SCALE,   // C64: * rscale (real)
 };
 int engine_crt_zq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+// engine_axis.cu -- one prime power at a time in registers; -1 = shape not supported, use engine_crt_*
+int engine_axis_crt_zq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int engine_axis_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cudaStream_t st);
+bool engine_axis_supported(const lolb_plan* pl, bool inverse);
 int engine_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cudaStream_t st);
 int engine_line_zq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
 int engine_line_i64(const lolb_plan* pl, int kind, int64_t divisor, int16_t* ok, int64_t* y, int64_t batch, cudaStream_t st);
