@@ -62,6 +62,21 @@ __device__ __forceinline__ void dense_regs(typename R::T (&v)[PHI], const R& rin
         out[0] = ring.add(in[0], in[1]);
         out[1] = ring.sub(in[0], in[1]);
       } else {
+        if constexpr (sizeof(T) == 4) {
+          // Z_q with q < 2^30 (checked on the host): a row is accumulated as exact 64-bit products (at most 13 terms
+          // < 2^60 each) and reduced ONCE; same residue as the reference's term-by-term reduction
+#pragma unroll
+          for (int row = 0; row < D; row++) {
+            uint64_t acc = 0, shift = 0;
+#pragma unroll
+            for (int col = 0; col < D; col++) {
+              const int wi = KIND == PASS_DFT ? (row * col) % P_ : KIND == PASS_CRT ? ((row + 1) * col) % P_ : (row * (col + 1)) % P_;
+              acc += (uint64_t)in[col] * w[wi];
+              if (KIND == PASS_CRTINV) shift += (uint64_t)in[col] * w[P_ - col - 1];
+            }
+            out[row] = KIND == PASS_CRTINV ? ring.sub(ring.reduce64(acc), ring.reduce64(shift)) : ring.reduce64(acc);
+          }
+        } else {
 #pragma unroll
         for (int row = 0; row < D; row++) {
           T acc = ring.zero();
@@ -81,6 +96,7 @@ __device__ __forceinline__ void dense_regs(typename R::T (&v)[PHI], const R& rin
             acc = ring.sub(acc, shift);
           }
           out[row] = acc;
+        }
         }
       }
 #pragma unroll
@@ -327,6 +343,7 @@ int launch_axis(const lolb_plan* pl, bool inverse, typename R::IO* y, int64_t ba
 int engine_axis_crt_zq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
 {
   if (batch <= 0) return LOLB_OK;
+  for (int64_t q : pl->qs) if (q >= ((int64_t)1 << 30)) return -1;      // lazy 64-bit row accumulation needs q < 2^30
   AxParams<ZqRing, uint32_t> P{};
   P.zc = inverse ? pl->zq_mhat : pl->zq_plain;
   return launch_axis<ZqRing, uint32_t>(pl, inverse, y, batch, inverse ? pl->d_tab_inv : pl->d_tab_fwd,
@@ -348,6 +365,7 @@ bool engine_axis_supported(const lolb_plan* pl, bool inverse)
   const PassList& PL = inverse ? pl->crt_inv : pl->crt_fwd;
   if (!(inverse ? pl->has_inv : pl->has_fwd)) return false;
   if (!build_axes(pl, PL, inverse, &AX)) return false;
+  if (pl->kind == PLAN_RQ) for (int64_t q : pl->qs) if (q >= ((int64_t)1 << 30)) return false;
   const int64_t nk = (int64_t)pl->n * pl->k;
   const size_t bytes = (size_t)((pl->n - 1) + ((pl->n - 1) >> 5) + 1) * pl->k * (pl->kind == PLAN_C ? 16 : 4);
   return nk < 32768 && bytes <= 96 * 1024;

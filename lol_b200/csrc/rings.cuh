@@ -35,6 +35,14 @@ struct ZqRing {
     if (r >= q) r -= q;
     return (T)r;
   }
+  // any 64-bit x -> x mod q (same Barrett step as mul)
+  __device__ __forceinline__ T reduce64(uint64_t x) const
+  {
+    uint64_t r = x - __umul64hi(x, mu) * q;   // in [0, 3q)
+    if (r >= q) r -= q;
+    if (r >= q) r -= q;
+    return (T)r;
+  }
   __device__ __forceinline__ T from_int(int i) const { return (uint32_t)i % q; }
   __device__ __forceinline__ T load(IO x) const
   {
