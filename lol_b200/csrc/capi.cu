@@ -169,7 +169,7 @@ extern "C" void lolb_plan_destroy(lolb_plan* pl)
   if (!pl) return;
   fused_release(pl);
   void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_ws, pl->d_stage,
-                  pl->ws_alt[0], pl->ws_alt[1], pl->ws_alt[2]};
+                  pl->ws_alt[0], pl->ws_alt[1], pl->ws_alt[2], pl->d_tab_fwd_m, pl->d_tab_inv_m};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : pl->streams) if (s) cudaStreamDestroy(s);
   for (auto& e : pl->events) if (e) cudaEventDestroy(e);

@@ -40,11 +40,38 @@ struct AxParams {
   int32_t tab_stride;
   int32_t finish;
   ZqConsts zc;
+  uint32_t qinv[kMaxLimbs];   // Zq: -q^-1 mod 2^32
+  uint32_t mscale[kMaxLimbs]; // Zq: final scalar (mhat^-1) in Montgomery form
   double2 cscale[kMaxLimbs];
 };
 
-__device__ __forceinline__ ZqRing ax_ring(const ZqRing*, const ZqConsts& zc, int limb) { return ZqRing::make(zc, limb); }
-__device__ __forceinline__ C64Ring ax_ring(const C64Ring*, const ZqConsts&, int) { return C64Ring{}; }
+// Z_q for this engine: odd q < 2^28, canonical residues, CONSTANTS (roots, twiddles, final scalar) in Montgomery form
+// c * 2^32 mod q, so  value x constant  is one REDC (IMAD.WIDE, IMAD, IMAD.HI) and a row of <= 13 products one REDC
+struct ZqMontRing {
+  typedef uint32_t T;
+  typedef int64_t IO;
+  uint32_t q, qinv;
+  __device__ __forceinline__ T zero() const { return 0u; }
+  __device__ __forceinline__ T add(T a, T b) const { const uint32_t s = a + b; return min(s, s - q); }
+  __device__ __forceinline__ T sub(T a, T b) const { const uint32_t d = a - b; return min(d, d + q); }
+  __device__ __forceinline__ T reduce64(uint64_t x) const      // x < q 2^32  ->  x 2^-32 mod q, canonical
+  {
+    const uint32_t m = (uint32_t)x * qinv;
+    const uint32_t t = (uint32_t)((x + (uint64_t)m * q) >> 32);
+    return min(t, t - q);
+  }
+  __device__ __forceinline__ T mul(T a, T w_mont) const { return reduce64((uint64_t)a * w_mont); }
+  __device__ __forceinline__ T load(IO x) const
+  {
+    if ((uint64_t)x < (uint64_t)q) return (T)x;
+    int64_t r = x % (int64_t)q;
+    return (T)(r < 0 ? r + (int64_t)q : r);
+  }
+  __device__ __forceinline__ IO store(T v) const { return (IO)v; }
+};
+
+template <class W> __device__ __forceinline__ ZqMontRing ax_ring(const ZqMontRing*, const AxParams<ZqMontRing, W>& P, int limb) { return ZqMontRing{P.zc.q[limb], P.qinv[limb]}; }
+template <class W> __device__ __forceinline__ C64Ring ax_ring(const C64Ring*, const AxParams<C64Ring, W>&, int) { return C64Ring{}; }
 
 // I_{PHI/(D*C)} (x) A_D (x) I_C on the registers of a line; KIND: PASS_DFT / PASS_CRT / PASS_CRTINV (engine.cu pass_dense)
 template <class R, int P_, int PHI, int D, int C, int KIND>
@@ -63,8 +90,8 @@ __device__ __forceinline__ void dense_regs(typename R::T (&v)[PHI], const R& rin
         out[1] = ring.sub(in[0], in[1]);
       } else {
         if constexpr (sizeof(T) == 4) {
-          // Z_q with q < 2^30 (checked on the host): a row is accumulated as exact 64-bit products (at most 13 terms
-          // < 2^60 each) and reduced ONCE; same residue as the reference's term-by-term reduction
+          // Z_q: a row is accumulated as exact 64-bit products (at most 13 terms, 13 q^2 < q 2^32 checked on the host)
+          // and reduced ONCE; same residue as the reference's term-by-term reduction
 #pragma unroll
           for (int row = 0; row < D; row++) {
             uint64_t acc = 0, shift = 0;
@@ -197,7 +224,7 @@ k_engine_axis(const __grid_constant__ AxParams<R, W> P, const __grid_constant__ 
     for (int idx = threadIdx.x; idx < total; idx += kAxThreads) {
       const int tq = ax_div(idx, k, P.magic_k), limb = idx - tq * k;
       const int el = ax_div(tq, n, P.magic_n), j = tq - el * n;
-      const R ring = ax_ring((const R*)nullptr, P.zc, limb);
+      const R ring = ax_ring((const R*)nullptr, P, limb);
       buf[(el * k + limb) * np + ax_pad(j, pad)] = ring.load(base[idx]);
     }
     __syncthreads();
@@ -209,7 +236,7 @@ k_engine_axis(const __grid_constant__ AxParams<R, W> P, const __grid_constant__ 
         const int slot = ln / lps, l = ln - slot * lps;
         const int hi = l / rts, r = l - hi * rts;
         const int limb = slot % k;
-        const R ring = ax_ring((const R*)nullptr, P.zc, limb);
+        const R ring = ax_ring((const R*)nullptr, P, limb);
         const W* tab = P.tab + (size_t)limb * P.tab_stride;
         const int j0 = r + rts * phi * hi;
         // with padding every line stays linear: the host pads only when the first axis is 2^6 (lines of 32 at stride 1)
@@ -233,10 +260,10 @@ k_engine_axis(const __grid_constant__ AxParams<R, W> P, const __grid_constant__ 
     for (int idx = threadIdx.x; idx < total; idx += kAxThreads) {
       const int tq = ax_div(idx, k, P.magic_k), limb = idx - tq * k;
       const int el = ax_div(tq, n, P.magic_n), j = tq - el * n;
-      const R ring = ax_ring((const R*)nullptr, P.zc, limb);
+      const R ring = ax_ring((const R*)nullptr, P, limb);
       T x = buf[(el * k + limb) * np + ax_pad(j, pad)];
       if (P.finish == FIN_SCALE) {
-        if constexpr (sizeof(T) == 4) x = ring.mul(x, (T)P.zc.scale[limb]);
+        if constexpr (sizeof(T) == 4) x = ring.mul(x, (T)P.mscale[limb]);
         else x = ring.mul(x, P.cscale[limb]);
       }
       base[idx] = ring.store(x);
@@ -343,11 +370,18 @@ int launch_axis(const lolb_plan* pl, bool inverse, typename R::IO* y, int64_t ba
 int engine_axis_crt_zq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
 {
   if (batch <= 0) return LOLB_OK;
-  for (int64_t q : pl->qs) if (q >= ((int64_t)1 << 30)) return -1;      // lazy 64-bit row accumulation needs q < 2^30
-  AxParams<ZqRing, uint32_t> P{};
+  const uint32_t* tabm = inverse ? pl->d_tab_inv_m : pl->d_tab_fwd_m;
+  if (!tabm) return -1;                                  // an even modulus or one >= 2^28: engine.cu
+  AxParams<ZqMontRing, uint32_t> P{};
   P.zc = inverse ? pl->zq_mhat : pl->zq_plain;
-  return launch_axis<ZqRing, uint32_t>(pl, inverse, y, batch, inverse ? pl->d_tab_inv : pl->d_tab_fwd,
-                                       inverse ? pl->tab_stride_inv : pl->tab_stride_fwd, P, st);
+  for (int t = 0; t < pl->k; t++) {
+    const uint32_t q = (uint32_t)pl->qs[t];
+    uint32_t inv = q;
+    for (int i = 0; i < 5; i++) inv *= 2u - q * inv;
+    P.qinv[t] = 0u - inv;
+    P.mscale[t] = (uint32_t)((((uint64_t)P.zc.scale[t]) << 32) % q);
+  }
+  return launch_axis<ZqMontRing, uint32_t>(pl, inverse, y, batch, tabm, inverse ? pl->tab_stride_inv : pl->tab_stride_fwd, P, st);
 }
 
 int engine_axis_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cudaStream_t st)
@@ -365,7 +399,7 @@ bool engine_axis_supported(const lolb_plan* pl, bool inverse)
   const PassList& PL = inverse ? pl->crt_inv : pl->crt_fwd;
   if (!(inverse ? pl->has_inv : pl->has_fwd)) return false;
   if (!build_axes(pl, PL, inverse, &AX)) return false;
-  if (pl->kind == PLAN_RQ) for (int64_t q : pl->qs) if (q >= ((int64_t)1 << 30)) return false;
+  if (pl->kind == PLAN_RQ && !(inverse ? pl->d_tab_inv_m : pl->d_tab_fwd_m)) return false;
   const int64_t nk = (int64_t)pl->n * pl->k;
   const size_t bytes = (size_t)((pl->n - 1) + ((pl->n - 1) >> 5) + 1) * pl->k * (pl->kind == PLAN_C ? 16 : 4);
   return nk < 32768 && bytes <= 96 * 1024;

@@ -81,6 +81,8 @@ struct lolb_plan {
   lolb::ZqConsts zq_plain{}, zq_mhat{}, zq_radinv{};   // scale = 1 / mhat^-1 / rad_odd^-1
   uint32_t* d_tab_fwd = nullptr;    // [k][tab_stride_fwd] u32: root tables then diagonal tables
   uint32_t* d_tab_inv = nullptr;
+  uint32_t* d_tab_fwd_m = nullptr;  // the same table blocks in Montgomery form (x 2^32 mod q) for engine_axis; nullptr when a modulus is even or >= 2^28
+  uint32_t* d_tab_inv_m = nullptr;
   int32_t tab_stride_fwd = 0, tab_stride_inv = 0;
   int64_t* d_gcrt = nullptr;        // [n][k]
   int64_t* d_gcrtinv = nullptr;

@@ -264,6 +264,22 @@ int plan_upload_rq_dir(lolb_plan* pl, bool inverse)
   auto one = [&]() -> uint32_t { return 1u; };
   int rc = build_crt_dir<uint32_t>(pl, inverse, root, one, inverse ? &pl->crt_inv : &pl->crt_fwd, &host, &stride);
   if (rc) return rc;
+  // Montgomery-form copy for engine_axis (odd moduli below 2^28: a row of <= 13 products then fits one REDC)
+  std::vector<uint32_t> hm;
+  bool mont_ok = true;
+  for (int t = 0; t < k; t++) if (!(pl->qs[t] & 1) || pl->qs[t] >= ((int64_t)1 << 28)) mont_ok = false;
+  if (mont_ok) {
+    hm.resize(host.size());
+    for (int t = 0; t < k; t++) {
+      const uint64_t q = (uint64_t)pl->qs[t];
+      for (int32_t j = 0; j < stride; j++) hm[(size_t)t * stride + j] = (uint32_t)((((uint64_t)host[(size_t)t * stride + j]) << 32) % q);
+    }
+  }
+  {
+    uint32_t** dm = inverse ? &pl->d_tab_inv_m : &pl->d_tab_fwd_m;
+    int rcm = upload(dm, hm);          // empty vector frees a stale copy
+    if (rcm) return rcm;
+  }
   // q = 1 would make "1" non-canonical; moduli are >= 2 (checked at creation)
   if (inverse) {
     rc = upload(&pl->d_tab_inv, host);
