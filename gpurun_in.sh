@@ -1,6 +1,3 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-for cfg in "1728 3457 131072" "5184 10369 65536" "42 8191 1000000" "64 257 1000000" "2016 12097 100000"; do
-  set -- $cfg
-  for op in CRT CRTInv; do timeout 120 python tools/run_op.py $1 $2 $3 $op 5; done
-done
-timeout 120 python tools/run_plain.py 1728 65536 2>&1 | grep CRT
+timeout 120 python tools/sanitize_probe.py 2>&1 | tail -16
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_probe.py > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|Invalid|MISMATCH" gpurun_out/memcheck.log | head -10
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_probe.py > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|MISMATCH" gpurun_out/racecheck.log | head -10
