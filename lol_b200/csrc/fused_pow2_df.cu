@@ -1,15 +1,7 @@
-// fused_pow2_df.cu -- Z_q CRT / CRT^-1 for power-of-two index m = 2^e, 12 <= e <= 16, as ONE persistent
-// dataflow kernel with an L2-resident exchange ring (BASELINE.json config B: m = 2^16, four ~30-bit primes).
-//
-// Operator.  For p = 2 the reference's  crtTwiddle ; {dftp ; dftTwiddle} x (e-1)  (crt.cpp:43-58, 137-149, 92-106,
-// 459-486, 518-538) evaluates  f(x) = sum_i y[i] x^rev(i)  at  psi^(2 pos + 1),  pos = 0 .. n-1, psi = ru[0][1]
-// (pinned on the CPU by tests/test_*_pinning.py::test_pow2_crt_is_negacyclic_evaluation).  Over Z_q every exact
-// evaluation order gives the same residues, so the kernel uses the twist-free Cooley-Tukey form of the same map:
-//   round r = 0 .. e-2, pairs (pos, pos + 2^r) with bit r of pos clear, p = pos mod 2^r:
-//     forward   (u, t) -> (u + T t, u - T t),      T = psi^((2p+1) n / 2^(r+1))          rounds ascending
-//     inverse   (u, t) -> (u + t, (u - t) / T),    rounds descending, then * mhat^-1      (crt.cpp:488-516, 573-579)
-// No crtTwiddle table, no separate scaling pass; the twiddle of round r depends on the LOW r bits of pos only, so
-// rounds 0-4 use 31 per-limb constants (kernel-parameter bank), rounds 5-9 a 4 KB L1-resident table.
+// fused_pow2_df.cu -- Z_q CRT / CRT^-1 for power-of-two index m = 2^e, 13 <= e <= 16, as ONE persistent dataflow kernel
+// with an L2-resident exchange ring (BASELINE.json config B: m = 2^16, four ~30-bit primes), plus the plan-level
+// selection and dispatch of all power-of-two kernels (operator and arithmetic: pow2_common.cuh; m <= 2^14 with the
+// element resident on chip: fused_pow2_res.cu).
 //
 // Schedule.  The limb (n <= 32768 coefficients, 128 KB as u32) is never resident in one SM.  Position bits [0,10)
 // ("chunk" rounds) and bits [10, e-1) ("column" rounds) are two task kinds of 128 threads each:
@@ -18,94 +10,20 @@
 //                that owns 32 consecutive coefficients, rounds 5-9 by the lane that owns stride-32 coefficients
 //   column task  128 consecutive (coefficient, limb) pairs x all 2^(e-11) chunks: rounds 10 .. e-2 in registers,
 //                no shared memory; every int64 store / load of the element is part of a fully used 32-byte sector
-// The two kinds exchange u32 residues through a ring of `ring` element slots in global memory that is sized to stay
-// in the 126 MB L2 (default 48 slots = 24 MB at config B), so HBM sees one read and one write of the element.
-// CTAs are persistent and take tasks from an atomic counter; per-element counters order  first kind -> second kind
-// -> slot reuse.  A task only waits for tasks with a smaller index, which are already running: no deadlock.
-//
-// Arithmetic (odd q, 4q < 2^32): lazy residues in [0,4q) (forward) / [0,2q) (inverse), twiddles in Montgomery form
-// (IMAD.WIDE, IMAD, IMAD.HI), fold = one VIADDMNMX, canonical [0,q) only at the final store.
+// The two kinds exchange u32 residues through a ring of element slots in global memory that is sized to stay in the
+// 126 MB L2 (72 slots = 37 MB at config B), so HBM sees one read and one write of the element.  CTAs are persistent
+// and take tasks from an atomic counter; per-element counters order  first kind -> second kind -> slot reuse.  A task
+// only waits for tasks with a smaller index, which are already running: no deadlock.
 #include <cstdlib>
 
-#include "fused.cuh"
 #include "numtheory.h"
+#include "pow2_common.cuh"
 
 namespace lolb {
 
+using namespace pow2;
+
 namespace {
-
-constexpr int kDfUnit = 1024 + 32 + 8;   // words per (chunk, limb) unit in shared memory: +1 per 32 (padding), +8 (bank shift per unit)
-constexpr int kDfMaxK = 4;
-constexpr int kDfCtrHead = 16;           // ctr[0] = task counter; per-element counters start here
-
-struct DfLimb {
-  uint32_t q, q2, qinv;
-  uint32_t sA, sB;         // inverse: mont(mhat^-1), mont(mhat^-1 / T_0)
-  uint32_t c0[31];         // Montgomery twiddles of rounds 0..4: entry (2^a - 1) + p
-  const uint32_t* tw;      // all rounds: entry (2^r - 1) + p, p < 2^r, Montgomery form
-};
-
-struct DfParams {
-  int32_t n, k;
-  int32_t ring, lag;       // exchange-ring slots; distance (in elements) between the two task kinds in the queue
-  DfLimb limb[kDfMaxK];
-};
-
-struct Mont {
-  uint32_t q, q2, qinv;    // qinv = -q^-1 mod 2^32
-  // x any u32, w < q in Montgomery form  ->  x * w mod q  in [0, 2q)
-  __device__ __forceinline__ uint32_t mul(uint32_t x, uint32_t w) const
-  {
-    const uint64_t p = (uint64_t)x * w;
-    const uint32_t m = (uint32_t)p * qinv;
-    return (uint32_t)((p + (uint64_t)m * q) >> 32);
-  }
-  __device__ __forceinline__ uint32_t fold(uint32_t x) const { return min(x, x - q2); }    // [0,4q) -> [0,2q)
-  __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }    // [0,2q) -> [0,q)
-};
-
-__device__ __noinline__ uint32_t df_reduce_any64(int64_t x, uint32_t q)
-{
-  int64_t r = x % (int64_t)q;
-  return (uint32_t)(r < 0 ? r + q : r);
-}
-
-// S forward rounds on the 2^S registers of one block; tw(a, jj) = twiddle of the pairs with j0 mod 2^a = jj
-template <int S, bool CANON_IN, class TW>
-__device__ __forceinline__ void ct_rounds(uint32_t (&v)[1 << S], const Mont& M, TW tw)
-{
-#pragma unroll
-  for (int a = 0; a < S; a++) {
-#pragma unroll
-    for (int j0 = 0; j0 < (1 << S); j0++) {
-      if (j0 & (1 << a)) continue;
-      const int j1 = j0 | (1 << a);
-      const uint32_t w = tw(a, j0 & ((1 << a) - 1));
-      const uint32_t u = (CANON_IN && a == 0) ? v[j0] : M.fold(v[j0]);
-      const uint32_t t = M.mul(v[j1], w);
-      v[j0] = u + t;
-      v[j1] = u + M.q2 - t;
-    }
-  }
-}
-
-// inverse rounds S-1 .. LOW on residues in [0,2q)
-template <int S, int LOW, class TW>
-__device__ __forceinline__ void gs_rounds(uint32_t (&v)[1 << S], const Mont& M, TW tw)
-{
-#pragma unroll
-  for (int a = S - 1; a >= LOW; a--) {
-#pragma unroll
-    for (int j0 = 0; j0 < (1 << S); j0++) {
-      if (j0 & (1 << a)) continue;
-      const int j1 = j0 | (1 << a);
-      const uint32_t w = tw(a, j0 & ((1 << a) - 1));
-      const uint32_t u = v[j0], t = v[j1];
-      v[j0] = M.fold(u + t);
-      v[j1] = M.mul(u + M.q2 - t, w);
-    }
-  }
-}
 
 // rounds 0-4 of one unit: lane owns coefficients 32*lane .. 32*lane+31 (padded word 33*lane + j, conflict free).
 // LIMB is a template parameter so the 31 twiddles and q, q', 2q are constant-bank operands, not registers.
@@ -159,32 +77,6 @@ __device__ __forceinline__ void unit_rounds_0_4_any(int limb, uint32_t* Uu, cons
 #endif
 constexpr int kDfWarps = LOLB_DF_NW;
 constexpr int kDfThreads = 32 * kDfWarps;
-
-// rounds 0-4 with a run-time limb: one copy of the code, twiddles fetched with LDC
-template <bool INV>
-__device__ __forceinline__ void unit_rounds_0_4_rt(int limb, uint32_t* Uu, const DfParams& P, int lane)
-{
-  const DfLimb& L = P.limb[limb];
-  const Mont M{L.q, L.q2, L.qinv};
-  uint32_t* base = Uu + 33 * lane;
-  uint32_t v[32];
-#pragma unroll
-  for (int j = 0; j < 32; j++) v[j] = base[j];
-  if (!INV) {
-    ct_rounds<5, true>(v, M, [&](int a, int jj) { return L.c0[(1 << a) - 1 + jj]; });
-  } else {
-    gs_rounds<5, 1>(v, M, [&](int a, int jj) { return L.c0[(1 << a) - 1 + jj]; });
-    const uint32_t sA = L.sA, sB = L.sB;
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 2) {
-      const uint32_t u = v[j0], t = v[j0 + 1];
-      v[j0] = M.canon(M.mul(u + t, sA));
-      v[j0 + 1] = M.canon(M.mul(u + M.q2 - t, sB));
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; j++) base[j] = v[j];
-}
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
 {
@@ -773,353 +665,6 @@ k_pow2_dfm(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams 
   flush();
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Small indices m = 2^10, 2^11 (n = 512, 1024: the reference's own benchmark parameters, lol/.../Benchmarks/
-// Default.hs:41-46): a limb fits one warp -- 32 residues per lane -- so the whole transform is the two register passes
-// of a chunk task with a warp-private transposition through 4 KB of shared memory.  No queue, no ring, no counters.
-// tupSize 1: every warp is independent (own loads, __syncwarp only).  tupSize 2, 4: the CTA de-interleaves a 32 KB piece
-// cooperatively (three CTA barriers per piece).  n = 512: a warp holds two limbs (16 + 16 residues per lane in the
-// second pass).
-template <bool INV, int K, int E>
-__global__ void __launch_bounds__(128, 5)
-k_pow2_small(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P)
-{
-  constexpr int n = 1 << (E - 1);                       // 512 or 1024
-  constexpr int UPW = 1024 / n;                         // (element, limb) units per warp
-  constexpr int UW = n + n / 32 + (E == 11 ? 8 : 0);    // words per unit: 1064 / 528 (528 = 16 mod 32: the two units of a warp hit disjoint banks)
-  constexpr int S1 = E - 6;                             // rounds of the second pass: 5 or 4
-  constexpr int V1 = 1 << S1;                           // residues per lane and unit in the second pass
-  constexpr int LG = K == 1 ? 32 : 128;                 // threads that load one contiguous piece together
-  constexpr int UPG = K == 1 ? UPW : 4 * UPW;           // units per loader group
-  constexpr int EPG = UPG / K;                          // ring elements per loader group
-  constexpr int PIECES = (UPG * n) / (2 * LG);          // 16-byte pieces per thread (= 16)
-  constexpr int STEP = (2 * LG) / K;                    // coefficients between consecutive pieces of a thread
-  static_assert(EPG >= 1 && PIECES == 16 && n % STEP == 0 && STEP % 32 == 0, "geometry");
-  __shared__ __align__(16) uint32_t U[4 * UPW * UW];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tg = K == 1 ? lane : tid;                   // index inside the loader group
-  const int grp = K == 1 ? warp : 0;                    // loader group inside the CTA
-  const int groups_per_cta = K == 1 ? 4 : 1;
-  const int l0 = (2 * tg) % K, c0 = (2 * tg) / K;
-  uint32_t* ubase = U + (grp * UPG + l0) * UW + c0 + (c0 >> 5);
-  constexpr int second = K == 1 ? 1 : UW;
-  auto piece_off = [](int ii) { return ((STEP * ii) / n) * K * UW + ((STEP * ii) % n) + (((STEP * ii) % n) >> 5); };
-  auto piece_el = [](int ii) { return (STEP * ii) / n; };                 // element (inside the group) of piece ii
-  auto sync_group = [&]() { if (K == 1) __syncwarp(); else __syncthreads(); };
-
-  const int64_t ngroups = (batch + EPG - 1) / EPG;
-  for (int64_t g = (int64_t)blockIdx.x * groups_per_cta + grp; g < ngroups; g += (int64_t)gridDim.x * groups_per_cta) {
-    const int64_t e0 = g * EPG;
-    const int cnt = (int)(batch - e0 < EPG ? batch - e0 : EPG);           // ring elements of this group that exist
-    longlong2* gp = reinterpret_cast<longlong2*>(y + (size_t)e0 * n * K) + tg;
-    // this warp's units: u = first + h, element u / K, limb u % K
-    const int ufirst = K == 1 ? 0 : warp * UPW;                           // inside the group
-    uint32_t* Uw = U + (grp * UPG + ufirst) * UW;                         // this warp's first unit
-
-    if (!INV || K > 1) {
-      // contiguous piece -> units, limbs de-interleaved
-      const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
-      longlong2 raw[PIECES];
-#pragma unroll
-      for (int ii = 0; ii < PIECES; ii++) raw[ii] = piece_el(ii) < cnt ? __ldcs(gp + LG * ii) : make_longlong2(0, 0);
-      uint32_t hi_or = 0, max0 = 0, max1 = 0;
-#pragma unroll
-      for (int ii = 0; ii < PIECES; ii++) {
-        hi_or |= (uint32_t)((uint64_t)raw[ii].x >> 32) | (uint32_t)((uint64_t)raw[ii].y >> 32);
-        max0 = max(max0, (uint32_t)raw[ii].x);
-        max1 = max(max1, (uint32_t)raw[ii].y);
-        ubase[piece_off(ii)] = (uint32_t)raw[ii].x;
-        ubase[piece_off(ii) + second] = (uint32_t)raw[ii].y;
-      }
-      if (hi_or != 0 || max0 >= q0 || max1 >= q1) {      // outside the Haskell contract: reduce like the reference's c % q
-#pragma unroll 1
-        for (int ii = 0; ii < PIECES; ii++) {
-          if (piece_el(ii) >= cnt) continue;
-          const longlong2 r = gp[LG * ii];
-          ubase[piece_off(ii)] = df_reduce_any64(r.x, q0);
-          ubase[piece_off(ii) + second] = df_reduce_any64(r.y, q1);
-        }
-      }
-      sync_group();
-    }
-
-    // ---- the two register passes on this warp's unit(s)
-    if (!INV) {
-      // rounds 0-4: lane owns 32 consecutive residues (n = 512: lanes 0-15 the first unit, 16-31 the second)
-      {
-        const int hu = UPW == 1 ? 0 : lane >> 4, blk = UPW == 1 ? lane : lane & 15;
-        const int limb = (ufirst + hu) % K;
-        unit_rounds_0_4_rt<false>(limb, Uw + hu * UW - 33 * lane + 33 * blk, P, lane);      // base + 33 * blk
-      }
-      __syncwarp();
-      // rounds 5 .. e-2: lane owns residues lane + 32 j of each unit
-#pragma unroll
-      for (int h = 0; h < UPW; h++) {
-        const int u = ufirst + h, limb = u % K, el = u / K;
-        const DfLimb& L = P.limb[limb];
-        const Mont M{L.q, L.q2, L.qinv};
-        uint32_t* ub = Uw + h * UW + lane;
-        uint32_t v[V1];
-#pragma unroll
-        for (int j = 0; j < V1; j++) v[j] = ub[33 * j];
-        const uint32_t* twl = L.tw + lane;
-        ct_rounds<S1, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
-        if (K == 1) {
-          if (el < cnt) {
-            int64_t* out = y + (size_t)(e0 + el) * n + lane;
-#pragma unroll
-            for (int j = 0; j < V1; j++) __stcs(out + 32 * j, (int64_t)M.canon(M.fold(v[j])));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < V1; j++) ub[33 * j] = M.canon(M.fold(v[j]));
-        }
-      }
-    } else {
-#pragma unroll
-      for (int h = 0; h < UPW; h++) {
-        const int u = ufirst + h, limb = u % K, el = u / K;
-        const DfLimb& L = P.limb[limb];
-        const Mont M{L.q, L.q2, L.qinv};
-        uint32_t* ub = Uw + h * UW + lane;
-        uint32_t v[V1];
-        if (K == 1) {
-          const int64_t* in = y + (size_t)(e0 + (el < cnt ? el : 0)) * n + lane;
-          uint32_t hi_or = 0, lo_max = 0;
-#pragma unroll
-          for (int j = 0; j < V1; j++) {
-            const int64_t raw = __ldcs(in + 32 * j);
-            v[j] = (uint32_t)raw;
-            hi_or |= (uint32_t)((uint64_t)raw >> 32);
-            lo_max = max(lo_max, v[j]);
-          }
-          if (hi_or != 0 || lo_max >= L.q) {
-#pragma unroll
-            for (int j = 0; j < V1; j++) v[j] = df_reduce_any64(in[32 * j], L.q);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < V1; j++) v[j] = ub[33 * j];
-        }
-        const uint32_t* twl = L.tw + lane;
-        gs_rounds<S1, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
-#pragma unroll
-        for (int j = 0; j < V1; j++) ub[33 * j] = v[j];
-      }
-      __syncwarp();
-      {
-        const int hu = UPW == 1 ? 0 : lane >> 4, blk = UPW == 1 ? lane : lane & 15;
-        const int limb = (ufirst + hu) % K;
-        unit_rounds_0_4_rt<true>(limb, Uw + hu * UW - 33 * lane + 33 * blk, P, lane);
-      }
-    }
-
-    if (INV || K > 1) {
-      // units -> contiguous piece (canonical residues), coalesced 128-bit stores
-      sync_group();
-#pragma unroll
-      for (int ii = 0; ii < PIECES; ii++) {
-        if (piece_el(ii) < cnt) {
-          const uint32_t x0 = ubase[piece_off(ii)], x1 = ubase[piece_off(ii) + second];
-          __stcs(gp + LG * ii, make_longlong2((int64_t)x0, (int64_t)x1));
-        }
-      }
-    }
-    sync_group();      // U is reused by the next group
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Middle indices m = 2^12, 2^13 (tupSize 1, 2, 4) and 2^14 (tupSize 1): one ring element (all limbs, 17-68 KB as u32) is
-// resident in the shared memory of a 128-thread CTA.  The (chunk, limb) units of 1024 residues go through the two
-// register passes of a chunk task, one warp per unit; the remaining 1-3 rounds couple the chunks and run with a thread
-// per coefficient (2-4 residues at stride 1024, eight coefficients per thread in flight).  Four CTA barriers per
-// element, no queue and no ring; 5 CTAs per SM overlap each other's phases.
-template <bool INV, int K, int E>
-__global__ void __launch_bounds__(128, 5)
-k_pow2_mid(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ DfParams P)
-{
-  constexpr int n = 1 << (E - 1);                       // 2048 .. 8192
-  constexpr int NCH = n / 1024;                         // chunks per limb: 2, 4, 8
-  constexpr int T = E - 11;                             // top rounds: 1 .. 3
-  constexpr int XI = T <= 2 ? 8 : 4;                    // coefficients per thread in flight in the top pass (<= 32 residues)
-  constexpr int NV = 1 << T;
-  constexpr int UW = kDfUnit;
-  constexpr int EPC = NCH * K >= 4 ? 1 : 4 / (NCH * K);   // ring elements per CTA iteration: every warp gets a unit (2 at m = 2^12, tupSize 1)
-  constexpr int UNITS = NCH * K * EPC;
-  constexpr int PIECES = (n * K * EPC) / (2 * 128);     // 16-byte pieces per thread: 16 or 32
-  constexpr int STEP = 256 / K;
-  static_assert(UNITS * UW * 4 <= 72 * 1024 && 1024 % STEP == 0 && STEP % 32 == 0, "geometry");
-  extern __shared__ __align__(16) uint32_t U[];         // [UNITS][UW], unit = (element * NCH + chunk) * K + limb
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int l0 = (2 * tid) % K, c0 = (2 * tid) / K;
-  uint32_t* ubase = U + l0 * UW + c0 + (c0 >> 5);
-  constexpr int second = K == 1 ? 1 : UW;
-  auto piece_off = [](int ii) { return ((STEP * ii) >> 10) * K * UW + ((STEP * ii) & 1023) + (((STEP * ii) & 1023) >> 5); };
-
-  // rounds 10 .. e-2 on the residues x + 1024 j of limb l, eight coefficients x = tid + 128 i per thread
-  auto top_pass = [&](int64_t* gbase, int cnt) {
-#pragma unroll 1
-    for (int el_l = 0; el_l < EPC * K; el_l++) {
-      const int l = el_l % K, eo = el_l / K;
-      if (eo >= cnt) break;
-      int64_t* ebase = gbase + (size_t)eo * n * K;
-      uint32_t* Ue = U + eo * NCH * K * UW;
-      const DfLimb& L = P.limb[l];
-      const Mont M{L.q, L.q2, L.qinv};
-#pragma unroll 1
-      for (int ib = 0; ib < 8; ib += XI) {
-      uint32_t v[XI][NV];
-      const int xt = tid + 128 * ib;                      // first coefficient of this thread in this block
-      if (INV && K == 1) {                              // straight from HBM: lanes are consecutive coefficients
-        uint32_t hi_or = 0, lo_max = 0;
-#pragma unroll
-        for (int i = 0; i < XI; i++)
-#pragma unroll
-          for (int j = 0; j < NV; j++) {
-            const int64_t raw = __ldcs(ebase + xt + 128 * i + 1024 * j);
-            v[i][j] = (uint32_t)raw;
-            hi_or |= (uint32_t)((uint64_t)raw >> 32);
-            lo_max = max(lo_max, v[i][j]);
-          }
-        if (hi_or != 0 || lo_max >= L.q) {
-#pragma unroll
-          for (int i = 0; i < XI; i++)
-#pragma unroll
-            for (int j = 0; j < NV; j++) v[i][j] = df_reduce_any64(ebase[xt + 128 * i + 1024 * j], L.q);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < XI; i++) {
-          const int x = xt + 128 * i;
-#pragma unroll
-          for (int j = 0; j < NV; j++) v[i][j] = Ue[(j * K + l) * UW + x + (x >> 5)];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < XI; i++) {
-        const uint32_t* twx = L.tw + xt + 128 * i;
-        if (!INV) ct_rounds<T, false>(v[i], M, [&](int a, int jj) { return __ldg(twx + ((1024 << a) - 1 + 1024 * jj)); });
-        else gs_rounds<T, 0>(v[i], M, [&](int a, int jj) { return __ldg(twx + ((1024 << a) - 1 + 1024 * jj)); });
-      }
-      if (!INV && K == 1) {                             // straight to HBM
-#pragma unroll
-        for (int i = 0; i < XI; i++)
-#pragma unroll
-          for (int j = 0; j < NV; j++) __stcs(ebase + xt + 128 * i + 1024 * j, (int64_t)M.canon(M.fold(v[i][j])));
-      } else {
-#pragma unroll
-        for (int i = 0; i < XI; i++) {
-          const int x = xt + 128 * i;
-#pragma unroll
-          for (int j = 0; j < NV; j++) Ue[(j * K + l) * UW + x + (x >> 5)] = INV ? v[i][j] : M.canon(M.fold(v[i][j]));
-        }
-      }
-      }
-    }
-  };
-
-  // the two register passes of every (chunk, limb) unit, one warp per unit
-  auto unit_passes = [&]() {
-#pragma unroll 1
-    for (int u = warp; u < UNITS; u += 4) {
-      const int limb = u % K;
-      const DfLimb& L = P.limb[limb];
-      const Mont M{L.q, L.q2, L.qinv};
-      uint32_t* Uu = U + u * UW;
-      const uint32_t* twl = L.tw + lane;
-      if (!INV) {
-        unit_rounds_0_4_rt<false>(limb, Uu, P, lane);
-        __syncwarp();
-        uint32_t v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
-        ct_rounds<5, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
-#pragma unroll
-        for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
-      } else {
-        uint32_t v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
-        gs_rounds<5, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
-#pragma unroll
-        for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
-        __syncwarp();
-        unit_rounds_0_4_rt<true>(limb, Uu, P, lane);
-      }
-    }
-  };
-
-  auto piece_el = [](int ii) { return (STEP * ii) / n; };                 // element (inside the CTA's group) of piece ii
-  const int64_t ngroups = (batch + EPC - 1) / EPC;
-  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const int64_t e = g * EPC;
-    const int cnt = (int)(batch - e < EPC ? batch - e : EPC);
-    int64_t* ebase = y + (size_t)e * n * K;
-    longlong2* gp = reinterpret_cast<longlong2*>(ebase) + tid;
-    if (!(INV && K == 1)) {
-      // element -> units, limbs de-interleaved (at most 16 pieces in flight per thread)
-      const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
-#pragma unroll
-      for (int part = 0; part < (PIECES + 15) / 16; part++) {
-        constexpr int PP = PIECES < 16 ? PIECES : 16;
-        longlong2 raw[PP];
-#pragma unroll
-        for (int i = 0; i < PP; i++) raw[i] = piece_el(part * 16 + i) < cnt ? __ldcs(gp + 128 * (part * 16 + i)) : make_longlong2(0, 0);
-        uint32_t hi_or = 0, max0 = 0, max1 = 0;
-#pragma unroll
-        for (int i = 0; i < PP; i++) {
-          hi_or |= (uint32_t)((uint64_t)raw[i].x >> 32) | (uint32_t)((uint64_t)raw[i].y >> 32);
-          max0 = max(max0, (uint32_t)raw[i].x);
-          max1 = max(max1, (uint32_t)raw[i].y);
-          ubase[piece_off(part * 16 + i)] = (uint32_t)raw[i].x;
-          ubase[piece_off(part * 16 + i) + second] = (uint32_t)raw[i].y;
-        }
-        if (hi_or != 0 || max0 >= q0 || max1 >= q1) {      // outside the Haskell contract: reduce like the reference's c % q
-#pragma unroll 1
-          for (int i = 0; i < PP; i++) {
-            if (piece_el(part * 16 + i) >= cnt) continue;
-            const longlong2 r = gp[128 * (part * 16 + i)];
-            ubase[piece_off(part * 16 + i)] = df_reduce_any64(r.x, q0);
-            ubase[piece_off(part * 16 + i) + second] = df_reduce_any64(r.y, q1);
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (!INV) {
-      unit_passes();
-      __syncthreads();
-      top_pass(ebase, cnt);
-    } else {
-      top_pass(ebase, cnt);
-      __syncthreads();
-      unit_passes();
-    }
-    if (!(!INV && K == 1)) {
-      // units -> element (canonical residues), coalesced 128-bit stores
-      __syncthreads();
-#pragma unroll
-      for (int ii = 0; ii < PIECES; ii++) {
-        if (piece_el(ii) < cnt) {
-          const uint32_t x0 = ubase[piece_off(ii)], x1 = ubase[piece_off(ii) + second];
-          __stcs(gp + 128 * ii, make_longlong2((int64_t)x0, (int64_t)x1));
-        }
-      }
-    }
-    __syncthreads();      // U is reused by the next group
-  }
-}
-
-struct FusedPow2Df {
-  bool ok_fwd = false, ok_inv = false;
-  DfParams fwd{}, inv{};
-  uint32_t* d_tab = nullptr;
-  int top = 0;
-};
-
 uint32_t neg_inv32(uint32_t q)
 {
   uint32_t inv = q;
@@ -1224,59 +769,13 @@ int launch_dfm(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t ba
   }
 }
 
-template <bool INV, int K, int E>
-int launch_small(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
-{
-  static int per_sm = 0;
-  if (!per_sm) {
-    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_small<INV, K, E>, 128, 0));
-    if (per_sm < 1) per_sm = 1;
-  }
-  constexpr int n = 1 << (E - 1), upw = 1024 / n;
-  const int64_t el_per_cta = K == 1 ? 4 * upw : (4 * upw) / K;      // ring elements one CTA iteration covers
-  int64_t grid = (int64_t)pl->num_sms * per_sm;
-  const int64_t need = (batch + el_per_cta - 1) / el_per_cta;
-  if (grid > need) grid = need;
-  k_pow2_small<INV, K, E><<<(int)grid, 128, 0, st>>>(y, batch, INV ? F->inv : F->fwd);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "k_pow2_small");
-  count_launch();
-  return LOLB_OK;
-}
-
-template <bool INV, int K, int E>
-int launch_mid(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
-{
-  constexpr int units1 = ((1 << (E - 1)) / 1024) * K, epc = units1 >= 4 ? 1 : 4 / units1;
-  constexpr int smem = units1 * epc * kDfUnit * 4;
-  static int per_sm = 0;
-  if (!per_sm) {
-    LOLB_CUDA(cudaFuncSetAttribute(k_pow2_mid<INV, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_mid<INV, K, E>, 128, smem));
-    if (per_sm < 1) per_sm = 1;
-  }
-  int64_t grid = (int64_t)pl->num_sms * per_sm;
-  if (grid > (batch + epc - 1) / epc) grid = (batch + epc - 1) / epc;
-  k_pow2_mid<INV, K, E><<<(int)grid, 128, smem, st>>>(y, batch, INV ? F->inv : F->fwd);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "k_pow2_mid");
-  count_launch();
-  return LOLB_OK;
-}
-
 template <bool INV, int K>
 int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
-  if (F->top == 1) return launch_mid<INV, K, 12>(pl, F, y, batch, st);
-  // measured (B200, % of HBM peak forward / inverse, element-resident vs dataflow): m = 2^13: tupSize 1 82 / 78 vs 62 / 51,
-  // tupSize 2 69 / 67 vs 56 / -, tupSize 4 (68 KB, 3 CTAs/SM) 55 / 56 vs 30 / 27; m = 2^14: tupSize 1 70 / 58 vs 65 / 56,
-  // tupSize 2 (68 KB) 55 / 54 vs 63 / 54 -> dataflow from there on
-  if (!getenv("LOLB_POW2_MID_OFF")) {
-    if (F->top == 2) return launch_mid<INV, K, 13>(pl, F, y, batch, st);
-    if constexpr (K == 1) { if (F->top == 3) return launch_mid<INV, K, 14>(pl, F, y, batch, st); }
+  {
+    const int rc = pow2_resident_crt(pl, F, INV, y, batch, st);      // m <= 2^14: element-resident kernels where they win
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
   }
-  if (F->top == 0) return launch_small<INV, K, 11>(pl, F, y, batch, st);
-  if (F->top == -1) return launch_small<INV, K, 10>(pl, F, y, batch, st);
   // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2
   // paired (63 % / 59 %, 60 % / 58 % vs 61 % / 59 %, 58 % / 57 %).  Keeping the rounds 5-9 twiddles in shared memory
   // instead of L1 was measured too: no gain, and it costs the paired kernel a CTA per SM.
