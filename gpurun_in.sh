@@ -1,5 +1,3 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-Q4=537133057,537591809,537722881,538116097
-timeout 120 python tools/run_op.py 65536 $Q4 1024 CRT 20
-timeout 120 python tools/run_op.py 2048 12289 131072 CRT 10
-timeout 120 python tools/run_op.py 8192 40961 32768 CRTInv 10
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+tail -c 200 gpurun_out/bench_n8.err
+python tools/bsum.py gpurun_out/bench_n8.json 2>/dev/null | head -6
