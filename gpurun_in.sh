@@ -1,3 +1,3 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
-tail -c 200 gpurun_out/bench_n8.err
-python tools/bsum.py gpurun_out/bench_n8.json 2>/dev/null | head -6
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "batched_rq or full_size or dropin_zq or golden or fused_crt_mul or non_canonical" 2>&1 | tail -3
+for op in CRT CRTInv; do timeout 120 python tools/run_op.py 14400 14401 65536 $op 30; done
+timeout 120 python tools/run_op.py 14400 429336001 65536 CRTInv 20

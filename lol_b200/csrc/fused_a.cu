@@ -190,6 +190,26 @@ __device__ __forceinline__ void exchange_round(uint32_t (&c0)[3], uint32_t (&c1)
   }
 }
 
+// Last inverse round (lane bit 0) merged with the inverse crtTwiddle of the 2^6 axis that follows it: the lane ends up
+// with columns 2c (c0) and 2c+1 (c1), whose twiddles a, b are per-lane constants, so
+//   c0 = a (u + tw t) = a u + (a tw) t,   c1 = b (u - tw t) = b u + (-b tw) t
+// are two 2-term rows with host-folded constants: one reduction each instead of three.
+template <class AR>
+__device__ __forceinline__ void exchange_last_inv(uint32_t (&c0)[3], uint32_t (&c1)[3], int lane, uint32_t a, uint32_t atw,
+                                                  uint32_t b, uint32_t nbtw, const AR& A)
+{
+  const bool hi = lane & 1;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const uint32_t send = hi ? c0[j] : c1[j];
+    const uint32_t keep = hi ? c1[j] : c0[j];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
+    c0[j] = A.red(A.mad(A.mul(a, u), atw, t));
+    c1[j] = A.red(A.mad(A.mul(b, u), nbtw, t));
+  }
+}
+
 // slow path for non-canonical input (outside the Haskell contract, tolerated like `c % q`, types.h:62-66)
 __device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
 {
@@ -214,9 +234,9 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // per-lane twiddles of the 2^6 axis, loaded once
-  uint32_t ltw[7], m3l[12];
+  uint32_t ltw[9], m3l[12];        // inverse: [7] = crtTwiddle(even column) * tw_0, [8] = -crtTwiddle(odd column) * tw_0
 #pragma unroll
-  for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
+  for (int i = 0; i < 9; i++) ltw[i] = C.lane_tw[i * 32 + lane];
 #pragma unroll
   for (int i = 0; i < 12; i++) m3l[i] = C.lane_tw[(8 + i) * 32 + lane];
 
@@ -333,17 +353,19 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll
         for (int u = 0; u < U; u++) exchange_round<true, AR, true>(c0[u], c1[u], lane, 4, 0u, A);
 #pragma unroll
-        for (int r = 3; r >= 0; r--)
+        for (int r = 3; r >= 1; r--)
 #pragma unroll
           for (int u = 0; u < U; u++) exchange_round<true, AR>(c0[u], c1[u], lane, r, ltw[r], A);
-        // lane owns rows 2j + (lane>>4), columns 2*(lane&15) and 2*(lane&15)+1; crtTwiddle with inverse roots last
+        // last round merged with the inverse crtTwiddle: lane owns rows 2j + (lane>>4), columns 2*(lane&15) and +1
+#pragma unroll
+        for (int u = 0; u < U; u++) exchange_last_inv<AR>(c0[u], c1[u], lane, ltw[5], ltw[7], ltw[6], ltw[8], A);
 #pragma unroll
         for (int u = 0; u < U; u++)
           if (live[u]) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-              const int64_t a = (int64_t)A.canon(A.red(A.mul(ltw[5], c0[u][j])));
-              const int64_t b = (int64_t)A.canon(A.red(A.mul(ltw[6], c1[u][j])));
+              const int64_t a = (int64_t)A.canon(c0[u][j]);
+              const int64_t b = (int64_t)A.canon(c1[u][j]);
               if (K == 1) {
                 __stcs(reinterpret_cast<longlong2*>(out[u] + j * 64), make_longlong2(a, b));
               } else {
@@ -675,6 +697,9 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
         const int col = 2 * (lane & 15) + s;
         lane_tw[(5 + s) * 32 + lane] = col ? (uint32_t)r64(digit_rev(2, 5, col)) : 1;
       }
+      // the last round (r = 0) merged with the crtTwiddle above: a * tw_0 and -(b * tw_0)  (exchange_last_inv)
+      lane_tw[7 * 32 + lane] = (uint32_t)mulmod64(lane_tw[5 * 32 + lane], lane_tw[0 * 32 + lane], q);
+      lane_tw[8 * 32 + lane] = (uint32_t)((q - mulmod64(lane_tw[6 * 32 + lane], lane_tw[0 * 32 + lane], q)) % q);
     }
   }
   if (arith_class(q) == ARITH_M) {
