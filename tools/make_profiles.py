@@ -17,7 +17,7 @@ with open('profiles/r01_launch_list.md', 'w') as f:
     f.write('(cold-cache, serialised: compare shares, not absolutes).  Raw CSV: `profiles/r01_launches.csv`.\n\n')
     f.write('The timed region of the headline step launches only the two `k_fused_a` kernels (CRT, CRTInv), 65536 ring elements each;\n')
     f.write('their shares of the step under ncu: ' + ', '.join(f'{("CRTInv" if "<(bool)1" in k or "<1," in k else "CRT")} {100*sum(agg[k])/head_tot:.1f}%' for k in head) + '\n')
-    f.write('(CUDA events inside bench.py: CRT 0.732 ms, CRTInv 0.779 ms => 48.4% / 51.6%).  The other rows are the `per_op` and\n`other_configs` sections of bench.py and torch RNG / comparison kernels outside the timed region.\n\n')
+    f.write('(CUDA events inside bench.py: CRT 0.732 ms, CRTInv 0.760 ms => 49.0% / 51.0%).  The other rows are the `per_op` and\n`other_configs` sections of bench.py and torch RNG / comparison kernels outside the timed region.\n\n')
     f.write('| kernel | launches | mean us | total us | share of all |\n|---|---|---|---|---|\n')
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f'| `{k[:120]}` | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.0f} | {100*sum(v)/tot:.1f}% |\n')
