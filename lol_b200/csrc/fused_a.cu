@@ -475,11 +475,11 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
   extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN]
   const AR A0(CC.c[0]), A1(CC.c[1]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t ltw[2][7], m3l[2][12];
+  uint32_t ltw[2][9], m3l[2][12];
 #pragma unroll
   for (int l = 0; l < 2; l++) {
 #pragma unroll
-    for (int i = 0; i < 7; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
+    for (int i = 0; i < 9; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
 #pragma unroll
     for (int i = 0; i < 12; i++) m3l[l][i] = CC.c[l].lane_tw[(8 + i) * 32 + lane];
   }
@@ -507,8 +507,8 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
         }
       }
       if (hi_or != 0 || max0 >= CC.c[0].q || max1 >= CC.c[1].q) {
-#pragma unroll 1
-        for (int a = 0; a < 20; a++) {
+#pragma unroll
+        for (int a = 0; a < 20; a++) {            // static indices: a rolled loop would push v0 / v1 into local memory
           const longlong2 raw = src[a * 192];
           v0[a] = reduce_any(raw.x, CC.c[0].q);
           v1[a] = reduce_any(raw.y, CC.c[1].q);
@@ -587,17 +587,17 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
         exchange_round<true, AR, true>(c0[0], c1[0], lane, 4, 0u, A0);
         exchange_round<true, AR, true>(c0[1], c1[1], lane, 4, 0u, A1);
 #pragma unroll
-        for (int r = 3; r >= 0; r--) {
+        for (int r = 3; r >= 1; r--) {
           exchange_round<true, AR>(c0[0], c1[0], lane, r, ltw[0][r], A0);
           exchange_round<true, AR>(c0[1], c1[1], lane, r, ltw[1][r], A1);
         }
+        exchange_last_inv<AR>(c0[0], c1[0], lane, ltw[0][5], ltw[0][7], ltw[0][6], ltw[0][8], A0);     // last round + inverse crtTwiddle
+        exchange_last_inv<AR>(c0[1], c1[1], lane, ltw[1][5], ltw[1][7], ltw[1][6], ltw[1][8], A1);
         longlong2* out = ebase + i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          __stcs(out + j * 64, make_longlong2((int64_t)A0.canon(A0.red(A0.mul(ltw[0][5], c0[0][j]))),
-                                              (int64_t)A1.canon(A1.red(A1.mul(ltw[1][5], c0[1][j])))));
-          __stcs(out + j * 64 + 1, make_longlong2((int64_t)A0.canon(A0.red(A0.mul(ltw[0][6], c1[0][j]))),
-                                                  (int64_t)A1.canon(A1.red(A1.mul(ltw[1][6], c1[1][j])))));
+          __stcs(out + j * 64, make_longlong2((int64_t)A0.canon(c0[0][j]), (int64_t)A1.canon(c0[1][j])));
+          __stcs(out + j * 64 + 1, make_longlong2((int64_t)A0.canon(c1[0][j]), (int64_t)A1.canon(c1[1][j])));
         }
       }
     }
@@ -822,9 +822,11 @@ int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t
     int64_t grid = (int64_t)pl->num_sms * MB;
     if (grid > batch) grid = batch;
     const int64_t b_stride = b_batch == 1 ? 0 : (int64_t)kN * 2;
-    if (F->cls[0] == ARITH_M) {
-      if (inverse) k_fused_a_k2<true, ArithM, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
-      else k_fused_a_k2<false, ArithM, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+    if (F->cls[0] == ARITH_M) {      // 4 CTAs/SM: the Montgomery class needs the registers (see fused_a_crt)
+      int64_t g4 = (int64_t)pl->num_sms * 4;
+      if (g4 > batch) g4 = batch;
+      if (inverse) k_fused_a_k2<true, ArithM, W, 4, true><<<(int)g4, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+      else k_fused_a_k2<false, ArithM, W, 4, true><<<(int)g4, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
     } else {
       if (inverse) k_fused_a_k2<true, ArithS, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
       else k_fused_a_k2<false, ArithS, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
@@ -864,8 +866,19 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
     int64_t grid = (int64_t)pl->num_sms * MB;
     if (grid > batch) grid = batch;
     if (F->cls[0] == ARITH_M) {
-      if (inverse) k_fused_a_k2<true, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
-      else k_fused_a_k2<false, ArithM, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
+      // ArithM with both limbs in flight needs more than the 128 registers that 5 CTAs/SM leave: measured (config C
+      // moduli, % of HBM peak forward / inverse) 5 CTAs x 128 registers (spills) 57.5 / 52.8, 4 x 168 62.4 / 54.8
+      static int mbv = -1;        // LOLB_FUSED_A_K2_MB: tuning override (3, 4 or 5 CTAs per SM)
+      if (mbv < 0) { const char* v = getenv("LOLB_FUSED_A_K2_MB"); mbv = v ? atoi(v) : 4; }
+#define K2M(MBV)                                                                                                   \
+      do {                                                                                                         \
+        int64_t gg = (int64_t)pl->num_sms * MBV;                                                                   \
+        if (gg > batch) gg = batch;                                                                                \
+        if (inverse) k_fused_a_k2<true, ArithM, W, MBV><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);   \
+        else k_fused_a_k2<false, ArithM, W, MBV><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);          \
+      } while (0)
+      if (mbv == 3) K2M(3); else if (mbv == 5) K2M(5); else K2M(4);
+#undef K2M
     } else {
       if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
       else k_fused_a_k2<false, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
