@@ -842,7 +842,7 @@ int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t
 #define LM(AR, KK, MB) (inverse ? launch_a_mul<true, AR, KK, MB>(pl, y, b, batch, b_batch, t, C, st) \
                                 : launch_a_mul<false, AR, KK, MB>(pl, y, b, batch, b_batch, t, C, st))
     if (F->cls[t] == ARITH_M) rc = pl->k == 1 ? LM(ArithM, 1, 8) : LM(ArithM, 0, 8);
-    else rc = pl->k == 1 ? LM(ArithS, 1, 10) : LM(ArithS, 0, 10);
+    else rc = pl->k == 1 ? LM(ArithS, 1, 8) : LM(ArithS, 0, 8);
 #undef LM
     if (rc) return rc;
   }
@@ -906,12 +906,18 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
           count_launch();
           rc = LOLB_OK;
         } break;
+        case 8: rc = LA(ArithS, 1, 1, 3, 9, 1); break;
+        case 9: rc = LA(ArithS, 1, 1, 3, 8, 1); break;
+        case 10: rc = LA(ArithS, 1, 1, 3, 7, 1); break;
+        case 11: rc = LA(ArithS, 1, 1, 4, 6, 1); break;
+        case 12: rc = LA(ArithS, 1, 1, 2, 12, 1); break;
         case 0: rc = LA(ArithS, 1, 1, 6, 5, 2); break;
         case 1: rc = LA(ArithS, 1, 5, 10, 3, 1); break;
-        default: rc = LA(ArithS, 1, 1, 3, 10, 1); break;
+        case 13: rc = LA(ArithS, 1, 1, 3, 10, 1); break;     // the previous default: 64 registers, 32 bytes of spills
+        default: rc = LA(ArithS, 1, 1, 3, 8, 1); break;      // 3 warps x 8 CTAs/SM, 80 registers, no spills
       }
     } else {
-      rc = LA(ArithS, 0, 1, 3, 10, 1);
+      rc = LA(ArithS, 0, 1, 3, 8, 1);
     }
 #undef LA
     if (rc) return rc;
