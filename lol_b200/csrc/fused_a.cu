@@ -605,6 +605,102 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
   }
 }
 
+// tupSize >= 3 (and mixed-class pairs): every limb of one ring element in the same CTA iteration.  A launch per limb
+// reads 8 of every 8k bytes it touches, so HBM moves the whole batch k times; here a warp walks the limbs of its column
+// block back to back, the first limb's loads bring the sectors on chip and the others hit L1/L2, and the k partial-
+// sector stores of a row meet in L2 before they are written back: one HBM read and one HBM write per element again.
+// The limb index is a uniform loop counter, so one copy of the code reads its constants through c[limb].
+constexpr int kMaxLimbsN = 7;      // 7 x sizeof(FusedAConsts) fits the 4 KB kernel-parameter space
+struct FusedAConstsN { FusedAConsts c[kMaxLimbsN]; };
+
+template <bool INV, class AR, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_fused_a_kn(int64_t* __restrict__ y, int64_t batch, int k, const __grid_constant__ FusedAConstsN CC)
+{
+  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [k][kN]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
+    int64_t* ebase = y + (size_t)e * kN * k;
+    // ---------------- phase 1: 5^2 axis; warp-task = column block i2, all limbs in turn
+    for (int i2 = warp; i2 < kD2; i2 += WARPS) {
+      const int col = i2 * 32 + lane;
+#pragma unroll 1
+      for (int limb = 0; limb < k; limb++) {
+        const FusedAConsts& C = CC.c[limb];
+        const AR A(C);
+        const int64_t* src = ebase + (size_t)col * k + limb;
+        uint32_t v[20];
+        uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+        for (int a = 0; a < 20; a++) {
+          const int64_t raw = src[(size_t)(a * 192) * k];
+          v[a] = (uint32_t)raw;
+          hi_or |= (uint32_t)((uint64_t)raw >> 32);
+          lo_max = max(lo_max, v[a]);
+        }
+        if (hi_or != 0 || lo_max >= C.q) {
+#pragma unroll
+          for (int a = 0; a < 20; a++) v[a] = reduce_any(src[(size_t)(a * 192) * k], C.q);
+        }
+        axis5<INV, AR>(v, C, A);
+        uint32_t* dst = sm_dyn + limb * kN + col;
+#pragma unroll
+        for (int a = 0; a < 20; a++) dst[a * 192] = v[a];
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp; warp-task = row block i3, all limbs in turn
+    for (int i3 = warp; i3 < kD3; i3 += WARPS) {
+#pragma unroll 1
+      for (int limb = 0; limb < k; limb++) {
+        const FusedAConsts& C = CC.c[limb];
+        const AR A(C);
+        const uint32_t* lt = C.lane_tw + lane;
+        uint32_t x[6], c0[3], c1[3];
+#pragma unroll
+        for (int j = 0; j < 6; j++) x[j] = sm_dyn[limb * kN + i3 * 192 + j * 32 + lane];
+        if (!INV) {
+          uint32_t m3l[12], ltw[4];
+#pragma unroll
+          for (int i = 0; i < 12; i++) m3l[i] = __ldg(lt + (8 + i) * 32);
+#pragma unroll
+          for (int i = 0; i < 4; i++) ltw[i] = __ldg(lt + (1 + i) * 32);
+          axis3<false, AR>(x, C, A, m3l);
+#pragma unroll
+          for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+#pragma unroll
+          for (int r = 0; r < 4; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[r], A);
+          exchange_round<false, AR, true>(c0, c1, lane, 4, 0u, A);
+          int64_t* out = ebase + (size_t)(i3 * 192 + (lane & 1) * 32 + (lane >> 1)) * k + limb;
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            out[(size_t)(j * 64) * k] = (int64_t)A.canon(c0[j]);
+            out[(size_t)(j * 64 + 16) * k] = (int64_t)A.canon(c1[j]);
+          }
+        } else {
+          uint32_t m3l[12] = {}, ltw[9];
+#pragma unroll
+          for (int i = 1; i < 9; i++) ltw[i] = (i == 4) ? 0u : __ldg(lt + i * 32);
+          axis3<true, AR>(x, C, A, m3l);
+#pragma unroll
+          for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+          exchange_round<true, AR, true>(c0, c1, lane, 4, 0u, A);
+#pragma unroll
+          for (int r = 3; r >= 1; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
+          exchange_last_inv<AR>(c0, c1, lane, ltw[5], ltw[7], ltw[6], ltw[8], A);
+          int64_t* out = ebase + (size_t)(i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k + limb;
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            out[(size_t)(j * 64) * k] = (int64_t)A.canon(c0[j]);
+            out[(size_t)(j * 64 + 1) * k] = (int64_t)A.canon(c1[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ host: constants from the plan's root tables
 
 enum ArithClass { ARITH_NONE = 0, ARITH_S, ARITH_M };
@@ -631,7 +727,7 @@ inline uint64_t rd(const std::vector<int64_t>& tab, int64_t j, int k, int limb, 
   return (uint64_t)v;
 }
 
-void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, uint32_t* lane_tw /* [kLaneRows][32] */)
+void build_consts(const lolb_plan* pl, bool inverse, int limb, int cls, FusedAConsts* C, uint32_t* lane_tw /* [kLaneRows][32] */)
 {
   const int k = pl->k;
   const uint64_t q = (uint64_t)pl->qs[limb];
@@ -702,7 +798,7 @@ void build_consts(const lolb_plan* pl, bool inverse, int limb, FusedAConsts* C, 
       lane_tw[8 * 32 + lane] = (uint32_t)((q - mulmod64(lane_tw[6 * 32 + lane], lane_tw[0 * 32 + lane], q)) % q);
     }
   }
-  if (arith_class(q) == ARITH_M) {
+  if (cls == ARITH_M) {
     // constants to Montgomery form c * 2^32 mod q; r0 = -q^-1 mod 2^32 (Newton iteration on the odd q)
     auto mont = [&](uint32_t c) { return (uint32_t)((((uint64_t)c) << 32) % q); };
     uint32_t inv = (uint32_t)q;                       // q * inv == 1 mod 2^3 initially
@@ -739,13 +835,18 @@ int fused_a_select(lolb_plan* pl, void** slot)
   std::vector<uint32_t> lt((size_t)k * 2 * kLaneRows * 32, 1u);
   F->cls.assign(k, ARITH_NONE);
   for (int t = 0; t < k; t++) F->cls[t] = arith_class((uint64_t)pl->qs[t]);
+  // mixed classes: every odd modulus of the small class also fits the Montgomery class, and one class for all limbs
+  // lets the multi-limb kernels (k_fused_a_k2, k_fused_a_kn) take the element in one pass
+  bool any_m = false, all_odd = true;
+  for (int t = 0; t < k; t++) { any_m |= F->cls[t] == ARITH_M; all_odd &= (pl->qs[t] & 1) != 0; }
+  if (any_m && all_odd) F->cls.assign(k, ARITH_M);
   F->fwd.assign(k, FusedAConsts{});
   F->inv.assign(k, FusedAConsts{});
   F->ok_fwd = pl->has_fwd && pl->ru.size() == 3;
   F->ok_inv = pl->has_inv && pl->ruinv.size() == 3 && (int)pl->mhatinv.size() == k;
   for (int t = 0; t < k; t++) {
-    if (F->ok_fwd) build_consts(pl, false, t, &F->fwd[t], lt.data() + ((size_t)t * 2 + 0) * kLaneRows * 32);
-    if (F->ok_inv) build_consts(pl, true, t, &F->inv[t], lt.data() + ((size_t)t * 2 + 1) * kLaneRows * 32);
+    if (F->ok_fwd) build_consts(pl, false, t, F->cls[t], &F->fwd[t], lt.data() + ((size_t)t * 2 + 0) * kLaneRows * 32);
+    if (F->ok_inv) build_consts(pl, true, t, F->cls[t], &F->inv[t], lt.data() + ((size_t)t * 2 + 1) * kLaneRows * 32);
   }
   if (F->d_lane_tw) { cudaFree(F->d_lane_tw); F->d_lane_tw = nullptr; }
   LOLB_CUDA(cudaMalloc((void**)&F->d_lane_tw, lt.size() * sizeof(uint32_t)));
@@ -887,6 +988,37 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
     if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_k2");
     count_launch();
     return LOLB_OK;
+  }
+  if (pl->k >= 2 && pl->k <= kMaxLimbsN && !getenv("LOLB_FUSED_A_PER_LIMB")) {
+    bool same = true;
+    for (int t = 1; t < pl->k; t++) same &= F->cls[t] == F->cls[0];
+    if (same) {
+      FusedAConstsN CC;
+      for (int t = 0; t < pl->k; t++) CC.c[t] = inverse ? F->inv[t] : F->fwd[t];
+      static int knv = -1;        // LOLB_FUSED_A_KN: tuning override of the CTA shape
+      if (knv < 0) { const char* v = getenv("LOLB_FUSED_A_KN"); knv = v ? atoi(v) : 0; }
+      const size_t smem = (size_t)pl->k * kN * sizeof(uint32_t);
+      const int fit = (int)((227 * 1024) / (smem + 1024));      // CTAs per SM the tile allows
+      cudaError_t e = cudaSuccess;
+#define KN(AR, W, MB)                                                                                             \
+      do {                                                                                                         \
+        auto kern = inverse ? k_fused_a_kn<true, AR, W, MB> : k_fused_a_kn<false, AR, W, MB>;                      \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+        int64_t gg = (int64_t)pl->num_sms * (fit < MB ? fit : MB);                                                 \
+        if (gg > batch) gg = batch;                                                                                \
+        if (e == cudaSuccess) kern<<<(int)gg, W * 32, smem, st>>>(y, batch, pl->k, CC);                            \
+      } while (0)
+      if (F->cls[0] == ARITH_M) {
+        if (knv == 1) KN(ArithM, 4, 5); else if (knv == 2) KN(ArithM, 10, 2); else if (knv == 3) KN(ArithM, 5, 4); else KN(ArithM, 6, 4);
+      } else {
+        if (knv == 1) KN(ArithS, 4, 5); else if (knv == 2) KN(ArithS, 10, 2); else if (knv == 3) KN(ArithS, 5, 4); else KN(ArithS, 6, 4);
+      }
+#undef KN
+      if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_kn");
+      count_launch();
+      return LOLB_OK;
+    }
   }
   for (int t = 0; t < pl->k; t++) {
     const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];

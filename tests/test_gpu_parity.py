@@ -199,7 +199,11 @@ def test_config_b_matches_reference_digests(dropin):
 # (14400, [43201]): first modulus past the 32-bit-accumulate bound; the triple mixes both arithmetic classes
 BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
                 (1024, [12289]), (64 * 27, [3457]), CONFIG_A, CONFIG_C, (14400, [429336001]), (14400, [43201]),
-                (14400, [14401, 1008001, 429336001]), (14400, [2148249601])]
+                (14400, [14401, 1008001, 429336001]), (14400, [2148249601]),
+                # tupSize 4, 5, 7: all limbs of an element in one CTA iteration (k_fused_a_kn); 8: one launch per limb again
+                (14400, [43201, 57601, 100801, 115201]), (14400, [14401, 43201, 57601, 100801, 115201]),
+                (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201]),
+                (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201, 273601])]
 
 
 @pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
