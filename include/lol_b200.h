@@ -178,6 +178,27 @@ int lolb_mulRq(const lolb_plan* plan, hInt_t* a, const hInt_t* b, int64_t batch,
 int lolb_crtMulRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream);
 int lolb_mulCrtInvRq(const lolb_plan* plan, hInt_t* y, const hInt_t* b, int64_t batch, int64_t b_batch, void* stream);
 
+/* The coefficient-wise steps of SymmSHE's ciphertext multiply and quadratic key switch, which the reference runs on the
+ * host between its FFI calls (lol-apps/Crypto/Lol/Applications/SymmSHE.hs); here one streaming pass each over the
+ * device-resident batch.  Operands are [batch][n][tupSize] arrays of canonical residues.
+ *   lolb_ctMulRq      (d0,d1,d2) <- (a0 b0, a0 b1 + a1 b0, a1 b1) [. gCRT when mul_g]: the product of two linear
+ *                     ciphertexts whose components are in the CRT basis, SymmSHE.hs:443-449 (`mulG <$> c1 * c2`;
+ *                     zipWithT (*) of UCyc.hs:232; mulGCRT of CPP.hs:230).  Outputs may alias inputs.
+ *   lolb_gadgetLength number of gadget digits l over this plan's moduli: base 0 = TrivGad (one per limb,
+ *                     ZqBasic.hs:227-232), base b >= 2 = BaseBGad b (gadlen, ZqBasic.hs:241-243); tuples concatenate
+ *                     (Gadget.hs:92-101).  -1 on a bad argument.
+ *   lolb_decomposeRq  digits[d] <- reduce(decompose(x)[d]) for a Pow-basis x (SymmSHE.hs:314; Cyc.hs:603; lift =
+ *                     decode', ZqBasic.hs:92-94; decomp / divModCent, Numeric.hs:202-205, 227-234); digits is
+ *                     [l][batch][n][tupSize].
+ *   lolb_knapsackRq   c0 += sum_d digits[d] . hints[d][0],  c1 += sum_d digits[d] . hints[d][1]  (SymmSHE.hs:302-305 and
+ *                     :372); digits in the CRT basis, hints is [l][2][n][tupSize] (one ring element each). */
+int lolb_ctMulRq(const lolb_plan* plan, const hInt_t* a0, const hInt_t* a1, const hInt_t* b0, const hInt_t* b1,
+                 hInt_t* d0, hInt_t* d1, hInt_t* d2, int64_t batch, int mul_g, void* stream);
+int lolb_gadgetLength(const lolb_plan* plan, int64_t base);
+int lolb_decomposeRq(const lolb_plan* plan, const hInt_t* x, hInt_t* digits, int64_t batch, int64_t base, void* stream);
+int lolb_knapsackRq(const lolb_plan* plan, const hInt_t* digits, int ell, const hInt_t* hints, hInt_t* c0, hInt_t* c1,
+                    int64_t batch, void* stream);
+
 /* modulus-free rings; plan from lolb_plan_create_c */
 int lolb_tensorLR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);
 int lolb_tensorLInvR(const lolb_plan* plan, hInt_t* y, int64_t batch, void* stream);

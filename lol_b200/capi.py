@@ -148,6 +148,23 @@ class PlanRq:
     def mul_crt_inv(self, y_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
         return int(lib().lolb_mulCrtInvRq(self._h, _p(y_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
 
+    # SymmSHE steps between the CRTs (lolb_ctMulRq / lolb_decomposeRq / lolb_knapsackRq)
+    def ct_mul(self, a0: int, a1: int, b0: int, b1: int, d0: int, d1: int, d2: int, batch: int, mul_g: bool = True, stream: int = 0) -> int:
+        return int(lib().lolb_ctMulRq(self._h, _p(a0), _p(a1), _p(b0), _p(b1), _p(d0), _p(d1), _p(d2), _i64(batch),
+                                      C.c_int(int(mul_g)), _p(stream)))
+
+    def gadget_length(self, base: int = 0) -> int:
+        ell = int(lib().lolb_gadgetLength(self._h, _i64(base)))
+        if ell < 0:
+            raise LolB200Error(LOLB_ERR_ARG, last_error())
+        return ell
+
+    def decompose(self, x: int, digits: int, batch: int, base: int = 0, stream: int = 0) -> int:
+        return int(lib().lolb_decomposeRq(self._h, _p(x), _p(digits), _i64(batch), _i64(base), _p(stream)))
+
+    def knapsack(self, digits: int, ell: int, hints: int, c0: int, c1: int, batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_knapsackRq(self._h, _p(digits), C.c_int(ell), _p(hints), _p(c0), _p(c1), _i64(batch), _p(stream)))
+
     def apply_host(self, ops: str, host_ptr: int, batch: int) -> int:
         return int(lib().lolb_rq_apply_host(self._h, ops.encode(), _p(host_ptr), _i64(batch)))
 

@@ -304,6 +304,41 @@ extern "C" int lolb_mulCrtInvRq(const lolb_plan* plan, hInt_t* y, const hInt_t* 
   return rc ? rc : crt_rq(plan, true, y, batch, stream);
 }
 
+// SymmSHE's steps between the CRTs (BASELINE.json configs[3]).  Device pointers, canonical
+// residues, the batch layout of every other entry point.
+extern "C" int lolb_ctMulRq(const lolb_plan* plan, const hInt_t* a0, const hInt_t* a1, const hInt_t* b0, const hInt_t* b1,
+                            hInt_t* d0, hInt_t* d1, hInt_t* d2, int64_t batch, int mul_g, void* stream)
+{
+  if (!plan || plan->kind != PLAN_RQ) { set_error(std::string(__func__) + ": wrong or NULL plan"); return LOLB_ERR_ARG; }
+  if (batch < 0) { set_error(std::string(__func__) + ": bad batch"); return LOLB_ERR_ARG; }
+  if (batch > 0 && (!a0 || !a1 || !b0 || !b1 || !d0 || !d1 || !d2)) { set_error("lolb_ctMulRq: null operand"); return LOLB_ERR_ARG; }
+  if (mul_g && !plan->d_gcrt) { set_error("lolb_ctMulRq: no gCRT vector (no CRT over this modulus / index)"); return LOLB_ERR_NO_CRT; }
+  return she_ct_mul(plan, a0, a1, b0, b1, mul_g ? plan->d_gcrt : nullptr, d0, d1, d2, batch, (cudaStream_t)stream);
+}
+
+extern "C" int lolb_gadgetLength(const lolb_plan* plan, int64_t base)
+{
+  if (!plan || plan->kind != PLAN_RQ) { set_error("lolb_gadgetLength: needs an Rq plan"); return -1; }
+  return she_gadget_length(plan, base);
+}
+
+extern "C" int lolb_decomposeRq(const lolb_plan* plan, const hInt_t* x, hInt_t* digits, int64_t batch, int64_t base, void* stream)
+{
+  if (!plan || plan->kind != PLAN_RQ) { set_error(std::string(__func__) + ": wrong or NULL plan"); return LOLB_ERR_ARG; }
+  if (batch < 0) { set_error(std::string(__func__) + ": bad batch"); return LOLB_ERR_ARG; }
+  if (batch > 0 && (!x || !digits || x == digits)) { set_error("lolb_decomposeRq: x and digits must be distinct device arrays"); return LOLB_ERR_ARG; }
+  return she_decompose(plan, x, digits, batch, base, (cudaStream_t)stream);
+}
+
+extern "C" int lolb_knapsackRq(const lolb_plan* plan, const hInt_t* digits, int ell, const hInt_t* hints, hInt_t* c0, hInt_t* c1,
+                               int64_t batch, void* stream)
+{
+  if (!plan || plan->kind != PLAN_RQ) { set_error(std::string(__func__) + ": wrong or NULL plan"); return LOLB_ERR_ARG; }
+  if (batch < 0) { set_error(std::string(__func__) + ": bad batch"); return LOLB_ERR_ARG; }
+  if (batch > 0 && ell > 0 && (!digits || !hints || !c0 || !c1 || c0 == c1)) { set_error("lolb_knapsackRq: null or aliased operand"); return LOLB_ERR_ARG; }
+  return she_knapsack(plan, digits, ell, hints, c0, c1, batch, (cudaStream_t)stream);
+}
+
 // modulus-free rings: streaming kernel when the index has one or two small odd primes, generic engine otherwise
 static int plain_line(const lolb_plan* plan, int ring, int kind, void* y, int64_t batch, double rscale, void* stream)
 {

@@ -622,12 +622,14 @@ k_fused_a_kn(int64_t* __restrict__ y, int64_t batch, int k, const __grid_constan
   for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
     int64_t* ebase = y + (size_t)e * kN * k;
     // ---------------- phase 1: 5^2 axis; warp-task = column block i2, all limbs in turn
-    for (int i2 = warp; i2 < kD2; i2 += WARPS) {
-      const int col = i2 * 32 + lane;
+    // (work items (limb, task) are dealt round-robin in limb-major order, so the warps stay balanced whenever W divides
+    // 6k and 20k, while the limb stays the uniform counter of the outer loop)
 #pragma unroll 1
-      for (int limb = 0; limb < k; limb++) {
-        const FusedAConsts& C = CC.c[limb];
-        const AR A(C);
+    for (int limb = 0; limb < k; limb++) {
+      const FusedAConsts& C = CC.c[limb];
+      const AR A(C);
+      for (int i2 = (warp + WARPS * kD2 - limb * kD2 % WARPS) % WARPS; i2 < kD2; i2 += WARPS) {
+        const int col = i2 * 32 + lane;
         const int64_t* src = ebase + (size_t)col * k + limb;
         uint32_t v[20];
         uint32_t hi_or = 0, lo_max = 0;
@@ -650,12 +652,12 @@ k_fused_a_kn(int64_t* __restrict__ y, int64_t batch, int k, const __grid_constan
     }
     __syncthreads();
     // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp; warp-task = row block i3, all limbs in turn
-    for (int i3 = warp; i3 < kD3; i3 += WARPS) {
 #pragma unroll 1
-      for (int limb = 0; limb < k; limb++) {
-        const FusedAConsts& C = CC.c[limb];
-        const AR A(C);
-        const uint32_t* lt = C.lane_tw + lane;
+    for (int limb = 0; limb < k; limb++) {
+      const FusedAConsts& C = CC.c[limb];
+      const AR A(C);
+      const uint32_t* lt = C.lane_tw + lane;
+      for (int i3 = (warp + WARPS * kD3 - limb * kD3 % WARPS) % WARPS; i3 < kD3; i3 += WARPS) {
         uint32_t x[6], c0[3], c1[3];
 #pragma unroll
         for (int j = 0; j < 6; j++) x[j] = sm_dyn[limb * kN + i3 * 192 + j * 32 + lane];
@@ -1008,11 +1010,20 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
         if (gg > batch) gg = batch;                                                                                \
         if (e == cudaSuccess) kern<<<(int)gg, W * 32, smem, st>>>(y, batch, pl->k, CC);                            \
       } while (0)
-      if (F->cls[0] == ARITH_M) {
-        if (knv == 1) KN(ArithM, 4, 5); else if (knv == 2) KN(ArithM, 10, 2); else if (knv == 3) KN(ArithM, 5, 4); else KN(ArithM, 6, 4);
-      } else {
-        if (knv == 1) KN(ArithS, 4, 5); else if (knv == 2) KN(ArithS, 10, 2); else if (knv == 3) KN(ArithS, 5, 4); else KN(ArithS, 6, 4);
+      // warps per CTA: a divisor pattern of 6k and 20k that keeps about 24 warps per SM next to the k x 15 KB tile
+      int shape = knv ? knv : (pl->k == 3 || pl->k == 6) ? 6 : pl->k == 4 ? 8 : pl->k == 5 ? 10 : 7;
+      if (pl->k == 6 && !knv) shape = 12;
+#define KNS(AR)                                                                                                   \
+      switch (shape) {                                                                                             \
+        case 6: KN(AR, 6, 4); break;                                                                               \
+        case 8: KN(AR, 8, 3); break;                                                                               \
+        case 10: KN(AR, 10, 2); break;                                                                             \
+        case 12: KN(AR, 12, 2); break;                                                                             \
+        case 4: KN(AR, 4, 5); break;                                                                               \
+        default: KN(AR, 7, 2); break;                                                                              \
       }
+      if (F->cls[0] == ARITH_M) { KNS(ArithM) } else { KNS(ArithS) }
+#undef KNS
 #undef KN
       if (e == cudaSuccess) e = cudaGetLastError();
       if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_kn");

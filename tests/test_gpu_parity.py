@@ -554,3 +554,83 @@ def test_full_size_properties(torch_cuda, oracle, cfg, B):
     ref = oracle.tensorCRTInvRq(oracle.mulRq(oracle.tensorCRTRq(x[b].cpu().numpy(), pe, ru, qs),
                                              oracle.tensorCRTRq(x2[b].cpu().numpy(), pe, ru, qs), qs), pe, rui, mh, qs)
     assert np.array_equal(prod[b].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------ SymmSHE ciphertext multiply + key switch (configs[3])
+def _hint(rng, ell, n, qs):
+    return np.stack([np.stack([zq_input(rng, n, qs) for _ in range(2)]) for _ in range(ell)])
+
+
+@pytest.mark.parametrize("m,qs,base", [(14400, [1008001, 1065601], 0), (14400, [1008001, 1065601], 1000), (21, [43, 127, 379], 0),
+                                       (21, [43, 127, 379], 2), (2, [13, 17, 19], 3), (45, [2148249601], 65536), (16, [97], 0)],
+                         ids=lambda v: str(v))
+def test_symmshe_steps_match_oracle(torch_cuda, oracle, m, qs, base):
+    """lolb_ctMulRq / lolb_decomposeRq / lolb_knapsackRq and their composition (SymmSHE.hs:302-314, 359-372, 443-449)
+    against the numpy restatement, step by step and end to end, bit-exact."""
+    torch = torch_cuda
+    from lol_b200.symmshe import CudaSymmSHE
+    from oracle import symmshe as S
+    B = 3 if m == 14400 else 11
+    rng = np.random.default_rng(m * 7 + base)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    g, _ = T.g_crt_vectors(m, qs)
+    she = CudaSymmSHE(m, qs, gad_base=base)
+    assert she.ell == S.gadget_length(qs, base) and she.gadget() == S.gadget(qs, base)
+    cts = [zq_input(rng, n, qs, batch=B) for _ in range(4)]
+    dev = [torch.from_numpy(c).cuda() for c in cts]
+    # ciphertext product on CRT-basis components
+    d = she.mulCT(dev[:2], dev[2:], basis="crt")
+    ref = S.ct_mul_crt(cts[:2], cts[2:], g, qs)
+    for got, want in zip(d, ref):
+        assert np.array_equal(got.cpu().numpy(), want)
+    assert all(torch.equal(x, torch.from_numpy(c).cuda()) for x, c in zip(dev, cts))      # pure
+    # gadget digits of a Pow-basis element
+    digits = she.decompose(dev[0])
+    assert np.array_equal(digits.cpu().numpy(), S.decompose_reduced(cts[0], qs, base))
+    # knapsack
+    hint = _hint(rng, she.ell, n, qs)
+    hint_d = torch.from_numpy(hint).cuda()
+    o = she.knapsack(hint_d, digits, dev[1], dev[2])
+    want = S.knapsack(hint, S.decompose_reduced(cts[0], qs, base), cts[1], cts[2], qs)
+    assert np.array_equal(o[0].cpu().numpy(), want[0]) and np.array_equal(o[1].cpu().numpy(), want[1])
+    # the whole sequence from Pow-basis ciphertexts, one oracle composition per ciphertext pair
+    out = she.mulAndSwitch(dev[:2], dev[2:], hint_d, basis="pow")
+    for b in range(B):
+        w = S.mul_and_switch(oracle, [cts[0][b], cts[1][b]], [cts[2][b], cts[3][b]], hint, (pe, ru, rui, mh, g), qs, base)
+        assert np.array_equal(out[0][b].cpu().numpy(), w[0]) and np.array_equal(out[1][b].cpu().numpy(), w[1])
+    assert all(torch.equal(x, torch.from_numpy(c).cuda()) for x, c in zip(dev, cts))
+    # in-place variant gives the same result
+    work = [x.clone() for x in dev]
+    out2 = she.mulAndSwitch(work[:2], work[2:], hint_d, basis="pow", inplace=True)
+    assert torch.equal(out2[0], out[0]) and torch.equal(out2[1], out[1])
+    # empty batch and argument errors
+    e = torch.empty(0, n, len(qs), dtype=torch.int64, device="cuda")
+    assert she.decompose(e).shape == (she.ell, 0, n, len(qs))
+    from lol_b200 import capi
+    with pytest.raises(capi.LolB200Error):
+        she.mulCT(dev[:2], dev[2:3])
+    with pytest.raises(capi.LolB200Error):
+        CudaSymmSHE(m, qs, gad_base=1)
+
+
+@pytest.mark.parametrize("base", [0, 256], ids=["TrivGad", "BaseBGad256"])
+def test_symmshe_full_size_identity_hint(torch_cuda, base):
+    """Config C at bench size: with the hint polynomials (gadget_i, 0) the key switch returns (c0 + c2, c1), because
+    sum_i gadget_i * decompose(c2)_i = c2 (Gadget.hs:60-66) and CRT . CRT^-1 = id; the ciphertext product commutes."""
+    torch = torch_cuda
+    from lol_b200.symmshe import CudaSymmSHE
+    m, qs = CONFIG_C
+    B = 2048
+    she = CudaSymmSHE(m, qs, gad_base=base)
+    n, k = she.n, she.k
+    q = torch.tensor(qs, dtype=torch.int64, device="cuda")
+    c = [_device_uniform(torch, B, n, qs, seed=s) for s in range(4)]
+    d = she.mulCT(c[:2], c[2:], basis="pow")
+    d_sw = she.mulCT(c[2:], c[:2], basis="pow")
+    assert all(torch.equal(u, v) for u, v in zip(d, d_sw))
+    assert all(int(u.min()) >= 0 and bool((u < q).all()) for u in d)
+    hint = torch.zeros(she.ell, 2, n, k, dtype=torch.int64, device="cuda")
+    for i, gi in enumerate(she.gadget()):
+        hint[i, 0] = she.t.scalarCRT(gi, batch=1)[0]
+    o = she.keySwitchQuadCirc(hint, d)
+    assert torch.equal(o[0], (d[0] + d[2]) % q) and torch.equal(o[1], d[1])

@@ -195,3 +195,42 @@ def test_pow2_crt_is_negacyclic_evaluation(oracle, e, q):
                 w[pos], w[pos + st] = (u + t) % q, (u - t) * tw[pos & (st - 1)] % q
     s = T.mhat_inv(m, q)
     assert [c * s % q for c in w] == [int(c) for c in y.reshape(-1)]
+
+
+# ------------------------------------------------------------------ SymmSHE host-side steps (oracle/symmshe.py)
+@pytest.mark.parametrize("qs", [[1008001, 1065601], [14401], [17, 257, 65537], [2148249601]], ids=str)
+@pytest.mark.parametrize("base", [0, 2, 3, 16, 1000], ids=lambda b: f"base{b}")
+def test_gadget_identity_and_digit_ranges(qs, base):
+    """sum_i gadget_i * decompose(x)_i = x (Gadget.hs:60-66), digits centered in [-b/2, b/2) (Numeric.hs:225-234),
+    lift in [-q/2, q/2) (ZqBasic.hs:91-94), gadlen = number of base-b digits of q (ZqBasic.hs:241-243)."""
+    from oracle import symmshe as S
+    rng = np.random.default_rng(len(qs) * 1000 + base)
+    x = zq_input(rng, 24, qs, batch=3)
+    x[0, 0, :] = 0
+    x[0, 1, :] = [q - 1 for q in qs]
+    x[0, 2, :] = [q // 2 for q in qs]
+    x[0, 3, :] = [(q + 1) // 2 for q in qs]
+    g, ints, red = S.gadget(qs, base), S.decompose(x, qs, base), S.decompose_reduced(x, qs, base)
+    assert len(g) == len(ints) == red.shape[0] == S.gadget_length(qs, base)
+    acc = np.zeros_like(x)
+    for gi, di in zip(g, red):
+        acc = (acc + di * np.asarray(gi, dtype=np.int64)) % np.asarray(qs)
+    assert np.array_equal(acc, x)
+    pos = 0
+    for l, q in enumerate(qs):
+        lf = S.lift(x[..., l], q)
+        assert lf.min() >= -(q // 2) - (q % 2 == 0) * 0 - 1 and 2 * lf.max() < q and np.array_equal(lf % q, x[..., l])
+        nd = 1 if base == 0 else S.gadlen(base, q)
+        if base:
+            assert base ** (nd - 1) <= q < base ** nd
+            for d in ints[pos:pos + nd - 1]:
+                assert d.min() >= -(base // 2) and d.max() < base - base // 2
+        pos += nd
+
+
+def test_div_mod_cent_matches_haskell_semantics():
+    from oracle import symmshe as S
+    a = np.arange(-50, 50, dtype=np.int64)
+    for b in (2, 3, 7, 10):
+        quo, r = S.div_mod_cent(a, b)
+        assert np.array_equal(quo * b + r, a) and r.min() >= -(b // 2) and r.max() < b - b // 2
