@@ -364,6 +364,75 @@ def run_gpu_arm(args):
         del dg, zg, cg
         x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
 
+    # ---- configs[3]: SymmSHE ciphertext multiply + quadratic key switch, ciphertext pairs sharded over the ranks
+    # (SymmSHE.hs:443-449 then :359-372; op sequence of SURVEY.md section 3.5 with TrivGad over the two limbs, l = 2:
+    # 4 CRT, tensor product with mulG, CRTInv, decompose, l CRT, knapsack -- (22 + 4l) x 8nk algorithmic bytes per pair)
+    she_res = None
+    if not args.no_per_op:
+        from lol_b200.symmshe import CudaSymmSHE
+        del x
+        torch.cuda.empty_cache()
+        qs_c, Bs = [1008001, 1065601], args.she_pairs
+        she = CudaSymmSHE(M, qs_c, gad_base=0)
+        cts = [torch.cat([torch.randint(0, q, (Bs, she.n, 1), dtype=torch.int64, device="cuda", generator=gen) for q in qs_c], dim=2).contiguous()
+               for _ in range(4)]
+        hint = torch.cat([torch.randint(0, q, (she.ell, 2, she.n, 1), dtype=torch.int64, device="cuda", generator=gen) for q in qs_c], dim=3).contiguous()
+
+        def she_step():
+            she.mulAndSwitch(cts[:2], cts[2:], hint, basis="pow", inplace=True)
+
+        for _ in range(3):
+            she_step()
+        l0 = capi.kernel_launch_count()
+        she_step()
+        she_launches = capi.kernel_launch_count() - l0
+        if world > 1:
+            dist.barrier()
+        ms = time_op(torch, she_step, 10)
+        if world > 1:
+            tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        elem = 8 * she.n * she.k
+        alg = (22 + 4 * she.ell) * elem
+        she_res = {"workload": f"configs[3]: m=14400, q=(1008001,1065601), TrivGad (l={she.ell}), {Bs} ciphertext pairs per GPU, "
+                               "Pow-basis inputs, in place", "ms": ms, "ct_pairs_per_s": world * Bs / (ms * 1e-3),
+                   "algorithmic_bytes_per_pair": alg, "GB/s_per_gpu": alg * Bs / (ms * 1e-3) / 1e9,
+                   "frac": alg * Bs / (ms * 1e-3) / 1e9 / peak, "kernel_launches_per_step": int(she_launches)}
+        if world == 1:
+            d3 = she.mulCT(cts[:2], cts[2:], basis="crt")
+            dg = she.decompose(cts[0])
+            steps = {"ct_mul": (lambda: capi.check(she.t.plan.ct_mul(*[c.data_ptr() for c in cts], *[d.data_ptr() for d in d3], Bs, True, stream)), 7),
+                     "decompose": (lambda: capi.check(she.t.plan.decompose(cts[0].data_ptr(), dg.data_ptr(), Bs, 0, stream)), 1 + she.ell),
+                     "knapsack": (lambda: capi.check(she.t.plan.knapsack(dg.data_ptr(), she.ell, hint.data_ptr(), d3[0].data_ptr(), d3[1].data_ptr(), Bs, stream)), she.ell + 4)}
+            for name, (fn, passes) in steps.items():
+                fn(); fn()
+                sms = time_op(torch, fn, 10)
+                she_res[name] = {"ms": sms, "GB/s": passes * elem * Bs / (sms * 1e-3) / 1e9, "frac": passes * elem * Bs / (sms * 1e-3) / 1e9 / peak}
+            del d3, dg
+            if not args.no_cpu:      # the same sequence on one host core: compiled reference CRTs + numpy for the Haskell-side steps
+                import time as _time
+                import numpy as np
+                from oracle import cpu as ocpu, symmshe as osym, tables as T
+                lib = ocpu.reference() if ocpu.have_reference() else ocpu.restatement()
+                pe = T.pe_array(M)
+                tabs = (pe, T.ru_tables_zq(M, qs_c), T.ru_tables_zq(M, qs_c, True), [T.mhat_inv(M, q) for q in qs_c], T.g_crt_vectors(M, qs_c)[0])
+                rng = np.random.default_rng(0)
+                mk = lambda: np.stack([rng.integers(0, q, size=she.n) for q in qs_c], axis=-1).astype(np.int64)
+                hint_h = hint.cpu().numpy()
+                sample = 8
+                t0 = _time.perf_counter()
+                for _ in range(sample):
+                    osym.mul_and_switch(lib, [mk(), mk()], [mk(), mk()], hint_h, tabs, qs_c, 0)
+                she_res["cpu_baseline"] = {"value": sample / (_time.perf_counter() - t0), "unit": "ct_pairs/s", "cores": 1,
+                                           "kind": "reference" if ocpu.have_reference() else "port",
+                                           "sample": f"{sample} ciphertext pairs, reference CRTs + numpy host steps"}
+        del cts, hint
+        torch.cuda.empty_cache()
+        x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
+    if she_res is not None:
+        other["configs[3]: SymmSHE ciphertext multiply + key switch"] = she_res
+
     cpu_base = None
     if world == 1 and not args.no_cpu:
         cpu_base = cpu_arm(args.cpu_pairs)
@@ -394,6 +463,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--e2e-batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--cpu-pairs", type=int, default=4096, help="CRT+CRTInv pairs per host process in the cpu_baseline sample")
+    ap.add_argument("--she-pairs", type=int, default=4096, help="ciphertext pairs per GPU in the configs[3] section")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-per-op", action="store_true")

@@ -11,5 +11,11 @@ for k, v in (d.get("per_op") or {}).items():
     print("  %-8s %.3f ms  frac %.3f  [%s]" % (k, v["ms"], v["frac"], v["kernel"]))
 for label, res in (d.get("other_configs") or {}).items():
     print("  ==", label)
+    if "ct_pairs_per_s" in res:
+        print("     %.3f ms/step  %.3gM ct pairs/s  %.0f GB/s per GPU  frac %.3f  launches/step %d" % (res["ms"], res["ct_pairs_per_s"] / 1e6, res["GB/s_per_gpu"], res["frac"], res["kernel_launches_per_step"]))
+        for k, v in res.items():
+            if isinstance(v, dict) and "ms" in v: print("     %-18s %.3f ms  frac %.3f" % (k, v["ms"], v["frac"]))
+        if "cpu_baseline" in res: print("     cpu", res["cpu_baseline"])
+        continue
     for k, v in res.items():
         if isinstance(v, dict): print("     %-18s %.3f ms  %.3gM elems/s  frac %.3f  %s" % (k, v["ms"], v["elems_per_s"] / 1e6, v["frac"], v.get("kernel", "")))
