@@ -364,11 +364,12 @@ def run_gpu_arm(args):
         del dg, zg, cg
         x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
 
-    # ---- configs[3]: SymmSHE ciphertext multiply + quadratic key switch, ciphertext pairs sharded over the ranks
-    # (SymmSHE.hs:443-449 then :359-372; op sequence of SURVEY.md section 3.5 with TrivGad over the two limbs, l = 2:
-    # 4 CRT, tensor product with mulG, CRTInv, decompose, l CRT, knapsack -- (22 + 4l) x 8nk algorithmic bytes per pair)
+    # ---- configs[3]: SymmSHE ciphertext multiply + quadratic key switch (SymmSHE.hs:443-449 then :359-372; op sequence of
+    # SURVEY.md section 3.5 with TrivGad over the two limbs, l = 2: 4 CRT, tensor product with mulG, CRTInv, decompose,
+    # l CRT, knapsack -- (22 + 4l) x 8nk algorithmic bytes per pair).  Measured on one GPU only: ranks other than 0 have
+    # left by now, and ciphertext pairs shard exactly like the ring elements of the headline step (no collective).
     she_res = None
-    if not args.no_per_op:
+    if not args.no_per_op and world == 1:
         from lol_b200.symmshe import CudaSymmSHE
         del x
         torch.cuda.empty_cache()
@@ -386,20 +387,14 @@ def run_gpu_arm(args):
         l0 = capi.kernel_launch_count()
         she_step()
         she_launches = capi.kernel_launch_count() - l0
-        if world > 1:
-            dist.barrier()
         ms = time_op(torch, she_step, 10)
-        if world > 1:
-            tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
         elem = 8 * she.n * she.k
         alg = (22 + 4 * she.ell) * elem
         she_res = {"workload": f"configs[3]: m=14400, q=(1008001,1065601), TrivGad (l={she.ell}), {Bs} ciphertext pairs per GPU, "
-                               "Pow-basis inputs, in place", "ms": ms, "ct_pairs_per_s": world * Bs / (ms * 1e-3),
+                               "Pow-basis inputs, in place", "ms": ms, "ct_pairs_per_s": Bs / (ms * 1e-3),
                    "algorithmic_bytes_per_pair": alg, "GB/s_per_gpu": alg * Bs / (ms * 1e-3) / 1e9,
                    "frac": alg * Bs / (ms * 1e-3) / 1e9 / peak, "kernel_launches_per_step": int(she_launches)}
-        if world == 1:
+        if True:
             d3 = she.mulCT(cts[:2], cts[2:], basis="crt")
             dg = she.decompose(cts[0])
             steps = {"ct_mul": (lambda: capi.check(she.t.plan.ct_mul(*[c.data_ptr() for c in cts], *[d.data_ptr() for d in d3], Bs, True, stream)), 7),

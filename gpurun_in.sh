@@ -1,3 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "symmshe" 2>&1 | tail -3
-timeout 120 python tools/run_she.py 4096 0 10
-timeout 120 python tools/run_she.py 4096 1024 10
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; echo rc=$?
+tail -3 gpurun_out/bench_2gpu.err
+python tools/bsum.py gpurun_out/bench_2gpu.json | tail -12
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_2gpu_ref.json 2> gpurun_out/bench_2gpu_ref.err; echo rc=$?
+tail -c 600 gpurun_out/bench_2gpu_ref.json
