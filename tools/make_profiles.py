@@ -13,11 +13,13 @@ head = [k for k in agg if 'k_fused_a<' in k and ', 1, 0>(' in k]      # the MUL 
 head_tot = sum(sum(agg[k]) for k in head)
 with open('profiles/r01_launch_list.md', 'w') as f:
     f.write('# Round 1 -- ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e`\n\n')
-    f.write('`ncu --metrics gpu__time_duration.sum --clock-control none -c 600` after the same command exited 0 without ncu\n')
+    f.write('`ncu --metrics gpu__time_duration.sum --clock-control none -c 700` after the same command exited 0 without ncu\n')
     f.write('(cold-cache, serialised: compare shares, not absolutes).  Raw CSV: `profiles/r01_launches.csv`.\n\n')
     f.write('The timed region of the headline step launches only the two `k_fused_a` kernels (CRT, CRTInv), 65536 ring elements each;\n')
     f.write('their shares of the step under ncu: ' + ', '.join(f'{("CRTInv" if "<(bool)1" in k or "<1," in k else "CRT")} {100*sum(agg[k])/head_tot:.1f}%' for k in head) + '\n')
-    f.write('(CUDA events inside bench.py: CRT 0.732 ms, CRTInv 0.760 ms => 49.0% / 51.0%).  The other rows are the `per_op` and\n`other_configs` sections of bench.py and torch RNG / comparison kernels outside the timed region.\n\n')
+    bl = json.loads(open('gpurun_out/bench_r01_final.json').read().strip().splitlines()[-1])['roofline']['ms_per_launch']
+    c, i = bl['tensorCRTRq'], bl['tensorCRTInvRq']
+    f.write(f'(CUDA events inside bench.py, same build: CRT {c:.3f} ms, CRTInv {i:.3f} ms => {100*c/(c+i):.1f}% / {100*i/(c+i):.1f}%).  The other rows are the `per_op` and\n`other_configs` sections of bench.py and torch RNG / comparison kernels outside the timed region.\n\n')
     f.write('| kernel | launches | mean us | total us | share of all |\n|---|---|---|---|---|\n')
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f'| `{k[:120]}` | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.0f} | {100*sum(v)/tot:.1f}% |\n')
