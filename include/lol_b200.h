@@ -196,6 +196,9 @@ int lolb_ctMulRq(const lolb_plan* plan, const hInt_t* a0, const hInt_t* a1, cons
                  hInt_t* d0, hInt_t* d1, hInt_t* d2, int64_t batch, int mul_g, void* stream);
 int lolb_gadgetLength(const lolb_plan* plan, int64_t base);
 int lolb_decomposeRq(const lolb_plan* plan, const hInt_t* x, hInt_t* digits, int64_t batch, int64_t base, void* stream);
+/* digits[d] <- tensorCRTRq(reduce(decompose(x)[d])): lolb_decomposeRq followed by the CRT of every digit (`adviseCRT <$> xs`,
+ * SymmSHE.hs:305), the decomposition folded into the CRT kernel's load stage where that pays (m = 14400, tupSize 2, TrivGad) */
+int lolb_decomposeCrtRq(const lolb_plan* plan, const hInt_t* x, hInt_t* digits, int64_t batch, int64_t base, void* stream);
 int lolb_knapsackRq(const lolb_plan* plan, const hInt_t* digits, int ell, const hInt_t* hints, hInt_t* c0, hInt_t* c1,
                     int64_t batch, void* stream);
 

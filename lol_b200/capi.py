@@ -162,6 +162,9 @@ class PlanRq:
     def decompose(self, x: int, digits: int, batch: int, base: int = 0, stream: int = 0) -> int:
         return int(lib().lolb_decomposeRq(self._h, _p(x), _p(digits), _i64(batch), _i64(base), _p(stream)))
 
+    def decompose_crt(self, x: int, digits: int, batch: int, base: int = 0, stream: int = 0) -> int:
+        return int(lib().lolb_decomposeCrtRq(self._h, _p(x), _p(digits), _i64(batch), _i64(base), _p(stream)))
+
     def knapsack(self, digits: int, ell: int, hints: int, c0: int, c1: int, batch: int, stream: int = 0) -> int:
         return int(lib().lolb_knapsackRq(self._h, _p(digits), C.c_int(ell), _p(hints), _p(c0), _p(c1), _i64(batch), _p(stream)))
 

@@ -330,6 +330,23 @@ extern "C" int lolb_decomposeRq(const lolb_plan* plan, const hInt_t* x, hInt_t* 
   return she_decompose(plan, x, digits, batch, base, (cudaStream_t)stream);
 }
 
+extern "C" int lolb_decomposeCrtRq(const lolb_plan* plan, const hInt_t* x, hInt_t* digits, int64_t batch, int64_t base, void* stream)
+{
+  if (!plan || plan->kind != PLAN_RQ) { set_error(std::string(__func__) + ": wrong or NULL plan"); return LOLB_ERR_ARG; }
+  if (batch < 0) { set_error(std::string(__func__) + ": bad batch"); return LOLB_ERR_ARG; }
+  if (batch > 0 && (!x || !digits || x == digits)) { set_error("lolb_decomposeCrtRq: x and digits must be distinct device arrays"); return LOLB_ERR_ARG; }
+  if (!plan->has_fwd) { set_error("no CRT over this modulus / index (ZqBasic.hs:159-165) or tables not supplied"); return LOLB_ERR_NO_CRT; }
+  int nd[kMaxLimbs], shift = -1;
+  const int ell = she_gadget_digits(plan, base, nd, &shift);
+  if (ell < 0) return LOLB_ERR_ARG;
+  if (!plan->force_generic) {
+    int rc = fused_decompose_crt_rq(plan, x, digits, batch, base, (cudaStream_t)stream);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  int rc = she_decompose(plan, x, digits, batch, base, (cudaStream_t)stream);
+  return rc ? rc : crt_rq(plan, false, digits, batch * ell, stream);
+}
+
 extern "C" int lolb_knapsackRq(const lolb_plan* plan, const hInt_t* digits, int ell, const hInt_t* hints, hInt_t* c0, hInt_t* c1,
                                int64_t batch, void* stream)
 {

@@ -10,6 +10,8 @@ int fused_a_select(lolb_plan* pl, void** slot);
 void fused_a_release(void* slot);
 bool fused_a_available(const void* slot, bool inverse);
 int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_a_decompose_crt(const lolb_plan* pl, const void* slot, const int64_t* x, int64_t* digits, int64_t batch, int64_t base,
+                          cudaStream_t st);
 int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, const int64_t* b, int64_t batch,
                     int64_t b_batch, cudaStream_t st);
 
@@ -104,6 +106,13 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_df_crt(pl, s->pow2_df, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_crt(pl, s->pow2, inverse, y, batch, st);
   return rc;
+}
+
+int fused_decompose_crt_rq(const lolb_plan* pl, const int64_t* x, int64_t* digits, int64_t batch, int64_t base, cudaStream_t st)
+{
+  const FusedSet* s = set_of(pl);
+  if (!s) return LOLB_FUSED_UNAVAILABLE;
+  return fused_a_decompose_crt(pl, s->a, x, digits, batch, base, st);
 }
 
 int fused_crt_mul_rq(const lolb_plan* pl, bool inverse, int64_t* y, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st)

@@ -13,11 +13,13 @@ void fused_release(lolb_plan* pl);
 const char* fused_kernel_name(const lolb_plan* pl, const char* op);
 int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 int fused_crt_mul_rq(const lolb_plan* pl, bool inverse, int64_t* y, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st);
+int fused_decompose_crt_rq(const lolb_plan* pl, const int64_t* x, int64_t* digits, int64_t batch, int64_t base, cudaStream_t st);
 int fused_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cudaStream_t st);
 int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
 int fused_mul_rq(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st);
 // coefficient-wise steps of SymmSHE's ciphertext multiply and key switch (she_stream.cu)
 int she_gadget_length(const lolb_plan* pl, int64_t base);      // -1 on a bad base
+int she_gadget_digits(const lolb_plan* pl, int64_t base, int* nd /* [tupSize] */, int* shift);      // digits per limb; returns l or -1
 int she_ct_mul(const lolb_plan* pl, const int64_t* a0, const int64_t* a1, const int64_t* b0, const int64_t* b1, const int64_t* g,
                int64_t* d0, int64_t* d1, int64_t* d2, int64_t batch, cudaStream_t st);
 int she_decompose(const lolb_plan* pl, const int64_t* x, int64_t* digits, int64_t batch, int64_t base, cudaStream_t st);

@@ -467,7 +467,20 @@ k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 // used) and runs the two limbs as independent instruction streams with their own constants.
 struct FusedAConsts2 { FusedAConsts c[2]; };
 
-template <bool INV, class AR, int WARPS, int MINB, bool MUL = false>
+// DIG mode of k_fused_a_k2 (TrivGad over two limbs, SymmSHE.hs:314 `fmap reduce <$> decompose`; she_stream.cu has the
+// stand-alone pass and the citations): the load stage reads a Pow-basis element and forms digit d of it on the fly, so
+// the CRT of the digits needs no decomposed copy in HBM.  Digit d is lift(x_d) reduced into both limbs: x_d itself in
+// limb d, and in the other limb x_d or x_d - q_d + q_other according to the sign of the lift -- exact while
+// q_other >= q_d / 2 (checked on the host), and three instructions per coefficient.  (A general BaseBGad digit in this
+// compute-bound kernel measured slower than the separate streaming pass.)
+__device__ __forceinline__ uint32_t triv_digit_other(uint32_t x, uint32_t q_own, uint32_t q_other)
+{
+  return (2 * (uint64_t)x < (uint64_t)q_own) ? x : x + (q_other - q_own);      // wraps through 2^32 to [0, q_other)
+}
+
+// DIG (forward only): y = the digit arrays [l * b_stride][n][2] (output), bmul = the Pow-basis source [b_stride][n][2];
+// element e of y is digit e / b_stride of source element e % b_stride.
+template <bool INV, class AR, int WARPS, int MINB, bool MUL = false, bool DIG = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts2 CC,
              const int64_t* __restrict__ bmul, int64_t b_stride)
@@ -486,10 +499,12 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
 
   for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
     longlong2* ebase = reinterpret_cast<longlong2*>(y + (size_t)e * kN * 2);
+    const int dsel = DIG ? (int)(e / b_stride) : 0;
+    const longlong2* sbase = DIG ? reinterpret_cast<const longlong2*>(bmul + (size_t)(e % b_stride) * kN * 2) : ebase;
     // ---------------- phase 1: 5^2 axis, both limbs of column (i2, lane)
     for (int i2 = warp; i2 < kD2; i2 += WARPS) {
       const int col = i2 * 32 + lane;
-      const longlong2* src = ebase + col;
+      const longlong2* src = sbase + col;
       uint32_t v0[20], v1[20];
       uint32_t hi_or = 0, max0 = 0, max1 = 0;
 #pragma unroll
@@ -512,6 +527,13 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
           const longlong2 raw = src[a * 192];
           v0[a] = reduce_any(raw.x, CC.c[0].q);
           v1[a] = reduce_any(raw.y, CC.c[1].q);
+        }
+      }
+      if (DIG) {
+#pragma unroll
+        for (int a = 0; a < 20; a++) {
+          if (dsel == 0) v1[a] = triv_digit_other(v0[a], CC.c[0].q, CC.c[1].q);
+          else v0[a] = triv_digit_other(v1[a], CC.c[1].q, CC.c[0].q);
         }
       }
       if (MUL && INV) {
@@ -949,6 +971,36 @@ int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t
 #undef LM
     if (rc) return rc;
   }
+  return LOLB_OK;
+}
+
+// digits[d] <- CRT(reduce(decompose(x)[d])), d = 0, 1, for TrivGad over two limbs and x in the powerful basis: the
+// decomposition happens in the load stage of the tupSize-2 kernel
+int fused_a_decompose_crt(const lolb_plan* pl, const void* slot, const int64_t* x, int64_t* digits, int64_t batch, int64_t base,
+                          cudaStream_t st)
+{
+  const FusedA* F = (const FusedA*)slot;
+  if (!fused_a_available(slot, false) || pl->k != 2 || F->cls[0] != F->cls[1] || base != 0) return LOLB_FUSED_UNAVAILABLE;
+  if (2 * pl->qs[0] < pl->qs[1] || 2 * pl->qs[1] < pl->qs[0]) return LOLB_FUSED_UNAVAILABLE;      // see triv_digit_other
+  if (batch <= 0) return LOLB_OK;
+  FusedAConsts2 CC;
+  CC.c[0] = F->fwd[0];
+  CC.c[1] = F->fwd[1];
+  const int64_t total = batch * 2;
+  constexpr int W = 3;
+  const size_t smem = 2 * kN * sizeof(uint32_t);
+  if (F->cls[0] == ARITH_M) {
+    int64_t gg = (int64_t)pl->num_sms * 4;
+    if (gg > total) gg = total;
+    k_fused_a_k2<false, ArithM, W, 4, false, true><<<(int)gg, W * 32, smem, st>>>(digits, total, CC, x, batch);
+  } else {
+    int64_t gg = (int64_t)pl->num_sms * 5;
+    if (gg > total) gg = total;
+    k_fused_a_k2<false, ArithS, W, 5, false, true><<<(int)gg, W * 32, smem, st>>>(digits, total, CC, x, batch);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_k2<DIG>");
+  count_launch();
   return LOLB_OK;
 }
 

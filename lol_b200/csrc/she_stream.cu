@@ -370,6 +370,15 @@ int she_gadget_length(const lolb_plan* pl, int64_t base)
   return G.ell;
 }
 
+int she_gadget_digits(const lolb_plan* pl, int64_t base, int* nd, int* shift)
+{
+  GadgetGeom G;
+  if (gadget_geom(pl, base, &G)) return -1;
+  for (int l = 0; l < pl->k; l++) nd[l] = G.digits[l];
+  *shift = G.shift;
+  return G.ell;
+}
+
 int she_ct_mul(const lolb_plan* pl, const int64_t* a0, const int64_t* a1, const int64_t* b0, const int64_t* b1,
                const int64_t* g, int64_t* d0, int64_t* d1, int64_t* d2, int64_t batch, cudaStream_t st)
 {

@@ -65,6 +65,14 @@ class CudaSymmSHE:
         capi.check(self.t.plan.decompose(x.data_ptr(), digits.data_ptr(), b, self.gad_base, _stream()))
         return digits
 
+    def decomposeCRT(self, x):
+        """`adviseCRT <$> (fmap reduce <$> decompose x)` (SymmSHE.hs:305, :314): the gadget digits of a Pow-basis x, each
+        in the CRT basis, [ell, batch, n, k]; one kernel where the CRT's load stage can form the digits itself."""
+        b = _require_cuda(x, torch.int64, self.n, self.k)
+        digits = torch.empty(self.ell, b, self.n, self.k, dtype=torch.int64, device=x.device)
+        capi.check(self.t.plan.decompose_crt(x.data_ptr(), digits.data_ptr(), b, self.gad_base, _stream()))
+        return digits
+
     def knapsack(self, hint, digits, c0, c1, inplace: bool = False):
         """[c0, c1] + sum_i digits[i] *>> hint[i]  (SymmSHE.hs:302-305, :372).  `hint` is [ell, 2, n, k] in the CRT
         basis (the linear polynomials of `ksHint`, :288-298), `digits` [ell, batch, n, k] in the CRT basis."""
@@ -81,15 +89,14 @@ class CudaSymmSHE:
 
     def keySwitchQuadCirc(self, hint, ct, inplace: bool = False):
         """Degree-2 ciphertext [c0, c1, c2] (CRT basis) -> degree 1 under the same key (SymmSHE.hs:359-372):
-        c2 to the powerful basis (tensorCRTInvRq), gadget digits, each digit back to CRT (one batched tensorCRTRq
+        c2 to the powerful basis (tensorCRTInvRq), gadget digits each taken back to CRT (lolb_decomposeCrtRq: one launch
         over all ell * batch digits), knapsack with the hint."""
         if len(ct) != 3:
             raise capi.LolB200Error(capi.LOLB_ERR_ARG, "keySwitchQuadCirc takes a ciphertext with three coefficients")
         c0, c1, c2 = ct
         b = _require_cuda(c2, torch.int64, self.n, self.k)
         p = self.t.crtInv(c2, inplace=inplace)
-        digits = self.decompose(p)
-        self.t.crt(digits.view(self.ell * b, self.n, self.k), inplace=True)
+        digits = self.decomposeCRT(p)
         return self.knapsack(hint, digits, c0, c1, inplace=inplace)
 
     def mulAndSwitch(self, c1, c2, hint, basis: str = "pow", inplace: bool = False):

@@ -561,7 +561,8 @@ def _hint(rng, ell, n, qs):
     return np.stack([np.stack([zq_input(rng, n, qs) for _ in range(2)]) for _ in range(ell)])
 
 
-@pytest.mark.parametrize("m,qs,base", [(14400, [1008001, 1065601], 0), (14400, [1008001, 1065601], 1000), (21, [43, 127, 379], 0),
+@pytest.mark.parametrize("m,qs,base", [(14400, [1008001, 1065601], 0), (14400, [1008001, 1065601], 1000), (14400, [1008001, 1065601], 2),
+                                       (14400, [14401, 429336001], 1024), (14400, [14401, 14401], 0), (14400, [14401, 429336001], 0), (14400, [1065601, 1008001], 0), (21, [43, 127, 379], 0),
                                        (21, [43, 127, 379], 2), (2, [13, 17, 19], 3), (45, [2148249601], 65536), (16, [97], 0)],
                          ids=lambda v: str(v))
 def test_symmshe_steps_match_oracle(torch_cuda, oracle, m, qs, base):
@@ -587,6 +588,12 @@ def test_symmshe_steps_match_oracle(torch_cuda, oracle, m, qs, base):
     # gadget digits of a Pow-basis element
     digits = she.decompose(dev[0])
     assert np.array_equal(digits.cpu().numpy(), S.decompose_reduced(cts[0], qs, base))
+    # digits taken to the CRT basis in one call (decomposition inside the CRT kernel's load stage at m = 14400, tupSize 2, TrivGad)
+    dc = she.decomposeCRT(dev[0])
+    assert torch.equal(dc, she.t.crt(digits.view(she.ell * B, n, len(qs))).view(she.ell, B, n, len(qs)))
+    she.t.plan.force_generic(True)
+    assert torch.equal(she.decomposeCRT(dev[0]), dc)
+    she.t.plan.force_generic(False)
     # knapsack
     hint = _hint(rng, she.ell, n, qs)
     hint_d = torch.from_numpy(hint).cuda()
