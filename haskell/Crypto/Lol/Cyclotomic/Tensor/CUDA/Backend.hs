@@ -15,6 +15,8 @@ adds what the C++ back end never had -- a plan handle and whole-batch calls.
 module Crypto.Lol.Cyclotomic.Tensor.CUDA.Backend
 ( Plan, withPlanRq, applyHostRq
 , lolbDeviceAvailable, lolbLastError
+  -- * device-resident SymmSHE steps (raw imports; operands are device addresses)
+, DevPtr, c_crtRq, c_crtInvRq, c_ctMulRq, c_gadgetLength, c_decomposeRq, c_decomposeCrtRq, c_knapsackRq
 ) where
 
 import Control.Exception      (bracket, throwIO, ErrorCall (..))
@@ -40,6 +42,26 @@ foreign import ccall unsafe "lolb_plan_create_rq" c_planCreateRq ::
 foreign import ccall unsafe "&lolb_plan_destroy" p_planDestroy :: FunPtr (Ptr PlanStruct -> IO ())
 foreign import ccall unsafe "lolb_rq_apply_host" c_applyHostRq ::
   Ptr PlanStruct -> CString -> Ptr Int64 -> Int64 -> IO Int32
+-- | Device-resident batches ([batch][n][tupSize] Int64 in GPU memory; allocation is the caller's, e.g. cudaMalloc).
+-- The SymmSHE steps between the CRTs (lol-apps SymmSHE.hs:302-314, 359-372, 443-449) on such batches:
+type DevPtr a = Ptr a
+foreign import ccall unsafe "lolb_tensorCRTRq" c_crtRq :: Ptr PlanStruct -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+foreign import ccall unsafe "lolb_tensorCRTInvRq" c_crtInvRq :: Ptr PlanStruct -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+-- (d0,d1,d2) <- mulG <$> [a0,a1] * [b0,b1]
+foreign import ccall unsafe "lolb_ctMulRq" c_ctMulRq ::
+  Ptr PlanStruct -> DevPtr Int64 -> DevPtr Int64 -> DevPtr Int64 -> DevPtr Int64
+  -> DevPtr Int64 -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Int32 -> Ptr () -> IO Int32
+-- number of gadget digits; base 0 = TrivGad, b >= 2 = BaseBGad b
+foreign import ccall unsafe "lolb_gadgetLength" c_gadgetLength :: Ptr PlanStruct -> Int64 -> IO Int32
+-- digits <- fmap reduce <$> decompose x          (x in the powerful basis)
+foreign import ccall unsafe "lolb_decomposeRq" c_decomposeRq ::
+  Ptr PlanStruct -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Int64 -> Ptr () -> IO Int32
+-- digits <- adviseCRT <$> (fmap reduce <$> decompose x)
+foreign import ccall unsafe "lolb_decomposeCrtRq" c_decomposeCrtRq ::
+  Ptr PlanStruct -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Int64 -> Ptr () -> IO Int32
+-- [c0,c1] += knapsack hint digits
+foreign import ccall unsafe "lolb_knapsackRq" c_knapsackRq ::
+  Ptr PlanStruct -> DevPtr Int64 -> Int32 -> DevPtr Int64 -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
 foreign import ccall unsafe "lolb_last_error" c_lastError :: IO CString
 foreign import ccall unsafe "lolb_device_available" c_deviceAvailable :: IO Int32
 
