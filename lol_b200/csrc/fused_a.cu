@@ -480,21 +480,30 @@ __device__ __forceinline__ uint32_t triv_digit_other(uint32_t x, uint32_t q_own,
 
 // DIG (forward only): y = the digit arrays [l * b_stride][n][2] (output), bmul = the Pow-basis source [b_stride][n][2];
 // element e of y is digit e / b_stride of source element e % b_stride.
-template <bool INV, class AR, int WARPS, int MINB, bool MUL = false, bool DIG = false>
+// LSM: the per-lane constants of phase 2 live in shared memory and are read at the start of every phase-2 task, instead
+// of sitting in 2 x 16 registers through phase 1 (where the 40-value column and its loads in flight set the peak).
+template <bool INV, class AR, int WARPS, int MINB, bool MUL = false, bool DIG = false, bool LSM = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts2 CC,
              const int64_t* __restrict__ bmul, int64_t b_stride)
 {
-  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN]
+  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN] (+ [2][kLaneRows][32] with LSM)
   const AR A0(CC.c[0]), A1(CC.c[1]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t ltw[2][9], m3l[2][12];
+  uint32_t* lt_s = sm_dyn + 2 * kN;
+  if (LSM) {
+    for (int i = threadIdx.x; i < 2 * kLaneRows * 32; i += WARPS * 32)
+      lt_s[i] = CC.c[i / (kLaneRows * 32)].lane_tw[i % (kLaneRows * 32)];
+    __syncthreads();
+  } else {
 #pragma unroll
-  for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < 2; l++) {
 #pragma unroll
-    for (int i = 0; i < 9; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
+      for (int i = 0; i < 9; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
 #pragma unroll
-    for (int i = 0; i < 12; i++) m3l[l][i] = CC.c[l].lane_tw[(8 + i) * 32 + lane];
+      for (int i = 0; i < 12; i++) m3l[l][i] = CC.c[l].lane_tw[(8 + i) * 32 + lane];
+    }
   }
 
   for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
@@ -563,6 +572,15 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
     // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp, both limbs of row block i3
     for (int i3 = warp; i3 < kD3; i3 += WARPS) {
       uint32_t x[2][6], c0[2][3], c1[2][3];
+      if (LSM) {
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+#pragma unroll
+          for (int i = 0; i < 9; i++) ltw[l][i] = lt_s[(l * kLaneRows + i) * 32 + lane];
+#pragma unroll
+          for (int i = 0; i < 12; i++) m3l[l][i] = lt_s[(l * kLaneRows + 8 + i) * 32 + lane];
+        }
+      }
 #pragma unroll
       for (int l = 0; l < 2; l++)
 #pragma unroll
@@ -1032,7 +1050,19 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
         if (inverse) k_fused_a_k2<true, ArithM, W, MBV><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);   \
         else k_fused_a_k2<false, ArithM, W, MBV><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);          \
       } while (0)
-      if (mbv == 3) K2M(3); else if (mbv == 5) K2M(5); else K2M(4);
+      if (mbv == 3) K2M(3); else if (mbv == 5) K2M(5); else if (mbv == 4) K2M(4);
+      else {      // 15/14/16: per-lane constants in shared memory (LSM), 5 / 4 / 6 CTAs per SM
+        const size_t smem_l = smem + 2 * kLaneRows * 32 * sizeof(uint32_t);
+#define K2L(MBV)                                                                                                                  \
+        do {                                                                                                                        \
+          int64_t gg = (int64_t)pl->num_sms * MBV;                                                                                  \
+          if (gg > batch) gg = batch;                                                                                               \
+          if (inverse) k_fused_a_k2<true, ArithM, W, MBV, false, false, true><<<(int)gg, W * 32, smem_l, st>>>(y, batch, CC, nullptr, 0);   \
+          else k_fused_a_k2<false, ArithM, W, MBV, false, false, true><<<(int)gg, W * 32, smem_l, st>>>(y, batch, CC, nullptr, 0);          \
+        } while (0)
+        if (mbv == 14) K2L(4); else if (mbv == 16) K2L(6); else K2L(5);
+#undef K2L
+      }
 #undef K2M
     } else {
       if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
