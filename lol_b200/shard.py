@@ -60,3 +60,15 @@ def gather_batch(local: torch.Tensor, batch: int, dst: int = 0, group=None) -> t
         lo, hi = shard_bounds(batch, world, r)
         parts.append(bufs[r][: hi - lo])
     return torch.cat(parts, dim=0)
+
+
+def broadcast_replicated(t: torch.Tensor | None, shape: tuple[int, ...], dtype: torch.dtype, device, src: int = 0,
+                         group=None) -> torch.Tensor:
+    """Per-(m, qs) data every rank needs whole -- key-switch hints (SymmSHE.hs:288-298), gCRT vectors: rank `src`
+    holds `t`, every rank returns a copy.  KBs to a few MBs, once per key, outside any timed region."""
+    rank = dist.get_rank(group)
+    buf = t.to(device).contiguous() if rank == src else torch.empty(shape, dtype=dtype, device=device)
+    if rank == src:
+        assert tuple(buf.shape) == tuple(shape) and buf.dtype == dtype
+    dist.broadcast(buf, src=src, group=group)
+    return buf

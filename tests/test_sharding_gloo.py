@@ -71,3 +71,45 @@ def test_scatter_transform_gather_world2(tmp_path, batch):
     result = tmp_path / "result.txt"
     mp.spawn(_worker, args=(2, _free_port(), batch, str(result)), nprocs=2, join=True)
     assert result.read_text() == "ok"
+
+
+# ------------------------------------------------------------------ configs[3]: ciphertext pairs sharded, hints replicated
+def _she_worker(rank, world, port, batch, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lol_b200.shard import broadcast_replicated
+        from oracle import cpu, symmshe as S, tables as T
+        m, qs, base = 21, [43, 127], 4
+        pe, n = T.pe_array(m), T.totient_pps(T.factor_pps(m))
+        tabs = (pe, T.ru_tables_zq(m, qs), T.ru_tables_zq(m, qs, inverse=True), [T.mhat_inv(m, q) for q in qs], T.g_crt_vectors(m, qs)[0])
+        ell = S.gadget_length(qs, base)
+        O = cpu.restatement()
+        comps, hint = [None] * 4, None
+        if rank == 0:
+            rng = np.random.default_rng(11)
+            mk = lambda *shape: torch.from_numpy(np.stack([rng.integers(0, q, size=shape) for q in qs], axis=-1).astype(np.int64))
+            comps = [mk(batch, n) for _ in range(4)]
+            hint = mk(ell, 2, n)
+        local = [scatter_batch(c, batch, (n, len(qs)), torch.int64, "cpu") for c in comps]
+        hint_l = broadcast_replicated(hint, (ell, 2, n, len(qs)), torch.int64, "cpu").numpy()
+        run = lambda a0, a1, b0, b1: S.mul_and_switch(O, [a0, a1], [b0, b1], hint_l, tabs, qs, base)
+        outs = [run(*[c[b].numpy() for c in local]) for b in range(local[0].shape[0])]
+        empty = np.zeros((0, n, len(qs)), dtype=np.int64)
+        got = [gather_batch(torch.from_numpy(np.stack([o[j] for o in outs]) if outs else empty), batch) for j in range(2)]
+        if rank == 0:
+            want = [run(*[c[b].numpy() for c in comps]) for b in range(batch)]
+            ok = all(np.array_equal(got[j].numpy(), np.stack([w[j] for w in want])) for j in range(2))
+            with open(result_path, "w") as f:
+                f.write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [3, 4])
+def test_symmshe_pairs_sharded_hints_replicated_world2(tmp_path, batch):
+    """keySwitchQuadCirc hint (c1 * c2) per ciphertext pair shards by pair with the hint replicated:
+    scatter -> per-rank pipeline -> gather equals the single-rank result."""
+    result = tmp_path / "result.txt"
+    mp.spawn(_she_worker, args=(2, _free_port(), batch, str(result)), nprocs=2, join=True)
+    assert result.read_text() == "ok"
