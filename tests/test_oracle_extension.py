@@ -1,0 +1,128 @@
+"""CPU suite: pin oracle/extension.py (the ring-extension index tables and operators, Haskell in the reference)
+through the reference's own two-index properties (lol/Crypto/Lol/Tests/TensorTests.hs:133-215), with the COMPILED
+reference supplying crt / crtInv / l / lInv / divG, over the reference's two-index parameter list
+(lol/Crypto/Lol/Tests/Default.hs:65-77) plus the ring-switching pairs below m = 14400."""
+import numpy as np
+import pytest
+
+from conftest import zq_input
+from oracle import extension as X
+from oracle import tables as T
+
+# (m, m', qs): Tests/Default.hs:65-77, then pairs under BASELINE's m = 14400 and a mixed odd pair
+TWO_INDEX_PARAMS = [
+    (1, 7, [29]), (4, 12, [536871001]), (4, 12, [2148249601]), (2, 8, [17]), (8, 8, [17]), (2, 8, [2148249601]),
+    (4, 8, [17]), (3, 21, [8191]), (7, 21, [8191]), (3, 42, [8191]), (3, 21, [18869761]),
+    (7, 21, [19393921, 18869761]), (3, 42, [19918081, 19393921, 18869761]),
+    (45, 225, [14401]), (64, 14400 // 25, [14401]), (75, 14400 // 64, [1008001, 1065601]), (15, 105, [2311]),
+]
+IDS = [f"m{m}_m{m2}_k{len(qs)}" for m, m2, qs in TWO_INDEX_PARAMS]
+
+
+class Ring:
+    """The reference's single-index operators over Z_q for one index (compiled lol-cpp through ctypes)."""
+
+    def __init__(self, lib, m, qs):
+        self.lib, self.m, self.qs = lib, m, qs
+        self.pe = T.pe_array(m)
+        self.n = T.totient_pps(T.factor_pps(m))
+        self.ru, self.rui = T.ru_tables_zq(m, qs), T.ru_tables_zq(m, qs, inverse=True)
+        self.mh = [T.mhat_inv(m, q) for q in qs]
+
+    def crt(self, x): return self.lib.tensorCRTRq(x, self.pe, self.ru, self.qs).reshape(x.shape)
+    def crt_inv(self, x): return self.lib.tensorCRTInvRq(x, self.pe, self.rui, self.mh, self.qs).reshape(x.shape)
+    def l(self, x): return self.lib.tensorLRq(x, self.pe, self.qs).reshape(x.shape)
+    def l_inv(self, x): return self.lib.tensorLInvRq(x, self.pe, self.qs).reshape(x.shape)
+
+    def scalar_pow(self, r):
+        x = np.zeros((self.n, len(self.qs)), dtype=np.int64)
+        x[0] = [r % q for q in self.qs]
+        return x
+
+    def div_g(self, name, x):
+        y, ok = getattr(self.lib, name)(x, self.pe, self.qs)
+        assert ok == 1
+        return y.reshape(x.shape)
+
+
+@pytest.mark.parametrize("m,m2,qs", TWO_INDEX_PARAMS, ids=IDS)
+def test_index_tables_are_consistent(m, m2, qs):
+    info = X.ExtInfo(m, m2)
+    # toIndexPair / fromIndexPair are inverse bijections [phi'] <-> [phi'/phi] x [phi]
+    for j in range(info.phi2):
+        assert X.from_index_pair(info.tots, X.to_index_pair(info.tots, j)) == j
+    assert sorted(info.ext_crt.tolist()) == list(range(info.phi2))
+    assert sorted(info.ext_coeffs.reshape(-1).tolist()) == list(range(info.phi2))
+    assert np.array_equal(info.ext_coeffs[0], info.ext_powdec)
+    # every base index is hit exactly once with j0 == 0 (embedPow is injective onto the j0 = 0 slots)
+    assert sorted(info.base_pow_j1[info.base_pow_j0 == 0].tolist()) == list(range(info.phi))
+
+
+@pytest.mark.parametrize("m,m2,qs", TWO_INDEX_PARAMS, ids=IDS)
+def test_twace_embed_identities(reference, m, m2, qs):
+    """prop_trem_pow, prop_trem_dec, prop_twace_dec, prop_twEmID."""
+    rng = np.random.default_rng(m * 1000 + m2)
+    info = X.ExtInfo(m, m2)
+    lo, hi = Ring(reference, m, qs), Ring(reference, m2, qs)
+    x = zq_input(rng, info.phi, qs)
+    assert np.array_equal(X.twace_powdec(info, X.embed_pow(info, x)), x)
+    assert np.array_equal(X.twace_powdec(info, X.embed_dec(info, x, qs)), x)
+    y = zq_input(rng, info.phi2, qs)
+    assert np.array_equal(X.twace_powdec(info, y), lo.l_inv(X.twace_powdec(info, hi.l(y))))
+    # embedDec == lInv . embedPow . l  (both express the same ring element)
+    assert np.array_equal(X.embed_dec(info, x, qs), hi.l_inv(X.embed_pow(info, lo.l(x))))
+    same = X.ExtInfo(m2, m2)
+    assert np.array_equal(X.twace_powdec(same, y), y)
+    assert np.array_equal(X.embed_pow(same, y), y)
+    assert np.array_equal(X.embed_dec(same, y, qs), y)
+    assert np.array_equal(X.embed_crt(same, y), y)
+    assert np.array_equal(X.twace_crt_zq(same, y, qs), y)
+
+
+@pytest.mark.parametrize("m,m2,qs", TWO_INDEX_PARAMS, ids=IDS)
+def test_crt_basis_operators_against_compiled_reference_crt(reference, m, m2, qs):
+    """prop_embed_crt: embedCRT = crt . embedPow . crtInv;  prop_twace_crt: twaceCRT = crt . twacePowDec . crtInv."""
+    rng = np.random.default_rng(m * 977 + m2)
+    info = X.ExtInfo(m, m2)
+    lo, hi = Ring(reference, m, qs), Ring(reference, m2, qs)
+    x = zq_input(rng, info.phi, qs)
+    assert np.array_equal(X.embed_crt(info, x), hi.crt(X.embed_pow(info, lo.crt_inv(x))))
+    y = zq_input(rng, info.phi2, qs)
+    assert np.array_equal(X.twace_crt_zq(info, y, qs), lo.crt(X.twace_powdec(info, hi.crt_inv(y))))
+
+
+@pytest.mark.parametrize("m,m2,qs", TWO_INDEX_PARAMS, ids=IDS)
+def test_twace_invariants(reference, m, m2, qs):
+    """prop_twace_invar1_{pow,dec,crt}: twace(mhat'/g') = mhat (phi'/phi) / g;  prop_twace_invar2: scalars are kept."""
+    if any(np.gcd(T.odd_radical(m2), q) != 1 for q in qs):
+        pytest.skip("g not invertible")
+    info = X.ExtInfo(m, m2)
+    lo, hi = Ring(reference, m, qs), Ring(reference, m2, qs)
+    mhat, mhat2 = T.value_hat(m), T.value_hat(m2)
+    out_s, in_s = lo.scalar_pow(mhat * info.rel), hi.scalar_pow(mhat2)
+    assert np.array_equal(X.twace_powdec(info, hi.div_g("tensorGInvPowRq", in_s)), lo.div_g("tensorGInvPowRq", out_s))
+    assert np.array_equal(X.twace_powdec(info, hi.div_g("tensorGInvDecRq", hi.l_inv(in_s))),
+                          lo.div_g("tensorGInvDecRq", lo.l_inv(out_s)))
+    _, gi_lo = T.g_crt_vectors(m, qs)
+    _, gi_hi = T.g_crt_vectors(m2, qs)
+    q = np.asarray(qs, dtype=object)
+    crt_in = (hi.crt(in_s).astype(object) * gi_hi.astype(object) % q).astype(np.int64)
+    crt_out = (lo.crt(out_s).astype(object) * gi_lo.astype(object) % q).astype(np.int64)
+    assert np.array_equal(X.twace_crt_zq(info, crt_in, qs), crt_out)
+    assert np.array_equal(X.twace_powdec(info, hi.scalar_pow(1)), lo.scalar_pow(1))
+    assert np.array_equal(X.twace_crt_zq(info, hi.crt(hi.scalar_pow(1)), qs), lo.crt(lo.scalar_pow(1)))
+
+
+@pytest.mark.parametrize("m,m2", [(3, 21), (4, 12), (45, 225), (1, 7)])
+def test_coeffs_reassembles_through_the_powerful_basis(m, m2):
+    """coeffs' splits an O_m' element into phi'/phi O_m elements; placing them back by extIndicesCoeffs is the identity,
+    and coefficient 0 is twacePowDec (Extension.hs:90-103)."""
+    rng = np.random.default_rng(5)
+    info = X.ExtInfo(m, m2)
+    y = rng.integers(-50, 50, size=(info.phi2, 1))
+    c = X.coeffs_powdec(info, y)
+    assert c.shape == (info.rel, info.phi, 1)
+    back = np.empty_like(y)
+    back[info.ext_coeffs.reshape(-1)] = c.reshape(-1, 1)
+    assert np.array_equal(back, y)
+    assert np.array_equal(c[0], X.twace_powdec(info, y))
