@@ -228,6 +228,52 @@ int lolb_tensorNormSqR(const lolb_plan* plan, const hInt_t* y, hInt_t* out, int6
 int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double* out, int64_t batch, void* stream);
 
 /*
+ * Ring extensions O_m'/O_m, m | m': the two-index methods of `class Tensor` (embedPow, embedDec, embedCRT, twacePowDec,
+ * twaceCRT, coeffs; lol/Crypto/Lol/Cyclotomic/Tensor.hs:160-190).  The reference runs them on the host in Haskell over
+ * index vectors (lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Extension.hs:54-129; tables Tensor.hs:380-510); here the tables
+ * of one (m, m') pair live on the device and each operator is one gather pass over a device-resident batch.
+ * An extension is created from the plans of O_m (`lo`) and O_m' (`hi`), which must be over the same ring (both Rq with
+ * equal tupSize and moduli, or both modulus-free with equal tupSize) and must outlive it.  `ring` selects the coefficient
+ * type of the call: LOLB_RING_RQ for Rq plans; LOLB_RING_R (int64), _DOUBLE or _C (complex) for modulus-free plans.
+ * Operands are DEVICE pointers, distinct, `x` with `batch` elements of the source ring and `y` of the target ring:
+ *   lolb_twacePowDec  O_m' -> O_m   y[i]  = x[extIndicesPowDec[i]]                       Extension.hs:99-103
+ *   lolb_embedPow     O_m  -> O_m'  y[i'] = j0(i') == 0 ? x[j1(i')] : 0                  Extension.hs:60-70
+ *   lolb_embedDec     O_m  -> O_m'  y[i'] = 0 | x[sh] | -x[sh] per baseIndicesDec        Extension.hs:71-77
+ *   lolb_embedCRT     O_m  -> O_m'  y[i'] = x[baseIndicesCRT[i']]                        Extension.hs:81-85
+ *   lolb_coeffsPowDec O_m' -> (O_m)^(phi'/phi), y laid out [batch][phi'/phi][phi][k]     Extension.hs:90-93
+ *   lolb_twaceCRT     O_m' -> O_m   y[i]  = sum of the phi'/phi entries of tweak . x lying above i, tweak =
+ *                                   m'hat^-1 mhat embedCRT(gInvCRT_m) gCRT_m'            Extension.hs:110-129
+ * embedCRT / twaceCRT return LOLB_ERR_NO_CRT where the reference's `CRTrans` yields Nothing (no CRT of index m' over the
+ * moduli) and for the R / Double rings.
+ */
+typedef struct lolb_ext lolb_ext;
+#define LOLB_RING_RQ     0
+#define LOLB_RING_R      1
+#define LOLB_RING_DOUBLE 2
+#define LOLB_RING_C      3
+int lolb_ext_create(lolb_ext** out, const lolb_plan* lo, const lolb_plan* hi);
+void lolb_ext_destroy(lolb_ext* ext);
+int32_t lolb_ext_totient(const lolb_ext* ext, int upper);   /* phi(m), or phi(m') when upper != 0 */
+/* copy an index table out (host int32 buffer), for cross-checking against Tensor.hs:429-478 */
+#define LOLB_EXT_INDICES_POWDEC 0   /* extIndicesPowDec  [phi]  */
+#define LOLB_EXT_INDICES_CRT    1   /* extIndicesCRT     [phi'] */
+#define LOLB_EXT_BASE_POW_J0    2   /* fst <$> baseIndicesPow [phi'] */
+#define LOLB_EXT_BASE_POW_J1    3   /* snd <$> baseIndicesPow = baseIndicesCRT [phi'] */
+#define LOLB_EXT_BASE_DEC       4   /* baseIndicesDec [phi']: -1 = Nothing, else 2 * index + (negate ? 1 : 0) */
+#define LOLB_EXT_INDICES_COEFFS 5   /* extIndicesCoeffs [phi'/phi][phi] */
+#define LOLB_EXT_TABLES         6
+int lolb_ext_get_table(const lolb_ext* ext, int which, int32_t* out);
+/* the same tables computed on the host from the two prime-power lists alone (no device, no plans): returns the entry
+ * count and fills `out` when it is not NULL; -1 on a bad argument or when m does not divide m' */
+int64_t lolb_ext_index_table(const PrimeExponent* pe, hShort_t nPE, const PrimeExponent* pe2, hShort_t nPE2, int which, int32_t* out);
+int lolb_twacePowDec(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+int lolb_embedPow(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+int lolb_embedDec(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+int lolb_embedCRT(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+int lolb_coeffsPowDec(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+int lolb_twaceCRT(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+
+/*
  * Host-buffer batched calls (what an FFI caller with Haskell-owned vectors
  * uses): `y` is a HOST pointer to batch elements; the call pipelines
  * host->device copy, kernel(s) and device->host copy over chunks on internal

@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
         _lib.lolb_host_alloc.restype = _p
         _lib.lolb_host_alloc.argtypes = [C.c_uint64]
         _lib.lolb_host_free.argtypes = [_p]
+        _lib.lolb_ext_index_table.restype = _i64
+        _lib.lolb_ext_totient.restype = _i32
     return _lib
 
 
@@ -216,6 +218,52 @@ class PlanC:
 
     def mul(self, a_ptr: int, b_ptr: int, batch: int, b_batch: int, stream: int = 0) -> int:
         return int(lib().lolb_mulC(self._h, _p(a_ptr), _p(b_ptr), _i64(batch), _i64(b_batch), _p(stream)))
+
+
+# ------------------------------------------------------------------ ring extensions O_m'/O_m (lolb_ext_*)
+RING_RQ, RING_R, RING_DOUBLE, RING_C = 0, 1, 2, 3
+EXT_INDICES_POWDEC, EXT_INDICES_CRT, EXT_BASE_POW_J0, EXT_BASE_POW_J1, EXT_BASE_DEC, EXT_INDICES_COEFFS = range(6)
+
+
+def ext_index_table(pps, pps2, which: int) -> np.ndarray:
+    """lolb_ext_index_table: one table of Tensor.hs:429-478 computed on the host (needs no GPU)."""
+    pe, pe2 = pe_array(pps), pe_array(pps2)
+    args = (pe.ctypes.data_as(_p), _i16(len(pe)), pe2.ctypes.data_as(_p), _i16(len(pe2)), C.c_int(which))
+    count = int(lib().lolb_ext_index_table(*args, None))
+    if count < 0:
+        raise LolB200Error(LOLB_ERR_ARG, last_error())
+    out = np.empty(count, dtype=np.int32)
+    lib().lolb_ext_index_table(*args, out.ctypes.data_as(_p))
+    return out
+
+
+class Extension:
+    """lolb_ext over the plans of O_m (`lo`) and O_m' (`hi`); the plans are kept alive by this object."""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
+        self._h = _p()
+        check(lib().lolb_ext_create(C.byref(self._h), lo.handle, hi.handle))
+        self.phi = int(lib().lolb_ext_totient(self._h, 0))
+        self.phi2 = int(lib().lolb_ext_totient(self._h, 1))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().lolb_ext_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def table(self, which: int) -> np.ndarray:
+        out = np.empty(self.phi if which == EXT_INDICES_POWDEC else self.phi2, dtype=np.int32)
+        check(lib().lolb_ext_get_table(self._h, C.c_int(which), out.ctypes.data_as(_p)))
+        return out
+
+    def op(self, name: str, ring: int, x_ptr: int, y_ptr: int, batch: int, stream: int = 0) -> int:
+        """name: 'twacePowDec', 'embedPow', 'embedDec', 'embedCRT', 'coeffsPowDec', 'twaceCRT'."""
+        f = getattr(lib(), "lolb_" + name)
+        return int(f(self._h, C.c_int(ring), _p(x_ptr), _p(y_ptr), _i64(batch), _p(stream)))
 
 
 # ------------------------------------------------------------------ drop-in symbols over numpy (host pointers)

@@ -126,3 +126,27 @@ def test_coeffs_reassembles_through_the_powerful_basis(m, m2):
     back[info.ext_coeffs.reshape(-1)] = c.reshape(-1, 1)
     assert np.array_equal(back, y)
     assert np.array_equal(c[0], X.twace_powdec(info, y))
+
+
+@pytest.mark.parametrize("m,m2", [(m, m2) for m, m2, _ in TWO_INDEX_PARAMS] + [(225, 14400), (576, 14400), (1, 14400), (1024, 65536)],
+                         ids=lambda v: str(v))
+def test_library_host_index_tables_match_oracle(m, m2):
+    """lolb_ext_index_table (host-only entry of libctensor_b200, ext_stream.cu: the tables the kernels gather through)
+    against the restatement of Tensor.hs:391-498 -- no GPU involved."""
+    from lol_b200 import build_library, capi
+    build_library()
+    info = X.ExtInfo(m, m2)
+    pps, pps2 = T.factor_pps(m), T.factor_pps(m2)
+    dec = np.where(info.base_dec_idx < 0, -1, info.base_dec_idx * 2 + info.base_dec_neg)
+    for which, want in ((capi.EXT_INDICES_POWDEC, info.ext_powdec), (capi.EXT_INDICES_CRT, info.ext_crt),
+                        (capi.EXT_BASE_POW_J0, info.base_pow_j0), (capi.EXT_BASE_POW_J1, info.base_pow_j1),
+                        (capi.EXT_BASE_DEC, dec), (capi.EXT_INDICES_COEFFS, info.ext_coeffs.reshape(-1))):
+        assert np.array_equal(capi.ext_index_table(pps, pps2, which), want), which
+
+
+def test_library_host_index_tables_reject_non_divisors():
+    from lol_b200 import build_library, capi
+    build_library()
+    for m, m2 in ((4, 6), (9, 3), (5, 12)):
+        with pytest.raises(capi.LolB200Error):
+            capi.ext_index_table(T.factor_pps(m), T.factor_pps(m2), capi.EXT_INDICES_POWDEC)
