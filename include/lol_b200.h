@@ -274,6 +274,27 @@ int lolb_coeffsPowDec(const lolb_ext* ext, int ring, const void* x, void* y, int
 int lolb_twaceCRT(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
 
 /*
+ * Coefficient-wise maps either side of the transforms when Lol switches moduli or rounds an error term; host `fmapT`
+ * closures in the reference (lol/Crypto/Lol/Cyclotomic/UCyc.hs:267-300, 427-445), one streaming pass each here.
+ * Device pointers, [batch][totm][tupSize] layout, Rq plans.
+ *   lolb_liftRq        y = lift x per limb: representative in [-q/2, q/2) (decode', ZqBasic.hs:92-94; UCyc.hs:288-296)
+ *   lolb_reduceRq      y[.][t] = z mod q_t; z has z_tupsize = 1 (one integer per coefficient, reduced into every limb) or
+ *                      tupSize int64 per coefficient (reduce', ZqBasic.hs:88-90; UCyc.hs:267-275)
+ *   lolb_rescaleDropRq removes limb `drop` of the product ring: y_t = q_d^-1 (x_t - reduce(lift x_d)), t != d, y is
+ *                      [batch][totm][tupSize-1] (Prelude.hs:226-232 drop = 0, :259-265 drop = tupSize-1; rescalePow,
+ *                      UCyc.hs:298-300; Cyc.hs:529-541).  LOLB_ERR_NOT_INVERTIBLE when q_d is not a unit mod some q_t.
+ *   lolb_rescaleModRq  y = fst (divModCent (q'_t * lift x) q_t) mod q'_t per limb (rescaleMod, Prelude.hs:143-153)
+ *   lolb_roundCosetRq  y = rep + p_t * round((e - rep) / p_t), rep = lift zp, p = the plan's moduli (roundCoset,
+ *                      Prelude.hs:155-162; errorCoset, UCyc.hs:436-445); zp == NULL: y = round e (errorRounded,
+ *                      UCyc.hs:427-434).  e is double, y int64, round is half-to-even.
+ */
+int lolb_liftRq(const lolb_plan* plan, const hInt_t* x, hInt_t* y, int64_t batch, void* stream);
+int lolb_reduceRq(const lolb_plan* plan, const hInt_t* z, int z_tupsize, hInt_t* y, int64_t batch, void* stream);
+int lolb_rescaleDropRq(const lolb_plan* plan, int drop, const hInt_t* x, hInt_t* y, int64_t batch, void* stream);
+int lolb_rescaleModRq(const lolb_plan* plan, const hInt_t* qs_new, const hInt_t* x, hInt_t* y, int64_t batch, void* stream);
+int lolb_roundCosetRq(const lolb_plan* plan, const double* e, const hInt_t* zp, hInt_t* y, int64_t batch, void* stream);
+
+/*
  * Host-buffer batched calls (what an FFI caller with Haskell-owned vectors
  * uses): `y` is a HOST pointer to batch elements; the call pipelines
  * host->device copy, kernel(s) and device->host copy over chunks on internal

@@ -170,6 +170,23 @@ class PlanRq:
     def knapsack(self, digits: int, ell: int, hints: int, c0: int, c1: int, batch: int, stream: int = 0) -> int:
         return int(lib().lolb_knapsackRq(self._h, _p(digits), C.c_int(ell), _p(hints), _p(c0), _p(c1), _i64(batch), _p(stream)))
 
+    # coefficient-wise maps (coeff_stream.cu)
+    def lift(self, x: int, y: int, batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_liftRq(self._h, _p(x), _p(y), _i64(batch), _p(stream)))
+
+    def reduce(self, z: int, z_tupsize: int, y: int, batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_reduceRq(self._h, _p(z), C.c_int(z_tupsize), _p(y), _i64(batch), _p(stream)))
+
+    def rescale_drop(self, drop: int, x: int, y: int, batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_rescaleDropRq(self._h, C.c_int(drop), _p(x), _p(y), _i64(batch), _p(stream)))
+
+    def rescale_mod(self, qs_new, x: int, y: int, batch: int, stream: int = 0) -> int:
+        qn = np.ascontiguousarray(qs_new, dtype=np.int64)
+        return int(lib().lolb_rescaleModRq(self._h, qn.ctypes.data_as(_p), _p(x), _p(y), _i64(batch), _p(stream)))
+
+    def round_coset(self, e: int, zp: int, y: int, batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_roundCosetRq(self._h, _p(e), _p(zp) if zp else None, _p(y), _i64(batch), _p(stream)))
+
     def apply_host(self, ops: str, host_ptr: int, batch: int) -> int:
         return int(lib().lolb_rq_apply_host(self._h, ops.encode(), _p(host_ptr), _i64(batch)))
 

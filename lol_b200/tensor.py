@@ -137,6 +137,45 @@ class CudaTensorRq:
     def _per_limb(self, r):
         return list(r) if isinstance(r, (list, tuple)) else [r] * self.k
 
+    # -- coefficient-wise maps around the transforms (fmapT lift / reduce / rescale, UCyc.hs:267-300; roundCoset, Prelude.hs:155-162)
+    def lift(self, x):
+        """fmapT lift: residues -> representatives in [-q/2, q/2), limb by limb."""
+        b = _require_cuda(x, torch.int64, self.n, self.k)
+        y = torch.empty_like(x)
+        capi.check(self.plan.lift(x.data_ptr(), y.data_ptr(), b, _stream()))
+        return y
+
+    def reduce(self, z):
+        """fmapT reduce: int64 [batch, n, 1] (or [batch, n, k]) -> residues modulo every q_t."""
+        kz = int(z.shape[2]) if z.dim() == 3 else -1
+        b = _require_cuda(z, torch.int64, self.n, kz)
+        y = torch.empty((b, self.n, self.k), dtype=torch.int64, device=z.device)
+        capi.check(self.plan.reduce(z.data_ptr(), kz, y.data_ptr(), b, _stream()))
+        return y
+
+    def rescaleDrop(self, x, drop=0):
+        """rescalePow over `Rescale (a,b) b` (drop = 0) / `Rescale (a,b) a` (drop = k-1): [batch, n, k] -> [batch, n, k-1]."""
+        b = _require_cuda(x, torch.int64, self.n, self.k)
+        y = torch.empty((b, self.n, self.k - 1), dtype=torch.int64, device=x.device)
+        capi.check(self.plan.rescale_drop(int(drop), x.data_ptr(), y.data_ptr(), b, _stream()))
+        return y
+
+    def rescaleMod(self, x, qs_new):
+        """fmapT rescaleMod: limb t from modulus q_t to qs_new[t]."""
+        b = _require_cuda(x, torch.int64, self.n, self.k)
+        y = torch.empty_like(x)
+        capi.check(self.plan.rescale_mod([int(q) for q in qs_new], x.data_ptr(), y.data_ptr(), b, _stream()))
+        return y
+
+    def roundCoset(self, e, zp=None):
+        """errorCoset's rounding (zp given: residues modulo this tensor's moduli) or errorRounded's (zp None): float64 -> int64."""
+        b = _require_cuda(e, torch.float64, self.n, self.k)
+        if zp is not None:
+            _require_cuda(zp, torch.int64, self.n, self.k)
+        y = torch.empty(e.shape, dtype=torch.int64, device=e.device)
+        capi.check(self.plan.round_coset(e.data_ptr(), zp.data_ptr() if zp is not None else 0, y.data_ptr(), b, _stream()))
+        return y
+
     def apply_host(self, ops: str, y_host: torch.Tensor) -> torch.Tensor:
         """Host-buffer call (lolb_rq_apply_host): `y_host` is a pinned or pageable CPU tensor [batch, n, k],
         transformed in place through the chunked H2D -> kernels -> D2H pipeline."""

@@ -22,7 +22,9 @@ pytestmark = pytest.mark.gpu
 
 FLOAT_TOL = 1e-9
 BIG_PARAMS = [(225, 14400, [14401]), (14400 // 25, 14400, [1008001, 1065601]), (64, 14400, [14401, 1008001, 1065601]),
-              (1, 14400, [14401])]
+              (1, 14400, [14401]),
+              # ~2^31 moduli: the exact 64-bit accumulation of twaceCRT reduces every 3 products (rel = 6 and 12)
+              (3, 42, [2148854401, 2148249601, 2150668801]), (1, 21, [2148249601])]
 
 
 @pytest.fixture(scope="module")

@@ -45,3 +45,30 @@ for name, (src, dst, words) in ops.items():
     gbs = words * 8 * k * B / ms / 1e6
     print(json.dumps({"op": name, "m": m, "m2": m2, "k": k, "batch": B, "ms": round(ms, 4), "elems_per_s": round(B / ms * 1e3),
                       "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "frac": round(gbs / peak, 3)}))
+
+# coefficient-wise maps (coeff_stream.cu) on the O_m' batch: words = 8-byte words read + written per coefficient word of the output
+e = torch.randn((B, phi2, k), device="cuda", dtype=torch.float64) * 1e4
+oi = torch.empty_like(y)
+od = torch.empty((B, phi2, k - 1), device="cuda", dtype=torch.int64)
+P = hi.plan
+cops = {
+    "liftRq": (lambda: P.lift(y.data_ptr(), oi.data_ptr(), B, st), 2 * phi2 * k),
+    "reduceRq": (lambda: P.reduce(oi.data_ptr(), k, oy.data_ptr(), B, st), 2 * phi2 * k),
+    "rescaleDropRq": (lambda: P.rescale_drop(0, y.data_ptr(), od.data_ptr(), B, st), phi2 * k + phi2 * (k - 1)),
+    "rescaleModRq": (lambda: P.rescale_mod(qs[::-1], y.data_ptr(), oi.data_ptr(), B, st), 2 * phi2 * k),
+    "roundCosetRq": (lambda: P.round_coset(e.data_ptr(), y.data_ptr(), oi.data_ptr(), B, st), 3 * phi2 * k),
+}
+for name, (fn, words) in cops.items():
+    for _ in range(3):
+        capi.check(fn())
+    s, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        fn()
+    e2.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e2) / iters
+    gbs = words * 8 * B / ms / 1e6
+    print(json.dumps({"op": name, "m": m2, "k": k, "batch": B, "ms": round(ms, 4), "elems_per_s": round(B / ms * 1e3),
+                      "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "frac": round(gbs / peak, 3)}))
