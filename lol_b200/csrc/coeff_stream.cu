@@ -22,123 +22,139 @@ using namespace lolb;
 
 namespace {
 
-__device__ __forceinline__ int64_t canon64(int64_t x, int64_t q)
+// x mod q for any uint64 x, q < 2^32, mu = floor(2^64 / q)
+__device__ __forceinline__ int64_t barrett_u64(uint64_t x, uint32_t q, uint64_t mu)
+{
+  uint64_t r = x - __umul64hi(x, mu) * q;                          // [0, 3q)
+  if (r >= q) r -= q;
+  if (r >= q) r -= q;
+  return (int64_t)r;
+}
+
+// Haskell `mod` (non-negative) of any int64; canonical inputs take the first branch
+__device__ __forceinline__ int64_t canon64(int64_t x, uint32_t q, uint64_t mu)
 {
   if ((uint64_t)x < (uint64_t)q) return x;
-  const int64_t r = x % q;
-  return r < 0 ? r + q : r;
+  if (x >= 0) return barrett_u64((uint64_t)x, q, mu);
+  const int64_t r = barrett_u64(0ull - (uint64_t)x, q, mu);        // |x| mod q
+  return r == 0 ? 0 : (int64_t)q - r;
 }
 
 __device__ __forceinline__ int64_t lift64(int64_t c, int64_t q) { return 2 * c < q ? c : c - q; }      // ZqBasic.hs:92-94
 
-__device__ __forceinline__ uint32_t barrett_mul(uint32_t a, uint32_t b, uint32_t q, uint64_t mu)
+// floor(a / q) for any int64 a (Haskell `div`), by a Barrett quotient with at most two corrections
+__device__ __forceinline__ int64_t floor_div(int64_t a, uint32_t q, uint64_t mu)
 {
-  const uint64_t x = (uint64_t)a * b;
-  uint64_t r = x - __umul64hi(x, mu) * q;
-  if (r >= q) r -= q;
-  if (r >= q) r -= q;
-  return (uint32_t)r;
+  const bool neg = a < 0;
+  const uint64_t x = neg ? 0ull - (uint64_t)a - 1 : (uint64_t)a;  // a < 0: floor(a / q) = -(floor((|a| - 1) / q) + 1)
+  uint64_t qh = __umul64hi(x, mu);
+  uint64_t r = x - qh * q;
+  if (r >= q) { r -= q; qh++; }
+  if (r >= q) { r -= q; qh++; }
+  return neg ? -(int64_t)qh - 1 : (int64_t)qh;
 }
 
+// Every operator sees an output word as (g, u): coefficient index g (over batch * n) and position u inside the
+// coefficient's tuple of `period` words.  The launch makes the grid stride a multiple of the period, so u (the limb) and
+// everything derived from it are loop invariants of a thread and no division runs inside the loop.
 struct OpLift {
   const long long* x; long long* y; int k; ZqConsts Z;
   typedef long long In;
-  __device__ In load(int64_t i) const { return __ldcs(x + i); }
-  __device__ void apply(int64_t i, In v) const
+  __device__ int period() const { return k; }
+  __device__ In load(int64_t g, int u) const { return __ldcs(x + g * k + u); }
+  __device__ void apply(int64_t g, int u, In v) const
   {
-    const int64_t q = Z.q[(int)(i % k)];
-    __stcs(y + i, (long long)lift64(canon64(v, q), q));
+    const uint32_t q = Z.q[u];
+    __stcs(y + g * k + u, (long long)lift64(canon64(v, q, Z.mu[u]), q));
   }
 };
 
 struct OpReduce {
   const long long* z; long long* y; int k; int kz; ZqConsts Z;
   typedef long long In;
-  __device__ In load(int64_t i) const { return kz == k ? __ldcs(z + i) : __ldg(z + i / k); }
-  __device__ void apply(int64_t i, In v) const { __stcs(y + i, (long long)canon64(v, (int64_t)Z.q[(int)(i % k)])); }
+  __device__ int period() const { return k; }
+  __device__ In load(int64_t g, int u) const { return kz == k ? __ldcs(z + g * k + u) : __ldg(z + g); }
+  __device__ void apply(int64_t g, int u, In v) const { __stcs(y + g * k + u, (long long)canon64(v, Z.q[u], Z.mu[u])); }
 };
 
 struct OpRescaleDrop {
   const long long* x; long long* y; int k; int d; ZqConsts Z;      // Z.scale[t] = q_d^-1 mod q_t
   typedef longlong2 In;                                            // (x_t, x_d)
-  __device__ int limb(int64_t i, int64_t* c) const
+  __device__ int period() const { return k - 1; }
+  __device__ int limb(int u) const { return u < d ? u : u + 1; }
+  __device__ In load(int64_t g, int u) const { return make_longlong2(__ldg(x + g * k + limb(u)), __ldg(x + g * k + d)); }
+  __device__ void apply(int64_t g, int u, In v) const
   {
-    *c = i / (k - 1);
-    const int u = (int)(i - *c * (k - 1));
-    return u < d ? u : u + 1;
-  }
-  __device__ In load(int64_t i) const
-  {
-    int64_t c;
-    const int t = limb(i, &c);
-    return make_longlong2(__ldg(x + c * k + t), __ldg(x + c * k + d));
-  }
-  __device__ void apply(int64_t i, In v) const
-  {
-    int64_t c;
-    const int t = limb(i, &c);
-    const int64_t qt = Z.q[t], qd = Z.q[d];
-    const int64_t xt = canon64(v.x, qt);
-    const int64_t z = lift64(canon64(v.y, qd), qd);              // lift x_d
-    int64_t diff = xt - canon64(z, qt);                          // x_t - reduce z
+    const int t = limb(u);
+    const uint32_t qt = Z.q[t], qd = Z.q[d];
+    const int64_t xt = canon64(v.x, qt, Z.mu[t]);
+    const int64_t z = lift64(canon64(v.y, qd, Z.mu[d]), qd);     // lift x_d
+    int64_t diff = xt - canon64(z, qt, Z.mu[t]);                 // x_t - reduce z
     if (diff < 0) diff += qt;
-    __stcs(y + i, (long long)barrett_mul((uint32_t)diff, Z.scale[t], (uint32_t)qt, Z.mu[t]));
+    __stcs(y + g * (k - 1) + u, barrett_u64((uint64_t)diff * Z.scale[t], qt, Z.mu[t]));
   }
 };
 
 struct OpRescaleMod {
   const long long* x; long long* y; int k; ZqConsts Z; uint32_t q2[kMaxLimbs];
   typedef long long In;
-  __device__ In load(int64_t i) const { return __ldcs(x + i); }
-  __device__ void apply(int64_t i, In v) const
+  __device__ int period() const { return k; }
+  __device__ In load(int64_t g, int u) const { return __ldcs(x + g * k + u); }
+  __device__ void apply(int64_t g, int u, In v) const
   {
-    const int t = (int)(i % k);
-    const int64_t q = Z.q[t], qn = q2[t];
-    const int64_t a = qn * lift64(canon64(v, q), q) + q / 2;     // |q' lift x| < 2^63: q' < 2^32, |lift x| <= 2^31
-    int64_t quot = a / q;                                        // divMod: floor
-    if (a % q < 0) quot -= 1;
-    __stcs(y + i, (long long)canon64(quot, qn));                 // fromIntegral into Z_q'
+    const uint32_t q = Z.q[u];
+    const int64_t qn = q2[u];
+    const int64_t a = qn * lift64(canon64(v, q, Z.mu[u]), q) + q / 2;      // |q' lift x| < 2^63: q' < 2^32, |lift x| <= 2^31
+    int64_t quot = floor_div(a, q, Z.mu[u]);                                // |quot| <= q'/2 + 1
+    while (quot < 0) quot += qn;                                            // fromIntegral into Z_q'
+    while (quot >= qn) quot -= qn;
+    __stcs(y + g * k + u, (long long)quot);
   }
 };
 
 struct OpRoundCoset {
   const double* e; const long long* zp; long long* y; int k; ZqConsts Z;
   struct In { double e; long long z; };
-  __device__ In load(int64_t i) const { return In{__ldcs(e + i), zp ? __ldcs(zp + i) : 0}; }
-  __device__ void apply(int64_t i, In v) const
+  __device__ int period() const { return k; }
+  __device__ In load(int64_t g, int u) const { return In{__ldcs(e + g * k + u), zp ? __ldcs(zp + g * k + u) : 0}; }
+  __device__ void apply(int64_t g, int u, In v) const
   {
-    if (!zp) { __stcs(y + i, (long long)rint(v.e)); return; }    // roundMult 1 = round (half to even)
-    const int64_t p = Z.q[(int)(i % k)];
-    const int64_t rep = lift64(canon64(v.z, p), p);
+    if (!zp) { __stcs(y + g * k + u, (long long)rint(v.e)); return; }      // roundMult 1 = round (half to even)
+    const uint32_t p = Z.q[u];
+    const int64_t rep = lift64(canon64(v.z, p, Z.mu[u]), p);
     const double r = __ddiv_rn(__dsub_rn(v.e, (double)rep), (double)p);
-    __stcs(y + i, (long long)(rep + (p == 1 ? (int64_t)rint(__dsub_rn(v.e, (double)rep)) : p * (int64_t)rint(r))));
+    __stcs(y + g * k + u, (long long)(rep + (int64_t)p * (int64_t)rint(r)));
   }
 };
 
 template <class OP>
-__global__ void __launch_bounds__(256) k_coeff_stream(const __grid_constant__ OP op, int64_t total)
+__global__ void __launch_bounds__(256) k_coeff_stream(const __grid_constant__ OP op, int64_t groups)
 {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < total; i += 4 * stride) {
+  const int period = op.period();
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t gstep = (int64_t)gridDim.x * blockDim.x / period;            // the launch makes this exact
+  const int u = (int)(i0 % period);
+  int64_t g = i0 / period;
+  for (; g + 3 * gstep < groups; g += 4 * gstep) {
     typename OP::In v[4];
 #pragma unroll
-    for (int a = 0; a < 4; a++) v[a] = op.load(i + a * stride);
+    for (int a = 0; a < 4; a++) v[a] = op.load(g + a * gstep, u);
 #pragma unroll
-    for (int a = 0; a < 4; a++) op.apply(i + a * stride, v[a]);
+    for (int a = 0; a < 4; a++) op.apply(g + a * gstep, u, v[a]);
   }
-  for (; i < total; i += stride) op.apply(i, op.load(i));
+  for (; g < groups; g += gstep) op.apply(g, u, op.load(g, u));
 }
 
 template <class OP>
-int launch(const lolb_plan* pl, const OP& op, int64_t total, void* stream, const char* what)
+int launch(const lolb_plan* pl, const OP& op, int64_t groups, int period, void* stream, const char* what)
 {
-  if (total <= 0) return LOLB_OK;
+  if (groups <= 0) return LOLB_OK;
+  const int64_t total = groups * period;
   int64_t blocks = (total + 1023) / 1024;                         // four words per thread
   const int64_t cap = (int64_t)pl->num_sms * 16;
   if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  k_coeff_stream<OP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(op, total);
+  blocks = (blocks + period - 1) / period * period;               // grid stride a multiple of the period: a thread keeps its limb
+  k_coeff_stream<OP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(op, groups);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, what);
   count_launch();
@@ -159,7 +175,7 @@ extern "C" int lolb_liftRq(const lolb_plan* plan, const hInt_t* x, hInt_t* y, in
   int rc = check(plan, x, y, batch, __func__);
   if (rc) return rc;
   OpLift op{(const long long*)x, (long long*)y, plan->k, plan->zq_plain};
-  return launch(plan, op, batch * plan->n * plan->k, stream, "k_coeff_stream<lift>");
+  return launch(plan, op, batch * plan->n, plan->k, stream, "k_coeff_stream<lift>");
 }
 
 extern "C" int lolb_reduceRq(const lolb_plan* plan, const hInt_t* z, int z_tupsize, hInt_t* y, int64_t batch, void* stream)
@@ -168,7 +184,7 @@ extern "C" int lolb_reduceRq(const lolb_plan* plan, const hInt_t* z, int z_tupsi
   if (rc) return rc;
   if (z_tupsize != 1 && z_tupsize != plan->k) { set_error("lolb_reduceRq: z_tupsize must be 1 or the plan's tupSize"); return LOLB_ERR_ARG; }
   OpReduce op{(const long long*)z, (long long*)y, plan->k, z_tupsize, plan->zq_plain};
-  return launch(plan, op, batch * plan->n * plan->k, stream, "k_coeff_stream<reduce>");
+  return launch(plan, op, batch * plan->n, plan->k, stream, "k_coeff_stream<reduce>");
 }
 
 extern "C" int lolb_rescaleDropRq(const lolb_plan* plan, int drop, const hInt_t* x, hInt_t* y, int64_t batch, void* stream)
@@ -184,7 +200,7 @@ extern "C" int lolb_rescaleDropRq(const lolb_plan* plan, int drop, const hInt_t*
     if (inv == 0) { set_error("lolb_rescaleDropRq: the dropped modulus is not invertible modulo another limb"); return LOLB_ERR_NOT_INVERTIBLE; }
     op.Z.scale[t] = (uint32_t)inv;
   }
-  return launch(plan, op, batch * plan->n * (plan->k - 1), stream, "k_coeff_stream<rescaleDrop>");
+  return launch(plan, op, batch * plan->n, plan->k - 1, stream, "k_coeff_stream<rescaleDrop>");
 }
 
 extern "C" int lolb_rescaleModRq(const lolb_plan* plan, const hInt_t* qs_new, const hInt_t* x, hInt_t* y, int64_t batch, void* stream)
@@ -197,7 +213,7 @@ extern "C" int lolb_rescaleModRq(const lolb_plan* plan, const hInt_t* qs_new, co
     if (qs_new[t] < 1 || qs_new[t] >= ((int64_t)1 << 32)) { set_error("lolb_rescaleModRq: target modulus out of range [1, 2^32)"); return LOLB_ERR_ARG; }
     op.q2[t] = (uint32_t)qs_new[t];
   }
-  return launch(plan, op, batch * plan->n * plan->k, stream, "k_coeff_stream<rescaleMod>");
+  return launch(plan, op, batch * plan->n, plan->k, stream, "k_coeff_stream<rescaleMod>");
 }
 
 extern "C" int lolb_roundCosetRq(const lolb_plan* plan, const double* e, const hInt_t* zp, hInt_t* y, int64_t batch, void* stream)
@@ -205,5 +221,5 @@ extern "C" int lolb_roundCosetRq(const lolb_plan* plan, const double* e, const h
   int rc = check(plan, e, y, batch, __func__);
   if (rc) return rc;
   OpRoundCoset op{e, (const long long*)zp, (long long*)y, plan->k, plan->zq_plain};
-  return launch(plan, op, batch * plan->n * plan->k, stream, "k_coeff_stream<roundCoset>");
+  return launch(plan, op, batch * plan->n, plan->k, stream, "k_coeff_stream<roundCoset>");
 }
