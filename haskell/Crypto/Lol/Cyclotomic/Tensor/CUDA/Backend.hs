@@ -17,6 +17,11 @@ module Crypto.Lol.Cyclotomic.Tensor.CUDA.Backend
 , lolbDeviceAvailable, lolbLastError
   -- * device-resident SymmSHE steps (raw imports; operands are device addresses)
 , DevPtr, c_crtRq, c_crtInvRq, c_ctMulRq, c_gadgetLength, c_decomposeRq, c_decomposeCrtRq, c_knapsackRq
+  -- * ring extensions O_m'/O_m (raw imports; one ExtStruct per '(m, m'), Tensor.hs:380-498 / CPP/Extension.hs:54-129)
+, ExtStruct, ringRq, ringInt, ringDouble, ringComplex
+, c_extCreate, p_extDestroy, c_twacePowDec, c_embedPow, c_embedDec, c_embedCRT, c_coeffsPowDec, c_twaceCRT
+  -- * coefficient-wise maps (fmapT lift / reduce / rescale, UCyc.hs:267-300; roundCoset, Prelude.hs:155-162)
+, c_liftRq, c_reduceRq, c_rescaleDropRq, c_rescaleModRq, c_roundCosetRq
 ) where
 
 import Control.Exception      (bracket, throwIO, ErrorCall (..))
@@ -62,6 +67,48 @@ foreign import ccall unsafe "lolb_decomposeCrtRq" c_decomposeCrtRq ::
 -- [c0,c1] += knapsack hint digits
 foreign import ccall unsafe "lolb_knapsackRq" c_knapsackRq ::
   Ptr PlanStruct -> DevPtr Int64 -> Int32 -> DevPtr Int64 -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+
+-- | Opaque @lolb_ext@: the index tables of one extension O_m'/O_m on the device.
+data ExtStruct
+-- | The @ring@ argument of the extension operators (LOLB_RING_* in lol_b200.h).
+ringRq, ringInt, ringDouble, ringComplex :: Int32
+ringRq = 0; ringInt = 1; ringDouble = 2; ringComplex = 3
+
+foreign import ccall unsafe "lolb_ext_create" c_extCreate ::
+  Ptr (Ptr ExtStruct) -> Ptr PlanStruct -> Ptr PlanStruct -> IO Int32
+foreign import ccall unsafe "&lolb_ext_destroy" p_extDestroy :: FunPtr (Ptr ExtStruct -> IO ())
+-- twacePowDec' (Extension.hs:99-103): O_m' -> O_m
+foreign import ccall unsafe "lolb_twacePowDec" c_twacePowDec ::
+  Ptr ExtStruct -> Int32 -> DevPtr a -> DevPtr a -> Int64 -> Ptr () -> IO Int32
+-- embedPow', embedDec', embedCRT' (Extension.hs:60-85): O_m -> O_m'
+foreign import ccall unsafe "lolb_embedPow" c_embedPow ::
+  Ptr ExtStruct -> Int32 -> DevPtr a -> DevPtr a -> Int64 -> Ptr () -> IO Int32
+foreign import ccall unsafe "lolb_embedDec" c_embedDec ::
+  Ptr ExtStruct -> Int32 -> DevPtr a -> DevPtr a -> Int64 -> Ptr () -> IO Int32
+foreign import ccall unsafe "lolb_embedCRT" c_embedCRT ::
+  Ptr ExtStruct -> Int32 -> DevPtr a -> DevPtr a -> Int64 -> Ptr () -> IO Int32
+-- coeffs' (Extension.hs:90-93): the phi'/phi output elements are laid out back to back per input element
+foreign import ccall unsafe "lolb_coeffsPowDec" c_coeffsPowDec ::
+  Ptr ExtStruct -> Int32 -> DevPtr a -> DevPtr a -> Int64 -> Ptr () -> IO Int32
+-- twaceCRT' (Extension.hs:110-129); status 2 (LOLB_ERR_NO_CRT) is the reference's Nothing
+foreign import ccall unsafe "lolb_twaceCRT" c_twaceCRT ::
+  Ptr ExtStruct -> Int32 -> DevPtr a -> DevPtr a -> Int64 -> Ptr () -> IO Int32
+
+-- fmapT lift / fmapT reduce (UCyc.hs:267-296); reduce takes 1 or tupSize integers per coefficient
+foreign import ccall unsafe "lolb_liftRq" c_liftRq ::
+  Ptr PlanStruct -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+foreign import ccall unsafe "lolb_reduceRq" c_reduceRq ::
+  Ptr PlanStruct -> DevPtr Int64 -> Int32 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+-- rescalePow over Rescale (a,b) b (drop = 0) / Rescale (a,b) a (drop = tupSize-1), Prelude.hs:226-265
+foreign import ccall unsafe "lolb_rescaleDropRq" c_rescaleDropRq ::
+  Ptr PlanStruct -> Int32 -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+-- fmapT rescaleMod (Prelude.hs:143-153); second argument: the target moduli (host pointer)
+foreign import ccall unsafe "lolb_rescaleModRq" c_rescaleModRq ::
+  Ptr PlanStruct -> Ptr Int64 -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+-- roundCoset <$> zp <*> e (Prelude.hs:155-162); a null coset pointer rounds to the nearest integer (errorRounded)
+foreign import ccall unsafe "lolb_roundCosetRq" c_roundCosetRq ::
+  Ptr PlanStruct -> DevPtr Double -> DevPtr Int64 -> DevPtr Int64 -> Int64 -> Ptr () -> IO Int32
+
 foreign import ccall unsafe "lolb_last_error" c_lastError :: IO CString
 foreign import ccall unsafe "lolb_device_available" c_deviceAvailable :: IO Int32
 
