@@ -150,3 +150,30 @@ def test_library_host_index_tables_reject_non_divisors():
     for m, m2 in ((4, 6), (9, 3), (5, 12)):
         with pytest.raises(capi.LolB200Error):
             capi.ext_index_table(T.factor_pps(m), T.factor_pps(m2), capi.EXT_INDICES_POWDEC)
+
+
+@pytest.mark.parametrize("m,m2", [(3, 21), (4, 12), (1, 7), (45, 225), (64, 576), (15, 105)], ids=lambda v: str(v))
+def test_complex_crt_basis_operators_against_compiled_reference_crt(reference, m, m2):
+    """prop_embed_crt / prop_twace_crt over Complex Double with the compiled reference's tensorCRTC / tensorCRTInvC / tensorGPowC:
+    pins twace_crt_c (and the g = crt(mulGPow 1) form of the gCRT vector the CUDA path uses) to 1e-9 relative."""
+    from conftest import rel_err
+    rng = np.random.default_rng(m + m2)
+    info = X.ExtInfo(m, m2)
+
+    def ring(mm):
+        pe = T.pe_array(mm)
+        n = T.totient_pps(T.factor_pps(mm))
+        ru, rui, mh = T.ru_tables_c(mm), T.ru_tables_c(mm, inverse=True), T.mhat_inv_c(mm)
+        crt = lambda v: reference.tensorCRTC(v, pe, ru).reshape(v.shape)
+        crt_inv = lambda v: reference.tensorCRTInvC(v, pe, rui, mh).reshape(v.shape)
+        unit = np.zeros((n, 1), dtype=np.complex128)
+        unit[0] = 1.0
+        g = crt(reference.tensorGPowC(unit, pe).reshape(unit.shape))[:, 0]
+        return n, crt, crt_inv, g
+
+    n_lo, crt_lo, crt_inv_lo, g_lo = ring(m)
+    n_hi, crt_hi, crt_inv_hi, g_hi = ring(m2)
+    x = rng.standard_normal((n_lo, 1)) + 1j * rng.standard_normal((n_lo, 1))
+    y = rng.standard_normal((n_hi, 1)) + 1j * rng.standard_normal((n_hi, 1))
+    assert rel_err(X.embed_crt(info, x), crt_hi(X.embed_pow(info, crt_inv_lo(x)))) <= 1e-9
+    assert rel_err(X.twace_crt_c(info, y, g_lo, g_hi), crt_lo(X.twace_powdec(info, crt_inv_hi(y)))) <= 1e-9
