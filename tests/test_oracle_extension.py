@@ -177,3 +177,20 @@ def test_complex_crt_basis_operators_against_compiled_reference_crt(reference, m
     y = rng.standard_normal((n_hi, 1)) + 1j * rng.standard_normal((n_hi, 1))
     assert rel_err(X.embed_crt(info, x), crt_hi(X.embed_pow(info, crt_inv_lo(x)))) <= 1e-9
     assert rel_err(X.twace_crt_c(info, y, g_lo, g_hi), crt_lo(X.twace_powdec(info, crt_inv_hi(y)))) <= 1e-9
+
+
+def test_library_host_index_tables_sweep_all_divisor_pairs():
+    """Every pair m | m' with m' <= 120 (and a few larger indices with three and four prime factors): the C++ tables of
+    ext_stream.cu (iterative mixed-radix forms) equal the recursive restatement of Tensor.hs:391-498."""
+    from lol_b200 import build_library, capi
+    build_library()
+    pairs = [(m, m2) for m2 in list(range(1, 121)) + [420, 1155, 2 * 3 * 5 * 7 * 11, 27 * 25 * 7] for m in range(1, m2 + 1) if m2 % m == 0]
+    assert len(pairs) > 600
+    for m, m2 in pairs:
+        info = X.ExtInfo(m, m2)
+        pps, pps2 = T.factor_pps(m), T.factor_pps(m2)
+        dec = np.where(info.base_dec_idx < 0, -1, info.base_dec_idx * 2 + info.base_dec_neg)
+        for which, want in ((capi.EXT_INDICES_POWDEC, info.ext_powdec), (capi.EXT_INDICES_CRT, info.ext_crt),
+                            (capi.EXT_BASE_POW_J0, info.base_pow_j0), (capi.EXT_BASE_DEC, dec),
+                            (capi.EXT_INDICES_COEFFS, info.ext_coeffs.reshape(-1))):
+            assert np.array_equal(capi.ext_index_table(pps, pps2, which), want), (m, m2, which)
