@@ -113,3 +113,38 @@ def test_symmshe_pairs_sharded_hints_replicated_world2(tmp_path, batch):
     result = tmp_path / "result.txt"
     mp.spawn(_she_worker, args=(2, _free_port(), batch, str(result)), nprocs=2, join=True)
     assert result.read_text() == "ok"
+
+
+# ------------------------------------------------------------------ ring switching: O_m' elements sharded, output in O_m with one limb fewer
+def _ext_worker(rank, world, port, batch, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import coeffwise as W, extension as X
+        m, m2, qs = 3, 21, [19393921, 18869761]
+        info = X.ExtInfo(m, m2)
+        full = None
+        if rank == 0:
+            rng = np.random.default_rng(13)
+            full = torch.from_numpy(np.stack([rng.integers(0, q, size=(batch, info.phi2)) for q in qs], axis=-1).astype(np.int64))
+        # twaceCRT then the RNS limb drop: [b, phi', k] -> [b, phi, k-1]; the index tables are per-(m, m') data every rank builds itself
+        step = lambda y: W.rescale_drop(X.twace_crt_zq(info, y, qs), qs, 0)
+        local = scatter_batch(full, batch, (info.phi2, len(qs)), torch.int64, "cpu")
+        out = (np.stack([step(local[b].numpy()) for b in range(local.shape[0])]) if local.shape[0]
+               else np.zeros((0, info.phi, len(qs) - 1), dtype=np.int64))
+        got = gather_batch(torch.from_numpy(out), batch)
+        if rank == 0:
+            want = np.stack([step(full[b].numpy()) for b in range(batch)])
+            ok = got.shape == (batch, info.phi, len(qs) - 1) and np.array_equal(got.numpy(), want)
+            with open(result_path, "w") as f:
+                f.write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_ring_switch_elements_sharded_world2(tmp_path, batch):
+    """twaceCRT + rescale shard by element like every other operator (batch 1: one rank owns nothing)."""
+    result = tmp_path / "result.txt"
+    mp.spawn(_ext_worker, args=(2, _free_port(), batch, str(result)), nprocs=2, join=True)
+    assert result.read_text() == "ok"
