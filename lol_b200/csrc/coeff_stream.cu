@@ -105,9 +105,9 @@ struct OpRescaleMod {
     const uint32_t q = Z.q[u];
     const int64_t qn = q2[u];
     const int64_t a = qn * lift64(canon64(v, q, Z.mu[u]), q) + q / 2;      // |q' lift x| < 2^63: q' < 2^32, |lift x| <= 2^31
-    int64_t quot = floor_div(a, q, Z.mu[u]);                                // |quot| <= q'/2 + 1
-    while (quot < 0) quot += qn;                                            // fromIntegral into Z_q'
-    while (quot >= qn) quot -= qn;
+    int64_t quot = floor_div(a, q, Z.mu[u]);                                // -ceil(q'/2) <= quot <= floor((q'+1)/2)
+    if (quot < 0) quot += qn;                                               // fromIntegral into Z_q': one correction is enough
+    if (quot >= qn) quot -= qn;                                             // (a `while` here compiles to a 64-bit division call)
     __stcs(y + g * k + u, (long long)quot);
   }
 };
