@@ -6,10 +6,12 @@ moduli or rounds an error term -- exact Python-integer / numpy restatement of
     rescaleMod         lol/Crypto/Lol/Prelude.hs:143-153 with divModCent, Types/Numeric.hs:227-234
     roundCoset         lol/Crypto/Lol/Prelude.hs:155-162 with roundMult, Types/Numeric.hs:207-210
 
-PARITY UNPINNED against a reference binary: these are Haskell closures and no GHC exists in this container.  The
-restatement is anchored instead by the identities tests/test_oracle_coeffwise.py checks with independent big-integer
-arithmetic (exact division after removing the centred remainder; |rescaleMod(x) q/q' - x| <= q/(2q') + 1/2; the coset
-property of roundCoset).  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+Bit-level parity with a reference run is UNPINNED: these are Haskell closures and no GHC exists in this container.  The
+restatement is anchored by the identities tests/test_oracle_coeffwise.py checks with independent big-integer arithmetic
+(exact division after removing the centred remainder; nearest rounding of q'/q * lift x; the coset property of
+roundCoset) and, semantically, by tests/test_oracle_symmshe_scheme.py: `round_coset` produces the encryption error
+(errorCoset), `lift` the decryption, and `rescale_drop` the ciphertext modulus switch (modSwitch, SymmSHE.hs:236-248),
+with the compiled reference doing every ring transform -- the switched ciphertext must still decrypt to the plaintext.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
 """
 from __future__ import annotations
 

@@ -2,8 +2,12 @@
 of the `Tensor` path, used to check lol_b200/symmshe.py and she_stream.cu.  Only tests/, __graft_entry__.smoke() and
 bench.py's CPU legs may import this module.
 
-The reference for these steps is Haskell (no GHC in this image), so nothing here is pinned against a run of the
-reference itself: PARITY UNPINNED for the formulas of this file.  They restate, line by line,
+The reference for these steps is Haskell (no GHC in this image), so nothing here can be compared bit for bit with a run
+of the reference itself.  The formulas are pinned SEMANTICALLY through the reference's own SymmSHE test properties
+(lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs: prop_encDec, prop_ctmul, prop_ksQuad) in
+tests/test_oracle_symmshe_scheme.py, where every ring transform is done by the COMPILED reference: a ciphertext product
+followed by `mul_and_switch` must decrypt to pt1 * pt2 for TrivGad and BaseBGad gadgets, and a random hint must not.
+Bit-level parity with a Haskell run stays UNPINNED.  They restate, line by line,
 
     lift = decode'            lol/Crypto/Lol/Types/Unsafe/ZqBasic.hs:92-94, 124-125
     TrivGad                   ZqBasic.hs:227-232          gadget = [1], decompose x = [lift x]

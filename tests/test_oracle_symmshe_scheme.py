@@ -1,0 +1,169 @@
+"""CPU suite: pin oracle/symmshe.py and oracle/coeffwise.py through the reference's own SymmSHE test properties
+(lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs): prop_encDec (:172-177), prop_ctmul (:148-158), prop_ksQuad (:200-209),
+plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
+
+The scheme around the restated steps -- encrypt, ksQuadCircHint, toMSD / toLSD, decryptUnrestricted -- is restated here
+from lol-apps/Crypto/Lol/Applications/SymmSHE.hs (:131-141, :199-206, :222-232, :259-287, :346-372) for m = m', with
+every ring transform (crt, crtInv, l, lInv, divGDec) done by the COMPILED reference.  If the restated decomposition,
+knapsack, ciphertext product, lift or limb drop disagreed with the reference's semantics, decryption would not return
+pt1 * pt2: the gadget identity and the noise bound both have to hold.
+"""
+import numpy as np
+import pytest
+
+from oracle import coeffwise as W
+from oracle import symmshe as S
+from oracle import tables as T
+from test_oracle_extension import Ring
+
+M, QS, P = 21, [19393921, 18869761], 5          # 21 | q - 1 for both primes; rad_odd(21) is a unit modulo 5
+BIGQ = 2148249601                               # 21 | BIGQ - 1: exact integer ring products through its CRT
+
+
+class Scheme:
+    def __init__(self, reference, rng):
+        self.ref, self.rng = reference, rng
+        self.R = Ring(reference, M, QS)
+        self.n, self.k = self.R.n, len(QS)
+        self.pe = T.pe_array(M)
+        self.g = T.g_crt_vectors(M, QS)[0]
+        self.tables = (self.pe, self.R.ru, self.R.rui, self.R.mh, self.g)
+        self.q = np.asarray(QS, dtype=np.int64)
+        # genSK (SymmSHE.hs:118-121): errorRounded -> small integers in the decoding basis
+        self.s_dec = rng.integers(-1, 2, size=self.n)
+        self.sq_crt = self.R.crt(self.dec_to_pow(self.s_dec))
+
+    # -- helpers over R_q (ABI arrays [n, k])
+    def dec_to_pow(self, z_dec):
+        """reduce an integer Dec-basis element into R_q and convert to the powerful basis (l: Dec -> Pow)."""
+        return self.R.l(S.reduce_digit(z_dec, QS))
+
+    def mul(self, a, b): return S._mulmod(a, b, QS)
+    def add(self, a, b): return S._addmod(a, b, QS)
+    def neg(self, a): return (self.q - a) % self.q
+    def uniform(self): return np.stack([self.rng.integers(0, q, size=self.n) for q in QS], axis=-1).astype(np.int64)
+
+    def small_error(self):
+        """errorRounded (UCyc.hs:427-429): round of a Gaussian in the decoding basis."""
+        return W.round_coset(self.rng.standard_normal((self.n, 1)) * 1.5, None, [P])[:, 0]
+
+    # -- SymmSHE.hs:131-141
+    def encrypt(self, pt_dec):
+        gauss = self.rng.standard_normal((self.n, 1)) * 1.5 * P                     # tGaussian (svar p^2), UCyc.hs:443
+        e_dec = W.round_coset(gauss, np.asarray(pt_dec, dtype=np.int64).reshape(-1, 1), [P])[:, 0]   # roundCoset <$> c <*> err
+        assert np.array_equal(e_dec % P, np.asarray(pt_dec) % P)
+        c1 = self.uniform()
+        c0 = self.add(self.R.crt(self.dec_to_pow(e_dec)), self.neg(self.mul(c1, self.sq_crt)))
+        return {"enc": "LSD", "k": 0, "l": 1, "c": [c0, c1]}                       # CRT-basis components
+
+    # -- SymmSHE.hs:222-232
+    def to_msd(self, ct):
+        if ct["enc"] == "MSD":
+            return ct
+        qprod = int(np.prod([int(q) for q in QS], dtype=object))       # zpScale = -q mod p (ZqBasic.hs:135-137; Prelude.hs:311-315)
+        return {"enc": "MSD", "k": ct["k"], "l": ct["l"] * (-qprod) % P, "c": [self.scal_inv_p(c) for c in ct["c"]]}
+
+    def scal_inv_p(self, a):
+        w = np.asarray([pow(P, -1, q) for q in QS], dtype=np.int64)      # zqScale = recip (reduce p), limb by limb
+        return S._mulmod(a, np.broadcast_to(w, a.shape), QS)
+
+    # -- SymmSHE.hs:259-287: ksHint sk (s*s) with lweSample; hint [ell, 2, n, k] in the CRT basis
+    def ks_quad_circ_hint(self, base):
+        val = self.mul(self.sq_crt, self.sq_crt)
+        hint = []
+        for gad in S.gadget(QS, base):
+            c1 = self.uniform()
+            b = self.add(self.mul(c1, self.neg(self.sq_crt)), self.R.crt(self.dec_to_pow(self.small_error())))
+            valgad = self.mul(val, np.broadcast_to(np.asarray(gad, dtype=np.int64), val.shape))
+            hint.append([self.add(valgad, b), c1])
+        return np.asarray(hint, dtype=np.int64)
+
+    # -- SymmSHE.hs:199-206 (decryptUnrestricted), for a polynomial of any degree over the limbs qs
+    def decrypt(self, ct, qs=None):
+        qs = QS if qs is None else qs
+        R = self.R if qs == QS else Ring(self.ref, M, qs)
+        sq = self.sq_crt if qs == QS else R.crt(R.l(S.reduce_digit(self.s_dec, qs)))
+        l = ct["l"]
+        comps = ct["c"]
+        if ct["enc"] == "MSD":                                                       # toLSD
+            qprod = int(np.prod([int(q) for q in qs], dtype=object))
+            l = l * pow((-qprod) % P, -1, P) % P
+            w = np.asarray([P % q for q in qs], dtype=np.int64)
+            comps = [S._mulmod(c, np.broadcast_to(w, c.shape), qs) for c in comps]
+        ev, spow = np.zeros_like(comps[0]), None
+        for i, c in enumerate(comps):                                                # evaluate c sq
+            spow = sq if i == 1 else (S._mulmod(spow, sq, qs) if i > 1 else None)
+            ev = S._addmod(ev, c if i == 0 else S._mulmod(c, spow, qs), qs)
+        dec = R.l_inv(R.crt_inv(ev))                                                 # uncycDec
+        Q = int(np.prod([int(q) for q in qs], dtype=object))
+        e = []
+        for row in dec:                                                              # lift over the product modulus, reduce mod p
+            x = sum(int(r) * (Q // q) * pow(Q // q, -1, q) for r, q in zip(row, qs)) % Q
+            e.append((x if 2 * x < Q else x - Q) % P)
+        e = np.asarray(e, dtype=np.int64).reshape(-1, 1)
+        for _ in range(ct["k"]):                                                     # iterate divG' e !! k
+            e, ok = self.ref.tensorGInvDecRq(e, self.pe, [P])
+            assert ok == 1
+            e = e.reshape(-1, 1)
+        return (e[:, 0] * l) % P
+
+    def plain_product(self, a_dec, b_dec):
+        """pt1 * pt2 in R_p, Dec-basis coefficients: exact integer product through the CRT of a large prime."""
+        B = Ring(self.ref, M, [BIGQ])
+        to_pow = lambda z: self.ref.tensorLR(np.asarray(z, dtype=np.int64).reshape(-1, 1), self.pe).reshape(-1, 1)
+        prod = B.crt_inv(S._mulmod(B.crt(to_pow(a_dec) % BIGQ), B.crt(to_pow(b_dec) % BIGQ), [BIGQ]))
+        prod = W.lift(prod, [BIGQ])
+        return self.ref.tensorLInvR(prod, self.pe).reshape(-1) % P
+
+
+@pytest.fixture()
+def scheme(reference):
+    return Scheme(reference, np.random.default_rng(2024))
+
+
+def test_prop_encDec(scheme):
+    for _ in range(3):
+        pt = scheme.rng.integers(0, P, size=scheme.n)
+        assert np.array_equal(scheme.decrypt(scheme.encrypt(pt)), pt)
+        assert np.array_equal(scheme.decrypt(scheme.to_msd(scheme.encrypt(pt))), pt)
+
+
+def test_prop_ctmul_quadratic_ciphertext(scheme):
+    """(*) on CT (SymmSHE.hs:443-449) = oracle/symmshe.ct_mul_crt: the degree-2 product decrypts to pt1 * pt2 with k = 1."""
+    pt1, pt2 = scheme.rng.integers(0, P, size=scheme.n), scheme.rng.integers(0, P, size=scheme.n)
+    ct1, ct2 = scheme.encrypt(pt1), scheme.encrypt(pt2)
+    prod = {"enc": "LSD", "k": 1, "l": 1, "c": S.ct_mul_crt(ct1["c"], ct2["c"], scheme.g, QS)}
+    assert np.array_equal(scheme.decrypt(prod), scheme.plain_product(pt1, pt2))
+
+
+@pytest.mark.parametrize("base", [0, 2, 16], ids=["TrivGad", "BaseBGad2", "BaseBGad16"])
+def test_prop_ksQuad(scheme, base):
+    """keySwitchQuadCirc hint (ct1 * ct2) through oracle/symmshe.mul_and_switch decrypts to pt1 * pt2."""
+    pt1, pt2 = scheme.rng.integers(0, P, size=scheme.n), scheme.rng.integers(0, P, size=scheme.n)
+    ct1, ct2 = scheme.encrypt(pt1), scheme.to_msd(scheme.encrypt(pt2))             # LSD * MSD -> MSD: toMSD inside the switch is id
+    hint = scheme.ks_quad_circ_hint(base)
+    assert hint.shape == (S.gadget_length(QS, base), 2, scheme.n, scheme.k)
+    pow_ = lambda ct: [scheme.R.crt_inv(c) for c in ct["c"]]
+    out = S.mul_and_switch(scheme.ref, pow_(ct1), pow_(ct2), hint, scheme.tables, QS, base)
+    lin = {"enc": "MSD", "k": ct1["k"] + ct2["k"] + 1, "l": ct1["l"] * ct2["l"] % P, "c": out}
+    assert np.array_equal(scheme.decrypt(lin), scheme.plain_product(pt1, pt2))
+    # a wrong hint must NOT decrypt (the test has teeth)
+    bad = hint.copy()
+    bad[0, 0] = scheme.uniform()
+    out_bad = S.mul_and_switch(scheme.ref, pow_(ct1), pow_(ct2), bad, scheme.tables, QS, base)
+    assert not np.array_equal(scheme.decrypt({**lin, "c": out_bad}), scheme.plain_product(pt1, pt2))
+
+
+@pytest.mark.parametrize("drop", [0, 1])
+def test_mod_switch_keeps_the_plaintext(scheme, drop):
+    """modSwitch (SymmSHE.hs:236-248): rescaleDec on c0, rescalePow on c1 with the limb-drop instance
+    (oracle/coeffwise.rescale_drop); the ciphertext over the remaining modulus decrypts to the same plaintext."""
+    pt = scheme.rng.integers(0, P, size=scheme.n)
+    ct = scheme.to_msd(scheme.encrypt(pt))
+    keep = [q for t, q in enumerate(QS) if t != drop]
+    Rk = Ring(scheme.ref, M, keep)
+    c0_dec = scheme.R.l_inv(scheme.R.crt_inv(ct["c"][0]))
+    c1_pow = scheme.R.crt_inv(ct["c"][1])
+    c0 = Rk.crt(Rk.l(W.rescale_drop(c0_dec, QS, drop)))                             # rescaleDec c0
+    c1 = Rk.crt(W.rescale_drop(c1_pow, QS, drop))                                   # rescalePow c1
+    assert np.array_equal(scheme.decrypt({"enc": "MSD", "k": 0, "l": ct["l"], "c": [c0, c1]}, keep), pt)
