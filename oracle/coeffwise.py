@@ -10,7 +10,8 @@ Bit-level parity with a reference run is UNPINNED: these are Haskell closures an
 restatement is anchored by the identities tests/test_oracle_coeffwise.py checks with independent big-integer arithmetic
 (exact division after removing the centred remainder; nearest rounding of q'/q * lift x; the coset property of
 roundCoset) and, semantically, by tests/test_oracle_symmshe_scheme.py: `round_coset` produces the encryption error
-(errorCoset), `lift` the decryption, and `rescale_drop` the ciphertext modulus switch (modSwitch, SymmSHE.hs:236-248),
+(errorCoset), `lift` the decryption, `rescale_mod` the plaintext rescale of prop_modSwPT (SHETests.hs:179-189), and
+`rescale_drop` the ciphertext modulus switch (modSwitch, SymmSHE.hs:236-248),
 with the compiled reference doing every ring transform -- the switched ciphertext must still decrypt to the plaintext.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
 """
 from __future__ import annotations

@@ -1,5 +1,5 @@
 """CPU suite: pin oracle/symmshe.py and oracle/coeffwise.py through the reference's own SymmSHE test properties
-(lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs): prop_encDec (:172-177), prop_ctmul (:148-158), prop_ksQuad (:200-209),
+(lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs): prop_encDec (:172-177), prop_ctmul (:148-158), prop_ksQuad (:200-209), prop_modSwPT (:179-189),
 plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
 
 The scheme around the restated steps -- encrypt, ksQuadCircHint, toMSD / toLSD, decryptUnrestricted -- is restated here
@@ -21,8 +21,8 @@ BIGQ = 2148249601                               # 21 | BIGQ - 1: exact integer r
 
 
 class Scheme:
-    def __init__(self, reference, rng):
-        self.ref, self.rng = reference, rng
+    def __init__(self, reference, rng, p=P):
+        self.ref, self.rng, self.p = reference, rng, p
         self.R = Ring(reference, M, QS)
         self.n, self.k = self.R.n, len(QS)
         self.pe = T.pe_array(M)
@@ -45,13 +45,13 @@ class Scheme:
 
     def small_error(self):
         """errorRounded (UCyc.hs:427-429): round of a Gaussian in the decoding basis."""
-        return W.round_coset(self.rng.standard_normal((self.n, 1)) * 1.5, None, [P])[:, 0]
+        return W.round_coset(self.rng.standard_normal((self.n, 1)) * 1.5, None, [self.p])[:, 0]
 
     # -- SymmSHE.hs:131-141
     def encrypt(self, pt_dec):
-        gauss = self.rng.standard_normal((self.n, 1)) * 1.5 * P                     # tGaussian (svar p^2), UCyc.hs:443
-        e_dec = W.round_coset(gauss, np.asarray(pt_dec, dtype=np.int64).reshape(-1, 1), [P])[:, 0]   # roundCoset <$> c <*> err
-        assert np.array_equal(e_dec % P, np.asarray(pt_dec) % P)
+        gauss = self.rng.standard_normal((self.n, 1)) * 1.5 * self.p                     # tGaussian (svar p^2), UCyc.hs:443
+        e_dec = W.round_coset(gauss, np.asarray(pt_dec, dtype=np.int64).reshape(-1, 1), [self.p])[:, 0]   # roundCoset <$> c <*> err
+        assert np.array_equal(e_dec % self.p, np.asarray(pt_dec) % self.p)
         c1 = self.uniform()
         c0 = self.add(self.R.crt(self.dec_to_pow(e_dec)), self.neg(self.mul(c1, self.sq_crt)))
         return {"enc": "LSD", "k": 0, "l": 1, "c": [c0, c1]}                       # CRT-basis components
@@ -61,10 +61,10 @@ class Scheme:
         if ct["enc"] == "MSD":
             return ct
         qprod = int(np.prod([int(q) for q in QS], dtype=object))       # zpScale = -q mod p (ZqBasic.hs:135-137; Prelude.hs:311-315)
-        return {"enc": "MSD", "k": ct["k"], "l": ct["l"] * (-qprod) % P, "c": [self.scal_inv_p(c) for c in ct["c"]]}
+        return {"enc": "MSD", "k": ct["k"], "l": ct["l"] * (-qprod) % self.p, "c": [self.scal_inv_p(c) for c in ct["c"]]}
 
     def scal_inv_p(self, a):
-        w = np.asarray([pow(P, -1, q) for q in QS], dtype=np.int64)      # zqScale = recip (reduce p), limb by limb
+        w = np.asarray([pow(self.p, -1, q) for q in QS], dtype=np.int64)      # zqScale = recip (reduce p), limb by limb
         return S._mulmod(a, np.broadcast_to(w, a.shape), QS)
 
     # -- SymmSHE.hs:259-287: ksHint sk (s*s) with lweSample; hint [ell, 2, n, k] in the CRT basis
@@ -79,8 +79,9 @@ class Scheme:
         return np.asarray(hint, dtype=np.int64)
 
     # -- SymmSHE.hs:199-206 (decryptUnrestricted), for a polynomial of any degree over the limbs qs
-    def decrypt(self, ct, qs=None):
+    def decrypt(self, ct, qs=None, p=None):
         qs = QS if qs is None else qs
+        P = self.p if p is None else p                                               # plaintext modulus of this ciphertext
         R = self.R if qs == QS else Ring(self.ref, M, qs)
         sq = self.sq_crt if qs == QS else R.crt(R.l(S.reduce_digit(self.s_dec, qs)))
         l = ct["l"]
@@ -113,7 +114,7 @@ class Scheme:
         to_pow = lambda z: self.ref.tensorLR(np.asarray(z, dtype=np.int64).reshape(-1, 1), self.pe).reshape(-1, 1)
         prod = B.crt_inv(S._mulmod(B.crt(to_pow(a_dec) % BIGQ), B.crt(to_pow(b_dec) % BIGQ), [BIGQ]))
         prod = W.lift(prod, [BIGQ])
-        return self.ref.tensorLInvR(prod, self.pe).reshape(-1) % P
+        return self.ref.tensorLInvR(prod, self.pe).reshape(-1) % self.p
 
 
 @pytest.fixture()
@@ -167,3 +168,23 @@ def test_mod_switch_keeps_the_plaintext(scheme, drop):
     c0 = Rk.crt(Rk.l(W.rescale_drop(c0_dec, QS, drop)))                             # rescaleDec c0
     c1 = Rk.crt(W.rescale_drop(c1_pow, QS, drop))                                   # rescalePow c1
     assert np.array_equal(scheme.decrypt({"enc": "MSD", "k": 0, "l": ct["l"], "c": [c0, c1]}, keep), pt)
+
+
+def test_prop_modSwPT(reference):
+    """SHETests.hs:179-189: z = (p/p') * ct; modSwitchPT z decrypts (mod p') to rescaleCyc Dec (decrypt z) -- pins
+    oracle/coeffwise.rescale_mod (the `Rescale (ZqBasic p) (ZqBasic p')` instance = rescaleMod, Prelude.hs:143-153)."""
+    p, p2 = 25, 5
+    sch = Scheme(reference, np.random.default_rng(7), p)
+    for _ in range(3):
+        pt = sch.rng.integers(0, p, size=sch.n)
+        y = sch.encrypt(pt)
+        # (fromIntegral (p `div` p')) * y : a CT product with the constant ciphertext CT LSD 0 one [c] (SymmSHE.hs:436-449)
+        w = np.asarray([(p // p2) % q for q in QS], dtype=np.int64)
+        comps = [S._mulmod(S._mulmod(c, np.broadcast_to(w, c.shape), QS), sch.g, QS) for c in y["c"]]
+        z = {"enc": "LSD", "k": 1, "l": 1, "c": comps}
+        x = sch.decrypt(z)
+        assert np.array_equal(x, (p // p2) * pt % p)
+        zm = sch.to_msd(z)
+        l2 = int(W.reduce(W.lift(np.asarray([[zm["l"]]]), [p]), [p2])[0, 0])        # modSwitchPT: reduce (lift l)
+        x2 = sch.decrypt({**zm, "l": l2}, p=p2)
+        assert np.array_equal(x2, W.rescale_mod(x.reshape(-1, 1), [p], [p2])[:, 0])
