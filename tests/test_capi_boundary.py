@@ -113,3 +113,31 @@ def test_factored_matches_oracle_tables():
         assert factored.value_hat(m) == T.value_hat(m)
         assert factored.radical_fact(m) == T.radical(m)
         assert factored.odd_radical_fact(m) == T.odd_radical(m)
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary must be bindable from a C / Haskell FFI: include/lol_b200.h compiles as strict C99 on its own."""
+    src = tmp_path / "h.c"
+    src.write_text('#include "lol_b200.h"\nint main(void) { return LOLB_EXT_TABLES + LOLB_RING_C + LOLB_ERR_NO_CRT; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_extension_and_coefficient_entry_points_reject_null_handles(libpath):
+    """No device needed: the argument checks of the §8f entry points come before any CUDA call."""
+    import ctypes as C
+    from lol_b200 import capi
+    L = capi.lib()
+    h = C.c_void_p()
+    assert L.lolb_ext_create(C.byref(h), None, None) == capi.LOLB_ERR_ARG and not h.value
+    for name in ("lolb_twacePowDec", "lolb_embedPow", "lolb_embedDec", "lolb_embedCRT", "lolb_coeffsPowDec", "lolb_twaceCRT"):
+        assert getattr(L, name)(None, C.c_int(0), None, None, C.c_int64(1), None) == capi.LOLB_ERR_ARG, name
+    assert L.lolb_liftRq(None, None, None, C.c_int64(1), None) == capi.LOLB_ERR_ARG
+    assert L.lolb_reduceRq(None, None, C.c_int(1), None, C.c_int64(1), None) == capi.LOLB_ERR_ARG
+    assert L.lolb_rescaleDropRq(None, C.c_int(0), None, None, C.c_int64(1), None) == capi.LOLB_ERR_ARG
+    assert L.lolb_rescaleModRq(None, None, None, None, C.c_int64(1), None) == capi.LOLB_ERR_ARG
+    assert L.lolb_roundCosetRq(None, None, None, None, C.c_int64(1), None) == capi.LOLB_ERR_ARG
+    assert "plan" in capi.last_error() or "NULL" in capi.last_error()
+    L.lolb_ext_destroy(None)                                   # destroying nothing is a no-op
+    assert capi.lib().lolb_ext_totient(None, 0) == 0
