@@ -189,6 +189,44 @@ def time_op(torch, fn, iters):
     return s.elapsed_time(e) / iters
 
 
+def ext_section(torch, capi, peak, stream):
+    """SURVEY.md section 8f ranks 2-3, device-resident and informational: the ring-extension gathers of O_14400 / O_576 and
+    the coefficient-wise maps at the configs[3] moduli (same shapes and byte accounting as tools/run_ext.py,
+    DESIGN.md 4.7 / 4.8).  Never lets a failure reach the headline line: the caller records the error text instead."""
+    from lol_b200.extension import CudaExtension
+    from lol_b200.tensor import CudaTensorRq
+    m, m2, qs, Be = 576, 14400, [1008001, 1065601], 16384
+    lo, hi = CudaTensorRq(m, qs), CudaTensorRq(m2, qs)
+    ext = CudaExtension(lo, hi)
+    k, phi, phi2 = ext.k, ext.phi, ext.phi2
+    q = torch.tensor(qs, device="cuda", dtype=torch.int64)
+    xe = torch.randint(0, 2**40, (Be, phi, k), device="cuda", dtype=torch.int64) % q
+    ye = torch.randint(0, 2**40, (Be, phi2, k), device="cuda", dtype=torch.int64) % q
+    ox, oy, oi = torch.empty_like(xe), torch.empty_like(ye), torch.empty_like(ye)
+    od = torch.empty((Be, phi2, k - 1), device="cuda", dtype=torch.int64)
+    ee = torch.randn((Be, phi2, k), device="cuda", dtype=torch.float64) * 1e4
+    P = hi.plan
+    op = lambda name, src, dst: (lambda: capi.check(ext.ext.op(name, capi.RING_RQ, src.data_ptr(), dst.data_ptr(), Be, stream)))
+    ops = {  # name: (launch, 8-byte words read + written per ring element)
+        "twacePowDec (100 MB working set: L2-resident)": (op("twacePowDec", ye, ox), 2 * phi * k),
+        "embedPow": (op("embedPow", xe, oy), (phi + phi2) * k), "embedDec": (op("embedDec", xe, oy), (phi + phi2) * k),
+        "embedCRT": (op("embedCRT", xe, oy), (phi + phi2) * k), "coeffsPowDec": (op("coeffsPowDec", ye, oy), 2 * phi2 * k),
+        "twaceCRT": (op("twaceCRT", ye, ox), (phi2 + phi) * k),
+        "liftRq": (lambda: capi.check(P.lift(ye.data_ptr(), oi.data_ptr(), Be, stream)), 2 * phi2 * k),
+        "reduceRq": (lambda: capi.check(P.reduce(oi.data_ptr(), k, oy.data_ptr(), Be, stream)), 2 * phi2 * k),
+        "rescaleDropRq": (lambda: capi.check(P.rescale_drop(0, ye.data_ptr(), od.data_ptr(), Be, stream)), phi2 * (2 * k - 1)),
+        "rescaleModRq": (lambda: capi.check(P.rescale_mod(qs[::-1], ye.data_ptr(), oi.data_ptr(), Be, stream)), 2 * phi2 * k),
+        "roundCosetRq": (lambda: capi.check(P.round_coset(ee.data_ptr(), ye.data_ptr(), oi.data_ptr(), Be, stream)), 3 * phi2 * k),
+    }
+    res = {"workload": f"m={m} | m'={m2}, q=(1008001,1065601), {Be} elements of O_m' (1 GiB) resident in HBM"}
+    for name, (fn, words) in ops.items():
+        fn(); fn(); fn()
+        ms = time_op(torch, fn, 10)
+        gbs = words * 8 * Be / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "elems_per_s": Be / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak}
+    return res
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -427,6 +465,12 @@ def run_gpu_arm(args):
         x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
     if she_res is not None:
         other["configs[3]: SymmSHE ciphertext multiply + key switch"] = she_res
+    if not args.no_per_op and world == 1:
+        try:
+            other["ring extensions + coefficient-wise maps (SURVEY 8f ranks 2-3)"] = ext_section(torch, capi, peak, stream)
+        except Exception as exc:      # informational section: never take the headline line down with it
+            other["ring extensions + coefficient-wise maps (SURVEY 8f ranks 2-3)"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
 
     cpu_base = None
     if world == 1 and not args.no_cpu:
