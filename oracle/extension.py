@@ -15,6 +15,9 @@ COMPILED reference (`oracle/_ref/libctensor_ref.so`) supplying crt / crtInv / l 
     twace (mhat'/g') == mhat * (phi'/phi) / g   in Pow, Dec and CRT     (prop_twace_invar1_*)
     twace preserves scalars                                             (prop_twace_invar2_*)
 
+and, inside a small SymmSHE, through prop_cttwace / prop_ctembed of lol-apps' SHETests.hs:211-226
+(tests/test_oracle_symmshe_scheme.py).
+
 Arrays are one ring element in the ABI layout [phi][k] (int64 residues, int64, double or complex128).
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
 """

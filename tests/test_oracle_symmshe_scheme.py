@@ -1,6 +1,6 @@
 """CPU suite: pin oracle/symmshe.py and oracle/coeffwise.py through the reference's own SymmSHE test properties
 (lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs): prop_encDec (:172-177), prop_ctmul (:148-158), prop_ksQuad (:200-209), prop_modSwPT (:179-189),
-plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
+prop_ctembed / prop_cttwace (:211-226), plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
 
 The scheme around the restated steps -- encrypt, ksQuadCircHint, toMSD / toLSD, decryptUnrestricted -- is restated here
 from lol-apps/Crypto/Lol/Applications/SymmSHE.hs (:131-141, :199-206, :222-232, :259-287, :346-372) for m = m', with
@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import coeffwise as W
+from oracle import extension as X
 from oracle import symmshe as S
 from oracle import tables as T
 from test_oracle_extension import Ring
@@ -21,16 +22,16 @@ BIGQ = 2148249601                               # 21 | BIGQ - 1: exact integer r
 
 
 class Scheme:
-    def __init__(self, reference, rng, p=P):
-        self.ref, self.rng, self.p = reference, rng, p
-        self.R = Ring(reference, M, QS)
+    def __init__(self, reference, rng, p=P, m=M, s_dec=None):
+        self.ref, self.rng, self.p, self.m = reference, rng, p, m
+        self.R = Ring(reference, m, QS)
         self.n, self.k = self.R.n, len(QS)
-        self.pe = T.pe_array(M)
-        self.g = T.g_crt_vectors(M, QS)[0]
+        self.pe = T.pe_array(m)
+        self.g = T.g_crt_vectors(m, QS)[0]
         self.tables = (self.pe, self.R.ru, self.R.rui, self.R.mh, self.g)
         self.q = np.asarray(QS, dtype=np.int64)
         # genSK (SymmSHE.hs:118-121): errorRounded -> small integers in the decoding basis
-        self.s_dec = rng.integers(-1, 2, size=self.n)
+        self.s_dec = rng.integers(-1, 2, size=self.n) if s_dec is None else np.asarray(s_dec, dtype=np.int64)
         self.sq_crt = self.R.crt(self.dec_to_pow(self.s_dec))
 
     # -- helpers over R_q (ABI arrays [n, k])
@@ -82,7 +83,7 @@ class Scheme:
     def decrypt(self, ct, qs=None, p=None):
         qs = QS if qs is None else qs
         P = self.p if p is None else p                                               # plaintext modulus of this ciphertext
-        R = self.R if qs == QS else Ring(self.ref, M, qs)
+        R = self.R if qs == QS else Ring(self.ref, self.m, qs)
         sq = self.sq_crt if qs == QS else R.crt(R.l(S.reduce_digit(self.s_dec, qs)))
         l = ct["l"]
         comps = ct["c"]
@@ -110,7 +111,7 @@ class Scheme:
 
     def plain_product(self, a_dec, b_dec):
         """pt1 * pt2 in R_p, Dec-basis coefficients: exact integer product through the CRT of a large prime."""
-        B = Ring(self.ref, M, [BIGQ])
+        B = Ring(self.ref, self.m, [BIGQ])
         to_pow = lambda z: self.ref.tensorLR(np.asarray(z, dtype=np.int64).reshape(-1, 1), self.pe).reshape(-1, 1)
         prod = B.crt_inv(S._mulmod(B.crt(to_pow(a_dec) % BIGQ), B.crt(to_pow(b_dec) % BIGQ), [BIGQ]))
         prod = W.lift(prod, [BIGQ])
@@ -188,3 +189,24 @@ def test_prop_modSwPT(reference):
         l2 = int(W.reduce(W.lift(np.asarray([[zm["l"]]]), [p]), [p2])[0, 0])        # modSwitchPT: reduce (lift l)
         x2 = sch.decrypt({**zm, "l": l2}, p=p2)
         assert np.array_equal(x2, W.rescale_mod(x.reshape(-1, 1), [p], [p2])[:, 0])
+
+
+@pytest.mark.parametrize("m,m2", [(3, 21), (7, 21), (1, 21)])
+def test_prop_cttwace_and_prop_ctembed(reference, m, m2):
+    """SHETests.hs:211-226 with r = r' = m', s = s' = m: twaceCT (SymmSHE.hs:497-503) of a ciphertext under embedSK sk decrypts
+    under sk to twace pt, and embedCT (:471-479) of a ciphertext under sk decrypts under embedSK sk to embed pt -- the
+    restated twaceCRT / embedCRT / embedDec / twacePowDec (oracle/extension.py) inside the scheme, compiled reference
+    transforms in both rings."""
+    rng = np.random.default_rng(100 * m + m2)
+    info = X.ExtInfo(m, m2)
+    small = Scheme(reference, rng, P, m)                                             # sk in O_m
+    big = Scheme(reference, rng, P, m2, s_dec=X.embed_dec(info, small.s_dec.reshape(-1, 1))[:, 0])    # embedSK: same key in O_m'
+    for _ in range(2):
+        pt = rng.integers(0, P, size=big.n)
+        ct = big.encrypt(pt)
+        tw = {"enc": "LSD", "k": 0, "l": 1, "c": [X.twace_crt_zq(info, c, QS) for c in ct["c"]]}
+        assert np.array_equal(small.decrypt(tw), X.twace_powdec(info, pt.reshape(-1, 1))[:, 0])
+        pt = rng.integers(0, P, size=small.n)
+        ct = small.encrypt(pt)
+        em = {"enc": "LSD", "k": 0, "l": 1, "c": [X.embed_crt(info, c) for c in ct["c"]]}
+        assert np.array_equal(big.decrypt(em), X.embed_dec(info, pt.reshape(-1, 1), [P])[:, 0])
