@@ -5,7 +5,7 @@ and of the operators `lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Extension.hs:54-1
 (embedPow', embedDec', embedCRT', twacePowDec', twaceCRT', coeffs').  Those operators are Haskell
 code; no GHC exists in this container, so this restatement cannot be run against the reference
 binary directly.  It is pinned instead through the reference's own two-index properties
-(`lol/Crypto/Lol/Tests/TensorTests.hs:133-215`), evaluated in tests/test_oracle_pinning.py with the
+(`lol/Crypto/Lol/Tests/TensorTests.hs:133-215`), evaluated in tests/test_oracle_extension.py with the
 COMPILED reference (`oracle/_ref/libctensor_ref.so`) supplying crt / crtInv / l / lInv / divG:
 
     twacePowDec . embedPow == id,  twacePowDec . embedDec == id         (prop_trem_pow, prop_trem_dec)
