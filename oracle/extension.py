@@ -14,6 +14,7 @@ COMPILED reference (`oracle/_ref/libctensor_ref.so`) supplying crt / crtInv / l 
     twaceCRT  == crt . twacePowDec . crtInv                             (prop_twace_crt)
     twace (mhat'/g') == mhat * (phi'/phi) / g   in Pow, Dec and CRT     (prop_twace_invar1_*)
     twace preserves scalars                                             (prop_twace_invar2_*)
+    x == sum_k embed(coeffs x)_k * powBasis_k                           (prop_coeffsBasis, CycTests.hs:71-76)
 
 and, inside a small SymmSHE, through prop_cttwace / prop_ctembed of lol-apps' SHETests.hs:211-226
 (tests/test_oracle_symmshe_scheme.py).

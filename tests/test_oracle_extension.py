@@ -194,3 +194,23 @@ def test_library_host_index_tables_sweep_all_divisor_pairs():
                             (capi.EXT_BASE_POW_J0, info.base_pow_j0), (capi.EXT_BASE_DEC, dec),
                             (capi.EXT_INDICES_COEFFS, info.ext_coeffs.reshape(-1))):
             assert np.array_equal(capi.ext_index_table(pps, pps2, which), want), (m, m2, which)
+
+
+@pytest.mark.parametrize("m,m2,qs", [p for p in TWO_INDEX_PARAMS if p[1] > 1], ids=[i for i, p in zip(IDS, TWO_INDEX_PARAMS) if p[1] > 1])
+def test_prop_coeffsBasis(reference, m, m2, qs):
+    """lol/Crypto/Lol/Tests/CycTests.hs:71-76: x == sum_k embed(coeffs x)_k * b_k over the powerful extension basis b
+    (powBasisPow', Extension.hs:131-141), the products taken in O_m' through the compiled reference's CRT."""
+    rng = np.random.default_rng(3 * m + m2)
+    info = X.ExtInfo(m, m2)
+    hi = Ring(reference, m2, qs)
+    x = zq_input(rng, info.phi2, qs)
+    q = np.asarray(qs, dtype=object)
+    acc = np.zeros((info.phi2, len(qs)), dtype=object)
+    cs = X.coeffs_powdec(info, x)
+    for k in range(info.rel):
+        b = np.zeros((info.phi2, len(qs)), dtype=np.int64)
+        b[(info.base_pow_j0 == k) & (info.base_pow_j1 == 0)] = 1            # powBasisPow': one where (j0, j1) == (k, 0)
+        assert b.sum() == len(qs)
+        prod = hi.crt(X.embed_pow(info, cs[k])).astype(object) * hi.crt(b).astype(object) % q
+        acc = (acc + prod) % q
+    assert np.array_equal(hi.crt_inv(acc.astype(np.int64)), x)
