@@ -95,6 +95,44 @@ struct OpRescaleDrop {
   }
 };
 
+// Tuning variant (-DLOLB_COEFF_FAST=1, tools/build_variant.py; NOT the default build, not yet measured): the limb drop in
+// 32-bit arithmetic for canonical inputs.  reduce(lift x_d) = (x_d mod q_t) - [2 x_d >= q_d] (q_d mod q_t)  (mod q_t), with
+// x_d mod q_t from a 32-bit Barrett quotient (mu >> 32), and the product with the constant q_d^-1 by Shoup's method
+// (w' = floor(w 2^32 / q_t)): 4 multiply-adds per word instead of three 64-bit Barrett steps.
+#ifndef LOLB_COEFF_FAST
+#define LOLB_COEFF_FAST 0
+#endif
+struct OpRescaleDropFast {
+  const long long* x; long long* y; int k; int d; ZqConsts Z;      // Z.scale[t] = w = q_d^-1 mod q_t
+  uint32_t dm[kMaxLimbs];                                           // q_d mod q_t
+  uint32_t shoup[kMaxLimbs];                                        // floor(w 2^32 / q_t)
+  typedef longlong2 In;
+  __device__ int period() const { return k - 1; }
+  __device__ int limb(int u) const { return u < d ? u : u + 1; }
+  __device__ In load(int64_t g, int u) const { return make_longlong2(__ldg(x + g * k + limb(u)), __ldg(x + g * k + d)); }
+  __device__ void apply(int64_t g, int u, In v) const
+  {
+    const int t = limb(u);
+    const uint32_t qt = Z.q[t], qd = Z.q[d];
+    const uint32_t xt = (uint32_t)canon64(v.x, qt, Z.mu[t]);
+    const uint32_t c = (uint32_t)canon64(v.y, qd, Z.mu[d]);
+    // r = c mod q_t: quotient estimate from the top half of mu, at most two corrections
+    const uint32_t qh = (uint32_t)(((uint64_t)c * (uint32_t)(Z.mu[t] >> 32)) >> 32);
+    uint64_t r = (uint64_t)c - (uint64_t)qh * qt;
+    if (r >= qt) r -= qt;
+    if (r >= qt) r -= qt;
+    if (r >= qt) r -= qt;
+    uint32_t zr = (uint32_t)r;                                      // reduce(lift x_d)
+    if (2 * (uint64_t)c >= qd) zr = zr >= dm[t] ? zr - dm[t] : zr + (qt - dm[t]);
+    const uint32_t diff = xt >= zr ? xt - zr : xt + (qt - zr);      // x_t - reduce z
+    // diff * w mod q_t, w constant: Shoup
+    const uint32_t sh = (uint32_t)(((uint64_t)diff * shoup[t]) >> 32);
+    uint64_t o = (uint64_t)diff * Z.scale[t] - (uint64_t)sh * qt;   // in [0, 2 q_t)
+    if (o >= qt) o -= qt;
+    __stcs(y + g * (k - 1) + u, (long long)o);
+  }
+};
+
 struct OpRescaleMod {
   const long long* x; long long* y; int k; ZqConsts Z; uint32_t q2[kMaxLimbs];
   typedef long long In;
@@ -193,12 +231,20 @@ extern "C" int lolb_rescaleDropRq(const lolb_plan* plan, int drop, const hInt_t*
   if (rc) return rc;
   if (plan->k < 2 || drop < 0 || drop >= plan->k) { set_error("lolb_rescaleDropRq: needs tupSize >= 2 and 0 <= drop < tupSize"); return LOLB_ERR_ARG; }
   if ((const void*)x == (const void*)y && batch > 0) { set_error("lolb_rescaleDropRq: operands must not alias"); return LOLB_ERR_ARG; }
+#if LOLB_COEFF_FAST
+  OpRescaleDropFast op{(const long long*)x, (long long*)y, plan->k, drop, plan->zq_plain, {}, {}};
+#else
   OpRescaleDrop op{(const long long*)x, (long long*)y, plan->k, drop, plan->zq_plain};
+#endif
   for (int t = 0; t < plan->k; t++) {
     if (t == drop) continue;
     const int64_t inv = mod_inverse(plan->qs[t], plan->qs[drop] % plan->qs[t]);      // recip (reduce q_d): `Field b`
     if (inv == 0) { set_error("lolb_rescaleDropRq: the dropped modulus is not invertible modulo another limb"); return LOLB_ERR_NOT_INVERTIBLE; }
     op.Z.scale[t] = (uint32_t)inv;
+#if LOLB_COEFF_FAST
+    op.dm[t] = (uint32_t)(plan->qs[drop] % plan->qs[t]);
+    op.shoup[t] = (uint32_t)((((u128)(uint64_t)inv) << 32) / (uint64_t)plan->qs[t]);
+#endif
   }
   return launch(plan, op, batch * plan->n, plan->k - 1, stream, "k_coeff_stream<rescaleDrop>");
 }
