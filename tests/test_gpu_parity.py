@@ -24,7 +24,8 @@ from oracle import tables as T
 pytestmark = pytest.mark.gpu
 
 FLOAT_TOL = 1e-9      # BASELINE.json: "within a stated relative tolerance (e.g. 1e-9)"
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(g for g in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(g).startswith("ext_"))      # ext_*: ring-extension fixtures, tests/test_*_extension.py
 SMALL_GOLDEN = [g for g in GOLDEN if "cfgB" not in g]
 
 

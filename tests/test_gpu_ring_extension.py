@@ -169,3 +169,28 @@ def test_extension_argument_errors(torch_cuda):
     # wrong ring tag / aliasing operands through the raw C ABI
     assert ext.ext.op("embedPow", capi.RING_C, x.data_ptr(), x.data_ptr() + 64, 1) == capi.LOLB_ERR_ARG
     assert ext.ext.op("twacePowDec", capi.RING_RQ, x.data_ptr(), x.data_ptr(), 1) == capi.LOLB_ERR_ARG
+
+
+import glob as _glob
+import os as _os
+
+EXT_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "ext_*.npz")))
+
+
+@pytest.mark.parametrize("path", EXT_GOLDEN, ids=[_os.path.basename(p)[:-4] for p in EXT_GOLDEN])
+def test_extension_matches_reference_derived_golden(torch_cuda, path):
+    """The CUDA operators against tests/golden/ext_*.npz, whose CRT- and Dec-basis vectors were computed by the compiled
+    reference (oracle/make_golden_ext.py)."""
+    torch = torch_cuda
+    from lol_b200.extension import CudaExtension
+    from lol_b200.tensor import CudaTensorRq
+    g = np.load(path)
+    m, m2, qs = int(g["m"]), int(g["m2"]), [int(q) for q in g["qs"]]
+    ext = CudaExtension(CudaTensorRq(m, qs), CudaTensorRq(m2, qs))
+    dx, dy = _dev(torch, g["x_in"]), _dev(torch, g["y_in"])
+    assert np.array_equal(ext.embedPow(dx).cpu().numpy(), g["embedPow"])
+    assert np.array_equal(ext.embedDec(dx).cpu().numpy(), g["embedDec"])
+    assert np.array_equal(ext.embedCRT(dx).cpu().numpy(), g["embedCRT"])
+    assert np.array_equal(ext.twacePowDec(dy).cpu().numpy(), g["twacePowDec"])
+    assert np.array_equal(ext.coeffs(dy).cpu().numpy(), g["coeffs"])
+    assert np.array_equal(ext.twaceCRT(dy).cpu().numpy(), g["twaceCRT"])

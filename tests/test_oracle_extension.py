@@ -214,3 +214,31 @@ def test_prop_coeffsBasis(reference, m, m2, qs):
         prod = hi.crt(X.embed_pow(info, cs[k])).astype(object) * hi.crt(b).astype(object) % q
         acc = (acc + prod) % q
     assert np.array_equal(hi.crt_inv(acc.astype(np.int64)), x)
+
+
+import glob as _glob
+import os as _os
+
+EXT_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "ext_*.npz")))
+
+
+def test_ext_golden_files_present():
+    assert len(EXT_GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", EXT_GOLDEN, ids=[_os.path.basename(p)[:-4] for p in EXT_GOLDEN])
+def test_restatement_matches_reference_derived_golden(path):
+    """tests/golden/ext_*.npz (oracle/make_golden_ext.py): CRT-basis and Dec-basis vectors computed by the COMPILED reference
+    through crt . embedPow . crtInv, crt . twacePowDec . crtInv and lInv . embedPow . l; the direct restatements of
+    embedCRT', twaceCRT' and embedDec' (Extension.hs:71-85, 110-129) must reproduce them bit for bit."""
+    g = np.load(path)
+    m, m2, qs = int(g["m"]), int(g["m2"]), [int(q) for q in g["qs"]]
+    info = X.ExtInfo(m, m2)
+    for b in range(g["x_in"].shape[0]):
+        x, y = g["x_in"][b], g["y_in"][b]
+        assert np.array_equal(X.embed_pow(info, x), g["embedPow"][b])
+        assert np.array_equal(X.embed_dec(info, x, qs), g["embedDec"][b])
+        assert np.array_equal(X.embed_crt(info, x), g["embedCRT"][b])
+        assert np.array_equal(X.twace_powdec(info, y), g["twacePowDec"][b])
+        assert np.array_equal(X.coeffs_powdec(info, y), g["coeffs"][b])
+        assert np.array_equal(X.twace_crt_zq(info, y, qs), g["twaceCRT"][b])

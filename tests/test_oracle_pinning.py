@@ -15,7 +15,8 @@ import pytest
 from conftest import CONFIG_B, NON_CRT_PARAMS, PAPER_PARAMS, REFERENCE_TEST_PARAMS, rel_err, zq_input
 from oracle import tables as T
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(g for g in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(g).startswith("ext_"))      # ext_*: ring-extension fixtures, tests/test_*_extension.py
 SMALL_GOLDEN = [g for g in GOLDEN if "cfgB" not in g]
 FLOAT_TOL = 1e-12   # restatement vs reference, double paths (same formulas, same order)
 
