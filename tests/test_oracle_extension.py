@@ -242,3 +242,26 @@ def test_restatement_matches_reference_derived_golden(path):
         assert np.array_equal(X.twace_powdec(info, y), g["twacePowDec"][b])
         assert np.array_equal(X.coeffs_powdec(info, y), g["coeffs"][b])
         assert np.array_equal(X.twace_crt_zq(info, y, qs), g["twaceCRT"][b])
+
+
+def test_two_index_properties_sweep_all_divisors(reference):
+    """prop_trem_pow / prop_trem_dec / prop_embed_crt / prop_twace_crt / prop_twace_dec for EVERY divisor m of
+    m' in {12, 21, 36, 42, 45, 63, 75, 105, 225}, over the first prime q = 1 (mod m') above 2^20 (goodQs, ZqBasic.hs:71-73),
+    with the compiled reference's crt / crtInv / l / lInv."""
+    count = 0
+    for m2 in (12, 21, 36, 42, 45, 63, 75, 105, 225):
+        q = next(iter(T.good_qs(m2, 1 << 20)))
+        hi = Ring(reference, m2, [q])
+        for m in (d for d in range(1, m2 + 1) if m2 % d == 0):
+            rng = np.random.default_rng(m2 * 1000 + m)
+            info = X.ExtInfo(m, m2)
+            lo = Ring(reference, m, [q])
+            x, y = zq_input(rng, info.phi, [q]), zq_input(rng, info.phi2, [q])
+            assert np.array_equal(X.twace_powdec(info, X.embed_pow(info, x)), x), (m, m2)
+            assert np.array_equal(X.twace_powdec(info, X.embed_dec(info, x, [q])), x), (m, m2)
+            assert np.array_equal(X.embed_crt(info, x), hi.crt(X.embed_pow(info, lo.crt_inv(x)))), (m, m2)
+            assert np.array_equal(X.twace_crt_zq(info, y, [q]), lo.crt(X.twace_powdec(info, hi.crt_inv(y)))), (m, m2)
+            assert np.array_equal(X.twace_powdec(info, y), lo.l_inv(X.twace_powdec(info, hi.l(y)))), (m, m2)
+            assert np.array_equal(X.embed_dec(info, x, [q]), hi.l_inv(X.embed_pow(info, lo.l(x)))), (m, m2)
+            count += 1
+    assert count >= 60
