@@ -141,3 +141,47 @@ def test_extension_and_coefficient_entry_points_reject_null_handles(libpath):
     assert "plan" in capi.last_error() or "NULL" in capi.last_error()
     L.lolb_ext_destroy(None)                                   # destroying nothing is a no-op
     assert capi.lib().lolb_ext_totient(None, 0) == 0
+
+
+def test_extension_mirror_refuses_cpu_tensors_and_maps_no_crt(monkeypatch):
+    """Host logic of lol_b200/extension.py without a device: CPU tensors are refused loudly (no CPU path), the ring tag
+    follows the tensor class, and LOLB_ERR_NO_CRT becomes the reference's `Nothing` (crtExtFuncs, Tensor.hs:176-180)."""
+    import torch
+    from lol_b200 import capi, extension as E
+    from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorRq
+
+    class FakeExt:
+        phi, phi2 = 2, 6
+
+        def __init__(self, lo, hi):
+            self.calls = []
+
+        def op(self, name, ring, x, y, batch, stream=0):
+            self.calls.append((name, ring, batch))
+            return capi.LOLB_ERR_NO_CRT if name in ("embedCRT", "twaceCRT") else capi.LOLB_OK
+
+    monkeypatch.setattr(capi, "Extension", FakeExt)
+    monkeypatch.setattr(capi, "last_error", lambda: "fake")
+
+    def bare(cls, k):
+        t = object.__new__(cls)
+        t.k, t.plan = k, None
+        return t
+
+    for cls, ring, dtype in ((CudaTensorRq, capi.RING_RQ, torch.int64), (CudaTensorInt, capi.RING_R, torch.int64),
+                             (CudaTensorComplex, capi.RING_C, torch.complex128)):
+        ext = E.CudaExtension(bare(cls, 1), bare(cls, 1))
+        assert (ext.ring, ext.dtype, ext.phi, ext.phi2) == (ring, dtype, 2, 6)
+        with pytest.raises(capi.LolB200Error) as ei:
+            ext.embedPow(torch.zeros((1, 2, 1), dtype=dtype))          # a CPU tensor
+        assert ei.value.status == capi.LOLB_ERR_ARG and "no CPU path" in str(ei.value)
+    with pytest.raises(capi.LolB200Error):
+        E.CudaExtension(bare(CudaTensorRq, 1), bare(CudaTensorInt, 1))     # different rings
+    # status mapping, with the device check out of the way
+    monkeypatch.setattr(E, "_require_cuda", lambda x, dtype, n, k: int(x.shape[0]))
+    monkeypatch.setattr(E, "_stream", lambda: 0)
+    ext = E.CudaExtension(bare(CudaTensorRq, 1), bare(CudaTensorRq, 1))
+    x, y = torch.zeros((3, 2, 1), dtype=torch.int64), torch.zeros((3, 6, 1), dtype=torch.int64)
+    assert ext.embedCRT(x) is None and ext.twaceCRT(y) is None
+    assert ext.embedPow(x).shape == (3, 6, 1) and ext.twacePowDec(y).shape == (3, 2, 1) and ext.coeffs(y).shape == (3, 3, 2, 1)
+    assert [c[0] for c in ext.ext.calls] == ["embedCRT", "twaceCRT", "embedPow", "twacePowDec", "coeffsPowDec"]
