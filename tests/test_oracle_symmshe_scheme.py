@@ -1,6 +1,6 @@
 """CPU suite: pin oracle/symmshe.py and oracle/coeffwise.py through the reference's own SymmSHE test properties
 (lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs): prop_encDec (:172-177), prop_ctmul (:148-158), prop_ksQuad (:200-209), prop_modSwPT (:179-189),
-prop_ctembed / prop_cttwace (:211-226), plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
+prop_ksLin (:191-198), prop_ctembed / prop_cttwace (:211-226), plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
 
 The scheme around the restated steps -- encrypt, ksQuadCircHint, toMSD / toLSD, decryptUnrestricted -- is restated here
 from lol-apps/Crypto/Lol/Applications/SymmSHE.hs (:131-141, :199-206, :222-232, :259-287, :346-372) for m = m', with
@@ -210,3 +210,25 @@ def test_prop_cttwace_and_prop_ctembed(reference, m, m2):
         ct = small.encrypt(pt)
         em = {"enc": "LSD", "k": 0, "l": 1, "c": [X.embed_crt(info, c) for c in ct["c"]]}
         assert np.array_equal(big.decrypt(em), X.embed_dec(info, pt.reshape(-1, 1), [P])[:, 0])
+
+
+@pytest.mark.parametrize("base", [0, 4], ids=["TrivGad", "BaseBGad4"])
+def test_prop_ksLin(reference, base):
+    """SHETests.hs:191-198: keySwitchLinear (SymmSHE.hs:333-344) from s_in to s_out with ksHint s_out s_in, built from the
+    restated decompose / reduce / knapsack: c0 + switch hint c1 decrypts under s_out to the same plaintext."""
+    rng = np.random.default_rng(77 + base)
+    sin, sout = Scheme(reference, rng), Scheme(reference, rng)
+    pt = rng.integers(0, P, size=sin.n)
+    ct = sin.to_msd(sin.encrypt(pt))
+    # ksHint skout sin: gadget * s_in + LWE samples under s_out
+    hint = []
+    for gad in S.gadget(QS, base):
+        c1 = sout.uniform()
+        b = sout.add(sout.mul(c1, sout.neg(sout.sq_crt)), sout.R.crt(sout.dec_to_pow(sout.small_error())))
+        hint.append([sout.add(sout.mul(sin.sq_crt, np.broadcast_to(np.asarray(gad, dtype=np.int64), c1.shape)), b), c1])
+    hint = np.asarray(hint, dtype=np.int64)
+    digits = S.decompose_reduced(sin.R.crt_inv(ct["c"][1]), QS, base)                 # fmap reduce <$> decompose c1 (Pow basis)
+    digits_crt = np.stack([sin.R.crt(np.ascontiguousarray(d)) for d in digits])
+    out = S.knapsack(hint, digits_crt, ct["c"][0], np.zeros_like(ct["c"][0]), QS)     # P.const c0 + switch hint c1
+    assert np.array_equal(sout.decrypt({**ct, "c": out}), pt)
+    assert not np.array_equal(sin.decrypt({**ct, "c": out}), pt)                      # and no longer under s_in
