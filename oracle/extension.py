@@ -16,7 +16,7 @@ COMPILED reference (`oracle/_ref/libctensor_ref.so`) supplying crt / crtInv / l 
     twace preserves scalars                                             (prop_twace_invar2_*)
     x == sum_k embed(coeffs x)_k * powBasis_k                           (prop_coeffsBasis, CycTests.hs:71-76)
 
-and, inside a small SymmSHE, through prop_cttwace / prop_ctembed of lol-apps' SHETests.hs:211-226
+and, inside a small SymmSHE, through prop_cttwace / prop_ctembed / prop_ringTunnel of lol-apps' SHETests.hs:211-248
 (tests/test_oracle_symmshe_scheme.py).
 
 Arrays are one ring element in the ABI layout [phi][k] (int64 residues, int64, double or complex128).

@@ -1,6 +1,6 @@
 """CPU suite: pin oracle/symmshe.py and oracle/coeffwise.py through the reference's own SymmSHE test properties
 (lol-apps/Crypto/Lol/Applications/Tests/SHETests.hs): prop_encDec (:172-177), prop_ctmul (:148-158), prop_ksQuad (:200-209), prop_modSwPT (:179-189),
-prop_ksLin (:191-198), prop_ctembed / prop_cttwace (:211-226), plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
+prop_ksLin (:191-198), prop_ctembed / prop_cttwace (:211-226), prop_ringTunnel (:228-248), plus the correctness of modSwitch (SymmSHE.hs:236-248), which the reference's benchmarks exercise but its tests do not.
 
 The scheme around the restated steps -- encrypt, ksQuadCircHint, toMSD / toLSD, decryptUnrestricted -- is restated here
 from lol-apps/Crypto/Lol/Applications/SymmSHE.hs (:131-141, :199-206, :222-232, :259-287, :346-372) for m = m', with
@@ -232,3 +232,64 @@ def test_prop_ksLin(reference, base):
     out = S.knapsack(hint, digits_crt, ct["c"][0], np.zeros_like(ct["c"][0]), QS)     # P.const c0 + switch hint c1
     assert np.array_equal(sout.decrypt({**ct, "c": out}), pt)
     assert not np.array_equal(sin.decrypt({**ct, "c": out}), pt)                      # and no longer under s_in
+
+
+def test_prop_ringTunnel(reference):
+    """SHETests.hs:228-248 with r = r' = 21, s = s' = 15, e = e' = 3: tunnel (SymmSHE.hs:548-572) applies a random E-linear
+    function R -> S homomorphically.  Restated from SymmSHE.hs:520-572 and Linear.hs:65-79, 113-119 on top of
+    oracle/extension.py (coeffs in the Dec and Pow bases, embedDec, embedPow, the powerful extension basis) and
+    oracle/symmshe.py (decompose, knapsack); every transform and ring product by the compiled reference."""
+    p, r, s, e = 2, 21, 15, 3
+    rng = np.random.default_rng(99)
+    skin, skout = Scheme(reference, rng, p, r), Scheme(reference, rng, p, s)
+    ext_r, ext_s = X.ExtInfo(e, r), X.ExtInfo(e, s)
+    nb = ext_r.rel                                                                   # |basis of R/E| = 6
+    bs_p = [rng.integers(0, p, size=skout.n) for _ in range(nb)]                     # linearDec bs: images in S_p (Dec basis)
+
+    # -- plaintext side: expected = evalLin f x = sum_i bs_i * embed (coeffsDec x)_i   (Linear.hs:75-79)
+    x = rng.integers(0, p, size=skin.n)
+    cs = X.coeffs_powdec(ext_r, x.reshape(-1, 1))                                    # [nb, phi(e), 1]
+    expected = np.zeros(skout.n, dtype=np.int64)
+    for i in range(nb):
+        expected = (expected + skout.plain_product(bs_p[i], X.embed_dec(ext_s, cs[i], [p])[:, 0])) % p
+
+    # -- f'q = reduce (extendLin (lift f)): the images mod q, CRT basis of S'
+    Rr, Rs = skin.R, skout.R
+    bs_q = [Rs.crt(skout.dec_to_pow(W.lift(b.reshape(-1, 1), [p])[:, 0])) for b in bs_p]
+
+    def eval_lin_q(c_crt):
+        """evalLin f'q on an element of R'_q given in the CRT basis -> element of S'_q in the CRT basis."""
+        parts = X.coeffs_powdec(ext_r, Rr.l_inv(Rr.crt_inv(c_crt)))                  # coeffsDec: [nb, phi(e), k]
+        acc = np.zeros((skout.n, len(QS)), dtype=np.int64)
+        for i in range(nb):
+            emb = Rs.crt(Rs.l(X.embed_dec(ext_s, parts[i], QS)))
+            acc = S._addmod(acc, S._mulmod(bs_q[i], emb, QS), QS)
+        return acc
+
+    # -- tunnelHint (SymmSHE.hs:520-533): ksHint skout (evalLin f' (sin * p_i)), p_i the powerful basis of R'/E'
+    base, hints = 0, []
+    for i in range(nb):
+        p_i = np.zeros((skin.n, len(QS)), dtype=np.int64)
+        p_i[(ext_r.base_pow_j0 == i) & (ext_r.base_pow_j1 == 0)] = 1
+        val = eval_lin_q(S._mulmod(skin.sq_crt, Rr.crt(p_i), QS))
+        hint = []
+        for gad in S.gadget(QS, base):
+            c1 = skout.uniform()
+            b = skout.add(skout.mul(c1, skout.neg(skout.sq_crt)), Rs.crt(skout.dec_to_pow(skout.small_error())))
+            hint.append([skout.add(skout.mul(val, np.broadcast_to(np.asarray(gad, dtype=np.int64), val.shape)), b), c1])
+        hints.append(np.asarray(hint, dtype=np.int64))
+
+    # -- tunnel (SymmSHE.hs:548-572)
+    ct = skin.to_msd(skin.encrypt(x))
+    c0, c1 = ct["c"]
+    out0 = eval_lin_q(c0)
+    out1 = np.zeros_like(out0)
+    c1s = X.coeffs_powdec(ext_r, Rr.crt_inv(c1))                                     # coeffsPow c1 :: [E'_q]
+    for i in range(nb):
+        emb_pow = X.embed_pow(ext_s, c1s[i])                                         # embed <$> c1s (Pow basis of S')
+        digits = S.decompose_reduced(emb_pow, QS, base)
+        digits_crt = np.stack([Rs.crt(np.ascontiguousarray(d)) for d in digits])
+        out0, out1 = S.knapsack(hints[i], digits_crt, out0, out1, QS)                # zipWith switch hints, summed
+    actual = skout.decrypt({"enc": "MSD", "k": 0, "l": ct["l"], "c": [out0, out1]})
+    assert np.array_equal(actual, expected)
+    assert expected.any()                                                            # not the trivial function
