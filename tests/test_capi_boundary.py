@@ -185,3 +185,36 @@ def test_extension_mirror_refuses_cpu_tensors_and_maps_no_crt(monkeypatch):
     assert ext.embedCRT(x) is None and ext.twaceCRT(y) is None
     assert ext.embedPow(x).shape == (3, 6, 1) and ext.twacePowDec(y).shape == (3, 2, 1) and ext.coeffs(y).shape == (3, 3, 2, 1)
     assert [c[0] for c in ext.ext.calls] == ["embedCRT", "twaceCRT", "embedPow", "twacePowDec", "coeffsPowDec"]
+
+
+def test_coefficient_mirror_shapes_and_tuple_inference(monkeypatch):
+    """Host logic of CudaTensorRq.lift / reduce / rescaleDrop / rescaleMod / roundCoset without a device: output shapes,
+    the z tuple size handed to lolb_reduceRq, and the NULL coset of errorRounded."""
+    import torch
+    from lol_b200 import capi, tensor as Tn
+
+    calls = []
+
+    class FakePlan:
+        def lift(self, x, y, b, st=0): calls.append(("lift", b)); return 0
+        def reduce(self, z, kz, y, b, st=0): calls.append(("reduce", kz, b)); return 0
+        def rescale_drop(self, d, x, y, b, st=0): calls.append(("drop", d, b)); return 0
+        def rescale_mod(self, qn, x, y, b, st=0): calls.append(("mod", tuple(qn), b)); return 0
+        def round_coset(self, e, zp, y, b, st=0): calls.append(("round", bool(zp), b)); return 0
+
+    t = object.__new__(Tn.CudaTensorRq)
+    t.n, t.k, t.qs, t.plan = 4, 2, [17, 29], FakePlan()
+    with pytest.raises(capi.LolB200Error):
+        t.lift(torch.zeros((1, 4, 2), dtype=torch.int64))                   # CPU tensor: no CPU path
+    monkeypatch.setattr(Tn, "_require_cuda", lambda x, dtype, n, k: (_ for _ in ()).throw(AssertionError((x.shape, n, k)))
+                        if tuple(x.shape[1:]) != (n, k) or x.dtype != dtype else int(x.shape[0]))
+    monkeypatch.setattr(Tn, "_stream", lambda: 0)
+    x = torch.zeros((3, 4, 2), dtype=torch.int64)
+    assert t.lift(x).shape == (3, 4, 2)
+    assert t.reduce(torch.zeros((3, 4, 1), dtype=torch.int64)).shape == (3, 4, 2)
+    assert t.reduce(x).shape == (3, 4, 2)
+    assert t.rescaleDrop(x, 1).shape == (3, 4, 1)
+    assert t.rescaleMod(x, [5, 7]).shape == (3, 4, 2)
+    e = torch.zeros((3, 4, 2), dtype=torch.float64)
+    assert t.roundCoset(e).dtype == torch.int64 and t.roundCoset(e, x).shape == (3, 4, 2)
+    assert calls == [("lift", 3), ("reduce", 1, 3), ("reduce", 2, 3), ("drop", 1, 3), ("mod", (5, 7), 3), ("round", False, 3), ("round", True, 3)]
