@@ -22,6 +22,12 @@
  *      device; every operator takes a device pointer to `batch` ring elements
  *      laid out back to back in the reference's element layout and a CUDA
  *      stream, launches asynchronously and returns a status.
+ *      Concurrency: a plan belongs to the device that was current when it was
+ *      created (calls made with another current device return LOLB_ERR_ARG).
+ *      It may be used from several streams and host threads at once: kernels
+ *      that need scratch memory (exchange ring, counters, spilled elements)
+ *      take a workspace private to the stream they are launched on, and calls
+ *      on one stream are ordered by that stream.
  *
  * Element layout (both groups; reference: tensor.h:69,91 and the tuple
  * `Storable` instance at Backend.hs:80-90): coefficient j of RNS limb t of

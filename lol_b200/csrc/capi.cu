@@ -168,9 +168,10 @@ extern "C" void lolb_plan_destroy(lolb_plan* pl)
 {
   if (!pl) return;
   fused_release(pl);
-  void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_ws, pl->d_stage,
-                  pl->ws_alt[0], pl->ws_alt[1], pl->ws_alt[2], pl->d_tab_fwd_m, pl->d_tab_inv_m};
+  void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_stage,
+                  pl->d_tab_fwd_m, pl->d_tab_inv_m};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& w : pl->ws) if (w.p) cudaFree(w.p);
   for (auto& s : pl->streams) if (s) cudaStreamDestroy(s);
   for (auto& e : pl->events) if (e) cudaEventDestroy(e);
   delete pl;
@@ -213,9 +214,19 @@ extern "C" const char* lolb_plan_kernel_name(const lolb_plan* pl, const char* op
 
 // ------------------------------------------------------------------ batched operators
 
+// a plan's tables live on the device that was current when it was created: calls from another device are refused
+static bool plan_device_ok(const lolb_plan* plan, const char* fn)
+{
+  int d = -1;
+  if (cudaGetDevice(&d) == cudaSuccess && d == plan->device) return true;
+  set_error(std::string(fn) + ": plan was created on device " + std::to_string(plan->device) + ", current device is " + std::to_string(d));
+  return false;
+}
+
 #define REQUIRE_PLAN(KIND)                                                                 \
   if (!plan || plan->kind != (KIND)) { set_error(std::string(__func__) + ": wrong or NULL plan"); return LOLB_ERR_ARG; } \
-  if (batch < 0 || (batch > 0 && !y)) { set_error(std::string(__func__) + ": bad batch / NULL data"); return LOLB_ERR_ARG; }
+  if (batch < 0 || (batch > 0 && !y)) { set_error(std::string(__func__) + ": bad batch / NULL data"); return LOLB_ERR_ARG; } \
+  if (!plan_device_ok(plan, __func__)) return LOLB_ERR_ARG;
 
 static int crt_rq(const lolb_plan* plan, bool inverse, hInt_t* y, int64_t batch, void* stream)
 {
@@ -518,14 +529,10 @@ extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t
     hInt_t* host = y + (size_t)done * plan->n * plan->k;
     cudaStream_t st = plan->streams[s];       // stream order makes slot reuse safe
     LOLB_CUDA(cudaMemcpyAsync(dev, host, (size_t)cnt * elem_bytes, cudaMemcpyHostToDevice, st));
-    std::swap(plan->d_ws, plan->ws_alt[s]);                  // this slot's private kernel workspace
-    std::swap(plan->ws_bytes, plan->ws_alt_bytes[s]);
-    for (const std::string& op : names) {
+    for (const std::string& op : names) {      // kernel workspaces are per stream (plan_ws): the slots never share one
       rc = apply_named_rq(plan, op, dev, cnt, st);
       if (rc) break;
     }
-    std::swap(plan->d_ws, plan->ws_alt[s]);
-    std::swap(plan->ws_bytes, plan->ws_alt_bytes[s]);
     if (rc) { cudaDeviceSynchronize(); return rc; }
     LOLB_CUDA(cudaMemcpyAsync(host, dev, (size_t)cnt * elem_bytes, cudaMemcpyDeviceToHost, st));
     done += cnt;
@@ -551,6 +558,9 @@ std::map<std::string, lolb_plan*> g_plans;
 std::string plan_key(int kind, hShort_t k, const PrimeExponent* pe, hShort_t npe, const hInt_t* qs)
 {
   std::string key((const char*)&kind, sizeof(kind));
+  int dev = 0;
+  cudaGetDevice(&dev);                               // plans (tables, staging) are per device
+  key.append((const char*)&dev, sizeof(dev));
   key.append((const char*)&k, sizeof(k));
   if (npe > 0) key.append((const char*)pe, sizeof(PrimeExponent) * (size_t)npe);
   if (qs) key.append((const char*)qs, sizeof(hInt_t) * (size_t)k);

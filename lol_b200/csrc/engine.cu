@@ -428,12 +428,15 @@ struct LaunchShape {
   int grid;
   size_t smem;
   bool use_ws;
+  void* ws;      // the stream's workspace when use_ws
 };
 
 // buffers: how many n-element buffers the kernel keeps; elem_bytes: sizeof(T)
-static int pick_shape(const lolb_plan* pl, const void* kernel, size_t bytes_per_cta, int64_t work_items, LaunchShape* out)
+static int pick_shape(const lolb_plan* pl, const void* kernel, size_t bytes_per_cta, int64_t work_items, cudaStream_t st,
+                      LaunchShape* out, size_t ws_bytes_per_cta = 0)
 {
   out->use_ws = bytes_per_cta > kSmemBudget;
+  out->ws = nullptr;
   out->smem = out->use_ws ? 0 : bytes_per_cta;
   int per_sm = 8;
   if (!out->use_ws && bytes_per_cta > 0) {
@@ -450,8 +453,8 @@ static int pick_shape(const lolb_plan* pl, const void* kernel, size_t bytes_per_
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   }
   if (out->use_ws) {
-    int rc = plan_reserve_ws(pl, (size_t)out->grid * bytes_per_cta);
-    if (rc) return rc;
+    out->ws = plan_ws(pl, st, (size_t)out->grid * (ws_bytes_per_cta ? ws_bytes_per_cta : bytes_per_cta));
+    if (!out->ws) return LOLB_ERR_CUDA;
   }
   return LOLB_OK;
 }
@@ -476,11 +479,10 @@ int engine_crt_zq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, 
   P.zc = inverse ? pl->zq_mhat : pl->zq_plain;
   LaunchShape sh;
   const void* kern = (const void*)k_engine_crt<ZqRing, uint32_t>;
-  int rc = pick_shape(pl, kern, (size_t)pl->n * 4 * (PL.needs_alt ? 2 : 1) * 1, batch * pl->k, &sh);
-  if (rc) return rc;
   // the kernel always addresses two buffers when it uses the workspace
-  if (sh.use_ws) { rc = plan_reserve_ws(pl, (size_t)sh.grid * 2 * pl->n * 4); if (rc) return rc; }
-  P.ws = sh.use_ws ? (uint32_t*)pl->d_ws : nullptr;
+  int rc = pick_shape(pl, kern, (size_t)pl->n * 4 * (PL.needs_alt ? 2 : 1) * 1, batch * pl->k, st, &sh, (size_t)2 * pl->n * 4);
+  if (rc) return rc;
+  P.ws = (uint32_t*)sh.ws;
   k_engine_crt<ZqRing, uint32_t><<<sh.grid, kEngineThreads, sh.smem, st>>>(P, PL);
   return check_launch("k_engine_crt<Zq>");
 }
@@ -497,10 +499,9 @@ int engine_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, c
   for (int i = 0; i < pl->k; i++) P.cscale[i] = pl->c_mhatinv[i];
   LaunchShape sh;
   const void* kern = (const void*)k_engine_crt<C64Ring, double2>;
-  int rc = pick_shape(pl, kern, (size_t)pl->n * 16 * (PL.needs_alt ? 2 : 1), batch * pl->k, &sh);
+  int rc = pick_shape(pl, kern, (size_t)pl->n * 16 * (PL.needs_alt ? 2 : 1), batch * pl->k, st, &sh, (size_t)2 * pl->n * 16);
   if (rc) return rc;
-  if (sh.use_ws) { rc = plan_reserve_ws(pl, (size_t)sh.grid * 2 * pl->n * 16); if (rc) return rc; }
-  P.ws = sh.use_ws ? (double2*)pl->d_ws : nullptr;
+  P.ws = (double2*)sh.ws;
   k_engine_crt<C64Ring, double2><<<sh.grid, kEngineThreads, sh.smem, st>>>(P, PL);
   return check_launch("k_engine_crt<C64>");
 }
@@ -510,9 +511,9 @@ static int launch_line(const lolb_plan* pl, LineParams<R>& P, const PassList& PL
 {
   LaunchShape sh;
   const void* kern = (const void*)k_engine_line<R>;
-  int rc = pick_shape(pl, kern, (size_t)P.n * sizeof(typename R::T), P.batch * P.k, &sh);
+  int rc = pick_shape(pl, kern, (size_t)P.n * sizeof(typename R::T), P.batch * P.k, st, &sh);
   if (rc) return rc;
-  P.ws = sh.use_ws ? (typename R::T*)pl->d_ws : nullptr;
+  P.ws = (typename R::T*)sh.ws;
   k_engine_line<R><<<sh.grid, kEngineThreads, sh.smem, st>>>(P, PL);
   return check_launch(what);
 }
@@ -561,9 +562,9 @@ int engine_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st)
   P.y = y; P.batch = batch; P.n = pl->n; P.k = pl->k;
   P.tab = pl->d_ctab_fwd; P.tab_stride = pl->ctab_stride_fwd;
   LaunchShape sh;
-  int rc = pick_shape(pl, (const void*)k_engine_gauss, (size_t)pl->n * 8 * 2, batch * pl->k, &sh);
+  int rc = pick_shape(pl, (const void*)k_engine_gauss, (size_t)pl->n * 8 * 2, batch * pl->k, st, &sh);
   if (rc) return rc;
-  P.ws = sh.use_ws ? (double*)pl->d_ws : nullptr;
+  P.ws = (double*)sh.ws;
   k_engine_gauss<<<sh.grid, kEngineThreads, sh.smem, st>>>(P, pl->line[PASS_GAUSS]);
   return check_launch("k_engine_gauss");
 }
@@ -575,9 +576,9 @@ static int launch_normsq(const lolb_plan* pl, const typename R::IO* y, typename 
   NormParams<R> P{};
   P.y = y; P.out = out; P.batch = batch; P.n = pl->n; P.k = pl->k;
   LaunchShape sh;
-  int rc = pick_shape(pl, (const void*)k_engine_normsq<R>, (size_t)pl->n * sizeof(typename R::T) * 2, batch * pl->k, &sh);
+  int rc = pick_shape(pl, (const void*)k_engine_normsq<R>, (size_t)pl->n * sizeof(typename R::T) * 2, batch * pl->k, st, &sh);
   if (rc) return rc;
-  P.ws = sh.use_ws ? (typename R::T*)pl->d_ws : nullptr;
+  P.ws = (typename R::T*)sh.ws;
   k_engine_normsq<R><<<sh.grid, kEngineThreads, sh.smem, st>>>(P, pl->line[PASS_NORMSQ]);
   return check_launch("k_engine_normsq");
 }

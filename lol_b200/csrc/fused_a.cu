@@ -218,18 +218,18 @@ __device__ __noinline__ uint32_t reduce_any(int64_t x, uint32_t q)
 }
 
 // K = compile-time tupSize (1: immediate address offsets, 128-bit stores) or 0 for a run-time k.
-// EPB ring elements per CTA iteration on WARPS warps: phase 1 has 6*EPB warp-tasks (32 columns each), phase 2 has
-// 20*EPB; (EPB, WARPS) = (5, 10) balances both exactly (3 and 10 tasks per warp).  EPB == 1 double-buffers the
-// shared tile (one barrier per element), EPB > 1 uses a single tile and two barriers per EPB elements.
+// One ring element per CTA iteration on WARPS warps (phase 1: 6 warp-tasks of 32 columns, phase 2: 20), one 15 KB tile, two
+// barriers per element.  Coarser shapes (5 elements x 10 warps, double-buffered tiles, a register software pipeline, an L2
+// prefetch of the next element) were all measured slower: DESIGN.md 4.1 keeps the numbers.
 // MUL fuses the pointwise product with a second operand b (canonical residues, same layout; b_stride = 0 broadcasts one
 // element): forward  y <- CRT(y) . b  (multiplied at the store), inverse  y <- CRT^-1(y . b)  (multiplied at the load).
-template <bool INV, class AR, int K, int EPB, int WARPS, int MINB, int NBUF, bool MUL = false>
+template <bool INV, class AR, int K, int WARPS, int MINB, bool MUL = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __grid_constant__ FusedAConsts C,
           const int64_t* __restrict__ bmul = nullptr, int64_t b_stride = 0)
 {
   const int k = K ? K : k_rt;
-  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [NBUF][EPB][kN]
+  __shared__ __align__(16) uint32_t tile[kN];
   const AR A(C);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -240,17 +240,12 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
 #pragma unroll
   for (int i = 0; i < 12; i++) m3l[i] = C.lane_tw[(8 + i) * 32 + lane];
 
-  int buf = 0;
-  const int64_t groups = (batch + EPB - 1) / EPB;
-  for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
-    const int64_t e0 = g * EPB;
-    const int cnt = (int)(batch - e0 < EPB ? batch - e0 : EPB);
-    uint32_t* tile = sm_dyn + (size_t)buf * EPB * kN;
-    // ---------------- phase 1: 5^2 axis; warp-task = (element slot, i2), lane = i1
-    for (int t = warp; t < 6 * EPB; t += WARPS) {
-      const int slot = t / 6, col = (t - slot * 6) * 32 + lane;
-      if (slot >= cnt) break;
-      const int64_t* src = y + ((size_t)(e0 + slot) * kN + col) * k + limb;
+  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
+    int64_t* ebase = y + (size_t)e * kN * k + limb;
+    // ---------------- phase 1: 5^2 axis; warp-task = i2, lane = i1
+    for (int i2 = warp; i2 < kD2; i2 += WARPS) {
+      const int col = i2 * 32 + lane;
+      const int64_t* src = ebase + (size_t)col * k;
       // all 20 loads are issued before the first use; the canonical-range check is two OR/max reductions
       uint32_t v[20];
       uint32_t hi_or = 0, lo_max = 0;
@@ -266,7 +261,7 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
         for (int a = 0; a < 20; a++) v[a] = reduce_any(src[(size_t)(a * 192) * k], C.q);
       }
       if (MUL && INV) {
-        const int64_t* bsrc = bmul + (size_t)(e0 + slot) * b_stride + (size_t)col * k + limb;
+        const int64_t* bsrc = bmul + (size_t)e * b_stride + (size_t)col * k + limb;
         uint32_t w[20];
         uint32_t bh = 0, bm = 0;
 #pragma unroll
@@ -284,181 +279,64 @@ k_fused_a(int64_t* __restrict__ y, int64_t batch, int k_rt, int limb, const __gr
         for (int a = 0; a < 20; a++) v[a] = A.mulv(v[a], w[a]);
       }
       axis5<INV, AR>(v, C, A);
-      uint32_t* dst = tile + slot * kN + col;
 #pragma unroll
-      for (int a = 0; a < 20; a++) dst[a * 192] = v[a];
+      for (int a = 0; a < 20; a++) tile[a * 192 + col] = v[a];
     }
     __syncthreads();
-    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp; warp-task = (element slot, i3).
-    // Two tasks are processed together (U = 2) so that two independent dependency chains interleave.
-    constexpr int U = 1;      // U = 2 measured slower (ragged pairs recompute a dead task)
-    for (int t0 = warp; t0 < kD3 * EPB; t0 += U * WARPS) {
-      int64_t* out[U];
-      const int64_t* bout[U];
-      uint32_t x[U][6], c0[U][3], c1[U][3];
-      bool live[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int t = t0 + u * WARPS;
-        const int slot = t / kD3, i3 = t - slot * kD3;
-        live[u] = t < kD3 * EPB && slot < cnt;
-        const int ts = live[u] ? slot : 0, ti = live[u] ? i3 : 0;     // dead lanes of the pair recompute task (0,0), never store
-        const uint32_t* srow = tile + ts * kN + ti * 192 + lane;
-#pragma unroll
-        for (int i2 = 0; i2 < 6; i2++) x[u][i2] = srow[i2 * 32];
-        int64_t* base = y + ((size_t)(e0 + ts) * kN) * k + limb;
-        out[u] = INV ? base + (size_t)(ti * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k
-                     : base + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k;
-        bout[u] = (MUL && !INV) ? bmul + (size_t)(e0 + ts) * b_stride + (size_t)(ti * 192 + (lane & 1) * 32 + (lane >> 1)) * k + limb : nullptr;
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) axis3<INV, AR>(x[u], C, A, m3l);
-      if (!INV) {
-#pragma unroll
-        for (int u = 0; u < U; u++)
-#pragma unroll
-          for (int j = 0; j < 3; j++) { c0[u][j] = x[u][2 * j]; c1[u][j] = x[u][2 * j + 1]; }   // crtTwiddle of 2^6 already in m3l
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-          for (int u = 0; u < U; u++) exchange_round<false, AR>(c0[u], c1[u], lane, r, ltw[1 + r], A);
-#pragma unroll
-        for (int u = 0; u < U; u++) exchange_round<false, AR, true>(c0[u], c1[u], lane, 4, 0u, A);
-        // lane owns rows 2j + (lane&1), columns (lane>>1) and (lane>>1)+16
-#pragma unroll
-        for (int u = 0; u < U; u++)
-          if (live[u]) {
-            if (MUL) {
-              const int64_t* bo = bout[u];
-              int64_t braw[6];
-#pragma unroll
-              for (int j = 0; j < 3; j++) { braw[2 * j] = __ldg(bo + (size_t)(j * 64) * k); braw[2 * j + 1] = __ldg(bo + (size_t)(j * 64 + 16) * k); }
-#pragma unroll
-              for (int j = 0; j < 6; j++) {
-                const uint32_t bw = (uint64_t)braw[j] < (uint64_t)C.q ? (uint32_t)braw[j] : reduce_any(braw[j], C.q);
-                if (j & 1) c1[u][j >> 1] = A.mulv(c1[u][j >> 1], bw); else c0[u][j >> 1] = A.mulv(c0[u][j >> 1], bw);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-              __stcs(out[u] + (size_t)(j * 64) * k, (int64_t)A.canon(c0[u][j]));
-              __stcs(out[u] + (size_t)(j * 64 + 16) * k, (int64_t)A.canon(c1[u][j]));
-            }
-          }
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; u++)
-#pragma unroll
-          for (int j = 0; j < 3; j++) { c0[u][j] = x[u][2 * j]; c1[u][j] = x[u][2 * j + 1]; }
-#pragma unroll
-        for (int u = 0; u < U; u++) exchange_round<true, AR, true>(c0[u], c1[u], lane, 4, 0u, A);
-#pragma unroll
-        for (int r = 3; r >= 1; r--)
-#pragma unroll
-          for (int u = 0; u < U; u++) exchange_round<true, AR>(c0[u], c1[u], lane, r, ltw[r], A);
-        // last round merged with the inverse crtTwiddle: lane owns rows 2j + (lane>>4), columns 2*(lane&15) and +1
-#pragma unroll
-        for (int u = 0; u < U; u++) exchange_last_inv<AR>(c0[u], c1[u], lane, ltw[5], ltw[7], ltw[6], ltw[8], A);
-#pragma unroll
-        for (int u = 0; u < U; u++)
-          if (live[u]) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-              const int64_t a = (int64_t)A.canon(c0[u][j]);
-              const int64_t b = (int64_t)A.canon(c1[u][j]);
-              if (K == 1) {
-                __stcs(reinterpret_cast<longlong2*>(out[u] + j * 64), make_longlong2(a, b));
-              } else {
-                __stcs(out[u] + (size_t)(j * 64) * k, a);
-                __stcs(out[u] + (size_t)(j * 64 + 1) * k, b);
-              }
-            }
-          }
-      }
-    }
-    if (NBUF == 1) __syncthreads(); else buf ^= 1;
-  }
-}
-
-// Software-pipelined variant for tupSize = 1: 6 warps, one ring element per iteration, double-buffered tile.  The 20
-// loads of the NEXT element are issued right after the barrier, so they are in flight during phase 2 of the current
-// element and phase 1 never waits on HBM (the price: 40 live registers through phase 2).
-template <bool INV, class AR, int MINB>
-__global__ void __launch_bounds__(192, MINB)
-k_fused_a_pf(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts C)
-{
-  __shared__ uint32_t sm[2][kN];
-  const AR A(C);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t ltw[7], m3l[12];
-#pragma unroll
-  for (int i = 0; i < 7; i++) ltw[i] = C.lane_tw[i * 32 + lane];
-#pragma unroll
-  for (int i = 0; i < 12; i++) m3l[i] = C.lane_tw[(8 + i) * 32 + lane];
-
-  int64_t raw[20];
-  int64_t e = blockIdx.x;
-  if (e < batch) {
-#pragma unroll
-    for (int a = 0; a < 20; a++) raw[a] = __ldcs(y + (size_t)e * kN + a * 192 + tid);
-  }
-  int buf = 0;
-  for (; e < batch; e += gridDim.x, buf ^= 1) {
-    int64_t* base = y + (size_t)e * kN;
-    {
-      uint32_t v[20];
-      uint32_t hi_or = 0, lo_max = 0;
-#pragma unroll
-      for (int a = 0; a < 20; a++) {
-        v[a] = (uint32_t)raw[a];
-        hi_or |= (uint32_t)((uint64_t)raw[a] >> 32);
-        lo_max = max(lo_max, v[a]);
-      }
-      if (hi_or != 0 || lo_max >= C.q) {
-#pragma unroll 1
-        for (int a = 0; a < 20; a++) v[a] = reduce_any(base[a * 192 + tid], C.q);
-      }
-      axis5<INV, AR>(v, C, A);
-#pragma unroll
-      for (int a = 0; a < 20; a++) sm[buf][a * 192 + tid] = v[a];
-    }
-    __syncthreads();
-    const int64_t en = e + gridDim.x;
-    if (en < batch) {
-#pragma unroll
-      for (int a = 0; a < 20; a++) raw[a] = __ldcs(y + (size_t)en * kN + a * 192 + tid);
-    }
-    for (int i3 = warp; i3 < kD3; i3 += 6) {
+    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp; warp-task = i3
+    for (int i3 = warp; i3 < kD3; i3 += WARPS) {
       uint32_t x[6], c0[3], c1[3];
+      const uint32_t* srow = tile + i3 * 192 + lane;
 #pragma unroll
-      for (int i2 = 0; i2 < 6; i2++) x[i2] = sm[buf][i3 * 192 + i2 * 32 + lane];
+      for (int i2 = 0; i2 < 6; i2++) x[i2] = srow[i2 * 32];
       axis3<INV, AR>(x, C, A, m3l);
-      if (!INV) {
 #pragma unroll
-        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+      for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+      if (!INV) {
+        // crtTwiddle of 2^6 is already in m3l
 #pragma unroll
         for (int r = 0; r < 4; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[1 + r], A);
         exchange_round<false, AR, true>(c0, c1, lane, 4, 0u, A);
-        int64_t* out = base + i3 * 192 + (lane & 1) * 32 + (lane >> 1);
+        // lane owns rows 2j + (lane&1), columns (lane>>1) and (lane>>1)+16
+        const int pos = i3 * 192 + (lane & 1) * 32 + (lane >> 1);
+        int64_t* out = ebase + (size_t)pos * k;
+        if (MUL) {
+          const int64_t* bo = bmul + (size_t)e * b_stride + (size_t)pos * k + limb;
+          int64_t braw[6];
+#pragma unroll
+          for (int j = 0; j < 3; j++) { braw[2 * j] = __ldg(bo + (size_t)(j * 64) * k); braw[2 * j + 1] = __ldg(bo + (size_t)(j * 64 + 16) * k); }
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const uint32_t bw = (uint64_t)braw[j] < (uint64_t)C.q ? (uint32_t)braw[j] : reduce_any(braw[j], C.q);
+            if (j & 1) c1[j >> 1] = A.mulv(c1[j >> 1], bw); else c0[j >> 1] = A.mulv(c0[j >> 1], bw);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          __stcs(out + j * 64, (int64_t)A.canon(c0[j]));
-          __stcs(out + j * 64 + 16, (int64_t)A.canon(c1[j]));
+          __stcs(out + (size_t)(j * 64) * k, (int64_t)A.canon(c0[j]));
+          __stcs(out + (size_t)(j * 64 + 16) * k, (int64_t)A.canon(c1[j]));
         }
       } else {
-#pragma unroll
-        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
-#pragma unroll
         exchange_round<true, AR, true>(c0, c1, lane, 4, 0u, A);
 #pragma unroll
-        for (int r = 3; r >= 0; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
-        int64_t* out = base + i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15);
+        for (int r = 3; r >= 1; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
+        // last round merged with the inverse crtTwiddle: lane owns rows 2j + (lane>>4), columns 2*(lane&15) and +1
+        exchange_last_inv<AR>(c0, c1, lane, ltw[5], ltw[7], ltw[6], ltw[8], A);
+        int64_t* out = ebase + (size_t)(i3 * 192 + (lane >> 4) * 32 + 2 * (lane & 15)) * k;
 #pragma unroll
-        for (int j = 0; j < 3; j++)
-          __stcs(reinterpret_cast<longlong2*>(out + j * 64),
-                 make_longlong2((int64_t)A.canon(A.red(A.mul(ltw[5], c0[j]))), (int64_t)A.canon(A.red(A.mul(ltw[6], c1[j])))));
+        for (int j = 0; j < 3; j++) {
+          const int64_t a = (int64_t)A.canon(c0[j]);
+          const int64_t b = (int64_t)A.canon(c1[j]);
+          if (K == 1) {
+            __stcs(reinterpret_cast<longlong2*>(out + j * 64), make_longlong2(a, b));
+          } else {
+            __stcs(out + (size_t)(j * 64) * k, a);
+            __stcs(out + (size_t)(j * 64 + 1) * k, b);
+          }
+        }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -480,30 +358,21 @@ __device__ __forceinline__ uint32_t triv_digit_other(uint32_t x, uint32_t q_own,
 
 // DIG (forward only): y = the digit arrays [l * b_stride][n][2] (output), bmul = the Pow-basis source [b_stride][n][2];
 // element e of y is digit e / b_stride of source element e % b_stride.
-// LSM: the per-lane constants of phase 2 live in shared memory and are read at the start of every phase-2 task, instead
-// of sitting in 2 x 16 registers through phase 1 (where the 40-value column and its loads in flight set the peak).
-template <bool INV, class AR, int WARPS, int MINB, bool MUL = false, bool DIG = false, bool LSM = false>
+template <bool INV, class AR, int WARPS, int MINB, bool MUL = false, bool DIG = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConsts2 CC,
              const int64_t* __restrict__ bmul, int64_t b_stride)
 {
-  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN] (+ [2][kLaneRows][32] with LSM)
+  extern __shared__ __align__(16) uint32_t sm_dyn[];       // [2 limbs][kN]
   const AR A0(CC.c[0]), A1(CC.c[1]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t ltw[2][9], m3l[2][12];
-  uint32_t* lt_s = sm_dyn + 2 * kN;
-  if (LSM) {
-    for (int i = threadIdx.x; i < 2 * kLaneRows * 32; i += WARPS * 32)
-      lt_s[i] = CC.c[i / (kLaneRows * 32)].lane_tw[i % (kLaneRows * 32)];
-    __syncthreads();
-  } else {
 #pragma unroll
-    for (int l = 0; l < 2; l++) {
+  for (int l = 0; l < 2; l++) {
 #pragma unroll
-      for (int i = 0; i < 9; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
+    for (int i = 0; i < 9; i++) ltw[l][i] = CC.c[l].lane_tw[i * 32 + lane];
 #pragma unroll
-      for (int i = 0; i < 12; i++) m3l[l][i] = CC.c[l].lane_tw[(8 + i) * 32 + lane];
-    }
+    for (int i = 0; i < 12; i++) m3l[l][i] = CC.c[l].lane_tw[(8 + i) * 32 + lane];
   }
 
   for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
@@ -572,15 +441,6 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
     // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp, both limbs of row block i3
     for (int i3 = warp; i3 < kD3; i3 += WARPS) {
       uint32_t x[2][6], c0[2][3], c1[2][3];
-      if (LSM) {
-#pragma unroll
-        for (int l = 0; l < 2; l++) {
-#pragma unroll
-          for (int i = 0; i < 9; i++) ltw[l][i] = lt_s[(l * kLaneRows + i) * 32 + lane];
-#pragma unroll
-          for (int i = 0; i < 12; i++) m3l[l][i] = lt_s[(l * kLaneRows + 8 + i) * 32 + lane];
-        }
-      }
 #pragma unroll
       for (int l = 0; l < 2; l++)
 #pragma unroll
@@ -914,21 +774,14 @@ bool fused_a_available(const void* slot, bool inverse)
   return F && (inverse ? F->ok_inv : F->ok_fwd);
 }
 
-template <bool INV, class AR, int K, int EPB, int WARPS, int MINB, int NBUF>
+// the default launch: 3 warps x 8 CTAs/SM (80 registers, no spills), grid-stride over the batch
+template <bool INV, class AR, int K>
 static int launch_a(const lolb_plan* pl, int64_t* y, int64_t batch, int limb, const FusedAConsts& C, cudaStream_t st)
 {
-  const size_t smem = (size_t)NBUF * EPB * kN * sizeof(uint32_t);
-  auto kern = k_fused_a<INV, AR, K, EPB, WARPS, MINB, NBUF>;
-  static bool attr_done = false;
-  if (smem > 48 * 1024 && !attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fused_a)");
-    attr_done = true;
-  }
-  const int64_t groups = (batch + EPB - 1) / EPB;
-  int64_t grid = (int64_t)pl->num_sms * MINB;
-  if (grid > groups) grid = groups;
-  kern<<<(int)grid, WARPS * 32, smem, st>>>(y, batch, pl->k, limb, C, nullptr, 0);
+  constexpr int W = 3, MB = 8;
+  int64_t grid = (int64_t)pl->num_sms * MB;
+  if (grid > batch) grid = batch;
+  k_fused_a<INV, AR, K, W, MB><<<(int)grid, W * 32, 0, st>>>(y, batch, pl->k, limb, C, nullptr, 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_fused_a");
   count_launch();
@@ -943,7 +796,7 @@ static int launch_a_mul(const lolb_plan* pl, int64_t* y, const int64_t* b, int64
   int64_t grid = (int64_t)pl->num_sms * MINB;
   if (grid > batch) grid = batch;
   const int64_t b_stride = b_batch == 1 ? 0 : (int64_t)kN * pl->k;
-  k_fused_a<INV, AR, K, 1, 3, MINB, 1, true><<<(int)grid, 96, kN * sizeof(uint32_t), st>>>(y, batch, pl->k, limb, C, b, b_stride);
+  k_fused_a<INV, AR, K, 3, MINB, true><<<(int)grid, 96, 0, st>>>(y, batch, pl->k, limb, C, b, b_stride);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_fused_a<MUL>");
   count_launch();
@@ -1022,15 +875,12 @@ int fused_a_decompose_crt(const lolb_plan* pl, const void* slot, const int64_t* 
   return LOLB_OK;
 }
 
-static int g_variant = -1;      // LOLB_FUSED_A_VARIANT selects (EPB, WARPS, CTAs/SM, buffers) for tuning runs
-
 int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
 {
   const FusedA* F = (const FusedA*)slot;
   if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  if (g_variant < 0) { const char* v = getenv("LOLB_FUSED_A_VARIANT"); g_variant = v ? atoi(v) : 2; }
-  if (pl->k == 2 && F->cls[0] == F->cls[1] && !getenv("LOLB_FUSED_A_PER_LIMB")) {
+  if (pl->k == 2 && F->cls[0] == F->cls[1]) {
     FusedAConsts2 CC;
     CC.c[0] = inverse ? F->inv[0] : F->fwd[0];
     CC.c[1] = inverse ? F->inv[1] : F->fwd[1];
@@ -1040,30 +890,12 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
     if (grid > batch) grid = batch;
     if (F->cls[0] == ARITH_M) {
       // ArithM with both limbs in flight needs more than the 128 registers that 5 CTAs/SM leave: measured (config C
-      // moduli, % of HBM peak forward / inverse) 5 CTAs x 128 registers (spills) 57.5 / 52.8, 4 x 168 62.4 / 54.8
-      static int mbv = -1;        // LOLB_FUSED_A_K2_MB: tuning override (3, 4 or 5 CTAs per SM)
-      if (mbv < 0) { const char* v = getenv("LOLB_FUSED_A_K2_MB"); mbv = v ? atoi(v) : 4; }
-#define K2M(MBV)                                                                                                   \
-      do {                                                                                                         \
-        int64_t gg = (int64_t)pl->num_sms * MBV;                                                                   \
-        if (gg > batch) gg = batch;                                                                                \
-        if (inverse) k_fused_a_k2<true, ArithM, W, MBV><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);   \
-        else k_fused_a_k2<false, ArithM, W, MBV><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);          \
-      } while (0)
-      if (mbv == 3) K2M(3); else if (mbv == 5) K2M(5); else if (mbv == 4) K2M(4);
-      else {      // 15/14/16: per-lane constants in shared memory (LSM), 5 / 4 / 6 CTAs per SM
-        const size_t smem_l = smem + 2 * kLaneRows * 32 * sizeof(uint32_t);
-#define K2L(MBV)                                                                                                                  \
-        do {                                                                                                                        \
-          int64_t gg = (int64_t)pl->num_sms * MBV;                                                                                  \
-          if (gg > batch) gg = batch;                                                                                               \
-          if (inverse) k_fused_a_k2<true, ArithM, W, MBV, false, false, true><<<(int)gg, W * 32, smem_l, st>>>(y, batch, CC, nullptr, 0);   \
-          else k_fused_a_k2<false, ArithM, W, MBV, false, false, true><<<(int)gg, W * 32, smem_l, st>>>(y, batch, CC, nullptr, 0);          \
-        } while (0)
-        if (mbv == 14) K2L(4); else if (mbv == 16) K2L(6); else K2L(5);
-#undef K2L
-      }
-#undef K2M
+      // moduli, % of HBM peak forward / inverse) 5 CTAs x 128 registers (spills) 57.5 / 52.8, 4 x 168 62.4 / 54.8; the
+      // per-lane constants in shared memory (5 / 6 CTAs per SM) were slower still
+      int64_t gg = (int64_t)pl->num_sms * 4;
+      if (gg > batch) gg = batch;
+      if (inverse) k_fused_a_k2<true, ArithM, W, 4><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
+      else k_fused_a_k2<false, ArithM, W, 4><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
     } else {
       if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
       else k_fused_a_k2<false, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
@@ -1073,14 +905,12 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
     count_launch();
     return LOLB_OK;
   }
-  if (pl->k >= 2 && pl->k <= kMaxLimbsN && !getenv("LOLB_FUSED_A_PER_LIMB")) {
+  if (pl->k >= 2 && pl->k <= kMaxLimbsN) {
     bool same = true;
     for (int t = 1; t < pl->k; t++) same &= F->cls[t] == F->cls[0];
     if (same) {
       FusedAConstsN CC;
       for (int t = 0; t < pl->k; t++) CC.c[t] = inverse ? F->inv[t] : F->fwd[t];
-      static int knv = -1;        // LOLB_FUSED_A_KN: tuning override of the CTA shape
-      if (knv < 0) { const char* v = getenv("LOLB_FUSED_A_KN"); knv = v ? atoi(v) : 0; }
       const size_t smem = (size_t)pl->k * kN * sizeof(uint32_t);
       const int fit = (int)((227 * 1024) / (smem + 1024));      // CTAs per SM the tile allows
       cudaError_t e = cudaSuccess;
@@ -1093,15 +923,13 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
         if (e == cudaSuccess) kern<<<(int)gg, W * 32, smem, st>>>(y, batch, pl->k, CC);                            \
       } while (0)
       // warps per CTA: a divisor pattern of 6k and 20k that keeps about 24 warps per SM next to the k x 15 KB tile
-      int shape = knv ? knv : (pl->k == 3 || pl->k == 6) ? 6 : pl->k == 4 ? 8 : pl->k == 5 ? 10 : 7;
-      if (pl->k == 6 && !knv) shape = 12;
+      const int shape = pl->k == 3 ? 6 : pl->k == 4 ? 8 : pl->k == 5 ? 10 : pl->k == 6 ? 12 : 7;
 #define KNS(AR)                                                                                                   \
       switch (shape) {                                                                                             \
         case 6: KN(AR, 6, 4); break;                                                                               \
         case 8: KN(AR, 8, 3); break;                                                                               \
         case 10: KN(AR, 10, 2); break;                                                                             \
         case 12: KN(AR, 12, 2); break;                                                                             \
-        case 4: KN(AR, 4, 5); break;                                                                               \
         default: KN(AR, 7, 2); break;                                                                              \
       }
       if (F->cls[0] == ARITH_M) { KNS(ArithM) } else { KNS(ArithS) }
@@ -1116,34 +944,9 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   for (int t = 0; t < pl->k; t++) {
     const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];
     int rc;
-#define LA(AR, ...) (inverse ? launch_a<true, AR, __VA_ARGS__>(pl, y, batch, t, C, st) : launch_a<false, AR, __VA_ARGS__>(pl, y, batch, t, C, st))
-    if (F->cls[t] == ARITH_M) {
-      rc = pl->k == 1 ? LA(ArithM, 1, 1, 3, 8, 1) : LA(ArithM, 0, 1, 3, 8, 1);
-    } else if (pl->k == 1) {
-      switch (g_variant) {
-        case 6: case 7: {
-          int64_t grid = (int64_t)pl->num_sms * 4;
-          if (grid > batch) grid = batch;
-          if (inverse) k_fused_a_pf<true, ArithS, 4><<<(int)grid, 192, 0, st>>>(y, batch, C);
-          else k_fused_a_pf<false, ArithS, 4><<<(int)grid, 192, 0, st>>>(y, batch, C);
-          cudaError_t e = cudaGetLastError();
-          if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_pf");
-          count_launch();
-          rc = LOLB_OK;
-        } break;
-        case 8: rc = LA(ArithS, 1, 1, 3, 9, 1); break;
-        case 9: rc = LA(ArithS, 1, 1, 3, 8, 1); break;
-        case 10: rc = LA(ArithS, 1, 1, 3, 7, 1); break;
-        case 11: rc = LA(ArithS, 1, 1, 4, 6, 1); break;
-        case 12: rc = LA(ArithS, 1, 1, 2, 12, 1); break;
-        case 0: rc = LA(ArithS, 1, 1, 6, 5, 2); break;
-        case 1: rc = LA(ArithS, 1, 5, 10, 3, 1); break;
-        case 13: rc = LA(ArithS, 1, 1, 3, 10, 1); break;     // the previous default: 64 registers, 32 bytes of spills
-        default: rc = LA(ArithS, 1, 1, 3, 8, 1); break;      // 3 warps x 8 CTAs/SM, 80 registers, no spills
-      }
-    } else {
-      rc = LA(ArithS, 0, 1, 3, 8, 1);
-    }
+#define LA(AR, KK) (inverse ? launch_a<true, AR, KK>(pl, y, batch, t, C, st) : launch_a<false, AR, KK>(pl, y, batch, t, C, st))
+    if (F->cls[t] == ARITH_M) rc = pl->k == 1 ? LA(ArithM, 1) : LA(ArithM, 0);
+    else rc = pl->k == 1 ? LA(ArithS, 1) : LA(ArithS, 0);
 #undef LA
     if (rc) return rc;
   }

@@ -347,13 +347,12 @@ template <int W, int MB>
 static int launch_ac(const lolb_plan* pl, const FusedAC* F, bool inverse, double2* y, int64_t batch, cudaStream_t st)
 {
   const size_t smem = (size_t)(kN + kLaneRows * 32) * sizeof(double2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     LOLB_CUDA(cudaFuncSetAttribute(k_fused_ac<true, 1, W, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LOLB_CUDA(cudaFuncSetAttribute(k_fused_ac<false, 1, W, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LOLB_CUDA(cudaFuncSetAttribute(k_fused_ac<true, 0, W, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LOLB_CUDA(cudaFuncSetAttribute(k_fused_ac<false, 0, W, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
   }
   int64_t grid = (int64_t)pl->num_sms * MB;
   if (grid > batch) grid = batch;

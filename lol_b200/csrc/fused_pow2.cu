@@ -606,12 +606,11 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
   if (!fused_pow2_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
   const size_t smem = (size_t)pl->n * sizeof(uint32_t);
-  static bool attr_done[2] = {false, false};
-  if (smem > 48 * 1024 && !attr_done[inverse]) {
+  static PerDeviceOnce once[2];
+  if (smem > 48 * 1024 && once[inverse].first()) {
     cudaError_t e = inverse ? cudaFuncSetAttribute(k_pow2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
                             : cudaFuncSetAttribute(k_pow2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_pow2)");
-    attr_done[inverse] = true;
   }
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   const int by_threads = 2048 / F->threads;
@@ -622,8 +621,8 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
   const int64_t items = batch * pl->k;
   if (grid > items) grid = items;
   if (pl->pe[0].exponent == kE16 && !getenv("LOLB_POW2_GENERIC")) {
-    static bool attr16 = false;
-    if (!attr16) {
+    static PerDeviceOnce once16;
+    if (once16.first()) {
       cudaFuncSetAttribute(k_pow2_e16<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_pow2_e16<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_pow2_e16<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -632,7 +631,6 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
       cudaFuncSetAttribute(k_pow2_e16<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_pow2_e16<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_pow2_e16<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr16 = true;
     }
     if (pl->k == 1) {
       if (inverse) k_pow2_e16<true, 1><<<(int)grid, kT16, smem, st>>>(y, batch, F->inv);
@@ -642,18 +640,16 @@ int fused_pow2_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t*
       // (28.7 % vs 24.8 % of HBM peak; inverse 28.3 % vs 30.8 %); part of the scratch is written back to HBM
       int64_t g2 = pl->num_sms;
       if (g2 > batch) g2 = batch;
-      int rc = plan_reserve_ws(pl, (size_t)g2 * pl->k * kN16 * sizeof(uint32_t));
-      if (rc) return rc;
-      uint32_t* scratch = (uint32_t*)pl->d_ws;
-      static bool attr_el = false;
-      if (!attr_el) {
+      uint32_t* scratch = (uint32_t*)plan_ws(pl, st, (size_t)g2 * pl->k * kN16 * sizeof(uint32_t));
+      if (!scratch) return LOLB_ERR_CUDA;
+      static PerDeviceOnce once_el;
+      if (once_el.first()) {
         cudaFuncSetAttribute(k_pow2_e16_elem<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_pow2_e16_elem<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_pow2_e16_elem<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_pow2_e16_elem<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_pow2_e16_elem<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_pow2_e16_elem<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_el = true;
       }
 #define LE(KK) (inverse ? k_pow2_e16_elem<true, KK><<<(int)g2, kT16, smem, st>>>(y, batch, F->inv, scratch) \
                         : k_pow2_e16_elem<false, KK><<<(int)g2, kT16, smem, st>>>(y, batch, F->fwd, scratch))

@@ -690,7 +690,8 @@ int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t bat
   else {
   typedef DfGeom<K, TOP> Geo;
   static int per_sm = 0;
-  if (!per_sm) {
+  static PerDeviceOnce once;      // the attribute is per device; the occupancy is the same on every B200
+  if (once.first() || !per_sm) {
     LOLB_CUDA(cudaFuncSetAttribute(k_pow2_df<INV, K, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo::SMEM_BYTES));
     LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_df<INV, K, TOP>, kDfThreads, Geo::SMEM_BYTES));
     if (per_sm < 1) per_sm = 1;
@@ -713,10 +714,9 @@ int launch_df(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t bat
   const size_t slot_bytes = (size_t)K * pl->n * sizeof(uint32_t);
   const size_t ring_bytes = (size_t)P.ring * slot_bytes;
   const size_t ctr_bytes = ((size_t)kDfCtrHead + 2 * (size_t)batch) * sizeof(unsigned);
-  int rc = plan_reserve_ws(pl, ring_bytes + ctr_bytes);
-  if (rc) return rc;
-  uint32_t* ring = (uint32_t*)pl->d_ws;
-  unsigned* ctr = (unsigned*)((char*)pl->d_ws + ring_bytes);
+  uint32_t* ring = (uint32_t*)plan_ws(pl, st, ring_bytes + ctr_bytes);      // per stream: concurrent launches never share the ring or its counters
+  if (!ring) return LOLB_ERR_CUDA;
+  unsigned* ctr = (unsigned*)((char*)ring + ring_bytes);
   LOLB_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
   k_pow2_df<INV, K, TOP><<<(int)grid, kDfThreads, Geo::SMEM_BYTES, st>>>(y, (int)batch, P, ring, ctr);
   cudaError_t e = cudaGetLastError();
@@ -734,7 +734,8 @@ int launch_dfm(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t ba
   typedef DfGeom<K, TOP> Geo;
   constexpr int smem = 2 * kDfWarps * kDfUnit * 4 + 64;
   static int per_sm = 0;
-  if (!per_sm) {
+  static PerDeviceOnce once;      // the attribute is per device; the occupancy is the same on every B200
+  if (once.first() || !per_sm) {
     LOLB_CUDA(cudaFuncSetAttribute(k_pow2_dfm<INV, K, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_dfm<INV, K, TOP>, kDfThreads, smem));
     if (per_sm < 1) per_sm = 1;
@@ -756,10 +757,9 @@ int launch_dfm(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t ba
   if (P.lag >= P.ring) P.lag = P.ring - 1;
   const size_t ring_bytes = (size_t)P.ring * K * pl->n * sizeof(uint32_t);
   const size_t ctr_bytes = ((size_t)kDfCtrHead + 2 * (size_t)batch) * sizeof(unsigned);
-  int rc = plan_reserve_ws(pl, ring_bytes + ctr_bytes);
-  if (rc) return rc;
-  uint32_t* ring = (uint32_t*)pl->d_ws;
-  unsigned* ctr = (unsigned*)((char*)pl->d_ws + ring_bytes);
+  uint32_t* ring = (uint32_t*)plan_ws(pl, st, ring_bytes + ctr_bytes);      // per stream: concurrent launches never share the ring or its counters
+  if (!ring) return LOLB_ERR_CUDA;
+  unsigned* ctr = (unsigned*)((char*)ring + ring_bytes);
   LOLB_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
   k_pow2_dfm<INV, K, TOP><<<(int)grid, kDfThreads, smem, st>>>(y, (int)batch, P, ring, ctr);
   cudaError_t e = cudaGetLastError();

@@ -353,7 +353,8 @@ template <bool INV, int K, int E>
 int launch_small(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
 {
   static int per_sm = 0;
-  if (!per_sm) {
+  static PerDeviceOnce once;      // the attribute is per device; the occupancy is the same on every B200
+  if (once.first() || !per_sm) {
     LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_small<INV, K, E>, 128, 0));
     if (per_sm < 1) per_sm = 1;
   }
@@ -375,7 +376,8 @@ int launch_mid(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t ba
   constexpr int units1 = ((1 << (E - 1)) / 1024) * K, epc = units1 >= 4 ? 1 : 4 / units1;
   constexpr int smem = units1 * epc * kDfUnit * 4;
   static int per_sm = 0;
-  if (!per_sm) {
+  static PerDeviceOnce once;      // the attribute is per device; the occupancy is the same on every B200
+  if (once.first() || !per_sm) {
     LOLB_CUDA(cudaFuncSetAttribute(k_pow2_mid<INV, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LOLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pow2_mid<INV, K, E>, 128, smem));
     if (per_sm < 1) per_sm = 1;

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -101,13 +103,12 @@ struct lolb_plan {
 
   // ---- fused kernels (selected at plan creation; nullptr / 0 = not available)
   void* fused = nullptr;            // lolb::FusedInfo*, owned
-  // ---- workspace for elements that do not fit in shared memory
-  mutable void* d_ws = nullptr;
-  mutable size_t ws_bytes = 0;
-  // one private workspace per stream slot of the host pipeline (kernels with a workspace -- exchange ring, counters,
-  // spilled elements -- must not share it across concurrently running streams); swapped into d_ws around a slot's launches
-  mutable void* ws_alt[3] = {nullptr, nullptr, nullptr};
-  mutable size_t ws_alt_bytes[3] = {0, 0, 0};
+  // ---- kernel workspaces (exchange ring + counters of the dataflow kernel, spilled elements of the generic engine):
+  // one per CUDA stream the plan has been used on, so that calls on different streams (or from different host threads
+  // on different streams) never share mutable device state; calls on ONE stream are ordered by the stream (plan_ws)
+  struct WsSlot { cudaStream_t st; void* p; size_t bytes; };
+  mutable std::vector<WsSlot> ws;
+  mutable std::mutex ws_mu;
   // ---- staging for the drop-in (host pointer) entry points and host-batched calls
   mutable void* d_stage = nullptr;
   mutable size_t stage_bytes = 0;
@@ -129,6 +130,18 @@ void count_launch(int n = 1);
     if (e__ != cudaSuccess) return ::lolb::cuda_fail(e__, #call);           \
   } while (0)
 
+// Function attributes (the dynamic shared memory opt-in) and occupancy are per device: a call-site flag that is true the
+// first time it is asked on each device
+struct PerDeviceOnce {
+  std::atomic<unsigned char> done[64] = {};
+  bool first()
+  {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    return done[d].exchange(1) == 0;
+  }
+};
+
 // plan.cu
 int plan_build_common(lolb_plan* pl, const PrimeExponent* pe, int npe, int k);
 int plan_derive_rq_roots(lolb_plan* pl);              // ZqBasic.hs:144-171 -> pl->ru, ruinv, mhatinv (LOLB_ERR_NO_CRT if none)
@@ -137,7 +150,7 @@ int plan_upload_rq_gcrt(lolb_plan* pl);               // gCRT / gInvCRT vectors 
 void plan_derive_c_roots(lolb_plan* pl);              // CRTrans.hs:88-95 -> pl->cru, cruinv, c_mhatinv
 int plan_upload_c_dir(lolb_plan* pl, bool inverse);
 uint64_t hash_bytes(const void* p, size_t bytes, uint64_t seed);
-int plan_reserve_ws(const lolb_plan* pl, size_t bytes);
+void* plan_ws(const lolb_plan* pl, cudaStream_t st, size_t bytes);   // the stream's workspace, grown to `bytes`; nullptr + error set on failure
 int plan_reserve_stage(const lolb_plan* pl, size_t bytes);
 
 // engine.cu -- generic pass engine

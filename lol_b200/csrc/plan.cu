@@ -28,13 +28,23 @@ uint64_t hash_bytes(const void* p, size_t bytes, uint64_t seed)
   return h;
 }
 
-int plan_reserve_ws(const lolb_plan* pl, size_t bytes)
+void* plan_ws(const lolb_plan* pl, cudaStream_t st, size_t bytes)
 {
-  if (bytes <= pl->ws_bytes) return LOLB_OK;
-  if (pl->d_ws) { LOLB_CUDA(cudaDeviceSynchronize()); cudaFree(pl->d_ws); pl->d_ws = nullptr; pl->ws_bytes = 0; }
-  LOLB_CUDA(cudaMalloc(&pl->d_ws, bytes));
-  pl->ws_bytes = bytes;
-  return LOLB_OK;
+  std::lock_guard<std::mutex> lock(pl->ws_mu);
+  lolb_plan::WsSlot* slot = nullptr;
+  for (auto& s : pl->ws) if (s.st == st) { slot = &s; break; }
+  if (!slot) { pl->ws.push_back({st, nullptr, 0}); slot = &pl->ws.back(); }
+  if (bytes <= slot->bytes && slot->p) return slot->p;
+  if (slot->p) {      // kernels of this stream may still use the old block
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize(workspace)"); return nullptr; }
+    cudaFree(slot->p);
+    slot->p = nullptr; slot->bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&slot->p, bytes);
+  if (e != cudaSuccess) { slot->p = nullptr; cuda_fail(e, "cudaMalloc(workspace)"); return nullptr; }
+  slot->bytes = bytes;
+  return slot->p;
 }
 
 int plan_reserve_stage(const lolb_plan* pl, size_t bytes)
