@@ -9,23 +9,31 @@ per GPU (BASELINE.json configs[1]), as an absolute number and as a fraction of t
 A "step" is one pass of the hot path over one batch: lolb_tensorCRTRq then lolb_tensorCRTInvRq,
 in place, on B ring elements resident in HBM.  value = (N*B) / max-over-ranks step time.  Ring
 elements are independent, so N GPUs shard the batch with no collective on the data path (weak
-scaling: B per GPU is fixed); NCCL is used for the barrier and the max-reduction of the timing only.
+scaling: B per GPU is fixed); NCCL is used for the barrier and the max-reductions of the timings only.
+
+Output: ONE JSON line on stdout (the headline).  Its last key, `summary`, holds the roofline
+fractions of the other BASELINE.json configurations in compact form (max over ranks at every N);
+the verbose per-operator tables go to stderr as a second JSON line prefixed "DETAIL ".
 
 Keys beyond the base contract: `roofline` (dominant kernel vs measured HBM copy bandwidth),
 `cpu_baseline` (the reference lol-cpp C++ -- oracle/_ref -- or the C restatement on the host
-cores, one process per core because the reference is not thread-safe: `static Zq::q`, types.h:59),
-`e2e` (same step through the host-buffer C-ABI call with pinned host memory, H2D and D2H inside
-the timed region), `per_op` (other operators of the path, device-resident).
+cores, timed by the C driver oracle/ref_bench, one process per core because the reference is not
+thread-safe: `static Zq::q`, types.h:59), `e2e` (same step through the host-buffer C-ABI call with
+pinned host memory, H2D and D2H inside the timed region, plus the copy-only ceiling of the same
+pipeline and the uint32 wire format).
 
 `--impl reference` times the reference's own CPU implementation of the same step on the host
-cores and prints the same line with "impl": "reference".
+cores (same metric, unit and config) and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import struct
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -40,6 +48,15 @@ BYTES_PER_ELEM = 16 * N_COEFF * len(QS)          # in-place transform: 8 B read 
 METRIC = "CRT+CRTInv ring elems/sec at m=14400"
 UNIT = "ring_elems/s"
 FALLBACK_HBM_GBS = 6650.0                         # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+WORKLOAD = ("configs[1]: m=14400=64*9*25 (n=3840), Zq 14401, CRT then CRTInv in place on uniform synthetic ring elements, "
+            "65536 per GPU")
+
+
+def config_dict(world: int) -> dict:
+    """The same dictionary in both arms (the reference arm runs a bounded sample of this workload on the host cores)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU,
+            "l2": "inputs (1.9 GB per GPU) larger than the 126 MB L2; no flush needed",
+            "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"}
 
 
 def measured_peak():
@@ -51,7 +68,8 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    """dram bytes per launch of the dominant kernels from the committed ncu --set full capture (profiles/traffic.json,
+    which names the capture it came from), or None.  Not measured in this run: ncu cannot run inside a timed bench."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)
@@ -61,9 +79,9 @@ def recorded_traffic():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml), every 2 ms."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.002):
         self.index, self.period = index, period_s
         self.samples, self.reasons = [], set()
         self.max_mhz = None
@@ -115,62 +133,64 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# ------------------------------------------------------------------ CPU arm
-def _cpu_worker(kind: str, pairs: int, seed: int):
+# ------------------------------------------------------------------ CPU arm (oracle/ref_bench, a C driver: no interpreter in the loop)
+def _write_tables(path: str):
+    """What the Haskell side hands to the C code (CPP.hs:422-442), in ref_bench.c's file layout."""
     import numpy as np
-    from oracle import cpu, tables as T
-    lib = cpu.reference() if kind == "reference" else cpu.restatement()
+    from oracle import tables as T
     pe = T.pe_array(M)
     ru, rui = T.ru_tables_zq(M, QS), T.ru_tables_zq(M, QS, inverse=True)
-    mh = [T.mhat_inv(M, q) for q in QS]
-    rng = np.random.default_rng(seed)
-    elems = rng.integers(0, QS[0], size=(256, N_COEFF, 1)).astype(np.int64)     # same distribution as the GPU batch
-    # warm-up + correctness of the sample itself
-    assert np.array_equal(lib.tensorCRTInvRq(lib.tensorCRTRq(elems[0], pe, ru, QS), pe, rui, mh, QS), elems[0])
-    t0 = time.perf_counter()
-    for i in range(pairs):
-        y = lib.tensorCRTRq(elems[i & 255], pe, ru, QS)
-        lib.tensorCRTInvRq(y, pe, rui, mh, QS)
-    return time.perf_counter() - t0
+    mh = np.array([T.mhat_inv(M, q) for q in QS], dtype=np.int64)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iii", len(pe), N_COEFF, len(QS)))
+        f.write(np.ascontiguousarray(pe, dtype=np.int16).tobytes())
+        f.write(np.array(QS, dtype=np.int64).tobytes())
+        for tabs in (ru, rui):
+            for t in tabs:
+                f.write(np.ascontiguousarray(t, dtype=np.int64).tobytes())
+        f.write(mh.tobytes())
 
 
-def cpu_arm(pairs_per_core: int, cores: int | None = None):
-    """One process per core (fork): elems/s = cores*pairs / slowest process."""
-    import multiprocessing as mp
+def cpu_arm(pairs_per_core: int, steps: int = 1, warmup: int = 0, cores: int | None = None):
+    """One process per core (fork inside ref_bench).  Returns the cpu_baseline dictionary plus per-step seconds."""
     from oracle import cpu
     kind = "reference" if cpu.have_reference() else "port"
     if kind == "port":
         cpu.restatement()
+    exe = os.path.join(ROOT, "oracle", "ref_bench")
+    if not os.path.exists(exe):
+        cpu.build("bench")
+    lib, prefix = (cpu.REF_SO, "") if kind == "reference" else (cpu.ORACLE_SO, "lo_")
     cores = cores or len(os.sched_getaffinity(0))
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        times = pool.starmap(_cpu_worker, [(kind, pairs_per_core, 1000 + c) for c in range(cores)])
-    slowest = max(times)
-    return {"value": cores * pairs_per_core / slowest, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{pairs_per_core} CRT+CRTInv pairs per process on {cores} processes (one per core), "
-                      f"256 distinct uniform ring elements each, m=14400 q=14401; slowest process {slowest:.2f} s",
-            "per_core": pairs_per_core / (sum(times) / len(times))}
+    with tempfile.TemporaryDirectory() as td:
+        tab = os.path.join(td, "tables.bin")
+        _write_tables(tab)
+        out = subprocess.run([exe, lib, prefix, tab, str(cores), str(pairs_per_core), str(steps), str(warmup)],
+                             check=True, capture_output=True, text=True).stdout
+    r = json.loads(out)
+    secs = r["step_seconds"]
+    total = sum(secs)
+    return {"value": cores * pairs_per_core * len(secs) / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{len(secs)} steps of {pairs_per_core} CRT+CRTInv pairs per process on {cores} processes (one per core, "
+                      f"C driver oracle/ref_bench), 256 distinct uniform ring elements each, m=14400 q=14401; "
+                      f"step = slowest process, {1e3 * total / len(secs):.1f} ms on average",
+            "per_core": pairs_per_core * len(secs) / sum(r["mean_process_seconds"])}, secs
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # one "step" = a bounded sample of the workload on every host core
-    pairs = 384
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_arm(32)
-    t0 = time.perf_counter()
-    results = [cpu_arm(pairs) for _ in range(max(1, min(args.steps, 3)))]
-    wall = time.perf_counter() - t0
-    best = max(results, key=lambda r: r["value"])
+    # one "step" = a bounded sample of the workload: `ref_pairs` CRT+CRTInv pairs on every host core at once
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    base, secs = cpu_arm(args.ref_pairs, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(results), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / len(results),
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "configs[1]: m=14400 (n=3840), Zq 14401, CRT then CRTInv per ring element", "host_cores": best["cores"]},
-        "cpu_baseline": best,
-        "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": config_dict(args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -189,10 +209,70 @@ def time_op(torch, fn, iters):
     return s.elapsed_time(e) / iters
 
 
-def ext_section(torch, capi, peak, stream):
+def bind_to_gpu_numa(local: int) -> dict:
+    """Pin this process (and therefore its first-touch pinned allocations) to the CPUs of the GPU's NUMA node, so that
+    N ranks do not stage through one memory controller.  Best effort: containers often hide the topology."""
+    info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0))}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus |= set(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info = {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return info
+
+
+class Recorder:
+    """Timings of the informational sections, keyed in a fixed order so that N ranks can max-reduce them in one tensor."""
+
+    def __init__(self):
+        self.rows = []      # (section, name, ms, algorithmic bytes per launch, units per launch, extra)
+
+    def add(self, section, name, ms, alg_bytes, units, **extra):
+        self.rows.append([section, name, float(ms), float(alg_bytes), float(units), extra])
+
+    def reduce_max(self, torch, dist, world):
+        if world > 1 and self.rows:
+            t = torch.tensor([r[2] for r in self.rows], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for r, v in zip(self.rows, t.tolist()):
+                r[2] = v
+
+    def table(self, peak, world):
+        out = {}
+        for section, name, ms, alg, units, extra in self.rows:
+            gbs = alg / (ms * 1e-3) / 1e9
+            row = {"ms": ms, "per_s_all_gpus": world * units / (ms * 1e-3), "GB/s_per_gpu": gbs, "frac": gbs / peak}
+            row.update(extra)
+            out.setdefault(section, {})[name] = row
+        return out
+
+    def frac(self, peak, section, name):
+        for s, n, ms, alg, _, _ in self.rows:
+            if s == section and n == name:
+                return round(alg / (ms * 1e-3) / 1e9 / peak, 4)
+        return None
+
+
+def ext_section(torch, capi, rec, stream):
     """SURVEY.md section 8f ranks 2-3, device-resident and informational: the ring-extension gathers of O_14400 / O_576 and
     the coefficient-wise maps at the configs[3] moduli (same shapes and byte accounting as tools/run_ext.py,
-    DESIGN.md 4.7 / 4.8).  Never lets a failure reach the headline line: the caller records the error text instead."""
+    DESIGN.md 4.7 / 4.8)."""
     from lol_b200.extension import CudaExtension
     from lol_b200.tensor import CudaTensorRq
     m, m2, qs, Be = 576, 14400, [1008001, 1065601], 16384
@@ -218,13 +298,10 @@ def ext_section(torch, capi, peak, stream):
         "rescaleModRq": (lambda: capi.check(P.rescale_mod(qs[::-1], ye.data_ptr(), oi.data_ptr(), Be, stream)), 2 * phi2 * k),
         "roundCosetRq": (lambda: capi.check(P.round_coset(ee.data_ptr(), ye.data_ptr(), oi.data_ptr(), Be, stream)), 3 * phi2 * k),
     }
-    res = {"workload": f"m={m} | m'={m2}, q=(1008001,1065601), {Be} elements of O_m' (1 GiB) resident in HBM"}
+    sec = f"ring extensions + coefficient-wise maps (SURVEY 8f ranks 2-3): m={m} | m'={m2}, q=(1008001,1065601), {Be} elements of O_m'"
     for name, (fn, words) in ops.items():
         fn(); fn(); fn()
-        ms = time_op(torch, fn, 10)
-        gbs = words * 8 * Be / (ms * 1e-3) / 1e9
-        res[name] = {"ms": ms, "elems_per_s": Be / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak}
-    return res
+        rec.add(sec, name, time_op(torch, fn, 10), words * 8 * Be, Be)
 
 
 def run_gpu_arm(args):
@@ -239,6 +316,7 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libctensor_b200 has no CPU path")
+    numa = bind_to_gpu_numa(local)      # before any pinned allocation
     torch.cuda.set_device(local)
     if rank == 0:
         build_library()
@@ -246,6 +324,13 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     assert capi.device_available()
+
+    def reduce_max(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     B = args.batch
     t = CudaTensorRq(M, QS)
@@ -260,7 +345,8 @@ def run_gpu_arm(args):
         capi.check(t.plan.op("CRT", ptr, B, stream))
         capi.check(t.plan.op("CRTInv", ptr, B, stream))
 
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         step()
     torch.cuda.synchronize()
     assert torch.equal(x[:4], x0), "CRTInv . CRT != id"
@@ -285,61 +371,62 @@ def run_gpu_arm(args):
     launches = capi.kernel_launch_count() - launches0
     if world > 1:
         dist.barrier()
-    ms_total = start.elapsed_time(end)
-    ms_t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_t.item()) / K
+    ms_step = reduce_max(start.elapsed_time(end)) / K
     assert torch.equal(x[:4], x0)
     crt_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     inv_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region);
-    # every rank drives its own GPU from its own host buffer, time = max over ranks
+    # every rank drives its own GPU from its own host buffer, time = max over ranks.  Beside it: the copy-only ceiling of
+    # the same three-slot pipeline (ops = "": one cudaMemcpyAsync per chunk each way, no kernel) and the uint32 wire format.
     e2e = None
     if not args.no_e2e:
         Be = min(B, args.e2e_batch)
+        ksteps = max(3, min(K, 10))
+
+        def timed_host(call):
+            call()                       # warm-up (allocates staging, creates streams)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                call()
+            return reduce_max((time.perf_counter() - t0) / ksteps)
+
         h = torch.empty(Be, t.n, 1, dtype=torch.int64).pin_memory()
         h.copy_(x[:Be])
         h0 = h[:2].clone()
-        t.apply_host("CRT,CRTInv", h)      # warm-up (allocates staging, creates streams)
-        ksteps = max(3, min(K, 10))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            capi.check(t.plan.apply_host("CRT,CRTInv", h.data_ptr(), Be))
-        dt = (time.perf_counter() - t0) / ksteps
-        dt_t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-        dt = float(dt_t.item())
+        dt = timed_host(lambda: capi.check(t.plan.apply_host("CRT,CRTInv", h.data_ptr(), Be)))
         assert torch.equal(h[:2], h0)
-        e2e = {"value": world * Be / dt, "unit": UNIT, "h2d_bytes_per_step": world * Be * N_COEFF * 8,
-               "d2h_bytes_per_step": world * Be * N_COEFF * 8, "batch_per_gpu": Be, "ms_per_step": dt * 1e3,
-               "api": "lolb_rq_apply_host(plan, \"CRT,CRTInv\", host_ptr, batch) per rank"}
+        dt_copy = timed_host(lambda: capi.check(t.plan.apply_host("", h.data_ptr(), Be)))
         del h
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        h32 = torch.empty(Be, t.n, 1, dtype=torch.int32).pin_memory()
+        h32.copy_(x[:Be])
+        h32_0 = h32[:2].clone()
+        dt32 = timed_host(lambda: capi.check(t.plan.apply_host_u32("CRT,CRTInv", h32.data_ptr(), Be)))
+        assert torch.equal(h32[:2], h32_0)
+        dt32_copy = timed_host(lambda: capi.check(t.plan.apply_host_u32("", h32.data_ptr(), Be)))
+        del h32
+        wire = world * Be * N_COEFF * 8
+        e2e = {"value": world * Be / dt, "unit": UNIT, "h2d_bytes_per_step": wire, "d2h_bytes_per_step": wire,
+               "batch_per_gpu": Be, "ms_per_step": dt * 1e3,
+               "api": "lolb_rq_apply_host(plan, \"CRT,CRTInv\", host_ptr, batch) per rank",
+               "GB/s_each_way": wire / dt / 1e9,
+               "copy_only_ceiling": {"value": world * Be / dt_copy, "ms_per_step": dt_copy * 1e3, "GB/s_each_way": wire / dt_copy / 1e9,
+                                     "what": "same 3-slot pipeline, same buffers, no kernels (ops = \"\")"},
+               "frac_of_copy_ceiling": dt_copy / dt,
+               "u32_wire": {"value": world * Be / dt32, "ms_per_step": dt32 * 1e3, "h2d_bytes_per_step": wire // 2,
+                            "d2h_bytes_per_step": wire // 2, "GB/s_each_way": wire / 2 / dt32 / 1e9,
+                            "frac_of_copy_ceiling": dt32_copy / dt32, "vs_int64_wire": dt / dt32,
+                            "api": "lolb_rq_apply_host_u32 (uint32 residues on the host, widened on the device)"},
+               "host_binding": numa}
 
     peak, peak_src = measured_peak()
-    dom_name, dom_ms = ("tensorCRTInvRq", inv_ms) if inv_ms >= crt_ms else ("tensorCRTRq", crt_ms)
-    alg_bytes = BYTES_PER_ELEM * B
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = recorded_traffic()
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic or {}).get(dom_name), "kernel": dom_name + " [" + t.plan.kernel_name("CRTInv" if dom_name.endswith("InvRq") else "CRT") + "]",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "ms_per_launch": {"tensorCRTRq": crt_ms, "tensorCRTInvRq": inv_ms},
-                "frac_per_kernel": {"tensorCRTRq": alg_bytes / (crt_ms * 1e-3) / 1e9 / peak,
-                                    "tensorCRTInvRq": alg_bytes / (inv_ms * 1e-3) / 1e9 / peak}}
+    rec = Recorder()
+    timed = lambda fn, iters=5: (fn(), fn(), time_op(torch, fn, iters))[2]
 
-    # ---- other operators of the path, device-resident (not part of the headline value)
-    per_op = {}
+    # ---- other operators of the path at config A, device-resident (not part of the headline value)
     if not args.no_per_op:
         y2 = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
         ops = {"L": (lambda: t.plan.op("L", ptr, B, stream), 16), "LInv": (lambda: t.plan.op("LInv", ptr, B, stream), 16),
@@ -349,68 +436,59 @@ def run_gpu_arm(args):
                "CRTMul": (lambda: t.plan.crt_mul(ptr, y2.data_ptr(), B, B, stream), 24),          # y <- CRT(y) . b, one pass
                "MulCRTInv": (lambda: t.plan.mul_crt_inv(ptr, y2.data_ptr(), B, B, stream), 24)}   # y <- CRTInv(y . b), one pass
         for name, (fn, bpc) in ops.items():
-            fn(); fn()
-            ms = time_op(torch, fn, 10)
-            gbs = bpc * N_COEFF * B / (ms * 1e-3) / 1e9
-            per_op[name] = {"ms": ms, "elems_per_s": B / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak, "kernel": t.plan.kernel_name(name)}
+            call = (lambda f: (lambda: capi.check(f())))(fn)      # a failing operator must not be timed as a no-op
+            rec.add("per_op (config A)", name, timed(call, 10), bpc * N_COEFF * B, B, kernel=t.plan.kernel_name(name))
         del y2
+    del x
+    torch.cuda.empty_cache()
 
-    # ---- the other BASELINE.json configurations, device-resident (informational; parity for each is in tests/)
-    other = {}
-    if not args.no_per_op and world == 1:
-        def timed(fn, iters=5):
-            fn(); fn()
-            return time_op(torch, fn, iters)
-
-        def rq_config(m, qs, Bc, label):
+    # ---- the other BASELINE.json configurations and the reference's own benchmark rings, device-resident, on every rank
+    # (informational; parity for each is in tests/)
+    if not args.no_per_op:
+        def rq_config(label, m, qs, Bc):
             tc = CudaTensorRq(m, qs)
             kc = len(qs)
             xc = torch.cat([torch.randint(0, q, (Bc, tc.n, 1), dtype=torch.int64, device="cuda", generator=gen) for q in qs], dim=2).contiguous()
-            res = {"m": m, "qs": qs, "batch": Bc, "bytes_per_elem_per_transform": 16 * tc.n * kc}
             for name in ("CRT", "CRTInv"):
                 ms = timed(lambda: capi.check(tc.plan.op(name, xc.data_ptr(), Bc, stream)))
-                gbs = 16 * tc.n * kc * Bc / (ms * 1e-3) / 1e9
-                res[name] = {"ms": ms, "elems_per_s": Bc / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak, "kernel": tc.plan.kernel_name(name)}
+                rec.add(label, name, ms, 16 * tc.n * kc * Bc, Bc, kernel=tc.plan.kernel_name(name), batch=Bc)
             xb = xc.clone()
             ms = timed(lambda: capi.check(tc.plan.mul(xc.data_ptr(), xb.data_ptr(), Bc, Bc, stream)))
-            gbs = 24 * tc.n * kc * Bc / (ms * 1e-3) / 1e9
-            res["mulRq"] = {"ms": ms, "elems_per_s": Bc / (ms * 1e-3), "GB/s": gbs, "frac": gbs / peak, "kernel": tc.plan.kernel_name("mulRq")}
-            other[label] = res
+            rec.add(label, "mulRq", ms, 24 * tc.n * kc * Bc, Bc, kernel=tc.plan.kernel_name("mulRq"), batch=Bc)
+            del xc, xb, tc
+            torch.cuda.empty_cache()
 
-        del x
-        torch.cuda.empty_cache()
-        rq_config(65536, [537133057, 537591809, 537722881, 538116097], 1024, "configs[2]: m=2^16, four ~30-bit primes")
-        rq_config(14400, [1008001, 1065601], 32768, "configs[3] moduli: m=14400, q=(1008001,1065601) (SymmSHE key-switch modulus)")
-        rq_config(2048, [12289], 131072, "the reference's own benchmark parameters (lol Benchmarks/Default.hs:41-46): m=2^11, q=12289")
+        rq_config("cfgB", 65536, [537133057, 537591809, 537722881, 538116097], 1024)       # configs[2]: m=2^16, four ~30-bit primes
+        rq_config("cfgC", 14400, [1008001, 1065601], 32768)                                  # configs[3] moduli (SymmSHE key-switch modulus)
+        # the reference's own benchmark parameters (lol Benchmarks/Default.hs:41-48), ~1 GiB batches
+        rq_config("F2048/12289", 2048, [12289], 131072)
+        rq_config("F64*F27/3457", 1728, [3457], 262144)
+        rq_config("F64*F81/10369", 5184, [10369], 81920)
+        rq_config("F32*F7*F13/8737", 2912, [8737], 122880)
+        rq_config("F8*F5*F7*F13/14561", 3640, [14561], 122880)
         from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
         Bg = 32768
         tr, ti, tcx = CudaTensorReal(M), CudaTensorInt(M), CudaTensorComplex(M)
         dg = torch.randn(Bg, tr.n, 1, dtype=torch.float64, device="cuda", generator=gen)
         zg = torch.randint(-8, 9, (Bg, tr.n, 1), dtype=torch.int64, device="cuda", generator=gen)
         og = torch.empty(Bg, 1, dtype=torch.int64, device="cuda")
-        res = {"m": M, "batch": Bg}
-        ms = timed(lambda: capi.check(tr.plan.op("GaussianDec", dg.data_ptr(), Bg, stream)))
-        res["tensorGaussianDec"] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 16 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak}
-        ms = timed(lambda: capi.check(ti.plan.normsq("R", zg.data_ptr(), og.data_ptr(), Bg, stream)))
-        res["tensorNormSqR"] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 8 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak}
+        sec = "cfg4"      # configs[4]: m=14400 tensorGaussianDec + tensorNormSqR (double / int64), complex CRT
+        rec.add(sec, "tensorGaussianDec", timed(lambda: capi.check(tr.plan.op("GaussianDec", dg.data_ptr(), Bg, stream))), 16 * tr.n * Bg, Bg)
+        rec.add(sec, "tensorNormSqR", timed(lambda: capi.check(ti.plan.normsq("R", zg.data_ptr(), og.data_ptr(), Bg, stream))), 8 * tr.n * Bg, Bg)
         cg = torch.randn(Bg, tr.n, 1, dtype=torch.complex128, device="cuda")
         for name in ("CRTC", "CRTInvC"):
             ms = timed(lambda: capi.check(tcx.plan.op(name, cg.data_ptr(), Bg, stream)))
-            res["tensor" + name] = {"ms": ms, "elems_per_s": Bg / (ms * 1e-3), "frac": 32 * tr.n * Bg / (ms * 1e-3) / 1e9 / peak,
-                                    "kernel": tcx.plan.kernel_name(name)}
-        other["configs[4]: m=14400 tensorGaussianDec + tensorNormSqR (double / int64), complex CRT"] = res
-        del dg, zg, cg
-        x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
+            rec.add(sec, "tensor" + name, ms, 32 * tr.n * Bg, Bg, kernel=tcx.plan.kernel_name(name))
+        del dg, zg, cg, og
+        torch.cuda.empty_cache()
 
     # ---- configs[3]: SymmSHE ciphertext multiply + quadratic key switch (SymmSHE.hs:443-449 then :359-372; op sequence of
     # SURVEY.md section 3.5 with TrivGad over the two limbs, l = 2: 4 CRT, tensor product with mulG, CRTInv, decompose,
-    # l CRT, knapsack -- (22 + 4l) x 8nk algorithmic bytes per pair).  Measured on one GPU only: ranks other than 0 have
-    # left by now, and ciphertext pairs shard exactly like the ring elements of the headline step (no collective).
-    she_res = None
-    if not args.no_per_op and world == 1:
+    # l CRT, knapsack -- (22 + 4l) x 8nk algorithmic bytes per pair).  Ciphertext pairs shard over the GPUs exactly like
+    # the ring elements of the headline step (hints replicated, no collective): every rank runs its shard.
+    she_extra = {}
+    if not args.no_per_op:
         from lol_b200.symmshe import CudaSymmSHE
-        del x
-        torch.cuda.empty_cache()
         qs_c, Bs = [1008001, 1065601], args.she_pairs
         she = CudaSymmSHE(M, qs_c, gad_base=0)
         cts = [torch.cat([torch.randint(0, q, (Bs, she.n, 1), dtype=torch.int64, device="cuda", generator=gen) for q in qs_c], dim=2).contiguous()
@@ -425,69 +503,106 @@ def run_gpu_arm(args):
         l0 = capi.kernel_launch_count()
         she_step()
         she_launches = capi.kernel_launch_count() - l0
-        ms = time_op(torch, she_step, 10)
         elem = 8 * she.n * she.k
         alg = (22 + 4 * she.ell) * elem
-        she_res = {"workload": f"configs[3]: m=14400, q=(1008001,1065601), TrivGad (l={she.ell}), {Bs} ciphertext pairs per GPU, "
-                               "Pow-basis inputs, in place", "ms": ms, "ct_pairs_per_s": Bs / (ms * 1e-3),
-                   "algorithmic_bytes_per_pair": alg, "GB/s_per_gpu": alg * Bs / (ms * 1e-3) / 1e9,
-                   "frac": alg * Bs / (ms * 1e-3) / 1e9 / peak, "kernel_launches_per_step": int(she_launches)}
-        if True:
-            d3 = she.mulCT(cts[:2], cts[2:], basis="crt")
-            dg = she.decompose(cts[0])
-            steps = {"ct_mul": (lambda: capi.check(she.t.plan.ct_mul(*[c.data_ptr() for c in cts], *[d.data_ptr() for d in d3], Bs, True, stream)), 7),
-                     "decompose": (lambda: capi.check(she.t.plan.decompose(cts[0].data_ptr(), dg.data_ptr(), Bs, 0, stream)), 1 + she.ell),
-                     "knapsack": (lambda: capi.check(she.t.plan.knapsack(dg.data_ptr(), she.ell, hint.data_ptr(), d3[0].data_ptr(), d3[1].data_ptr(), Bs, stream)), she.ell + 4)}
-            for name, (fn, passes) in steps.items():
-                fn(); fn()
-                sms = time_op(torch, fn, 10)
-                she_res[name] = {"ms": sms, "GB/s": passes * elem * Bs / (sms * 1e-3) / 1e9, "frac": passes * elem * Bs / (sms * 1e-3) / 1e9 / peak}
-            del d3, dg
-            if not args.no_cpu:      # the same sequence on one host core: compiled reference CRTs + numpy for the Haskell-side steps
-                import time as _time
-                import numpy as np
-                from oracle import cpu as ocpu, symmshe as osym, tables as T
-                lib = ocpu.reference() if ocpu.have_reference() else ocpu.restatement()
-                pe = T.pe_array(M)
-                tabs = (pe, T.ru_tables_zq(M, qs_c), T.ru_tables_zq(M, qs_c, True), [T.mhat_inv(M, q) for q in qs_c], T.g_crt_vectors(M, qs_c)[0])
-                rng = np.random.default_rng(0)
-                mk = lambda: np.stack([rng.integers(0, q, size=she.n) for q in qs_c], axis=-1).astype(np.int64)
-                hint_h = hint.cpu().numpy()
-                sample = 8
-                t0 = _time.perf_counter()
-                for _ in range(sample):
-                    osym.mul_and_switch(lib, [mk(), mk()], [mk(), mk()], hint_h, tabs, qs_c, 0)
-                she_res["cpu_baseline"] = {"value": sample / (_time.perf_counter() - t0), "unit": "ct_pairs/s", "cores": 1,
-                                           "kind": "reference" if ocpu.have_reference() else "port",
-                                           "sample": f"{sample} ciphertext pairs, reference CRTs + numpy host steps"}
+        sec = "she"
+        if world > 1:
+            dist.barrier()
+        rec.add(sec, "mulAndSwitch", time_op(torch, she_step, 10), alg * Bs, Bs, kernel_launches_per_step=int(she_launches),
+                workload=f"configs[3]: m=14400, q=(1008001,1065601), TrivGad (l={she.ell}), {Bs} ciphertext pairs per GPU, Pow-basis inputs, in place",
+                algorithmic_bytes_per_pair=alg)
+        d3 = she.mulCT(cts[:2], cts[2:], basis="crt")
+        dg = she.decompose(cts[0])
+        steps = {"ct_mul": (lambda: capi.check(she.t.plan.ct_mul(*[c.data_ptr() for c in cts], *[d.data_ptr() for d in d3], Bs, True, stream)), 7),
+                 "decompose": (lambda: capi.check(she.t.plan.decompose(cts[0].data_ptr(), dg.data_ptr(), Bs, 0, stream)), 1 + she.ell),
+                 "knapsack": (lambda: capi.check(she.t.plan.knapsack(dg.data_ptr(), she.ell, hint.data_ptr(), d3[0].data_ptr(), d3[1].data_ptr(), Bs, stream)), she.ell + 4)}
+        for name, (fn, passes) in steps.items():
+            rec.add(sec, name, timed(fn, 10), passes * elem * Bs, Bs)
+        del d3, dg
+        if rank == 0 and world == 1 and not args.no_cpu:      # the same sequence on one host core: compiled reference CRTs + numpy host steps
+            import numpy as np
+            from oracle import cpu as ocpu, symmshe as osym, tables as T
+            lib = ocpu.reference() if ocpu.have_reference() else ocpu.restatement()
+            pe = T.pe_array(M)
+            tabs = (pe, T.ru_tables_zq(M, qs_c), T.ru_tables_zq(M, qs_c, True), [T.mhat_inv(M, q) for q in qs_c], T.g_crt_vectors(M, qs_c)[0])
+            rng = np.random.default_rng(0)
+            mk = lambda: np.stack([rng.integers(0, q, size=she.n) for q in qs_c], axis=-1).astype(np.int64)
+            hint_h = hint.cpu().numpy()
+            sample = 8
+            t0 = time.perf_counter()
+            for _ in range(sample):
+                osym.mul_and_switch(lib, [mk(), mk()], [mk(), mk()], hint_h, tabs, qs_c, 0)
+            she_extra["cpu_baseline"] = {"value": sample / (time.perf_counter() - t0), "unit": "ct_pairs/s", "cores": 1,
+                                         "kind": "reference" if ocpu.have_reference() else "port",
+                                         "sample": f"{sample} ciphertext pairs, reference CRTs + numpy host steps"}
         del cts, hint
         torch.cuda.empty_cache()
-        x = torch.randint(0, QS[0], (B, t.n, 1), dtype=torch.int64, device="cuda", generator=gen)
-    if she_res is not None:
-        other["configs[3]: SymmSHE ciphertext multiply + key switch"] = she_res
-    if not args.no_per_op and world == 1:
         try:
-            other["ring extensions + coefficient-wise maps (SURVEY 8f ranks 2-3)"] = ext_section(torch, capi, peak, stream)
+            ext_section(torch, capi, rec, stream)
         except Exception as exc:      # informational section: never take the headline line down with it
-            other["ring extensions + coefficient-wise maps (SURVEY 8f ranks 2-3)"] = {"error": f"{type(exc).__name__}: {exc}"}
+            she_extra["ext_section_error"] = f"{type(exc).__name__}: {exc}"
         torch.cuda.empty_cache()
+
+    rec.reduce_max(torch, dist, world)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    dom_name, dom_ms = ("tensorCRTInvRq", inv_ms) if inv_ms >= crt_ms else ("tensorCRTRq", crt_ms)
+    alg_bytes = BYTES_PER_ELEM * B
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = recorded_traffic() or {}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get(dom_name), "traffic_source": traffic.get("source"),
+                "kernel": dom_name + " [" + t.plan.kernel_name("CRTInv" if dom_name.endswith("InvRq") else "CRT") + "]",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "ms_per_launch": {"tensorCRTRq": crt_ms, "tensorCRTInvRq": inv_ms},
+                "frac_per_kernel": {"tensorCRTRq": alg_bytes / (crt_ms * 1e-3) / 1e9 / peak,
+                                    "tensorCRTInvRq": alg_bytes / (inv_ms * 1e-3) / 1e9 / peak}}
 
     cpu_base = None
     if world == 1 and not args.no_cpu:
-        cpu_base = cpu_arm(args.cpu_pairs)
+        cpu_base, _ = cpu_arm(args.cpu_pairs, steps=3, warmup=1)
+
+    detail = rec.table(peak, world)
+    if she_extra:
+        detail["extra"] = she_extra
+    sys.stderr.write("DETAIL " + json.dumps({"n_gpus": world, "peak_GB/s": peak, "sections": detail}) + "\n")
+    sys.stderr.flush()
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        try:
+            with open(os.path.join(out_dir, f"bench_detail_n{world}.json"), "w") as f:
+                json.dump({"n_gpus": world, "peak_GB/s": peak, "sections": detail}, f, indent=1)
+        except OSError:
+            pass
+
+    fr = lambda s, n: rec.frac(peak, s, n)
+    # compact: fractions of the measured HBM peak (max-over-ranks times); she_n = ciphertext pairs/s over all GPUs
+    summary = {"cfgB_crt": fr("cfgB", "CRT"), "cfgB_inv": fr("cfgB", "CRTInv"), "cfgC_crt": fr("cfgC", "CRT"), "cfgC_inv": fr("cfgC", "CRTInv"),
+               "she": fr("she", "mulAndSwitch"), "she_n": None, "m1728": [fr("F64*F27/3457", "CRT"), fr("F64*F27/3457", "CRTInv")],
+               "m5184": [fr("F64*F81/10369", "CRT"), fr("F64*F81/10369", "CRTInv")],
+               "m2912": [fr("F32*F7*F13/8737", "CRT"), fr("F32*F7*F13/8737", "CRTInv")],
+               "m3640": [fr("F8*F5*F7*F13/14561", "CRT"), fr("F8*F5*F7*F13/14561", "CRTInv")],
+               "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec")}
+    for s, n, ms, _, units, _ in rec.rows:
+        if s == "she" and n == "mulAndSwitch":
+            summary["she_n"] = round(world * units / (ms * 1e-3))
+    if e2e:
+        summary["e2e_copy_frac"] = round(e2e["frac_of_copy_ceiling"], 3)
+        summary["e2e_u32"] = round(e2e["u32_wire"]["value"])
 
     line = {
         "metric": METRIC, "value": world * B / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 modular (int64 ABI)", "data": "synthetic",
-        "config": {"workload": "configs[1]: m=14400=64*9*25 (n=3840), Zq 14401, CRT then CRTInv in place, "
-                               f"{B} uniform ring elements per GPU resident in HBM",
-                   "batch_per_gpu": B, "l2": "inputs (1.9 GB per GPU) larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
+        "config": config_dict(world),
         "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clk.summary(), "per_op": per_op, "other_configs": other,
+        "clocks": clk.summary(), "summary": summary,
     }
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -501,7 +616,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--e2e-batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--cpu-pairs", type=int, default=4096, help="CRT+CRTInv pairs per host process in the cpu_baseline sample")
+    ap.add_argument("--cpu-pairs", type=int, default=2048, help="CRT+CRTInv pairs per host process and step in the cpu_baseline sample")
+    ap.add_argument("--ref-pairs", type=int, default=128, help="--impl reference: CRT+CRTInv pairs per host process in one step")
     ap.add_argument("--she-pairs", type=int, default=4096, help="ciphertext pairs per GPU in the configs[3] section")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

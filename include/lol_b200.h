@@ -310,6 +310,14 @@ int lolb_roundCosetRq(const lolb_plan* plan, const double* e, const hInt_t* zp, 
  * the `tensor` prefix and ring suffix).
  */
 int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t* y, int64_t batch);
+/*
+ * The same pipeline over a narrow wire format: `y` holds the residues as uint32 (every modulus the plan accepts is below
+ * 2^32, and the reference itself needs q^2 to fit an int64, types.h:79-84), in the element layout y[(b*totm + j)*tupSize + t].
+ * Half the bytes cross PCIe; the device widens each chunk to the int64 layout, runs the same kernels and narrows the
+ * result.  Replaces one `SV.thaw` + one FFI call per element (CPP.hs:325-337) for callers that keep Z_q vectors as Word32.
+ * An empty `ops` runs the copies alone: the pipeline's ceiling on this host.
+ */
+int lolb_rq_apply_host_u32(const lolb_plan* plan, const char* ops, uint32_t* y, int64_t batch);
 /* pinned host memory for the above (cudaHostAlloc / cudaFreeHost) */
 void* lolb_host_alloc(uint64_t bytes);
 void lolb_host_free(void* p);

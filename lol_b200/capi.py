@@ -190,6 +190,10 @@ class PlanRq:
     def apply_host(self, ops: str, host_ptr: int, batch: int) -> int:
         return int(lib().lolb_rq_apply_host(self._h, ops.encode(), _p(host_ptr), _i64(batch)))
 
+    def apply_host_u32(self, ops: str, host_ptr: int, batch: int) -> int:
+        """lolb_rq_apply_host_u32: the host pipeline over uint32 residues (half the PCIe bytes); ops = "" copies only."""
+        return int(lib().lolb_rq_apply_host_u32(self._h, ops.encode(), _p(host_ptr), _i64(batch)))
+
 
 class PlanC:
     """lolb_plan for the modulus-free rings: int64 'R', double, complex (lolb_plan_create_c)."""
@@ -240,6 +244,17 @@ class PlanC:
 # ------------------------------------------------------------------ ring extensions O_m'/O_m (lolb_ext_*)
 RING_RQ, RING_R, RING_DOUBLE, RING_C = 0, 1, 2, 3
 EXT_INDICES_POWDEC, EXT_INDICES_CRT, EXT_BASE_POW_J0, EXT_BASE_POW_J1, EXT_BASE_DEC, EXT_INDICES_COEFFS = range(6)
+
+
+def fused_w_emulate(pps, qs, y: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """lolb_fused_w_emulate: the fused_w schedule (host-built constants, the kernel's line code compiled for the host, a
+    lane-by-lane replica of the exchange network) on ONE ring element [n][k] in host memory.  Needs no GPU: CPU test hook."""
+    pe = pe_array(pps)
+    q = np.ascontiguousarray(qs, dtype=np.int64)
+    out = np.ascontiguousarray(y, dtype=np.int64).copy()
+    check(lib().lolb_fused_w_emulate(pe.ctypes.data_as(_p), _i16(len(pe)), _i16(len(q)), q.ctypes.data_as(_p), C.c_int(int(inverse)),
+                                     out.ctypes.data_as(_p)))
+    return out
 
 
 def ext_index_table(pps, pps2, which: int) -> np.ndarray:

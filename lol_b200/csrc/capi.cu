@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libctensor_b200.so (include/lol_b200.h): plan management, the batched
 // device-resident operators, the host-batched pipeline and the 29 drop-in symbols of
 // lol-cpp/Crypto/Lol/Cyclotomic/Tensor/CPP/Backend.hs:304-337.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -496,12 +497,34 @@ static int apply_named_rq(const lolb_plan* plan, const std::string& op, hInt_t* 
   return LOLB_ERR_ARG;
 }
 
-// Three-slot ring: slot s carries chunk c = s (mod 3) through  H2D -> kernels -> D2H  on its own stream, so
-// the copy engines (one per direction) and the SMs all stay busy.
-extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t* y, int64_t batch)
+// u32 wire format <-> the int64 ABI layout on the device (lolb_rq_apply_host_u32)
+__global__ void k_widen_u32(const uint32_t* __restrict__ src, int64_t* __restrict__ dst, int64_t n4)
 {
-  if (!plan || plan->kind != PLAN_RQ || !ops || batch < 0 || (batch > 0 && !y)) { set_error("lolb_rq_apply_host: bad argument"); return LOLB_ERR_ARG; }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+    longlong2* o = reinterpret_cast<longlong2*>(dst) + 2 * i;
+    o[0] = make_longlong2((int64_t)v.x, (int64_t)v.y);
+    o[1] = make_longlong2((int64_t)v.z, (int64_t)v.w);
+  }
+}
+__global__ void k_narrow_u32(const int64_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n4)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const longlong2* in = reinterpret_cast<const longlong2*>(src) + 2 * i;
+    const longlong2 a = in[0], b = in[1];
+    __stcs(reinterpret_cast<uint4*>(dst) + i, make_uint4((uint32_t)a.x, (uint32_t)a.y, (uint32_t)b.x, (uint32_t)b.y));
+  }
+}
+
+// Three-slot ring: slot s carries chunk c = s (mod 3) through  H2D -> kernels -> D2H  on its own stream, so
+// the copy engines (one per direction) and the SMs all stay busy.  WIRE = bytes per coefficient on the host side.
+template <class HostT>
+static int apply_host_pipeline(const lolb_plan* plan, const char* fn, const char* ops, HostT* y, int64_t batch)
+{
+  if (!plan || plan->kind != PLAN_RQ || !ops || batch < 0 || (batch > 0 && !y)) { set_error(std::string(fn) + ": bad argument"); return LOLB_ERR_ARG; }
+  if (!plan_device_ok(plan, fn)) return LOLB_ERR_ARG;
   if (batch == 0) return LOLB_OK;
+  constexpr bool NARROW = sizeof(HostT) == 4;
   std::vector<std::string> names;
   {
     std::string cur;
@@ -510,14 +533,17 @@ extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t
       else if (*c != ' ') cur.push_back(*c);
     }
   }
-  const size_t elem_bytes = (size_t)plan->n * plan->k * sizeof(int64_t);
+  const size_t elem_words = (size_t)plan->n * plan->k;
+  const size_t elem_bytes = elem_words * sizeof(int64_t), wire_bytes = elem_words * sizeof(HostT);
+  if (NARROW && elem_words % 4 != 0) { set_error(std::string(fn) + ": the u32 wire format needs totm * tupSize to be a multiple of 4"); return LOLB_ERR_ARG; }
   const int slots = 3;
   static size_t slot_mib = 0;                                          // LOLB_STAGE_MIB: tuning override
   if (!slot_mib) { const char* v = getenv("LOLB_STAGE_MIB"); slot_mib = v && atoi(v) > 0 ? (size_t)atoi(v) : 96; }
-  int64_t chunk = (int64_t)((slot_mib << 20) / elem_bytes);            // ~96 MiB per slot
+  int64_t chunk = (int64_t)((slot_mib << 20) / elem_bytes);            // ~96 MiB of int64 elements per slot
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
-  int rc = plan_reserve_stage(plan, (size_t)slots * chunk * elem_bytes);
+  const size_t slot_bytes = (size_t)chunk * (elem_bytes + (NARROW ? wire_bytes : 0));
+  int rc = plan_reserve_stage(plan, (size_t)slots * slot_bytes);
   if (rc) return rc;
   for (int s = 0; s < slots; s++)
     if (!plan->streams[s]) LOLB_CUDA(cudaStreamCreateWithFlags(&plan->streams[s], cudaStreamNonBlocking));
@@ -525,21 +551,33 @@ extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t
   for (int c = 0; done < batch; c++) {
     const int s = c % slots;
     const int64_t cnt = (batch - done < chunk) ? batch - done : chunk;
-    hInt_t* dev = (hInt_t*)((char*)plan->d_stage + (size_t)s * chunk * elem_bytes);
-    hInt_t* host = y + (size_t)done * plan->n * plan->k;
+    hInt_t* dev = (hInt_t*)((char*)plan->d_stage + (size_t)s * slot_bytes);
+    HostT* wire = NARROW ? (HostT*)((char*)dev + (size_t)chunk * elem_bytes) : (HostT*)dev;
+    HostT* host = y + (size_t)done * elem_words;
     cudaStream_t st = plan->streams[s];       // stream order makes slot reuse safe
-    LOLB_CUDA(cudaMemcpyAsync(dev, host, (size_t)cnt * elem_bytes, cudaMemcpyHostToDevice, st));
+    LOLB_CUDA(cudaMemcpyAsync(wire, host, (size_t)cnt * wire_bytes, cudaMemcpyHostToDevice, st));
+    const int64_t n4 = (int64_t)(cnt * elem_words / 4);
+    const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)plan->num_sms * 8);
+    if (NARROW && !names.empty()) { k_widen_u32<<<blocks, 256, 0, st>>>((const uint32_t*)wire, dev, n4); count_launch(); }
     for (const std::string& op : names) {      // kernel workspaces are per stream (plan_ws): the slots never share one
       rc = apply_named_rq(plan, op, dev, cnt, st);
       if (rc) break;
     }
     if (rc) { cudaDeviceSynchronize(); return rc; }
-    LOLB_CUDA(cudaMemcpyAsync(host, dev, (size_t)cnt * elem_bytes, cudaMemcpyDeviceToHost, st));
+    if (NARROW && !names.empty()) { k_narrow_u32<<<blocks, 256, 0, st>>>(dev, (uint32_t*)wire, n4); count_launch(); }
+    LOLB_CUDA(cudaMemcpyAsync(host, wire, (size_t)cnt * wire_bytes, cudaMemcpyDeviceToHost, st));
     done += cnt;
   }
   for (int s = 0; s < slots; s++) LOLB_CUDA(cudaStreamSynchronize(plan->streams[s]));
+  LOLB_CUDA(cudaGetLastError());
   return LOLB_OK;
 }
+
+extern "C" int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t* y, int64_t batch)
+{ return apply_host_pipeline<hInt_t>(plan, __func__, ops, y, batch); }
+
+extern "C" int lolb_rq_apply_host_u32(const lolb_plan* plan, const char* ops, uint32_t* y, int64_t batch)
+{ return apply_host_pipeline<uint32_t>(plan, __func__, ops, y, batch); }
 
 // ------------------------------------------------------------------ drop-in symbols (host pointers, one element)
 

@@ -15,6 +15,12 @@ int fused_a_decompose_crt(const lolb_plan* pl, const void* slot, const int64_t* 
 int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, const int64_t* b, int64_t batch,
                     int64_t b_batch, cudaStream_t st);
 
+// fused_w.cu
+int fused_w_select(lolb_plan* pl, void** slot);
+void fused_w_release(void* slot);
+bool fused_w_available(const void* slot, bool inverse);
+int fused_w_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+
 // fused_pow2.cu
 int fused_pow2_select(lolb_plan* pl, void** slot);
 void fused_pow2_release(void* slot);
@@ -44,6 +50,7 @@ struct FusedSet {
   void* pow2 = nullptr;   // m = 2^e CRT / CRT^-1, limb resident in shared memory (e <= 12, tupSize 3, ...)
   void* ac = nullptr;       // m = 14400 complex CRT / CRT^-1
   void* pow2_df = nullptr;  // m = 2^e CRT / CRT^-1, dataflow kernel with an L2 exchange ring (13 <= e <= 16)
+  void* w = nullptr;        // m = 2^a x odd prime powers (1728, 5184, 2912, 728, 3640, 2016) CRT / CRT^-1
 };
 FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
 }  // namespace
@@ -57,6 +64,7 @@ int fused_select(lolb_plan* pl)
   if (pl->kind != PLAN_RQ) return LOLB_OK;
   if (!pl->fused) pl->fused = new FusedSet();
   int rc = fused_a_select(pl, &set_of(pl)->a);
+  if (!rc) rc = fused_w_select(pl, &set_of(pl)->w);
   if (!rc) rc = fused_pow2_select(pl, &set_of(pl)->pow2);
   if (!rc) rc = fused_pow2_df_select(pl, &set_of(pl)->pow2_df);
   return rc;
@@ -67,6 +75,7 @@ void fused_release(lolb_plan* pl)
   FusedSet* s = set_of(pl);
   if (!s) return;
   fused_a_release(s->a);
+  fused_w_release(s->w);
   fused_pow2_release(s->pow2);
   fused_pow2_df_release(s->pow2_df);
   fused_ac_release(s->ac);
@@ -84,6 +93,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
     if (!strcmp(op, "CRTInvC") && fused_ac_available(s->ac, true)) return "fused_ac";
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
+    if (!strcmp(op, "CRT") && fused_w_available(s->w, false)) return "fused_w";
+    if (!strcmp(op, "CRTInv") && fused_w_available(s->w, true)) return "fused_w";
     if (!strcmp(op, "CRT") && fused_pow2_df_available(s->pow2_df, false)) return "fused_pow2_df";
     if (!strcmp(op, "CRTInv") && fused_pow2_df_available(s->pow2_df, true)) return "fused_pow2_df";
     if (!strcmp(op, "CRT") && fused_pow2_available(s->pow2, false)) return "fused_pow2";
@@ -103,6 +114,7 @@ int fused_crt_rq(const lolb_plan* pl, bool inverse, int64_t* y, int64_t batch, c
   const FusedSet* s = set_of(pl);
   if (!s) return LOLB_FUSED_UNAVAILABLE;
   int rc = fused_a_crt(pl, s->a, inverse, y, batch, st);
+  if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_w_crt(pl, s->w, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_df_crt(pl, s->pow2_df, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2_crt(pl, s->pow2, inverse, y, batch, st);
   return rc;

@@ -1,0 +1,857 @@
+// fused_w.cu -- fused Z_q CRT / CRT^-1 for indices m = 2^a * (one to three odd prime powers): the reference's other
+// benchmark rings (lol/Crypto/Lol/Benchmarks/Default.hs:41-48: F64*F27, F64*F81 and the Twace-Embed rings
+// F32*F7*F13, F8*F7*F13, F8*F5*F7*F13), one HBM read and one HBM write per ring element like fused_a.cu does for m = 14400.
+//
+// The operator is the reference's (crt.cpp:518-581 on tensor.h:76-95): CRT_m = (x)_i CRT_{p_i^e_i}, first factor fastest,
+// CRT_{p^e} = (DFT_{p^(e-1)} (x) I_{p-1}) . That . (I_{p^(e-1)} (x) CRT_p), DFT_{p^(e-1)} as e-1 radix-p rounds with diagonal
+// twiddles between them (ppDFT, crt.cpp:459-486).  Factors on different axes commute and the arithmetic is exact, so the
+// schedule below yields the reference's residues bit for bit.
+//
+//   element X[ic][ib][ia][i1]:  i1 < L = 2^(a-1) (the 2^a axis, fastest), ia, ib the "middle" odd prime powers, ic the last
+//
+//   line     all stages of ONE odd prime power on the phi(p^e) values a thread holds in registers, compile-time indices,
+//            every stage a set of small dense rows  sum_j c_j x_j  accumulated lazily and reduced once; the diagonal
+//            twiddles (crtTwiddle, dftTwiddle) and mhat^-1 are folded into the row constants on the host (kernel
+//            parameter bank: every lane of a warp uses the same constant)
+//   network  the 2^a axis across L lanes: the register-exchange butterfly network of fused_a.cu generalised to any
+//            L = 2 .. 32 and any number of value pairs per lane (sub-warp groups when L < 32)
+//
+//   k_fused_w1  (no last axis: m = 2^a p^e, e.g. 1728, 5184) a group of L lanes owns one ring element: loads its D2 values
+//               per lane straight from HBM, line(s), network, stores.  No shared memory, no barrier.
+//   k_fused_w2  (m = 2^a .. p_c^e_c) phase 1: thread <- one column along ic from HBM, line, u32 tile in shared memory;
+//               phase 2: group of L lanes <- one ic-row of the tile, middle line(s), network, stores.
+#include "fused.cuh"
+#include "numtheory.h"
+
+namespace lolb {
+
+namespace {
+
+#define WHD __host__ __device__ __forceinline__
+
+constexpr int ipw(int b, int e) { return e <= 0 ? 1 : b * ipw(b, e - 1); }
+
+WHD uint32_t w_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+WHD uint32_t w_mulhi(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// ------------------------------------------------------------------ arithmetic (the two policies of fused_a.cu, callable
+// from the host as well so that the device-free emulation below runs the very same line code)
+struct WMod {
+  uint32_t q, q2;
+  uint32_t r0;     // WS: floor(2^32 / q);  WM: -q^-1 mod 2^32
+  uint32_t one;    // WS: 1;                WM: 2^32 mod q
+  uint32_t r2;     // WM: 2^64 mod q
+};
+
+// WS: a row of T terms needs 2 T q^2 < 2^32; residues lazily in [0, 2q), Barrett reduction
+struct WS {
+  typedef uint32_t Acc;
+  uint32_t q, q2, mu, nq;
+  WHD WS(const WMod& M) : q(M.q), q2(M.q2), mu(M.r0), nq(0u - M.q) {}
+  WHD Acc mul(uint32_t c, uint32_t v) const { return c * v; }
+  WHD Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + c * v; }
+  WHD Acc unit(uint32_t v) const { return v; }
+  WHD uint32_t red(Acc x) const { return w_mulhi(x, mu) * nq + x; }
+  WHD uint32_t fold(uint32_t x) const { return w_min(x, x - q2); }
+  WHD uint32_t canon(uint32_t x) const { return w_min(x, x - q); }
+};
+
+// WM: odd q, 2 T q < 2^32; 64-bit accumulation, one Montgomery reduction per row, constants in Montgomery form
+struct WM {
+  typedef uint64_t Acc;
+  uint32_t q, q2, qinv, one;
+  WHD WM(const WMod& M) : q(M.q), q2(M.q2), qinv(M.r0), one(M.one) {}
+  WHD Acc mul(uint32_t c, uint32_t v) const { return (uint64_t)c * v; }
+  WHD Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + (uint64_t)c * v; }
+  WHD Acc unit(uint32_t v) const { return (uint64_t)one * v; }
+  WHD uint32_t red(Acc x) const
+  {
+    const uint32_t m = (uint32_t)x * qinv;
+    return (uint32_t)((x + (uint64_t)m * q) >> 32);
+  }
+  WHD uint32_t fold(uint32_t x) const { return w_min(x, x - q2); }
+  WHD uint32_t canon(uint32_t x) const { return w_min(x, x - q); }
+};
+
+// ------------------------------------------------------------------ one odd prime power p^e: constant layout
+//   M1[i0][r][c]          i0 < p^(e-1); forward  crtTwiddle(i0, r) . CRT_p[r][c]   (crt.cpp:60-79, 248-346)
+//                                       inverse  CRT_p^-1'[r][c] . crtTwiddle(i0, c) (. mhat^-1 on one axis) (crt.cpp:349-457)
+//   W_d[hi][r][a]         round on base-p digit d of i0, hi = the digits above d: forward dftTwiddle(hi, r) . DFT_p[r][a],
+//                         inverse DFT_p[r][a] . dftTwiddle(hi, a)   (crt.cpp:84-126, 131-246, 459-516)
+template <int P, int E>
+struct PPT {
+  static constexpr int p = P, e = E, R = E - 1, mp = ipw(P, E - 1), d = P - 1, phi = (P - 1) * ipw(P, E - 1);
+  static constexpr int n_m1 = mp * d * d;
+  static constexpr int w_off(int dig)
+  {
+    int o = n_m1;
+    for (int t = 0; t < dig; t++) o += ipw(P, R - 1 - t) * P * P;
+    return o;
+  }
+  static constexpr int n_consts = w_off(R);
+};
+template <>
+struct PPT<1, 1> {      // "no prime power here"
+  static constexpr int p = 1, e = 1, R = 0, mp = 1, d = 0, phi = 1, n_m1 = 0, n_consts = 0;
+  static constexpr int w_off(int) { return 0; }
+};
+typedef PPT<1, 1> PPNone;
+
+// one radix-p round on digit DIG of the block index, values of the line at v[base + (i0 * (p-1) + cc) * STRIDE]
+template <class PPx, bool INV, int DIG, int STRIDE, int COFF, class AR, class CT, int NV>
+WHD void pp_round(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
+{
+  constexpr int P = PPx::p, D = PPx::d, R = PPx::R;
+  constexpr int NHI = ipw(P, R - 1 - DIG), NLO = ipw(P, DIG), WOFF = COFF + PPx::w_off(DIG);
+#pragma unroll
+  for (int hi = 0; hi < NHI; hi++) {
+#pragma unroll
+    for (int lo = 0; lo < NLO; lo++) {
+#pragma unroll
+      for (int cc = 0; cc < D; cc++) {
+        uint32_t x[P], o[P];
+#pragma unroll
+        for (int a = 0; a < P; a++) x[a] = v[base + (((hi * P + a) * NLO + lo) * D + cc) * STRIDE];
+#pragma unroll
+        for (int r = 0; r < P; r++) {
+          const bool all_ones = r == 0 && (!INV || hi == 0);      // DFT row 0 carries no twiddle in the forward direction
+          const bool col0_one = INV || hi == 0;                   // the inverse twiddles its inputs: input 0 is never scaled
+          if (all_ones) {
+            uint32_t s = x[0];
+#pragma unroll
+            for (int a = 1; a < P; a++) s += x[a];
+            o[r] = A.red(A.unit(s));
+          } else {
+            typename AR::Acc acc = col0_one ? A.unit(x[0]) : A.mul(C.c[WOFF + (hi * P + r) * P], x[0]);
+#pragma unroll
+            for (int a = 1; a < P; a++) acc = A.mad(acc, C.c[WOFF + (hi * P + r) * P + a], x[a]);
+            o[r] = A.red(acc);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < P; r++) v[base + (((hi * P + r) * NLO + lo) * D + cc) * STRIDE] = o[r];
+      }
+    }
+  }
+}
+
+template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, int NV>
+WHD void pp_blocks(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
+{
+  constexpr int D = PPx::d, MP = PPx::mp;
+#pragma unroll
+  for (int i0 = 0; i0 < MP; i0++) {
+    uint32_t o[D];
+#pragma unroll
+    for (int r = 0; r < D; r++) {
+      typename AR::Acc acc = A.mul(C.c[COFF + (i0 * D + r) * D], v[base + (i0 * D) * STRIDE]);
+#pragma unroll
+      for (int cc = 1; cc < D; cc++) acc = A.mad(acc, C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]);
+      o[r] = A.red(acc);
+    }
+#pragma unroll
+    for (int r = 0; r < D; r++) v[base + (i0 * D + r) * STRIDE] = o[r];
+  }
+}
+
+// CRT_{p^e} / CRT_{p^e}^-1 on one line (ppcrt / ppcrtinv, crt.cpp:518-560)
+template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, int NV>
+WHD void pp_line(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
+{
+  if constexpr (PPx::p > 1) {
+    constexpr int R = PPx::R;
+    static_assert(R <= 4, "prime-power exponent too large for the unrolled rounds");
+    if constexpr (!INV) {
+      pp_blocks<PPx, false, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 0) pp_round<PPx, false, 0, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 1) pp_round<PPx, false, 1, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 2) pp_round<PPx, false, 2, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 3) pp_round<PPx, false, 3, STRIDE, COFF>(v, base, C, A);
+    } else {
+      if constexpr (R > 3) pp_round<PPx, true, 3, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 2) pp_round<PPx, true, 2, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 1) pp_round<PPx, true, 1, STRIDE, COFF>(v, base, C, A);
+      if constexpr (R > 0) pp_round<PPx, true, 0, STRIDE, COFF>(v, base, C, A);
+      pp_blocks<PPx, true, STRIDE, COFF>(v, base, C, A);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ shapes
+// A: exponent of 2 (0 or 1: no 2^a axis), PA / PB: the odd prime powers handled together with the 2^a axis, PC: the
+// last prime power (phase 1 of k_fused_w2; PPNone selects k_fused_w1).  EPB: ring elements per CTA iteration (w2).
+template <int A_, class PA_, class PB_, class PC_, int EPB_, int MINB_>
+struct WShape {
+  typedef PA_ PA;
+  typedef PB_ PB;
+  typedef PC_ PC;
+  static constexpr int A = A_, LOG = A_ >= 2 ? A_ - 1 : 0, L = 1 << LOG, GPW = 32 / L;
+  static constexpr int DA = PA::phi, DB = PB::phi, D2 = DA * DB, NP = D2 / 2;
+  static constexpr int COLS = L * D2, ROWS = PC::phi, N = COLS * ROWS;
+  static constexpr int OFF_A = 0, OFF_B = PA::n_consts, OFF_C = PA::n_consts + PB::n_consts;
+  static constexpr int NC = (PA::n_consts + PB::n_consts + PC::n_consts) > 0 ? (PA::n_consts + PB::n_consts + PC::n_consts) : 1;
+  static constexpr int EPB = EPB_, MINB = MINB_;
+  static constexpr bool TWO_PHASE = PC::p > 1;
+  // tile row stride: rows handled by the sub-warp groups of one warp must start in different banks
+  static constexpr int RS = (L >= 32 || COLS % 32 == L % 32) ? COLS : COLS + ((L + 32 - COLS % 32) % 32);
+  static_assert(D2 % 2 == 0, "an odd prime power is required next to the 2^a axis");
+};
+
+constexpr int kWLaneRows = 8;      // per-lane constants of the network (see build_lane_table)
+constexpr int kWThreads = 128;
+
+template <int NC>
+struct WConsts {
+  WMod mod;
+  const uint32_t* lane_tw;      // device [kWLaneRows][32]
+  uint32_t c[NC];
+};
+
+// ------------------------------------------------------------------ the 2^a axis across L lanes
+// State: the lane holds NP pairs (v[2j], v[2j+1]).  Round on lane bit b: the lane keeps one value of each pair, swaps the
+// other with lane ^ 2^b and then owns both inputs of NP butterflies.  Forward (u,t) -> (u+t, (u-t) tw); inverse
+// (u,t) -> (u + t tw, u - t tw).  Ownership afterwards (derived in DESIGN.md 4.9):
+//   forward: pair j, slot s  =  odd-axis row 2j + (l & 1),          column (s << (LOG-1)) | (l >> 1)
+//   inverse: pair j, slot s  =  odd-axis row 2j + (l >> (LOG-1)),   column 2 (l & (L/2 - 1)) + s
+template <bool INV, bool TRIVIAL, int NP, class AR>
+__device__ __forceinline__ void w_round(uint32_t (&v)[2 * NP], const int l, const int bit, const uint32_t tw, const AR& A)
+{
+  const bool hi = (l >> bit) & 1;
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    const uint32_t send = hi ? v[2 * j] : v[2 * j + 1];
+    const uint32_t keep = hi ? v[2 * j + 1] : v[2 * j];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+    if (TRIVIAL) {                 // every twiddle of the round is 1 (crt.cpp:92-106 skips i0 = 0)
+      const uint32_t u = hi ? recv : keep, t = hi ? keep : recv;
+      v[2 * j] = A.fold(u + t);
+      v[2 * j + 1] = A.fold(u + A.q2 - t);
+    } else if (!INV) {             // u + t is symmetric; the sign of u - t lives in the lane's twiddle (host: -tw for hi lanes)
+      v[2 * j] = A.fold(keep + recv);
+      v[2 * j + 1] = A.red(A.mul(tw, keep + A.q2 - recv));
+    } else {
+      const uint32_t t = A.red(A.mul(tw, hi ? keep : recv));
+      const uint32_t u = hi ? recv : keep;
+      v[2 * j] = A.fold(u + t);
+      v[2 * j + 1] = A.fold(u + A.q2 - t);
+    }
+  }
+}
+
+// last inverse round (lane bit 0) merged with the inverse crtTwiddle of the 2^a axis: the lane ends with columns 2c, 2c+1
+// whose twiddles a, b are per-lane constants:  a (u + tw t) = a u + (a tw) t,  b (u - tw t) = b u + (-b tw) t
+template <int NP, class AR>
+__device__ __forceinline__ void w_last_inv(uint32_t (&v)[2 * NP], const int l, const uint32_t a, const uint32_t atw, const uint32_t b,
+                                           const uint32_t nbtw, const AR& A)
+{
+  const bool hi = l & 1;
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    const uint32_t send = hi ? v[2 * j] : v[2 * j + 1];
+    const uint32_t keep = hi ? v[2 * j + 1] : v[2 * j];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
+    v[2 * j] = A.red(A.mad(A.mul(a, u), atw, t));
+    v[2 * j + 1] = A.red(A.mad(A.mul(b, u), nbtw, t));
+  }
+}
+
+// lane-table rows: forward [0] crtTwiddle of the lane's column, [1 + r] round r (r < LOG-1; the sign of hi lanes folded in);
+// inverse [r] round r (1 <= r < LOG-1), [4] a, [5] a tw_0, [6] b, [7] -b tw_0
+template <int LOG, bool INV, int NP, class AR>
+__device__ __forceinline__ void w_network(uint32_t (&v)[2 * NP], const int l, const uint32_t (&lt)[kWLaneRows], const AR& A)
+{
+  if constexpr (LOG >= 1) {
+    if constexpr (!INV) {
+#pragma unroll
+      for (int i = 0; i < 2 * NP; i++) v[i] = A.red(A.mul(lt[0], v[i]));      // crtTwiddle (crt.cpp:43-58)
+#pragma unroll
+      for (int r = 0; r < LOG - 1; r++) w_round<false, false, NP>(v, l, r, lt[1 + r], A);
+      w_round<false, true, NP>(v, l, LOG - 1, 0u, A);
+    } else {
+      if constexpr (LOG >= 2) w_round<true, true, NP>(v, l, LOG - 1, 0u, A);
+#pragma unroll
+      for (int r = LOG - 2; r >= 1; r--) w_round<true, false, NP>(v, l, r, lt[r], A);
+      w_last_inv<NP>(v, l, lt[4], lt[5], lt[6], lt[7], A);
+    }
+  }
+}
+
+// position inside a block of D2 * L coefficients of value (pair j, slot s) after the network
+template <int LOG, bool INV>
+__device__ __forceinline__ int w_out_pos(const int l, const int j, const int s)
+{
+  constexpr int L = 1 << LOG;
+  if constexpr (LOG == 0) return 2 * j + s;
+  else if constexpr (!INV) return (2 * j + (l & 1)) * L + ((s << (LOG - 1)) | (l >> 1));
+  else return (2 * j + (l >> (LOG - 1))) * L + 2 * (l & (L / 2 - 1)) + s;
+}
+
+__device__ __noinline__ uint32_t w_reduce_any(int64_t x, uint32_t q)      // non-canonical input, like `c % q` (types.h:62-66)
+{
+  int64_t r = x % (int64_t)q;
+  return (uint32_t)(r < 0 ? r + q : r);
+}
+
+// middle line(s) + network + store of one group's block of D2 * L coefficients
+template <class SH, bool INV, class AR, int K>
+__device__ __forceinline__ void w_finish(uint32_t (&v)[SH::D2], const int l, const uint32_t (&lt)[kWLaneRows], const WConsts<SH::NC>& C,
+                                         const AR& A, int64_t* __restrict__ dst /* block base (+ limb) */, const int k, const bool live)
+{
+  // axis a: stride 1, one line per ib;  axis b: stride DA, one line per ia
+#pragma unroll
+  for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v, ib * SH::DA, C, A);
+#pragma unroll
+  for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v, ia, C, A);
+  w_network<SH::LOG, INV, SH::NP>(v, l, lt, A);
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < SH::NP; j++) {
+      const int64_t a = (int64_t)A.canon(v[2 * j]), b = (int64_t)A.canon(v[2 * j + 1]);
+      if (INV && K == 1 && SH::LOG >= 1) {
+        __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LOG, INV>(l, j, 0)), make_longlong2(a, b));
+      } else {
+        __stcs(dst + (size_t)w_out_pos<SH::LOG, INV>(l, j, 0) * k, a);
+        __stcs(dst + (size_t)w_out_pos<SH::LOG, INV>(l, j, 1) * k, b);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ m = 2^a p^e (p_b^e_b): a group of L lanes per element
+template <class SH, bool INV, class AR, int K>
+__global__ void __launch_bounds__(kWThreads, SH::MINB)
+k_fused_w1(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const int limb, const __grid_constant__ WConsts<SH::NC> C)
+{
+  const int k = K ? K : k_rt;
+  const AR A(C.mod);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = lane & (SH::L - 1), sub = lane >> SH::LOG;
+  uint32_t lt[kWLaneRows];
+#pragma unroll
+  for (int i = 0; i < kWLaneRows; i++) lt[i] = C.lane_tw[i * 32 + lane];
+  const int64_t nwt = (batch + SH::GPW - 1) / SH::GPW;      // warp-tasks: GPW elements each
+  for (int64_t wt = (int64_t)blockIdx.x * (kWThreads / 32) + warp; wt < nwt; wt += (int64_t)gridDim.x * (kWThreads / 32)) {
+    const int64_t e = wt * SH::GPW + sub;
+    const bool live = e < batch;
+    int64_t* ebase = y + (size_t)(live ? e : 0) * SH::N * k + limb;
+    const int64_t* src = ebase + (size_t)l * k;
+    uint32_t v[SH::D2];
+    uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+    for (int i = 0; i < SH::D2; i++) {      // every load is issued before the first use
+      const int64_t raw = live ? __ldcs(src + (size_t)(i * SH::L) * k) : 0;
+      v[i] = (uint32_t)raw;
+      hi_or |= (uint32_t)((uint64_t)raw >> 32);
+      lo_max = max(lo_max, v[i]);
+    }
+    if (hi_or != 0 || lo_max >= C.mod.q) {
+#pragma unroll
+      for (int i = 0; i < SH::D2; i++) v[i] = w_reduce_any(src[(size_t)(i * SH::L) * k], C.mod.q);
+    }
+    w_finish<SH, INV, AR, K>(v, l, lt, C, A, ebase, k, live);
+  }
+}
+
+// ------------------------------------------------------------------ m = 2^a (p_a^e_a) (p_b^e_b) p_c^e_c: two phases, u32 tile
+template <class SH, bool INV, class AR, int K>
+__global__ void __launch_bounds__(kWThreads, SH::MINB)
+k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const int limb, const __grid_constant__ WConsts<SH::NC> C)
+{
+  typedef typename SH::PC PC;
+  constexpr int EPB = SH::EPB, COLS = SH::COLS, ROWS = SH::ROWS, RS = SH::RS, N = SH::N;
+  const int k = K ? K : k_rt;
+  __shared__ uint32_t tile[EPB * ROWS * RS];
+  const AR A(C.mod);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = lane & (SH::L - 1), sub = lane >> SH::LOG;
+  uint32_t lt[kWLaneRows];
+#pragma unroll
+  for (int i = 0; i < kWLaneRows; i++) lt[i] = C.lane_tw[i * 32 + lane];
+  const int64_t ngroups = (batch + EPB - 1) / EPB;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t e0 = g * EPB;
+    const int cnt = (int)(batch - e0 < EPB ? batch - e0 : EPB);
+    // ---------------- phase 1: the last prime power; thread-task = (element slot, column), coefficients at stride COLS
+    for (int t = threadIdx.x; t < cnt * COLS; t += kWThreads) {
+      const int slot = t / COLS, col = t - slot * COLS;
+      const int64_t* src = y + ((size_t)(e0 + slot) * N + col) * k + limb;
+      uint32_t v[ROWS];
+      uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) {
+        const int64_t raw = __ldcs(src + (size_t)(i * COLS) * k);
+        v[i] = (uint32_t)raw;
+        hi_or |= (uint32_t)((uint64_t)raw >> 32);
+        lo_max = max(lo_max, v[i]);
+      }
+      if (hi_or != 0 || lo_max >= C.mod.q) {
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) v[i] = w_reduce_any(src[(size_t)(i * COLS) * k], C.mod.q);
+      }
+      pp_line<PC, INV, 1, SH::OFF_C>(v, 0, C, A);
+      uint32_t* dst = tile + slot * ROWS * RS + col;
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) dst[i * RS] = v[i];
+    }
+    __syncthreads();
+    // ---------------- phase 2: group-task = (element slot, row ic); L lanes x D2 values, middle lines + network
+    const int ntask = cnt * ROWS;
+    for (int t0 = warp * SH::GPW; t0 < ntask; t0 += (kWThreads / 32) * SH::GPW) {      // warp-uniform trip count
+      const int t = t0 + sub;
+      const bool live = t < ntask;
+      const int tt = live ? t : 0;
+      const int slot = tt / ROWS, row = tt - slot * ROWS;
+      const uint32_t* srow = tile + (slot * ROWS + row) * RS + l;
+      uint32_t v[SH::D2];
+#pragma unroll
+      for (int i = 0; i < SH::D2; i++) v[i] = srow[i * SH::L];
+      int64_t* dst = y + ((size_t)(e0 + slot) * N + (size_t)row * COLS) * k + limb;
+      w_finish<SH, INV, AR, K>(v, l, lt, C, A, dst, k, live);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ host: constants from the plan's root tables
+
+enum WClass { WC_NONE = 0, WC_S, WC_M };
+
+inline WClass w_class(uint64_t q, int pmax)
+{
+  if (2 * (uint64_t)pmax * q * q < ((uint64_t)1 << 32)) return WC_S;
+  if ((q & 1) && 2 * (uint64_t)pmax * q < ((uint64_t)1 << 32)) return WC_M;
+  return WC_NONE;
+}
+
+struct RootTab {      // root table of one prime power for one limb (forward or inverse roots), canonical
+  const std::vector<int64_t>* tab;
+  int k, limb;
+  int64_t pp;
+  uint64_t q;
+  uint64_t operator()(int64_t j) const
+  {
+    int64_t v = (*tab)[(size_t)(((j % pp) + pp) % pp) * k + limb] % (int64_t)q;
+    if (v < 0) v += q;
+    return (uint64_t)v;
+  }
+};
+
+// constants of prime power (p, e) into out[0 .. n_consts): layout of PPT; `scale` multiplies the inverse block matrices
+void build_pp_consts(int p, int e, bool inverse, const RootTab& T, uint64_t scale, uint32_t* out)
+{
+  const uint64_t q = T.q;
+  const int d = p - 1, R = e - 1;
+  const int64_t mp = ipow64(p, e - 1);
+  size_t o = 0;
+  for (int64_t i0 = 0; i0 < mp; i0++)
+    for (int r = 0; r < d; r++)
+      for (int c = 0; c < d; c++) {
+        uint64_t v;
+        if (!inverse) {        // crtTwiddle(i0, r) . w_p^((r+1) c)
+          const uint64_t tw = i0 ? T(digit_rev(p, R, i0) * (r + 1)) : 1;
+          v = mulmod64(tw, T(mp * (((int64_t)(r + 1) * c) % p)), q);
+        } else {               // (w^-(r (c+1)) - w^(c+1)) . crtTwiddle(i0, c) . scale, T = inverse roots (crt.cpp:369-398)
+          const uint64_t tw = i0 ? T(digit_rev(p, R, i0) * (c + 1)) : 1;
+          const uint64_t mat = (T(mp * (((int64_t)r * (c + 1)) % p)) + q - T(mp * (p - c - 1))) % q;
+          v = mulmod64(mulmod64(tw, mat, q), scale % q, q);
+        }
+        out[o++] = (uint32_t)v;
+      }
+  for (int dig = 0; dig < R; dig++) {
+    const int64_t nhi = ipow64(p, R - 1 - dig), stride = ipow64(p, dig + 1);
+    for (int64_t hi = 0; hi < nhi; hi++)
+      for (int r = 0; r < p; r++)
+        for (int a = 0; a < p; a++) {
+          const int x = inverse ? a : r;      // the twiddled index: outputs (forward, after dftp) / inputs (inverse, before dftp)
+          const uint64_t tw = (hi && x) ? T(digit_rev(p, R - 1 - dig, hi) * x * stride) : 1;
+          out[o++] = (uint32_t)mulmod64(tw, T(mp * (((int64_t)r * a) % p)), q);
+        }
+  }
+}
+
+// per-lane constants of the network for 2^a (a >= 2): out[kWLaneRows][32], the group pattern repeated across the warp
+void build_lane_table(int a_exp, bool inverse, const RootTab& T, uint32_t* out)
+{
+  const uint64_t q = T.q;
+  const int LOG = a_exp >= 2 ? a_exp - 1 : 0, L = 1 << LOG;
+  for (int i = 0; i < kWLaneRows * 32; i++) out[i] = 1;
+  if (LOG == 0) return;
+  for (int lane = 0; lane < 32; lane++) {
+    const int l = lane & (L - 1);
+    auto round_tw = [&](int r, int hi_digits) -> uint64_t {      // dftTwiddle of the round on bit r (crt.cpp:92-106)
+      return hi_digits ? T(digit_rev(2, LOG - 1 - r, hi_digits) * ((int64_t)2 << r)) : 1;
+    };
+    if (!inverse) {
+      out[0 * 32 + lane] = (uint32_t)(l ? T(digit_rev(2, LOG, l)) : 1);      // crtTwiddle, column = l
+      for (int r = 0; r < LOG - 1; r++) {
+        const uint64_t tw = round_tw(r, l >> (r + 1));
+        // lanes whose bit r is set hold (t, u) instead of (u, t): they multiply (t - u) by -tw
+        out[(1 + r) * 32 + lane] = (uint32_t)(((l >> r) & 1) ? (q - tw) % q : tw);
+      }
+    } else {
+      for (int r = 1; r < LOG - 1; r++) out[r * 32 + lane] = (uint32_t)round_tw(r, (l >> r) & ((1 << (LOG - 1 - r)) - 1));
+      const uint64_t tw0 = round_tw(0, l & ((1 << (LOG - 1)) - 1));
+      const int col = 2 * (l & (L / 2 - 1));
+      const uint64_t ca = col ? T(digit_rev(2, LOG, col)) : 1, cb = T(digit_rev(2, LOG, col + 1));
+      out[4 * 32 + lane] = (uint32_t)ca;
+      out[5 * 32 + lane] = (uint32_t)mulmod64(ca, tw0, q);
+      out[6 * 32 + lane] = (uint32_t)cb;
+      out[7 * 32 + lane] = (uint32_t)((q - mulmod64(cb, tw0, q)) % q);
+    }
+  }
+}
+
+void w_mod_consts(uint64_t q, int cls, WMod* M)
+{
+  M->q = (uint32_t)q; M->q2 = (uint32_t)(2 * q); M->one = 1; M->r2 = 0;
+  M->r0 = (uint32_t)((((uint64_t)1) << 32) / q);
+  if (cls == WC_M) {
+    uint32_t inv = (uint32_t)q;                       // q * inv == 1 mod 2^3 initially (q odd)
+    for (int i = 0; i < 5; i++) inv *= 2u - (uint32_t)q * inv;
+    M->r0 = 0u - inv;
+    M->one = (uint32_t)((((uint64_t)1) << 32) % q);
+    M->r2 = (uint32_t)((((uint64_t)M->one) << 32) % q);
+  }
+}
+
+inline uint32_t w_mont(uint32_t c, uint64_t q) { return (uint32_t)((((uint64_t)c) << 32) % q); }
+
+// the shape list: one entry per instantiated kernel family
+struct WShapeId { int a; int pa, ea, pb, eb, pc, ec; };
+
+template <class SH>
+constexpr WShapeId shape_id() { return WShapeId{SH::A, SH::PA::p, SH::PA::e, SH::PB::p, SH::PB::e, SH::PC::p, SH::PC::e}; }
+
+#ifndef LOLB_W27_MINB
+#define LOLB_W27_MINB 6      // CTAs of 128 threads per SM the register allocation must allow (tuning: tools/build_variant.py)
+#endif
+#ifndef LOLB_W81_MINB
+#define LOLB_W81_MINB 3
+#endif
+typedef WShape<6, PPT<3, 3>, PPNone, PPNone, 1, LOLB_W27_MINB> SH_64_27;     // m = 1728  (n = 576)
+typedef WShape<6, PPT<3, 4>, PPNone, PPNone, 1, LOLB_W81_MINB> SH_64_81;     // m = 5184  (n = 1728)
+typedef WShape<5, PPT<7, 1>, PPNone, PPT<13, 1>, 4, 4> SH_32_7_13;           // m = 2912  (n = 1152)
+typedef WShape<3, PPT<7, 1>, PPNone, PPT<13, 1>, 16, 4> SH_8_7_13;           // m = 728   (n = 288)
+typedef WShape<3, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 4> SH_8_5_7_13;       // m = 3640  (n = 1152)
+typedef WShape<5, PPT<3, 2>, PPNone, PPT<7, 1>, 4, 4> SH_32_9_7;             // m = 2016  (n = 576)
+
+constexpr int kNumShapes = 6;
+
+struct FusedW {
+  int shape = -1;
+  bool ok_fwd = false, ok_inv = false;
+  std::vector<int> cls;                          // WClass per limb
+  std::vector<std::vector<uint32_t>> cf, ci;     // per limb: flat constants (already in the limb's representation)
+  std::vector<WMod> mod;
+  uint32_t* d_lane = nullptr;                    // [k][2][kWLaneRows][32]
+  std::vector<uint32_t> h_lane;
+};
+
+bool shape_matches(const lolb_plan* pl, const WShapeId& id, int* pmax)
+{
+  std::vector<PrimeExponent> want;
+  if (id.a > 0) want.push_back({2, (hShort_t)id.a});
+  if (id.pa > 1) want.push_back({(hShort_t)id.pa, (hShort_t)id.ea});
+  if (id.pb > 1) want.push_back({(hShort_t)id.pb, (hShort_t)id.eb});
+  if (id.pc > 1) want.push_back({(hShort_t)id.pc, (hShort_t)id.ec});
+  if (want.size() != pl->pe.size()) return false;
+  for (size_t i = 0; i < want.size(); i++)
+    if (want[i].prime != pl->pe[i].prime || want[i].exponent != pl->pe[i].exponent) return false;
+  *pmax = id.pc > 1 ? id.pc : id.pb > 1 ? id.pb : id.pa;
+  return true;
+}
+
+const WShapeId kShapeIds[kNumShapes] = {shape_id<SH_64_27>(), shape_id<SH_64_81>(), shape_id<SH_32_7_13>(),
+                                        shape_id<SH_8_7_13>(), shape_id<SH_8_5_7_13>(), shape_id<SH_32_9_7>()};
+
+// host-side constants of one plan (no CUDA calls): shared by fused_w_select and the device-free emulation
+int build_fused_w(const lolb_plan* pl, FusedW* F)
+{
+  F->shape = -1;
+  if (pl->kind != PLAN_RQ) return LOLB_OK;
+  int pmax = 0;
+  for (int s = 0; s < kNumShapes; s++)
+    if (shape_matches(pl, kShapeIds[s], &pmax)) { F->shape = s; break; }
+  if (F->shape < 0) return LOLB_OK;
+  const int k = pl->k;
+  F->cls.assign(k, WC_NONE);
+  for (int t = 0; t < k; t++) {
+    F->cls[t] = w_class((uint64_t)pl->qs[t], pmax);
+    if (F->cls[t] == WC_NONE) { F->shape = -1; return LOLB_OK; }
+  }
+  const WShapeId& id = kShapeIds[F->shape];
+  const int npe = (int)pl->pe.size();
+  F->ok_fwd = pl->ru.size() == (size_t)npe;
+  F->ok_inv = pl->ruinv.size() == (size_t)npe && (int)pl->mhatinv.size() == k;
+  F->cf.assign(k, {});
+  F->ci.assign(k, {});
+  F->mod.assign(k, WMod{});
+  F->h_lane.assign((size_t)k * 2 * kWLaneRows * 32, 1u);
+  const int first_odd = id.a > 0 ? 1 : 0;
+  for (int t = 0; t < k; t++) {
+    const uint64_t q = (uint64_t)pl->qs[t];
+    w_mod_consts(q, F->cls[t], &F->mod[t]);
+    for (int dir = 0; dir < 2; dir++) {
+      if (dir == 0 ? !F->ok_fwd : !F->ok_inv) continue;
+      const auto& tabs = dir ? pl->ruinv : pl->ru;
+      std::vector<uint32_t>& out = dir ? F->ci[t] : F->cf[t];
+      uint64_t scale = 1;
+      if (dir) { int64_t s = pl->mhatinv[t] % (int64_t)q; if (s < 0) s += q; scale = (uint64_t)s; }
+      for (int i = first_odd; i < npe; i++) {      // order = (PA, PB, PC) = the plan's odd prime powers in order
+        const int p = pl->pe[i].prime, e = pl->pe[i].exponent;
+        RootTab T{&tabs[i], k, t, ipow64(p, e), q};
+        const size_t n_m1 = (size_t)ipow64(p, e - 1) * (p - 1) * (p - 1);
+        size_t n_w = 0;
+        for (int dig = 0; dig < e - 1; dig++) n_w += (size_t)ipow64(p, e - 2 - dig) * p * p;
+        const size_t at = out.size();
+        out.resize(at + n_m1 + n_w);
+        build_pp_consts(p, e, dir != 0, T, i == first_odd ? scale : 1, out.data() + at);      // mhat^-1 rides on the first odd axis
+      }
+      uint32_t* lane = F->h_lane.data() + ((size_t)t * 2 + dir) * kWLaneRows * 32;
+      if (id.a >= 2) {
+        RootTab T2{&tabs[0], k, t, ipow64(2, id.a), q};
+        build_lane_table(id.a, dir != 0, T2, lane);
+      }
+      if (F->cls[t] == WC_M) {
+        for (auto& c : out) c = w_mont(c, q);
+        for (int i = 0; i < kWLaneRows * 32; i++) lane[i] = w_mont(lane[i], q);
+      }
+    }
+  }
+  return LOLB_OK;
+}
+
+template <class SH, bool INV, class AR, int K>
+int launch_w(const lolb_plan* pl, const FusedW* F, int limb, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  WConsts<SH::NC> C;
+  C.mod = F->mod[limb];
+  C.lane_tw = F->d_lane + ((size_t)limb * 2 + (INV ? 1 : 0)) * kWLaneRows * 32;
+  const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
+  if ((int)src.size() != (SH::PA::n_consts + SH::PB::n_consts + SH::PC::n_consts)) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
+  for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
+  int64_t grid = (int64_t)pl->num_sms * SH::MINB;
+  if constexpr (SH::TWO_PHASE) {
+    const int64_t groups = (batch + SH::EPB - 1) / SH::EPB;
+    if (grid > groups) grid = groups;
+    k_fused_w2<SH, INV, AR, K><<<(int)grid, kWThreads, 0, st>>>(y, batch, pl->k, limb, C);
+  } else {
+    const int64_t ctas = (batch + (kWThreads / 32) * SH::GPW - 1) / ((kWThreads / 32) * SH::GPW);
+    if (grid > ctas) grid = ctas;
+    k_fused_w1<SH, INV, AR, K><<<(int)grid, kWThreads, 0, st>>>(y, batch, pl->k, limb, C);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_fused_w");
+  count_launch();
+  return LOLB_OK;
+}
+
+template <class SH>
+int launch_shape(const lolb_plan* pl, const FusedW* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  for (int t = 0; t < pl->k; t++) {
+    int rc;
+    const bool m = F->cls[t] == WC_M, k1 = pl->k == 1;
+    if (inverse) rc = m ? (k1 ? launch_w<SH, true, WM, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WM, 0>(pl, F, t, y, batch, st))
+                        : (k1 ? launch_w<SH, true, WS, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WS, 0>(pl, F, t, y, batch, st));
+    else rc = m ? (k1 ? launch_w<SH, false, WM, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WM, 0>(pl, F, t, y, batch, st))
+                : (k1 ? launch_w<SH, false, WS, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WS, 0>(pl, F, t, y, batch, st));
+    if (rc) return rc;
+  }
+  return LOLB_OK;
+}
+
+// ------------------------------------------------------------------ device-free emulation (CPU tests of the constants, the
+// line code above compiled for the host, and a lane-by-lane replica of the network with the same ownership rules)
+template <class SH, bool INV, class AR>
+void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
+{
+  WConsts<SH::NC> C;
+  C.mod = F->mod[limb];
+  C.lane_tw = nullptr;
+  const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
+  for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
+  const uint32_t* lane_tab = F->h_lane.data() + ((size_t)limb * 2 + (INV ? 1 : 0)) * kWLaneRows * 32;
+  const AR A(C.mod);
+  constexpr int L = SH::L, LOG = SH::LOG, D2 = SH::D2, NP = SH::NP, COLS = SH::COLS, ROWS = SH::ROWS;
+  std::vector<uint32_t> tile((size_t)SH::N);
+  const uint32_t q = C.mod.q;
+  auto ld = [&](int j) { int64_t r = y[(size_t)j * k + limb] % (int64_t)q; if (r < 0) r += q; return (uint32_t)r; };
+  // phase 1
+  for (int col = 0; col < COLS; col++) {
+    uint32_t v[ROWS];
+    for (int i = 0; i < ROWS; i++) v[i] = ld(i * COLS + col);
+    pp_line<typename SH::PC, INV, 1, SH::OFF_C>(v, 0, C, A);
+    for (int i = 0; i < ROWS; i++) tile[(size_t)i * COLS + col] = v[i];
+  }
+  // phase 2, one row at a time, all L lanes of the group in lockstep
+  for (int row = 0; row < ROWS; row++) {
+    uint32_t v[L][D2];
+    for (int l = 0; l < L; l++) {
+      for (int i = 0; i < D2; i++) v[l][i] = tile[(size_t)row * COLS + i * L + l];
+      for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v[l], ib * SH::DA, C, A);
+      for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v[l], ia, C, A);
+    }
+    auto lt = [&](int r, int l) { return lane_tab[r * 32 + l]; };      // lane = l (group 0)
+    auto round = [&](bool trivial, int bit, int row_tw) {
+      uint32_t nv[L][D2];
+      for (int l = 0; l < L; l++) {
+        const bool hi = (l >> bit) & 1;
+        const int partner = l ^ (1 << bit);
+        for (int j = 0; j < NP; j++) {
+          const uint32_t keep = hi ? v[l][2 * j + 1] : v[l][2 * j];
+          const bool phi_ = (partner >> bit) & 1;
+          const uint32_t recv = phi_ ? v[partner][2 * j] : v[partner][2 * j + 1];      // what the partner sends
+          const uint32_t tw = trivial ? 0u : lt(row_tw, l);
+          if (trivial) {
+            const uint32_t u = hi ? recv : keep, t = hi ? keep : recv;
+            nv[l][2 * j] = A.fold(u + t);
+            nv[l][2 * j + 1] = A.fold(u + A.q2 - t);
+          } else if (!INV) {
+            nv[l][2 * j] = A.fold(keep + recv);
+            nv[l][2 * j + 1] = A.red(A.mul(tw, keep + A.q2 - recv));
+          } else {
+            const uint32_t t = A.red(A.mul(tw, hi ? keep : recv));
+            const uint32_t u = hi ? recv : keep;
+            nv[l][2 * j] = A.fold(u + t);
+            nv[l][2 * j + 1] = A.fold(u + A.q2 - t);
+          }
+        }
+      }
+      for (int l = 0; l < L; l++) for (int i = 0; i < D2; i++) v[l][i] = nv[l][i];
+    };
+    if (LOG >= 1) {
+      if (!INV) {
+        for (int l = 0; l < L; l++) for (int i = 0; i < D2; i++) v[l][i] = A.red(A.mul(lt(0, l), v[l][i]));
+        for (int r = 0; r < LOG - 1; r++) round(false, r, 1 + r);
+        round(true, LOG - 1, 0);
+      } else {
+        if (LOG >= 2) round(true, LOG - 1, 0);
+        for (int r = LOG - 2; r >= 1; r--) round(false, r, r);
+        uint32_t nv[L][D2];
+        for (int l = 0; l < L; l++) {
+          const bool hi = l & 1;
+          const int partner = l ^ 1;
+          for (int j = 0; j < NP; j++) {
+            const uint32_t keep = hi ? v[l][2 * j + 1] : v[l][2 * j];
+            const uint32_t recv = (partner & 1) ? v[partner][2 * j] : v[partner][2 * j + 1];
+            const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
+            nv[l][2 * j] = A.red(A.mad(A.mul(lt(4, l), u), lt(5, l), t));
+            nv[l][2 * j + 1] = A.red(A.mad(A.mul(lt(6, l), u), lt(7, l), t));
+          }
+        }
+        for (int l = 0; l < L; l++) for (int i = 0; i < D2; i++) v[l][i] = nv[l][i];
+      }
+    }
+    for (int l = 0; l < L; l++)
+      for (int j = 0; j < NP; j++)
+        for (int s = 0; s < 2; s++) {
+          int pos;
+          if (LOG == 0) pos = 2 * j + s;
+          else if (!INV) pos = (2 * j + (l & 1)) * L + ((s << (LOG - 1)) | (l >> 1));
+          else pos = (2 * j + (l >> (LOG - 1))) * L + 2 * (l & (L / 2 - 1)) + s;
+          y[((size_t)row * COLS + pos) * k + limb] = (int64_t)A.canon(v[l][2 * j + s]);
+        }
+  }
+}
+
+template <class SH>
+void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
+{
+  for (int t = 0; t < k; t++) {
+    const bool m = F->cls[t] == WC_M;
+    if (inverse) { if (m) emulate_shape<SH, true, WM>(F, t, k, y); else emulate_shape<SH, true, WS>(F, t, k, y); }
+    else { if (m) emulate_shape<SH, false, WM>(F, t, k, y); else emulate_shape<SH, false, WS>(F, t, k, y); }
+  }
+}
+
+#define W_FOR_SHAPE(F, CALL)                                       \
+  switch ((F)->shape) {                                            \
+    case 0: { typedef SH_64_27 SH; CALL; } break;                  \
+    case 1: { typedef SH_64_81 SH; CALL; } break;                  \
+    case 2: { typedef SH_32_7_13 SH; CALL; } break;                \
+    case 3: { typedef SH_8_7_13 SH; CALL; } break;                 \
+    case 4: { typedef SH_8_5_7_13 SH; CALL; } break;               \
+    case 5: { typedef SH_32_9_7 SH; CALL; } break;                 \
+    default: break;                                                \
+  }
+
+}  // namespace
+
+int fused_w_select(lolb_plan* pl, void** slot)
+{
+  FusedW* F = (FusedW*)*slot;
+  FusedW tmp;
+  int rc = build_fused_w(pl, &tmp);
+  if (rc) return rc;
+  if (tmp.shape < 0) {
+    if (F) { if (F->d_lane) cudaFree(F->d_lane); delete F; *slot = nullptr; }
+    return LOLB_OK;
+  }
+  if (!F) { F = new FusedW(); *slot = F; }
+  uint32_t* old = F->d_lane;
+  *F = tmp;
+  F->d_lane = nullptr;
+  if (old) cudaFree(old);
+  LOLB_CUDA(cudaMalloc((void**)&F->d_lane, F->h_lane.size() * sizeof(uint32_t)));
+  LOLB_CUDA(cudaMemcpy(F->d_lane, F->h_lane.data(), F->h_lane.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return LOLB_OK;
+}
+
+void fused_w_release(void* slot)
+{
+  FusedW* F = (FusedW*)slot;
+  if (!F) return;
+  if (F->d_lane) cudaFree(F->d_lane);
+  delete F;
+}
+
+bool fused_w_available(const void* slot, bool inverse)
+{
+  const FusedW* F = (const FusedW*)slot;
+  return F && F->shape >= 0 && (inverse ? F->ok_inv : F->ok_fwd);
+}
+
+int fused_w_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const FusedW* F = (const FusedW*)slot;
+  if (!fused_w_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
+  if (batch <= 0) return LOLB_OK;
+  int rc = LOLB_FUSED_UNAVAILABLE;
+  W_FOR_SHAPE(F, rc = launch_shape<SH>(pl, F, inverse, y, batch, st));
+  return rc;
+}
+
+}  // namespace lolb
+
+// Device-free: the fused_w schedule (host-built constants, the same line code compiled for the host, a lane-by-lane
+// replica of the exchange network) applied to ONE ring element in host memory, tables derived like lolb_plan_create_rq
+// does (ZqBasic.hs:144-171).  Test hook for `-m "not gpu"` (tests/test_fused_w_emulation.py); returns LOLB_ERR_ARG when
+// the index has no fused_w kernel and LOLB_ERR_NO_CRT when Z_q has no CRT of that index.
+extern "C" int lolb_fused_w_emulate(const PrimeExponent* peArr, hShort_t sizeOfPE, hShort_t tupSize, const hInt_t* qs, int inverse,
+                                    hInt_t* y)
+{
+  using namespace lolb;
+  if (!peArr || !qs || !y) { set_error("lolb_fused_w_emulate: NULL argument"); return LOLB_ERR_ARG; }
+  lolb_plan pl;
+  pl.kind = PLAN_RQ;
+  int rc = plan_build_common(&pl, peArr, sizeOfPE, tupSize);
+  if (rc) return rc;
+  pl.qs.assign(qs, qs + tupSize);
+  rc = plan_derive_rq_roots(&pl);
+  if (rc) return rc;
+  FusedW F;
+  rc = build_fused_w(&pl, &F);
+  if (rc) return rc;
+  if (F.shape < 0) { set_error("lolb_fused_w_emulate: no fused_w kernel for this index / modulus"); return LOLB_ERR_ARG; }
+  W_FOR_SHAPE(&F, emulate_dispatch<SH>(&F, inverse != 0, tupSize, y));
+  return LOLB_OK;
+}

@@ -184,6 +184,14 @@ class CudaTensorRq:
         capi.check(self.plan.apply_host(ops, y_host.data_ptr(), int(y_host.shape[0])))
         return y_host
 
+    def apply_host_u32(self, ops: str, y_host: torch.Tensor) -> torch.Tensor:
+        """The same pipeline over the narrow wire format (lolb_rq_apply_host_u32): `y_host` holds the residues as uint32 in an
+        int32 / uint32 CPU tensor [batch, n, k]; half the bytes cross PCIe."""
+        if y_host.is_cuda or y_host.element_size() != 4 or y_host.is_floating_point() or not y_host.is_contiguous():
+            raise capi.LolB200Error(capi.LOLB_ERR_ARG, "apply_host_u32 expects a contiguous 32-bit integer CPU tensor")
+        capi.check(self.plan.apply_host_u32(ops, y_host.data_ptr(), int(y_host.shape[0])))
+        return y_host
+
 
 class _CudaTensorPlain:
     dtype = None

@@ -204,7 +204,11 @@ BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249
                 # tupSize 4, 5, 7: all limbs of an element in one CTA iteration (k_fused_a_kn); 8: one launch per limb again
                 (14400, [43201, 57601, 100801, 115201]), (14400, [14401, 43201, 57601, 100801, 115201]),
                 (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201]),
-                (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201, 273601])]
+                (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201, 273601]),
+                # fused_w: the reference's other benchmark rings (Benchmarks/Default.hs:41-48) + m = 2016, both arithmetic classes
+                (64 * 81, [10369]), (32 * 7 * 13, [8737]), (8 * 7 * 13, [8737]), (8 * 5 * 7 * 13, [14561]), (2016, [2017]),
+                (64 * 27, [3457, 1002241]), (64 * 81, [10031041]), (32 * 7 * 13, [101921]), (8 * 5 * 7 * 13, [1015561, 1026481])]
+FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016}
 
 
 @pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
@@ -216,6 +220,8 @@ def test_batched_rq_matches_oracle(torch_cuda, oracle, m, qs, force_generic):
     rng = np.random.default_rng(m + 99)
     pe, n, ru, rui, mh = _tables(m, qs)
     t = CudaTensorRq(m, qs)                  # tables derived inside the library
+    if m in FUSED_W_INDICES:
+        assert t.plan.kernel_name("CRT") == "fused_w" and t.plan.kernel_name("CRTInv") == "fused_w"
     t.plan.force_generic(force_generic)
     for i in range(len(pe)):
         assert np.array_equal(t.plan.ru_table(i), ru[i]) and np.array_equal(t.plan.ru_table(i, True), rui[i])
