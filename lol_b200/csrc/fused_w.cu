@@ -53,6 +53,7 @@ struct WMod {
 // WS: a row of T terms needs 2 T q^2 < 2^32; residues lazily in [0, 2q), Barrett reduction
 struct WS {
   typedef uint32_t Acc;
+  static constexpr int MAXT = 1 << 20;      // terms per reduction: unbounded (the host checks 2 T q^2 < 2^32 for the longest row)
   uint32_t q, q2, mu, nq;
   WHD WS(const WMod& M) : q(M.q), q2(M.q2), mu(M.r0), nq(0u - M.q) {}
   WHD Acc mul(uint32_t c, uint32_t v) const { return c * v; }
@@ -63,9 +64,17 @@ struct WS {
   WHD uint32_t canon(uint32_t x) const { return w_min(x, x - q); }
 };
 
+// WS6: the same 32-bit arithmetic for moduli whose longest rows (12 or 13 terms: p = 13) would overflow: a row is cut into
+// pieces of at most 6 terms, each reduced on its own (2 * 6 * q^2 < 2^32), the pieces folded together
+struct WS6 : WS {
+  static constexpr int MAXT = 6;
+  WHD WS6(const WMod& M) : WS(M) {}
+};
+
 // WM: odd q, 2 T q < 2^32; 64-bit accumulation, one Montgomery reduction per row, constants in Montgomery form
 struct WM {
   typedef uint64_t Acc;
+  static constexpr int MAXT = 1 << 20;
   uint32_t q, q2, qinv, one;
   WHD WM(const WMod& M) : q(M.q), q2(M.q2), qinv(M.r0), one(M.one) {}
   WHD Acc mul(uint32_t c, uint32_t v) const { return (uint64_t)c * v; }
@@ -130,9 +139,13 @@ WHD void pp_round(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
             o[r] = A.red(A.unit(s));
           } else {
             typename AR::Acc acc = col0_one ? A.unit(x[0]) : A.mul(C.c[WOFF + (hi * P + r) * P], x[0]);
+            uint32_t part = 0;
 #pragma unroll
-            for (int a = 1; a < P; a++) acc = A.mad(acc, C.c[WOFF + (hi * P + r) * P + a], x[a]);
-            o[r] = A.red(acc);
+            for (int a = 1; a < P; a++) {
+              if (a % AR::MAXT == 0) { part = a == AR::MAXT ? A.red(acc) : A.fold(part + A.red(acc)); acc = A.mul(C.c[WOFF + (hi * P + r) * P + a], x[a]); }
+              else acc = A.mad(acc, C.c[WOFF + (hi * P + r) * P + a], x[a]);
+            }
+            o[r] = P > AR::MAXT ? A.fold(part + A.red(acc)) : A.red(acc);
           }
         }
 #pragma unroll
@@ -152,9 +165,13 @@ WHD void pp_blocks(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
 #pragma unroll
     for (int r = 0; r < D; r++) {
       typename AR::Acc acc = A.mul(C.c[COFF + (i0 * D + r) * D], v[base + (i0 * D) * STRIDE]);
+      uint32_t part = 0;
 #pragma unroll
-      for (int cc = 1; cc < D; cc++) acc = A.mad(acc, C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]);
-      o[r] = A.red(acc);
+      for (int cc = 1; cc < D; cc++) {
+        if (cc % AR::MAXT == 0) { part = cc == AR::MAXT ? A.red(acc) : A.fold(part + A.red(acc)); acc = A.mul(C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]); }
+        else acc = A.mad(acc, C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]);
+      }
+      o[r] = D > AR::MAXT ? A.fold(part + A.red(acc)) : A.red(acc);
     }
 #pragma unroll
     for (int r = 0; r < D; r++) v[base + (i0 * D + r) * STRIDE] = o[r];
@@ -422,11 +439,12 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
 
 // ------------------------------------------------------------------ host: constants from the plan's root tables
 
-enum WClass { WC_NONE = 0, WC_S, WC_M };
+enum WClass { WC_NONE = 0, WC_S, WC_M, WC_S6 };
 
 inline WClass w_class(uint64_t q, int pmax)
 {
   if (2 * (uint64_t)pmax * q * q < ((uint64_t)1 << 32)) return WC_S;
+  if (pmax > 6 && 2 * (uint64_t)6 * q * q + 4 * q < ((uint64_t)1 << 32)) return WC_S6;      // rows cut into pieces of 6 terms
   if ((q & 1) && 2 * (uint64_t)pmax * q < ((uint64_t)1 << 32)) return WC_M;
   return WC_NONE;
 }
@@ -531,10 +549,10 @@ template <class SH>
 constexpr WShapeId shape_id() { return WShapeId{SH::A, SH::PA::p, SH::PA::e, SH::PB::p, SH::PB::e, SH::PC::p, SH::PC::e}; }
 
 #ifndef LOLB_W27_MINB
-#define LOLB_W27_MINB 6      // CTAs of 128 threads per SM the register allocation must allow (tuning: tools/build_variant.py)
+#define LOLB_W27_MINB 4      // measured on B200, CRT / CRT^-1 of HBM peak: 4 -> 95 % / 94 %, 6 -> 87 % / 88 %, 8 -> 87 % / 87 %.  CTAs of 128 threads per SM the register allocation must allow (tuning: tools/build_variant.py)
 #endif
 #ifndef LOLB_W81_MINB
-#define LOLB_W81_MINB 3
+#define LOLB_W81_MINB 3      // 2 -> 72 % / 75 %, 3 -> 81 % / 83 %, 4 -> 71 % / 84 %
 #endif
 typedef WShape<6, PPT<3, 3>, PPNone, PPNone, 1, LOLB_W27_MINB> SH_64_27;     // m = 1728  (n = 576)
 typedef WShape<6, PPT<3, 4>, PPNone, PPNone, 1, LOLB_W81_MINB> SH_64_81;     // m = 5184  (n = 1728)
@@ -660,6 +678,14 @@ int launch_shape(const lolb_plan* pl, const FusedW* F, bool inverse, int64_t* y,
   for (int t = 0; t < pl->k; t++) {
     int rc;
     const bool m = F->cls[t] == WC_M, k1 = pl->k == 1;
+    if (F->cls[t] == WC_S6) {
+      if constexpr (SH::PC::p > 6 || SH::PB::p > 6 || SH::PA::p > 6) {
+        rc = inverse ? (k1 ? launch_w<SH, true, WS6, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WS6, 0>(pl, F, t, y, batch, st))
+                     : (k1 ? launch_w<SH, false, WS6, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WS6, 0>(pl, F, t, y, batch, st));
+      } else rc = LOLB_FUSED_UNAVAILABLE;
+      if (rc) return rc;
+      continue;
+    }
     if (inverse) rc = m ? (k1 ? launch_w<SH, true, WM, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WM, 0>(pl, F, t, y, batch, st))
                         : (k1 ? launch_w<SH, true, WS, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WS, 0>(pl, F, t, y, batch, st));
     else rc = m ? (k1 ? launch_w<SH, false, WM, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WM, 0>(pl, F, t, y, batch, st))
@@ -768,6 +794,10 @@ void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
 {
   for (int t = 0; t < k; t++) {
     const bool m = F->cls[t] == WC_M;
+    if (F->cls[t] == WC_S6) {
+      if (inverse) emulate_shape<SH, true, WS6>(F, t, k, y); else emulate_shape<SH, false, WS6>(F, t, k, y);
+      continue;
+    }
     if (inverse) { if (m) emulate_shape<SH, true, WM>(F, t, k, y); else emulate_shape<SH, true, WS>(F, t, k, y); }
     else { if (m) emulate_shape<SH, false, WM>(F, t, k, y); else emulate_shape<SH, false, WS>(F, t, k, y); }
   }
