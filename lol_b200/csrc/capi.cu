@@ -172,7 +172,11 @@ extern "C" void lolb_plan_destroy(lolb_plan* pl)
   void* ptrs[] = {pl->d_tab_fwd, pl->d_tab_inv, pl->d_gcrt, pl->d_gcrtinv, pl->d_ctab_fwd, pl->d_ctab_inv, pl->d_stage,
                   pl->d_tab_fwd_m, pl->d_tab_inv_m};
   for (void* p : ptrs) if (p) cudaFree(p);
-  for (auto& w : pl->ws) if (w.p) cudaFree(w.p);
+  for (auto& w : pl->ws) {
+    if (w.p) cudaFree(w.p);
+    if (w.aux) cudaStreamDestroy(w.aux);
+    for (auto& e : w.ev) if (e) cudaEventDestroy(e);
+  }
   for (auto& s : pl->streams) if (s) cudaStreamDestroy(s);
   for (auto& e : pl->events) if (e) cudaEventDestroy(e);
   delete pl;

@@ -603,6 +603,127 @@ k_fused_a_kn(int64_t* __restrict__ y, int64_t batch, int k, const __grid_constan
   }
 }
 
+// tupSize 2 .. 8, de-interleaving schedule: the element [n][K] is read and written ONLY with coalesced 128-bit accesses of
+// the whole 8 n K byte block (every sector fully used, for any K), the limbs are separated on the way into a [K][n] u32
+// tile, and both transform phases work tile -> registers -> tile:
+//   phase 0  all threads: 16-byte loads of the element, canonical check, u32 words to tile[limb][j]
+//   phase 1  warp-task (limb, i2): 5^2 axis on the 20-value column of a lane, in place in the tile
+//   phase 2  warp-task (limb, i3): 3^2 axis in the thread, 2^6 axis across the warp, canonical residues back to the tile
+//            (a row block is touched by its own warp-task only: the writes follow the last shuffle, which follows every
+//            lane's reads)
+//   phase 3  all threads: tile -> interleaved int64, 16-byte stores
+// With 2K warps every warp has exactly 3 tasks in phase 1 and 10 in phase 2.  The limb is a run-time index into the
+// per-limb constants (LDC), so one copy of the code serves every limb; per-lane constants come from L1.
+// (k_fused_a_kn, which this replaces for K >= 3, read 8 of every 8K bytes it touched per instruction: 49 % -> 31 % of
+// the HBM roofline for K = 3 .. 7.)
+constexpr int kMaxLimbsD = 8;
+template <int K> struct FusedAConstsK { FusedAConsts c[K]; };
+__host__ __device__ constexpr int kd_pad(int K) { return K == 4 ? 8 : K == 5 ? 4 : K == 6 ? 3 : K == 7 ? 4 : K == 8 ? 4 : 0; }   // limb stride kN + pad: fewest bank conflicts in phases 0 / 3
+
+template <bool INV, class AR, int K, int MINB>
+__global__ void __launch_bounds__(64 * K, MINB)
+k_fused_a_kd(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ FusedAConstsK<K> CC)
+{
+  constexpr int WARPS = 2 * K, T = 32 * WARPS, LS = kN + kd_pad(K), NPIECE = kN * K / 2, PPT = NPIECE / T, UB = 10;
+  static_assert(NPIECE % T == 0 && PPT % UB == 0, "pieces must tile the CTA");
+  extern __shared__ __align__(16) uint32_t tile[];       // [K][LS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t e = blockIdx.x; e < batch; e += gridDim.x) {
+    longlong2* e16 = reinterpret_cast<longlong2*>(y + (size_t)e * kN * K);
+    // ---------------- phase 0: coalesced load, limbs separated
+#pragma unroll 1
+    for (int b0 = 0; b0 < PPT; b0 += UB) {
+      longlong2 raw[UB];
+#pragma unroll
+      for (int u = 0; u < UB; u++) raw[u] = __ldcs(e16 + tid + (b0 + u) * T);
+#pragma unroll
+      for (int u = 0; u < UB; u++) {
+        const int f = 2 * (tid + (b0 + u) * T);
+        const int j0 = f / K, l0 = f - j0 * K, j1 = (f + 1) / K, l1 = (f + 1) - j1 * K;
+        const uint32_t q0 = CC.c[l0].q, q1 = CC.c[l1].q;
+        uint32_t w0 = (uint32_t)raw[u].x, w1 = (uint32_t)raw[u].y;
+        if ((uint64_t)raw[u].x >= (uint64_t)q0) w0 = reduce_any(raw[u].x, q0);      // outside the Haskell contract: like `c % q`
+        if ((uint64_t)raw[u].y >= (uint64_t)q1) w1 = reduce_any(raw[u].y, q1);
+        tile[l0 * LS + j0] = w0;
+        tile[l1 * LS + j1] = w1;
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 1: 5^2 axis, warp-task (limb, i2)
+#pragma unroll 1
+    for (int item = warp; item < K * kD2; item += WARPS) {
+      const int limb = item / kD2, i2 = item - limb * kD2;
+      const FusedAConsts& C = CC.c[limb];
+      const AR A(C);
+      uint32_t* colp = tile + limb * LS + i2 * 32 + lane;
+      uint32_t v[20];
+#pragma unroll
+      for (int a = 0; a < 20; a++) v[a] = colp[a * 192];
+      axis5<INV, AR>(v, C, A);
+#pragma unroll
+      for (int a = 0; a < 20; a++) colp[a * 192] = v[a];
+    }
+    __syncthreads();
+    // ---------------- phase 2: 3^2 axis in the thread, 2^6 axis across the warp, warp-task (limb, i3)
+#pragma unroll 1
+    for (int item = warp; item < K * kD3; item += WARPS) {
+      const int limb = item / kD3, i3 = item - limb * kD3;
+      const FusedAConsts& C = CC.c[limb];
+      const AR A(C);
+      const uint32_t* lt = C.lane_tw + lane;
+      uint32_t* row = tile + limb * LS + i3 * 192;
+      uint32_t x[6], c0[3], c1[3];
+#pragma unroll
+      for (int j = 0; j < 6; j++) x[j] = row[j * 32 + lane];
+      if (!INV) {
+        uint32_t m3l[12], ltw[4];
+#pragma unroll
+        for (int i = 0; i < 12; i++) m3l[i] = __ldg(lt + (8 + i) * 32);
+#pragma unroll
+        for (int i = 0; i < 4; i++) ltw[i] = __ldg(lt + (1 + i) * 32);
+        axis3<false, AR>(x, C, A, m3l);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+#pragma unroll
+        for (int r = 0; r < 4; r++) exchange_round<false, AR>(c0, c1, lane, r, ltw[r], A);
+        exchange_round<false, AR, true>(c0, c1, lane, 4, 0u, A);
+        uint32_t* out = row + (lane & 1) * 32 + (lane >> 1);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          out[j * 64] = A.canon(c0[j]);
+          out[j * 64 + 16] = A.canon(c1[j]);
+        }
+      } else {
+        uint32_t m3l[12] = {}, ltw[9];
+#pragma unroll
+        for (int i = 1; i < 9; i++) ltw[i] = (i == 4) ? 0u : __ldg(lt + i * 32);
+        axis3<true, AR>(x, C, A, m3l);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { c0[j] = x[2 * j]; c1[j] = x[2 * j + 1]; }
+        exchange_round<true, AR, true>(c0, c1, lane, 4, 0u, A);
+#pragma unroll
+        for (int r = 3; r >= 1; r--) exchange_round<true, AR>(c0, c1, lane, r, ltw[r], A);
+        exchange_last_inv<AR>(c0, c1, lane, ltw[5], ltw[7], ltw[6], ltw[8], A);
+        uint32_t* out = row + (lane >> 4) * 32 + 2 * (lane & 15);      // (the limb stride may be odd: no 64-bit store)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          out[j * 64] = A.canon(c0[j]);
+          out[j * 64 + 1] = A.canon(c1[j]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 3: coalesced store
+#pragma unroll 5
+    for (int b0 = 0; b0 < PPT; b0++) {
+      const int f = 2 * (tid + b0 * T);
+      const int j0 = f / K, l0 = f - j0 * K, j1 = (f + 1) / K, l1 = (f + 1) - j1 * K;
+      __stcs(e16 + tid + b0 * T, make_longlong2((int64_t)tile[l0 * LS + j0], (int64_t)tile[l1 * LS + j1]));
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ host: constants from the plan's root tables
 
 enum ArithClass { ARITH_NONE = 0, ARITH_S, ARITH_M };
@@ -880,6 +1001,43 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   const FusedA* F = (const FusedA*)slot;
   if (!fused_a_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
+  if (pl->k >= 2 && pl->k <= kMaxLimbsD) {
+    bool same = true;
+    for (int t = 1; t < pl->k; t++) same &= F->cls[t] == F->cls[0];
+    static int k2_mode = -1;      // LOLB_FUSED_A_K2 = "pair": tupSize 2 through k_fused_a_k2 (both limbs in one thread) instead
+    if (k2_mode < 0) { const char* v = getenv("LOLB_FUSED_A_K2"); k2_mode = (v && v[0] == 'p') ? 1 : 0; }
+    if (same && !(pl->k == 2 && k2_mode == 1)) {
+      cudaError_t e = cudaSuccess;
+#define KD(AR, KK, MB)                                                                                             \
+      do {                                                                                                          \
+        FusedAConstsK<KK> CC;                                                                                       \
+        for (int t = 0; t < KK; t++) CC.c[t] = inverse ? F->inv[t] : F->fwd[t];                                     \
+        const size_t smem = (size_t)KK * (kN + kd_pad(KK)) * sizeof(uint32_t);                                      \
+        auto kern = inverse ? k_fused_a_kd<true, AR, KK, MB> : k_fused_a_kd<false, AR, KK, MB>;                     \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+        int64_t gg = (int64_t)pl->num_sms * MB;                                                                     \
+        if (gg > batch) gg = batch;                                                                                 \
+        if (e == cudaSuccess) kern<<<(int)gg, 64 * KK, smem, st>>>(y, batch, CC);                                   \
+      } while (0)
+#define KDS(AR)                                                                                                    \
+      switch (pl->k) {                                                                                              \
+        case 2: KD(AR, 2, 6); break;                                                                                \
+        case 3: KD(AR, 3, 4); break;                                                                                \
+        case 4: KD(AR, 4, 3); break;                                                                                \
+        case 5: KD(AR, 5, 2); break;                                                                                \
+        case 6: KD(AR, 6, 2); break;                                                                                \
+        case 7: KD(AR, 7, 2); break;                                                                                \
+        default: KD(AR, 8, 1); break;                                                                               \
+      }
+      if (F->cls[0] == ARITH_M) { KDS(ArithM) } else { KDS(ArithS) }
+#undef KDS
+#undef KD
+      if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_kd");
+      count_launch();
+      return LOLB_OK;
+    }
+  }
   if (pl->k == 2 && F->cls[0] == F->cls[1]) {
     FusedAConsts2 CC;
     CC.c[0] = inverse ? F->inv[0] : F->fwd[0];

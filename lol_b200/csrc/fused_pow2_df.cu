@@ -779,7 +779,11 @@ int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t
   // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2
   // paired (63 % / 59 %, 60 % / 58 % vs 61 % / 59 %, 58 % / 57 %).  Keeping the rounds 5-9 twiddles in shared memory
   // instead of L1 was measured too: no gain, and it costs the paired kernel a CTA per SM.
-  const char* sched = getenv("LOLB_DF_SCHEDULE");      // "paired" / "unpaired" override
+  const char* sched = getenv("LOLB_DF_SCHEDULE");      // "split" / "paired" / "unpaired" override
+  if (!sched || sched[0] == 's') {
+    const int rc = pow2_split_crt(pl, F, INV, y, batch, st);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   const bool paired = sched ? sched[0] == 'p' : K != 4;
   if (paired) {
     switch (F->top) {

@@ -1,0 +1,254 @@
+// fused_pow2_split.cu -- Z_q CRT / CRT^-1 for m = 2^e, 14 <= e <= 16, as TWO plain streaming kernels per sub-batch that
+// overlap through the hardware's own block scheduler (BASELINE.json config B: m = 2^16, four ~30-bit primes).
+//
+// Same operator, arithmetic and task bodies as the dataflow kernel in fused_pow2_df.cu (pow2_common.cuh has the
+// citations): position bits [0,10) are "chunk" work (one contiguous 32 KB piece of the element per CTA, limbs
+// de-interleaved through shared memory, rounds 0-9 in registers), bits [10, e-1) are "column" work (128 (coefficient,
+// limb) pairs x all 2^(e-11) chunks per CTA, rounds 10 .. e-2 in registers, no shared memory).  The two kinds exchange
+// u32 residues through a ring in global memory that stays in L2.
+//
+// What differs is who orders the work.  There a persistent kernel claims tasks from an atomic queue and spins on
+// per-element counters (ncu: 25 % of the stalls at its hand-over barrier, 1.07x DRAM traffic, 55 % of HBM peak at tupSize
+// 4).  Here the batch is cut into sub-batches of S elements; kernel A(i) (reads the element from HBM, writes the ring) runs
+// on the caller's stream, kernel B(i) (reads the ring, writes the element) on an auxiliary stream behind an event, and
+// A(i + R) waits for B(i) before it reuses ring slot i mod R.  No CTA waits for another CTA: the block scheduler fills the
+// tail of B(i) with CTAs of A(i + 1), and each kernel gets its own register allocation (the column kernel needs half
+// the registers of the chunk kernel).
+#include <cstdlib>
+
+#include "pow2_common.cuh"
+
+namespace lolb {
+
+using namespace pow2;
+
+namespace {
+
+constexpr int kSpWarps = 4, kSpThreads = 32 * kSpWarps;
+
+template <int K, int TOP>
+struct SpGeom {
+  static constexpr int NCH = 1 << TOP;                 // chunks per limb
+  static constexpr int N = 1024 << TOP;                // coefficients per limb
+  static constexpr int G = kSpWarps / K;               // chunks per chunk CTA (kSpWarps units of 1024 residues)
+  static constexpr int NT_CHUNK = NCH / G;             // chunk CTAs per element
+  static constexpr int NT_COL = (1024 * K) / kSpThreads;   // column CTAs per element
+  static constexpr int NV = 1 << TOP;                  // residues per thread in a column CTA
+  static constexpr int PIECES = (kSpWarps * 1024) / (2 * kSpThreads);   // 16-byte pieces per thread in a chunk CTA
+  static constexpr int STEP = (2 * kSpThreads) / K;    // coefficients between consecutive pieces of a thread
+  // shared-memory word of piece ii of a thread, relative to  U + l0 * kDfUnit + c0 + (c0 >> 5),  c0 = 2 tid / K
+  static __host__ __device__ constexpr int piece_off(int ii)
+  {
+    return ((STEP * ii) >> 10) * K * kDfUnit + ((STEP * ii) & 1023) + (((STEP * ii) & 1023) >> 5);
+  }
+};
+
+#ifndef LOLB_SP_CHUNK_MINB
+#define LOLB_SP_CHUNK_MINB 5
+#endif
+#ifndef LOLB_SP_COL_MINB
+#define LOLB_SP_COL_MINB 8
+#endif
+
+// chunk kernel: bits [0,10).  Forward: HBM element -> ring.  Inverse: ring -> HBM element (canonical, mhat^-1 folded in).
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
+k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring)
+{
+  typedef SpGeom<K, TOP> Geo;
+  constexpr int N = Geo::N, G = Geo::G, PIECES = Geo::PIECES;
+  static_assert(G >= 1 && Geo::NCH % G == 0, "chunk CTAs must tile the element");
+  static_assert(Geo::STEP % 32 == 0 && 1024 % Geo::STEP == 0, "piece addressing");
+  __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int el = blockIdx.x / Geo::NT_CHUNK, task = blockIdx.x - el * Geo::NT_CHUNK;
+  uint32_t* slot = ring + (size_t)el * ((size_t)K * N);
+  int64_t* ebase = y + (size_t)el * ((size_t)K * N);
+
+  const int chunk0 = task * G;
+  int64_t* gpiece = ebase + (size_t)chunk0 * 1024 * K;              // kSpWarps * 1024 contiguous int64
+  const int unit = warp;                                             // (chunk in CTA, limb) of this warp
+  const int uch = unit / K, limb = unit % K;
+  uint32_t* Uu = U + unit * kDfUnit;
+  const DfLimb& L = P.limb[limb];
+  const Mont M{L.q, L.q2, L.qinv};
+  uint32_t* srow = slot + (size_t)limb * N + (size_t)(chunk0 + uch) * 1024 + lane;
+  // the pieces of this thread: int64 pairs (2 tid + 2 kSpThreads ii, +1); the limb of each half is fixed per thread
+  // and the shared-memory word of piece ii is a compile-time offset from `ubase`
+  const int l0 = (2 * tid) % K, c0 = (2 * tid) / K;
+  uint32_t* ubase = U + l0 * kDfUnit + c0 + (c0 >> 5);
+  constexpr int second = K == 1 ? 1 : kDfUnit;                      // the other half: next coefficient / next limb
+  if (!INV) {
+    const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
+    const longlong2* src = reinterpret_cast<const longlong2*>(gpiece) + tid;
+    {
+      // coalesced read of the piece (all 16-byte loads in flight at once), limbs de-interleaved into the units
+      longlong2 raw[PIECES];
+#pragma unroll
+      for (int ii = 0; ii < PIECES; ii++) raw[ii] = __ldcs(src + kSpThreads * ii);
+      uint32_t hi_or = 0, max0 = 0, max1 = 0;
+#pragma unroll
+      for (int ii = 0; ii < PIECES; ii++) {
+        hi_or |= (uint32_t)((uint64_t)raw[ii].x >> 32) | (uint32_t)((uint64_t)raw[ii].y >> 32);
+        max0 = max(max0, (uint32_t)raw[ii].x);
+        max1 = max(max1, (uint32_t)raw[ii].y);
+        ubase[Geo::piece_off(ii)] = (uint32_t)raw[ii].x;
+        ubase[Geo::piece_off(ii) + second] = (uint32_t)raw[ii].y;
+      }
+      if (hi_or != 0 || max0 >= q0 || max1 >= q1) {
+        // outside the Haskell contract (values not in [0,q)): redo this thread's pieces like the reference's c % q
+#pragma unroll 1
+        for (int ii = 0; ii < PIECES; ii++) {
+          const longlong2 r = src[kSpThreads * ii];
+          const int off = Geo::piece_off(ii);
+          ubase[off] = df_reduce_any64(r.x, q0);
+          ubase[off + second] = df_reduce_any64(r.y, q1);
+        }
+      }
+    }
+    __syncthreads();
+    unit_rounds_0_4_rt<false>(limb, Uu, P, lane);
+    __syncwarp();
+    // rounds 5-9: lane owns coefficients lane + 32 j
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = Uu[lane + 33 * j];
+    const uint32_t* twl = L.tw + lane;
+    ct_rounds<5, false>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+    for (int j = 0; j < 32; j++) srow[32 * j] = v[j];
+  } else {
+    {
+      uint32_t v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = __ldcg(srow + 32 * j);
+      const uint32_t* twl = L.tw + lane;
+      gs_rounds<5, 0>(v, M, [&](int a, int jj) { return __ldg(twl + ((32 << a) - 1 + 32 * jj)); });
+#pragma unroll
+      for (int j = 0; j < 32; j++) Uu[lane + 33 * j] = v[j];
+    }
+    __syncwarp();
+    unit_rounds_0_4_rt<true>(limb, Uu, P, lane);
+    __syncthreads();
+    // canonical residues -> interleaved int64, coalesced 128-bit stores
+#pragma unroll
+    for (int ii = 0; ii < PIECES; ii++) {
+      const uint32_t x0 = ubase[Geo::piece_off(ii)], x1 = ubase[Geo::piece_off(ii) + second];
+      __stcs(reinterpret_cast<longlong2*>(gpiece) + tid + kSpThreads * ii, make_longlong2((int64_t)x0, (int64_t)x1));
+    }
+  }
+}
+
+// column kernel: bits [10, 10 + TOP).  Forward: ring -> HBM element (canonical).  Inverse: HBM element -> ring.
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_COL_MINB)
+k_pow2_col(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring)
+{
+  typedef SpGeom<K, TOP> Geo;
+  constexpr int N = Geo::N, NV = Geo::NV;
+  const int tid = threadIdx.x;
+  const int el = blockIdx.x / Geo::NT_COL, task = blockIdx.x - el * Geo::NT_COL;
+  uint32_t* slot = ring + (size_t)el * ((size_t)K * N);
+  int64_t* ebase = y + (size_t)el * ((size_t)K * N);
+  const int f = task * kSpThreads + tid;                             // (coefficient b, limb) pair, ABI order
+  const int b = f / K, limb = f % K;
+  const DfLimb& L = P.limb[limb];
+  const Mont M{L.q, L.q2, L.qinv};
+  uint32_t* scol = slot + (size_t)limb * N + b;
+  int64_t* gcol = ebase + f;
+  const uint32_t* twb = L.tw + b;
+  uint32_t v[NV];
+  if (!INV) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = __ldcg(scol + 1024 * j);
+    ct_rounds<TOP, false>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
+#pragma unroll
+    for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
+  } else {
+    uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const int64_t raw = __ldcs(gcol + (size_t)1024 * K * j);
+      v[j] = (uint32_t)raw;
+      hi_or |= (uint32_t)((uint64_t)raw >> 32);
+      lo_max = max(lo_max, v[j]);
+    }
+    if (hi_or != 0 || lo_max >= L.q) {      // outside the Haskell contract: reduce like the reference's c % q
+#pragma unroll
+      for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(gcol[(size_t)1024 * K * j], L.q);
+    }
+    gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
+#pragma unroll
+    for (int j = 0; j < NV; j++) scol[1024 * j] = v[j];
+  }
+}
+
+constexpr int kSpRing = 3;      // sub-batches of ring in flight: one being written, one being read, one of slack
+
+template <bool INV, int K, int TOP>
+int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  if constexpr ((1 << TOP) * K < kSpWarps || ((1 << TOP) * K) % kSpWarps != 0) return LOLB_FUSED_UNAVAILABLE;
+  else {
+    typedef SpGeom<K, TOP> Geo;
+    const DfParams P = INV ? F->inv : F->fwd;
+    const size_t el_words = (size_t)K * Geo::N;
+    // sub-batch: about 16 MB of u32 ring (three of them stay in the 126 MB L2 beside the streamed element data)
+    const char* mb_env = getenv("LOLB_SPLIT_MB");      // tuning / test override of the sub-batch size
+    const int64_t mb = mb_env && atoi(mb_env) > 0 ? atoi(mb_env) : 16;
+    int64_t S = (mb << 20) / (int64_t)(el_words * sizeof(uint32_t));
+    if (S < 1) S = 1;
+    if (S > batch) S = batch;
+    const int64_t nsub = (batch + S - 1) / S;
+    const int R = (int)(nsub < kSpRing ? nsub : kSpRing);
+    uint32_t* ring = (uint32_t*)plan_ws(pl, st, (size_t)R * S * el_words * sizeof(uint32_t));
+    if (!ring) return LOLB_ERR_CUDA;
+    cudaStream_t aux = nullptr;
+    cudaEvent_t* ev = nullptr;      // [0 .. kSpRing): A done, [kSpRing .. 2 kSpRing): B done
+    int rc = plan_ws_aux(pl, st, &aux, &ev);
+    if (rc) return rc;
+    for (int64_t i = 0; i < nsub; i++) {
+      const int s = (int)(i % R);
+      const int64_t cnt = batch - i * S < S ? batch - i * S : S;
+      int64_t* ys = y + (size_t)i * S * el_words;
+      uint32_t* rs = ring + (size_t)s * S * el_words;
+      if (i >= R) LOLB_CUDA(cudaStreamWaitEvent(st, ev[kSpRing + s], 0));      // B(i - R) has drained this ring slot
+      if (!INV) k_pow2_chunk<false, K, TOP><<<(unsigned)(cnt * Geo::NT_CHUNK), kSpThreads, 0, st>>>(ys, P, rs);
+      else k_pow2_col<true, K, TOP><<<(unsigned)(cnt * Geo::NT_COL), kSpThreads, 0, st>>>(ys, P, rs);
+      LOLB_CUDA(cudaEventRecord(ev[s], st));
+      LOLB_CUDA(cudaStreamWaitEvent(aux, ev[s], 0));
+      if (!INV) k_pow2_col<false, K, TOP><<<(unsigned)(cnt * Geo::NT_COL), kSpThreads, 0, aux>>>(ys, P, rs);
+      else k_pow2_chunk<true, K, TOP><<<(unsigned)(cnt * Geo::NT_CHUNK), kSpThreads, 0, aux>>>(ys, P, rs);
+      LOLB_CUDA(cudaEventRecord(ev[kSpRing + s], aux));
+    }
+    LOLB_CUDA(cudaStreamWaitEvent(st, ev[kSpRing + (int)((nsub - 1) % R)], 0));      // join: aux is in order, the last B covers all
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_pow2_chunk / k_pow2_col");
+    count_launch((int)(2 * nsub));
+    return LOLB_OK;
+  }
+}
+
+}  // namespace
+
+// LOLB_FUSED_UNAVAILABLE when the shape is not served here (e < 14: the element-resident kernels win)
+int pow2_split_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const int k = pl->k;
+#define SP(TOPV)                                                                                                  \
+  do {                                                                                                             \
+    if (k == 1) return inverse ? launch_split<true, 1, TOPV>(pl, F, y, batch, st) : launch_split<false, 1, TOPV>(pl, F, y, batch, st); \
+    if (k == 2) return inverse ? launch_split<true, 2, TOPV>(pl, F, y, batch, st) : launch_split<false, 2, TOPV>(pl, F, y, batch, st); \
+    if (k == 4) return inverse ? launch_split<true, 4, TOPV>(pl, F, y, batch, st) : launch_split<false, 4, TOPV>(pl, F, y, batch, st); \
+  } while (0)
+  switch (F->top) {
+    case 3: SP(3); break;
+    case 4: SP(4); break;
+    case 5: SP(5); break;
+    default: break;
+  }
+#undef SP
+  return LOLB_FUSED_UNAVAILABLE;
+}
+
+}  // namespace lolb

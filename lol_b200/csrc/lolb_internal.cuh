@@ -106,7 +106,11 @@ struct lolb_plan {
   // ---- kernel workspaces (exchange ring + counters of the dataflow kernel, spilled elements of the generic engine):
   // one per CUDA stream the plan has been used on, so that calls on different streams (or from different host threads
   // on different streams) never share mutable device state; calls on ONE stream are ordered by the stream (plan_ws)
-  struct WsSlot { cudaStream_t st; void* p; size_t bytes; };
+  struct WsSlot {
+    cudaStream_t st; void* p; size_t bytes;
+    cudaStream_t aux = nullptr;       // second stream of the split power-of-two schedule, forked from / joined to `st` by events
+    cudaEvent_t ev[8] = {};
+  };
   mutable std::vector<WsSlot> ws;
   mutable std::mutex ws_mu;
   // ---- staging for the drop-in (host pointer) entry points and host-batched calls
@@ -150,7 +154,8 @@ int plan_upload_rq_gcrt(lolb_plan* pl);               // gCRT / gInvCRT vectors 
 void plan_derive_c_roots(lolb_plan* pl);              // CRTrans.hs:88-95 -> pl->cru, cruinv, c_mhatinv
 int plan_upload_c_dir(lolb_plan* pl, bool inverse);
 uint64_t hash_bytes(const void* p, size_t bytes, uint64_t seed);
-void* plan_ws(const lolb_plan* pl, cudaStream_t st, size_t bytes);   // the stream's workspace, grown to `bytes`; nullptr + error set on failure
+void* plan_ws(const lolb_plan* pl, cudaStream_t st, size_t bytes);
+int plan_ws_aux(const lolb_plan* pl, cudaStream_t st, cudaStream_t* aux, cudaEvent_t** events /* [8], untimed */);   // the stream's workspace, grown to `bytes`; nullptr + error set on failure
 int plan_reserve_stage(const lolb_plan* pl, size_t bytes);
 
 // engine.cu -- generic pass engine

@@ -33,7 +33,7 @@ void* plan_ws(const lolb_plan* pl, cudaStream_t st, size_t bytes)
   std::lock_guard<std::mutex> lock(pl->ws_mu);
   lolb_plan::WsSlot* slot = nullptr;
   for (auto& s : pl->ws) if (s.st == st) { slot = &s; break; }
-  if (!slot) { pl->ws.push_back({st, nullptr, 0}); slot = &pl->ws.back(); }
+  if (!slot) { pl->ws.push_back(lolb_plan::WsSlot{st, nullptr, 0}); slot = &pl->ws.back(); }
   if (bytes <= slot->bytes && slot->p) return slot->p;
   if (slot->p) {      // kernels of this stream may still use the old block
     cudaError_t e = cudaStreamSynchronize(st);
@@ -45,6 +45,27 @@ void* plan_ws(const lolb_plan* pl, cudaStream_t st, size_t bytes)
   if (e != cudaSuccess) { slot->p = nullptr; cuda_fail(e, "cudaMalloc(workspace)"); return nullptr; }
   slot->bytes = bytes;
   return slot->p;
+}
+
+// the auxiliary stream (highest priority: it runs the finishing half of a split schedule) and eight untimed events of
+// the slot of stream `st`, created on first use.  The events live as long as the plan: the returned pointer stays valid
+// because slots are only ever appended while ws_mu is held and std::vector growth moves the handles, not the objects
+// they name -- callers copy the handles before the next plan_ws* call.
+int plan_ws_aux(const lolb_plan* pl, cudaStream_t st, cudaStream_t* aux, cudaEvent_t** events)
+{
+  std::lock_guard<std::mutex> lock(pl->ws_mu);
+  lolb_plan::WsSlot* slot = nullptr;
+  for (auto& s : pl->ws) if (s.st == st) { slot = &s; break; }
+  if (!slot) { pl->ws.push_back(lolb_plan::WsSlot{st, nullptr, 0}); slot = &pl->ws.back(); }
+  if (!slot->aux) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    LOLB_CUDA(cudaStreamCreateWithPriority(&slot->aux, cudaStreamNonBlocking, hi));
+    for (auto& e : slot->ev) LOLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  *aux = slot->aux;
+  *events = slot->ev;
+  return LOLB_OK;
 }
 
 int plan_reserve_stage(const lolb_plan* pl, size_t bytes)

@@ -201,10 +201,11 @@ def test_config_b_matches_reference_digests(dropin):
 BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
                 (1024, [12289]), (64 * 27, [3457]), CONFIG_A, CONFIG_C, (14400, [429336001]), (14400, [43201]),
                 (14400, [14401, 1008001, 429336001]), (14400, [2148249601]),
-                # tupSize 4, 5, 7: all limbs of an element in one CTA iteration (k_fused_a_kn); 8: one launch per limb again
+                # tupSize 3 .. 8: the de-interleaving kernel (k_fused_a_kd), every limb of an element in one CTA iteration
                 (14400, [43201, 57601, 100801, 115201]), (14400, [14401, 43201, 57601, 100801, 115201]),
                 (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201]),
                 (14400, [14401, 43201, 57601, 100801, 115201, 172801, 259201, 273601]),
+                (14400, [43201, 57601, 100801, 115201, 172801, 259201]),      # tupSize 6: odd limb stride in the de-interleaved tile
                 # fused_w: the reference's other benchmark rings (Benchmarks/Default.hs:41-48) + m = 2016, both arithmetic classes
                 (64 * 81, [10369]), (32 * 7 * 13, [8737]), (8 * 7 * 13, [8737]), (8 * 5 * 7 * 13, [14561]), (2016, [2017]),
                 (64 * 27, [3457, 1002241]), (64 * 81, [10031041]), (32 * 7 * 13, [101921]), (8 * 5 * 7 * 13, [1015561, 1026481])]
@@ -329,6 +330,42 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
     smp = tr.tGaussianDec(0.1, 8)
     assert smp.shape == (8, n, 1) and torch.isfinite(smp).all()
     assert (tr.gSqNormDec(smp) > 0).all()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("mb", [1, 16], ids=lambda v: f"sub-batch {v} MiB")
+@pytest.mark.parametrize("e,k", [(14, 1), (14, 2), (14, 4), (15, 1), (15, 2), (15, 4), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
+def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb):
+    """fused_pow2_split (m = 2^14 .. 2^16, tupSize 1, 2, 4): chunk kernel and column kernel of one sub-batch on two streams behind
+    events, ring slots reused three sub-batches later.  1 MiB sub-batches force many ragged sub-batches and every ring slot to
+    be reused; oracle parity on a sample, the generic engine on all elements, crtInv . crt = id, and two calls back to back
+    (the second call's first kernel must wait for the first call's last one)."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    monkeypatch.setenv("LOLB_SPLIT_MB", str(mb))
+    monkeypatch.setenv("LOLB_DF_SCHEDULE", "split")
+    monkeypatch.setenv("LOLB_POW2_MID_OFF", "1")
+    m, qs = 2 ** e, CONFIG_B[1][:k]
+    B = 29 if mb == 1 else 7
+    rng = np.random.default_rng(e * 10 + k + 1)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    y = zq_input(rng, n, qs, batch=B)
+    x = torch.from_numpy(y).cuda()
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, 1, B // 2, B - 1):
+        assert np.array_equal(f[b].cpu().numpy(), oracle.tensorCRTRq(y[b], pe, ru, qs)), b
+        assert np.array_equal(g[b].cpu().numpy(), oracle.tensorCRTInvRq(y[b], pe, rui, mh, qs)), b
+    assert torch.equal(t.crtInv(f), x) and torch.equal(t.crt(g), x)
+    z = x.clone()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    from lol_b200 import capi
+    for _ in range(3):      # in place, back to back on one stream
+        capi.check(t.plan.op("CRT", z.data_ptr(), B, st))
+        capi.check(t.plan.op("CRTInv", z.data_ptr(), B, st))
+    assert torch.equal(z, x)
+    t.plan.force_generic(True)
+    assert torch.equal(t.crt(x), f) and torch.equal(t.crtInv(x), g)
 
 
 @pytest.mark.timeout(120)
