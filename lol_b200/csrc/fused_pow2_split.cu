@@ -232,7 +232,7 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
 }  // namespace
 
 // LOLB_FUSED_UNAVAILABLE when the shape is not served here (e < 14: the element-resident kernels win)
-int pow2_split_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+int pow2::pow2_split_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
 {
   const int k = pl->k;
 #define SP(TOPV)                                                                                                  \

@@ -56,6 +56,6 @@ def test_sixteen_byte_paths_use_128_bit_accesses():
 def test_coefficient_loops_have_no_division_call():
     """Two calls remain per kernel: the once-per-thread split of the global index into (coefficient, limb)."""
     funcs = _sass("coeff_stream.o")
-    for op in ("OpLift", "OpReduce", "OpRescaleDrop", "OpRescaleMod"):
+    for op in ("OpLift", "OpReduce", "OpRescaleDropFast", "OpRescaleMod"):
         ins = _find(funcs, "k_coeff_stream", op + ">")
         assert sum(i.startswith("CALL") for i in ins) <= 2, op
