@@ -53,7 +53,7 @@ struct SpGeom {
 // chunk kernel: bits [0,10).  Forward: HBM element -> ring.  Inverse: ring -> HBM element (canonical, mhat^-1 folded in).
 template <bool INV, int K, int TOP>
 __global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
-k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring)
+k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
 {
   typedef SpGeom<K, TOP> Geo;
   constexpr int N = Geo::N, G = Geo::G, PIECES = Geo::PIECES;
@@ -61,7 +61,8 @@ k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32
   static_assert(Geo::STEP % 32 == 0 && 1024 % Geo::STEP == 0, "piece addressing");
   __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int el = blockIdx.x / Geo::NT_CHUNK, task = blockIdx.x - el * Geo::NT_CHUNK;
+  const int el_l = blockIdx.x / Geo::NT_CHUNK, task = blockIdx.x - el_l * Geo::NT_CHUNK;
+  const int el = rev_n ? rev_n - 1 - el_l : el_l;      // the second kernel of a sub-batch walks it backwards: the ring words written last are still in L2
   uint32_t* slot = ring + (size_t)el * ((size_t)K * N);
   int64_t* ebase = y + (size_t)el * ((size_t)K * N);
 
@@ -142,12 +143,13 @@ k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32
 // column kernel: bits [10, 10 + TOP).  Forward: ring -> HBM element (canonical).  Inverse: HBM element -> ring.
 template <bool INV, int K, int TOP>
 __global__ void __launch_bounds__(kSpThreads, LOLB_SP_COL_MINB)
-k_pow2_col(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring)
+k_pow2_col(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
 {
   typedef SpGeom<K, TOP> Geo;
   constexpr int N = Geo::N, NV = Geo::NV;
   const int tid = threadIdx.x;
-  const int el = blockIdx.x / Geo::NT_COL, task = blockIdx.x - el * Geo::NT_COL;
+  const int el_l = blockIdx.x / Geo::NT_COL, task = blockIdx.x - el_l * Geo::NT_COL;
+  const int el = rev_n ? rev_n - 1 - el_l : el_l;
   uint32_t* slot = ring + (size_t)el * ((size_t)K * N);
   int64_t* ebase = y + (size_t)el * ((size_t)K * N);
   const int f = task * kSpThreads + tid;                             // (coefficient b, limb) pair, ABI order
@@ -213,12 +215,12 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
       int64_t* ys = y + (size_t)i * S * el_words;
       uint32_t* rs = ring + (size_t)s * S * el_words;
       if (i >= R) LOLB_CUDA(cudaStreamWaitEvent(st, ev[kSpRing + s], 0));      // B(i - R) has drained this ring slot
-      if (!INV) k_pow2_chunk<false, K, TOP><<<(unsigned)(cnt * Geo::NT_CHUNK), kSpThreads, 0, st>>>(ys, P, rs);
-      else k_pow2_col<true, K, TOP><<<(unsigned)(cnt * Geo::NT_COL), kSpThreads, 0, st>>>(ys, P, rs);
+      if (!INV) k_pow2_chunk<false, K, TOP><<<(unsigned)(cnt * Geo::NT_CHUNK), kSpThreads, 0, st>>>(ys, P, rs, 0);
+      else k_pow2_col<true, K, TOP><<<(unsigned)(cnt * Geo::NT_COL), kSpThreads, 0, st>>>(ys, P, rs, 0);
       LOLB_CUDA(cudaEventRecord(ev[s], st));
       LOLB_CUDA(cudaStreamWaitEvent(aux, ev[s], 0));
-      if (!INV) k_pow2_col<false, K, TOP><<<(unsigned)(cnt * Geo::NT_COL), kSpThreads, 0, aux>>>(ys, P, rs);
-      else k_pow2_chunk<true, K, TOP><<<(unsigned)(cnt * Geo::NT_CHUNK), kSpThreads, 0, aux>>>(ys, P, rs);
+      if (!INV) k_pow2_col<false, K, TOP><<<(unsigned)(cnt * Geo::NT_COL), kSpThreads, 0, aux>>>(ys, P, rs, (int)cnt);
+      else k_pow2_chunk<true, K, TOP><<<(unsigned)(cnt * Geo::NT_CHUNK), kSpThreads, 0, aux>>>(ys, P, rs, (int)cnt);
       LOLB_CUDA(cudaEventRecord(ev[kSpRing + s], aux));
     }
     LOLB_CUDA(cudaStreamWaitEvent(st, ev[kSpRing + (int)((nsub - 1) % R)], 0));      // join: aux is in order, the last B covers all
