@@ -505,12 +505,12 @@ k_fused_a_k2(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Fus
   }
 }
 
-// tupSize >= 3 (and mixed-class pairs): every limb of one ring element in the same CTA iteration.  A launch per limb
+// tupSize 3: every limb of one ring element in the same CTA iteration.  A launch per limb
 // reads 8 of every 8k bytes it touches, so HBM moves the whole batch k times; here a warp walks the limbs of its column
 // block back to back, the first limb's loads bring the sectors on chip and the others hit L1/L2, and the k partial-
 // sector stores of a row meet in L2 before they are written back: one HBM read and one HBM write per element again.
 // The limb index is a uniform loop counter, so one copy of the code reads its constants through c[limb].
-constexpr int kMaxLimbsN = 7;      // 7 x sizeof(FusedAConsts) fits the 4 KB kernel-parameter space
+constexpr int kMaxLimbsN = 3;      // serves tupSize 3 (the de-interleaving kernel below is faster from tupSize 4 on)
 struct FusedAConstsN { FusedAConsts c[kMaxLimbsN]; };
 
 template <bool INV, class AR, int WARPS, int MINB>
@@ -1004,9 +1004,12 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   if (pl->k >= 2 && pl->k <= kMaxLimbsD) {
     bool same = true;
     for (int t = 1; t < pl->k; t++) same &= F->cls[t] == F->cls[0];
-    static int k2_mode = -1;      // LOLB_FUSED_A_K2 = "pair": tupSize 2 through k_fused_a_k2 (both limbs in one thread) instead
-    if (k2_mode < 0) { const char* v = getenv("LOLB_FUSED_A_K2"); k2_mode = (v && v[0] == 'p') ? 1 : 0; }
-    if (same && !(pl->k == 2 && k2_mode == 1)) {
+    // Measured on B200 (CRT / CRT^-1, % of the HBM roofline, Montgomery class): tupSize 2  k_fused_a_k2 62 / 55, this kernel
+    // 54 / 48 (ncu: 26 % more instructions for the two extra shared-memory stages);  tupSize 3  k_fused_a_kn 49 / 44, this
+    // kernel 44 / 42;  tupSize 4 / 5 / 7 / 8  this kernel 47 / 46, 41 / 39, 37 / 36, 36 / 36 against 41 / 38, 38 / -, 31 / -
+    // and one launch per limb.  LOLB_FUSED_A_KD=1 forces this kernel for tupSize 2 and 3 too (tests, tuning).
+    const char* kd_env = getenv("LOLB_FUSED_A_KD");
+    if (same && (pl->k >= 4 || (kd_env && kd_env[0] == '1'))) {
       cudaError_t e = cudaSuccess;
 #define KD(AR, KK, MB)                                                                                             \
       do {                                                                                                          \
@@ -1063,41 +1066,26 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
     count_launch();
     return LOLB_OK;
   }
-  if (pl->k >= 2 && pl->k <= kMaxLimbsN) {
-    bool same = true;
-    for (int t = 1; t < pl->k; t++) same &= F->cls[t] == F->cls[0];
-    if (same) {
-      FusedAConstsN CC;
-      for (int t = 0; t < pl->k; t++) CC.c[t] = inverse ? F->inv[t] : F->fwd[t];
-      const size_t smem = (size_t)pl->k * kN * sizeof(uint32_t);
-      const int fit = (int)((227 * 1024) / (smem + 1024));      // CTAs per SM the tile allows
-      cudaError_t e = cudaSuccess;
-#define KN(AR, W, MB)                                                                                             \
-      do {                                                                                                         \
-        auto kern = inverse ? k_fused_a_kn<true, AR, W, MB> : k_fused_a_kn<false, AR, W, MB>;                      \
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
-        int64_t gg = (int64_t)pl->num_sms * (fit < MB ? fit : MB);                                                 \
-        if (gg > batch) gg = batch;                                                                                \
-        if (e == cudaSuccess) kern<<<(int)gg, W * 32, smem, st>>>(y, batch, pl->k, CC);                            \
-      } while (0)
-      // warps per CTA: a divisor pattern of 6k and 20k that keeps about 24 warps per SM next to the k x 15 KB tile
-      const int shape = pl->k == 3 ? 6 : pl->k == 4 ? 8 : pl->k == 5 ? 10 : pl->k == 6 ? 12 : 7;
-#define KNS(AR)                                                                                                   \
-      switch (shape) {                                                                                             \
-        case 6: KN(AR, 6, 4); break;                                                                               \
-        case 8: KN(AR, 8, 3); break;                                                                               \
-        case 10: KN(AR, 10, 2); break;                                                                             \
-        case 12: KN(AR, 12, 2); break;                                                                             \
-        default: KN(AR, 7, 2); break;                                                                              \
-      }
-      if (F->cls[0] == ARITH_M) { KNS(ArithM) } else { KNS(ArithS) }
-#undef KNS
+  if (pl->k == 3 && F->cls[1] == F->cls[0] && F->cls[2] == F->cls[0]) {      // tupSize 3: limb loop over strided 8-byte accesses
+    FusedAConstsN CC;
+    for (int t = 0; t < 3; t++) CC.c[t] = inverse ? F->inv[t] : F->fwd[t];
+    const size_t smem = (size_t)3 * kN * sizeof(uint32_t);
+    constexpr int W = 6, MB = 4;      // 6 warps: 3 phase-1 and 10 phase-2 tasks per warp; 4 CTAs per SM next to the 45 KB tile
+    cudaError_t e = cudaSuccess;
+#define KN(AR)                                                                                                    \
+    do {                                                                                                           \
+      auto kern = inverse ? k_fused_a_kn<true, AR, W, MB> : k_fused_a_kn<false, AR, W, MB>;                        \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
+      int64_t gg = (int64_t)pl->num_sms * MB;                                                                      \
+      if (gg > batch) gg = batch;                                                                                  \
+      if (e == cudaSuccess) kern<<<(int)gg, W * 32, smem, st>>>(y, batch, 3, CC);                                  \
+    } while (0)
+    if (F->cls[0] == ARITH_M) KN(ArithM); else KN(ArithS);
 #undef KN
-      if (e == cudaSuccess) e = cudaGetLastError();
-      if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_kn");
-      count_launch();
-      return LOLB_OK;
-    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_fused_a_kn");
+    count_launch();
+    return LOLB_OK;
   }
   for (int t = 0; t < pl->k; t++) {
     const FusedAConsts& C = inverse ? F->inv[t] : F->fwd[t];

@@ -776,11 +776,14 @@ int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t
     const int rc = pow2_resident_crt(pl, F, INV, y, batch, st);      // m <= 2^14: element-resident kernels where they win
     if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
   }
-  // measured (B200, e = 16): tupSize 4 is faster unpaired (56 % / 54 % vs 54 % / 54 % of HBM peak), tupSize 1 and 2
-  // paired (63 % / 59 %, 60 % / 58 % vs 61 % / 59 %, 58 % / 57 %).  Keeping the rounds 5-9 twiddles in shared memory
-  // instead of L1 was measured too: no gain, and it costs the paired kernel a CTA per SM.
+  // Measured on B200, CRT / CRT^-1 as % of the HBM roofline:
+  //   e = 16: tupSize 4  split 56.4 / 56.1, unpaired 55.9 / 54.6, paired 54 / 54;  tupSize 1  split 65.6 / 60.5, paired 62.7 / 59.5;
+  //           tupSize 2  paired 60.2 / 57.8, split 58.9 / 56.4
+  //   e = 15, tupSize 4: split 61.6 / 59.4, unpaired 51.9 / 49.1;   e = 14, tupSize 4: split 61.8 / 61.5, unpaired 42 / 38
+  // so the split schedule (two plain kernels, the u32 intermediate through a workspace) serves everything except tupSize 2 at
+  // e = 16; keeping the rounds 5-9 twiddles in shared memory instead of L1 was measured too: no gain.
   const char* sched = getenv("LOLB_DF_SCHEDULE");      // "split" / "paired" / "unpaired" override
-  if (!sched || sched[0] == 's') {
+  if (sched ? sched[0] == 's' : !(K == 2 && F->top == 5)) {
     const int rc = pow2_split_crt(pl, F, INV, y, batch, st);
     if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
   }

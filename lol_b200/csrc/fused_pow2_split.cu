@@ -195,9 +195,13 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
     typedef SpGeom<K, TOP> Geo;
     const DfParams P = INV ? F->inv : F->fwd;
     const size_t el_words = (size_t)K * Geo::N;
-    // sub-batch: about 16 MB of u32 ring (three of them stay in the 126 MB L2 beside the streamed element data)
+    // Sub-batch size.  Measured at config B (CRT / CRT^-1, % of HBM roofline): 4 MiB 16 / 26, 8 MiB 36 / 38, 16 MiB 38 / 50,
+    // 32 MiB 47 / 46, 64 MiB 52 / 50, 128 MiB 54 / 53, 256 MiB 55 / 54, 512 MiB 56.4 / 56.1: every kernel boundary costs
+    // about 10 us of drain, fill and cross-stream dependency latency, more than an L2-resident ring wins back, so the
+    // sub-batch is as large as a 512 MiB workspace allows and the intermediate mostly travels through HBM (ncu: both kernels
+    // run at 78-82 % of the measured HBM peak on 1.5x the algorithmic traffic).
     const char* mb_env = getenv("LOLB_SPLIT_MB");      // tuning / test override of the sub-batch size
-    const int64_t mb = mb_env && atoi(mb_env) > 0 ? atoi(mb_env) : 16;
+    const int64_t mb = mb_env && atoi(mb_env) > 0 ? atoi(mb_env) : 512;
     int64_t S = (mb << 20) / (int64_t)(el_words * sizeof(uint32_t));
     if (S < 1) S = 1;
     if (S > batch) S = batch;

@@ -247,6 +247,24 @@ def test_batched_rq_matches_oracle(torch_cuda, oracle, m, qs, force_generic):
     assert t.crt(e).shape[0] == 0
 
 
+@pytest.mark.parametrize("qs", [CONFIG_C[1], [14401, 43201], [14401, 1008001, 429336001]], ids=lambda v: str(v))
+def test_deinterleaving_kernel_small_tuples(torch_cuda, oracle, monkeypatch, qs):
+    """k_fused_a_kd is the default from tupSize 4 on (BATCH_PARAMS above); LOLB_FUSED_A_KD=1 selects it for tupSize 2 and 3 as
+    well, where k_fused_a_k2 / k_fused_a_kn measured faster.  Same parity bar: bit-exact against the oracle, ragged batch."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    monkeypatch.setenv("LOLB_FUSED_A_KD", "1")
+    m, B = 14400, 19
+    rng = np.random.default_rng(len(qs) + 41)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    y = zq_input(rng, n, qs, batch=B)
+    y[3, :5] = y[3, :5] + np.array(qs) * 3      # non-canonical input is reduced like the reference's `c % q`
+    x = torch.from_numpy(y).cuda()
+    assert np.array_equal(t.crt(x).cpu().numpy(), np.stack([oracle.tensorCRTRq(y[b], pe, ru, qs) for b in range(B)]))
+    assert np.array_equal(t.crtInv(x).cpu().numpy(), np.stack([oracle.tensorCRTInvRq(y[b], pe, rui, mh, qs) for b in range(B)]))
+
+
 @pytest.mark.parametrize("m,qs", [CONFIG_A, CONFIG_C, (14400, [14401, 1008001, 429336001]), (42, [8191]), (2 ** 13, [537133057])],
                          ids=lambda v: str(v))
 def test_fused_crt_mul_pairs(torch_cuda, oracle, m, qs):
