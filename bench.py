@@ -543,6 +543,28 @@ def run_gpu_arm(args):
             she_extra["ext_section_error"] = f"{type(exc).__name__}: {exc}"
         torch.cuda.empty_cache()
 
+    # ---- N > 1 only: inputs that start on one rank.  NCCL over NVLink scatters a batch from rank 0 and gathers the results
+    # (lol_b200/shard.py: grouped ncclSend / ncclRecv); outside the headline step, which generates its data per rank.
+    shard_io = None
+    if world > 1 and not args.no_per_op:
+        from lol_b200.shard import gather_batch, scatter_batch
+        Bn = 4096 * world
+        full = torch.randint(0, QS[0], (Bn, N_COEFF, 1), dtype=torch.int64, device="cuda", generator=gen) if rank == 0 else None
+        loc = scatter_batch(full, Bn, (N_COEFF, 1), torch.int64, torch.device("cuda", local))      # warm-up (NCCL channels)
+        gather_batch(loc, Bn)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        loc = scatter_batch(full, Bn, (N_COEFF, 1), torch.int64, torch.device("cuda", local))
+        torch.cuda.synchronize(); dist.barrier()
+        t1 = time.perf_counter()
+        back = gather_batch(loc, Bn)
+        torch.cuda.synchronize(); dist.barrier()
+        t2 = time.perf_counter()
+        moved = (Bn - 4096) * N_COEFF * 8
+        shard_io = {"bytes_over_nvlink": moved, "scatter_GB/s": moved / reduce_max(t1 - t0) / 1e9, "gather_GB/s": moved / reduce_max(t2 - t1) / 1e9,
+                    "roundtrip_identical": bool(rank != 0 or torch.equal(back, full))}
+        del full, loc, back
+
     rec.reduce_max(torch, dist, world)
     if rank != 0:
         if world > 1:
@@ -568,6 +590,8 @@ def run_gpu_arm(args):
     detail = rec.table(peak, world)
     if she_extra:
         detail["extra"] = she_extra
+    if shard_io:
+        detail["nccl_shard_io"] = shard_io
     sys.stderr.write("DETAIL " + json.dumps({"n_gpus": world, "peak_GB/s": peak, "sections": detail}) + "\n")
     sys.stderr.flush()
     out_dir = os.path.join(ROOT, "gpurun_out")
@@ -589,6 +613,9 @@ def run_gpu_arm(args):
     for s, n, ms, _, units, _ in rec.rows:
         if s == "she" and n == "mulAndSwitch":
             summary["she_n"] = round(world * units / (ms * 1e-3))
+    if shard_io:
+        summary["nvl_scatter_GBs"] = round(shard_io["scatter_GB/s"], 1)
+        summary["nvl_gather_GBs"] = round(shard_io["gather_GB/s"], 1)
     if e2e:
         summary["e2e_copy_frac"] = round(e2e["frac_of_copy_ceiling"], 3)
         summary["e2e_u32"] = round(e2e["u32_wire"]["value"])

@@ -25,41 +25,50 @@ def max_shard(batch: int, world: int) -> int:
 
 def scatter_batch(full: torch.Tensor | None, batch: int, tail: tuple[int, ...], dtype: torch.dtype,
                   device, src: int = 0, group=None) -> torch.Tensor:
-    """Rank `src` holds `full` ([batch, *tail]); every rank returns its shard ([hi-lo, *tail]).
-    Shards travel padded to the largest shard so the collective is one `scatter`."""
+    """Rank `src` holds `full` ([batch, *tail], on `device`); every rank returns its shard ([hi-lo, *tail]).
+    One grouped send/receive (ncclSend / ncclRecv over NVLink on GPUs): rank `src` sends the contiguous slices of `full`
+    themselves -- no padded or staged copies -- and every other rank receives straight into its shard."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    pad = max_shard(batch, world)
-    recv = torch.empty((pad, *tail), dtype=dtype, device=device)
-    chunks = None
-    if rank == src:
-        assert full is not None and tuple(full.shape) == (batch, *tail)
-        chunks = []
-        for r in range(world):
-            lo, hi = shard_bounds(batch, world, r)
-            c = torch.zeros((pad, *tail), dtype=dtype, device=device)
-            c[: hi - lo] = full[lo:hi].to(device)
-            chunks.append(c)
-    dist.scatter(recv, chunks, src=src, group=group)
     lo, hi = shard_bounds(batch, world, rank)
-    return recv[: hi - lo].contiguous()
+    if rank == src:
+        assert full is not None and tuple(full.shape) == (batch, *tail) and full.dtype == dtype and full.is_contiguous()
+        ops = []
+        for r in range(world):
+            rlo, rhi = shard_bounds(batch, world, r)
+            if r != src and rhi > rlo:
+                ops.append(dist.P2POp(dist.isend, full[rlo:rhi], r, group))
+        for req in (dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
+        return full[lo:hi].clone()
+    recv = torch.empty((hi - lo, *tail), dtype=dtype, device=device)
+    if hi > lo:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, recv, src, group)]):
+            req.wait()
+    return recv
 
 
 def gather_batch(local: torch.Tensor, batch: int, dst: int = 0, group=None) -> torch.Tensor | None:
-    """Inverse of `scatter_batch`: rank `dst` returns the [batch, *tail] tensor, the others None."""
+    """Inverse of `scatter_batch`: rank `dst` returns the [batch, *tail] tensor, the others None.  Rank `dst` receives every
+    shard straight into its slice of the result."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    pad = max_shard(batch, world)
-    tail = tuple(local.shape[1:])
-    send = torch.zeros((pad, *tail), dtype=local.dtype, device=local.device)
-    send[: local.shape[0]] = local
-    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send, bufs, dst=dst, group=group)
+    lo, hi = shard_bounds(batch, world, rank)
+    assert local.shape[0] == hi - lo and local.is_contiguous()
     if rank != dst:
+        if hi > lo:
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]):
+                req.wait()
         return None
-    parts = []
+    out = torch.empty((batch, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    ops = []
     for r in range(world):
-        lo, hi = shard_bounds(batch, world, r)
-        parts.append(bufs[r][: hi - lo])
-    return torch.cat(parts, dim=0)
+        rlo, rhi = shard_bounds(batch, world, r)
+        if r != dst and rhi > rlo:
+            ops.append(dist.P2POp(dist.irecv, out[rlo:rhi], r, group))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    out[lo:hi] = local
+    for req in reqs:
+        req.wait()
+    return out
 
 
 def broadcast_replicated(t: torch.Tensor | None, shape: tuple[int, ...], dtype: torch.dtype, device, src: int = 0,
