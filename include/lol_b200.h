@@ -249,6 +249,8 @@ int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double* out, int6
  *   lolb_coeffsPowDec O_m' -> (O_m)^(phi'/phi), y laid out [batch][phi'/phi][phi][k]     Extension.hs:90-93
  *   lolb_twaceCRT     O_m' -> O_m   y[i]  = sum of the phi'/phi entries of tweak . x lying above i, tweak =
  *                                   m'hat^-1 mhat embedCRT(gInvCRT_m) gCRT_m'            Extension.hs:110-129
+ *   lolb_powBasisPow  -> (O_m')^(phi'/phi), y laid out [phi'/phi][phi'][k]: vector r is `one` where baseIndicesPow = (r, 0),
+ *                                   the O_m-basis of O_m' in the powerful basis (no input, no batch)   Extension.hs:133-143
  * embedCRT / twaceCRT return LOLB_ERR_NO_CRT where the reference's `CRTrans` yields Nothing (no CRT of index m' over the
  * moduli) and for the R / Double rings.
  */
@@ -278,6 +280,7 @@ int lolb_embedDec(const lolb_ext* ext, int ring, const void* x, void* y, int64_t
 int lolb_embedCRT(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
 int lolb_coeffsPowDec(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
 int lolb_twaceCRT(const lolb_ext* ext, int ring, const void* x, void* y, int64_t batch, void* stream);
+int lolb_powBasisPow(const lolb_ext* ext, int ring, void* y, void* stream);
 
 /*
  * Coefficient-wise maps either side of the transforms when Lol switches moduli or rounds an error term; host `fmapT`

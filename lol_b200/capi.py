@@ -292,6 +292,9 @@ class Extension:
         check(lib().lolb_ext_get_table(self._h, C.c_int(which), out.ctypes.data_as(_p)))
         return out
 
+    def pow_basis_pow(self, ring: int, y_ptr: int, stream: int = 0) -> int:
+        return int(lib().lolb_powBasisPow(self._h, C.c_int(ring), _p(y_ptr), _p(stream)))
+
     def op(self, name: str, ring: int, x_ptr: int, y_ptr: int, batch: int, stream: int = 0) -> int:
         """name: 'twacePowDec', 'embedPow', 'embedDec', 'embedCRT', 'coeffsPowDec', 'twaceCRT'."""
         f = getattr(lib(), "lolb_" + name)

@@ -17,6 +17,7 @@
 // invariants; consecutive threads write consecutive words.  Bytes per ring element: 8 k (phi_out + phi_read) for the
 // gathers (phi_read = number of non-zero outputs), 8 k (phi' + phi) for twaceCRT, tables excluded (L1/L2 resident).
 // Z_q arithmetic is exact on canonical residues (64-bit Barrett), so results equal the host formulas bit for bit.
+#include <algorithm>
 #include <cstring>
 
 #include "fused.cuh"
@@ -32,6 +33,7 @@ struct lolb_ext {
   int32_t phi = 1, phi2 = 1, rel = 1;
   std::vector<int32_t> h_tab[LOLB_EXT_TABLES];
   int32_t* d_code[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // twace, embedPow, embedDec, embedCRT, coeffs
+  int32_t* d_base_j = nullptr;     // [2][phi']: baseIndicesPow as (j0, j1) planes, for powBasisPow
   int32_t* d_crt_idx = nullptr;    // [rel][phi]: extIndicesCRT transposed so that consecutive threads read consecutive entries
   uint32_t* d_tweak = nullptr;     // Rq: [rel][phi][k] canonical residues
   double2* d_ctweak = nullptr;     // complex: [rel][phi][k]
@@ -362,6 +364,9 @@ int build_tables(lolb_ext* x, const std::vector<MergedPP>& mp)
   if (!rc) rc = upload_i32(&x->d_code[CODE_COEFFS], code);
   for (int32_t j = 0; j < phi2; j++) code[(int64_t)(j % rel) * phi + j / rel] = crt[j];      // [rel][phi]
   if (!rc) rc = upload_i32(&x->d_crt_idx, code);
+  code.assign(j0.begin(), j0.end());
+  code.insert(code.end(), j1.begin(), j1.end());
+  if (!rc) rc = upload_i32(&x->d_base_j, code);
   return rc;
 }
 
@@ -529,6 +534,7 @@ extern "C" void lolb_ext_destroy(lolb_ext* x)
   if (!x) return;
   for (int32_t* p : x->d_code) if (p) cudaFree(p);
   if (x->d_crt_idx) cudaFree(x->d_crt_idx);
+  if (x->d_base_j) cudaFree(x->d_base_j);
   if (x->d_tweak) cudaFree(x->d_tweak);
   if (x->d_ctweak) cudaFree(x->d_ctweak);
   delete x;
@@ -557,6 +563,35 @@ extern "C" int lolb_ext_get_table(const lolb_ext* x, int which, int32_t* out)
 {
   if (!x || !out || which < 0 || which >= LOLB_EXT_TABLES) { set_error("lolb_ext_get_table: bad argument"); return LOLB_ERR_ARG; }
   memcpy(out, x->h_tab[which].data(), x->h_tab[which].size() * sizeof(int32_t));
+  return LOLB_OK;
+}
+
+// powBasisPow' (Extension.hs:133-143): the phi'/phi vectors of O_m' that form an O_m-basis of O_m', in the powerful basis:
+// vector r has `one` where baseIndicesPow = (r, 0) and zero elsewhere.  One thread per 8-byte (or 16-byte complex) word.
+template <class T>
+__global__ void k_ext_pow_basis(T* __restrict__ y, const int32_t* __restrict__ base_j, int32_t phi2, int32_t k, int64_t total, T one, T zero)
+{
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t w = idx / k;
+    const int32_t j = (int32_t)(w % phi2), r = (int32_t)(w / phi2);
+    y[idx] = (base_j[j] == r && base_j[phi2 + j] == 0) ? one : zero;
+  }
+}
+
+extern "C" int lolb_powBasisPow(const lolb_ext* x, int ring, void* y, void* stream)
+{
+  int rc = check_ring(x, ring, __func__);
+  if (rc) return rc;
+  if (!y) { set_error("lolb_powBasisPow: NULL output"); return LOLB_ERR_ARG; }
+  const int64_t total = (int64_t)x->rel * x->phi2 * x->k;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)x->hi->num_sms * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ring == LOLB_RING_C) k_ext_pow_basis<double2><<<blocks, 256, 0, st>>>((double2*)y, x->d_base_j, x->phi2, x->k, total, make_double2(1.0, 0.0), make_double2(0.0, 0.0));
+  else if (ring == LOLB_RING_DOUBLE) k_ext_pow_basis<double><<<blocks, 256, 0, st>>>((double*)y, x->d_base_j, x->phi2, x->k, total, 1.0, 0.0);
+  else k_ext_pow_basis<long long><<<blocks, 256, 0, st>>>((long long*)y, x->d_base_j, x->phi2, x->k, total, 1LL, 0LL);      // q >= 2: one = 1 in every limb
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_ext_pow_basis");
+  count_launch();
   return LOLB_OK;
 }
 

@@ -6,6 +6,7 @@
     embedPow / embedDec                embedPow', embedDec'  Extension.hs:60-77          .embedPow / .embedDec
     crtExtFuncs: twaceCRT, embedCRT    twaceCRT', embedCRT'  Extension.hs:81-85, 110-129 .twaceCRT / .embedCRT (None = Nothing)
     coeffs                             coeffs'  Extension.hs:90-93                       .coeffs
+    powBasisPow                        powBasisPow'  Extension.hs:133-143                .powBasisPow
 
 An extension is built from two single-index tensors of `lol_b200.tensor` over the same ring (`CudaTensorRq` with equal
 moduli, or two of `CudaTensorInt` / `CudaTensorReal` / `CudaTensorComplex` with equal tupSize).  Operands are torch CUDA
@@ -58,6 +59,12 @@ class CudaExtension:
     def embedDec(self, x): return self._run("embedDec", x, self.phi, (self.phi2, self.k))
     def embedCRT(self, x): return self._run_crt("embedCRT", x, self.phi, (self.phi2, self.k))
     def twaceCRT(self, x): return self._run_crt("twaceCRT", x, self.phi2, (self.phi, self.k))
+
+    def powBasisPow(self):
+        """[phi'/phi, phi', k]: the vectors of O_m' (powerful basis) that form an O_m-basis of O_m' (Tensor.hs:177)."""
+        y = torch.empty((self.phi2 // self.phi, self.phi2, self.k), dtype=self.dtype, device="cuda")
+        capi.check(self.ext.pow_basis_pow(self.ring, y.data_ptr(), _stream()))
+        return y
 
     def coeffs(self, x):
         """[batch, phi', k] -> [batch, phi'/phi, phi, k]: the O_m coefficients w.r.t. the powerful / decoding extension basis."""

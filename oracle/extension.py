@@ -158,6 +158,14 @@ def embed_crt(info: ExtInfo, x):
     return x[info.base_crt]
 
 
+def pow_basis_pow(info: ExtInfo, k: int = 1, dtype=np.int64):
+    """Extension.hs:133-143 (powBasisPow'): [phi'/phi][phi'][k], vector r = one where baseIndicesPow = (r, 0), zero elsewhere."""
+    out = np.zeros((info.rel, info.phi2, k), dtype=dtype)
+    for r in range(info.rel):
+        out[r, (info.base_pow_j0 == r) & (info.base_pow_j1 == 0), :] = 1
+    return out
+
+
 def coeffs_powdec(info: ExtInfo, x):
     """Extension.hs:90-93 (coeffs'): [phi'/phi][phi][k]."""
     return x[info.ext_coeffs]

@@ -23,6 +23,12 @@ from oracle import tables as T
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(scope="module")
+def oracle(gpu_oracle):
+    """GPU suites compare with the compiled reference when it is present (conftest.gpu_oracle)."""
+    return gpu_oracle
+
 FLOAT_TOL = 1e-9      # BASELINE.json: "within a stated relative tolerance (e.g. 1e-9)"
 GOLDEN = sorted(g for g in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
                 if not os.path.basename(g).startswith("ext_"))      # ext_*: ring-extension fixtures, tests/test_*_extension.py

@@ -146,6 +146,14 @@ def test_extension_properties_at_full_size(torch_cuda):
     assert torch.equal(ext.embedDec(x), hi.lInv(ext.embedPow(lo.l(x))))
     c = ext.coeffs(y)
     assert torch.equal(c[:, 0], ext.twacePowDec(y))
+    # prop_coeffsBasis (CycTests.hs:71-76): y == sum_r embed(coeffs y)_r * powBasis_r, products through the CRT basis of O_m'
+    from oracle import extension as X
+    basis = ext.powBasisPow()
+    assert np.array_equal(basis.cpu().numpy(), X.pow_basis_pow(X.ExtInfo(m, m2), 2))
+    acc = torch.zeros_like(y[:256])
+    for r in range(basis.shape[0]):
+        acc = (acc + hi.crtMul(ext.embedPow(c[:256, r].contiguous()), hi.crt(basis[r:r + 1]))) % q
+    assert torch.equal(hi.crtInv(acc), y[:256])
 
 
 def test_extension_argument_errors(torch_cuda):

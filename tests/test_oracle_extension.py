@@ -207,9 +207,9 @@ def test_prop_coeffsBasis(reference, m, m2, qs):
     q = np.asarray(qs, dtype=object)
     acc = np.zeros((info.phi2, len(qs)), dtype=object)
     cs = X.coeffs_powdec(info, x)
+    basis = X.pow_basis_pow(info, len(qs))                                  # powBasisPow': one where (j0, j1) == (k, 0)
     for k in range(info.rel):
-        b = np.zeros((info.phi2, len(qs)), dtype=np.int64)
-        b[(info.base_pow_j0 == k) & (info.base_pow_j1 == 0)] = 1            # powBasisPow': one where (j0, j1) == (k, 0)
+        b = basis[k]
         assert b.sum() == len(qs)
         prod = hi.crt(X.embed_pow(info, cs[k])).astype(object) * hi.crt(b).astype(object) % q
         acc = (acc + prod) % q
