@@ -229,6 +229,19 @@ int lolb_tensorCRTInvC(const lolb_plan* plan, lolb_complex* y, int64_t batch, vo
 int lolb_mulC(const lolb_plan* plan, lolb_complex* a, const lolb_complex* b, int64_t batch, int64_t b_batch, void* stream);
 /* y: batch elements of totm*tupSize doubles, i.i.d. Gaussians in, decoding-basis coefficients out (random.cpp:61-64) */
 int lolb_tensorGaussianDec(const lolb_plan* plan, double* y, int64_t batch, void* stream);
+/*
+ * The Gaussian source on the device.  In the reference the inputs of tensorGaussianDec are drawn on the host by
+ * `realGaussians` (lol/Crypto/Lol/GaussRandom.hs:34-59, polar Box-Muller over a MonadRandom) and handed to C
+ * (lol-cpp/.../CPP.hs:376-389).  Here the same transform runs over a counter-based generator (Philox4x32-10): a value is a
+ * pure function of (seed, first_element + b, position), so a batch can be produced in pieces and does not depend on
+ * the launch shape.  Parity with the reference is distributional (another uniform source).
+ *   lolb_realGaussians  y[batch][n] (device) <- i.i.d. Gaussians of scaled variance svar, i.e. true variance svar / (2 pi)
+ *   lolb_tGaussianDec   `tGaussianDec v` of class Tensor (Tensor.hs:143): draws of scaled variance v * m / rad(m), then the
+ *                       transform of tensorGaussianDec, in one pass over y (8 n bytes per element) where the streaming kernel
+ *                       serves the index
+ */
+int lolb_realGaussians(double svar, uint64_t seed, uint64_t first_element, double* y, int64_t n, int64_t batch, void* stream);
+int lolb_tGaussianDec(const lolb_plan* plan, double v, uint64_t seed, uint64_t first_element, double* y, int64_t batch, void* stream);
 /* out[b*tupSize + t] (device) <- the value the drop-in symbol leaves in y[t]; y is not modified */
 int lolb_tensorNormSqR(const lolb_plan* plan, const hInt_t* y, hInt_t* out, int64_t batch, void* stream);
 int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double* out, int64_t batch, void* stream);

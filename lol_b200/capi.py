@@ -229,6 +229,9 @@ class PlanC:
         f = getattr(lib(), "lolb_tensor" + name)
         return int(f(self._h, _p(ptr), _i64(batch), _p(stream)))
 
+    def t_gaussian_dec(self, v: float, seed: int, first: int, ptr: int, batch: int, stream: int = 0) -> int:
+        return int(lib().lolb_tGaussianDec(self._h, C.c_double(v), C.c_uint64(seed), C.c_uint64(first), _p(ptr), _i64(batch), _p(stream)))
+
     def ginv_r(self, name: str, ptr: int, ok_ptr: int, batch: int, stream: int = 0) -> int:
         f = getattr(lib(), "lolb_tensor" + name + "R")
         return int(f(self._h, _p(ptr), _p(ok_ptr), _i64(batch), _p(stream)))
@@ -244,6 +247,11 @@ class PlanC:
 # ------------------------------------------------------------------ ring extensions O_m'/O_m (lolb_ext_*)
 RING_RQ, RING_R, RING_DOUBLE, RING_C = 0, 1, 2, 3
 EXT_INDICES_POWDEC, EXT_INDICES_CRT, EXT_BASE_POW_J0, EXT_BASE_POW_J1, EXT_BASE_DEC, EXT_INDICES_COEFFS = range(6)
+
+
+def real_gaussians(svar: float, seed: int, first: int, ptr: int, n: int, batch: int, stream: int = 0) -> int:
+    """lolb_realGaussians: [batch][n] doubles on the device, i.i.d. N(0, svar / (2 pi))."""
+    return int(lib().lolb_realGaussians(C.c_double(svar), C.c_uint64(seed), C.c_uint64(first), _p(ptr), _i64(n), _i64(batch), _p(stream)))
 
 
 def fused_w_emulate(pps, qs, y: np.ndarray, inverse: bool = False) -> np.ndarray:

@@ -454,6 +454,32 @@ extern "C" int lolb_tensorGaussianDec(const lolb_plan* plan, double* y, int64_t 
   }
   return engine_gauss(plan, y, batch, (cudaStream_t)stream);
 }
+// GaussRandom.hs:52-59 on the device: y[batch][n] i.i.d. Gaussians of scaled variance svar (true variance svar / (2 pi))
+extern "C" int lolb_realGaussians(double svar, uint64_t seed, uint64_t first_element, double* y, int64_t n, int64_t batch, void* stream)
+{
+  if (n < 0 || batch < 0 || (n > 0 && batch > 0 && !y) || !(svar >= 0.0)) { set_error("lolb_realGaussians: bad argument"); return LOLB_ERR_ARG; }
+  return fused_plain_real_gaussians(nullptr, y, n, batch, seed, first_element, svar / 3.14159265358979323846, (cudaStream_t)stream);
+}
+
+// tGaussianDec (Tensor.hs:143; CPP.hs:376-389): n reals of scaled variance v * m / rad(m), then the E_m transform
+// (tensorGaussianDec), both on the device -- one pass where the streaming kernel serves the index, two otherwise
+extern "C" int lolb_tGaussianDec(const lolb_plan* plan, double v, uint64_t seed, uint64_t first_element, double* y, int64_t batch, void* stream)
+{
+  REQUIRE_PLAN(PLAN_C);
+  if (!plan->has_fwd) return LOLB_ERR_NO_CRT;
+  if (!(v >= 0.0)) { set_error("lolb_tGaussianDec: negative variance"); return LOLB_ERR_ARG; }
+  int64_t rad = 1;
+  for (const PrimeExponent& pe : plan->pe) rad *= pe.prime;
+  const double var2 = v * (double)(plan->m / rad) / 3.14159265358979323846;      // twice the true variance
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!plan->force_generic) {
+    int rc = fused_plain_gauss_gen(plan, y, batch, st, true, seed, first_element, var2);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
+  int rc = fused_plain_real_gaussians(plan, y, (int64_t)plan->n * plan->k, batch, seed, first_element, var2, st);
+  return rc ? rc : lolb_tensorGaussianDec(plan, y, batch, stream);
+}
+
 extern "C" int lolb_tensorNormSqR(const lolb_plan* plan, const hInt_t* y, hInt_t* out, int64_t batch, void* stream)
 {
   REQUIRE_PLAN(PLAN_C);

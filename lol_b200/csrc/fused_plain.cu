@@ -4,6 +4,8 @@
 // (pA-1)*(pB-1) coefficients that share all other tensor digits, applies axis A then axis B in registers, one HBM
 // read and one HBM write per coefficient, no shared memory.  tupSize > 1 is folded into the strides for the
 // element-wise operators (I (x) A (x) I_{R*k}); Gaussian and norm are per-limb and take tupSize = 1 here.
+#include <algorithm>
+
 #include "fused.cuh"
 #include "rings.cuh"
 
@@ -152,9 +154,72 @@ __device__ __forceinline__ void gauss_line(double (&v)[P - 1], const double (&E)
   for (int row = 0; row < D; row++) v[row] = o[row];
 }
 
-template <int PA, int PB>
+// ------------------------------------------------------------------ on-device Gaussian source (GaussRandom.hs:34-59)
+// The reference draws its continuous Gaussians on the host: `realGaussian` is the polar form of Box-Muller over a
+// `MonadRandom` -- (u, v) uniform in (-1, 1)^2 until 0 < t = u^2 + v^2 < 1, then (u, v) * sqrt(-var ln t / t) with
+// var = svar / pi (svar = 2 pi x the true variance).  Here the same transform runs per thread over a counter-based
+// generator, Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): a draw is a pure function of (seed, ring element, pair
+// index, attempt), so results do not depend on the launch shape and batches can be generated in pieces.  A different
+// uniform source than any Haskell `RandomGen`, so parity with the reference is distributional (tests: moments, KS, the
+// reference's gSqNorm bound).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// 53 random bits -> uniform on the open interval (-1, 1), symmetric about 0
+__device__ __forceinline__ double uniform_pm1(uint32_t hi, uint32_t lo)
+{
+  const uint64_t bits = ((uint64_t)hi << 21) | (lo >> 11);                   // 53 bits
+  return ((double)bits + 0.5) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+// one accepted pair of independent N(0, var2 / 2) values
+__device__ __forceinline__ void gauss_pair(uint64_t seed, uint64_t element, uint32_t pair, double var2, double& g0, double& g1)
+{
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (uint32_t attempt = 0;; attempt++) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)element, (uint32_t)(element >> 32), pair, attempt), key);
+    const double u = uniform_pm1(r.x, r.y), v = uniform_pm1(r.z, r.w);
+    const double t = u * u + v * v;
+    if (t < 1.0 && t > 0.0) {                                                // uvGuard, GaussRandom.hs:47
+      const double com = sqrt(-var2 * log(t) / t);
+      g0 = u * com;
+      g1 = v * com;
+      return;
+    }
+  }
+}
+
+// realGaussians (GaussRandom.hs:52-59): y[e][0 .. n) i.i.d. N(0, var2 / 2); one thread per pair, coefficients (2p, 2p+1)
 __global__ void __launch_bounds__(256)
-k_gauss_stream(double* __restrict__ y, int64_t batch, const __grid_constant__ PlainGeom G, const __grid_constant__ GaussMats E)
+k_real_gaussians(double* __restrict__ y, int64_t n, int64_t batch, uint64_t seed, uint64_t first, double var2)
+{
+  const int64_t pairs = (n + 1) / 2, total = pairs * batch;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / pairs, p = idx - e * pairs;
+    double g0, g1;
+    gauss_pair(seed, first + (uint64_t)e, (uint32_t)p, var2, g0, g1);
+    double* dst = y + e * n + 2 * p;
+    if (2 * p + 1 < n) {
+      if ((n & 1) == 0) __stcs(reinterpret_cast<double2*>(dst), make_double2(g0, g1));
+      else { dst[0] = g0; dst[1] = g1; }
+    } else dst[0] = g0;
+  }
+}
+
+template <int PA, int PB, bool GEN = false>
+__global__ void __launch_bounds__(256)
+k_gauss_stream(double* __restrict__ y, int64_t batch, const __grid_constant__ PlainGeom G, const __grid_constant__ GaussMats E,
+               uint64_t seed = 0, uint64_t first = 0, double var2 = 0.0)
 {
   constexpr int DA = PA - 1, DB = PB > 1 ? PB - 1 : 1;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,10 +228,20 @@ k_gauss_stream(double* __restrict__ y, int64_t batch, const __grid_constant__ Pl
   for (int64_t e = blockIdx.y; e < batch; e += gridDim.y) {
     double* base = y + (size_t)e * G.n + ix.off;
     double v[DB][DA];
+    if (GEN) {
+      // tGaussianDec in one pass (CPP.hs:376-389): the tile's inputs are drawn here instead of read -- 8 n bytes per
+      // element move instead of 24 n (fill + in-place transform); pair (b, i) of tile t is stream (e, (t DB + b) DA/2 + i)
 #pragma unroll
-    for (int b = 0; b < DB; b++)
+      for (int b = 0; b < DB; b++)
 #pragma unroll
-      for (int a = 0; a < DA; a++) v[b][a] = __ldcs(base + ix.sa * a + ix.sb * b);
+        for (int i = 0; i < DA / 2; i++)
+          gauss_pair(seed, first + (uint64_t)e, (uint32_t)((t * DB + b) * (DA / 2) + i), var2, v[b][2 * i], v[b][2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) v[b][a] = __ldcs(base + ix.sa * a + ix.sb * b);
+    }
 #pragma unroll
     for (int b = 0; b < DB; b++) gauss_line<PA>(v[b], E.a);
     if constexpr (PB > 1) {
@@ -363,7 +438,22 @@ int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t b
   return line_combo<C64Ring>(pl, kind, G, cnt, p, (double2*)y, batch, rscale, st);
 }
 
+int fused_plain_gauss_gen(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st, bool gen, uint64_t seed, uint64_t first, double var2);
+
 int fused_plain_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st)
+{ return fused_plain_gauss_gen(pl, y, batch, st, false, 0, 0, 0.0); }
+
+int fused_plain_real_gaussians(const lolb_plan* pl, double* y, int64_t n, int64_t batch, uint64_t seed, uint64_t first, double var2, cudaStream_t st)
+{
+  if (batch <= 0 || n <= 0) return LOLB_OK;
+  const int64_t total = ((n + 1) / 2) * batch;
+  const int sms = pl ? pl->num_sms : 148;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+  k_real_gaussians<<<blocks, 256, 0, st>>>(y, n, batch, seed, first, var2);
+  return launched("k_real_gaussians");
+}
+
+int fused_plain_gauss_gen(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st, bool gen, uint64_t seed, uint64_t first, double var2)
 {
   if (batch <= 0) return LOLB_OK;
   if (pl->k != 1) return LOLB_FUSED_UNAVAILABLE;
@@ -384,13 +474,19 @@ int fused_plain_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_
   }
   int threads;
   const dim3 grid = tile_grid(pl, G, batch, &threads);
+#define GS(PA, PB)                                                                                               \
+  do {                                                                                                            \
+    if (gen) k_gauss_stream<PA, PB, true><<<grid, threads, 0, st>>>(y, batch, G, E, seed, first, var2);           \
+    else k_gauss_stream<PA, PB, false><<<grid, threads, 0, st>>>(y, batch, G, E);                                 \
+  } while (0)
   if (cnt == 1) {
-    if (p[0] == 3) k_gauss_stream<3, 1><<<grid, threads, 0, st>>>(y, batch, G, E);
-    else if (p[0] == 5) k_gauss_stream<5, 1><<<grid, threads, 0, st>>>(y, batch, G, E);
-    else k_gauss_stream<7, 1><<<grid, threads, 0, st>>>(y, batch, G, E);
-  } else if (p[1] == 5) k_gauss_stream<3, 5><<<grid, threads, 0, st>>>(y, batch, G, E);
-  else k_gauss_stream<3, 7><<<grid, threads, 0, st>>>(y, batch, G, E);
-  return launched("k_gauss_stream");
+    if (p[0] == 3) GS(3, 1);
+    else if (p[0] == 5) GS(5, 1);
+    else GS(7, 1);
+  } else if (p[1] == 5) GS(3, 5);
+  else GS(3, 7);
+#undef GS
+  return launched(gen ? "k_gauss_stream<gen>" : "k_gauss_stream");
 }
 
 template <class R>

@@ -257,13 +257,19 @@ class CudaTensorReal(_CudaTensorPlain):
         capi.check(self.plan.op("GaussianDec", out.data_ptr(), b, _stream()))
         return out
 
-    def tGaussianDec(self, v: float, batch: int, generator: torch.Generator | None = None, device="cuda"):
-        """CPP.hs:376-389: n reals of scaled variance v*m/rad(m) (true variance svar/(2 pi),
-        GaussRandom.hs:34-59), then the E_m transform."""
-        svar = float(v) * (self.m // radical_fact(self.m))
-        y = torch.randn(batch, self.n, self.k, dtype=torch.float64, device=device, generator=generator)
-        y.mul_(math.sqrt(svar / (2.0 * math.pi)))
-        return self.gaussianDecTransform(y, inplace=True)
+    def tGaussianDec(self, v: float, batch: int, seed: int = 0, first: int = 0, device="cuda"):
+        """`tGaussianDec v` (Tensor.hs:143; CPP.hs:376-389): per element n reals of scaled variance v*m/rad(m) (true variance
+        svar/(2 pi), polar Box-Muller as GaussRandom.hs:34-59) drawn ON THE DEVICE from a counter-based generator keyed by
+        (seed, first + element index), then the E_m transform -- lolb_tGaussianDec, one pass where the streaming kernel applies."""
+        y = torch.empty(batch, self.n, self.k, dtype=torch.float64, device=device)
+        capi.check(self.plan.t_gaussian_dec(float(v), int(seed), int(first), y.data_ptr(), batch, _stream()))
+        return y
+
+    def realGaussians(self, svar: float, batch: int, seed: int = 0, first: int = 0, device="cuda"):
+        """`realGaussians svar n` (GaussRandom.hs:52-59) on the device: [batch, n, k] i.i.d. N(0, svar / (2 pi))."""
+        y = torch.empty(batch, self.n, self.k, dtype=torch.float64, device=device)
+        capi.check(capi.real_gaussians(float(svar), int(seed), int(first), y.data_ptr(), self.n * self.k, batch, _stream()))
+        return y
 
 
 class CudaTensorComplex(_CudaTensorPlain):
