@@ -52,16 +52,15 @@ struct SpGeom {
 
 // chunk kernel: bits [0,10).  Forward: HBM element -> ring.  Inverse: ring -> HBM element (canonical, mhat^-1 folded in).
 template <bool INV, int K, int TOP>
-__global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
-k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+__device__ __forceinline__ void chunk_body(uint32_t* U, const int bid, int64_t* __restrict__ y, const DfParams& P, uint32_t* __restrict__ ring,
+                                           const int rev_n)
 {
   typedef SpGeom<K, TOP> Geo;
   constexpr int N = Geo::N, G = Geo::G, PIECES = Geo::PIECES;
   static_assert(G >= 1 && Geo::NCH % G == 0, "chunk CTAs must tile the element");
   static_assert(Geo::STEP % 32 == 0 && 1024 % Geo::STEP == 0, "piece addressing");
-  __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int el_l = blockIdx.x / Geo::NT_CHUNK, task = blockIdx.x - el_l * Geo::NT_CHUNK;
+  const int el_l = bid / Geo::NT_CHUNK, task = bid - el_l * Geo::NT_CHUNK;
   const int el = rev_n ? rev_n - 1 - el_l : el_l;      // the second kernel of a sub-batch walks it backwards: the ring words written last are still in L2
   uint32_t* slot = ring + (size_t)el * ((size_t)K * N);
   int64_t* ebase = y + (size_t)el * ((size_t)K * N);
@@ -140,15 +139,22 @@ k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32
   }
 }
 
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
+k_pow2_chunk(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+{
+  __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
+  chunk_body<INV, K, TOP>(U, (int)blockIdx.x, y, P, ring, rev_n);
+}
+
 // column kernel: bits [10, 10 + TOP).  Forward: ring -> HBM element (canonical).  Inverse: HBM element -> ring.
 template <bool INV, int K, int TOP>
-__global__ void __launch_bounds__(kSpThreads, LOLB_SP_COL_MINB)
-k_pow2_col(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+__device__ __forceinline__ void col_body(const int bid, int64_t* __restrict__ y, const DfParams& P, uint32_t* __restrict__ ring, const int rev_n)
 {
   typedef SpGeom<K, TOP> Geo;
   constexpr int N = Geo::N, NV = Geo::NV;
   const int tid = threadIdx.x;
-  const int el_l = blockIdx.x / Geo::NT_COL, task = blockIdx.x - el_l * Geo::NT_COL;
+  const int el_l = bid / Geo::NT_COL, task = bid - el_l * Geo::NT_COL;
   const int el = rev_n ? rev_n - 1 - el_l : el_l;
   uint32_t* slot = ring + (size_t)el * ((size_t)K * N);
   int64_t* ebase = y + (size_t)el * ((size_t)K * N);
@@ -185,6 +191,38 @@ k_pow2_col(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t
   }
 }
 
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_COL_MINB)
+k_pow2_col(int64_t* __restrict__ y, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+{
+  col_body<INV, K, TOP>((int)blockIdx.x, y, P, ring, rev_n);
+}
+
+// Mixed launch: the first-kind work of sub-batch i + 1 and the second-kind work of sub-batch i in ONE grid, interleaved by
+// block index, so that consecutive launches on one stream need neither events nor a second stream: launch i's second-kind
+// CTAs read what launch i - 1's first-kind CTAs wrote (stream order), and two ring slots alternate.  Compute-heavy chunk
+// CTAs and latency-bound column CTAs share every SM.
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
+k_pow2_mix(int64_t* __restrict__ yA, uint32_t* __restrict__ ringA, const int nA, int64_t* __restrict__ yB, uint32_t* __restrict__ ringB,
+           const int nB, const int rev_nB, const __grid_constant__ DfParams P)
+{
+  __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
+  // blocks alternate A, B, A, B ... while both kinds have work left
+  const int b = (int)blockIdx.x, m = nA < nB ? nA : nB;
+  bool isA;
+  int idx;
+  if (b < 2 * m) { isA = (b & 1) == 0; idx = b >> 1; }
+  else { isA = nA > nB; idx = b - m; }
+  if (isA) {
+    if (!INV) chunk_body<false, K, TOP>(U, idx, yA, P, ringA, 0);
+    else col_body<true, K, TOP>(idx, yA, P, ringA, 0);
+  } else {
+    if (!INV) col_body<false, K, TOP>(idx, yB, P, ringB, rev_nB);
+    else chunk_body<true, K, TOP>(U, idx, yB, P, ringB, rev_nB);
+  }
+}
+
 constexpr int kSpRing = 3;      // sub-batches of ring in flight: one being written, one being read, one of slack
 
 template <bool INV, int K, int TOP>
@@ -206,6 +244,26 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
     if (S < 1) S = 1;
     if (S > batch) S = batch;
     const int64_t nsub = (batch + S - 1) / S;
+    const char* mix_env = getenv("LOLB_SPLIT_MIX");
+    if (mix_env && mix_env[0] == '1' && nsub >= 2) {
+      uint32_t* ring2 = (uint32_t*)plan_ws(pl, st, (size_t)2 * S * el_words * sizeof(uint32_t));
+      if (!ring2) return LOLB_ERR_CUDA;
+      constexpr int NTA = INV ? Geo::NT_COL : Geo::NT_CHUNK, NTB = INV ? Geo::NT_CHUNK : Geo::NT_COL;
+      for (int64_t i = 0; i <= nsub; i++) {      // launch i: first kind of sub-batch i, second kind of sub-batch i - 1
+        const int64_t cntA = i < nsub ? (batch - i * S < S ? batch - i * S : S) : 0;
+        const int64_t cntB = i > 0 ? (batch - (i - 1) * S < S ? batch - (i - 1) * S : S) : 0;
+        int64_t* yA = y + (size_t)i * S * el_words;
+        int64_t* yB = y + (size_t)(i > 0 ? i - 1 : 0) * S * el_words;
+        uint32_t* rA = ring2 + (size_t)(i & 1) * S * el_words;
+        uint32_t* rB = ring2 + (size_t)((i + 1) & 1) * S * el_words;
+        const int nA = (int)(cntA * NTA), nB = (int)(cntB * NTB);
+        k_pow2_mix<INV, K, TOP><<<(unsigned)(nA + nB), kSpThreads, 0, st>>>(yA, rA, nA, yB, rB, nB, (int)cntB, P);
+      }
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "k_pow2_mix");
+      count_launch((int)(nsub + 1));
+      return LOLB_OK;
+    }
     const int R = (int)(nsub < kSpRing ? nsub : kSpRing);
     uint32_t* ring = (uint32_t*)plan_ws(pl, st, (size_t)R * S * el_words * sizeof(uint32_t));
     if (!ring) return LOLB_ERR_CUDA;

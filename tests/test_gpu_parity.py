@@ -357,9 +357,10 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
 
 
 @pytest.mark.timeout(120)
+@pytest.mark.parametrize("mix", [0, 1], ids=["two-streams", "mixed-launches"])
 @pytest.mark.parametrize("mb", [1, 16], ids=lambda v: f"sub-batch {v} MiB")
 @pytest.mark.parametrize("e,k", [(14, 1), (14, 2), (14, 4), (15, 1), (15, 2), (15, 4), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
-def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb):
+def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb, mix):
     """fused_pow2_split (m = 2^14 .. 2^16, tupSize 1, 2, 4): chunk kernel and column kernel of one sub-batch on two streams behind
     events, ring slots reused three sub-batches later.  1 MiB sub-batches force many ragged sub-batches and every ring slot to
     be reused; oracle parity on a sample, the generic engine on all elements, crtInv . crt = id, and two calls back to back
@@ -367,6 +368,7 @@ def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb):
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorRq
     monkeypatch.setenv("LOLB_SPLIT_MB", str(mb))
+    monkeypatch.setenv("LOLB_SPLIT_MIX", str(mix))      # 1: both kinds of work in one grid per sub-batch, two ring slots, one stream
     monkeypatch.setenv("LOLB_DF_SCHEDULE", "split")
     monkeypatch.setenv("LOLB_POW2_MID_OFF", "1")
     m, qs = 2 ** e, CONFIG_B[1][:k]
