@@ -70,8 +70,11 @@ int fused_select(lolb_plan* pl)
   return rc;
 }
 
+namespace pow2 { void pow2_split_release(const lolb_plan* pl); }
+
 void fused_release(lolb_plan* pl)
 {
+  pow2::pow2_split_release(pl);      // CUDA graphs of the split power-of-two schedule are keyed by the plan
   FusedSet* s = set_of(pl);
   if (!s) return;
   fused_a_release(s->a);

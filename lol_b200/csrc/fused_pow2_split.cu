@@ -15,6 +15,8 @@
 // tail of B(i) with CTAs of A(i + 1), and each kernel gets its own register allocation (the column kernel needs half
 // the registers of the chunk kernel).
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "pow2_common.cuh"
 
@@ -223,6 +225,116 @@ k_pow2_mix(int64_t* __restrict__ yA, uint32_t* __restrict__ ringA, const int nA,
   }
 }
 
+// ---- graph-scheduled variant: the element base pointer comes from a device cell (the graph is built once per batch size and
+// replayed for any y), the sub-batch is an element offset
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
+k_pow2_chunk_g(int64_t* const* __restrict__ cell, const int64_t el0, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+{
+  __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
+  chunk_body<INV, K, TOP>(U, (int)blockIdx.x, *cell + (size_t)el0 * ((size_t)K * SpGeom<K, TOP>::N), P, ring, rev_n);
+}
+template <bool INV, int K, int TOP>
+__global__ void __launch_bounds__(kSpThreads, LOLB_SP_COL_MINB)
+k_pow2_col_g(int64_t* const* __restrict__ cell, const int64_t el0, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+{
+  col_body<INV, K, TOP>((int)blockIdx.x, *cell + (size_t)el0 * ((size_t)K * SpGeom<K, TOP>::N), P, ring, rev_n);
+}
+__global__ void k_set_cell(int64_t** cell, int64_t* y) { *cell = y; }
+
+// one instantiated CUDA graph per (plan, direction, batch, sub-batch, ring depth): nodes A(i) (first kind of sub-batch i) and
+// B(i) (second kind), edges A(i) -> B(i) and B(i) -> A(i + R) (ring slot reuse).  Nothing else orders the nodes, so up to R
+// first-kind kernels and their second-kind partners are in flight at once: no kernel waits on a stream neighbour, the
+// dependency latency of one pair hides behind the others, and the ring (R x sub-batch) stays in L2.
+struct SplitGraph {
+  const lolb_plan* plan;
+  cudaStream_t st;       // an executable graph (and its cell / ring) serves one stream: launches on it are ordered by the stream
+  int inv, k, top;
+  int64_t batch, S;
+  int R;
+  int device;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  uint32_t* ring = nullptr;
+  int64_t** cell = nullptr;
+};
+std::mutex g_graph_mu;
+std::vector<SplitGraph> g_graphs;
+
+template <bool INV, int K, int TOP>
+int build_split_graph(const lolb_plan* pl, const DfParams& P, int64_t batch, int64_t S, int R, SplitGraph* out)
+{
+  typedef SpGeom<K, TOP> Geo;
+  const size_t el_words = (size_t)K * Geo::N;
+  const int64_t nsub = (batch + S - 1) / S;
+  if (R > nsub) R = (int)nsub;
+  out->R = R;
+  LOLB_CUDA(cudaMalloc((void**)&out->ring, (size_t)R * S * el_words * sizeof(uint32_t)));
+  LOLB_CUDA(cudaMalloc((void**)&out->cell, sizeof(int64_t*)));
+  LOLB_CUDA(cudaGraphCreate(&out->graph, 0));
+  std::vector<cudaGraphNode_t> nodeA((size_t)nsub), nodeB((size_t)nsub);
+  DfParams Pc = P;
+  for (int64_t i = 0; i < nsub; i++) {
+    const int64_t cnt = batch - i * S < S ? batch - i * S : S;
+    int64_t el0 = i * S;
+    uint32_t* rs = out->ring + (size_t)(i % R) * S * el_words;
+    int zero = 0, rev = (int)cnt;
+    int64_t** cell = out->cell;
+    void* argsA[5] = {&cell, &el0, &Pc, &rs, &zero};
+    void* argsB[5] = {&cell, &el0, &Pc, &rs, &rev};
+    cudaKernelNodeParams kp{};
+    kp.blockDim = dim3(kSpThreads); kp.sharedMemBytes = 0; kp.extra = nullptr;
+    // A(i): depends on B(i - R)
+    kp.func = INV ? (void*)k_pow2_col_g<true, K, TOP> : (void*)k_pow2_chunk_g<false, K, TOP>;
+    kp.gridDim = dim3((unsigned)(cnt * (INV ? Geo::NT_COL : Geo::NT_CHUNK)));
+    kp.kernelParams = argsA;
+    cudaGraphNode_t depA[1];
+    size_t ndepA = 0;
+    if (i >= R) depA[ndepA++] = nodeB[(size_t)(i - R)];
+    LOLB_CUDA(cudaGraphAddKernelNode(&nodeA[(size_t)i], out->graph, depA, ndepA, &kp));
+    // B(i): depends on A(i)
+    kp.func = INV ? (void*)k_pow2_chunk_g<true, K, TOP> : (void*)k_pow2_col_g<false, K, TOP>;
+    kp.gridDim = dim3((unsigned)(cnt * (INV ? Geo::NT_CHUNK : Geo::NT_COL)));
+    kp.kernelParams = argsB;
+    cudaGraphNode_t depB[1] = {nodeA[(size_t)i]};
+    LOLB_CUDA(cudaGraphAddKernelNode(&nodeB[(size_t)i], out->graph, depB, 1, &kp));
+  }
+  LOLB_CUDA(cudaGraphInstantiate(&out->exec, out->graph, 0));
+  return LOLB_OK;
+}
+
+void free_split_graph(SplitGraph& g)
+{
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.graph) cudaGraphDestroy(g.graph);
+  if (g.ring) cudaFree(g.ring);
+  if (g.cell) cudaFree(g.cell);
+  g.exec = nullptr; g.graph = nullptr; g.ring = nullptr; g.cell = nullptr;
+}
+
+template <bool INV, int K, int TOP>
+int launch_split_graph(const lolb_plan* pl, const DfParams& P, int64_t* y, int64_t batch, int64_t S, int R, cudaStream_t st)
+{
+  std::lock_guard<std::mutex> lock(g_graph_mu);
+  SplitGraph* g = nullptr;
+  for (auto& e : g_graphs)
+    if (e.plan == pl && e.st == st && e.inv == (INV ? 1 : 0) && e.k == K && e.top == TOP && e.batch == batch && e.S == S && e.device == pl->device) { g = &e; break; }
+  if (!g) {
+    if (g_graphs.size() >= 16) { free_split_graph(g_graphs.front()); g_graphs.erase(g_graphs.begin()); }
+    SplitGraph ng{};
+    ng.plan = pl; ng.st = st; ng.inv = INV ? 1 : 0; ng.k = K; ng.top = TOP; ng.batch = batch; ng.S = S; ng.device = pl->device;
+    int rc = build_split_graph<INV, K, TOP>(pl, P, batch, S, R, &ng);
+    if (rc) { free_split_graph(ng); return rc; }
+    g_graphs.push_back(ng);
+    g = &g_graphs.back();
+  }
+  k_set_cell<<<1, 1, 0, st>>>(g->cell, y);
+  LOLB_CUDA(cudaGraphLaunch(g->exec, st));
+  const int64_t nsub = (batch + S - 1) / S;
+  count_launch((int)(2 * nsub + 1));
+  return LOLB_OK;
+}
+
 constexpr int kSpRing = 3;      // sub-batches of ring in flight: one being written, one being read, one of slack
 
 template <bool INV, int K, int TOP>
@@ -244,6 +356,8 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
     if (S < 1) S = 1;
     if (S > batch) S = batch;
     const int64_t nsub = (batch + S - 1) / S;
+    const char* gr_env = getenv("LOLB_SPLIT_GRAPH");      // R = ring depth in sub-batches; 0 / unset = off
+    if (gr_env && atoi(gr_env) > 0 && nsub >= 2) return launch_split_graph<INV, K, TOP>(pl, P, y, batch, S, atoi(gr_env), st);
     const char* mix_env = getenv("LOLB_SPLIT_MIX");
     if (mix_env && mix_env[0] == '1' && nsub >= 2) {
       uint32_t* ring2 = (uint32_t*)plan_ws(pl, st, (size_t)2 * S * el_words * sizeof(uint32_t));
@@ -294,6 +408,16 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
 }
 
 }  // namespace
+
+// drop the graphs of a plan that is being destroyed
+void pow2::pow2_split_release(const lolb_plan* pl)
+{
+  std::lock_guard<std::mutex> lock(g_graph_mu);
+  for (size_t i = 0; i < g_graphs.size();) {
+    if (g_graphs[i].plan == pl) { free_split_graph(g_graphs[i]); g_graphs.erase(g_graphs.begin() + (long)i); }
+    else i++;
+  }
+}
 
 // LOLB_FUSED_UNAVAILABLE when the shape is not served here (e < 14: the element-resident kernels win)
 int pow2::pow2_split_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)

@@ -131,6 +131,7 @@ int pow2_resident_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, i
 
 // fused_pow2_split.cu: m = 2^14 .. 2^16 as two streaming kernels per sub-batch on two streams (no CTA waits for another)
 int pow2_split_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+void pow2_split_release(const lolb_plan* pl);
 
 }  // namespace pow2
 }  // namespace lolb

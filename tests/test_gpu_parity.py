@@ -357,7 +357,7 @@ def test_batched_plain_rings_match_oracle(torch_cuda, oracle):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("mix", [0, 1], ids=["two-streams", "mixed-launches"])
+@pytest.mark.parametrize("mix", [0, 1, 2], ids=["two-streams", "mixed-launches", "graph"])
 @pytest.mark.parametrize("mb", [1, 16], ids=lambda v: f"sub-batch {v} MiB")
 @pytest.mark.parametrize("e,k", [(14, 1), (14, 2), (14, 4), (15, 1), (15, 2), (15, 4), (16, 1), (16, 2), (16, 4)], ids=lambda v: str(v))
 def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb, mix):
@@ -368,7 +368,8 @@ def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb, 
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorRq
     monkeypatch.setenv("LOLB_SPLIT_MB", str(mb))
-    monkeypatch.setenv("LOLB_SPLIT_MIX", str(mix))      # 1: both kinds of work in one grid per sub-batch, two ring slots, one stream
+    monkeypatch.setenv("LOLB_SPLIT_MIX", "1" if mix == 1 else "0")      # 1: both kinds of work in one grid per sub-batch, two ring slots, one stream
+    monkeypatch.setenv("LOLB_SPLIT_GRAPH", "4" if mix == 2 else "0")    # 2: one CUDA graph, ring of 4 sub-batches
     monkeypatch.setenv("LOLB_DF_SCHEDULE", "split")
     monkeypatch.setenv("LOLB_POW2_MID_OFF", "1")
     m, qs = 2 ** e, CONFIG_B[1][:k]
