@@ -229,16 +229,23 @@ k_pow2_mix(int64_t* __restrict__ yA, uint32_t* __restrict__ ringA, const int nA,
 // replayed for any y), the sub-batch is an element offset
 template <bool INV, int K, int TOP>
 __global__ void __launch_bounds__(kSpThreads, LOLB_SP_CHUNK_MINB)
-k_pow2_chunk_g(int64_t* const* __restrict__ cell, const int64_t el0, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+k_pow2_chunk_g(int64_t* const* __restrict__ cell, const int64_t el0, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n,
+               const int total)
 {
   __shared__ __align__(16) uint32_t U[kSpWarps * kDfUnit];
-  chunk_body<INV, K, TOP>(U, (int)blockIdx.x, *cell + (size_t)el0 * ((size_t)K * SpGeom<K, TOP>::N), P, ring, rev_n);
+  int64_t* y = *cell + (size_t)el0 * ((size_t)K * SpGeom<K, TOP>::N);
+  for (int bid = (int)blockIdx.x; bid < total; bid += (int)gridDim.x) {      // a throttled grid walks its tasks
+    chunk_body<INV, K, TOP>(U, bid, y, P, ring, rev_n);
+    __syncthreads();
+  }
 }
 template <bool INV, int K, int TOP>
 __global__ void __launch_bounds__(kSpThreads, LOLB_SP_COL_MINB)
-k_pow2_col_g(int64_t* const* __restrict__ cell, const int64_t el0, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n)
+k_pow2_col_g(int64_t* const* __restrict__ cell, const int64_t el0, const __grid_constant__ DfParams P, uint32_t* __restrict__ ring, const int rev_n,
+             const int total)
 {
-  col_body<INV, K, TOP>((int)blockIdx.x, *cell + (size_t)el0 * ((size_t)K * SpGeom<K, TOP>::N), P, ring, rev_n);
+  int64_t* y = *cell + (size_t)el0 * ((size_t)K * SpGeom<K, TOP>::N);
+  for (int bid = (int)blockIdx.x; bid < total; bid += (int)gridDim.x) col_body<INV, K, TOP>(bid, y, P, ring, rev_n);
 }
 __global__ void k_set_cell(int64_t** cell, int64_t* y) { *cell = y; }
 
@@ -272,6 +279,11 @@ int build_split_graph(const lolb_plan* pl, const DfParams& P, int64_t batch, int
   LOLB_CUDA(cudaMalloc((void**)&out->ring, (size_t)R * S * el_words * sizeof(uint32_t)));
   LOLB_CUDA(cudaMalloc((void**)&out->cell, sizeof(int64_t*)));
   LOLB_CUDA(cudaGraphCreate(&out->graph, 0));
+  int prio_lo = 0, prio_hi = 0, prio_b = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  { const char* pe = getenv("LOLB_SPLIT_PRIO"); if (pe && pe[0] == '1') prio_b = prio_hi; }      // measured: no effect
+  int agrid = 0, bgrid = 0;      // tuning: cap the grid of one kernel kind (CTAs), 0 = one CTA per task
+  { const char* ge = getenv("LOLB_SPLIT_AGRID"); if (ge) agrid = atoi(ge); ge = getenv("LOLB_SPLIT_BGRID"); if (ge) bgrid = atoi(ge); }
   std::vector<cudaGraphNode_t> nodeA((size_t)nsub), nodeB((size_t)nsub);
   DfParams Pc = P;
   for (int64_t i = 0; i < nsub; i++) {
@@ -280,13 +292,14 @@ int build_split_graph(const lolb_plan* pl, const DfParams& P, int64_t batch, int
     uint32_t* rs = out->ring + (size_t)(i % R) * S * el_words;
     int zero = 0, rev = (int)cnt;
     int64_t** cell = out->cell;
-    void* argsA[5] = {&cell, &el0, &Pc, &rs, &zero};
-    void* argsB[5] = {&cell, &el0, &Pc, &rs, &rev};
+    int totA = (int)(cnt * (INV ? Geo::NT_COL : Geo::NT_CHUNK)), totB = (int)(cnt * (INV ? Geo::NT_CHUNK : Geo::NT_COL));
+    void* argsA[6] = {&cell, &el0, &Pc, &rs, &zero, &totA};
+    void* argsB[6] = {&cell, &el0, &Pc, &rs, &rev, &totB};
     cudaKernelNodeParams kp{};
     kp.blockDim = dim3(kSpThreads); kp.sharedMemBytes = 0; kp.extra = nullptr;
     // A(i): depends on B(i - R)
     kp.func = INV ? (void*)k_pow2_col_g<true, K, TOP> : (void*)k_pow2_chunk_g<false, K, TOP>;
-    kp.gridDim = dim3((unsigned)(cnt * (INV ? Geo::NT_COL : Geo::NT_CHUNK)));
+    kp.gridDim = dim3((unsigned)(agrid > 0 && agrid < totA ? agrid : totA));
     kp.kernelParams = argsA;
     cudaGraphNode_t depA[1];
     size_t ndepA = 0;
@@ -294,10 +307,15 @@ int build_split_graph(const lolb_plan* pl, const DfParams& P, int64_t batch, int
     LOLB_CUDA(cudaGraphAddKernelNode(&nodeA[(size_t)i], out->graph, depA, ndepA, &kp));
     // B(i): depends on A(i)
     kp.func = INV ? (void*)k_pow2_chunk_g<true, K, TOP> : (void*)k_pow2_col_g<false, K, TOP>;
-    kp.gridDim = dim3((unsigned)(cnt * (INV ? Geo::NT_CHUNK : Geo::NT_COL)));
+    kp.gridDim = dim3((unsigned)(bgrid > 0 && bgrid < totB ? bgrid : totB));
     kp.kernelParams = argsB;
     cudaGraphNode_t depB[1] = {nodeA[(size_t)i]};
     LOLB_CUDA(cudaGraphAddKernelNode(&nodeB[(size_t)i], out->graph, depB, 1, &kp));
+    if (prio_b != 0) {      // the finishing kernels first: they free ring slots, and their CTAs are not crowded out by ready first-kind work
+      cudaKernelNodeAttrValue v{};
+      v.priority = prio_b;
+      LOLB_CUDA(cudaGraphKernelNodeSetAttribute(nodeB[(size_t)i], cudaKernelNodeAttributePriority, &v));
+    }
   }
   LOLB_CUDA(cudaGraphInstantiate(&out->exec, out->graph, 0));
   return LOLB_OK;
@@ -351,13 +369,24 @@ int launch_split(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t 
     // sub-batch is as large as a 512 MiB workspace allows and the intermediate mostly travels through HBM (ncu: both kernels
     // run at 78-82 % of the measured HBM peak on 1.5x the algorithmic traffic).
     const char* mb_env = getenv("LOLB_SPLIT_MB");      // tuning / test override of the sub-batch size
-    const int64_t mb = mb_env && atoi(mb_env) > 0 ? atoi(mb_env) : 512;
-    int64_t S = (mb << 20) / (int64_t)(el_words * sizeof(uint32_t));
-    if (S < 1) S = 1;
-    if (S > batch) S = batch;
+    const char* gr_env = getenv("LOLB_SPLIT_GRAPH");   // ring depth of the graph schedule; "0" = off; unset = the measured policy
+    // Graph schedule (launch_split_graph): measured at config B, % of HBM roofline CRT / CRT^-1: 2 MiB x 16 slots 61.5 / 52.7,
+    // 8 MiB x 6 59.9 / 53.2, 16 MiB x 3 59.8 / 53.6 -- against 56.4 / 57.8 for one 512 MiB sub-batch.  The forward transform
+    // (compute-heavy producer, light consumer) gains 5 points from the L2-resident ring; the inverse (light producer,
+    // compute-heavy consumer) loses 4, with or without node priorities or throttled grids.  tupSize 1: 67.9 / 59.7 against
+    // 65.6 / 60.5.  So: forward transforms at e = 16 take the graph, everything else one large sub-batch.
+    auto sub_batch = [&](int64_t mib) {
+      int64_t v = (mib << 20) / (int64_t)(el_words * sizeof(uint32_t));
+      if (v < 1) v = 1;
+      return v > batch ? batch : v;
+    };
+    const int graph_r = gr_env ? atoi(gr_env) : ((!INV && TOP == 5 && !mb_env) ? 16 : 0);
+    if (graph_r > 0) {
+      const int64_t Sg = sub_batch(mb_env && atoi(mb_env) > 0 ? atoi(mb_env) : 2);
+      if ((batch + Sg - 1) / Sg >= 2) return launch_split_graph<INV, K, TOP>(pl, P, y, batch, Sg, graph_r, st);
+    }
+    const int64_t S = sub_batch(mb_env && atoi(mb_env) > 0 ? atoi(mb_env) : 512);
     const int64_t nsub = (batch + S - 1) / S;
-    const char* gr_env = getenv("LOLB_SPLIT_GRAPH");      // R = ring depth in sub-batches; 0 / unset = off
-    if (gr_env && atoi(gr_env) > 0 && nsub >= 2) return launch_split_graph<INV, K, TOP>(pl, P, y, batch, S, atoi(gr_env), st);
     const char* mix_env = getenv("LOLB_SPLIT_MIX");
     if (mix_env && mix_env[0] == '1' && nsub >= 2) {
       uint32_t* ring2 = (uint32_t*)plan_ws(pl, st, (size_t)2 * S * el_words * sizeof(uint32_t));
