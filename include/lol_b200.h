@@ -334,6 +334,16 @@ int lolb_rq_apply_host(const lolb_plan* plan, const char* ops, hInt_t* y, int64_
  * An empty `ops` runs the copies alone: the pipeline's ceiling on this host.
  */
 int lolb_rq_apply_host_u32(const lolb_plan* plan, const char* ops, uint32_t* y, int64_t batch);
+/*
+ * Device memory for callers without a CUDA binding of their own (haskell/.../Tensor/CUDA.hs keeps a ring element in GPU
+ * memory behind a ForeignPtr whose finalizer is lolb_dev_free, so the `Tensor` methods chain without crossing PCIe):
+ * cudaMalloc / cudaFree / cudaMemcpyAsync on the current device.  lolb_dev_download returns when the bytes are in dst.
+ */
+void* lolb_dev_alloc(uint64_t bytes);
+void lolb_dev_free(void* p);
+int lolb_dev_upload(void* dst_dev, const void* src_host, uint64_t bytes, void* stream);
+int lolb_dev_download(void* dst_host, const void* src_dev, uint64_t bytes, void* stream);
+int lolb_dev_copy(void* dst_dev, const void* src_dev, uint64_t bytes, void* stream);
 /* pinned host memory for the above (cudaHostAlloc / cudaFreeHost) */
 void* lolb_host_alloc(uint64_t bytes);
 void lolb_host_free(void* p);

@@ -503,6 +503,35 @@ extern "C" int lolb_tensorNormSqD(const lolb_plan* plan, const double* y, double
 
 // ------------------------------------------------------------------ host-batched pipeline
 
+// Device memory for callers without a CUDA binding of their own (the Haskell instance keeps ring elements in GPU memory behind a
+// ForeignPtr whose finalizer is lolb_dev_free).  Plain cudaMalloc / cudaFree / cudaMemcpy on the current device.
+extern "C" void* lolb_dev_alloc(uint64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); return nullptr; }
+  return p;
+}
+extern "C" void lolb_dev_free(void* p) { if (p) cudaFree(p); }
+extern "C" int lolb_dev_upload(void* dst_dev, const void* src_host, uint64_t bytes, void* stream)
+{
+  if (bytes && (!dst_dev || !src_host)) { set_error("lolb_dev_upload: NULL pointer"); return LOLB_ERR_ARG; }
+  LOLB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return LOLB_OK;
+}
+extern "C" int lolb_dev_download(void* dst_host, const void* src_dev, uint64_t bytes, void* stream)
+{
+  if (bytes && (!dst_host || !src_dev)) { set_error("lolb_dev_download: NULL pointer"); return LOLB_ERR_ARG; }
+  LOLB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LOLB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));      // the host reads the result next
+  return LOLB_OK;
+}
+extern "C" int lolb_dev_copy(void* dst_dev, const void* src_dev, uint64_t bytes, void* stream)
+{
+  if (bytes && (!dst_dev || !src_dev)) { set_error("lolb_dev_copy: NULL pointer"); return LOLB_ERR_ARG; }
+  LOLB_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return LOLB_OK;
+}
+
 extern "C" void* lolb_host_alloc(uint64_t bytes)
 {
   void* p = nullptr;
