@@ -249,6 +249,32 @@ RING_RQ, RING_R, RING_DOUBLE, RING_C = 0, 1, 2, 3
 EXT_INDICES_POWDEC, EXT_INDICES_CRT, EXT_BASE_POW_J0, EXT_BASE_POW_J1, EXT_BASE_DEC, EXT_INDICES_COEFFS = range(6)
 
 
+def dev_alloc(nbytes: int) -> int:
+    lib().lolb_dev_alloc.restype = _p
+    lib().lolb_dev_alloc.argtypes = [C.c_uint64]
+    p = lib().lolb_dev_alloc(nbytes)
+    if not p:
+        raise LolB200Error(LOLB_ERR_CUDA, last_error())
+    return int(p)
+
+
+def dev_free(ptr: int) -> None:
+    lib().lolb_dev_free.argtypes = [_p]
+    lib().lolb_dev_free(_p(ptr))
+
+
+def dev_upload(dst: int, src: np.ndarray) -> None:
+    check(lib().lolb_dev_upload(_p(dst), src.ctypes.data_as(_p), C.c_uint64(src.nbytes), _p(0)))
+
+
+def dev_download(dst: np.ndarray, src: int) -> None:
+    check(lib().lolb_dev_download(dst.ctypes.data_as(_p), _p(src), C.c_uint64(dst.nbytes), _p(0)))
+
+
+def dev_copy(dst: int, src: int, nbytes: int) -> None:
+    check(lib().lolb_dev_copy(_p(dst), _p(src), C.c_uint64(nbytes), _p(0)))
+
+
 def real_gaussians(svar: float, seed: int, first: int, ptr: int, n: int, batch: int, stream: int = 0) -> int:
     """lolb_realGaussians: [batch][n] doubles on the device, i.i.d. N(0, svar / (2 pi))."""
     return int(lib().lolb_realGaussians(C.c_double(svar), C.c_uint64(seed), C.c_uint64(first), _p(ptr), _i64(n), _i64(batch), _p(stream)))

@@ -66,11 +66,8 @@ __device__ __forceinline__ void unit_rounds_0_4_any(int limb, uint32_t* Uu, cons
 #ifndef LOLB_DF_NW
 #define LOLB_DF_NW 4            // warps per CTA = (chunk, limb) units per chunk task
 #endif
-#ifndef LOLB_DF_STAGE
-#define LOLB_DF_STAGE 0           // 1: first-kind tasks read their HBM input through a TMA-filled staging buffer (measured slower: 4 CTAs/SM instead of 5, copy only one 1.5 us task ahead)
-#endif
 #ifndef LOLB_DF_MINB
-#define LOLB_DF_MINB ((LOLB_DF_STAGE ? 512 : 640) / (32 * LOLB_DF_NW))   // CTAs per SM the register allocation must allow
+#define LOLB_DF_MINB (640 / (32 * LOLB_DF_NW))   // CTAs per SM the register allocation must allow
 #endif
 #ifndef LOLB_DF_SWITCH
 #define LOLB_DF_SWITCH 0        // 1: rounds 0-4 specialised per limb (twiddles as constant-bank operands); 0: one copy, LDC
@@ -85,31 +82,8 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
   return v;
 }
 
-// ---- mbarrier + bulk-copy (TMA, 1-D) primitives: the HBM input of a task is copied into a staging buffer by the
-// copy engine one task ahead, so no thread waits on HBM latency
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra WAIT_%=;\n\t}"
-      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
+// (A TMA-staged variant -- cp.async.bulk + mbarrier filling a staging buffer one task ahead -- was measured slower, 46 % / 48 %
+// against 56 % / 54 %: 4 CTAs/SM instead of 5 and the copy runs only one 1.5 us task ahead; removed in round 2)
 
 // exchange-ring accesses: L2 only (the reader is another SM), optionally tagged evict_last so the ring stays in L2
 // while the streamed element data (ld.cs / st.cs) passes through
@@ -172,8 +146,7 @@ struct DfGeom {
   static constexpr int STEP = (2 * kDfThreads) / K;    // coefficients between consecutive pieces of a thread
   static constexpr int CHUNK_BYTES = kDfWarps * 1024 * 8;
   static constexpr int COL_BYTES = NV * kDfThreads * 8;
-  static constexpr int STAGE_BYTES = LOLB_DF_STAGE ? (CHUNK_BYTES > COL_BYTES ? CHUNK_BYTES : COL_BYTES) : 0;
-  static constexpr int SMEM_BYTES = STAGE_BYTES + kDfWarps * kDfUnit * 4 + 64;
+  static constexpr int SMEM_BYTES = kDfWarps * kDfUnit * 4 + 64;
   // shared-memory word of piece ii of a thread, relative to  U + l0 * kDfUnit + c0 + (c0 >> 5),  c0 = 2 tid / K
   static __host__ __device__ constexpr int piece_off(int ii)
   {
@@ -191,15 +164,12 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
   constexpr int N = Geo::N, G = Geo::G, NV = Geo::NV, PIECES = Geo::PIECES;
   constexpr int NT_A = INV ? Geo::NT_COL : Geo::NT_CHUNK;     // first kind (reads the element from HBM)
   constexpr int NT_B = INV ? Geo::NT_CHUNK : Geo::NT_COL;     // second kind (writes the element to HBM)
-  constexpr bool STAGE = LOLB_DF_STAGE != 0;
   static_assert(G >= 1 && Geo::NCH % G == 0, "chunk tasks must tile the element");
   static_assert(Geo::STEP % 32 == 0 && 1024 % Geo::STEP == 0, "piece addressing");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* stage = smem_raw;                                       // HBM input of the current first-kind task
-  uint32_t* U = reinterpret_cast<uint32_t*>(smem_raw + Geo::STAGE_BYTES);   // kDfWarps units of u32 residues
+  uint32_t* U = reinterpret_cast<uint32_t*>(smem_raw);                    // kDfWarps units of u32 residues
   unsigned* mail = U + kDfWarps * kDfUnit;                               // [2][4]: task, ready, element, ring slot
-  uint64_t* bar = reinterpret_cast<uint64_t*>(mail + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t pol = ring_policy();
@@ -218,25 +188,6 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
   };
   auto dep_target = [&](const Tid& id) -> unsigned { return id.first ? NT_B : NT_A; };
 
-  // warp 0: start the copy of task tn's HBM input into `stage` (first-kind tasks only; their input is never
-  // written before all of them are done, so it can be fetched before the task's own dependency is met)
-  auto stage_issue = [&](unsigned tn) {
-    if (!STAGE || tn >= total) return;
-    const Tid idn(tn, batch, P.lag);
-    if (!idn.valid || !idn.first) return;
-    const int64_t* eb = y + (size_t)idn.el * ((size_t)K * N);
-    if (!INV) {
-      if (lane == 0) {
-        mbar_expect_tx(bar, Geo::CHUNK_BYTES);
-        bulk_g2s(stage, eb + (size_t)(idn.task * G) * 1024 * K, Geo::CHUNK_BYTES, bar);
-      }
-    } else {
-      if (lane == 0) mbar_expect_tx(bar, Geo::COL_BYTES);
-      __syncwarp();
-      if (lane < NV) bulk_g2s(stage + lane * (kDfThreads * 8), eb + (size_t)idn.task * kDfThreads + (size_t)1024 * K * lane, kDfThreads * 8, bar);
-    }
-  };
-
   // Thread 0 runs two tasks ahead: the atomic that hands out task i+2, the counter read for task i+1 and the copy
   // of task i+1's input are in flight while task i is computed.  One CTA barrier per task hands over the decoded
   // task through a double-buffered mailbox; the completion signal of task i (fence + atomic) is issued by thread 0
@@ -245,16 +196,13 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
   // holding back its own completion) and then spins.
   unsigned t_next = 0;
   unsigned* pending = nullptr;                  // thread 0: completion counter of the task that just ended
-  unsigned stage_phase = 0;
   if (tid == 0) {
     const unsigned t0 = atomicAdd(ctr, 1u);
     t_next = atomicAdd(ctr, 1u);
     const Tid id0(t0, batch, P.lag);
     mail[0] = t0; mail[1] = 0u; mail[2] = (unsigned)id0.el; mail[3] = id0.valid ? (unsigned)id0.el % (unsigned)P.ring : 0u;
-    if (STAGE) mbar_init(bar, 1);
   }
   __syncthreads();
-  if (warp == 0) stage_issue(__shfl_sync(0xffffffffu, mail[0], 0));
 
   for (int it = 0;; it++) {
     const unsigned* mc = mail + 4 * (it & 1);
@@ -286,9 +234,6 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
         if (dp) { dep_next = ld_acquire(dp); dep_need = dep_target(idn); }
       }
     }
-    const bool staged = STAGE && id.valid && id.first;
-    // the staging buffer is idle during a second-kind task: fetch the next task's input right away
-    if (!staged && warp == 0) stage_issue(__shfl_sync(0xffffffffu, t_next, 0));
 
     if (id.valid) {
     const int el = id.el;
@@ -315,13 +260,12 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
       constexpr int second = K == 1 ? 1 : kDfUnit;                      // the other half: next coefficient / next limb
       if (!INV) {
         const uint32_t q0 = P.limb[l0].q, q1 = P.limb[K == 1 ? 0 : l0 + 1].q;
-        const longlong2* src = STAGE ? reinterpret_cast<const longlong2*>(stage) + tid : reinterpret_cast<const longlong2*>(gpiece) + tid;
-        if (STAGE) { mbar_wait(bar, stage_phase); stage_phase ^= 1u; }
+        const longlong2* src = reinterpret_cast<const longlong2*>(gpiece) + tid;
         // coalesced read of the piece (all 16-byte loads in flight at once), limbs de-interleaved into the units
         {
           longlong2 raw[PIECES];
 #pragma unroll
-          for (int ii = 0; ii < PIECES; ii++) raw[ii] = STAGE ? src[kDfThreads * ii] : __ldcs(src + kDfThreads * ii);
+          for (int ii = 0; ii < PIECES; ii++) raw[ii] = __ldcs(src + kDfThreads * ii);
           uint32_t hi_or = 0, max0 = 0, max1 = 0;
 #pragma unroll
           for (int ii = 0; ii < PIECES; ii++) {
@@ -343,7 +287,6 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
           }
         }
         __syncthreads();
-        if (STAGE && warp == 0) stage_issue(__shfl_sync(0xffffffffu, t_next, 0));      // staging buffer is free again
 #if LOLB_DF_SWITCH
         unit_rounds_0_4_any<false>(limb, Uu, P, lane);
 #else
@@ -401,23 +344,17 @@ k_pow2_df(int64_t* __restrict__ y, int batch, const __grid_constant__ DfParams P
 #pragma unroll
         for (int j = 0; j < NV; j++) __stcs(gcol + (size_t)1024 * K * j, (int64_t)M.canon(M.fold(v[j])));
       } else {
-        const int64_t* srcw = reinterpret_cast<const int64_t*>(stage) + tid;
-        if (STAGE) { mbar_wait(bar, stage_phase); stage_phase ^= 1u; }
         uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-          const int64_t raw = STAGE ? srcw[kDfThreads * j] : __ldcs(gcol + (size_t)1024 * K * j);
+          const int64_t raw = __ldcs(gcol + (size_t)1024 * K * j);
           v[j] = (uint32_t)raw;
           hi_or |= (uint32_t)((uint64_t)raw >> 32);
           lo_max = max(lo_max, v[j]);
         }
         if (hi_or != 0 || lo_max >= L.q) {      // outside the Haskell contract: reduce like the reference's c % q
 #pragma unroll
-          for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(STAGE ? srcw[kDfThreads * j] : gcol[(size_t)1024 * K * j], L.q);
-        }
-        if (STAGE) {
-          __syncthreads();
-          if (warp == 0) stage_issue(__shfl_sync(0xffffffffu, t_next, 0));             // staging buffer is free again
+          for (int j = 0; j < NV; j++) v[j] = df_reduce_any64(gcol[(size_t)1024 * K * j], L.q);
         }
         gs_rounds<TOP, 0>(v, M, [&](int a, int jj) { return __ldg(twb + ((1024 << a) - 1 + 1024 * jj)); });
 #pragma unroll

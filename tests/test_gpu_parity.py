@@ -712,3 +712,29 @@ def test_symmshe_full_size_identity_hint(torch_cuda, base):
         hint[i, 0] = she.t.scalarCRT(gi, batch=1)[0]
     o = she.keySwitchQuadCirc(hint, d)
     assert torch.equal(o[0], (d[0] + d[2]) % q) and torch.equal(o[1], d[1])
+
+
+def test_device_memory_entry_points_without_torch(torch_cuda, oracle):
+    """lolb_dev_alloc / upload / copy / download (what the Haskell GT type is built on): a ring element goes to the device, is
+    transformed there twice without crossing PCIe, comes back, and equals the oracle's crtInv(mulG(crt x)) composition."""
+    from lol_b200 import capi
+    m, qs = 14400, [14401]
+    rng = np.random.default_rng(8)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    plan = capi.PlanRq(T.factor_pps(m), qs)
+    y = zq_input(rng, n, qs)
+    a, b = capi.dev_alloc(y.nbytes), capi.dev_alloc(y.nbytes)
+    try:
+        capi.dev_upload(a, y)
+        capi.dev_copy(b, a, y.nbytes)
+        capi.check(plan.op("CRT", b, 1, 0))
+        capi.check(plan.op("CRTInv", b, 1, 0))
+        capi.check(plan.op("CRT", a, 1, 0))
+        back, f = np.empty_like(y), np.empty_like(y)
+        capi.dev_download(back, b)
+        capi.dev_download(f, a)
+    finally:
+        capi.dev_free(a)
+        capi.dev_free(b)
+    assert np.array_equal(back, y)
+    assert np.array_equal(f, oracle.tensorCRTRq(y, pe, ru, qs))
