@@ -466,6 +466,7 @@ def run_gpu_arm(args):
         rq_config("F64*F81/10369", 5184, [10369], 81920)
         rq_config("F32*F7*F13/8737", 2912, [8737], 122880)
         rq_config("F8*F5*F7*F13/14561", 3640, [14561], 122880)
+        rq_config("F128*F7*F13/23297", 11648, [23297], 30720)
         from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
         Bg = 32768
         tr, ti, tcx = CudaTensorReal(M), CudaTensorInt(M), CudaTensorComplex(M)
@@ -609,6 +610,7 @@ def run_gpu_arm(args):
                "m5184": [fr("F64*F81/10369", "CRT"), fr("F64*F81/10369", "CRTInv")],
                "m2912": [fr("F32*F7*F13/8737", "CRT"), fr("F32*F7*F13/8737", "CRTInv")],
                "m3640": [fr("F8*F5*F7*F13/14561", "CRT"), fr("F8*F5*F7*F13/14561", "CRTInv")],
+               "m11648": [fr("F128*F7*F13/23297", "CRT"), fr("F128*F7*F13/23297", "CRTInv")],
                "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec")}
     for s, n, ms, _, units, _ in rec.rows:
         if s == "she" and n == "mulAndSwitch":

@@ -1,6 +1,6 @@
 // fused_w.cu -- fused Z_q CRT / CRT^-1 for indices m = 2^a * (one to three odd prime powers): the reference's other
 // benchmark rings (lol/Crypto/Lol/Benchmarks/Default.hs:41-48: F64*F27, F64*F81 and the Twace-Embed rings
-// F32*F7*F13, F8*F7*F13, F8*F5*F7*F13), one HBM read and one HBM write per ring element like fused_a.cu does for m = 14400.
+// F32*F7*F13, F8*F7*F13, F8*F5*F7*F13; lol-apps tunnel ring F64*F7*F13), one HBM read and one HBM write per ring element like fused_a.cu does for m = 14400.
 //
 // The operator is the reference's (crt.cpp:518-581 on tensor.h:76-95): CRT_m = (x)_i CRT_{p_i^e_i}, first factor fastest,
 // CRT_{p^e} = (DFT_{p^(e-1)} (x) I_{p-1}) . That . (I_{p^(e-1)} (x) CRT_p), DFT_{p^(e-1)} as e-1 radix-p rounds with diagonal
@@ -209,7 +209,10 @@ struct WShape {
   typedef PA_ PA;
   typedef PB_ PB;
   typedef PC_ PC;
-  static constexpr int A = A_, LOG = A_ >= 2 ? A_ - 1 : 0, L = 1 << LOG, GPW = 32 / L;
+  static constexpr int A = A_, LOG = A_ >= 2 ? A_ - 1 : 0, L = 1 << LOG;
+  // the 2^a axis spans LL lane bits; beyond 32 columns (a = 7) a lane holds H = 2 column halves (col, col + 32) of every row
+  static constexpr int LL = LOG > 5 ? 5 : LOG, LW = 1 << LL, H = L / LW, GPW = 32 / LW;
+  static_assert(LOG <= 6, "2^a axis: a <= 7");
   static constexpr int DA = PA::phi, DB = PB::phi, D2 = DA * DB, NP = D2 / 2;
   static constexpr int COLS = L * D2, ROWS = PC::phi, N = COLS * ROWS;
   static constexpr int OFF_A = 0, OFF_B = PA::n_consts, OFF_C = PA::n_consts + PB::n_consts;
@@ -218,16 +221,17 @@ struct WShape {
   static constexpr bool TWO_PHASE = PC::p > 1;
   // tile row stride: rows handled by the sub-warp groups of one warp must start in different banks
   static constexpr int RS = (L >= 32 || COLS % 32 == L % 32) ? COLS : COLS + ((L + 32 - COLS % 32) % 32);
+  static_assert(H == 1 || TWO_PHASE, "a = 7 is served by the two-phase kernel only");
   static_assert(D2 % 2 == 0, "an odd prime power is required next to the 2^a axis");
 };
 
-constexpr int kWLaneRows = 8;      // per-lane constants of the network (see build_lane_table)
+constexpr int kWLaneRows = 10;     // per-lane constants of the network, per column half (see build_lane_table)
 constexpr int kWThreads = 128;
 
 template <int NC>
 struct WConsts {
   WMod mod;
-  const uint32_t* lane_tw;      // device [kWLaneRows][32]
+  const uint32_t* lane_tw;      // device [2 halves][kWLaneRows][32]
   uint32_t c[NC];
 };
 
@@ -280,35 +284,49 @@ __device__ __forceinline__ void w_last_inv(uint32_t (&v)[2 * NP], const int l, c
   }
 }
 
-// lane-table rows: forward [0] crtTwiddle of the lane's column, [1 + r] round r (r < LOG-1; the sign of hi lanes folded in);
-// inverse [r] round r (1 <= r < LOG-1), [4] a, [5] a tw_0, [6] b, [7] -b tw_0
-template <int LOG, bool INV, int NP, class AR>
+// lane-table rows (per column half): forward [0] crtTwiddle of the lane's column, [1 + r] round r (the sign of hi lanes folded
+// in); inverse [r] round r (r >= 1), [6] a, [7] a tw_0, [8] b, [9] -b tw_0.  LL = lane bits of the axis; TOP_IN_LANES: the
+// highest column bit is a lane bit (a <= 6), so its round carries no twiddle (crt.cpp:92-106 skips i0 = 0).
+template <int LL, bool TOP_IN_LANES, bool INV, int NP, class AR>
 __device__ __forceinline__ void w_network(uint32_t (&v)[2 * NP], const int l, const uint32_t (&lt)[kWLaneRows], const AR& A)
 {
-  if constexpr (LOG >= 1) {
+  if constexpr (LL >= 1) {
+    constexpr int NT = TOP_IN_LANES ? LL - 1 : LL;      // rounds with twiddles
     if constexpr (!INV) {
 #pragma unroll
       for (int i = 0; i < 2 * NP; i++) v[i] = A.red(A.mul(lt[0], v[i]));      // crtTwiddle (crt.cpp:43-58)
 #pragma unroll
-      for (int r = 0; r < LOG - 1; r++) w_round<false, false, NP>(v, l, r, lt[1 + r], A);
-      w_round<false, true, NP>(v, l, LOG - 1, 0u, A);
+      for (int r = 0; r < NT; r++) w_round<false, false, NP>(v, l, r, lt[1 + r], A);
+      if constexpr (TOP_IN_LANES) w_round<false, true, NP>(v, l, LL - 1, 0u, A);
     } else {
-      if constexpr (LOG >= 2) w_round<true, true, NP>(v, l, LOG - 1, 0u, A);
+      if constexpr (TOP_IN_LANES && LL >= 2) w_round<true, true, NP>(v, l, LL - 1, 0u, A);
 #pragma unroll
-      for (int r = LOG - 2; r >= 1; r--) w_round<true, false, NP>(v, l, r, lt[r], A);
-      w_last_inv<NP>(v, l, lt[4], lt[5], lt[6], lt[7], A);
+      for (int r = NT - 1; r >= 1; r--) w_round<true, false, NP>(v, l, r, lt[r], A);
+      w_last_inv<NP>(v, l, lt[6], lt[7], lt[8], lt[9], A);
     }
   }
 }
 
-// position inside a block of D2 * L coefficients of value (pair j, slot s) after the network
-template <int LOG, bool INV>
-__device__ __forceinline__ int w_out_pos(const int l, const int j, const int s)
+// the round on the column bit above the lanes (a = 7): both inputs sit in the same thread, the twiddle is 1
+template <int N2, class AR>
+__device__ __forceinline__ void w_top_round(uint32_t (&v0)[N2], uint32_t (&v1)[N2], const AR& A)
 {
-  constexpr int L = 1 << LOG;
-  if constexpr (LOG == 0) return 2 * j + s;
-  else if constexpr (!INV) return (2 * j + (l & 1)) * L + ((s << (LOG - 1)) | (l >> 1));
-  else return (2 * j + (l >> (LOG - 1))) * L + 2 * (l & (L / 2 - 1)) + s;
+#pragma unroll
+  for (int i = 0; i < N2; i++) {
+    const uint32_t u = v0[i], t = v1[i];
+    v0[i] = A.fold(u + t);
+    v1[i] = A.fold(u + A.q2 - t);
+  }
+}
+
+// position inside a block of D2 * L coefficients of value (pair j, slot s, column half h) after the network
+template <int LL, int L, bool INV>
+__device__ __forceinline__ int w_out_pos(const int l, const int j, const int s, const int h)
+{
+  constexpr int LW = 1 << LL;
+  if constexpr (LL == 0) return 2 * j + s;
+  else if constexpr (!INV) return (2 * j + (l & 1)) * L + ((s << (LL - 1)) | (l >> 1)) + LW * h;
+  else return (2 * j + (l >> (LL - 1))) * L + 2 * (l & (LW / 2 - 1)) + s + LW * h;
 }
 
 __device__ __noinline__ uint32_t w_reduce_any(int64_t x, uint32_t q)      // non-canonical input, like `c % q` (types.h:62-66)
@@ -317,26 +335,36 @@ __device__ __noinline__ uint32_t w_reduce_any(int64_t x, uint32_t q)      // non
   return (uint32_t)(r < 0 ? r + q : r);
 }
 
-// middle line(s) + network + store of one group's block of D2 * L coefficients
+// middle line(s) + network + store of one group's block of D2 * L coefficients; v[h] = the lane's values of column half h
 template <class SH, bool INV, class AR, int K>
-__device__ __forceinline__ void w_finish(uint32_t (&v)[SH::D2], const int l, const uint32_t (&lt)[kWLaneRows], const WConsts<SH::NC>& C,
-                                         const AR& A, int64_t* __restrict__ dst /* block base (+ limb) */, const int k, const bool live)
+__device__ __forceinline__ void w_finish(uint32_t (&v)[SH::H][SH::D2], const int l, const uint32_t (&lt)[SH::H][kWLaneRows],
+                                         const WConsts<SH::NC>& C, const AR& A, int64_t* __restrict__ dst /* block base (+ limb) */,
+                                         const int k, const bool live)
 {
-  // axis a: stride 1, one line per ib;  axis b: stride DA, one line per ia
 #pragma unroll
-  for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v, ib * SH::DA, C, A);
+  for (int h = 0; h < SH::H; h++) {
+    // axis a: stride 1, one line per ib;  axis b: stride DA, one line per ia
 #pragma unroll
-  for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v, ia, C, A);
-  w_network<SH::LOG, INV, SH::NP>(v, l, lt, A);
+    for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v[h], ib * SH::DA, C, A);
+#pragma unroll
+    for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v[h], ia, C, A);
+  }
+  if constexpr (SH::H == 2 && INV) w_top_round<SH::D2>(v[0], v[1], A);
+#pragma unroll
+  for (int h = 0; h < SH::H; h++) w_network<SH::LL, SH::H == 1, INV, SH::NP>(v[h], l, lt[h], A);
+  if constexpr (SH::H == 2 && !INV) w_top_round<SH::D2>(v[0], v[1], A);
   if (live) {
 #pragma unroll
-    for (int j = 0; j < SH::NP; j++) {
-      const int64_t a = (int64_t)A.canon(v[2 * j]), b = (int64_t)A.canon(v[2 * j + 1]);
-      if (INV && K == 1 && SH::LOG >= 1) {
-        __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LOG, INV>(l, j, 0)), make_longlong2(a, b));
-      } else {
-        __stcs(dst + (size_t)w_out_pos<SH::LOG, INV>(l, j, 0) * k, a);
-        __stcs(dst + (size_t)w_out_pos<SH::LOG, INV>(l, j, 1) * k, b);
+    for (int h = 0; h < SH::H; h++) {
+#pragma unroll
+      for (int j = 0; j < SH::NP; j++) {
+        const int64_t a = (int64_t)A.canon(v[h][2 * j]), b = (int64_t)A.canon(v[h][2 * j + 1]);
+        if (INV && K == 1 && SH::LL >= 1) {
+          __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h)), make_longlong2(a, b));
+        } else {
+          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, a);
+          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, b);
+        }
       }
     }
   }
@@ -350,28 +378,28 @@ k_fused_w1(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
   const int k = K ? K : k_rt;
   const AR A(C.mod);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l = lane & (SH::L - 1), sub = lane >> SH::LOG;
-  uint32_t lt[kWLaneRows];
+  const int l = lane & (SH::LW - 1), sub = lane >> SH::LL;
+  uint32_t lt[1][kWLaneRows];
 #pragma unroll
-  for (int i = 0; i < kWLaneRows; i++) lt[i] = C.lane_tw[i * 32 + lane];
+  for (int i = 0; i < kWLaneRows; i++) lt[0][i] = C.lane_tw[i * 32 + lane];
   const int64_t nwt = (batch + SH::GPW - 1) / SH::GPW;      // warp-tasks: GPW elements each
   for (int64_t wt = (int64_t)blockIdx.x * (kWThreads / 32) + warp; wt < nwt; wt += (int64_t)gridDim.x * (kWThreads / 32)) {
     const int64_t e = wt * SH::GPW + sub;
     const bool live = e < batch;
     int64_t* ebase = y + (size_t)(live ? e : 0) * SH::N * k + limb;
     const int64_t* src = ebase + (size_t)l * k;
-    uint32_t v[SH::D2];
+    uint32_t v[1][SH::D2];
     uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
     for (int i = 0; i < SH::D2; i++) {      // every load is issued before the first use
       const int64_t raw = live ? __ldcs(src + (size_t)(i * SH::L) * k) : 0;
-      v[i] = (uint32_t)raw;
+      v[0][i] = (uint32_t)raw;
       hi_or |= (uint32_t)((uint64_t)raw >> 32);
-      lo_max = max(lo_max, v[i]);
+      lo_max = max(lo_max, v[0][i]);
     }
     if (hi_or != 0 || lo_max >= C.mod.q) {
 #pragma unroll
-      for (int i = 0; i < SH::D2; i++) v[i] = w_reduce_any(src[(size_t)(i * SH::L) * k], C.mod.q);
+      for (int i = 0; i < SH::D2; i++) v[0][i] = w_reduce_any(src[(size_t)(i * SH::L) * k], C.mod.q);
     }
     w_finish<SH, INV, AR, K>(v, l, lt, C, A, ebase, k, live);
   }
@@ -388,10 +416,12 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
   __shared__ uint32_t tile[EPB * ROWS * RS];
   const AR A(C.mod);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l = lane & (SH::L - 1), sub = lane >> SH::LOG;
-  uint32_t lt[kWLaneRows];
+  const int l = lane & (SH::LW - 1), sub = lane >> SH::LL;
+  uint32_t lt[SH::H][kWLaneRows];
 #pragma unroll
-  for (int i = 0; i < kWLaneRows; i++) lt[i] = C.lane_tw[i * 32 + lane];
+  for (int h = 0; h < SH::H; h++)
+#pragma unroll
+    for (int i = 0; i < kWLaneRows; i++) lt[h][i] = C.lane_tw[(h * kWLaneRows + i) * 32 + lane];
   const int64_t ngroups = (batch + EPB - 1) / EPB;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t e0 = g * EPB;
@@ -427,9 +457,11 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
       const int tt = live ? t : 0;
       const int slot = tt / ROWS, row = tt - slot * ROWS;
       const uint32_t* srow = tile + (slot * ROWS + row) * RS + l;
-      uint32_t v[SH::D2];
+      uint32_t v[SH::H][SH::D2];
 #pragma unroll
-      for (int i = 0; i < SH::D2; i++) v[i] = srow[i * SH::L];
+      for (int h = 0; h < SH::H; h++)
+#pragma unroll
+        for (int i = 0; i < SH::D2; i++) v[h][i] = srow[i * SH::L + h * SH::LW];
       int64_t* dst = y + ((size_t)(e0 + slot) * N + (size_t)row * COLS) * k + limb;
       w_finish<SH, INV, AR, K>(v, l, lt, C, A, dst, k, live);
     }
@@ -495,34 +527,42 @@ void build_pp_consts(int p, int e, bool inverse, const RootTab& T, uint64_t scal
   }
 }
 
-// per-lane constants of the network for 2^a (a >= 2): out[kWLaneRows][32], the group pattern repeated across the warp
+// per-lane constants of the network for 2^a (a >= 2): out[2 column halves][kWLaneRows][32], the group pattern repeated across
+// the warp.  LOG = a - 1 column bits, LL = min(LOG, 5) of them lane bits; with a = 7 the top bit is the column half h.
 void build_lane_table(int a_exp, bool inverse, const RootTab& T, uint32_t* out)
 {
   const uint64_t q = T.q;
-  const int LOG = a_exp >= 2 ? a_exp - 1 : 0, L = 1 << LOG;
-  for (int i = 0; i < kWLaneRows * 32; i++) out[i] = 1;
+  const int LOG = a_exp >= 2 ? a_exp - 1 : 0, LL = LOG > 5 ? 5 : LOG, LW = 1 << LL, H = (1 << LOG) / LW;
+  for (int i = 0; i < 2 * kWLaneRows * 32; i++) out[i] = 1;
   if (LOG == 0) return;
-  for (int lane = 0; lane < 32; lane++) {
-    const int l = lane & (L - 1);
-    auto round_tw = [&](int r, int hi_digits) -> uint64_t {      // dftTwiddle of the round on bit r (crt.cpp:92-106)
-      return hi_digits ? T(digit_rev(2, LOG - 1 - r, hi_digits) * ((int64_t)2 << r)) : 1;
-    };
-    if (!inverse) {
-      out[0 * 32 + lane] = (uint32_t)(l ? T(digit_rev(2, LOG, l)) : 1);      // crtTwiddle, column = l
-      for (int r = 0; r < LOG - 1; r++) {
-        const uint64_t tw = round_tw(r, l >> (r + 1));
-        // lanes whose bit r is set hold (t, u) instead of (u, t): they multiply (t - u) by -tw
-        out[(1 + r) * 32 + lane] = (uint32_t)(((l >> r) & 1) ? (q - tw) % q : tw);
+  const int NT = H == 1 ? LL - 1 : LL;      // rounds with twiddles among the lane rounds (the top column bit carries none)
+  for (int h = 0; h < H; h++) {
+    uint32_t* o = out + (size_t)h * kWLaneRows * 32;
+    for (int lane = 0; lane < 32; lane++) {
+      const int l = lane & (LW - 1);
+      // dftTwiddle of the round on column bit r for the butterfly whose higher column bits are `hi_bits` (crt.cpp:92-106)
+      auto round_tw = [&](int r, int hi_bits) -> uint64_t {
+        return hi_bits ? T(digit_rev(2, LOG - 1 - r, hi_bits) * ((int64_t)2 << r)) : 1;
+      };
+      if (!inverse) {
+        const int col = h * LW + l;
+        o[0 * 32 + lane] = (uint32_t)(col ? T(digit_rev(2, LOG, col)) : 1);      // crtTwiddle of the lane's column
+        for (int r = 0; r < NT; r++) {
+          const uint64_t tw = round_tw(r, (h << (LL - 1 - r)) | (l >> (r + 1)));
+          // lanes whose bit r is set hold (t, u) instead of (u, t): they multiply (t - u) by -tw
+          o[(1 + r) * 32 + lane] = (uint32_t)(((l >> r) & 1) ? (q - tw) % q : tw);
+        }
+      } else {
+        for (int r = 1; r < NT; r++)
+          o[r * 32 + lane] = (uint32_t)round_tw(r, (h << (LL - 1 - r)) | ((l >> r) & ((1 << (LL - 1 - r)) - 1)));
+        const uint64_t tw0 = round_tw(0, (h << (LL - 1)) | (l & ((1 << (LL - 1)) - 1)));
+        const int col = 2 * (l & (LW / 2 - 1)) + h * LW;
+        const uint64_t ca = col ? T(digit_rev(2, LOG, col)) : 1, cb = T(digit_rev(2, LOG, col + 1));
+        o[6 * 32 + lane] = (uint32_t)ca;
+        o[7 * 32 + lane] = (uint32_t)mulmod64(ca, tw0, q);
+        o[8 * 32 + lane] = (uint32_t)cb;
+        o[9 * 32 + lane] = (uint32_t)((q - mulmod64(cb, tw0, q)) % q);
       }
-    } else {
-      for (int r = 1; r < LOG - 1; r++) out[r * 32 + lane] = (uint32_t)round_tw(r, (l >> r) & ((1 << (LOG - 1 - r)) - 1));
-      const uint64_t tw0 = round_tw(0, l & ((1 << (LOG - 1)) - 1));
-      const int col = 2 * (l & (L / 2 - 1));
-      const uint64_t ca = col ? T(digit_rev(2, LOG, col)) : 1, cb = T(digit_rev(2, LOG, col + 1));
-      out[4 * 32 + lane] = (uint32_t)ca;
-      out[5 * 32 + lane] = (uint32_t)mulmod64(ca, tw0, q);
-      out[6 * 32 + lane] = (uint32_t)cb;
-      out[7 * 32 + lane] = (uint32_t)((q - mulmod64(cb, tw0, q)) % q);
     }
   }
 }
@@ -560,8 +600,10 @@ typedef WShape<5, PPT<7, 1>, PPNone, PPT<13, 1>, 4, 4> SH_32_7_13;           // 
 typedef WShape<3, PPT<7, 1>, PPNone, PPT<13, 1>, 16, 4> SH_8_7_13;           // m = 728   (n = 288)
 typedef WShape<3, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 4> SH_8_5_7_13;       // m = 3640  (n = 1152)
 typedef WShape<5, PPT<3, 2>, PPNone, PPT<7, 1>, 4, 4> SH_32_9_7;             // m = 2016  (n = 576)
+typedef WShape<6, PPT<7, 1>, PPNone, PPT<13, 1>, 2, 4> SH_64_7_13;           // m = 5824  (n = 2304; lol-apps tunnel benchmark ring H1)
+typedef WShape<7, PPT<7, 1>, PPNone, PPT<13, 1>, 1, 4> SH_128_7_13;          // m = 11648 (n = 4608; Twace-Embed / tunnel H0): two column halves per lane
 
-constexpr int kNumShapes = 6;
+constexpr int kNumShapes = 8;
 
 struct FusedW {
   int shape = -1;
@@ -569,7 +611,7 @@ struct FusedW {
   std::vector<int> cls;                          // WClass per limb
   std::vector<std::vector<uint32_t>> cf, ci;     // per limb: flat constants (already in the limb's representation)
   std::vector<WMod> mod;
-  uint32_t* d_lane = nullptr;                    // [k][2][kWLaneRows][32]
+  uint32_t* d_lane = nullptr;                    // [k][2 directions][2 column halves][kWLaneRows][32]
   std::vector<uint32_t> h_lane;
 };
 
@@ -588,7 +630,8 @@ bool shape_matches(const lolb_plan* pl, const WShapeId& id, int* pmax)
 }
 
 const WShapeId kShapeIds[kNumShapes] = {shape_id<SH_64_27>(), shape_id<SH_64_81>(), shape_id<SH_32_7_13>(),
-                                        shape_id<SH_8_7_13>(), shape_id<SH_8_5_7_13>(), shape_id<SH_32_9_7>()};
+                                        shape_id<SH_8_7_13>(), shape_id<SH_8_5_7_13>(), shape_id<SH_32_9_7>(), shape_id<SH_64_7_13>(),
+                                        shape_id<SH_128_7_13>()};
 
 // host-side constants of one plan (no CUDA calls): shared by fused_w_select and the device-free emulation
 int build_fused_w(const lolb_plan* pl, FusedW* F)
@@ -612,7 +655,7 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
   F->cf.assign(k, {});
   F->ci.assign(k, {});
   F->mod.assign(k, WMod{});
-  F->h_lane.assign((size_t)k * 2 * kWLaneRows * 32, 1u);
+  F->h_lane.assign((size_t)k * 2 * 2 * kWLaneRows * 32, 1u);
   const int first_odd = id.a > 0 ? 1 : 0;
   for (int t = 0; t < k; t++) {
     const uint64_t q = (uint64_t)pl->qs[t];
@@ -633,14 +676,14 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
         out.resize(at + n_m1 + n_w);
         build_pp_consts(p, e, dir != 0, T, i == first_odd ? scale : 1, out.data() + at);      // mhat^-1 rides on the first odd axis
       }
-      uint32_t* lane = F->h_lane.data() + ((size_t)t * 2 + dir) * kWLaneRows * 32;
+      uint32_t* lane = F->h_lane.data() + ((size_t)t * 2 + dir) * 2 * kWLaneRows * 32;
       if (id.a >= 2) {
         RootTab T2{&tabs[0], k, t, ipow64(2, id.a), q};
         build_lane_table(id.a, dir != 0, T2, lane);
       }
       if (F->cls[t] == WC_M) {
         for (auto& c : out) c = w_mont(c, q);
-        for (int i = 0; i < kWLaneRows * 32; i++) lane[i] = w_mont(lane[i], q);
+        for (int i = 0; i < 2 * kWLaneRows * 32; i++) lane[i] = w_mont(lane[i], q);
       }
     }
   }
@@ -652,7 +695,7 @@ int launch_w(const lolb_plan* pl, const FusedW* F, int limb, int64_t* y, int64_t
 {
   WConsts<SH::NC> C;
   C.mod = F->mod[limb];
-  C.lane_tw = F->d_lane + ((size_t)limb * 2 + (INV ? 1 : 0)) * kWLaneRows * 32;
+  C.lane_tw = F->d_lane + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
   const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
   if ((int)src.size() != (SH::PA::n_consts + SH::PB::n_consts + SH::PC::n_consts)) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
   for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
@@ -705,9 +748,9 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
   C.lane_tw = nullptr;
   const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
   for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
-  const uint32_t* lane_tab = F->h_lane.data() + ((size_t)limb * 2 + (INV ? 1 : 0)) * kWLaneRows * 32;
+  const uint32_t* lane_tab = F->h_lane.data() + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
   const AR A(C.mod);
-  constexpr int L = SH::L, LOG = SH::LOG, D2 = SH::D2, NP = SH::NP, COLS = SH::COLS, ROWS = SH::ROWS;
+  constexpr int L = SH::L, D2 = SH::D2, NP = SH::NP, COLS = SH::COLS, ROWS = SH::ROWS;
   std::vector<uint32_t> tile((size_t)SH::N);
   const uint32_t q = C.mod.q;
   auto ld = [&](int j) { int64_t r = y[(size_t)j * k + limb] % (int64_t)q; if (r < 0) r += q; return (uint32_t)r; };
@@ -718,25 +761,37 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
     pp_line<typename SH::PC, INV, 1, SH::OFF_C>(v, 0, C, A);
     for (int i = 0; i < ROWS; i++) tile[(size_t)i * COLS + col] = v[i];
   }
-  // phase 2, one row at a time, all L lanes of the group in lockstep
+  // phase 2, one row at a time, all LW lanes of the group in lockstep, H column halves per lane
+  constexpr int LW = SH::LW, LL = SH::LL, H = SH::H;
+  constexpr bool TOP_IN_LANES = H == 1;
+  constexpr int NT = TOP_IN_LANES ? LL - 1 : LL;
   for (int row = 0; row < ROWS; row++) {
-    uint32_t v[L][D2];
-    for (int l = 0; l < L; l++) {
-      for (int i = 0; i < D2; i++) v[l][i] = tile[(size_t)row * COLS + i * L + l];
-      for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v[l], ib * SH::DA, C, A);
-      for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v[l], ia, C, A);
-    }
-    auto lt = [&](int r, int l) { return lane_tab[r * 32 + l]; };      // lane = l (group 0)
-    auto round = [&](bool trivial, int bit, int row_tw) {
-      uint32_t nv[L][D2];
-      for (int l = 0; l < L; l++) {
+    uint32_t v[H][LW][D2];
+    for (int h = 0; h < H; h++)
+      for (int l = 0; l < LW; l++) {
+        for (int i = 0; i < D2; i++) v[h][l][i] = tile[(size_t)row * COLS + i * L + h * LW + l];
+        for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v[h][l], ib * SH::DA, C, A);
+        for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v[h][l], ia, C, A);
+      }
+    auto lt = [&](int h, int r, int l) { return lane_tab[(h * kWLaneRows + r) * 32 + l]; };      // lane = l (group 0)
+    auto top_round = [&]() {
+      for (int l = 0; l < LW; l++)
+        for (int i = 0; i < D2; i++) {
+          const uint32_t u = v[0][l][i], t = v[H - 1][l][i];
+          v[0][l][i] = A.fold(u + t);
+          v[H - 1][l][i] = A.fold(u + A.q2 - t);
+        }
+    };
+    auto round = [&](int h, bool trivial, int bit, int row_tw) {
+      uint32_t nv[LW][D2];
+      for (int l = 0; l < LW; l++) {
         const bool hi = (l >> bit) & 1;
         const int partner = l ^ (1 << bit);
         for (int j = 0; j < NP; j++) {
-          const uint32_t keep = hi ? v[l][2 * j + 1] : v[l][2 * j];
+          const uint32_t keep = hi ? v[h][l][2 * j + 1] : v[h][l][2 * j];
           const bool phi_ = (partner >> bit) & 1;
-          const uint32_t recv = phi_ ? v[partner][2 * j] : v[partner][2 * j + 1];      // what the partner sends
-          const uint32_t tw = trivial ? 0u : lt(row_tw, l);
+          const uint32_t recv = phi_ ? v[h][partner][2 * j] : v[h][partner][2 * j + 1];      // what the partner sends
+          const uint32_t tw = trivial ? 0u : lt(h, row_tw, l);
           if (trivial) {
             const uint32_t u = hi ? recv : keep, t = hi ? keep : recv;
             nv[l][2 * j] = A.fold(u + t);
@@ -752,40 +807,45 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
           }
         }
       }
-      for (int l = 0; l < L; l++) for (int i = 0; i < D2; i++) v[l][i] = nv[l][i];
+      for (int l = 0; l < LW; l++) for (int i = 0; i < D2; i++) v[h][l][i] = nv[l][i];
     };
-    if (LOG >= 1) {
-      if (!INV) {
-        for (int l = 0; l < L; l++) for (int i = 0; i < D2; i++) v[l][i] = A.red(A.mul(lt(0, l), v[l][i]));
-        for (int r = 0; r < LOG - 1; r++) round(false, r, 1 + r);
-        round(true, LOG - 1, 0);
-      } else {
-        if (LOG >= 2) round(true, LOG - 1, 0);
-        for (int r = LOG - 2; r >= 1; r--) round(false, r, r);
-        uint32_t nv[L][D2];
-        for (int l = 0; l < L; l++) {
-          const bool hi = l & 1;
-          const int partner = l ^ 1;
-          for (int j = 0; j < NP; j++) {
-            const uint32_t keep = hi ? v[l][2 * j + 1] : v[l][2 * j];
-            const uint32_t recv = (partner & 1) ? v[partner][2 * j] : v[partner][2 * j + 1];
-            const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
-            nv[l][2 * j] = A.red(A.mad(A.mul(lt(4, l), u), lt(5, l), t));
-            nv[l][2 * j + 1] = A.red(A.mad(A.mul(lt(6, l), u), lt(7, l), t));
+    if (LL >= 1) {
+      if (H == 2 && INV) top_round();
+      for (int h = 0; h < H; h++) {
+        if (!INV) {
+          for (int l = 0; l < LW; l++) for (int i = 0; i < D2; i++) v[h][l][i] = A.red(A.mul(lt(h, 0, l), v[h][l][i]));
+          for (int r = 0; r < NT; r++) round(h, false, r, 1 + r);
+          if (TOP_IN_LANES) round(h, true, LL - 1, 0);
+        } else {
+          if (TOP_IN_LANES && LL >= 2) round(h, true, LL - 1, 0);
+          for (int r = NT - 1; r >= 1; r--) round(h, false, r, r);
+          uint32_t nv[LW][D2];
+          for (int l = 0; l < LW; l++) {
+            const bool hi = l & 1;
+            const int partner = l ^ 1;
+            for (int j = 0; j < NP; j++) {
+              const uint32_t keep = hi ? v[h][l][2 * j + 1] : v[h][l][2 * j];
+              const uint32_t recv = (partner & 1) ? v[h][partner][2 * j] : v[h][partner][2 * j + 1];
+              const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
+              nv[l][2 * j] = A.red(A.mad(A.mul(lt(h, 6, l), u), lt(h, 7, l), t));
+              nv[l][2 * j + 1] = A.red(A.mad(A.mul(lt(h, 8, l), u), lt(h, 9, l), t));
+            }
           }
+          for (int l = 0; l < LW; l++) for (int i = 0; i < D2; i++) v[h][l][i] = nv[l][i];
         }
-        for (int l = 0; l < L; l++) for (int i = 0; i < D2; i++) v[l][i] = nv[l][i];
       }
+      if (H == 2 && !INV) top_round();
     }
-    for (int l = 0; l < L; l++)
-      for (int j = 0; j < NP; j++)
-        for (int s = 0; s < 2; s++) {
-          int pos;
-          if (LOG == 0) pos = 2 * j + s;
-          else if (!INV) pos = (2 * j + (l & 1)) * L + ((s << (LOG - 1)) | (l >> 1));
-          else pos = (2 * j + (l >> (LOG - 1))) * L + 2 * (l & (L / 2 - 1)) + s;
-          y[((size_t)row * COLS + pos) * k + limb] = (int64_t)A.canon(v[l][2 * j + s]);
-        }
+    for (int h = 0; h < H; h++)
+      for (int l = 0; l < LW; l++)
+        for (int j = 0; j < NP; j++)
+          for (int s = 0; s < 2; s++) {
+            int pos;
+            if (LL == 0) pos = 2 * j + s;
+            else if (!INV) pos = (2 * j + (l & 1)) * L + ((s << (LL - 1)) | (l >> 1)) + LW * h;
+            else pos = (2 * j + (l >> (LL - 1))) * L + 2 * (l & (LW / 2 - 1)) + s + LW * h;
+            y[((size_t)row * COLS + pos) * k + limb] = (int64_t)A.canon(v[h][l][2 * j + s]);
+          }
   }
 }
 
@@ -811,6 +871,8 @@ void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
     case 3: { typedef SH_8_7_13 SH; CALL; } break;                 \
     case 4: { typedef SH_8_5_7_13 SH; CALL; } break;               \
     case 5: { typedef SH_32_9_7 SH; CALL; } break;                 \
+    case 6: { typedef SH_64_7_13 SH; CALL; } break;                \
+    case 7: { typedef SH_128_7_13 SH; CALL; } break;               \
     default: break;                                                \
   }
 

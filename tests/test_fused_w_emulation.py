@@ -28,6 +28,8 @@ FUSED_W_PARAMS = [
     (1728, _prime_1_mod(1728, 10 ** 6)), (5184, _prime_1_mod(5184, 10 ** 7)), (2912, _prime_1_mod(2912, 10 ** 5)),
     (3640, _prime_1_mod(3640, 10 ** 6, 2)), (728, _prime_1_mod(728, 3 * 10 ** 7)), (2016, _prime_1_mod(2016, 10 ** 8)),
     (1728, [3457, 1002241]),      # mixed arithmetic classes, tupSize 2
+    (5824, [3144961]), (2912, [3144961]), (3640, [3144961]),      # lol-apps tunnel benchmark rings and modulus (Benchmarks/Default.hs:52-82)
+    (11648, [23297]), (11648, [3144961]), (11648, [174721]),      # F128*F7*F13: two column halves per lane (a = 7)
 ]
 
 

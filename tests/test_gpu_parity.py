@@ -214,8 +214,10 @@ BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249
                 (14400, [43201, 57601, 100801, 115201, 172801, 259201]),      # tupSize 6: odd limb stride in the de-interleaved tile
                 # fused_w: the reference's other benchmark rings (Benchmarks/Default.hs:41-48) + m = 2016, both arithmetic classes
                 (64 * 81, [10369]), (32 * 7 * 13, [8737]), (8 * 7 * 13, [8737]), (8 * 5 * 7 * 13, [14561]), (2016, [2017]),
-                (64 * 27, [3457, 1002241]), (64 * 81, [10031041]), (32 * 7 * 13, [101921]), (8 * 5 * 7 * 13, [1015561, 1026481])]
-FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016}
+                (64 * 27, [3457, 1002241]), (64 * 81, [10031041]), (32 * 7 * 13, [101921]), (8 * 5 * 7 * 13, [1015561, 1026481]),
+                (64 * 7 * 13, [3144961]), (64 * 7 * 13, [23297]),
+                (128 * 7 * 13, [23297]), (128 * 7 * 13, [3144961])]      # a = 7: two column halves per lane      # lol-apps tunnel ring H1 at its modulus, and the Twace-Embed benchmark modulus (Montgomery class)
+FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016, 64 * 7 * 13, 128 * 7 * 13}
 
 
 @pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
