@@ -467,6 +467,9 @@ def run_gpu_arm(args):
         rq_config("F32*F7*F13/8737", 2912, [8737], 122880)
         rq_config("F8*F5*F7*F13/14561", 3640, [14561], 122880)
         rq_config("F128*F7*F13/23297", 11648, [23297], 30720)
+        # the ring-tunnelling chain of lol-apps' benchmarks at its modulus (lol-apps Benchmarks/Default.hs:52-82)
+        for mt, bt in ((11648, 30720), (5824, 61440), (2912, 122880), (3640, 122880), (5460, 122880), (4095, 81920)):
+            rq_config(f"tunnel m={mt}/3144961", mt, [3144961], bt)
         from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
         Bg = 32768
         tr, ti, tcx = CudaTensorReal(M), CudaTensorInt(M), CudaTensorComplex(M)
@@ -611,6 +614,7 @@ def run_gpu_arm(args):
                "m2912": [fr("F32*F7*F13/8737", "CRT"), fr("F32*F7*F13/8737", "CRTInv")],
                "m3640": [fr("F8*F5*F7*F13/14561", "CRT"), fr("F8*F5*F7*F13/14561", "CRTInv")],
                "m11648": [fr("F128*F7*F13/23297", "CRT"), fr("F128*F7*F13/23297", "CRTInv")],
+               "tunnel": [[fr(f"tunnel m={mt}/3144961", "CRT"), fr(f"tunnel m={mt}/3144961", "CRTInv")] for mt in (11648, 5824, 2912, 3640, 5460, 4095)],
                "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec")}
     for s, n, ms, _, units, _ in rec.rows:
         if s == "she" and n == "mulAndSwitch":

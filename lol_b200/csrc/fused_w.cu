@@ -203,24 +203,31 @@ WHD void pp_line(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
 
 // ------------------------------------------------------------------ shapes
 // A: exponent of 2 (0 or 1: no 2^a axis), PA / PB: the odd prime powers handled together with the 2^a axis, PC: the
-// last prime power (phase 1 of k_fused_w2; PPNone selects k_fused_w1).  EPB: ring elements per CTA iteration (w2).
-template <int A_, class PA_, class PB_, class PC_, int EPB_, int MINB_>
+// last prime power (phase 1 of k_fused_w2; PPNone selects k_fused_w1), PD: an optional prime power between them that is
+// transformed in place in the tile (phase 1b), for indices with four odd prime powers.  EPB: ring elements per CTA
+// iteration (w2).  Tensor order (fastest first): 2^a, PA, PB, PD, PC.
+template <int A_, class PA_, class PB_, class PD_, class PC_, int EPB_, int MINB_>
 struct WShape {
   typedef PA_ PA;
   typedef PB_ PB;
+  typedef PD_ PD;
   typedef PC_ PC;
   static constexpr int A = A_, LOG = A_ >= 2 ? A_ - 1 : 0, L = 1 << LOG;
   // the 2^a axis spans LL lane bits; beyond 32 columns (a = 7) a lane holds H = 2 column halves (col, col + 32) of every row
   static constexpr int LL = LOG > 5 ? 5 : LOG, LW = 1 << LL, H = L / LW, GPW = 32 / LW;
   static_assert(LOG <= 6, "2^a axis: a <= 7");
-  static constexpr int DA = PA::phi, DB = PB::phi, D2 = DA * DB, NP = D2 / 2;
-  static constexpr int COLS = L * D2, ROWS = PC::phi, N = COLS * ROWS;
-  static constexpr int OFF_A = 0, OFF_B = PA::n_consts, OFF_C = PA::n_consts + PB::n_consts;
-  static constexpr int NC = (PA::n_consts + PB::n_consts + PC::n_consts) > 0 ? (PA::n_consts + PB::n_consts + PC::n_consts) : 1;
+  static constexpr int DA = PA::phi, DB = PB::phi, D2 = DA * DB, NP = D2 / 2, DD = PD::phi;
+  static constexpr int SUB = L * D2;                      // coefficients of one phase-2 block (fixed id, ic)
+  static constexpr int COLS = SUB * DD, ROWS = PC::phi, N = COLS * ROWS;
+  static constexpr int OFF_A = 0, OFF_B = PA::n_consts, OFF_D = OFF_B + PB::n_consts, OFF_C = OFF_D + PD::n_consts;
+  static constexpr int NC = (OFF_C + PC::n_consts) > 0 ? (OFF_C + PC::n_consts) : 1;
   static constexpr int EPB = EPB_, MINB = MINB_;
   static constexpr bool TWO_PHASE = PC::p > 1;
-  // tile row stride: rows handled by the sub-warp groups of one warp must start in different banks
-  static constexpr int RS = (L >= 32 || COLS % 32 == L % 32) ? COLS : COLS + ((L + 32 - COLS % 32) % 32);
+  // tile strides: the blocks handled by the sub-warp groups of one warp must start in different banks
+  // (block b of a warp's 32/L groups sits at b * SRS: with SRS = L * odd the groups cover all 32 banks exactly once)
+  static constexpr int SRS = L >= 32 ? SUB : L * (D2 | 1);      // block stride
+  static constexpr int RS = DD * SRS;                                                                      // stride of ic
+  static_assert(DD == 1 || TWO_PHASE, "the in-tile axis needs the tile");
   static_assert(H == 1 || TWO_PHASE, "a = 7 is served by the two-phase kernel only");
   static_assert(D2 % 2 == 0, "an odd prime power is required next to the 2^a axis");
 };
@@ -444,25 +451,42 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
         for (int i = 0; i < ROWS; i++) v[i] = w_reduce_any(src[(size_t)(i * COLS) * k], C.mod.q);
       }
       pp_line<PC, INV, 1, SH::OFF_C>(v, 0, C, A);
-      uint32_t* dst = tile + slot * ROWS * RS + col;
+      const int cd = col / SH::SUB, cx = col - cd * SH::SUB;
+      uint32_t* dst = tile + slot * ROWS * RS + cd * SH::SRS + cx;
 #pragma unroll
       for (int i = 0; i < ROWS; i++) dst[i * RS] = v[i];
     }
     __syncthreads();
-    // ---------------- phase 2: group-task = (element slot, row ic); L lanes x D2 values, middle lines + network
-    const int ntask = cnt * ROWS;
+    // ---------------- phase 1b (four odd prime powers): the PD axis in place in the tile; thread-task = (slot, ic, x)
+    if constexpr (SH::DD > 1) {
+      for (int t = threadIdx.x; t < cnt * ROWS * SH::SUB; t += kWThreads) {
+        const int sr = t / SH::SUB, x = t - sr * SH::SUB;      // sr = slot * ROWS + ic
+        uint32_t* line = tile + sr * RS + x;
+        uint32_t v[SH::DD];
+#pragma unroll
+        for (int i = 0; i < SH::DD; i++) v[i] = line[i * SH::SRS];
+        pp_line<typename SH::PD, INV, 1, SH::OFF_D>(v, 0, C, A);
+#pragma unroll
+        for (int i = 0; i < SH::DD; i++) line[i * SH::SRS] = v[i];
+      }
+      __syncthreads();
+    }
+    // ---------------- phase 2: group-task = (element slot, ic, id); L lanes x D2 values, middle lines + network
+    constexpr int BLOCKS = ROWS * SH::DD;      // phase-2 blocks per element
+    const int ntask = cnt * BLOCKS;
     for (int t0 = warp * SH::GPW; t0 < ntask; t0 += (kWThreads / 32) * SH::GPW) {      // warp-uniform trip count
       const int t = t0 + sub;
       const bool live = t < ntask;
       const int tt = live ? t : 0;
-      const int slot = tt / ROWS, row = tt - slot * ROWS;
-      const uint32_t* srow = tile + (slot * ROWS + row) * RS + l;
+      const int slot = tt / BLOCKS, blk = tt - slot * BLOCKS;      // blk = ic * DD + id: the block's position in the element
+      const int row = blk / SH::DD, bd = blk - row * SH::DD;
+      const uint32_t* srow = tile + (slot * ROWS + row) * RS + bd * SH::SRS + l;
       uint32_t v[SH::H][SH::D2];
 #pragma unroll
       for (int h = 0; h < SH::H; h++)
 #pragma unroll
         for (int i = 0; i < SH::D2; i++) v[h][i] = srow[i * SH::L + h * SH::LW];
-      int64_t* dst = y + ((size_t)(e0 + slot) * N + (size_t)row * COLS) * k + limb;
+      int64_t* dst = y + ((size_t)(e0 + slot) * N + (size_t)blk * SH::SUB) * k + limb;
       w_finish<SH, INV, AR, K>(v, l, lt, C, A, dst, k, live);
     }
     __syncthreads();
@@ -583,10 +607,10 @@ void w_mod_consts(uint64_t q, int cls, WMod* M)
 inline uint32_t w_mont(uint32_t c, uint64_t q) { return (uint32_t)((((uint64_t)c) << 32) % q); }
 
 // the shape list: one entry per instantiated kernel family
-struct WShapeId { int a; int pa, ea, pb, eb, pc, ec; };
+struct WShapeId { int a; int pa, ea, pb, eb, pd, ed, pc, ec; };
 
 template <class SH>
-constexpr WShapeId shape_id() { return WShapeId{SH::A, SH::PA::p, SH::PA::e, SH::PB::p, SH::PB::e, SH::PC::p, SH::PC::e}; }
+constexpr WShapeId shape_id() { return WShapeId{SH::A, SH::PA::p, SH::PA::e, SH::PB::p, SH::PB::e, SH::PD::p, SH::PD::e, SH::PC::p, SH::PC::e}; }
 
 #ifndef LOLB_W27_MINB
 #define LOLB_W27_MINB 4      // measured on B200, CRT / CRT^-1 of HBM peak: 4 -> 95 % / 94 %, 6 -> 87 % / 88 %, 8 -> 87 % / 87 %.  CTAs of 128 threads per SM the register allocation must allow (tuning: tools/build_variant.py)
@@ -594,16 +618,18 @@ constexpr WShapeId shape_id() { return WShapeId{SH::A, SH::PA::p, SH::PA::e, SH:
 #ifndef LOLB_W81_MINB
 #define LOLB_W81_MINB 3      // 2 -> 72 % / 75 %, 3 -> 81 % / 83 %, 4 -> 71 % / 84 %
 #endif
-typedef WShape<6, PPT<3, 3>, PPNone, PPNone, 1, LOLB_W27_MINB> SH_64_27;     // m = 1728  (n = 576)
-typedef WShape<6, PPT<3, 4>, PPNone, PPNone, 1, LOLB_W81_MINB> SH_64_81;     // m = 5184  (n = 1728)
-typedef WShape<5, PPT<7, 1>, PPNone, PPT<13, 1>, 4, 4> SH_32_7_13;           // m = 2912  (n = 1152)
-typedef WShape<3, PPT<7, 1>, PPNone, PPT<13, 1>, 16, 4> SH_8_7_13;           // m = 728   (n = 288)
-typedef WShape<3, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 4> SH_8_5_7_13;       // m = 3640  (n = 1152)
-typedef WShape<5, PPT<3, 2>, PPNone, PPT<7, 1>, 4, 4> SH_32_9_7;             // m = 2016  (n = 576)
-typedef WShape<6, PPT<7, 1>, PPNone, PPT<13, 1>, 2, 4> SH_64_7_13;           // m = 5824  (n = 2304; lol-apps tunnel benchmark ring H1)
-typedef WShape<7, PPT<7, 1>, PPNone, PPT<13, 1>, 1, 4> SH_128_7_13;          // m = 11648 (n = 4608; Twace-Embed / tunnel H0): two column halves per lane
+typedef WShape<6, PPT<3, 3>, PPNone, PPNone, PPNone, 1, LOLB_W27_MINB> SH_64_27;     // m = 1728  (n = 576)
+typedef WShape<6, PPT<3, 4>, PPNone, PPNone, PPNone, 1, LOLB_W81_MINB> SH_64_81;     // m = 5184  (n = 1728)
+typedef WShape<5, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 4, 4> SH_32_7_13;           // m = 2912  (n = 1152)
+typedef WShape<3, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 16, 4> SH_8_7_13;           // m = 728   (n = 288)
+typedef WShape<3, PPT<5, 1>, PPT<7, 1>, PPNone, PPT<13, 1>, 8, 4> SH_8_5_7_13;       // m = 3640  (n = 1152)
+typedef WShape<5, PPT<3, 2>, PPNone, PPNone, PPT<7, 1>, 4, 4> SH_32_9_7;             // m = 2016  (n = 576)
+typedef WShape<6, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 2, 4> SH_64_7_13;           // m = 5824  (n = 2304; lol-apps tunnel benchmark ring H1)
+typedef WShape<7, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 1, 4> SH_128_7_13;  // m = 11648 (n = 4608; Twace-Embed / tunnel H0): two column halves per lane
+typedef WShape<2, PPT<3, 1>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 4> SH_4_3_5_7_13;      // m = 5460 (n = 1152; tunnel H4): 7 in the tile
+typedef WShape<0, PPT<3, 2>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 4, 4> SH_9_5_7_13;        // m = 4095 (n = 1728; tunnel H5): odd index, no network
 
-constexpr int kNumShapes = 8;
+constexpr int kNumShapes = 10;
 
 struct FusedW {
   int shape = -1;
@@ -621,17 +647,18 @@ bool shape_matches(const lolb_plan* pl, const WShapeId& id, int* pmax)
   if (id.a > 0) want.push_back({2, (hShort_t)id.a});
   if (id.pa > 1) want.push_back({(hShort_t)id.pa, (hShort_t)id.ea});
   if (id.pb > 1) want.push_back({(hShort_t)id.pb, (hShort_t)id.eb});
+  if (id.pd > 1) want.push_back({(hShort_t)id.pd, (hShort_t)id.ed});
   if (id.pc > 1) want.push_back({(hShort_t)id.pc, (hShort_t)id.ec});
   if (want.size() != pl->pe.size()) return false;
   for (size_t i = 0; i < want.size(); i++)
     if (want[i].prime != pl->pe[i].prime || want[i].exponent != pl->pe[i].exponent) return false;
-  *pmax = id.pc > 1 ? id.pc : id.pb > 1 ? id.pb : id.pa;
+  *pmax = id.pc > 1 ? id.pc : id.pd > 1 ? id.pd : id.pb > 1 ? id.pb : id.pa;
   return true;
 }
 
 const WShapeId kShapeIds[kNumShapes] = {shape_id<SH_64_27>(), shape_id<SH_64_81>(), shape_id<SH_32_7_13>(),
                                         shape_id<SH_8_7_13>(), shape_id<SH_8_5_7_13>(), shape_id<SH_32_9_7>(), shape_id<SH_64_7_13>(),
-                                        shape_id<SH_128_7_13>()};
+                                        shape_id<SH_128_7_13>(), shape_id<SH_4_3_5_7_13>(), shape_id<SH_9_5_7_13>()};
 
 // host-side constants of one plan (no CUDA calls): shared by fused_w_select and the device-free emulation
 int build_fused_w(const lolb_plan* pl, FusedW* F)
@@ -666,7 +693,7 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
       std::vector<uint32_t>& out = dir ? F->ci[t] : F->cf[t];
       uint64_t scale = 1;
       if (dir) { int64_t s = pl->mhatinv[t] % (int64_t)q; if (s < 0) s += q; scale = (uint64_t)s; }
-      for (int i = first_odd; i < npe; i++) {      // order = (PA, PB, PC) = the plan's odd prime powers in order
+      for (int i = first_odd; i < npe; i++) {      // order = (PA, PB, PD, PC) = the plan's odd prime powers in order
         const int p = pl->pe[i].prime, e = pl->pe[i].exponent;
         RootTab T{&tabs[i], k, t, ipow64(p, e), q};
         const size_t n_m1 = (size_t)ipow64(p, e - 1) * (p - 1) * (p - 1);
@@ -697,7 +724,7 @@ int launch_w(const lolb_plan* pl, const FusedW* F, int limb, int64_t* y, int64_t
   C.mod = F->mod[limb];
   C.lane_tw = F->d_lane + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
   const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
-  if ((int)src.size() != (SH::PA::n_consts + SH::PB::n_consts + SH::PC::n_consts)) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
+  if ((int)src.size() != SH::OFF_C + SH::PC::n_consts) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
   for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
   int64_t grid = (int64_t)pl->num_sms * SH::MINB;
   if constexpr (SH::TWO_PHASE) {
@@ -722,7 +749,7 @@ int launch_shape(const lolb_plan* pl, const FusedW* F, bool inverse, int64_t* y,
     int rc;
     const bool m = F->cls[t] == WC_M, k1 = pl->k == 1;
     if (F->cls[t] == WC_S6) {
-      if constexpr (SH::PC::p > 6 || SH::PB::p > 6 || SH::PA::p > 6) {
+      if constexpr (SH::PC::p > 6 || SH::PD::p > 6 || SH::PB::p > 6 || SH::PA::p > 6) {
         rc = inverse ? (k1 ? launch_w<SH, true, WS6, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WS6, 0>(pl, F, t, y, batch, st))
                      : (k1 ? launch_w<SH, false, WS6, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WS6, 0>(pl, F, t, y, batch, st));
       } else rc = LOLB_FUSED_UNAVAILABLE;
@@ -761,15 +788,26 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
     pp_line<typename SH::PC, INV, 1, SH::OFF_C>(v, 0, C, A);
     for (int i = 0; i < ROWS; i++) tile[(size_t)i * COLS + col] = v[i];
   }
-  // phase 2, one row at a time, all LW lanes of the group in lockstep, H column halves per lane
+  // phase 1b: the in-tile axis
+  constexpr int DD = SH::DD, SUB = SH::SUB;
+  if (DD > 1) {
+    for (int ic = 0; ic < ROWS; ic++)
+      for (int x = 0; x < SUB; x++) {
+        uint32_t v[DD];
+        for (int i = 0; i < DD; i++) v[i] = tile[(size_t)ic * COLS + i * SUB + x];
+        pp_line<typename SH::PD, INV, 1, SH::OFF_D>(v, 0, C, A);
+        for (int i = 0; i < DD; i++) tile[(size_t)ic * COLS + i * SUB + x] = v[i];
+      }
+  }
+  // phase 2, one block (ic, id) at a time, all LW lanes of the group in lockstep, H column halves per lane
   constexpr int LW = SH::LW, LL = SH::LL, H = SH::H;
   constexpr bool TOP_IN_LANES = H == 1;
   constexpr int NT = TOP_IN_LANES ? LL - 1 : LL;
-  for (int row = 0; row < ROWS; row++) {
+  for (int row = 0; row < ROWS * DD; row++) {
     uint32_t v[H][LW][D2];
     for (int h = 0; h < H; h++)
       for (int l = 0; l < LW; l++) {
-        for (int i = 0; i < D2; i++) v[h][l][i] = tile[(size_t)row * COLS + i * L + h * LW + l];
+        for (int i = 0; i < D2; i++) v[h][l][i] = tile[(size_t)row * SUB + i * L + h * LW + l];
         for (int ib = 0; ib < SH::DB; ib++) pp_line<typename SH::PA, INV, 1, SH::OFF_A>(v[h][l], ib * SH::DA, C, A);
         for (int ia = 0; ia < SH::DA; ia++) pp_line<typename SH::PB, INV, SH::DA, SH::OFF_B>(v[h][l], ia, C, A);
       }
@@ -844,7 +882,7 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
             if (LL == 0) pos = 2 * j + s;
             else if (!INV) pos = (2 * j + (l & 1)) * L + ((s << (LL - 1)) | (l >> 1)) + LW * h;
             else pos = (2 * j + (l >> (LL - 1))) * L + 2 * (l & (LW / 2 - 1)) + s + LW * h;
-            y[((size_t)row * COLS + pos) * k + limb] = (int64_t)A.canon(v[h][l][2 * j + s]);
+            y[((size_t)row * SUB + pos) * k + limb] = (int64_t)A.canon(v[h][l][2 * j + s]);
           }
   }
 }
@@ -873,6 +911,8 @@ void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
     case 5: { typedef SH_32_9_7 SH; CALL; } break;                 \
     case 6: { typedef SH_64_7_13 SH; CALL; } break;                \
     case 7: { typedef SH_128_7_13 SH; CALL; } break;               \
+    case 8: { typedef SH_4_3_5_7_13 SH; CALL; } break;             \
+    case 9: { typedef SH_9_5_7_13 SH; CALL; } break;               \
     default: break;                                                \
   }
 

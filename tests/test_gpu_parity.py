@@ -216,8 +216,9 @@ BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249
                 (64 * 81, [10369]), (32 * 7 * 13, [8737]), (8 * 7 * 13, [8737]), (8 * 5 * 7 * 13, [14561]), (2016, [2017]),
                 (64 * 27, [3457, 1002241]), (64 * 81, [10031041]), (32 * 7 * 13, [101921]), (8 * 5 * 7 * 13, [1015561, 1026481]),
                 (64 * 7 * 13, [3144961]), (64 * 7 * 13, [23297]),
-                (128 * 7 * 13, [23297]), (128 * 7 * 13, [3144961])]      # a = 7: two column halves per lane      # lol-apps tunnel ring H1 at its modulus, and the Twace-Embed benchmark modulus (Montgomery class)
-FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016, 64 * 7 * 13, 128 * 7 * 13}
+                (128 * 7 * 13, [23297]), (128 * 7 * 13, [3144961]),      # a = 7: two column halves per lane
+                (4 * 3 * 5 * 7 * 13, [3144961]), (9 * 5 * 7 * 13, [3144961]), (4 * 3 * 5 * 7 * 13, [21841]), (9 * 5 * 7 * 13, [8191])]      # four odd prime powers      # lol-apps tunnel ring H1 at its modulus, and the Twace-Embed benchmark modulus (Montgomery class)
+FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016, 64 * 7 * 13, 128 * 7 * 13, 5460, 4095}
 
 
 @pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
