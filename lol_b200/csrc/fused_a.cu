@@ -76,6 +76,18 @@ struct ArithM {
   __device__ __forceinline__ uint32_t canon(uint32_t x) const { return min(x, x - q); }
 };
 
+// CTA shape of the Montgomery class (tuning: tools/build_variant.py).  Two warps balance both phases exactly (3 and 10 tasks
+// per warp).  Measured on B200, CRT / CRT^-1 % of the HBM roofline, warps x CTAs per SM: one limb (q = 1008001) 2x12 66.2 / 61.6,
+// 2x10 66.6 / 60.9, 3x8 63.8 / 58.8, 4x6 61.4 / 57.5, 5x4 56.9 / 52.6; tupSize 2 (config C) 2x6 62.5 / 55.7, 3x4 62.3 / 54.7,
+// 4x3 58.2 / 53.0, 2x5 54.2 / 48.4, 5x2 46.1 / 40.4.  (The 32-bit class keeps 3x8: 2x14 measured 70 / 67 against 88 / 86.)
+#ifndef LOLB_A_M_W
+#define LOLB_A_M_W 2
+#define LOLB_A_M_MB 12
+#endif
+#ifndef LOLB_A_K2_W
+#define LOLB_A_K2_W 2
+#define LOLB_A_K2_MB 6
+#endif
 constexpr int kLaneRows = 20;      // rows 0-7: 2^6-axis twiddles; rows 8-19: forward m3[i0][r][c] * crtTwiddle_64(lane)
 constexpr int kN = 3840, kD1 = 32, kD2 = 6, kD3 = 20;
 
@@ -899,7 +911,8 @@ bool fused_a_available(const void* slot, bool inverse)
 template <bool INV, class AR, int K>
 static int launch_a(const lolb_plan* pl, int64_t* y, int64_t batch, int limb, const FusedAConsts& C, cudaStream_t st)
 {
-  constexpr int W = 3, MB = 8;
+  constexpr bool MONT = sizeof(typename AR::Acc) == 8;
+  constexpr int W = MONT ? LOLB_A_M_W : 3, MB = MONT ? LOLB_A_M_MB : 8;
   int64_t grid = (int64_t)pl->num_sms * MB;
   if (grid > batch) grid = batch;
   k_fused_a<INV, AR, K, W, MB><<<(int)grid, W * 32, 0, st>>>(y, batch, pl->k, limb, C, nullptr, 0);
@@ -939,11 +952,12 @@ int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t
     int64_t grid = (int64_t)pl->num_sms * MB;
     if (grid > batch) grid = batch;
     const int64_t b_stride = b_batch == 1 ? 0 : (int64_t)kN * 2;
-    if (F->cls[0] == ARITH_M) {      // 4 CTAs/SM: the Montgomery class needs the registers (see fused_a_crt)
-      int64_t g4 = (int64_t)pl->num_sms * 4;
+    if (F->cls[0] == ARITH_M) {      // the Montgomery class needs the registers: CTA shape of fused_a_crt
+      constexpr int W2 = LOLB_A_K2_W, MB2 = LOLB_A_K2_MB;
+      int64_t g4 = (int64_t)pl->num_sms * MB2;
       if (g4 > batch) g4 = batch;
-      if (inverse) k_fused_a_k2<true, ArithM, W, 4, true><<<(int)g4, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
-      else k_fused_a_k2<false, ArithM, W, 4, true><<<(int)g4, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
+      if (inverse) k_fused_a_k2<true, ArithM, W2, MB2, true><<<(int)g4, W2 * 32, smem, st>>>(y, batch, CC, b, b_stride);
+      else k_fused_a_k2<false, ArithM, W2, MB2, true><<<(int)g4, W2 * 32, smem, st>>>(y, batch, CC, b, b_stride);
     } else {
       if (inverse) k_fused_a_k2<true, ArithS, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
       else k_fused_a_k2<false, ArithS, W, MB, true><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, b, b_stride);
@@ -982,9 +996,10 @@ int fused_a_decompose_crt(const lolb_plan* pl, const void* slot, const int64_t* 
   constexpr int W = 3;
   const size_t smem = 2 * kN * sizeof(uint32_t);
   if (F->cls[0] == ARITH_M) {
-    int64_t gg = (int64_t)pl->num_sms * 4;
+    constexpr int W2 = LOLB_A_K2_W, MB2 = LOLB_A_K2_MB;
+    int64_t gg = (int64_t)pl->num_sms * MB2;
     if (gg > total) gg = total;
-    k_fused_a_k2<false, ArithM, W, 4, false, true><<<(int)gg, W * 32, smem, st>>>(digits, total, CC, x, batch);
+    k_fused_a_k2<false, ArithM, W2, MB2, false, true><<<(int)gg, W2 * 32, smem, st>>>(digits, total, CC, x, batch);
   } else {
     int64_t gg = (int64_t)pl->num_sms * 5;
     if (gg > total) gg = total;
@@ -1053,10 +1068,11 @@ int fused_a_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
       // ArithM with both limbs in flight needs more than the 128 registers that 5 CTAs/SM leave: measured (config C
       // moduli, % of HBM peak forward / inverse) 5 CTAs x 128 registers (spills) 57.5 / 52.8, 4 x 168 62.4 / 54.8; the
       // per-lane constants in shared memory (5 / 6 CTAs per SM) were slower still
-      int64_t gg = (int64_t)pl->num_sms * 4;
+      constexpr int W2 = LOLB_A_K2_W, MB2 = LOLB_A_K2_MB;
+      int64_t gg = (int64_t)pl->num_sms * MB2;
       if (gg > batch) gg = batch;
-      if (inverse) k_fused_a_k2<true, ArithM, W, 4><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
-      else k_fused_a_k2<false, ArithM, W, 4><<<(int)gg, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
+      if (inverse) k_fused_a_k2<true, ArithM, W2, MB2><<<(int)gg, W2 * 32, smem, st>>>(y, batch, CC, nullptr, 0);
+      else k_fused_a_k2<false, ArithM, W2, MB2><<<(int)gg, W2 * 32, smem, st>>>(y, batch, CC, nullptr, 0);
     } else {
       if (inverse) k_fused_a_k2<true, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
       else k_fused_a_k2<false, ArithS, W, MB><<<(int)grid, W * 32, smem, st>>>(y, batch, CC, nullptr, 0);
