@@ -485,6 +485,19 @@ def run_gpu_arm(args):
             rec.add(sec, "tensor" + name, ms, 32 * tr.n * Bg, Bg, kernel=tcx.plan.kernel_name(name))
         del dg, zg, cg, og
         torch.cuda.empty_cache()
+        # complex CRT of the other benchmark rings: the fused_w schedule over complex doubles, the pass engine beside it
+        for mt, bt in ((1728, 131072), (2912, 65536), (11648, 16384)):
+            tw = CudaTensorComplex(mt)
+            cw = torch.randn(bt, tw.n, 1, dtype=torch.complex128, device="cuda")
+            for name in ("CRTC", "CRTInvC"):
+                ms = timed(lambda: capi.check(tw.plan.op(name, cw.data_ptr(), bt, stream)))
+                rec.add(sec, f"m={mt} tensor{name}", ms, 32 * tw.n * bt, bt, kernel=tw.plan.kernel_name(name))
+                tw.plan.force_generic(True)
+                ms = timed(lambda: capi.check(tw.plan.op(name, cw.data_ptr(), bt, stream)))
+                rec.add(sec, f"m={mt} tensor{name} (pass engine)", ms, 32 * tw.n * bt, bt, kernel="generic")
+                tw.plan.force_generic(False)
+            del cw
+            torch.cuda.empty_cache()
 
     # ---- configs[3]: SymmSHE ciphertext multiply + quadratic key switch (SymmSHE.hs:443-449 then :359-372; op sequence of
     # SURVEY.md section 3.5 with TrivGad over the two limbs, l = 2: 4 CRT, tensor product with mulG, CRTInv, decompose,

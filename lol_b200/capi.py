@@ -291,6 +291,15 @@ def fused_w_emulate(pps, qs, y: np.ndarray, inverse: bool = False) -> np.ndarray
     return out
 
 
+def fused_w_emulate_c(pps, y: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """lolb_fused_w_emulate_c: the same device-free replica over complex doubles; y = [n][k] complex128."""
+    pe = pe_array(pps)
+    out = np.ascontiguousarray(y, dtype=np.complex128).copy()
+    k = 1 if out.ndim == 1 else out.shape[-1]
+    check(lib().lolb_fused_w_emulate_c(pe.ctypes.data_as(_p), _i16(len(pe)), _i16(k), C.c_int(int(inverse)), out.ctypes.data_as(_p)))
+    return out
+
+
 def ext_index_table(pps, pps2, which: int) -> np.ndarray:
     """lolb_ext_index_table: one table of Tensor.hs:429-478 computed on the host (needs no GPU)."""
     pe, pe2 = pe_array(pps), pe_array(pps2)

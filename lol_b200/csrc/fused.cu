@@ -20,6 +20,10 @@ int fused_w_select(lolb_plan* pl, void** slot);
 void fused_w_release(void* slot);
 bool fused_w_available(const void* slot, bool inverse);
 int fused_w_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_wc_select(lolb_plan* pl, void** slot);
+void fused_wc_release(void* slot);
+bool fused_wc_available(const void* slot, bool inverse);
+int fused_wc_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st);
 
 // fused_pow2.cu
 int fused_pow2_select(lolb_plan* pl, void** slot);
@@ -50,7 +54,8 @@ struct FusedSet {
   void* pow2 = nullptr;   // m = 2^e CRT / CRT^-1, limb resident in shared memory (e <= 12, tupSize 3, ...)
   void* ac = nullptr;       // m = 14400 complex CRT / CRT^-1
   void* pow2_df = nullptr;  // m = 2^e CRT / CRT^-1, dataflow kernel with an L2 exchange ring (13 <= e <= 16)
-  void* w = nullptr;        // m = 2^a x odd prime powers (1728, 5184, 2912, 728, 3640, 2016) CRT / CRT^-1
+  void* w = nullptr;        // m = 2^a x odd prime powers (1728, 5184, 2912, 728, 3640, 2016, ...) CRT / CRT^-1
+  void* wc = nullptr;       // the same schedule over complex doubles (tensorCRTC / tensorCRTInvC of those indices)
 };
 FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
 }  // namespace
@@ -59,7 +64,9 @@ int fused_select(lolb_plan* pl)
 {
   if (pl->kind == PLAN_C) {
     if (!pl->fused) pl->fused = new FusedSet();
-    return fused_ac_select(pl, &set_of(pl)->ac);
+    int rc = fused_ac_select(pl, &set_of(pl)->ac);
+    if (!rc) rc = fused_wc_select(pl, &set_of(pl)->wc);
+    return rc;
   }
   if (pl->kind != PLAN_RQ) return LOLB_OK;
   if (!pl->fused) pl->fused = new FusedSet();
@@ -79,6 +86,7 @@ void fused_release(lolb_plan* pl)
   if (!s) return;
   fused_a_release(s->a);
   fused_w_release(s->w);
+  fused_wc_release(s->wc);
   fused_pow2_release(s->pow2);
   fused_pow2_df_release(s->pow2_df);
   fused_ac_release(s->ac);
@@ -94,6 +102,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
     if (!strcmp(op, "MulCRTInv") && fused_a_available(s->a, true)) return "fused_a+mul";
     if (!strcmp(op, "CRTC") && fused_ac_available(s->ac, false)) return "fused_ac";
     if (!strcmp(op, "CRTInvC") && fused_ac_available(s->ac, true)) return "fused_ac";
+    if (!strcmp(op, "CRTC") && fused_wc_available(s->wc, false)) return "fused_w";
+    if (!strcmp(op, "CRTInvC") && fused_wc_available(s->wc, true)) return "fused_w";
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
     if (!strcmp(op, "CRT") && fused_w_available(s->w, false)) return "fused_w";
@@ -141,7 +151,9 @@ int fused_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cu
 {
   const FusedSet* s = set_of(pl);
   if (!s) return LOLB_FUSED_UNAVAILABLE;
-  return fused_ac_crt(pl, s->ac, inverse, y, batch, st);
+  int rc = fused_ac_crt(pl, s->ac, inverse, y, batch, st);
+  if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_wc_crt(pl, s->wc, inverse, y, batch, st);
+  return rc;
 }
 
 int fused_line_rq(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)

@@ -20,6 +20,8 @@
 //               per lane straight from HBM, line(s), network, stores.  No shared memory, no barrier.
 //   k_fused_w2  (m = 2^a .. p_c^e_c) phase 1: thread <- one column along ic from HBM, line, u32 tile in shared memory;
 //               phase 2: group of L lanes <- one ic-row of the tile, middle line(s), network, stores.
+#include <complex>
+
 #include "fused.cuh"
 #include "numtheory.h"
 
@@ -52,9 +54,14 @@ struct WMod {
 
 // WS: a row of T terms needs 2 T q^2 < 2^32; residues lazily in [0, 2q), Barrett reduction
 struct WS {
+  typedef uint32_t T;       // value in registers / shared memory
+  typedef int64_t IO;       // value in HBM (the ABI)
   typedef uint32_t Acc;
+  static constexpr bool kZq = true;
   static constexpr int MAXT = 1 << 20;      // terms per reduction: unbounded (the host checks 2 T q^2 < 2^32 for the longest row)
   uint32_t q, q2, mu, nq;
+  WHD uint32_t add(uint32_t a, uint32_t b) const { return a + b; }                  // lazy: the caller folds or reduces
+  WHD uint32_t sub(uint32_t u, uint32_t t) const { return u + q2 - t; }             // u - t + 2q, t < 2q
   WHD WS(const WMod& M) : q(M.q), q2(M.q2), mu(M.r0), nq(0u - M.q) {}
   WHD Acc mul(uint32_t c, uint32_t v) const { return c * v; }
   WHD Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + c * v; }
@@ -73,9 +80,14 @@ struct WS6 : WS {
 
 // WM: odd q, 2 T q < 2^32; 64-bit accumulation, one Montgomery reduction per row, constants in Montgomery form
 struct WM {
+  typedef uint32_t T;
+  typedef int64_t IO;
   typedef uint64_t Acc;
+  static constexpr bool kZq = true;
   static constexpr int MAXT = 1 << 20;
   uint32_t q, q2, qinv, one;
+  WHD uint32_t add(uint32_t a, uint32_t b) const { return a + b; }
+  WHD uint32_t sub(uint32_t u, uint32_t t) const { return u + q2 - t; }
   WHD WM(const WMod& M) : q(M.q), q2(M.q2), qinv(M.r0), one(M.one) {}
   WHD Acc mul(uint32_t c, uint32_t v) const { return (uint64_t)c * v; }
   WHD Acc mad(Acc a, uint32_t c, uint32_t v) const { return a + (uint64_t)c * v; }
@@ -87,6 +99,26 @@ struct WM {
   }
   WHD uint32_t fold(uint32_t x) const { return w_min(x, x - q2); }
   WHD uint32_t canon(uint32_t x) const { return w_min(x, x - q); }
+};
+
+// WC: complex double (tensorCRTC / tensorCRTInvC, crt.cpp:583-598; class Complex, types.h:122-164).  The same schedule; no
+// reductions, no lazy ranges.  Rounding differs from the reference's evaluation order (FMA contraction, folded twiddles):
+// parity is to 1e-9 relative like every floating-point path.
+struct WC {
+  typedef double2 T;
+  typedef double2 IO;
+  typedef double2 Acc;
+  static constexpr bool kZq = false;
+  static constexpr int MAXT = 1 << 20;
+  WHD WC(const WMod&) {}
+  WHD Acc mul(double2 c, double2 v) const { return make_double2(c.x * v.x - c.y * v.y, c.x * v.y + c.y * v.x); }
+  WHD Acc mad(Acc a, double2 c, double2 v) const { return make_double2(a.x + (c.x * v.x - c.y * v.y), a.y + (c.x * v.y + c.y * v.x)); }
+  WHD Acc unit(double2 v) const { return v; }
+  WHD double2 red(Acc x) const { return x; }
+  WHD double2 fold(double2 x) const { return x; }
+  WHD double2 canon(double2 x) const { return x; }
+  WHD double2 add(double2 a, double2 b) const { return make_double2(a.x + b.x, a.y + b.y); }
+  WHD double2 sub(double2 a, double2 b) const { return make_double2(a.x - b.x, a.y - b.y); }
 };
 
 // ------------------------------------------------------------------ one odd prime power p^e: constant layout
@@ -114,8 +146,8 @@ struct PPT<1, 1> {      // "no prime power here"
 typedef PPT<1, 1> PPNone;
 
 // one radix-p round on digit DIG of the block index, values of the line at v[base + (i0 * (p-1) + cc) * STRIDE]
-template <class PPx, bool INV, int DIG, int STRIDE, int COFF, class AR, class CT, int NV>
-WHD void pp_round(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
+template <class PPx, bool INV, int DIG, int STRIDE, int COFF, class AR, class CT, class TV, int NV>
+WHD void pp_round(TV (&v)[NV], const int base, const CT& C, const AR& A)
 {
   constexpr int P = PPx::p, D = PPx::d, R = PPx::R;
   constexpr int NHI = ipw(P, R - 1 - DIG), NLO = ipw(P, DIG), WOFF = COFF + PPx::w_off(DIG);
@@ -125,7 +157,7 @@ WHD void pp_round(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
     for (int lo = 0; lo < NLO; lo++) {
 #pragma unroll
       for (int cc = 0; cc < D; cc++) {
-        uint32_t x[P], o[P];
+        TV x[P], o[P];
 #pragma unroll
         for (int a = 0; a < P; a++) x[a] = v[base + (((hi * P + a) * NLO + lo) * D + cc) * STRIDE];
 #pragma unroll
@@ -133,19 +165,19 @@ WHD void pp_round(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
           const bool all_ones = r == 0 && (!INV || hi == 0);      // DFT row 0 carries no twiddle in the forward direction
           const bool col0_one = INV || hi == 0;                   // the inverse twiddles its inputs: input 0 is never scaled
           if (all_ones) {
-            uint32_t s = x[0];
+            TV s = x[0];
 #pragma unroll
-            for (int a = 1; a < P; a++) s += x[a];
+            for (int a = 1; a < P; a++) s = A.add(s, x[a]);
             o[r] = A.red(A.unit(s));
           } else {
             typename AR::Acc acc = col0_one ? A.unit(x[0]) : A.mul(C.c[WOFF + (hi * P + r) * P], x[0]);
-            uint32_t part = 0;
+            TV part = TV();
 #pragma unroll
             for (int a = 1; a < P; a++) {
-              if (a % AR::MAXT == 0) { part = a == AR::MAXT ? A.red(acc) : A.fold(part + A.red(acc)); acc = A.mul(C.c[WOFF + (hi * P + r) * P + a], x[a]); }
+              if (a % AR::MAXT == 0) { part = a == AR::MAXT ? A.red(acc) : A.fold(A.add(part, A.red(acc))); acc = A.mul(C.c[WOFF + (hi * P + r) * P + a], x[a]); }
               else acc = A.mad(acc, C.c[WOFF + (hi * P + r) * P + a], x[a]);
             }
-            o[r] = P > AR::MAXT ? A.fold(part + A.red(acc)) : A.red(acc);
+            o[r] = P > AR::MAXT ? A.fold(A.add(part, A.red(acc))) : A.red(acc);
           }
         }
 #pragma unroll
@@ -155,23 +187,23 @@ WHD void pp_round(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
   }
 }
 
-template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, int NV>
-WHD void pp_blocks(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
+template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, class TV, int NV>
+WHD void pp_blocks(TV (&v)[NV], const int base, const CT& C, const AR& A)
 {
   constexpr int D = PPx::d, MP = PPx::mp;
 #pragma unroll
   for (int i0 = 0; i0 < MP; i0++) {
-    uint32_t o[D];
+    TV o[D];
 #pragma unroll
     for (int r = 0; r < D; r++) {
       typename AR::Acc acc = A.mul(C.c[COFF + (i0 * D + r) * D], v[base + (i0 * D) * STRIDE]);
-      uint32_t part = 0;
+      TV part = TV();
 #pragma unroll
       for (int cc = 1; cc < D; cc++) {
-        if (cc % AR::MAXT == 0) { part = cc == AR::MAXT ? A.red(acc) : A.fold(part + A.red(acc)); acc = A.mul(C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]); }
+        if (cc % AR::MAXT == 0) { part = cc == AR::MAXT ? A.red(acc) : A.fold(A.add(part, A.red(acc))); acc = A.mul(C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]); }
         else acc = A.mad(acc, C.c[COFF + (i0 * D + r) * D + cc], v[base + (i0 * D + cc) * STRIDE]);
       }
-      o[r] = D > AR::MAXT ? A.fold(part + A.red(acc)) : A.red(acc);
+      o[r] = D > AR::MAXT ? A.fold(A.add(part, A.red(acc))) : A.red(acc);
     }
 #pragma unroll
     for (int r = 0; r < D; r++) v[base + (i0 * D + r) * STRIDE] = o[r];
@@ -179,8 +211,8 @@ WHD void pp_blocks(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
 }
 
 // CRT_{p^e} / CRT_{p^e}^-1 on one line (ppcrt / ppcrtinv, crt.cpp:518-560)
-template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, int NV>
-WHD void pp_line(uint32_t (&v)[NV], const int base, const CT& C, const AR& A)
+template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, class TV, int NV>
+WHD void pp_line(TV (&v)[NV], const int base, const CT& C, const AR& A)
 {
   if constexpr (PPx::p > 1) {
     constexpr int R = PPx::R;
@@ -235,12 +267,18 @@ struct WShape {
 constexpr int kWLaneRows = 10;     // per-lane constants of the network, per column half (see build_lane_table)
 constexpr int kWThreads = 128;
 
-template <int NC>
+template <class T, int NC>
 struct WConsts {
   WMod mod;
-  const uint32_t* lane_tw;      // device [2 halves][kWLaneRows][32]
-  uint32_t c[NC];
+  const T* lane_tw;      // device [2 halves][kWLaneRows][32]
+  T c[NC];
 };
+
+__device__ __forceinline__ uint32_t w_shfl_xor(uint32_t v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+__device__ __forceinline__ double2 w_shfl_xor(double2 v, int mask)
+{
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+}
 
 // ------------------------------------------------------------------ the 2^a axis across L lanes
 // State: the lane holds NP pairs (v[2j], v[2j+1]).  Round on lane bit b: the lane keeps one value of each pair, swaps the
@@ -249,26 +287,27 @@ struct WConsts {
 //   forward: pair j, slot s  =  odd-axis row 2j + (l & 1),          column (s << (LOG-1)) | (l >> 1)
 //   inverse: pair j, slot s  =  odd-axis row 2j + (l >> (LOG-1)),   column 2 (l & (L/2 - 1)) + s
 template <bool INV, bool TRIVIAL, int NP, class AR>
-__device__ __forceinline__ void w_round(uint32_t (&v)[2 * NP], const int l, const int bit, const uint32_t tw, const AR& A)
+__device__ __forceinline__ void w_round(typename AR::T (&v)[2 * NP], const int l, const int bit, const typename AR::T tw, const AR& A)
 {
+  typedef typename AR::T T;
   const bool hi = (l >> bit) & 1;
 #pragma unroll
   for (int j = 0; j < NP; j++) {
-    const uint32_t send = hi ? v[2 * j] : v[2 * j + 1];
-    const uint32_t keep = hi ? v[2 * j + 1] : v[2 * j];
-    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+    const T send = hi ? v[2 * j] : v[2 * j + 1];
+    const T keep = hi ? v[2 * j + 1] : v[2 * j];
+    const T recv = w_shfl_xor(send, 1 << bit);
     if (TRIVIAL) {                 // every twiddle of the round is 1 (crt.cpp:92-106 skips i0 = 0)
-      const uint32_t u = hi ? recv : keep, t = hi ? keep : recv;
-      v[2 * j] = A.fold(u + t);
-      v[2 * j + 1] = A.fold(u + A.q2 - t);
+      const T u = hi ? recv : keep, t = hi ? keep : recv;
+      v[2 * j] = A.fold(A.add(u, t));
+      v[2 * j + 1] = A.fold(A.sub(u, t));
     } else if (!INV) {             // u + t is symmetric; the sign of u - t lives in the lane's twiddle (host: -tw for hi lanes)
-      v[2 * j] = A.fold(keep + recv);
-      v[2 * j + 1] = A.red(A.mul(tw, keep + A.q2 - recv));
+      v[2 * j] = A.fold(A.add(keep, recv));
+      v[2 * j + 1] = A.red(A.mul(tw, A.sub(keep, recv)));
     } else {
-      const uint32_t t = A.red(A.mul(tw, hi ? keep : recv));
-      const uint32_t u = hi ? recv : keep;
-      v[2 * j] = A.fold(u + t);
-      v[2 * j + 1] = A.fold(u + A.q2 - t);
+      const T t = A.red(A.mul(tw, hi ? keep : recv));
+      const T u = hi ? recv : keep;
+      v[2 * j] = A.fold(A.add(u, t));
+      v[2 * j + 1] = A.fold(A.sub(u, t));
     }
   }
 }
@@ -276,16 +315,17 @@ __device__ __forceinline__ void w_round(uint32_t (&v)[2 * NP], const int l, cons
 // last inverse round (lane bit 0) merged with the inverse crtTwiddle of the 2^a axis: the lane ends with columns 2c, 2c+1
 // whose twiddles a, b are per-lane constants:  a (u + tw t) = a u + (a tw) t,  b (u - tw t) = b u + (-b tw) t
 template <int NP, class AR>
-__device__ __forceinline__ void w_last_inv(uint32_t (&v)[2 * NP], const int l, const uint32_t a, const uint32_t atw, const uint32_t b,
-                                           const uint32_t nbtw, const AR& A)
+__device__ __forceinline__ void w_last_inv(typename AR::T (&v)[2 * NP], const int l, const typename AR::T a, const typename AR::T atw,
+                                           const typename AR::T b, const typename AR::T nbtw, const AR& A)
 {
+  typedef typename AR::T T;
   const bool hi = l & 1;
 #pragma unroll
   for (int j = 0; j < NP; j++) {
-    const uint32_t send = hi ? v[2 * j] : v[2 * j + 1];
-    const uint32_t keep = hi ? v[2 * j + 1] : v[2 * j];
-    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
+    const T send = hi ? v[2 * j] : v[2 * j + 1];
+    const T keep = hi ? v[2 * j + 1] : v[2 * j];
+    const T recv = w_shfl_xor(send, 1);
+    const T t = hi ? keep : recv, u = hi ? recv : keep;
     v[2 * j] = A.red(A.mad(A.mul(a, u), atw, t));
     v[2 * j + 1] = A.red(A.mad(A.mul(b, u), nbtw, t));
   }
@@ -295,7 +335,7 @@ __device__ __forceinline__ void w_last_inv(uint32_t (&v)[2 * NP], const int l, c
 // in); inverse [r] round r (r >= 1), [6] a, [7] a tw_0, [8] b, [9] -b tw_0.  LL = lane bits of the axis; TOP_IN_LANES: the
 // highest column bit is a lane bit (a <= 6), so its round carries no twiddle (crt.cpp:92-106 skips i0 = 0).
 template <int LL, bool TOP_IN_LANES, bool INV, int NP, class AR>
-__device__ __forceinline__ void w_network(uint32_t (&v)[2 * NP], const int l, const uint32_t (&lt)[kWLaneRows], const AR& A)
+__device__ __forceinline__ void w_network(typename AR::T (&v)[2 * NP], const int l, const typename AR::T (&lt)[kWLaneRows], const AR& A)
 {
   if constexpr (LL >= 1) {
     constexpr int NT = TOP_IN_LANES ? LL - 1 : LL;      // rounds with twiddles
@@ -304,9 +344,9 @@ __device__ __forceinline__ void w_network(uint32_t (&v)[2 * NP], const int l, co
       for (int i = 0; i < 2 * NP; i++) v[i] = A.red(A.mul(lt[0], v[i]));      // crtTwiddle (crt.cpp:43-58)
 #pragma unroll
       for (int r = 0; r < NT; r++) w_round<false, false, NP>(v, l, r, lt[1 + r], A);
-      if constexpr (TOP_IN_LANES) w_round<false, true, NP>(v, l, LL - 1, 0u, A);
+      if constexpr (TOP_IN_LANES) w_round<false, true, NP>(v, l, LL - 1, lt[0], A);
     } else {
-      if constexpr (TOP_IN_LANES && LL >= 2) w_round<true, true, NP>(v, l, LL - 1, 0u, A);
+      if constexpr (TOP_IN_LANES && LL >= 2) w_round<true, true, NP>(v, l, LL - 1, lt[0], A);
 #pragma unroll
       for (int r = NT - 1; r >= 1; r--) w_round<true, false, NP>(v, l, r, lt[r], A);
       w_last_inv<NP>(v, l, lt[6], lt[7], lt[8], lt[9], A);
@@ -316,13 +356,13 @@ __device__ __forceinline__ void w_network(uint32_t (&v)[2 * NP], const int l, co
 
 // the round on the column bit above the lanes (a = 7): both inputs sit in the same thread, the twiddle is 1
 template <int N2, class AR>
-__device__ __forceinline__ void w_top_round(uint32_t (&v0)[N2], uint32_t (&v1)[N2], const AR& A)
+__device__ __forceinline__ void w_top_round(typename AR::T (&v0)[N2], typename AR::T (&v1)[N2], const AR& A)
 {
 #pragma unroll
   for (int i = 0; i < N2; i++) {
-    const uint32_t u = v0[i], t = v1[i];
-    v0[i] = A.fold(u + t);
-    v1[i] = A.fold(u + A.q2 - t);
+    const typename AR::T u = v0[i], t = v1[i];
+    v0[i] = A.fold(A.add(u, t));
+    v1[i] = A.fold(A.sub(u, t));
   }
 }
 
@@ -343,10 +383,35 @@ __device__ __noinline__ uint32_t w_reduce_any(int64_t x, uint32_t q)      // non
 }
 
 // middle line(s) + network + store of one group's block of D2 * L coefficients; v[h] = the lane's values of column half h
+// the loads of one thread-task: NV values at `step` apart, all issued before the first use.  Zq: 64-bit words narrowed to the
+// 32-bit working range; one out-of-range word sends the task through `c % q` like the reference's constructor.
+template <class AR, int NV>
+__device__ __forceinline__ void w_load(typename AR::T (&v)[NV], const typename AR::IO* __restrict__ src, const size_t step, const bool live,
+                                       const uint32_t q)
+{
+  if constexpr (AR::kZq) {
+    uint32_t hi_or = 0, lo_max = 0;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int64_t raw = live ? __ldcs(src + (size_t)i * step) : 0;
+      v[i] = (uint32_t)raw;
+      hi_or |= (uint32_t)((uint64_t)raw >> 32);
+      lo_max = max(lo_max, v[i]);
+    }
+    if (hi_or != 0 || lo_max >= q) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) v[i] = w_reduce_any(src[(size_t)i * step], q);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = live ? __ldcs(src + (size_t)i * step) : make_double2(0.0, 0.0);
+  }
+}
+
 template <class SH, bool INV, class AR, int K>
-__device__ __forceinline__ void w_finish(uint32_t (&v)[SH::H][SH::D2], const int l, const uint32_t (&lt)[SH::H][kWLaneRows],
-                                         const WConsts<SH::NC>& C, const AR& A, int64_t* __restrict__ dst /* block base (+ limb) */,
-                                         const int k, const bool live)
+__device__ __forceinline__ void w_finish(typename AR::T (&v)[SH::H][SH::D2], const int l, const typename AR::T (&lt)[SH::H][kWLaneRows],
+                                         const WConsts<typename AR::T, SH::NC>& C, const AR& A,
+                                         typename AR::IO* __restrict__ dst /* block base (+ limb) */, const int k, const bool live)
 {
 #pragma unroll
   for (int h = 0; h < SH::H; h++) {
@@ -365,12 +430,17 @@ __device__ __forceinline__ void w_finish(uint32_t (&v)[SH::H][SH::D2], const int
     for (int h = 0; h < SH::H; h++) {
 #pragma unroll
       for (int j = 0; j < SH::NP; j++) {
-        const int64_t a = (int64_t)A.canon(v[h][2 * j]), b = (int64_t)A.canon(v[h][2 * j + 1]);
-        if (INV && K == 1 && SH::LL >= 1) {
-          __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h)), make_longlong2(a, b));
+        if constexpr (AR::kZq) {
+          const int64_t a = (int64_t)A.canon(v[h][2 * j]), b = (int64_t)A.canon(v[h][2 * j + 1]);
+          if (INV && K == 1 && SH::LL >= 1) {
+            __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h)), make_longlong2(a, b));
+          } else {
+            __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, a);
+            __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, b);
+          }
         } else {
-          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, a);
-          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, b);
+          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, v[h][2 * j]);
+          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, v[h][2 * j + 1]);
         }
       }
     }
@@ -379,56 +449,58 @@ __device__ __forceinline__ void w_finish(uint32_t (&v)[SH::H][SH::D2], const int
 
 // ------------------------------------------------------------------ m = 2^a p^e (p_b^e_b): a group of L lanes per element
 template <class SH, bool INV, class AR, int K>
-__global__ void __launch_bounds__(kWThreads, SH::MINB)
-k_fused_w1(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const int limb, const __grid_constant__ WConsts<SH::NC> C)
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : 1)
+k_fused_w1(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
+           const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
 {
+  typedef typename AR::T T;
   const int k = K ? K : k_rt;
   const AR A(C.mod);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = lane & (SH::LW - 1), sub = lane >> SH::LL;
-  uint32_t lt[1][kWLaneRows];
+  T lt[1][kWLaneRows];
 #pragma unroll
   for (int i = 0; i < kWLaneRows; i++) lt[0][i] = C.lane_tw[i * 32 + lane];
   const int64_t nwt = (batch + SH::GPW - 1) / SH::GPW;      // warp-tasks: GPW elements each
   for (int64_t wt = (int64_t)blockIdx.x * (kWThreads / 32) + warp; wt < nwt; wt += (int64_t)gridDim.x * (kWThreads / 32)) {
     const int64_t e = wt * SH::GPW + sub;
     const bool live = e < batch;
-    int64_t* ebase = y + (size_t)(live ? e : 0) * SH::N * k + limb;
-    const int64_t* src = ebase + (size_t)l * k;
-    uint32_t v[1][SH::D2];
-    uint32_t hi_or = 0, lo_max = 0;
-#pragma unroll
-    for (int i = 0; i < SH::D2; i++) {      // every load is issued before the first use
-      const int64_t raw = live ? __ldcs(src + (size_t)(i * SH::L) * k) : 0;
-      v[0][i] = (uint32_t)raw;
-      hi_or |= (uint32_t)((uint64_t)raw >> 32);
-      lo_max = max(lo_max, v[0][i]);
-    }
-    if (hi_or != 0 || lo_max >= C.mod.q) {
-#pragma unroll
-      for (int i = 0; i < SH::D2; i++) v[0][i] = w_reduce_any(src[(size_t)(i * SH::L) * k], C.mod.q);
-    }
+    typename AR::IO* ebase = y + (size_t)(live ? e : 0) * SH::N * k + limb;
+    T v[1][SH::D2];
+    w_load<AR>(v[0], ebase + (size_t)l * k, (size_t)SH::L * k, live, C.mod.q);
     w_finish<SH, INV, AR, K>(v, l, lt, C, A, ebase, k, live);
   }
 }
 
-// ------------------------------------------------------------------ m = 2^a (p_a^e_a) (p_b^e_b) p_c^e_c: two phases, u32 tile
+// ------------------------------------------------------------------ m = 2^a (p_a^e_a) (p_b^e_b) p_c^e_c: two phases, on-chip tile
+// (u32 words for Zq; complex doubles with a quarter of the elements per CTA, in dynamic shared memory)
+template <class SH, class AR> struct WTile {
+  static constexpr int EPB = AR::kZq ? SH::EPB : (SH::EPB >= 4 ? SH::EPB / 4 : 1);
+  static constexpr size_t BYTES = (size_t)EPB * SH::ROWS * SH::RS * sizeof(typename AR::T);
+};
+
 template <class SH, bool INV, class AR, int K>
-__global__ void __launch_bounds__(kWThreads, SH::MINB)
-k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const int limb, const __grid_constant__ WConsts<SH::NC> C)
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : 1)
+k_fused_w2(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
+           const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
 {
   typedef typename SH::PC PC;
-  constexpr int EPB = SH::EPB, COLS = SH::COLS, ROWS = SH::ROWS, RS = SH::RS, N = SH::N;
+  typedef typename AR::T T;
+  constexpr int EPB = WTile<SH, AR>::EPB, COLS = SH::COLS, ROWS = SH::ROWS, RS = SH::RS, N = SH::N;
   const int k = K ? K : k_rt;
-  __shared__ uint32_t tile[EPB * ROWS * RS];
+  extern __shared__ __align__(16) unsigned char w2_smem[];
+  T* tile = reinterpret_cast<T*>(w2_smem);
   const AR A(C.mod);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = lane & (SH::LW - 1), sub = lane >> SH::LL;
-  uint32_t lt[SH::H][kWLaneRows];
+  T lt[SH::H][kWLaneRows];
+  auto load_lane_table = [&]() {
 #pragma unroll
-  for (int h = 0; h < SH::H; h++)
+    for (int h = 0; h < SH::H; h++)
 #pragma unroll
-    for (int i = 0; i < kWLaneRows; i++) lt[h][i] = C.lane_tw[(h * kWLaneRows + i) * 32 + lane];
+      for (int i = 0; i < kWLaneRows; i++) lt[h][i] = C.lane_tw[(h * kWLaneRows + i) * 32 + lane];
+  };
+  if constexpr (AR::kZq) load_lane_table();      // complex: 40 registers per column half, loaded where phase 2 starts instead
   const int64_t ngroups = (batch + EPB - 1) / EPB;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t e0 = g * EPB;
@@ -436,23 +508,11 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
     // ---------------- phase 1: the last prime power; thread-task = (element slot, column), coefficients at stride COLS
     for (int t = threadIdx.x; t < cnt * COLS; t += kWThreads) {
       const int slot = t / COLS, col = t - slot * COLS;
-      const int64_t* src = y + ((size_t)(e0 + slot) * N + col) * k + limb;
-      uint32_t v[ROWS];
-      uint32_t hi_or = 0, lo_max = 0;
-#pragma unroll
-      for (int i = 0; i < ROWS; i++) {
-        const int64_t raw = __ldcs(src + (size_t)(i * COLS) * k);
-        v[i] = (uint32_t)raw;
-        hi_or |= (uint32_t)((uint64_t)raw >> 32);
-        lo_max = max(lo_max, v[i]);
-      }
-      if (hi_or != 0 || lo_max >= C.mod.q) {
-#pragma unroll
-        for (int i = 0; i < ROWS; i++) v[i] = w_reduce_any(src[(size_t)(i * COLS) * k], C.mod.q);
-      }
+      T v[ROWS];
+      w_load<AR>(v, y + ((size_t)(e0 + slot) * N + col) * k + limb, (size_t)COLS * k, true, C.mod.q);
       pp_line<PC, INV, 1, SH::OFF_C>(v, 0, C, A);
       const int cd = col / SH::SUB, cx = col - cd * SH::SUB;
-      uint32_t* dst = tile + slot * ROWS * RS + cd * SH::SRS + cx;
+      T* dst = tile + slot * ROWS * RS + cd * SH::SRS + cx;
 #pragma unroll
       for (int i = 0; i < ROWS; i++) dst[i * RS] = v[i];
     }
@@ -461,8 +521,8 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
     if constexpr (SH::DD > 1) {
       for (int t = threadIdx.x; t < cnt * ROWS * SH::SUB; t += kWThreads) {
         const int sr = t / SH::SUB, x = t - sr * SH::SUB;      // sr = slot * ROWS + ic
-        uint32_t* line = tile + sr * RS + x;
-        uint32_t v[SH::DD];
+        T* line = tile + sr * RS + x;
+        T v[SH::DD];
 #pragma unroll
         for (int i = 0; i < SH::DD; i++) v[i] = line[i * SH::SRS];
         pp_line<typename SH::PD, INV, 1, SH::OFF_D>(v, 0, C, A);
@@ -474,19 +534,20 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
     // ---------------- phase 2: group-task = (element slot, ic, id); L lanes x D2 values, middle lines + network
     constexpr int BLOCKS = ROWS * SH::DD;      // phase-2 blocks per element
     const int ntask = cnt * BLOCKS;
+    if constexpr (!AR::kZq) load_lane_table();
     for (int t0 = warp * SH::GPW; t0 < ntask; t0 += (kWThreads / 32) * SH::GPW) {      // warp-uniform trip count
       const int t = t0 + sub;
       const bool live = t < ntask;
       const int tt = live ? t : 0;
       const int slot = tt / BLOCKS, blk = tt - slot * BLOCKS;      // blk = ic * DD + id: the block's position in the element
       const int row = blk / SH::DD, bd = blk - row * SH::DD;
-      const uint32_t* srow = tile + (slot * ROWS + row) * RS + bd * SH::SRS + l;
-      uint32_t v[SH::H][SH::D2];
+      const T* srow = tile + (slot * ROWS + row) * RS + bd * SH::SRS + l;
+      T v[SH::H][SH::D2];
 #pragma unroll
       for (int h = 0; h < SH::H; h++)
 #pragma unroll
         for (int i = 0; i < SH::D2; i++) v[h][i] = srow[i * SH::L + h * SH::LW];
-      int64_t* dst = y + ((size_t)(e0 + slot) * N + (size_t)blk * SH::SUB) * k + limb;
+      typename AR::IO* dst = y + ((size_t)(e0 + slot) * N + (size_t)blk * SH::SUB) * k + limb;
       w_finish<SH, INV, AR, K>(v, l, lt, C, A, dst, k, live);
     }
     __syncthreads();
@@ -495,7 +556,7 @@ k_fused_w2(int64_t* __restrict__ y, const int64_t batch, const int k_rt, const i
 
 // ------------------------------------------------------------------ host: constants from the plan's root tables
 
-enum WClass { WC_NONE = 0, WC_S, WC_M, WC_S6 };
+enum WClass { WC_NONE = 0, WC_S, WC_M, WC_S6, WC_C };
 
 inline WClass w_class(uint64_t q, int pmax)
 {
@@ -504,6 +565,27 @@ inline WClass w_class(uint64_t q, int pmax)
   if ((q & 1) && 2 * (uint64_t)pmax * q < ((uint64_t)1 << 32)) return WC_M;
   return WC_NONE;
 }
+
+// the field the constants are computed in on the host, and the type they are stored as
+struct FieldZq {
+  typedef uint64_t V;
+  typedef uint32_t Out;
+  uint64_t q;
+  V one() const { return 1; }
+  V mul(V a, V b) const { return mulmod64(a, b, q); }
+  V sub(V a, V b) const { return (a + q - b) % q; }
+  V neg(V a) const { return (q - a) % q; }
+  Out out(V a) const { return (uint32_t)a; }
+};
+struct FieldC {
+  typedef std::complex<double> V;
+  typedef double2 Out;
+  V one() const { return V(1.0, 0.0); }
+  V mul(V a, V b) const { return V(a.real() * b.real() - a.imag() * b.imag(), a.real() * b.imag() + a.imag() * b.real()); }
+  V sub(V a, V b) const { return a - b; }
+  V neg(V a) const { return -a; }
+  Out out(V a) const { return make_double2(a.real(), a.imag()); }
+};
 
 struct RootTab {      // root table of one prime power for one limb (forward or inverse roots), canonical
   const std::vector<int64_t>* tab;
@@ -517,27 +599,38 @@ struct RootTab {      // root table of one prime power for one limb (forward or 
     return (uint64_t)v;
   }
 };
+struct RootTabC {     // the same over C: the plan's cis tables (CRTrans.hs:88-95)
+  const std::vector<lolb_complex>* tab;
+  int k, limb;
+  int64_t pp;
+  std::complex<double> operator()(int64_t j) const
+  {
+    const lolb_complex c = (*tab)[(size_t)(((j % pp) + pp) % pp) * k + limb];
+    return std::complex<double>(c.real, c.imag);
+  }
+};
 
 // constants of prime power (p, e) into out[0 .. n_consts): layout of PPT; `scale` multiplies the inverse block matrices
-void build_pp_consts(int p, int e, bool inverse, const RootTab& T, uint64_t scale, uint32_t* out)
+template <class FLD, class TAB>
+void build_pp_consts(int p, int e, bool inverse, const FLD& f, const TAB& T, typename FLD::V scale, typename FLD::Out* out)
 {
-  const uint64_t q = T.q;
+  typedef typename FLD::V V;
   const int d = p - 1, R = e - 1;
   const int64_t mp = ipow64(p, e - 1);
   size_t o = 0;
   for (int64_t i0 = 0; i0 < mp; i0++)
     for (int r = 0; r < d; r++)
       for (int c = 0; c < d; c++) {
-        uint64_t v;
+        V v;
         if (!inverse) {        // crtTwiddle(i0, r) . w_p^((r+1) c)
-          const uint64_t tw = i0 ? T(digit_rev(p, R, i0) * (r + 1)) : 1;
-          v = mulmod64(tw, T(mp * (((int64_t)(r + 1) * c) % p)), q);
+          const V tw = i0 ? T(digit_rev(p, R, i0) * (r + 1)) : f.one();
+          v = f.mul(tw, T(mp * (((int64_t)(r + 1) * c) % p)));
         } else {               // (w^-(r (c+1)) - w^(c+1)) . crtTwiddle(i0, c) . scale, T = inverse roots (crt.cpp:369-398)
-          const uint64_t tw = i0 ? T(digit_rev(p, R, i0) * (c + 1)) : 1;
-          const uint64_t mat = (T(mp * (((int64_t)r * (c + 1)) % p)) + q - T(mp * (p - c - 1))) % q;
-          v = mulmod64(mulmod64(tw, mat, q), scale % q, q);
+          const V tw = i0 ? T(digit_rev(p, R, i0) * (c + 1)) : f.one();
+          const V mat = f.sub(T(mp * (((int64_t)r * (c + 1)) % p)), T(mp * (p - c - 1)));
+          v = f.mul(f.mul(tw, mat), scale);
         }
-        out[o++] = (uint32_t)v;
+        out[o++] = f.out(v);
       }
   for (int dig = 0; dig < R; dig++) {
     const int64_t nhi = ipow64(p, R - 1 - dig), stride = ipow64(p, dig + 1);
@@ -545,47 +638,48 @@ void build_pp_consts(int p, int e, bool inverse, const RootTab& T, uint64_t scal
       for (int r = 0; r < p; r++)
         for (int a = 0; a < p; a++) {
           const int x = inverse ? a : r;      // the twiddled index: outputs (forward, after dftp) / inputs (inverse, before dftp)
-          const uint64_t tw = (hi && x) ? T(digit_rev(p, R - 1 - dig, hi) * x * stride) : 1;
-          out[o++] = (uint32_t)mulmod64(tw, T(mp * (((int64_t)r * a) % p)), q);
+          const V tw = (hi && x) ? T(digit_rev(p, R - 1 - dig, hi) * x * stride) : f.one();
+          out[o++] = f.out(f.mul(tw, T(mp * (((int64_t)r * a) % p))));
         }
   }
 }
 
 // per-lane constants of the network for 2^a (a >= 2): out[2 column halves][kWLaneRows][32], the group pattern repeated across
 // the warp.  LOG = a - 1 column bits, LL = min(LOG, 5) of them lane bits; with a = 7 the top bit is the column half h.
-void build_lane_table(int a_exp, bool inverse, const RootTab& T, uint32_t* out)
+template <class FLD, class TAB>
+void build_lane_table(int a_exp, bool inverse, const FLD& f, const TAB& T, typename FLD::Out* out)
 {
-  const uint64_t q = T.q;
+  typedef typename FLD::V V;
   const int LOG = a_exp >= 2 ? a_exp - 1 : 0, LL = LOG > 5 ? 5 : LOG, LW = 1 << LL, H = (1 << LOG) / LW;
-  for (int i = 0; i < 2 * kWLaneRows * 32; i++) out[i] = 1;
+  for (int i = 0; i < 2 * kWLaneRows * 32; i++) out[i] = f.out(f.one());
   if (LOG == 0) return;
   const int NT = H == 1 ? LL - 1 : LL;      // rounds with twiddles among the lane rounds (the top column bit carries none)
   for (int h = 0; h < H; h++) {
-    uint32_t* o = out + (size_t)h * kWLaneRows * 32;
+    typename FLD::Out* o = out + (size_t)h * kWLaneRows * 32;
     for (int lane = 0; lane < 32; lane++) {
       const int l = lane & (LW - 1);
       // dftTwiddle of the round on column bit r for the butterfly whose higher column bits are `hi_bits` (crt.cpp:92-106)
-      auto round_tw = [&](int r, int hi_bits) -> uint64_t {
-        return hi_bits ? T(digit_rev(2, LOG - 1 - r, hi_bits) * ((int64_t)2 << r)) : 1;
+      auto round_tw = [&](int r, int hi_bits) -> V {
+        return hi_bits ? T(digit_rev(2, LOG - 1 - r, hi_bits) * ((int64_t)2 << r)) : f.one();
       };
       if (!inverse) {
         const int col = h * LW + l;
-        o[0 * 32 + lane] = (uint32_t)(col ? T(digit_rev(2, LOG, col)) : 1);      // crtTwiddle of the lane's column
+        o[0 * 32 + lane] = f.out(col ? T(digit_rev(2, LOG, col)) : f.one());      // crtTwiddle of the lane's column
         for (int r = 0; r < NT; r++) {
-          const uint64_t tw = round_tw(r, (h << (LL - 1 - r)) | (l >> (r + 1)));
+          const V tw = round_tw(r, (h << (LL - 1 - r)) | (l >> (r + 1)));
           // lanes whose bit r is set hold (t, u) instead of (u, t): they multiply (t - u) by -tw
-          o[(1 + r) * 32 + lane] = (uint32_t)(((l >> r) & 1) ? (q - tw) % q : tw);
+          o[(1 + r) * 32 + lane] = f.out(((l >> r) & 1) ? f.neg(tw) : tw);
         }
       } else {
         for (int r = 1; r < NT; r++)
-          o[r * 32 + lane] = (uint32_t)round_tw(r, (h << (LL - 1 - r)) | ((l >> r) & ((1 << (LL - 1 - r)) - 1)));
-        const uint64_t tw0 = round_tw(0, (h << (LL - 1)) | (l & ((1 << (LL - 1)) - 1)));
+          o[r * 32 + lane] = f.out(round_tw(r, (h << (LL - 1 - r)) | ((l >> r) & ((1 << (LL - 1 - r)) - 1))));
+        const V tw0 = round_tw(0, (h << (LL - 1)) | (l & ((1 << (LL - 1)) - 1)));
         const int col = 2 * (l & (LW / 2 - 1)) + h * LW;
-        const uint64_t ca = col ? T(digit_rev(2, LOG, col)) : 1, cb = T(digit_rev(2, LOG, col + 1));
-        o[6 * 32 + lane] = (uint32_t)ca;
-        o[7 * 32 + lane] = (uint32_t)mulmod64(ca, tw0, q);
-        o[8 * 32 + lane] = (uint32_t)cb;
-        o[9 * 32 + lane] = (uint32_t)((q - mulmod64(cb, tw0, q)) % q);
+        const V ca = col ? T(digit_rev(2, LOG, col)) : f.one(), cb = T(digit_rev(2, LOG, col + 1));
+        o[6 * 32 + lane] = f.out(ca);
+        o[7 * 32 + lane] = f.out(f.mul(ca, tw0));
+        o[8 * 32 + lane] = f.out(cb);
+        o[9 * 32 + lane] = f.out(f.neg(f.mul(cb, tw0)));
       }
     }
   }
@@ -631,15 +725,18 @@ typedef WShape<0, PPT<3, 2>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 4, 4> SH_9_5_7_13
 
 constexpr int kNumShapes = 10;
 
-struct FusedW {
+template <class T>
+struct FusedWT {
   int shape = -1;
   bool ok_fwd = false, ok_inv = false;
-  std::vector<int> cls;                          // WClass per limb
-  std::vector<std::vector<uint32_t>> cf, ci;     // per limb: flat constants (already in the limb's representation)
+  std::vector<int> cls;                   // WClass per limb
+  std::vector<std::vector<T>> cf, ci;     // per limb: flat constants (already in the limb's representation)
   std::vector<WMod> mod;
-  uint32_t* d_lane = nullptr;                    // [k][2 directions][2 column halves][kWLaneRows][32]
-  std::vector<uint32_t> h_lane;
+  T* d_lane = nullptr;                    // [k][2 directions][2 column halves][kWLaneRows][32]
+  std::vector<T> h_lane;
 };
+typedef FusedWT<uint32_t> FusedW;
+typedef FusedWT<double2> FusedWC;      // the complex plans (tensorCRTC / tensorCRTInvC)
 
 bool shape_matches(const lolb_plan* pl, const WShapeId& id, int* pmax)
 {
@@ -661,13 +758,38 @@ const WShapeId kShapeIds[kNumShapes] = {shape_id<SH_64_27>(), shape_id<SH_64_81>
                                         shape_id<SH_128_7_13>(), shape_id<SH_4_3_5_7_13>(), shape_id<SH_9_5_7_13>()};
 
 // host-side constants of one plan (no CUDA calls): shared by fused_w_select and the device-free emulation
+template <class FW, class FLD, class MKTAB>
+void fill_consts(const lolb_plan* pl, FW* F, int t, int dir, const FLD& f, typename FLD::V scale, const MKTAB& mktab)
+{
+  const WShapeId& id = kShapeIds[F->shape];
+  const int npe = (int)pl->pe.size(), first_odd = id.a > 0 ? 1 : 0;
+  auto& out = dir ? F->ci[t] : F->cf[t];
+  for (int i = first_odd; i < npe; i++) {      // order = (PA, PB, PD, PC) = the plan's odd prime powers in order
+    const int p = pl->pe[i].prime, e = pl->pe[i].exponent;
+    const size_t n_m1 = (size_t)ipow64(p, e - 1) * (p - 1) * (p - 1);
+    size_t n_w = 0;
+    for (int dig = 0; dig < e - 1; dig++) n_w += (size_t)ipow64(p, e - 2 - dig) * p * p;
+    const size_t at = out.size();
+    out.resize(at + n_m1 + n_w);
+    build_pp_consts(p, e, dir != 0, f, mktab(i, ipow64(p, e)), i == first_odd ? scale : f.one(), out.data() + at);      // mhat^-1 rides on the first odd axis
+  }
+  if (id.a >= 2)
+    build_lane_table(id.a, dir != 0, f, mktab(0, ipow64(2, id.a)), F->h_lane.data() + ((size_t)t * 2 + dir) * 2 * kWLaneRows * 32);
+}
+
+int find_shape(const lolb_plan* pl, int* pmax)
+{
+  for (int s = 0; s < kNumShapes; s++)
+    if (shape_matches(pl, kShapeIds[s], pmax)) return s;
+  return -1;
+}
+
 int build_fused_w(const lolb_plan* pl, FusedW* F)
 {
   F->shape = -1;
   if (pl->kind != PLAN_RQ) return LOLB_OK;
   int pmax = 0;
-  for (int s = 0; s < kNumShapes; s++)
-    if (shape_matches(pl, kShapeIds[s], &pmax)) { F->shape = s; break; }
+  F->shape = find_shape(pl, &pmax);
   if (F->shape < 0) return LOLB_OK;
   const int k = pl->k;
   F->cls.assign(k, WC_NONE);
@@ -675,7 +797,6 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
     F->cls[t] = w_class((uint64_t)pl->qs[t], pmax);
     if (F->cls[t] == WC_NONE) { F->shape = -1; return LOLB_OK; }
   }
-  const WShapeId& id = kShapeIds[F->shape];
   const int npe = (int)pl->pe.size();
   F->ok_fwd = pl->ru.size() == (size_t)npe;
   F->ok_inv = pl->ruinv.size() == (size_t)npe && (int)pl->mhatinv.size() == k;
@@ -683,33 +804,18 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
   F->ci.assign(k, {});
   F->mod.assign(k, WMod{});
   F->h_lane.assign((size_t)k * 2 * 2 * kWLaneRows * 32, 1u);
-  const int first_odd = id.a > 0 ? 1 : 0;
   for (int t = 0; t < k; t++) {
     const uint64_t q = (uint64_t)pl->qs[t];
     w_mod_consts(q, F->cls[t], &F->mod[t]);
     for (int dir = 0; dir < 2; dir++) {
       if (dir == 0 ? !F->ok_fwd : !F->ok_inv) continue;
       const auto& tabs = dir ? pl->ruinv : pl->ru;
-      std::vector<uint32_t>& out = dir ? F->ci[t] : F->cf[t];
       uint64_t scale = 1;
       if (dir) { int64_t s = pl->mhatinv[t] % (int64_t)q; if (s < 0) s += q; scale = (uint64_t)s; }
-      for (int i = first_odd; i < npe; i++) {      // order = (PA, PB, PD, PC) = the plan's odd prime powers in order
-        const int p = pl->pe[i].prime, e = pl->pe[i].exponent;
-        RootTab T{&tabs[i], k, t, ipow64(p, e), q};
-        const size_t n_m1 = (size_t)ipow64(p, e - 1) * (p - 1) * (p - 1);
-        size_t n_w = 0;
-        for (int dig = 0; dig < e - 1; dig++) n_w += (size_t)ipow64(p, e - 2 - dig) * p * p;
-        const size_t at = out.size();
-        out.resize(at + n_m1 + n_w);
-        build_pp_consts(p, e, dir != 0, T, i == first_odd ? scale : 1, out.data() + at);      // mhat^-1 rides on the first odd axis
-      }
-      uint32_t* lane = F->h_lane.data() + ((size_t)t * 2 + dir) * 2 * kWLaneRows * 32;
-      if (id.a >= 2) {
-        RootTab T2{&tabs[0], k, t, ipow64(2, id.a), q};
-        build_lane_table(id.a, dir != 0, T2, lane);
-      }
+      fill_consts(pl, F, t, dir, FieldZq{q}, scale, [&](int i, int64_t pp) { return RootTab{&tabs[i], k, t, pp, q}; });
       if (F->cls[t] == WC_M) {
-        for (auto& c : out) c = w_mont(c, q);
+        uint32_t* lane = F->h_lane.data() + ((size_t)t * 2 + dir) * 2 * kWLaneRows * 32;
+        for (auto& c : (dir ? F->ci[t] : F->cf[t])) c = w_mont(c, q);
         for (int i = 0; i < 2 * kWLaneRows * 32; i++) lane[i] = w_mont(lane[i], q);
       }
     }
@@ -717,20 +823,52 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
   return LOLB_OK;
 }
 
-template <class SH, bool INV, class AR, int K>
-int launch_w(const lolb_plan* pl, const FusedW* F, int limb, int64_t* y, int64_t batch, cudaStream_t st)
+int build_fused_wc(const lolb_plan* pl, FusedWC* F)
 {
-  WConsts<SH::NC> C;
+  F->shape = -1;
+  if (pl->kind != PLAN_C) return LOLB_OK;
+  int pmax = 0;
+  F->shape = find_shape(pl, &pmax);
+  if (F->shape < 0) return LOLB_OK;
+  const int k = pl->k, npe = (int)pl->pe.size();
+  F->cls.assign(k, WC_C);
+  F->ok_fwd = pl->cru.size() == (size_t)npe;
+  F->ok_inv = pl->cruinv.size() == (size_t)npe;
+  F->cf.assign(k, {});
+  F->ci.assign(k, {});
+  F->mod.assign(k, WMod{});
+  F->h_lane.assign((size_t)k * 2 * 2 * kWLaneRows * 32, make_double2(1.0, 0.0));
+  for (int t = 0; t < k; t++)
+    for (int dir = 0; dir < 2; dir++) {
+      if (dir == 0 ? !F->ok_fwd : !F->ok_inv) continue;
+      const auto& tabs = dir ? pl->cruinv : pl->cru;
+      const std::complex<double> scale = dir ? std::complex<double>(pl->c_mhatinv[t].x, pl->c_mhatinv[t].y) : std::complex<double>(1.0, 0.0);
+      fill_consts(pl, F, t, dir, FieldC{}, scale, [&](int i, int64_t pp) { return RootTabC{&tabs[i], k, t, pp}; });
+    }
+  return LOLB_OK;
+}
+
+template <class SH, bool INV, class AR, int K>
+int launch_w(const lolb_plan* pl, const FusedWT<typename AR::T>* F, int limb, typename AR::IO* y, int64_t batch, cudaStream_t st)
+{
+  typedef typename AR::T T;
+  WConsts<T, SH::NC> C;
   C.mod = F->mod[limb];
   C.lane_tw = F->d_lane + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
-  const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
+  const std::vector<T>& src = INV ? F->ci[limb] : F->cf[limb];
   if ((int)src.size() != SH::OFF_C + SH::PC::n_consts) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
   for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
-  int64_t grid = (int64_t)pl->num_sms * SH::MINB;
+  int64_t grid = (int64_t)pl->num_sms * (AR::kZq ? SH::MINB : 2);
   if constexpr (SH::TWO_PHASE) {
-    const int64_t groups = (batch + SH::EPB - 1) / SH::EPB;
+    constexpr int EPB = WTile<SH, AR>::EPB;
+    constexpr size_t BYTES = WTile<SH, AR>::BYTES;
+    const int64_t groups = (batch + EPB - 1) / EPB;
     if (grid > groups) grid = groups;
-    k_fused_w2<SH, INV, AR, K><<<(int)grid, kWThreads, 0, st>>>(y, batch, pl->k, limb, C);
+    if (BYTES > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_fused_w2<SH, INV, AR, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BYTES);
+      if (e != cudaSuccess) return cuda_fail(e, "k_fused_w2 shared memory");
+    }
+    k_fused_w2<SH, INV, AR, K><<<(int)grid, kWThreads, BYTES, st>>>(y, batch, pl->k, limb, C);
   } else {
     const int64_t ctas = (batch + (kWThreads / 32) * SH::GPW - 1) / ((kWThreads / 32) * SH::GPW);
     if (grid > ctas) grid = ctas;
@@ -739,6 +877,18 @@ int launch_w(const lolb_plan* pl, const FusedW* F, int limb, int64_t* y, int64_t
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_fused_w");
   count_launch();
+  return LOLB_OK;
+}
+
+template <class SH>
+int launch_shape_c(const lolb_plan* pl, const FusedWC* F, bool inverse, double2* y, int64_t batch, cudaStream_t st)
+{
+  for (int t = 0; t < pl->k; t++) {
+    const bool k1 = pl->k == 1;
+    int rc = inverse ? (k1 ? launch_w<SH, true, WC, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WC, 0>(pl, F, t, y, batch, st))
+                     : (k1 ? launch_w<SH, false, WC, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WC, 0>(pl, F, t, y, batch, st));
+    if (rc) return rc;
+  }
   return LOLB_OK;
 }
 
@@ -768,22 +918,29 @@ int launch_shape(const lolb_plan* pl, const FusedW* F, bool inverse, int64_t* y,
 // ------------------------------------------------------------------ device-free emulation (CPU tests of the constants, the
 // line code above compiled for the host, and a lane-by-lane replica of the network with the same ownership rules)
 template <class SH, bool INV, class AR>
-void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
+void emulate_shape(const FusedWT<typename AR::T>* F, int limb, int k, typename AR::IO* y)
 {
-  WConsts<SH::NC> C;
+  typedef typename AR::T T;
+  WConsts<T, SH::NC> C;
   C.mod = F->mod[limb];
   C.lane_tw = nullptr;
-  const std::vector<uint32_t>& src = INV ? F->ci[limb] : F->cf[limb];
+  const std::vector<T>& src = INV ? F->ci[limb] : F->cf[limb];
   for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
-  const uint32_t* lane_tab = F->h_lane.data() + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
+  const T* lane_tab = F->h_lane.data() + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
   const AR A(C.mod);
   constexpr int L = SH::L, D2 = SH::D2, NP = SH::NP, COLS = SH::COLS, ROWS = SH::ROWS;
-  std::vector<uint32_t> tile((size_t)SH::N);
-  const uint32_t q = C.mod.q;
-  auto ld = [&](int j) { int64_t r = y[(size_t)j * k + limb] % (int64_t)q; if (r < 0) r += q; return (uint32_t)r; };
+  std::vector<T> tile((size_t)SH::N);
+  auto ld = [&](int j) -> T {
+    if constexpr (AR::kZq) {
+      const T q = C.mod.q;
+      int64_t r = y[(size_t)j * k + limb] % (int64_t)q;
+      if (r < 0) r += q;
+      return (T)r;
+    } else return y[(size_t)j * k + limb];
+  };
   // phase 1
   for (int col = 0; col < COLS; col++) {
-    uint32_t v[ROWS];
+    T v[ROWS];
     for (int i = 0; i < ROWS; i++) v[i] = ld(i * COLS + col);
     pp_line<typename SH::PC, INV, 1, SH::OFF_C>(v, 0, C, A);
     for (int i = 0; i < ROWS; i++) tile[(size_t)i * COLS + col] = v[i];
@@ -793,7 +950,7 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
   if (DD > 1) {
     for (int ic = 0; ic < ROWS; ic++)
       for (int x = 0; x < SUB; x++) {
-        uint32_t v[DD];
+        T v[DD];
         for (int i = 0; i < DD; i++) v[i] = tile[(size_t)ic * COLS + i * SUB + x];
         pp_line<typename SH::PD, INV, 1, SH::OFF_D>(v, 0, C, A);
         for (int i = 0; i < DD; i++) tile[(size_t)ic * COLS + i * SUB + x] = v[i];
@@ -804,7 +961,7 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
   constexpr bool TOP_IN_LANES = H == 1;
   constexpr int NT = TOP_IN_LANES ? LL - 1 : LL;
   for (int row = 0; row < ROWS * DD; row++) {
-    uint32_t v[H][LW][D2];
+    T v[H][LW][D2];
     for (int h = 0; h < H; h++)
       for (int l = 0; l < LW; l++) {
         for (int i = 0; i < D2; i++) v[h][l][i] = tile[(size_t)row * SUB + i * L + h * LW + l];
@@ -815,33 +972,33 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
     auto top_round = [&]() {
       for (int l = 0; l < LW; l++)
         for (int i = 0; i < D2; i++) {
-          const uint32_t u = v[0][l][i], t = v[H - 1][l][i];
-          v[0][l][i] = A.fold(u + t);
-          v[H - 1][l][i] = A.fold(u + A.q2 - t);
+          const T u = v[0][l][i], t = v[H - 1][l][i];
+          v[0][l][i] = A.fold(A.add(u, t));
+          v[H - 1][l][i] = A.fold(A.sub(u, t));
         }
     };
     auto round = [&](int h, bool trivial, int bit, int row_tw) {
-      uint32_t nv[LW][D2];
+      T nv[LW][D2];
       for (int l = 0; l < LW; l++) {
         const bool hi = (l >> bit) & 1;
         const int partner = l ^ (1 << bit);
         for (int j = 0; j < NP; j++) {
-          const uint32_t keep = hi ? v[h][l][2 * j + 1] : v[h][l][2 * j];
+          const T keep = hi ? v[h][l][2 * j + 1] : v[h][l][2 * j];
           const bool phi_ = (partner >> bit) & 1;
-          const uint32_t recv = phi_ ? v[h][partner][2 * j] : v[h][partner][2 * j + 1];      // what the partner sends
-          const uint32_t tw = trivial ? 0u : lt(h, row_tw, l);
+          const T recv = phi_ ? v[h][partner][2 * j] : v[h][partner][2 * j + 1];      // what the partner sends
+          const T tw = lt(h, row_tw, l);
           if (trivial) {
-            const uint32_t u = hi ? recv : keep, t = hi ? keep : recv;
-            nv[l][2 * j] = A.fold(u + t);
-            nv[l][2 * j + 1] = A.fold(u + A.q2 - t);
+            const T u = hi ? recv : keep, t = hi ? keep : recv;
+            nv[l][2 * j] = A.fold(A.add(u, t));
+            nv[l][2 * j + 1] = A.fold(A.sub(u, t));
           } else if (!INV) {
-            nv[l][2 * j] = A.fold(keep + recv);
-            nv[l][2 * j + 1] = A.red(A.mul(tw, keep + A.q2 - recv));
+            nv[l][2 * j] = A.fold(A.add(keep, recv));
+            nv[l][2 * j + 1] = A.red(A.mul(tw, A.sub(keep, recv)));
           } else {
-            const uint32_t t = A.red(A.mul(tw, hi ? keep : recv));
-            const uint32_t u = hi ? recv : keep;
-            nv[l][2 * j] = A.fold(u + t);
-            nv[l][2 * j + 1] = A.fold(u + A.q2 - t);
+            const T t = A.red(A.mul(tw, hi ? keep : recv));
+            const T u = hi ? recv : keep;
+            nv[l][2 * j] = A.fold(A.add(u, t));
+            nv[l][2 * j + 1] = A.fold(A.sub(u, t));
           }
         }
       }
@@ -857,14 +1014,14 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
         } else {
           if (TOP_IN_LANES && LL >= 2) round(h, true, LL - 1, 0);
           for (int r = NT - 1; r >= 1; r--) round(h, false, r, r);
-          uint32_t nv[LW][D2];
+          T nv[LW][D2];
           for (int l = 0; l < LW; l++) {
             const bool hi = l & 1;
             const int partner = l ^ 1;
             for (int j = 0; j < NP; j++) {
-              const uint32_t keep = hi ? v[h][l][2 * j + 1] : v[h][l][2 * j];
-              const uint32_t recv = (partner & 1) ? v[h][partner][2 * j] : v[h][partner][2 * j + 1];
-              const uint32_t t = hi ? keep : recv, u = hi ? recv : keep;
+              const T keep = hi ? v[h][l][2 * j + 1] : v[h][l][2 * j];
+              const T recv = (partner & 1) ? v[h][partner][2 * j] : v[h][partner][2 * j + 1];
+              const T t = hi ? keep : recv, u = hi ? recv : keep;
               nv[l][2 * j] = A.red(A.mad(A.mul(lt(h, 6, l), u), lt(h, 7, l), t));
               nv[l][2 * j + 1] = A.red(A.mad(A.mul(lt(h, 8, l), u), lt(h, 9, l), t));
             }
@@ -882,7 +1039,8 @@ void emulate_shape(const FusedW* F, int limb, int k, int64_t* y)
             if (LL == 0) pos = 2 * j + s;
             else if (!INV) pos = (2 * j + (l & 1)) * L + ((s << (LL - 1)) | (l >> 1)) + LW * h;
             else pos = (2 * j + (l >> (LL - 1))) * L + 2 * (l & (LW / 2 - 1)) + s + LW * h;
-            y[((size_t)row * SUB + pos) * k + limb] = (int64_t)A.canon(v[h][l][2 * j + s]);
+            if constexpr (AR::kZq) y[((size_t)row * SUB + pos) * k + limb] = (int64_t)A.canon(v[h][l][2 * j + s]);
+            else y[((size_t)row * SUB + pos) * k + limb] = v[h][l][2 * j + s];
           }
   }
 }
@@ -918,37 +1076,50 @@ void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
 
 }  // namespace
 
-int fused_w_select(lolb_plan* pl, void** slot)
+namespace {
+template <class FW, class BUILD>
+int select_impl(lolb_plan* pl, void** slot, BUILD build)
 {
-  FusedW* F = (FusedW*)*slot;
-  FusedW tmp;
-  int rc = build_fused_w(pl, &tmp);
+  FW* F = (FW*)*slot;
+  FW tmp;
+  int rc = build(pl, &tmp);
   if (rc) return rc;
   if (tmp.shape < 0) {
     if (F) { if (F->d_lane) cudaFree(F->d_lane); delete F; *slot = nullptr; }
     return LOLB_OK;
   }
-  if (!F) { F = new FusedW(); *slot = F; }
-  uint32_t* old = F->d_lane;
+  if (!F) { F = new FW(); *slot = F; }
+  auto* old = F->d_lane;
   *F = tmp;
   F->d_lane = nullptr;
   if (old) cudaFree(old);
-  LOLB_CUDA(cudaMalloc((void**)&F->d_lane, F->h_lane.size() * sizeof(uint32_t)));
-  LOLB_CUDA(cudaMemcpy(F->d_lane, F->h_lane.data(), F->h_lane.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  LOLB_CUDA(cudaMalloc((void**)&F->d_lane, F->h_lane.size() * sizeof(F->h_lane[0])));
+  LOLB_CUDA(cudaMemcpy(F->d_lane, F->h_lane.data(), F->h_lane.size() * sizeof(F->h_lane[0]), cudaMemcpyHostToDevice));
   return LOLB_OK;
 }
-
-void fused_w_release(void* slot)
+template <class FW>
+void release_impl(void* slot)
 {
-  FusedW* F = (FusedW*)slot;
+  FW* F = (FW*)slot;
   if (!F) return;
   if (F->d_lane) cudaFree(F->d_lane);
   delete F;
 }
+}  // namespace
+
+int fused_w_select(lolb_plan* pl, void** slot) { return select_impl<FusedW>(pl, slot, build_fused_w); }
+int fused_wc_select(lolb_plan* pl, void** slot) { return select_impl<FusedWC>(pl, slot, build_fused_wc); }
+void fused_w_release(void* slot) { release_impl<FusedW>(slot); }
+void fused_wc_release(void* slot) { release_impl<FusedWC>(slot); }
 
 bool fused_w_available(const void* slot, bool inverse)
 {
   const FusedW* F = (const FusedW*)slot;
+  return F && F->shape >= 0 && (inverse ? F->ok_inv : F->ok_fwd);
+}
+bool fused_wc_available(const void* slot, bool inverse)
+{
+  const FusedWC* F = (const FusedWC*)slot;
   return F && F->shape >= 0 && (inverse ? F->ok_inv : F->ok_fwd);
 }
 
@@ -959,6 +1130,16 @@ int fused_w_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   if (batch <= 0) return LOLB_OK;
   int rc = LOLB_FUSED_UNAVAILABLE;
   W_FOR_SHAPE(F, rc = launch_shape<SH>(pl, F, inverse, y, batch, st));
+  return rc;
+}
+
+int fused_wc_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st)
+{
+  const FusedWC* F = (const FusedWC*)slot;
+  if (!fused_wc_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
+  if (batch <= 0) return LOLB_OK;
+  int rc = LOLB_FUSED_UNAVAILABLE;
+  W_FOR_SHAPE(F, rc = launch_shape_c<SH>(pl, F, inverse, y, batch, st));
   return rc;
 }
 
@@ -985,5 +1166,26 @@ extern "C" int lolb_fused_w_emulate(const PrimeExponent* peArr, hShort_t sizeOfP
   if (rc) return rc;
   if (F.shape < 0) { set_error("lolb_fused_w_emulate: no fused_w kernel for this index / modulus"); return LOLB_ERR_ARG; }
   W_FOR_SHAPE(&F, emulate_dispatch<SH>(&F, inverse != 0, tupSize, y));
+  return LOLB_OK;
+}
+
+// The same for the complex plans: roots derived like lolb_plan_create_c does (CRTrans.hs:88-95); y = [phi(m)][tupSize] complex.
+extern "C" int lolb_fused_w_emulate_c(const PrimeExponent* peArr, hShort_t sizeOfPE, hShort_t tupSize, int inverse, lolb_complex* y)
+{
+  using namespace lolb;
+  if (!peArr || !y) { set_error("lolb_fused_w_emulate_c: NULL argument"); return LOLB_ERR_ARG; }
+  lolb_plan pl;
+  pl.kind = PLAN_C;
+  int rc = plan_build_common(&pl, peArr, sizeOfPE, tupSize);
+  if (rc) return rc;
+  plan_derive_c_roots(&pl);
+  FusedWC F;
+  rc = build_fused_wc(&pl, &F);
+  if (rc) return rc;
+  if (F.shape < 0) { set_error("lolb_fused_w_emulate_c: no fused_w kernel for this index"); return LOLB_ERR_ARG; }
+  for (int t = 0; t < tupSize; t++) {
+    if (inverse) { W_FOR_SHAPE(&F, (emulate_shape<SH, true, WC>(&F, t, tupSize, (double2*)y))); }
+    else { W_FOR_SHAPE(&F, (emulate_shape<SH, false, WC>(&F, t, tupSize, (double2*)y))); }
+  }
   return LOLB_OK;
 }

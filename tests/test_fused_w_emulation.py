@@ -9,7 +9,7 @@ m = 2016, each also with a modulus of the 64-bit-accumulate (Montgomery) class a
 import numpy as np
 import pytest
 
-from conftest import zq_input
+from conftest import rel_err, zq_input
 from lol_b200 import build_library, capi
 from oracle import tables as T
 
@@ -63,3 +63,22 @@ def test_fused_w_emulation_refuses_other_shapes():
         capi.fused_w_emulate(T.factor_pps(14400), [14401], np.zeros((3840, 1), dtype=np.int64))
     with pytest.raises(capi.LolB200Error):      # no CRT of index 1728 over Z_17
         capi.fused_w_emulate(T.factor_pps(1728), [17], np.zeros((576, 1), dtype=np.int64))
+
+
+FUSED_W_COMPLEX = [1728, 5184, 2912, 728, 3640, 2016, 5824, 11648, 5460, 4095]
+
+
+@pytest.mark.parametrize("m", FUSED_W_COMPLEX)
+@pytest.mark.parametrize("k", [1, 2])
+def test_fused_w_schedule_complex_matches_oracle(oracle, m, k):
+    """The same schedule over complex doubles (tensorCRTC / tensorCRTInvC, crt.cpp:583-598): 1e-9 relative, the
+    floating-point tolerance of BASELINE.json's north_star (operation order and FMA contraction differ from the reference)."""
+    rng = np.random.default_rng(m + k)
+    pps, pe = T.factor_pps(m), T.pe_array(m)
+    n = T.totient_pps(pps)
+    ruc, ruci = T.ru_tables_c(m, k), T.ru_tables_c(m, k, inverse=True)
+    c = rng.standard_normal((n, k)) + 1j * rng.standard_normal((n, k))
+    f = capi.fused_w_emulate_c(pps, c, False)
+    assert rel_err(f, oracle.tensorCRTC(c, pe, ruc, k)) <= 1e-9
+    assert rel_err(capi.fused_w_emulate_c(pps, c, True), oracle.tensorCRTInvC(c, pe, ruci, T.mhat_inv_c(m, k), k)) <= 1e-9
+    assert rel_err(capi.fused_w_emulate_c(pps, f, True), c) <= 1e-9

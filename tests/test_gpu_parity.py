@@ -465,6 +465,33 @@ def test_complex_crt_fused_kernel_m14400(torch_cuda, oracle, k):
     assert rel_err(t.crtInv(x).cpu().numpy(), g.cpu().numpy()) <= 1e-12
 
 
+@pytest.mark.parametrize("m,k", [(1728, 1), (5184, 1), (2912, 2), (728, 1), (3640, 1), (2016, 3), (5824, 1), (11648, 1), (5460, 2), (4095, 1)],
+                         ids=lambda v: str(v))
+def test_complex_crt_fused_w_rings(torch_cuda, gpu_oracle, m, k):
+    """tensorCRTC / tensorCRTInvC of the fused_w indices (every lol / lol-apps benchmark ring that is not 2^e or 14400) run on
+    the fused_w schedule over complex doubles: per element against the oracle (1e-9), the whole ragged batch against the
+    generic pass engine, crtInv . crt = id."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorComplex
+    B = 37
+    rng = np.random.default_rng(m + k)
+    pe = T.pe_array(m)
+    t = CudaTensorComplex(m, k)
+    assert t.plan.kernel_name("CRTC") == "fused_w" and t.plan.kernel_name("CRTInvC") == "fused_w"
+    c = rng.normal(size=(B, t.n, k)) + 1j * rng.normal(size=(B, t.n, k))
+    x = torch.from_numpy(c).cuda()
+    ruc, ruci = T.ru_tables_c(m, k), T.ru_tables_c(m, k, inverse=True)
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, 17, B - 1):
+        assert rel_err(f[b].cpu().numpy(), gpu_oracle.tensorCRTC(c[b], pe, ruc, k)) <= FLOAT_TOL
+        assert rel_err(g[b].cpu().numpy(), gpu_oracle.tensorCRTInvC(c[b], pe, ruci, T.mhat_inv_c(m, k), k)) <= FLOAT_TOL
+    assert rel_err(t.crtInv(f).cpu().numpy(), c) <= 1e-11
+    t.plan.force_generic(True)
+    assert t.plan.kernel_name("CRTC") == "generic"
+    assert rel_err(t.crt(x).cpu().numpy(), f.cpu().numpy()) <= 1e-11
+    assert rel_err(t.crtInv(x).cpu().numpy(), g.cpu().numpy()) <= 1e-11
+
+
 @pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89], ids=str)
 def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
     """The streaming kernels of the modulus-free rings (one or two small odd primes) against the generic pass
