@@ -7,6 +7,7 @@
     crtExtFuncs: twaceCRT, embedCRT    twaceCRT', embedCRT'  Extension.hs:81-85, 110-129 .twaceCRT / .embedCRT (None = Nothing)
     coeffs                             coeffs'  Extension.hs:90-93                       .coeffs
     powBasisPow                        powBasisPow'  Extension.hs:133-143                .powBasisPow
+    crtSetDec                          crtSetDec'  Extension.hs:145-164                  .crtSetDec (host precomputation, crtset.py)
 
 An extension is built from two single-index tensors of `lol_b200.tensor` over the same ring (`CudaTensorRq` with equal
 moduli, or two of `CudaTensorInt` / `CudaTensorReal` / `CudaTensorComplex` with equal tupSize).  Operands are torch CUDA
@@ -65,6 +66,13 @@ class CudaExtension:
         y = torch.empty((self.phi2 // self.phi, self.phi2, self.k), dtype=self.dtype, device="cuda")
         capi.check(self.ext.pow_basis_pow(self.ring, y.data_ptr(), _stream()))
         return y
+
+    def crtSetDec(self, p: int):
+        """[count, phi', 1] int64 residues mod the prime p: the mod-p CRT set of O_m'/O_m in the decoding basis (Tensor.hs:184-186).
+        Built once on the host like the reference does (GF(p^d) arithmetic, crtset.py) and uploaded."""
+        from . import crtset
+        cs = crtset.crt_set_dec(self.lo.m, self.hi.m, int(p))
+        return torch.from_numpy(cs).to("cuda").unsqueeze(-1).contiguous()
 
     def coeffs(self, x):
         """[batch, phi', k] -> [batch, phi'/phi, phi, k]: the O_m coefficients w.r.t. the powerful / decoding extension basis."""

@@ -156,6 +156,28 @@ def test_extension_properties_at_full_size(torch_cuda):
     assert torch.equal(hi.crtInv(acc), y[:256])
 
 
+@pytest.mark.parametrize("m,m2,p", [(3, 21, 2), (5, 45, 2), (4, 20, 3)], ids=lambda v: str(v))
+def test_crt_set_dec_on_the_device(torch_cuda, gpu_oracle, m, m2, p):
+    """crtSetDec (Tensor.hs:184-186; CPP/Extension.hs:145-164): the host-built set uploaded by CudaExtension, taken to the
+    powerful basis on the device the way UCyc.crtSet does for e = 1 (UCyc.hs:556-564: toPow . Dec): equals the oracle's L of
+    the same vectors and sums to the ring's 1.  The set property itself (c_i c_j = delta_ij c_i) is tests/test_crt_set.py."""
+    torch = torch_cuda
+    from lol_b200 import crtset
+    from lol_b200.extension import CudaExtension
+    from lol_b200.tensor import CudaTensorRq
+    lo, hi = CudaTensorRq(m, [p]), CudaTensorRq(m2, [p])
+    ext = CudaExtension(lo, hi)
+    cs = ext.crtSetDec(p)
+    host = crtset.crt_set_dec(m, m2, p)
+    assert cs.shape == (host.shape[0], hi.n, 1) and np.array_equal(cs.cpu().numpy()[..., 0], host)
+    pw = hi.l(cs)
+    pe = T.pe_array(m2)
+    for r in range(host.shape[0]):
+        assert np.array_equal(pw[r].cpu().numpy(), gpu_oracle.tensorLRq(host[r].reshape(-1, 1), pe, [p]))
+    total = pw.sum(dim=0) % p
+    assert int(total[0, 0]) == 1 and int(total[1:].abs().sum()) == 0
+
+
 def test_extension_argument_errors(torch_cuda):
     torch = torch_cuda
     from lol_b200 import capi
