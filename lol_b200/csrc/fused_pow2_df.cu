@@ -719,7 +719,11 @@ int launch_df_top(const lolb_plan* pl, const FusedPow2Df* F, int64_t* y, int64_t
   //   e = 15, tupSize 4: split 61.6 / 59.4, unpaired 51.9 / 49.1;   e = 14, tupSize 4: split 61.8 / 61.5, unpaired 42 / 38
   // so the split schedule (two plain kernels, the u32 intermediate through a workspace) serves everything except tupSize 2 at
   // e = 16; keeping the rounds 5-9 twiddles in shared memory instead of L1 was measured too: no gain.
-  const char* sched = getenv("LOLB_DF_SCHEDULE");      // "split" / "paired" / "unpaired" override
+  const char* sched = getenv("LOLB_DF_SCHEDULE");      // "split" / "paired" / "unpaired" / "cluster" override
+  if (sched && sched[0] == 'c') {
+    const int rc = pow2_cluster_crt(pl, F, INV, y, batch, st);
+    if (rc != LOLB_FUSED_UNAVAILABLE) return rc;
+  }
   if (sched ? sched[0] == 's' : !(K == 2 && F->top == 5)) {
     const int rc = pow2_split_crt(pl, F, INV, y, batch, st);
     if (rc != LOLB_FUSED_UNAVAILABLE) return rc;

@@ -133,5 +133,9 @@ int pow2_resident_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, i
 int pow2_split_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
 void pow2_split_release(const lolb_plan* pl);
 
+
+// fused_pow2_cl.cu: m = 2^16 with the element resident across a thread-block cluster (one kernel, DSMEM exchange)
+int pow2_cluster_crt(const lolb_plan* pl, const FusedPow2Df* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+
 }  // namespace pow2
 }  // namespace lolb

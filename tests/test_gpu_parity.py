@@ -399,6 +399,41 @@ def test_power_of_two_split_schedule(torch_cuda, oracle, monkeypatch, e, k, mb, 
 
 
 @pytest.mark.timeout(120)
+@pytest.mark.parametrize("k", [1, 2, 4], ids=lambda v: f"k={v}")
+def test_power_of_two_cluster_kernel(torch_cuda, oracle, monkeypatch, k):
+    """fused_pow2_cl (m = 2^16, tupSize 1, 2, 4): the element resident across a thread-block cluster, residues exchanged through
+    distributed shared memory.  Oracle parity on a sample, the generic engine on all elements (more elements than clusters fit
+    on the device at once), crtInv . crt = id, out-of-range input words, calls back to back in place."""
+    torch = torch_cuda
+    from lol_b200 import capi
+    from lol_b200.tensor import CudaTensorRq
+    monkeypatch.setenv("LOLB_DF_SCHEDULE", "cluster")
+    m, qs = 2 ** 16, CONFIG_B[1][:k]
+    B = 150 // k + 3
+    rng = np.random.default_rng(160 + k)
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    y = zq_input(rng, n, qs, batch=B)
+    y[1, :64] += np.array(qs) * 3          # outside [0, q): reduced like the reference's constructor
+    y[2, 5:9] -= np.array(qs) * 2
+    x = torch.from_numpy(y).cuda()
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, 1, 2, B // 2, B - 1):
+        assert np.array_equal(f[b].cpu().numpy(), oracle.tensorCRTRq(y[b], pe, ru, qs)), b
+        assert np.array_equal(g[b].cpu().numpy(), oracle.tensorCRTInvRq(y[b], pe, rui, mh, qs)), b
+    xc = torch.from_numpy(y % np.array(qs)).cuda()
+    assert torch.equal(t.crtInv(f), xc) and torch.equal(t.crt(g), xc)
+    z = xc.clone()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        capi.check(t.plan.op("CRT", z.data_ptr(), B, st))
+        capi.check(t.plan.op("CRTInv", z.data_ptr(), B, st))
+    assert torch.equal(z, xc)
+    t.plan.force_generic(True)
+    assert torch.equal(t.crt(x), f) and torch.equal(t.crtInv(x), g)
+
+
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("schedule", ["paired", "unpaired", "resident"])
 @pytest.mark.parametrize("ring,lag", [(3, 1), (5, 4), (48, 12)], ids=lambda v: str(v))
 @pytest.mark.parametrize("e,k", [(10, 1), (10, 2), (10, 4), (11, 1), (11, 2), (11, 4), (12, 1), (12, 2), (12, 4), (13, 1), (13, 2), (13, 4), (14, 1),
