@@ -58,6 +58,7 @@ struct WS {
   typedef int64_t IO;       // value in HBM (the ABI)
   typedef uint32_t Acc;
   static constexpr bool kZq = true;
+  static constexpr bool kSym = false;
   static constexpr int MAXT = 1 << 20;      // terms per reduction: unbounded (the host checks 2 T q^2 < 2^32 for the longest row)
   uint32_t q, q2, mu, nq;
   WHD uint32_t add(uint32_t a, uint32_t b) const { return a + b; }                  // lazy: the caller folds or reduces
@@ -74,6 +75,7 @@ struct WS {
 // WS6: the same 32-bit arithmetic for moduli whose longest rows (12 or 13 terms: p = 13) would overflow: a row is cut into
 // pieces of at most 6 terms, each reduced on its own (2 * 6 * q^2 < 2^32), the pieces folded together
 struct WS6 : WS {
+  static constexpr bool kSym = true;
   static constexpr int MAXT = 6;
   WHD WS6(const WMod& M) : WS(M) {}
 };
@@ -84,6 +86,7 @@ struct WM {
   typedef int64_t IO;
   typedef uint64_t Acc;
   static constexpr bool kZq = true;
+  static constexpr bool kSym = true;
   static constexpr int MAXT = 1 << 20;
   uint32_t q, q2, qinv, one;
   WHD uint32_t add(uint32_t a, uint32_t b) const { return a + b; }
@@ -109,6 +112,7 @@ struct WC {
   typedef double2 IO;
   typedef double2 Acc;
   static constexpr bool kZq = false;
+  static constexpr bool kSym = true;
   static constexpr int MAXT = 1 << 20;
   WHD WC(const WMod&) {}
   WHD Acc mul(double2 c, double2 v) const { return make_double2(c.x * v.x - c.y * v.y, c.x * v.y + c.y * v.x); }
@@ -210,11 +214,92 @@ WHD void pp_blocks(TV (&v)[NV], const int base, const CT& C, const AR& A)
   }
 }
 
+#ifndef LOLB_W_SYM
+#define LOLB_W_SYM 1      // 0: dense (p-1) x (p-1) blocks for the primes too (the first version; A/B builds)
+#endif
+// Used where a product costs more than an addition: the 64-bit-accumulate class (IMAD.WIDE, half rate), the class whose rows are
+// cut into 6-term pieces, and complex doubles.  For the plain 32-bit class (one IMAD per product) the dense block measured faster
+// (m = 2912, q = 8737: 71 % / 72 % of HBM dense, 69 % / 67 % with the split), so WS keeps it.
+template <class PPx, class AR> struct PPSym { static constexpr bool on = LOLB_W_SYM && AR::kSym && PPx::e == 1 && PPx::p >= 5; };
+
+// CRT_p / CRT_p^-1 of a PRIME p >= 5 (no twiddles: crtTwiddle and ppDFT are empty for e = 1) with half the multiplications.
+// With k = row + 1 and w = w_p:   forward  out_k = sum_{c=0}^{p-2} w^(kc) x_c,  k = 1 .. p-1   (crtp, crt.cpp:248-346)
+//                                 inverse  out_r = s (sum_{k=1}^{p-1} w^(-rk) y_k - sum_k w^k y_k),  r = 0 .. p-2   (crtpinv, :349-457)
+// Pair the inputs (c, p - c) -- e_c = x_c + x_{p-c}, d_c = x_c - x_{p-c} (x_{p-1} = 0 forward) -- and the outputs (k, p - k):
+//   C_k = sum_c cos_kc e_c,  S_k = sum_c sin_kc d_c,  cos_kc = (w^kc + w^-kc) / 2,  sin_kc = (w^kc - w^-kc) / 2,  c, k = 1 .. h = (p-1)/2
+//   forward  out_k = x_0 + C_k + S_k,  out_{p-k} = x_0 + C_k - S_k
+//   inverse  A_r = C_r - S_r,  A_{p-r} = C_r + S_r,  A_0 = s sum_c e_c;  the common term is A_{p-1} = C_1 + S_1;  out_r = A_r - A_{p-1}
+// 2 h^2 = (p-1)^2 / 2 products instead of (p-1)^2; exact arithmetic, so the residues are the reference's.
+// Constants at COFF: cos[k-1][c-1] (h x h), then sin[k-1][c-1], then s (inverse; cos and sin carry it too).
+template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, class TV, int NV>
+WHD void pp_prime_sym(TV (&v)[NV], const int base, const CT& C, const AR& A)
+{
+  constexpr int P = PPx::p, H = (P - 1) / 2;
+  static_assert(H <= AR::MAXT, "a row of the half-size blocks must fit one lazy accumulation");      // h products (< 2 q^2 each) + x_0 < 2q: inside every class bound (w_class)
+  TV e[H], d[H], cs[H], sn[H];
+  if constexpr (!INV) {
+    const TV x0 = v[base];
+    e[0] = d[0] = v[base + STRIDE];
+#pragma unroll
+    for (int c = 2; c <= H; c++) {
+      const TV a = v[base + c * STRIDE], b = v[base + (P - c) * STRIDE];
+      e[c - 1] = A.fold(A.add(a, b));
+      d[c - 1] = A.fold(A.sub(a, b));
+    }
+#pragma unroll
+    for (int k = 1; k <= H; k++) {
+      typename AR::Acc ac = A.unit(x0), as = A.mul(C.c[COFF + H * H + (k - 1) * H], d[0]);
+#pragma unroll
+      for (int c = 1; c <= H; c++) ac = A.mad(ac, C.c[COFF + (k - 1) * H + (c - 1)], e[c - 1]);
+#pragma unroll
+      for (int c = 2; c <= H; c++) as = A.mad(as, C.c[COFF + H * H + (k - 1) * H + (c - 1)], d[c - 1]);
+      cs[k - 1] = A.red(ac);
+      sn[k - 1] = A.red(as);
+    }
+#pragma unroll
+    for (int k = 1; k <= H; k++) {
+      v[base + (k - 1) * STRIDE] = A.fold(A.add(cs[k - 1], sn[k - 1]));
+      v[base + (P - k - 1) * STRIDE] = A.fold(A.sub(cs[k - 1], sn[k - 1]));
+    }
+  } else {
+#pragma unroll
+    for (int k = 1; k <= H; k++) {
+      const TV a = v[base + (k - 1) * STRIDE], b = v[base + (P - k - 1) * STRIDE];
+      e[k - 1] = A.fold(A.add(a, b));
+      d[k - 1] = A.fold(A.sub(a, b));
+    }
+    TV sum = e[0];
+#pragma unroll
+    for (int k = 2; k <= H; k++) sum = A.add(sum, e[k - 1]);
+    const TV a0 = A.red(A.mul(C.c[COFF + 2 * H * H], sum));
+#pragma unroll
+    for (int r = 1; r <= H; r++) {
+      typename AR::Acc ac = A.mul(C.c[COFF + (r - 1) * H], e[0]), as = A.mul(C.c[COFF + H * H + (r - 1) * H], d[0]);
+#pragma unroll
+      for (int k = 2; k <= H; k++) {
+        ac = A.mad(ac, C.c[COFF + (r - 1) * H + (k - 1)], e[k - 1]);
+        as = A.mad(as, C.c[COFF + H * H + (r - 1) * H + (k - 1)], d[k - 1]);
+      }
+      cs[r - 1] = A.red(ac);
+      sn[r - 1] = A.red(as);
+    }
+    const TV shift = A.fold(A.add(cs[0], sn[0]));      // A_{p-1}
+    v[base] = A.fold(A.sub(a0, shift));
+#pragma unroll
+    for (int r = 1; r <= H; r++) {
+      v[base + r * STRIDE] = A.fold(A.sub(A.fold(A.sub(cs[r - 1], sn[r - 1])), shift));
+      if (r >= 2) v[base + (P - r) * STRIDE] = A.fold(A.sub(A.fold(A.add(cs[r - 1], sn[r - 1])), shift));
+    }
+  }
+}
+
 // CRT_{p^e} / CRT_{p^e}^-1 on one line (ppcrt / ppcrtinv, crt.cpp:518-560)
 template <class PPx, bool INV, int STRIDE, int COFF, class AR, class CT, class TV, int NV>
 WHD void pp_line(TV (&v)[NV], const int base, const CT& C, const AR& A)
 {
-  if constexpr (PPx::p > 1) {
+  if constexpr (PPSym<PPx, AR>::on) {
+    pp_prime_sym<PPx, INV, STRIDE, COFF>(v, base, C, A);
+  } else if constexpr (PPx::p > 1) {
     constexpr int R = PPx::R;
     static_assert(R <= 4, "prime-power exponent too large for the unrolled rounds");
     if constexpr (!INV) {
@@ -573,8 +658,10 @@ struct FieldZq {
   uint64_t q;
   V one() const { return 1; }
   V mul(V a, V b) const { return mulmod64(a, b, q); }
+  V add(V a, V b) const { return (a + b) % q; }
   V sub(V a, V b) const { return (a + q - b) % q; }
   V neg(V a) const { return (q - a) % q; }
+  V half() const { return (q + 1) / 2; }      // q odd
   Out out(V a) const { return (uint32_t)a; }
 };
 struct FieldC {
@@ -582,8 +669,10 @@ struct FieldC {
   typedef double2 Out;
   V one() const { return V(1.0, 0.0); }
   V mul(V a, V b) const { return V(a.real() * b.real() - a.imag() * b.imag(), a.real() * b.imag() + a.imag() * b.real()); }
+  V add(V a, V b) const { return a + b; }
   V sub(V a, V b) const { return a - b; }
   V neg(V a) const { return -a; }
+  V half() const { return V(0.5, 0.0); }
   Out out(V a) const { return make_double2(a.real(), a.imag()); }
 };
 
@@ -612,12 +701,26 @@ struct RootTabC {     // the same over C: the plan's cis tables (CRTrans.hs:88-9
 
 // constants of prime power (p, e) into out[0 .. n_consts): layout of PPT; `scale` multiplies the inverse block matrices
 template <class FLD, class TAB>
-void build_pp_consts(int p, int e, bool inverse, const FLD& f, const TAB& T, typename FLD::V scale, typename FLD::Out* out)
+void build_pp_consts(int p, int e, bool inverse, bool sym, const FLD& f, const TAB& T, typename FLD::V scale, typename FLD::Out* out)
 {
   typedef typename FLD::V V;
   const int d = p - 1, R = e - 1;
   const int64_t mp = ipow64(p, e - 1);
   size_t o = 0;
+  if (LOLB_W_SYM && sym && e == 1 && p >= 5) {      // a prime: the half-size cosine / sine blocks of pp_prime_sym (same storage: (p-1)^2 words)
+    const int h = (p - 1) / 2;
+    auto w = [&](int64_t j) { return inverse ? T(-j) : T(j); };      // w_p^j from either table
+    const V s = inverse ? scale : f.one();
+    for (int k = 1; k <= h; k++)
+      for (int c = 1; c <= h; c++) {
+        const V a = w((int64_t)k * c), b = w(-(int64_t)k * c);
+        out[(k - 1) * h + (c - 1)] = f.out(f.mul(s, f.mul(f.half(), f.add(a, b))));
+        out[h * h + (k - 1) * h + (c - 1)] = f.out(f.mul(s, f.mul(f.half(), f.sub(a, b))));
+      }
+    out[2 * h * h] = f.out(s);
+    for (int i = 2 * h * h + 1; i < d * d; i++) out[i] = f.out(f.sub(f.one(), f.one()));
+    return;
+  }
   for (int64_t i0 = 0; i0 < mp; i0++)
     for (int r = 0; r < d; r++)
       for (int c = 0; c < d; c++) {
@@ -761,6 +864,7 @@ const WShapeId kShapeIds[kNumShapes] = {shape_id<SH_64_27>(), shape_id<SH_64_81>
 template <class FW, class FLD, class MKTAB>
 void fill_consts(const lolb_plan* pl, FW* F, int t, int dir, const FLD& f, typename FLD::V scale, const MKTAB& mktab)
 {
+  const bool sym = F->cls[t] != WC_S;      // = AR::kSym of the limb's arithmetic class
   const WShapeId& id = kShapeIds[F->shape];
   const int npe = (int)pl->pe.size(), first_odd = id.a > 0 ? 1 : 0;
   auto& out = dir ? F->ci[t] : F->cf[t];
@@ -771,7 +875,7 @@ void fill_consts(const lolb_plan* pl, FW* F, int t, int dir, const FLD& f, typen
     for (int dig = 0; dig < e - 1; dig++) n_w += (size_t)ipow64(p, e - 2 - dig) * p * p;
     const size_t at = out.size();
     out.resize(at + n_m1 + n_w);
-    build_pp_consts(p, e, dir != 0, f, mktab(i, ipow64(p, e)), i == first_odd ? scale : f.one(), out.data() + at);      // mhat^-1 rides on the first odd axis
+    build_pp_consts(p, e, dir != 0, sym, f, mktab(i, ipow64(p, e)), i == first_odd ? scale : f.one(), out.data() + at);      // mhat^-1 rides on the first odd axis
   }
   if (id.a >= 2)
     build_lane_table(id.a, dir != 0, f, mktab(0, ipow64(2, id.a)), F->h_lane.data() + ((size_t)t * 2 + dir) * 2 * kWLaneRows * 32);
