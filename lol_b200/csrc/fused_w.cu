@@ -517,7 +517,11 @@ __device__ __forceinline__ void w_finish(typename AR::T (&v)[SH::H][SH::D2], con
       for (int j = 0; j < SH::NP; j++) {
         if constexpr (AR::kZq) {
           const int64_t a = (int64_t)A.canon(v[h][2 * j]), b = (int64_t)A.canon(v[h][2 * j + 1]);
-          if (INV && K == 1 && SH::LL >= 1) {
+          // the pair is adjacent in memory (inverse: always; forward: 2^a axes of <= 2 lanes): one 16-byte store.  Measured at
+          // q = 3144961: m = 4095 36 % / 35 % -> 51 % / 49 % of HBM, m = 5460 52 % -> 58 % forward.  Sending the blocks of the
+          // narrow shapes (L <= 4) back through the tile for a coalesced third phase was measured too and is slower
+          // (4095: 50 / 47, 5460: 50 / 48, 3640: 58 / 56): the extra barrier and tile pass cost more than the sectors save.
+          if (K == 1 && (INV || SH::LL <= 1)) {
             __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h)), make_longlong2(a, b));
           } else {
             __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, a);
