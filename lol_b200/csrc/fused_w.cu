@@ -821,14 +821,18 @@ constexpr WShapeId shape_id() { return WShapeId{SH::A, SH::PA::p, SH::PA::e, SH:
 #endif
 typedef WShape<6, PPT<3, 3>, PPNone, PPNone, PPNone, 1, LOLB_W27_MINB> SH_64_27;     // m = 1728  (n = 576)
 typedef WShape<6, PPT<3, 4>, PPNone, PPNone, PPNone, 1, LOLB_W81_MINB> SH_64_81;     // m = 5184  (n = 1728)
-typedef WShape<5, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 4, 4> SH_32_7_13;           // m = 2912  (n = 1152)
-typedef WShape<3, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 16, 4> SH_8_7_13;           // m = 728   (n = 288)
-typedef WShape<3, PPT<5, 1>, PPT<7, 1>, PPNone, PPT<13, 1>, 8, 4> SH_8_5_7_13;       // m = 3640  (n = 1152)
-typedef WShape<5, PPT<3, 2>, PPNone, PPNone, PPT<7, 1>, 4, 4> SH_32_9_7;             // m = 2016  (n = 576)
-typedef WShape<6, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 2, 4> SH_64_7_13;           // m = 5824  (n = 2304; lol-apps tunnel benchmark ring H1)
-typedef WShape<7, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 1, 4> SH_128_7_13;  // m = 11648 (n = 4608; Twace-Embed / tunnel H0): two column halves per lane
-typedef WShape<2, PPT<3, 1>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 4> SH_4_3_5_7_13;      // m = 5460 (n = 1152; tunnel H4): 7 in the tile
-typedef WShape<0, PPT<3, 2>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 4, 4> SH_9_5_7_13;        // m = 4095 (n = 1728; tunnel H5): odd index, no network
+// Two-phase shapes: CTAs of 128 threads per SM asked for (the last WShape argument).  Measured on B200 after the half-size prime
+// blocks, % of HBM CRT / CRT^-1 at 4 -> 8 CTAs/SM: m = 2912 / 8737 71 / 72 -> 81 / 82 (10: 66 / 66), / 3144961 61 / 58 -> 66 / 64;
+// m = 728 / 8737 77 / 79 -> 86 / 89; m = 3640 / 14561 71 / 74 -> 74 / 76; m = 5824 / 3144961 62 / 59 -> 68 / 65; m = 11648 63 / 59 ->
+// 69 / 65; m = 5460 58 / 55 -> 61 / 58; m = 2016 / 2017 63 / 63 -> 82 / 84 (10: 86 / 88); m = 4095: 6 is best (56 / 49; 8: 47 / 46).
+typedef WShape<5, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 4, 8> SH_32_7_13;           // m = 2912  (n = 1152)
+typedef WShape<3, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 16, 8> SH_8_7_13;           // m = 728   (n = 288)
+typedef WShape<3, PPT<5, 1>, PPT<7, 1>, PPNone, PPT<13, 1>, 8, 8> SH_8_5_7_13;       // m = 3640  (n = 1152)
+typedef WShape<5, PPT<3, 2>, PPNone, PPNone, PPT<7, 1>, 4, 10> SH_32_9_7;            // m = 2016  (n = 576)
+typedef WShape<6, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 2, 8> SH_64_7_13;           // m = 5824  (n = 2304; lol-apps tunnel benchmark ring H1)
+typedef WShape<7, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 1, 8> SH_128_7_13;  // m = 11648 (n = 4608; Twace-Embed / tunnel H0): two column halves per lane
+typedef WShape<2, PPT<3, 1>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 8> SH_4_3_5_7_13;      // m = 5460 (n = 1152; tunnel H4): 7 in the tile
+typedef WShape<0, PPT<3, 2>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 4, 6> SH_9_5_7_13;        // m = 4095 (n = 1728; tunnel H5): odd index, no network
 
 constexpr int kNumShapes = 10;
 
