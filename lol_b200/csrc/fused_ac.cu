@@ -376,19 +376,10 @@ int fused_ac_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y
   const FusedAC* F = (const FusedAC*)slot;
   if (!fused_ac_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  static int variant = -1;      // LOLB_FUSED_AC_VARIANT: tuning runs
-  if (variant < 0) { const char* v = getenv("LOLB_FUSED_AC_VARIANT"); variant = v ? atoi(v) : 0; }
-  switch (variant) {
-    // measured at m = 14400, batch 32768 (% of HBM peak, forward / inverse): 3 warps x 3 CTAs/SM (168 registers, spills)
-    // 47 / 42; 3 x 2 (255 registers) 47 / 49; 4 x 3 49 / 49; 2 x 3 47 / 39; 6 warps x 2 CTAs/SM (158 registers, no
-    // spill, phase 1 = one column task per warp) 61 / 61
-    case 1: return launch_ac<3, 2>(pl, F, inverse, y, batch, st);
-    case 2: return launch_ac<4, 3>(pl, F, inverse, y, batch, st);
-    case 3: return launch_ac<3, 3>(pl, F, inverse, y, batch, st);
-    case 4: return launch_ac<12, 1>(pl, F, inverse, y, batch, st);
-    case 5: return launch_ac<6, 3>(pl, F, inverse, y, batch, st);
-    default: return launch_ac<6, 2>(pl, F, inverse, y, batch, st);
-  }
+  // measured at m = 14400, batch 32768 (% of HBM peak, forward / inverse): 3 warps x 3 CTAs/SM (168 registers, spills)
+  // 47 / 42; 3 x 2 (255 registers) 47 / 49; 4 x 3 49 / 49; 2 x 3 47 / 39; 6 warps x 2 CTAs/SM (158 registers, no
+  // spill, phase 1 = one column task per warp) 61 / 61 -- the only configuration kept
+  return launch_ac<6, 2>(pl, F, inverse, y, batch, st);
 }
 
 }  // namespace lolb
