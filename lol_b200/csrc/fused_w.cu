@@ -349,6 +349,16 @@ struct WShape {
   static_assert(D2 % 2 == 0, "an odd prime power is required next to the 2^a axis");
 };
 
+// complex doubles: CTAs of 128 threads per SM asked for.  Measured on B200 (% of the 32 n-byte roofline, CRT / CRT^-1, at 1 -> 3 -> 4):
+// m = 1728  42 / 79 -> 58 / 66 -> 61 / 68;  m = 2912  44 / 42 -> 55 / 52 -> 61 / 55;  m = 3640  25 / 24 -> 32 / 30 -> 36 / 33;
+// m = 11648  35 / 33 -> 41 / 39 -> 30 / 24;  m = 5184  27 / 34 -> 23 / 29 -> 17 / 21 (54 complex values per lane need every register)
+template <class SH, bool INV>
+constexpr int wc_minb()
+{
+  if (SH::D2 * SH::H >= 48) return 1;
+  if (!SH::TWO_PHASE) return INV ? 1 : 4;
+  return SH::H == 2 ? 3 : 4;
+}
 constexpr int kWLaneRows = 10;     // per-lane constants of the network, per column half (see build_lane_table)
 constexpr int kWThreads = 128;
 
@@ -538,7 +548,7 @@ __device__ __forceinline__ void w_finish(typename AR::T (&v)[SH::H][SH::D2], con
 
 // ------------------------------------------------------------------ m = 2^a p^e (p_b^e_b): a group of L lanes per element
 template <class SH, bool INV, class AR, int K>
-__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : 1)
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
 k_fused_w1(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
            const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
 {
@@ -569,7 +579,7 @@ template <class SH, class AR> struct WTile {
 };
 
 template <class SH, bool INV, class AR, int K>
-__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : 1)
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
 k_fused_w2(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
            const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
 {
@@ -970,7 +980,7 @@ int launch_w(const lolb_plan* pl, const FusedWT<typename AR::T>* F, int limb, ty
   const std::vector<T>& src = INV ? F->ci[limb] : F->cf[limb];
   if ((int)src.size() != SH::OFF_C + SH::PC::n_consts) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
   for (size_t i = 0; i < src.size(); i++) C.c[i] = src[i];
-  int64_t grid = (int64_t)pl->num_sms * (AR::kZq ? SH::MINB : 2);
+  int64_t grid = (int64_t)pl->num_sms * (AR::kZq ? SH::MINB : (wc_minb<SH, INV>() < 2 ? 2 : wc_minb<SH, INV>()));
   if constexpr (SH::TWO_PHASE) {
     constexpr int EPB = WTile<SH, AR>::EPB;
     constexpr size_t BYTES = WTile<SH, AR>::BYTES;
