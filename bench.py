@@ -470,6 +470,9 @@ def run_gpu_arm(args):
         # the ring-tunnelling chain of lol-apps' benchmarks at its modulus (lol-apps Benchmarks/Default.hs:52-82)
         for mt, bt in ((11648, 30720), (5824, 61440), (2912, 122880), (3640, 122880), (5460, 122880), (4095, 81920)):
             rq_config(f"tunnel m={mt}/3144961", mt, [3144961], bt)
+        # the HomomPRF example's modulus chains on its rings (lol-apps Examples/HomomPRFParams.hs:24-45): tupSize 2 and 4
+        rq_config("HomomPRF H1'=F64*F7*F13 ZQ2", 5824, [19393921, 18869761], 32768)
+        rq_config("HomomPRF H1'=F64*F7*F13 ZQ4", 5824, [25159681, 19918081, 19393921, 18869761], 16384)
         from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
         Bg = 32768
         tr, ti, tcx = CudaTensorReal(M), CudaTensorInt(M), CudaTensorComplex(M)
@@ -628,6 +631,8 @@ def run_gpu_arm(args):
                "m3640": [fr("F8*F5*F7*F13/14561", "CRT"), fr("F8*F5*F7*F13/14561", "CRTInv")],
                "m11648": [fr("F128*F7*F13/23297", "CRT"), fr("F128*F7*F13/23297", "CRTInv")],
                "tunnel": [[fr(f"tunnel m={mt}/3144961", "CRT"), fr(f"tunnel m={mt}/3144961", "CRTInv")] for mt in (11648, 5824, 2912, 3640, 5460, 4095)],
+               "prf_k2": [fr("HomomPRF H1'=F64*F7*F13 ZQ2", "CRT"), fr("HomomPRF H1'=F64*F7*F13 ZQ2", "CRTInv")],
+               "prf_k4": [fr("HomomPRF H1'=F64*F7*F13 ZQ4", "CRT"), fr("HomomPRF H1'=F64*F7*F13 ZQ4", "CRTInv")],
                "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec")}
     for s, n, ms, _, units, _ in rec.rows:
         if s == "she" and n == "mulAndSwitch":

@@ -21,6 +21,8 @@
 //   k_fused_w2  (m = 2^a .. p_c^e_c) phase 1: thread <- one column along ic from HBM, line, u32 tile in shared memory;
 //               phase 2: group of L lanes <- one ic-row of the tile, middle line(s), network, stores.
 #include <complex>
+#include <cstdlib>
+#include <mutex>
 
 #include "fused.cuh"
 #include "numtheory.h"
@@ -480,7 +482,14 @@ __device__ __noinline__ uint32_t w_reduce_any(int64_t x, uint32_t q)      // non
 // middle line(s) + network + store of one group's block of D2 * L coefficients; v[h] = the lane's values of column half h
 // the loads of one thread-task: NV values at `step` apart, all issued before the first use.  Zq: 64-bit words narrowed to the
 // 32-bit working range; one out-of-range word sends the task through `c % q` like the reference's constructor.
-template <class AR, int NV>
+// STREAM: the words are touched once (tupSize 1): evict-first.  With several limbs per tuple the sectors are shared with the CTAs
+// of the other limbs and must stay in L2 until those have come by: default policy.
+template <bool STREAM, class TP>
+__device__ __forceinline__ TP w_ld(const TP* p) { if constexpr (STREAM) return __ldcs(p); else return __ldcg(p); }
+template <bool STREAM, class TP>
+__device__ __forceinline__ void w_st(TP* p, const TP v) { if constexpr (STREAM) __stcs(p, v); else __stcg(p, v); }
+
+template <class AR, bool STREAM, int NV>
 __device__ __forceinline__ void w_load(typename AR::T (&v)[NV], const typename AR::IO* __restrict__ src, const size_t step, const bool live,
                                        const uint32_t q)
 {
@@ -488,7 +497,7 @@ __device__ __forceinline__ void w_load(typename AR::T (&v)[NV], const typename A
     uint32_t hi_or = 0, lo_max = 0;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-      const int64_t raw = live ? __ldcs(src + (size_t)i * step) : 0;
+      const int64_t raw = live ? w_ld<STREAM>(src + (size_t)i * step) : 0;
       v[i] = (uint32_t)raw;
       hi_or |= (uint32_t)((uint64_t)raw >> 32);
       lo_max = max(lo_max, v[i]);
@@ -499,7 +508,7 @@ __device__ __forceinline__ void w_load(typename AR::T (&v)[NV], const typename A
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < NV; i++) v[i] = live ? __ldcs(src + (size_t)i * step) : make_double2(0.0, 0.0);
+    for (int i = 0; i < NV; i++) v[i] = live ? w_ld<STREAM>(src + (size_t)i * step) : make_double2(0.0, 0.0);
   }
 }
 
@@ -532,14 +541,14 @@ __device__ __forceinline__ void w_finish(typename AR::T (&v)[SH::H][SH::D2], con
           // narrow shapes (L <= 4) back through the tile for a coalesced third phase was measured too and is slower
           // (4095: 50 / 47, 5460: 50 / 48, 3640: 58 / 56): the extra barrier and tile pass cost more than the sectors save.
           if (K == 1 && (INV || SH::LL <= 1)) {
-            __stcs(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h)), make_longlong2(a, b));
+            w_st<true>(reinterpret_cast<longlong2*>(dst + w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h)), make_longlong2(a, b));
           } else {
-            __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, a);
-            __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, b);
+            w_st<K == 1>(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, a);
+            w_st<K == 1>(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, b);
           }
         } else {
-          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, v[h][2 * j]);
-          __stcs(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, v[h][2 * j + 1]);
+          w_st<K == 1>(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 0, h) * k, v[h][2 * j]);
+          w_st<K == 1>(dst + (size_t)w_out_pos<SH::LL, SH::L, INV>(l, j, 1, h) * k, v[h][2 * j + 1]);
         }
       }
     }
@@ -548,9 +557,8 @@ __device__ __forceinline__ void w_finish(typename AR::T (&v)[SH::H][SH::D2], con
 
 // ------------------------------------------------------------------ m = 2^a p^e (p_b^e_b): a group of L lanes per element
 template <class SH, bool INV, class AR, int K>
-__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
-k_fused_w1(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
-           const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
+__device__ __forceinline__ void w1_body(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
+                                        const WConsts<typename AR::T, SH::NC>& C, const int bid, const int nblk)
 {
   typedef typename AR::T T;
   const int k = K ? K : k_rt;
@@ -561,14 +569,22 @@ k_fused_w1(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt,
 #pragma unroll
   for (int i = 0; i < kWLaneRows; i++) lt[0][i] = C.lane_tw[i * 32 + lane];
   const int64_t nwt = (batch + SH::GPW - 1) / SH::GPW;      // warp-tasks: GPW elements each
-  for (int64_t wt = (int64_t)blockIdx.x * (kWThreads / 32) + warp; wt < nwt; wt += (int64_t)gridDim.x * (kWThreads / 32)) {
+  for (int64_t wt = (int64_t)bid * (kWThreads / 32) + warp; wt < nwt; wt += (int64_t)nblk * (kWThreads / 32)) {
     const int64_t e = wt * SH::GPW + sub;
     const bool live = e < batch;
     typename AR::IO* ebase = y + (size_t)(live ? e : 0) * SH::N * k + limb;
     T v[1][SH::D2];
-    w_load<AR>(v[0], ebase + (size_t)l * k, (size_t)SH::L * k, live, C.mod.q);
+    w_load<AR, K == 1>(v[0], ebase + (size_t)l * k, (size_t)SH::L * k, live, C.mod.q);
     w_finish<SH, INV, AR, K>(v, l, lt, C, A, ebase, k, live);
   }
+}
+
+template <class SH, bool INV, class AR, int K>
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
+k_fused_w1(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
+           const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
+{
+  w1_body<SH, INV, AR, K>(y, batch, k_rt, limb, C, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ------------------------------------------------------------------ m = 2^a (p_a^e_a) (p_b^e_b) p_c^e_c: two phases, on-chip tile
@@ -579,9 +595,8 @@ template <class SH, class AR> struct WTile {
 };
 
 template <class SH, bool INV, class AR, int K>
-__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
-k_fused_w2(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
-           const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
+__device__ __forceinline__ void w2_body(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
+                                        const WConsts<typename AR::T, SH::NC>& C, const int bid, const int nblk)
 {
   typedef typename SH::PC PC;
   typedef typename AR::T T;
@@ -601,14 +616,14 @@ k_fused_w2(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt,
   };
   if constexpr (AR::kZq) load_lane_table();      // complex: 40 registers per column half, loaded where phase 2 starts instead
   const int64_t ngroups = (batch + EPB - 1) / EPB;
-  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+  for (int64_t g = bid; g < ngroups; g += nblk) {
     const int64_t e0 = g * EPB;
     const int cnt = (int)(batch - e0 < EPB ? batch - e0 : EPB);
     // ---------------- phase 1: the last prime power; thread-task = (element slot, column), coefficients at stride COLS
     for (int t = threadIdx.x; t < cnt * COLS; t += kWThreads) {
       const int slot = t / COLS, col = t - slot * COLS;
       T v[ROWS];
-      w_load<AR>(v, y + ((size_t)(e0 + slot) * N + col) * k + limb, (size_t)COLS * k, true, C.mod.q);
+      w_load<AR, K == 1>(v, y + ((size_t)(e0 + slot) * N + col) * k + limb, (size_t)COLS * k, true, C.mod.q);
       pp_line<PC, INV, 1, SH::OFF_C>(v, 0, C, A);
       const int cd = col / SH::SUB, cx = col - cd * SH::SUB;
       T* dst = tile + slot * ROWS * RS + cd * SH::SRS + cx;
@@ -651,6 +666,43 @@ k_fused_w2(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt,
     }
     __syncthreads();
   }
+}
+
+template <class SH, bool INV, class AR, int K>
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
+k_fused_w2(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb,
+           const __grid_constant__ WConsts<typename AR::T, SH::NC> C)
+{
+  w2_body<SH, INV, AR, K>(y, batch, k_rt, limb, C, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// ------------------------------------------------------------------ tupSize > 1: KL limbs of the same elements in ONE launch
+// A limb's CTA uses 8 of every 8 k bytes, i.e. a part of every 32-byte sector of its elements; launched limb after limb, each
+// launch moves the batch ~6x through HBM (sector fetch for the load, read-fill + write-back for the partial store; ncu: 5.9x).
+// Here block b works on limb b % KL of element group b / KL, so the KL CTAs that share the sectors of a group are dispatched
+// together: the first fetch serves all of them from L2 and their partial writes merge there before the sectors go back.  Each limb
+// keeps its own compile-time constant offsets (one copy of the body per limb, selected once per CTA).
+template <class T, int NC, int KL>
+struct WConstsM { WConsts<T, NC> l[KL]; };
+
+template <class SH, bool INV, class AR, int KL>
+__global__ void __launch_bounds__(kWThreads, AR::kZq ? SH::MINB : wc_minb<SH, INV>())
+k_fused_wm(typename AR::IO* __restrict__ y, const int64_t batch, const int k_rt, const int limb0,
+           const __grid_constant__ WConstsM<typename AR::T, SH::NC, KL> CM)
+{
+  const int t = (int)blockIdx.x % KL, bid = (int)blockIdx.x / KL, nblk = (int)gridDim.x / KL;
+#define LOLB_WM_CASE(I)                                                                                          \
+  case I:                                                                                                        \
+    if constexpr (I < KL) {                                                                                      \
+      if constexpr (SH::TWO_PHASE) w2_body<SH, INV, AR, 0>(y, batch, k_rt, limb0 + I, CM.l[I < KL ? I : 0], bid, nblk);   \
+      else w1_body<SH, INV, AR, 0>(y, batch, k_rt, limb0 + I, CM.l[I < KL ? I : 0], bid, nblk);                  \
+    }                                                                                                            \
+    break;
+  switch (t) {
+    LOLB_WM_CASE(0) LOLB_WM_CASE(1) LOLB_WM_CASE(2) LOLB_WM_CASE(3)
+    default: break;
+  }
+#undef LOLB_WM_CASE
 }
 
 // ------------------------------------------------------------------ host: constants from the plan's root tables
@@ -919,6 +971,12 @@ int build_fused_w(const lolb_plan* pl, FusedW* F)
     F->cls[t] = w_class((uint64_t)pl->qs[t], pmax);
     if (F->cls[t] == WC_NONE) { F->shape = -1; return LOLB_OK; }
   }
+  if (k > 1) {      // one launch serves several limbs (k_fused_wm): all limbs in the widest class any of them needs (each class contains the narrower ones' moduli)
+    auto rank = [](int c) { return c == WC_S ? 0 : c == WC_S6 ? 1 : 2; };
+    int widest = F->cls[0];
+    for (int t = 1; t < k; t++) if (rank(F->cls[t]) > rank(widest)) widest = F->cls[t];
+    for (int t = 0; t < k; t++) F->cls[t] = widest;
+  }
   const int npe = (int)pl->pe.size();
   F->ok_fwd = pl->ru.size() == (size_t)npe;
   F->ok_inv = pl->ruinv.size() == (size_t)npe && (int)pl->mhatinv.size() == k;
@@ -1014,24 +1072,73 @@ int launch_shape_c(const lolb_plan* pl, const FusedWC* F, bool inverse, double2*
   return LOLB_OK;
 }
 
+// KL limbs (limb0 .. limb0 + KL - 1) of a Z_q plan in one launch
+template <class SH, bool INV, class AR, int KL>
+int launch_wm(const lolb_plan* pl, const FusedW* F, int limb0, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  typedef typename AR::T T;
+  static WConstsM<T, SH::NC, KL> CM;      // filled under the lock below: too large for the stack of a deep call chain
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < KL; i++) {
+    const int limb = limb0 + i;
+    CM.l[i].mod = F->mod[limb];
+    CM.l[i].lane_tw = F->d_lane + ((size_t)limb * 2 + (INV ? 1 : 0)) * 2 * kWLaneRows * 32;
+    const std::vector<T>& src = INV ? F->ci[limb] : F->cf[limb];
+    if ((int)src.size() != SH::OFF_C + SH::PC::n_consts) { set_error("fused_w: constant layout mismatch"); return LOLB_ERR_ARG; }
+    for (size_t j = 0; j < src.size(); j++) CM.l[i].c[j] = src[j];
+  }
+  int64_t groups_in_flight = (int64_t)pl->num_sms * SH::MINB / KL;
+  if (groups_in_flight < 1) groups_in_flight = 1;
+  size_t smem = 0;
+  if constexpr (SH::TWO_PHASE) {
+    constexpr int EPB = WTile<SH, AR>::EPB;
+    smem = WTile<SH, AR>::BYTES;
+    const int64_t groups = (batch + EPB - 1) / EPB;
+    if (groups_in_flight > groups) groups_in_flight = groups;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_fused_wm<SH, INV, AR, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "k_fused_wm shared memory");
+    }
+  } else {
+    const int64_t ctas = (batch + (kWThreads / 32) * SH::GPW - 1) / ((kWThreads / 32) * SH::GPW);
+    if (groups_in_flight > ctas) groups_in_flight = ctas;
+  }
+  k_fused_wm<SH, INV, AR, KL><<<(int)(groups_in_flight * KL), kWThreads, smem, st>>>(y, batch, pl->k, limb0, CM);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_fused_wm");
+  count_launch();
+  return LOLB_OK;
+}
+
+template <class SH, class AR>
+int launch_limbs(const lolb_plan* pl, const FusedW* F, bool inverse, int limb0, int kl, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const bool k1 = pl->k == 1;
+  switch (kl) {
+    case 1: return inverse ? (k1 ? launch_w<SH, true, AR, 1>(pl, F, limb0, y, batch, st) : launch_w<SH, true, AR, 0>(pl, F, limb0, y, batch, st))
+                           : (k1 ? launch_w<SH, false, AR, 1>(pl, F, limb0, y, batch, st) : launch_w<SH, false, AR, 0>(pl, F, limb0, y, batch, st));
+    case 2: return inverse ? launch_wm<SH, true, AR, 2>(pl, F, limb0, y, batch, st) : launch_wm<SH, false, AR, 2>(pl, F, limb0, y, batch, st);
+    case 3: return inverse ? launch_wm<SH, true, AR, 3>(pl, F, limb0, y, batch, st) : launch_wm<SH, false, AR, 3>(pl, F, limb0, y, batch, st);
+    case 4: return inverse ? launch_wm<SH, true, AR, 4>(pl, F, limb0, y, batch, st) : launch_wm<SH, false, AR, 4>(pl, F, limb0, y, batch, st);
+  }
+  return LOLB_ERR_ARG;
+}
+
 template <class SH>
 int launch_shape(const lolb_plan* pl, const FusedW* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
 {
-  for (int t = 0; t < pl->k; t++) {
+  const char* me = getenv("LOLB_W_MULTI");      // 0: one launch per limb (tests, A/B)
+  const bool multi = !me || atoi(me) != 0;
+  const int k = pl->k, step = multi ? 4 : 1;
+  for (int t = 0; t < k; t += step) {
+    const int kl = k - t < step ? k - t : step;
     int rc;
-    const bool m = F->cls[t] == WC_M, k1 = pl->k == 1;
     if (F->cls[t] == WC_S6) {
-      if constexpr (SH::PC::p > 6 || SH::PD::p > 6 || SH::PB::p > 6 || SH::PA::p > 6) {
-        rc = inverse ? (k1 ? launch_w<SH, true, WS6, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WS6, 0>(pl, F, t, y, batch, st))
-                     : (k1 ? launch_w<SH, false, WS6, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WS6, 0>(pl, F, t, y, batch, st));
-      } else rc = LOLB_FUSED_UNAVAILABLE;
-      if (rc) return rc;
-      continue;
-    }
-    if (inverse) rc = m ? (k1 ? launch_w<SH, true, WM, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WM, 0>(pl, F, t, y, batch, st))
-                        : (k1 ? launch_w<SH, true, WS, 1>(pl, F, t, y, batch, st) : launch_w<SH, true, WS, 0>(pl, F, t, y, batch, st));
-    else rc = m ? (k1 ? launch_w<SH, false, WM, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WM, 0>(pl, F, t, y, batch, st))
-                : (k1 ? launch_w<SH, false, WS, 1>(pl, F, t, y, batch, st) : launch_w<SH, false, WS, 0>(pl, F, t, y, batch, st));
+      if constexpr (SH::PC::p > 6 || SH::PD::p > 6 || SH::PB::p > 6 || SH::PA::p > 6) rc = launch_limbs<SH, WS6>(pl, F, inverse, t, kl, y, batch, st);
+      else rc = LOLB_FUSED_UNAVAILABLE;
+    } else if (F->cls[t] == WC_M) rc = launch_limbs<SH, WM>(pl, F, inverse, t, kl, y, batch, st);
+    else rc = launch_limbs<SH, WS>(pl, F, inverse, t, kl, y, batch, st);
     if (rc) return rc;
   }
   return LOLB_OK;

@@ -500,6 +500,39 @@ def test_complex_crt_fused_kernel_m14400(torch_cuda, oracle, k):
     assert rel_err(t.crtInv(x).cpu().numpy(), g.cpu().numpy()) <= 1e-12
 
 
+HOMOM_PRF_QS = [18869761, 19393921, 19918081, 25159681, 3144961, 7338241]      # lol-apps Examples/HomomPRFParams.hs:35-45 (the ones below 2^31)
+
+
+@pytest.mark.parametrize("m,qs", [(2912, HOMOM_PRF_QS[:2]), (5824, HOMOM_PRF_QS[:3]), (5824, HOMOM_PRF_QS[:4]), (11648, HOMOM_PRF_QS[:4]),
+                                  (3640, HOMOM_PRF_QS[:6]), (5460, HOMOM_PRF_QS[:5]), (4095, HOMOM_PRF_QS[:4]), (1728, [3457, 1002241, 10369]),
+                                  (5184, [10369, 1073089]), (2912, [8737, 14561, 3144961, 23297])], ids=lambda v: str(v))
+def test_fused_w_several_limbs_in_one_launch(torch_cuda, gpu_oracle, monkeypatch, m, qs):
+    """tupSize 2 ... 6 on the fused_w rings (the HomomPRF example's modulus chains): k_fused_wm runs up to four limbs of the same
+    elements in one launch (limbs of different arithmetic classes are promoted to the widest one).  Oracle parity on a sample,
+    bit-identical to one launch per limb and to the generic engine on the whole ragged batch, crtInv . crt = id."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    B = 41
+    rng = np.random.default_rng(m + len(qs))
+    pe, n, ru, rui, mh = _tables(m, qs)
+    t = CudaTensorRq(m, qs)
+    assert t.plan.kernel_name("CRT") == "fused_w" and t.plan.kernel_name("CRTInv") == "fused_w"
+    y = zq_input(rng, n, qs, batch=B)
+    y[3, :5] += np.array(qs) * 2                 # outside [0, q): reduced like the reference's constructor
+    x = torch.from_numpy(y).cuda()
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, 3, B - 1):
+        assert np.array_equal(f[b].cpu().numpy(), gpu_oracle.tensorCRTRq(y[b], pe, ru, qs)), b
+        assert np.array_equal(g[b].cpu().numpy(), gpu_oracle.tensorCRTInvRq(y[b], pe, rui, mh, qs)), b
+    xc = torch.from_numpy(y % np.array(qs)).cuda()
+    assert torch.equal(t.crtInv(f), xc) and torch.equal(t.crt(g), xc)
+    monkeypatch.setenv("LOLB_W_MULTI", "0")
+    assert torch.equal(t.crt(x), f) and torch.equal(t.crtInv(x), g)
+    monkeypatch.delenv("LOLB_W_MULTI")
+    t.plan.force_generic(True)
+    assert torch.equal(t.crt(x), f) and torch.equal(t.crtInv(x), g)
+
+
 @pytest.mark.parametrize("m,k", [(1728, 1), (5184, 1), (2912, 2), (728, 1), (3640, 1), (2016, 3), (5824, 1), (11648, 1), (5460, 2), (4095, 1)],
                          ids=lambda v: str(v))
 def test_complex_crt_fused_w_rings(torch_cuda, gpu_oracle, m, k):
