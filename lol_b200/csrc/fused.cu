@@ -15,7 +15,7 @@ int fused_a_decompose_crt(const lolb_plan* pl, const void* slot, const int64_t* 
 int fused_a_crt_mul(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y, const int64_t* b, int64_t batch,
                     int64_t b_batch, cudaStream_t st);
 
-// fused_w.cu
+// fused_w_impl.cuh (fused_w_p0..p4.cu)
 int fused_w_select(lolb_plan* pl, void** slot);
 void fused_w_release(void* slot);
 bool fused_w_available(const void* slot, bool inverse);

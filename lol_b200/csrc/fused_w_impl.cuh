@@ -1,4 +1,4 @@
-// fused_w.cu -- fused Z_q CRT / CRT^-1 for indices m = 2^a * (one to three odd prime powers): the reference's other
+// fused_w_impl.cuh -- fused Z_q CRT / CRT^-1 for indices m = 2^a * (one to three odd prime powers): the reference's other
 // benchmark rings (lol/Crypto/Lol/Benchmarks/Default.hs:41-48: F64*F27, F64*F81 and the Twace-Embed rings
 // F32*F7*F13, F8*F7*F13, F8*F5*F7*F13; lol-apps tunnel ring F64*F7*F13), one HBM read and one HBM write per ring element like fused_a.cu does for m = 14400.
 //
@@ -20,6 +20,9 @@
 //               per lane straight from HBM, line(s), network, stores.  No shared memory, no barrier.
 //   k_fused_w2  (m = 2^a .. p_c^e_c) phase 1: thread <- one column along ic from HBM, line, u32 tile in shared memory;
 //               phase 2: group of L lanes <- one ic-row of the tile, middle line(s), network, stores.
+#ifndef LOLB_W_PART
+#error "fused_w_impl.cuh is compiled through fused_w_p0.cu .. fused_w_p4.cu (LOLB_W_PART selects the kernels a translation unit instantiates)"
+#endif
 #include <complex>
 #include <cstdlib>
 #include <mutex>
@@ -1305,6 +1308,52 @@ void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
 
 }  // namespace
 
+// ------------------------------------------------------------------ the kernels are instantiated in five translation units
+// (a single one took six minutes of nvcc): Z_q shapes 0-1 / 2-5 / 6-9 in parts 0 / 1 / 2, complex shapes 0-4 / 5-9 in parts 3 / 4.
+// Part 0 also holds the host side (constants, selection, dispatch, the device-free emulation).  Plans cross the parts as void*.
+int fused_w_launch_p0(const lolb_plan* pl, const void* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_w_launch_p1(const lolb_plan* pl, const void* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_w_launch_p2(const lolb_plan* pl, const void* F, bool inverse, int64_t* y, int64_t batch, cudaStream_t st);
+int fused_w_launch_c_p3(const lolb_plan* pl, const void* F, bool inverse, double2* y, int64_t batch, cudaStream_t st);
+int fused_w_launch_c_p4(const lolb_plan* pl, const void* F, bool inverse, double2* y, int64_t batch, cudaStream_t st);
+
+#define W_CASE(N, SHT, CALL) case N: { typedef SHT SH; CALL; } break;
+#if LOLB_W_PART == 0
+#define W_PART_FN fused_w_launch_p0
+#define W_PART_CASES(CALL) W_CASE(0, SH_64_27, CALL) W_CASE(1, SH_64_81, CALL)
+#elif LOLB_W_PART == 1
+#define W_PART_FN fused_w_launch_p1
+#define W_PART_CASES(CALL) W_CASE(2, SH_32_7_13, CALL) W_CASE(3, SH_8_7_13, CALL) W_CASE(4, SH_8_5_7_13, CALL) W_CASE(5, SH_32_9_7, CALL)
+#elif LOLB_W_PART == 2
+#define W_PART_FN fused_w_launch_p2
+#define W_PART_CASES(CALL) W_CASE(6, SH_64_7_13, CALL) W_CASE(7, SH_128_7_13, CALL) W_CASE(8, SH_4_3_5_7_13, CALL) W_CASE(9, SH_9_5_7_13, CALL)
+#elif LOLB_W_PART == 3
+#define W_PART_FN fused_w_launch_c_p3
+#define W_PART_CASES(CALL) W_CASE(0, SH_64_27, CALL) W_CASE(1, SH_64_81, CALL) W_CASE(2, SH_32_7_13, CALL) W_CASE(3, SH_8_7_13, CALL) W_CASE(4, SH_8_5_7_13, CALL)
+#else
+#define W_PART_FN fused_w_launch_c_p4
+#define W_PART_CASES(CALL) W_CASE(5, SH_32_9_7, CALL) W_CASE(6, SH_64_7_13, CALL) W_CASE(7, SH_128_7_13, CALL) W_CASE(8, SH_4_3_5_7_13, CALL) W_CASE(9, SH_9_5_7_13, CALL)
+#endif
+
+#if LOLB_W_PART <= 2
+int W_PART_FN(const lolb_plan* pl, const void* Fv, bool inverse, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  const FusedW* F = (const FusedW*)Fv;
+  int rc = LOLB_FUSED_UNAVAILABLE;
+  switch (F->shape) { W_PART_CASES(rc = launch_shape<SH>(pl, F, inverse, y, batch, st)) default: break; }
+  return rc;
+}
+#else
+int W_PART_FN(const lolb_plan* pl, const void* Fv, bool inverse, double2* y, int64_t batch, cudaStream_t st)
+{
+  const FusedWC* F = (const FusedWC*)Fv;
+  int rc = LOLB_FUSED_UNAVAILABLE;
+  switch (F->shape) { W_PART_CASES(rc = launch_shape_c<SH>(pl, F, inverse, y, batch, st)) default: break; }
+  return rc;
+}
+#endif
+
+#if LOLB_W_PART == 0
 namespace {
 template <class FW, class BUILD>
 int select_impl(lolb_plan* pl, void** slot, BUILD build)
@@ -1357,9 +1406,8 @@ int fused_w_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   const FusedW* F = (const FusedW*)slot;
   if (!fused_w_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  int rc = LOLB_FUSED_UNAVAILABLE;
-  W_FOR_SHAPE(F, rc = launch_shape<SH>(pl, F, inverse, y, batch, st));
-  return rc;
+  return F->shape <= 1 ? fused_w_launch_p0(pl, F, inverse, y, batch, st)
+       : F->shape <= 5 ? fused_w_launch_p1(pl, F, inverse, y, batch, st) : fused_w_launch_p2(pl, F, inverse, y, batch, st);
 }
 
 int fused_wc_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st)
@@ -1367,9 +1415,7 @@ int fused_wc_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y
   const FusedWC* F = (const FusedWC*)slot;
   if (!fused_wc_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  int rc = LOLB_FUSED_UNAVAILABLE;
-  W_FOR_SHAPE(F, rc = launch_shape_c<SH>(pl, F, inverse, y, batch, st));
-  return rc;
+  return F->shape <= 4 ? fused_w_launch_c_p3(pl, F, inverse, y, batch, st) : fused_w_launch_c_p4(pl, F, inverse, y, batch, st);
 }
 
 }  // namespace lolb
@@ -1418,3 +1464,7 @@ extern "C" int lolb_fused_w_emulate_c(const PrimeExponent* peArr, hShort_t sizeO
   }
   return LOLB_OK;
 }
+
+#else
+}  // namespace lolb
+#endif  // LOLB_W_PART == 0

@@ -1,0 +1,3 @@
+// fused_w, translation unit 0 of 5: see fused_w_impl.cuh (LOLB_W_PART selects the kernels instantiated here)
+#define LOLB_W_PART 0
+#include "fused_w_impl.cuh"

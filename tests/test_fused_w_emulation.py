@@ -1,4 +1,4 @@
-"""fused_w (lol_b200/csrc/fused_w.cu) without a GPU: the library's host-built constants, the kernel's own line code compiled
+"""fused_w (lol_b200/csrc/fused_w_impl.cuh) without a GPU: the library's host-built constants, the kernel's own line code compiled
 for the host and a lane-by-lane replica of its exchange network, run on one ring element through
 `lolb_fused_w_emulate`, must reproduce the oracle's tensorCRTRq / tensorCRTInvRq bit for bit.
 
