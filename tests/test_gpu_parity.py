@@ -689,7 +689,14 @@ def _device_uniform(torch, B, n, qs, seed):
     return torch.cat(cols, dim=2).contiguous()
 
 
-@pytest.mark.parametrize("cfg,B", [(CONFIG_A, 65536), (CONFIG_C, 8192), (CONFIG_B, 256)], ids=["A", "C", "B"])
+# the reference's other benchmark rings at the batch sizes bench.py times them at (lol Benchmarks/Default.hs:41-48; lol-apps
+# Benchmarks/Default.hs:52-82 tunnel rings at q = 3144961; Examples/HomomPRFParams.hs modulus chain ZQ4 on H1')
+FULL_SIZE = [(CONFIG_A, 65536), (CONFIG_C, 8192), (CONFIG_B, 256), ((1728, [3457]), 131072), ((5184, [10369]), 40960), ((2912, [8737]), 61440),
+             ((3640, [14561]), 61440), ((11648, [3144961]), 15360), ((5460, [3144961]), 61440), ((4095, [3144961]), 40960),
+             ((5824, [25159681, 19918081, 19393921, 18869761]), 8192)]
+
+
+@pytest.mark.parametrize("cfg,B", FULL_SIZE, ids=["A", "C", "B"] + [f"m={c[0]}/k={len(c[1])}" for c, _ in FULL_SIZE[3:]])
 def test_full_size_properties(torch_cuda, oracle, cfg, B):
     torch = torch_cuda
     from lol_b200.tensor import CudaTensorRq
