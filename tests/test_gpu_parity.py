@@ -843,3 +843,59 @@ def test_device_memory_entry_points_without_torch(torch_cuda, oracle):
         capi.dev_free(b)
     assert np.array_equal(back, y)
     assert np.array_equal(f, oracle.tensorCRTRq(y, pe, ru, qs))
+
+
+# ------------------------------------------------------------------ guard zones (compute-sanitizer is not available on the pool)
+GUARDED = [(14400, [14401]), (14400, [1008001, 1065601]), (14400, [14401, 1008001, 1065601, 429336001]), (1728, [3457]), (5184, [10369]),
+           (2912, [8737]), (2912, [3144961]), (3640, [14561]), (11648, [3144961]), (5460, [3144961]), (4095, [3144961]), (2016, [2017]), (728, [8737]),
+           (5824, HOMOM_PRF_QS[:4]), (2912, HOMOM_PRF_QS[:6]), (1728, [3457, 1002241, 10369]), (2 ** 16, CONFIG_B[1]), (2 ** 15, CONFIG_B[1][:2]),
+           (2 ** 11, [12289]), (2 ** 13, CONFIG_B[1]), (21, [43, 127]), (45, [2148249601])]
+
+
+@pytest.mark.parametrize("m,qs", GUARDED, ids=lambda v: str(v))
+@pytest.mark.parametrize("B", [1, 37], ids=lambda v: f"B={v}")
+def test_kernels_write_inside_their_batch_only(torch_cuda, m, qs, B):
+    """Out-of-bounds WRITES of the in-place kernels, found with sentinel-filled guard zones on both sides of a ragged batch
+    (the pool has no compute-sanitizer): CRT, CRT^-1, L, L^-1, the g operators and mulRq must leave the guards untouched."""
+    torch = torch_cuda
+    from lol_b200 import capi
+    from lol_b200.tensor import CudaTensorRq
+    t = CudaTensorRq(m, qs)
+    n, k = t.n, t.k
+    G = 4096                                                 # guard words on each side
+    sentinel = -0x5A5A5A5A5A5A5A5B
+    buf = torch.full((G + B * n * k + G,), sentinel, dtype=torch.int64, device="cuda")
+    body = buf[G:G + B * n * k].view(B, n, k)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(m)
+    for i, q in enumerate(qs):
+        body[:, :, i] = torch.randint(0, q, (B, n), dtype=torch.int64, device="cuda", generator=g)
+    other = body.clone()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    ptr = buf.data_ptr() + 8 * G
+    for name in ("CRT", "CRTInv", "L", "LInv", "GPow", "GDec", "GInvPow", "GInvDec"):
+        capi.check(t.plan.op(name, ptr, B, st))
+    capi.check(t.plan.mul(ptr, other.data_ptr(), B, B, st))
+    torch.cuda.synchronize()
+    assert bool((buf[:G] == sentinel).all()) and bool((buf[G + B * n * k:] == sentinel).all())
+    assert int(body.min()) >= 0
+
+
+@pytest.mark.parametrize("m,k", [(14400, 1), (1728, 1), (5184, 1), (2912, 2), (11648, 1), (5460, 1), (4095, 3), (21, 1)], ids=lambda v: str(v))
+def test_complex_kernels_write_inside_their_batch_only(torch_cuda, m, k):
+    torch = torch_cuda
+    from lol_b200 import capi
+    from lol_b200.tensor import CudaTensorComplex
+    t = CudaTensorComplex(m, k)
+    n, B, G = t.n, 19, 2048
+    buf = torch.full((G + B * n * k + G,), complex(-7.25e300, 3.5e299), dtype=torch.complex128, device="cuda")
+    body = buf[G:G + B * n * k].view(B, n, k)
+    body.copy_(torch.randn(B, n, k, dtype=torch.complex128, device="cuda"))
+    st = int(torch.cuda.current_stream().cuda_stream)
+    ptr = buf.data_ptr() + 16 * G
+    for name in ("CRTC", "CRTInvC"):
+        capi.check(t.plan.op(name, ptr, B, st))
+    torch.cuda.synchronize()
+    guard = torch.tensor(complex(-7.25e300, 3.5e299), dtype=torch.complex128, device="cuda")
+    assert bool((buf[:G] == guard).all()) and bool((buf[G + B * n * k:] == guard).all())
+    assert bool(torch.isfinite(torch.view_as_real(body)).all()) and float(torch.view_as_real(body).abs().max()) < 1e6
