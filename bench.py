@@ -452,6 +452,10 @@ def run_gpu_arm(args):
             for name in ("CRT", "CRTInv"):
                 ms = timed(lambda: capi.check(tc.plan.op(name, xc.data_ptr(), Bc, stream)))
                 rec.add(label, name, ms, 16 * tc.n * kc * Bc, Bc, kernel=tc.plan.kernel_name(name), batch=Bc)
+            if tc.plan.kernel_name("L") != "identity":      # the linear operators of the path on this ring (one representative of each cost)
+                for name in ("L", "GInvDec"):
+                    ms = timed(lambda: capi.check(tc.plan.op(name, xc.data_ptr(), Bc, stream)))
+                    rec.add(label, name, ms, 16 * tc.n * kc * Bc, Bc, kernel=tc.plan.kernel_name(name), batch=Bc)
             xb = xc.clone()
             ms = timed(lambda: capi.check(tc.plan.mul(xc.data_ptr(), xb.data_ptr(), Bc, Bc, stream)))
             rec.add(label, "mulRq", ms, 24 * tc.n * kc * Bc, Bc, kernel=tc.plan.kernel_name("mulRq"), batch=Bc)

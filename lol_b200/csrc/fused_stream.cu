@@ -8,6 +8,7 @@
 // digit, so each warp instruction touches contiguous memory), applies axis A then axis B exactly over the
 // integers in int64 (|entries| <= p, <= p terms: no overflow for q < 2^32), reduces once per axis modulo q,
 // and stores.  Algorithmic traffic: 16 bytes per coefficient, one read and one write.
+#include <cstdlib>
 #include <type_traits>
 
 #include "fused.cuh"
@@ -241,47 +242,75 @@ static int odd_axes(const lolb_plan* pl, int (&p)[4], int64_t (&rts)[4])
   return cnt;
 }
 
-const char* fused_stream_line_name(const lolb_plan* pl)
+// The operators of different prime axes commute (a Kronecker product), so an index with more odd primes than one kernel's tile
+// can hold is served by a few launches, each applying one or two axes: every launch is one read and one write of the batch.
+// Kernels exist for the single primes 3, 5, 7, 13 and the pairs below; preference = fewest launches for the reference's rings
+// ({7,13}, {5,7,13}, {3,5,7,13}: two launches each).
+struct LineStep { int pa, pb; int64_t ra, rb; };
+
+static int line_steps(const lolb_plan* pl, LineStep (&steps)[4])
 {
   int p[4]; int64_t r[4];
   const int cnt = odd_axes(pl, p, r);
-  if (cnt == 0) return "identity";
-  if (cnt == 1 && (p[0] == 3 || p[0] == 5 || p[0] == 7)) return "line_stream";
-  if (cnt == 2 && p[0] == 3 && (p[1] == 5 || p[1] == 7)) return "line_stream";
-  return "generic";
+  if (cnt > 4) return -1;
+  for (int i = 0; i < cnt; i++) if (p[i] != 3 && p[i] != 5 && p[i] != 7 && p[i] != 13) return -1;
+  // (a 6 x 12 tile for {7,13} in one launch was measured: 255 registers + 0.8 KB of spills, 32 % of the roofline at m = 2912 and 10 % at
+  // m = 728 against 48 % / 46 % for the two single-axis launches -- not instantiated)
+  static const int pref[][2] = {{5, 7}, {3, 13}, {3, 5}, {3, 7}};
+  bool used[4] = {false, false, false, false};
+  int ns = 0;
+  for (const auto& pr : pref) {
+    int ia = -1, ib = -1;
+    for (int i = 0; i < cnt; i++) { if (!used[i] && p[i] == pr[0]) ia = i; if (!used[i] && p[i] == pr[1]) ib = i; }
+    if (ia >= 0 && ib >= 0) { used[ia] = used[ib] = true; steps[ns++] = LineStep{p[ia], p[ib], r[ia], r[ib]}; }
+  }
+  for (int i = 0; i < cnt; i++) if (!used[i]) steps[ns++] = LineStep{p[i], 1, r[i], 0};
+  return ns;
+}
+
+const char* fused_stream_line_name(const lolb_plan* pl)
+{
+  LineStep st[4];
+  const int ns = line_steps(pl, st);
+  return ns == 0 ? "identity" : ns > 0 ? "line_stream" : "generic";
 }
 
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
 {
-  int p[4]; int64_t r[4];
-  const int cnt = odd_axes(pl, p, r);
+  LineStep steps[4];
+  const int ns = line_steps(pl, steps);
   if (batch <= 0) return LOLB_OK;
-  if (cnt == 0) {
-    // every prime-index operator is the identity for p = 2 (l.cpp:35, g.cpp:18,39,62,94) and rad_odd = 1:
-    // canonical input is already the result, no launch
-    return LOLB_OK;
-  }
-  LineGeom G{};
-  G.n = pl->n; G.k = pl->k;
-  G.RA = (int32_t)r[0];
-  if (cnt == 1) {
-    G.RB = pl->n; G.M = (int32_t)(pl->n / (r[0] * (p[0] - 1))); G.tiles = pl->n / (p[0] - 1);
-    // with a single axis "hi" is always 0: fold everything above the axis into `mid`
-    switch (p[0]) {
-      case 3: return dispatch_kind<3, 1>(pl, kind, G, zc, scale, y, batch, st);
-      case 5: return dispatch_kind<5, 1>(pl, kind, G, zc, scale, y, batch, st);
-      case 7: return dispatch_kind<7, 1>(pl, kind, G, zc, scale, y, batch, st);
-      default: return LOLB_FUSED_UNAVAILABLE;
+  if (ns < 0) return LOLB_FUSED_UNAVAILABLE;
+  // ns == 0: every prime-index operator is the identity for p = 2 (l.cpp:35, g.cpp:18,39,62,94) and rad_odd = 1:
+  // canonical input is already the result, no launch
+  for (int i = 0; i < ns; i++) {
+    const LineStep& S = steps[i];
+    const bool sc = scale && i == ns - 1;      // the rad_odd^-1 factor of the divisions by g rides on the last launch
+    LineGeom G{};
+    G.n = pl->n; G.k = pl->k;
+    G.RA = (int32_t)S.ra;
+    int rc;
+    if (S.pb == 1) {
+      // a single axis: "hi" is always 0, everything above the axis folds into `mid`
+      G.RB = pl->n; G.M = (int32_t)(pl->n / (S.ra * (S.pa - 1))); G.tiles = pl->n / (S.pa - 1);
+      switch (S.pa) {
+        case 3: rc = dispatch_kind<3, 1>(pl, kind, G, zc, sc, y, batch, st); break;
+        case 5: rc = dispatch_kind<5, 1>(pl, kind, G, zc, sc, y, batch, st); break;
+        case 7: rc = dispatch_kind<7, 1>(pl, kind, G, zc, sc, y, batch, st); break;
+        default: rc = dispatch_kind<13, 1>(pl, kind, G, zc, sc, y, batch, st); break;
+      }
+    } else {
+      G.RB = (int32_t)S.rb;
+      G.M = (int32_t)(S.rb / (S.ra * (S.pa - 1)));
+      G.tiles = pl->n / ((S.pa - 1) * (S.pb - 1));
+      if (S.pa == 5) rc = dispatch_kind<5, 7>(pl, kind, G, zc, sc, y, batch, st);
+      else if (S.pb == 13) rc = dispatch_kind<3, 13>(pl, kind, G, zc, sc, y, batch, st);
+      else if (S.pb == 5) rc = dispatch_kind<3, 5>(pl, kind, G, zc, sc, y, batch, st);
+      else rc = dispatch_kind<3, 7>(pl, kind, G, zc, sc, y, batch, st);
     }
+    if (rc) return rc;
   }
-  if (cnt == 2 && p[0] == 3 && (p[1] == 5 || p[1] == 7)) {
-    G.RB = (int32_t)r[1];
-    G.M = (int32_t)(r[1] / (r[0] * (p[0] - 1)));
-    G.tiles = pl->n / ((p[0] - 1) * (p[1] - 1));
-    if (p[1] == 5) return dispatch_kind<3, 5>(pl, kind, G, zc, scale, y, batch, st);
-    return dispatch_kind<3, 7>(pl, kind, G, zc, scale, y, batch, st);
-  }
-  return LOLB_FUSED_UNAVAILABLE;
+  return LOLB_OK;
 }
 
 int fused_stream_mul(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st)
