@@ -108,59 +108,74 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
   const size_t off = ((size_t)lo + (size_t)G.RA * DA * mid + (size_t)G.RB * DB * hi) * k + limb;
   const size_t sa = (size_t)G.RA * k, sb = (size_t)G.RB * k;
   typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
-  for (int64_t e = blockIdx.y; e < batch; e += gridDim.y) {
-    int64_t* base = y + (size_t)e * G.n * k + off;
-    int64_t raw[DB][DA];
+  // U ring elements per iteration, so that a thread with a small tile (2 values for a single axis of p = 3) still has 8 loads in flight
+  constexpr int U = DA * DB <= 2 ? 4 : DA * DB <= 4 ? 2 : 1;
+  for (int64_t e0 = (int64_t)blockIdx.y * U; e0 < batch; e0 += (int64_t)gridDim.y * U) {
+    int64_t raw[U][DB][DA];      // every load is issued before the first use
 #pragma unroll
-    for (int b = 0; b < DB; b++)
+    for (int u = 0; u < U; u++) {
+      const int64_t* base = y + (size_t)(e0 + u < batch ? e0 + u : e0) * G.n * k + off;
 #pragma unroll
-      for (int a = 0; a < DA; a++) raw[b][a] = __ldcs(base + sa * a + sb * b);
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) raw[u][b][a] = __ldcs(base + sa * a + sb * b);
+    }
     // canonical input is the contract; anything else is reduced first like `c % q` (types.h:62-66)
     bool odd_input = false;
 #pragma unroll
-    for (int b = 0; b < DB; b++)
+    for (int u = 0; u < U; u++)
 #pragma unroll
-      for (int a = 0; a < DA; a++) odd_input |= (uint64_t)raw[b][a] >= (uint64_t)q;
+      for (int b = 0; b < DB; b++)
+#pragma unroll
+        for (int a = 0; a < DA; a++) odd_input |= (uint64_t)raw[u][b][a] >= (uint64_t)q;
     if (odd_input) {
 #pragma unroll
-      for (int b = 0; b < DB; b++)
-#pragma unroll
-        for (int a = 0; a < DA; a++) { int64_t r = raw[b][a] % (int64_t)q; raw[b][a] = r < 0 ? r + q : r; }
-    }
-    I v[DB][DA];
-#pragma unroll
-    for (int b = 0; b < DB; b++)
-#pragma unroll
-      for (int a = 0; a < DA; a++) v[b][a] = (I)raw[b][a];
-#pragma unroll
-    for (int b = 0; b < DB; b++) {
-      line_op<KIND, PA, I>(v[b]);
-#pragma unroll
-      for (int a = 0; a < DA; a++)
-        v[b][a] = reduce_biased(v[b][a], biasA, q, mu);
-    }
-    if constexpr (PB > 1) {
-#pragma unroll
-      for (int a = 0; a < DA; a++) {
-        I w[DB];
-#pragma unroll
-        for (int b = 0; b < DB; b++) w[b] = v[b][a];
-        line_op<KIND, PB, I>(w);
+      for (int u = 0; u < U; u++)
 #pragma unroll
         for (int b = 0; b < DB; b++)
-          v[b][a] = reduce_biased(w[b], biasB, q, mu);
-      }
+#pragma unroll
+          for (int a = 0; a < DA; a++) { int64_t r = raw[u][b][a] % (int64_t)q; raw[u][b][a] = r < 0 ? r + q : r; }
     }
-    if (scale) {
+    I v[U][DB][DA];
+#pragma unroll
+    for (int u = 0; u < U; u++)
 #pragma unroll
       for (int b = 0; b < DB; b++)
 #pragma unroll
-        for (int a = 0; a < DA; a++) v[b][a] = (I)barrett64((uint64_t)(uint32_t)v[b][a] * s, q, mu);
+        for (int a = 0; a < DA; a++) v[u][b][a] = (I)raw[u][b][a];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int b = 0; b < DB; b++) {
+        line_op<KIND, PA, I>(v[u][b]);
+#pragma unroll
+        for (int a = 0; a < DA; a++) v[u][b][a] = reduce_biased(v[u][b][a], biasA, q, mu);
+      }
+      if constexpr (PB > 1) {
+#pragma unroll
+        for (int a = 0; a < DA; a++) {
+          I w[DB];
+#pragma unroll
+          for (int b = 0; b < DB; b++) w[b] = v[u][b][a];
+          line_op<KIND, PB, I>(w);
+#pragma unroll
+          for (int b = 0; b < DB; b++) v[u][b][a] = reduce_biased(w[b], biasB, q, mu);
+        }
+      }
+      if (scale) {
+#pragma unroll
+        for (int b = 0; b < DB; b++)
+#pragma unroll
+          for (int a = 0; a < DA; a++) v[u][b][a] = (I)barrett64((uint64_t)(uint32_t)v[u][b][a] * s, q, mu);
+      }
+      if (e0 + u < batch) {
+        int64_t* base = y + (size_t)(e0 + u) * G.n * k + off;
+#pragma unroll
+        for (int b = 0; b < DB; b++)
+#pragma unroll
+          for (int a = 0; a < DA; a++) __stcs(base + sa * a + sb * b, (int64_t)(uint32_t)v[u][b][a]);
+      }
     }
-#pragma unroll
-    for (int b = 0; b < DB; b++)
-#pragma unroll
-      for (int a = 0; a < DA; a++) __stcs(base + sa * a + sb * b, (int64_t)(uint32_t)v[b][a]);
   }
 }
 
@@ -191,8 +206,9 @@ int launch_line_n(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bo
   int threads = per_elem >= 256 ? 256 : ((per_elem + 31) / 32) * 32;
   for (int c = 256; c >= 128; c -= 32) if (per_elem % c == 0) { threads = c; break; }   // avoid a ragged last block
   dim3 grid((per_elem + threads - 1) / threads, 1, 1);
+  constexpr int DT = (PA - 1) * (PB > 1 ? PB - 1 : 1), U = DT <= 2 ? 4 : DT <= 4 ? 2 : 1;      // elements per iteration (k_line_stream)
   int64_t gy = ((int64_t)pl->num_sms * 2048 / threads + grid.x - 1) / grid.x * 2;     // ~2 waves of resident threads
-  if (gy > batch) gy = batch;
+  if (gy > (batch + U - 1) / U) gy = (batch + U - 1) / U;
   if (gy > 65535) gy = 65535;
   grid.y = (unsigned)gy;
   k_line_stream<KIND, PA, PB, NARROW><<<grid, threads, 0, st>>>(y, batch, G, zc, scale ? 1 : 0);
