@@ -179,6 +179,88 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
   }
 }
 
+// ------------------------------------------------------------------ the same operators with the ring elements staged in shared memory
+// For indices with more odd-prime axes than a register tile can hold ({7,13}: 72 values) or with short runs below the axes (m = 5460,
+// 4095: 16- / 32-byte runs per lane group), a CTA loads whole ring elements (tupSize 1, contiguous 16-byte loads) into a u32 tile,
+// runs one in-place pass per odd-prime axis (a thread per line of p - 1 words, consecutive threads on consecutive lines) and
+// writes the elements back the same way: one HBM round trip for any number of axes.
+struct TileGeom {
+  int32_t n, naxes, epb;
+  int32_t p[4], rts[4], lines[4];
+  uint32_t m_rts[4];              // ceil(2^32 / d): exact floor(x / d) by __umulhi for x d < 2^32
+};
+
+__device__ __forceinline__ int fdiv(uint32_t x, int d, uint32_t magic) { return d == 1 ? (int)x : (int)__umulhi(x, magic); }
+
+template <int KIND, int P, typename I>
+__device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, const int ax, const int units, const ZqConsts& Z, const bool scale)
+{
+  constexpr int D = P - 1;
+  const int rts = G.rts[ax], lines = G.lines[ax];
+  const int total = units * lines;
+  for (int L = threadIdx.x; L < total; L += blockDim.x) {
+    // line L of the CTA's elements: element e, block hi, offset lo -> e n + hi rts D + lo = (L / rts) rts D + lo: one division per line
+    const int uh = fdiv((uint32_t)L, rts, G.m_rts[ax]), lo = L - uh * rts;
+    uint32_t* base = tile + (size_t)uh * rts * D + lo;
+    const uint32_t q = Z.q[0];
+    const uint64_t mu = Z.mu[0];
+    I v[D];
+#pragma unroll
+    for (int a = 0; a < D; a++) v[a] = (I)base[a * rts];
+    line_op<KIND, P, I>(v);
+    const int64_t bias = (int64_t)q * (P * P);
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+      uint32_t r = (uint32_t)reduce_biased(v[a], bias, q, mu);
+      if (scale) r = barrett64((uint64_t)r * Z.scale[0], q, mu);
+      base[a * rts] = r;
+    }
+  }
+}
+
+template <int KIND, bool NARROW>
+__global__ void __launch_bounds__(256)
+k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ TileGeom G, const __grid_constant__ ZqConsts Z, int scale)
+{
+  typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
+  extern __shared__ __align__(16) uint32_t line_tile[];
+  const uint32_t q = Z.q[0];
+  const int64_t ngroups = (batch + G.epb - 1) / G.epb;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t e0 = g * G.epb;
+    const int cnt = (int)(batch - e0 < G.epb ? batch - e0 : G.epb);
+    longlong2* src = reinterpret_cast<longlong2*>(y + (size_t)e0 * G.n);
+    const int pairs = cnt * G.n / 2;      // n is even (checked by the host)
+    // ---- in: word w of the piece -> tile[w]
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+      const longlong2 r = __ldcs(src + i);
+      uint32_t c0 = (uint32_t)r.x, c1 = (uint32_t)r.y;
+      if ((uint64_t)r.x >= (uint64_t)q) { int64_t t = r.x % (int64_t)q; c0 = (uint32_t)(t < 0 ? t + q : t); }      // like the reference's c % q
+      if ((uint64_t)r.y >= (uint64_t)q) { int64_t t = r.y % (int64_t)q; c1 = (uint32_t)(t < 0 ? t + q : t); }
+      *reinterpret_cast<uint2*>(line_tile + 2 * i) = make_uint2(c0, c1);
+    }
+    __syncthreads();
+    // ---- one pass per odd-prime axis, in place
+    for (int ax = 0; ax < G.naxes; ax++) {
+      const bool sc = scale && ax == G.naxes - 1;
+      switch (G.p[ax]) {
+        case 3: tile_axis<KIND, 3, I>(line_tile, G, ax, cnt, Z, sc); break;
+        case 5: tile_axis<KIND, 5, I>(line_tile, G, ax, cnt, Z, sc); break;
+        case 7: tile_axis<KIND, 7, I>(line_tile, G, ax, cnt, Z, sc); break;
+        case 11: tile_axis<KIND, 11, I>(line_tile, G, ax, cnt, Z, sc); break;
+        default: tile_axis<KIND, 13, I>(line_tile, G, ax, cnt, Z, sc); break;
+      }
+      __syncthreads();
+    }
+    // ---- out
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+      const uint2 v = *reinterpret_cast<const uint2*>(line_tile + 2 * i);
+      __stcs(src + i, make_longlong2((int64_t)v.x, (int64_t)v.y));
+    }
+    __syncthreads();
+  }
+}
+
 // coefficient-wise product, two coefficients (16 bytes) per thread per operand
 __global__ void __launch_bounds__(256)
 k_mul_stream(longlong2* __restrict__ a, const longlong2* __restrict__ b, int64_t pairs, int64_t b_pairs, int k,
@@ -284,18 +366,95 @@ static int line_steps(const lolb_plan* pl, LineStep (&steps)[4])
   return ns;
 }
 
+static uint32_t magic_div(uint32_t d) { return (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); }      // exact floor(x / d) by umulhi while x d < 2^32
+
+// the shared-memory kernel: odd primes from {3, 5, 7, 11, 13}, at most four odd axes, n k even, one element within the opt-in shared memory
+static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
+{
+  int p[4]; int64_t r[4];
+  const int cnt = odd_axes(pl, p, r);
+  if (pl->k != 1 || cnt < 1 || cnt > 4) return false;
+  for (int i = 0; i < cnt; i++) if (p[i] != 3 && p[i] != 5 && p[i] != 7 && p[i] != 11 && p[i] != 13) return false;
+  if ((pl->n & 1) || pl->n > 40960) return false;
+  G->n = pl->n;
+  G->naxes = cnt;
+  // measured 2048 / 4096 / 8192 / 16384 words per CTA: m = 2912 L 50 / 60 / 55 / 58 %, m = 5460 38 / 49 / 47 / 46 % of HBM
+  static const int tile_words = [] { const char* e = getenv("LOLB_LINE_TILE_WORDS"); return e ? atoi(e) : 4096; }();
+  int64_t epb = tile_words / pl->n;
+  if (epb < 1) epb = 1;
+  G->epb = (int32_t)epb;
+  for (int i = 0; i < cnt; i++) {
+    G->p[i] = p[i]; G->rts[i] = (int32_t)r[i]; G->lines[i] = pl->n / (p[i] - 1);
+    G->m_rts[i] = magic_div((uint32_t)r[i]);
+  }
+  return true;
+}
+
+template <int KIND>
+static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
+{
+  bool narrow = true;
+  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * 13 * 13 < ((int64_t)1 << 31);
+  const size_t smem = (size_t)G.epb * G.n * sizeof(uint32_t);
+  const int64_t groups = (batch + G.epb - 1) / G.epb;
+  int per_sm = (int)(200 * 1024 / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > groups) grid = groups;
+  cudaError_t e = cudaSuccess;
+  auto go = [&](auto kern) {
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) kern<<<(int)grid, 256, smem, st>>>(y, batch, G, zc, scale ? 1 : 0);
+  };
+  if (narrow) go(k_line_tile<KIND, true>); else go(k_line_tile<KIND, false>);
+  if (e != cudaSuccess) return cuda_fail(e, "k_line_tile shared memory");
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_line_tile");
+  count_launch();
+  return LOLB_OK;
+}
+
+// which kernel serves the plan: 0 identity, 1 register tiles (one launch), 2 shared-memory tile, 3 register tiles in several launches, -1 none
+static int line_route(const lolb_plan* pl, LineStep (&st)[4], int* nsteps, TileGeom* G)
+{
+  const int ns = line_steps(pl, st);
+  *nsteps = ns;
+  if (ns == 0) return 0;
+  if (ns == 1) return 1;
+  static const bool use_tile = [] { const char* e = getenv("LOLB_LINE_TILE"); return !e || atoi(e) != 0; }();
+  if (use_tile && line_tile_geom(pl, G)) return 2;      // tupSize 1 only: with several limbs two register-tile launches measured faster (46 % against 36 % at m = 5824, k = 4)
+  return ns > 1 ? 3 : -1;
+}
+
 const char* fused_stream_line_name(const lolb_plan* pl)
 {
   LineStep st[4];
-  const int ns = line_steps(pl, st);
-  return ns == 0 ? "identity" : ns > 0 ? "line_stream" : "generic";
+  TileGeom G;
+  int ns;
+  const int route = line_route(pl, st, &ns, &G);
+  return route == 0 ? "identity" : route == 2 ? "line_tile" : route > 0 ? "line_stream" : "generic";
 }
 
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
 {
   LineStep steps[4];
-  const int ns = line_steps(pl, steps);
+  TileGeom TG;
+  int ns;
+  const int route = line_route(pl, steps, &ns, &TG);
   if (batch <= 0) return LOLB_OK;
+  if (route < 0) return LOLB_FUSED_UNAVAILABLE;
+  if (route == 2 && !((uintptr_t)y & 15)) {
+    switch (kind) {
+      case PASS_L: return launch_line_tile<PASS_L>(pl, TG, zc, scale, y, batch, st);
+      case PASS_LINV: return launch_line_tile<PASS_LINV>(pl, TG, zc, scale, y, batch, st);
+      case PASS_GPOW: return launch_line_tile<PASS_GPOW>(pl, TG, zc, scale, y, batch, st);
+      case PASS_GDEC: return launch_line_tile<PASS_GDEC>(pl, TG, zc, scale, y, batch, st);
+      case PASS_GINVPOW: return launch_line_tile<PASS_GINVPOW>(pl, TG, zc, scale, y, batch, st);
+      case PASS_GINVDEC: return launch_line_tile<PASS_GINVDEC>(pl, TG, zc, scale, y, batch, st);
+      default: return LOLB_FUSED_UNAVAILABLE;
+    }
+  }
   if (ns < 0) return LOLB_FUSED_UNAVAILABLE;
   // ns == 0: every prime-index operator is the identity for p = 2 (l.cpp:35, g.cpp:18,39,62,94) and rad_odd = 1:
   // canonical input is already the result, no launch
