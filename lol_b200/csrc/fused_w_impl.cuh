@@ -899,7 +899,9 @@ typedef WShape<7, PPT<7, 1>, PPNone, PPNone, PPT<13, 1>, 1, 8> SH_128_7_13;  // 
 typedef WShape<2, PPT<3, 1>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 8, 8> SH_4_3_5_7_13;      // m = 5460 (n = 1152; tunnel H4): 7 in the tile
 typedef WShape<0, PPT<3, 2>, PPT<5, 1>, PPT<7, 1>, PPT<13, 1>, 4, 6> SH_9_5_7_13;        // m = 4095 (n = 1728; tunnel H5): odd index, no network
 
-constexpr int kNumShapes = 10;
+typedef WShape<6, PPT<7, 1>, PPNone, PPNone, PPNone, 1, 8> SH_64_7;      // m = 448 (n = 192): the plaintext-side ring H1 = F64*F7 of the tunnel benchmark / HomomPRF example
+
+constexpr int kNumShapes = 11;
 
 template <class T>
 struct FusedWT {
@@ -931,7 +933,7 @@ bool shape_matches(const lolb_plan* pl, const WShapeId& id, int* pmax)
 
 const WShapeId kShapeIds[kNumShapes] = {shape_id<SH_64_27>(), shape_id<SH_64_81>(), shape_id<SH_32_7_13>(),
                                         shape_id<SH_8_7_13>(), shape_id<SH_8_5_7_13>(), shape_id<SH_32_9_7>(), shape_id<SH_64_7_13>(),
-                                        shape_id<SH_128_7_13>(), shape_id<SH_4_3_5_7_13>(), shape_id<SH_9_5_7_13>()};
+                                        shape_id<SH_128_7_13>(), shape_id<SH_4_3_5_7_13>(), shape_id<SH_9_5_7_13>(), shape_id<SH_64_7>()};
 
 // host-side constants of one plan (no CUDA calls): shared by fused_w_select and the device-free emulation
 template <class FW, class FLD, class MKTAB>
@@ -1303,6 +1305,7 @@ void emulate_dispatch(const FusedW* F, bool inverse, int k, int64_t* y)
     case 7: { typedef SH_128_7_13 SH; CALL; } break;               \
     case 8: { typedef SH_4_3_5_7_13 SH; CALL; } break;             \
     case 9: { typedef SH_9_5_7_13 SH; CALL; } break;               \
+    case 10: { typedef SH_64_7 SH; CALL; } break;                  \
     default: break;                                                \
   }
 
@@ -1320,7 +1323,7 @@ int fused_w_launch_c_p4(const lolb_plan* pl, const void* F, bool inverse, double
 #define W_CASE(N, SHT, CALL) case N: { typedef SHT SH; CALL; } break;
 #if LOLB_W_PART == 0
 #define W_PART_FN fused_w_launch_p0
-#define W_PART_CASES(CALL) W_CASE(0, SH_64_27, CALL) W_CASE(1, SH_64_81, CALL)
+#define W_PART_CASES(CALL) W_CASE(0, SH_64_27, CALL) W_CASE(1, SH_64_81, CALL) W_CASE(10, SH_64_7, CALL)
 #elif LOLB_W_PART == 1
 #define W_PART_FN fused_w_launch_p1
 #define W_PART_CASES(CALL) W_CASE(2, SH_32_7_13, CALL) W_CASE(3, SH_8_7_13, CALL) W_CASE(4, SH_8_5_7_13, CALL) W_CASE(5, SH_32_9_7, CALL)
@@ -1329,7 +1332,7 @@ int fused_w_launch_c_p4(const lolb_plan* pl, const void* F, bool inverse, double
 #define W_PART_CASES(CALL) W_CASE(6, SH_64_7_13, CALL) W_CASE(7, SH_128_7_13, CALL) W_CASE(8, SH_4_3_5_7_13, CALL) W_CASE(9, SH_9_5_7_13, CALL)
 #elif LOLB_W_PART == 3
 #define W_PART_FN fused_w_launch_c_p3
-#define W_PART_CASES(CALL) W_CASE(0, SH_64_27, CALL) W_CASE(1, SH_64_81, CALL) W_CASE(2, SH_32_7_13, CALL) W_CASE(3, SH_8_7_13, CALL) W_CASE(4, SH_8_5_7_13, CALL)
+#define W_PART_CASES(CALL) W_CASE(0, SH_64_27, CALL) W_CASE(1, SH_64_81, CALL) W_CASE(2, SH_32_7_13, CALL) W_CASE(3, SH_8_7_13, CALL) W_CASE(4, SH_8_5_7_13, CALL) W_CASE(10, SH_64_7, CALL)
 #else
 #define W_PART_FN fused_w_launch_c_p4
 #define W_PART_CASES(CALL) W_CASE(5, SH_32_9_7, CALL) W_CASE(6, SH_64_7_13, CALL) W_CASE(7, SH_128_7_13, CALL) W_CASE(8, SH_4_3_5_7_13, CALL) W_CASE(9, SH_9_5_7_13, CALL)
@@ -1406,7 +1409,7 @@ int fused_w_crt(const lolb_plan* pl, const void* slot, bool inverse, int64_t* y,
   const FusedW* F = (const FusedW*)slot;
   if (!fused_w_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  return F->shape <= 1 ? fused_w_launch_p0(pl, F, inverse, y, batch, st)
+  return (F->shape <= 1 || F->shape == 10) ? fused_w_launch_p0(pl, F, inverse, y, batch, st)
        : F->shape <= 5 ? fused_w_launch_p1(pl, F, inverse, y, batch, st) : fused_w_launch_p2(pl, F, inverse, y, batch, st);
 }
 
@@ -1415,7 +1418,7 @@ int fused_wc_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y
   const FusedWC* F = (const FusedWC*)slot;
   if (!fused_wc_available(slot, inverse)) return LOLB_FUSED_UNAVAILABLE;
   if (batch <= 0) return LOLB_OK;
-  return F->shape <= 4 ? fused_w_launch_c_p3(pl, F, inverse, y, batch, st) : fused_w_launch_c_p4(pl, F, inverse, y, batch, st);
+  return (F->shape <= 4 || F->shape == 10) ? fused_w_launch_c_p3(pl, F, inverse, y, batch, st) : fused_w_launch_c_p4(pl, F, inverse, y, batch, st);
 }
 
 }  // namespace lolb

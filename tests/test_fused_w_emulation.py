@@ -30,7 +30,7 @@ FUSED_W_PARAMS = [
     (1728, [3457, 1002241]),      # mixed arithmetic classes, tupSize 2
     (5824, [3144961]), (2912, [3144961]), (3640, [3144961]),      # lol-apps tunnel benchmark rings and modulus (Benchmarks/Default.hs:52-82)
     (11648, [23297]), (11648, [3144961]), (11648, [174721]),      # F128*F7*F13: two column halves per lane (a = 7)
-    (5460, [3144961]), (4095, [3144961]), (5460, [21841]), (4095, [8191]),      # tunnel rings H4, H5: four odd prime powers, one in the tile
+    (5460, [3144961]), (4095, [3144961]), (5460, [21841]), (4095, [8191]), (448, [3144961]), (448, [449]),      # tunnel rings H4, H5: four odd prime powers, one in the tile
 ]
 
 
@@ -65,7 +65,7 @@ def test_fused_w_emulation_refuses_other_shapes():
         capi.fused_w_emulate(T.factor_pps(1728), [17], np.zeros((576, 1), dtype=np.int64))
 
 
-FUSED_W_COMPLEX = [1728, 5184, 2912, 728, 3640, 2016, 5824, 11648, 5460, 4095]
+FUSED_W_COMPLEX = [1728, 5184, 2912, 728, 3640, 2016, 5824, 11648, 5460, 4095, 448]
 
 
 @pytest.mark.parametrize("m", FUSED_W_COMPLEX)

@@ -204,7 +204,7 @@ def test_config_b_matches_reference_digests(dropin):
 # ------------------------------------------------------------------ batched device API
 # (14400, [429336001]): largest prime = 1 mod 14400 the 64-bit-accumulate fused kernel accepts (10q < 2^32);
 # (14400, [43201]): first modulus past the 32-bit-accumulate bound; the triple mixes both arithmetic classes
-BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
+BATCH_PARAMS = [(7, [29]), (448, [3144961]), (448, [449, 3144961]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
                 (1024, [12289]), (64 * 27, [3457]), CONFIG_A, CONFIG_C, (14400, [429336001]), (14400, [43201]),
                 (14400, [14401, 1008001, 429336001]), (14400, [2148249601]),
                 # tupSize 3 .. 8: the de-interleaving kernel (k_fused_a_kd), every limb of an element in one CTA iteration
@@ -218,7 +218,7 @@ BATCH_PARAMS = [(7, [29]), (42, [19393921, 18869761]), (42, [2148854401, 2148249
                 (64 * 7 * 13, [3144961]), (64 * 7 * 13, [23297]),
                 (128 * 7 * 13, [23297]), (128 * 7 * 13, [3144961]),      # a = 7: two column halves per lane
                 (4 * 3 * 5 * 7 * 13, [3144961]), (9 * 5 * 7 * 13, [3144961]), (4 * 3 * 5 * 7 * 13, [21841]), (9 * 5 * 7 * 13, [8191])]      # four odd prime powers      # lol-apps tunnel ring H1 at its modulus, and the Twace-Embed benchmark modulus (Montgomery class)
-FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016, 64 * 7 * 13, 128 * 7 * 13, 5460, 4095}
+FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016, 64 * 7 * 13, 128 * 7 * 13, 5460, 4095, 448}
 
 
 @pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
