@@ -232,12 +232,22 @@ k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Tile
     longlong2* src = reinterpret_cast<longlong2*>(y + (size_t)e0 * G.n);
     const int pairs = cnt * G.n / 2;      // n is even (checked by the host)
     // ---- in: word w of the piece -> tile[w]
-    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-      const longlong2 r = __ldcs(src + i);
-      uint32_t c0 = (uint32_t)r.x, c1 = (uint32_t)r.y;
-      if ((uint64_t)r.x >= (uint64_t)q) { int64_t t = r.x % (int64_t)q; c0 = (uint32_t)(t < 0 ? t + q : t); }      // like the reference's c % q
-      if ((uint64_t)r.y >= (uint64_t)q) { int64_t t = r.y % (int64_t)q; c1 = (uint32_t)(t < 0 ? t + q : t); }
-      *reinterpret_cast<uint2*>(line_tile + 2 * i) = make_uint2(c0, c1);
+    for (int i0 = threadIdx.x; i0 < pairs; i0 += 4 * blockDim.x) {      // four 16-byte loads in flight per thread (ncu: one was 59 % long_scoreboard)
+      longlong2 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * blockDim.x;
+        r[u] = i < pairs ? __ldcs(src + i) : make_longlong2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * blockDim.x;
+        if (i >= pairs) break;
+        uint32_t c0 = (uint32_t)r[u].x, c1 = (uint32_t)r[u].y;
+        if ((uint64_t)r[u].x >= (uint64_t)q) { int64_t t = r[u].x % (int64_t)q; c0 = (uint32_t)(t < 0 ? t + q : t); }      // like the reference's c % q
+        if ((uint64_t)r[u].y >= (uint64_t)q) { int64_t t = r[u].y % (int64_t)q; c1 = (uint32_t)(t < 0 ? t + q : t); }
+        *reinterpret_cast<uint2*>(line_tile + 2 * i) = make_uint2(c0, c1);
+      }
     }
     __syncthreads();
     // ---- one pass per odd-prime axis, in place
