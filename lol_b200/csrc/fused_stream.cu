@@ -80,6 +80,13 @@ __device__ __forceinline__ uint32_t barrett32(uint32_t x, uint32_t q, uint32_t m
   return min(r, r - q);
 }
 
+// x s mod q for a fixed s < q < 2^31 with sp = floor(s 2^32 / q) (Shoup): three 32-bit multiplies instead of a 64-bit Barrett step
+__device__ __forceinline__ uint32_t mul_fixed(uint32_t x, uint32_t s, uint32_t sp, uint32_t q)
+{
+  const uint32_t r = x * s - __umulhi(x, sp) * q;      // [0, 2q)
+  return min(r, r - q);
+}
+
 __device__ __forceinline__ int32_t reduce_biased(int32_t x, int64_t bias, uint32_t q, uint64_t mu)
 { return (int32_t)barrett32((uint32_t)x + (uint32_t)bias, q, (uint32_t)(mu >> 32)); }
 __device__ __forceinline__ int64_t reduce_biased(int64_t x, int64_t bias, uint32_t q, uint64_t mu)
@@ -103,6 +110,7 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
   const uint32_t q = Z.q[limb];
   const uint64_t mu = Z.mu[limb];
   const uint32_t s = Z.scale[limb];
+  const uint32_t sp = (NARROW && scale) ? (uint32_t)(((uint64_t)s << 32) / q) : 0u;      // NARROW implies q < 2^31
   // bias: a multiple of q above the largest negative intermediate (|x| <= P*P*q)
   const int64_t biasA = (int64_t)q * (PA * PA), biasB = (int64_t)q * (PB * PB);
   const size_t off = ((size_t)lo + (size_t)G.RA * DA * mid + (size_t)G.RB * DB * hi) * k + limb;
@@ -166,7 +174,8 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
 #pragma unroll
         for (int b = 0; b < DB; b++)
 #pragma unroll
-          for (int a = 0; a < DA; a++) v[u][b][a] = (I)barrett64((uint64_t)(uint32_t)v[u][b][a] * s, q, mu);
+          for (int a = 0; a < DA; a++)
+            v[u][b][a] = NARROW ? (I)mul_fixed((uint32_t)v[u][b][a], s, sp, q) : (I)barrett64((uint64_t)(uint32_t)v[u][b][a] * s, q, mu);
       }
       if (e0 + u < batch) {
         int64_t* base = y + (size_t)(e0 + u) * G.n * k + off;
@@ -193,7 +202,8 @@ struct TileGeom {
 __device__ __forceinline__ int fdiv(uint32_t x, int d, uint32_t magic) { return d == 1 ? (int)x : (int)__umulhi(x, magic); }
 
 template <int KIND, int P, typename I>
-__device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, const int ax, const int units, const ZqConsts& Z, const bool scale)
+__device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, const int ax, const int units, const ZqConsts& Z, const bool scale,
+                                          const uint32_t sp)
 {
   constexpr int D = P - 1;
   const int rts = G.rts[ax], lines = G.lines[ax];
@@ -212,7 +222,7 @@ __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, con
 #pragma unroll
     for (int a = 0; a < D; a++) {
       uint32_t r = (uint32_t)reduce_biased(v[a], bias, q, mu);
-      if (scale) r = barrett64((uint64_t)r * Z.scale[0], q, mu);
+      if (scale) r = sizeof(I) == 4 ? mul_fixed(r, Z.scale[0], sp, q) : barrett64((uint64_t)r * Z.scale[0], q, mu);
       base[a * rts] = r;
     }
   }
@@ -225,6 +235,7 @@ k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Tile
   typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
   extern __shared__ __align__(16) uint32_t line_tile[];
   const uint32_t q = Z.q[0];
+  const uint32_t sp = (NARROW && scale) ? (uint32_t)(((uint64_t)Z.scale[0] << 32) / q) : 0u;      // NARROW implies q < 2^31
   const int64_t ngroups = (batch + G.epb - 1) / G.epb;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t e0 = g * G.epb;
@@ -254,11 +265,11 @@ k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Tile
     for (int ax = 0; ax < G.naxes; ax++) {
       const bool sc = scale && ax == G.naxes - 1;
       switch (G.p[ax]) {
-        case 3: tile_axis<KIND, 3, I>(line_tile, G, ax, cnt, Z, sc); break;
-        case 5: tile_axis<KIND, 5, I>(line_tile, G, ax, cnt, Z, sc); break;
-        case 7: tile_axis<KIND, 7, I>(line_tile, G, ax, cnt, Z, sc); break;
-        case 11: tile_axis<KIND, 11, I>(line_tile, G, ax, cnt, Z, sc); break;
-        default: tile_axis<KIND, 13, I>(line_tile, G, ax, cnt, Z, sc); break;
+        case 3: tile_axis<KIND, 3, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
+        case 5: tile_axis<KIND, 5, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
+        case 7: tile_axis<KIND, 7, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
+        case 11: tile_axis<KIND, 11, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
+        default: tile_axis<KIND, 13, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
       }
       __syncthreads();
     }
