@@ -1,5 +1,5 @@
 """Time the ring-extension operators (ext_stream.cu) on device-resident batches; prints one JSON line per operator.
-usage: run_ext.py [m] [m'] [batch of O_m' elements] [iters]      (moduli: config C's pair when m' | 14400, else 12289-like)
+usage: run_ext.py [m] [m'] [batch of O_m' elements] [iters] [q1,q2,..]      (default moduli: config C's pair)
 Algorithmic bytes per element: words read once + words written, 8 k bytes each (tables excluded, L1/L2 resident)."""
 import json
 import sys
@@ -15,7 +15,7 @@ m = int(sys.argv[1]) if len(sys.argv) > 1 else 576
 m2 = int(sys.argv[2]) if len(sys.argv) > 2 else 14400
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-qs = [1008001, 1065601]
+qs = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [1008001, 1065601]
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
 lo, hi = CudaTensorRq(m, qs), CudaTensorRq(m2, qs)
 ext = CudaExtension(lo, hi)
@@ -58,6 +58,8 @@ cops = {
     "rescaleModRq": (lambda: P.rescale_mod(qs[::-1], y.data_ptr(), oi.data_ptr(), B, st), 2 * phi2 * k),
     "roundCosetRq": (lambda: P.round_coset(e.data_ptr(), y.data_ptr(), oi.data_ptr(), B, st), 3 * phi2 * k),
 }
+if k == 1:
+    del cops["rescaleDropRq"]      # nothing to drop with a single limb
 for name, (fn, words) in cops.items():
     for _ in range(3):
         capi.check(fn())
