@@ -204,7 +204,7 @@ def test_config_b_matches_reference_digests(dropin):
 # ------------------------------------------------------------------ batched device API
 # (14400, [429336001]): largest prime = 1 mod 14400 the 64-bit-accumulate fused kernel accepts (10q < 2^32);
 # (14400, [43201]): first modulus past the 32-bit-accumulate bound; the triple mixes both arithmetic classes
-BATCH_PARAMS = [(7, [29]), (448, [3144961]), (448, [449, 3144961]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
+BATCH_PARAMS = [(7, [29]), (33, [67]), (77, [463]), (143, [859]), (448, [3144961]), (448, [449, 3144961]), (42, [19393921, 18869761]), (42, [2148854401, 2148249601, 2150668801]), (89, [179]),
                 (1024, [12289]), (64 * 27, [3457]), CONFIG_A, CONFIG_C, (14400, [429336001]), (14400, [43201]),
                 (14400, [14401, 1008001, 429336001]), (14400, [2148249601]),
                 # tupSize 3 .. 8: the de-interleaving kernel (k_fused_a_kd), every limb of an element in one CTA iteration
