@@ -67,6 +67,12 @@ __device__ __forceinline__ void line_op(I (&v)[P - 1])
   }
 }
 
+// |intermediates| of line_op<KIND, P> for inputs in [0, q), as a multiple of q: the divisions by g multiply by up to P twice; L, L^-1
+// and the multiplications by g only add up to P terms (and go below zero by less than q).  The bias added before the reduction and
+// the 32-bit mode (everything below 2^31) are sized from it.
+template <int KIND>
+__host__ __device__ constexpr int line_mult(int P) { return (KIND == PASS_GINVPOW || KIND == PASS_GINVDEC) ? P * P : P + 2; }
+
 struct LineGeom {
   int32_t n, k;
   int32_t RA, RB;        // strides (rts) of the two axes; RB = n when there is no second axis
@@ -111,8 +117,8 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
   const uint64_t mu = Z.mu[limb];
   const uint32_t s = Z.scale[limb];
   const uint32_t sp = (NARROW && scale) ? (uint32_t)(((uint64_t)s << 32) / q) : 0u;      // NARROW implies q < 2^31
-  // bias: a multiple of q above the largest negative intermediate (|x| <= P*P*q)
-  const int64_t biasA = (int64_t)q * (PA * PA), biasB = (int64_t)q * (PB * PB);
+  // bias: a multiple of q above the largest negative intermediate
+  const int64_t biasA = (int64_t)q * line_mult<KIND>(PA), biasB = (int64_t)q * line_mult<KIND>(PB);
   const size_t off = ((size_t)lo + (size_t)G.RA * DA * mid + (size_t)G.RB * DB * hi) * k + limb;
   const size_t sa = (size_t)G.RA * k, sb = (size_t)G.RB * k;
   typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
@@ -218,7 +224,7 @@ __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, con
 #pragma unroll
     for (int a = 0; a < D; a++) v[a] = (I)base[a * rts];
     line_op<KIND, P, I>(v);
-    const int64_t bias = (int64_t)q * (P * P);
+    const int64_t bias = (int64_t)q * line_mult<KIND>(P);
 #pragma unroll
     for (int a = 0; a < D; a++) {
       uint32_t r = (uint32_t)reduce_biased(v[a], bias, q, mu);
@@ -326,7 +332,7 @@ int launch_line(const lolb_plan* pl, const LineGeom& G, const ZqConsts& zc, bool
 {
   constexpr int64_t PM = (PA > PB ? PA : PB);
   bool narrow = true;
-  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * PM * PM < ((int64_t)1 << 31);
+  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * line_mult<KIND>((int)PM) < ((int64_t)1 << 31);
   return narrow ? launch_line_n<KIND, PA, PB, true>(pl, G, zc, scale, y, batch, st)
                 : launch_line_n<KIND, PA, PB, false>(pl, G, zc, scale, y, batch, st);
 }
@@ -415,7 +421,7 @@ template <int KIND>
 static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
 {
   bool narrow = true;
-  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * 13 * 13 < ((int64_t)1 << 31);
+  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * line_mult<KIND>(13) < ((int64_t)1 << 31);
   const size_t smem = (size_t)G.epb * G.n * sizeof(uint32_t);
   const int64_t groups = (batch + G.epb - 1) / G.epb;
   int per_sm = (int)(200 * 1024 / (smem + 1024));

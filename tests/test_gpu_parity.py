@@ -899,3 +899,33 @@ def test_complex_kernels_write_inside_their_batch_only(torch_cuda, m, k):
     guard = torch.tensor(complex(-7.25e300, 3.5e299), dtype=torch.complex128, device="cuda")
     assert bool((buf[:G] == guard).all()) and bool((buf[G + B * n * k:] == guard).all())
     assert bool(torch.isfinite(torch.view_as_real(body)).all()) and float(torch.view_as_real(body).abs().max()) < 1e6
+
+
+# moduli on both sides of the thresholds of the line kernels' 32-bit mode: (P + 2) q < 2^31 for L, L^-1, *g and P^2 q < 2^31 for /g
+LINE_MODE_EDGES = [(2912, 143165569), (2912, 143171393), (2912, 12655553), (2912, 12719617), (14400, 306748801), (14400, 306864001),
+                   (14400, 85852801), (14400, 85924801), (1728, 429496129), (1728, 429501313), (1728, 238600513), (1728, 238610881)]
+
+
+@pytest.mark.parametrize("m,q", LINE_MODE_EDGES, ids=lambda v: str(v))
+def test_line_operators_at_the_arithmetic_mode_thresholds(torch_cuda, gpu_oracle, m, q):
+    """L, L^-1, *g, /g with every coefficient at q - 1 (the largest intermediates), at 0 / q - 1 alternating (the most negative
+    ones) and random, for moduli just below and just above the bounds that select int32 or int64 intermediates."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    t = CudaTensorRq(m, [q])
+    n, pe = t.n, T.pe_array(m)
+    rng = np.random.default_rng(q % 1000)
+    y = np.zeros((4, n, 1), dtype=np.int64)
+    y[0] = q - 1
+    y[1, ::2] = q - 1
+    y[2, 1::2] = q - 1
+    y[3] = rng.integers(0, q, size=(n, 1))
+    x = torch.from_numpy(y).cuda()
+    for meth, nm in (("l", "tensorLRq"), ("lInv", "tensorLInvRq"), ("mulGPow", "tensorGPowRq"), ("mulGDec", "tensorGDecRq")):
+        got = getattr(t, meth)(x).cpu().numpy()
+        for b in range(4):
+            assert np.array_equal(got[b], getattr(gpu_oracle, nm)(y[b], pe, [q])), (nm, b)
+    for meth, nm in (("divGPow", "tensorGInvPowRq"), ("divGDec", "tensorGInvDecRq")):
+        got = getattr(t, meth)(x).cpu().numpy()
+        for b in range(4):
+            assert np.array_equal(got[b], getattr(gpu_oracle, nm)(y[b], pe, [q])[0]), (nm, b)
