@@ -492,6 +492,22 @@ def run_gpu_arm(args):
             rec.add(sec, "tensor" + name, ms, 32 * tr.n * Bg, Bg, kernel=tcx.plan.kernel_name(name))
         del dg, zg, cg, og
         torch.cuda.empty_cache()
+        # the reference's `error` benchmark (tGaussianDec, lol Benchmarks/TensorBenches.hs) and the line operators over doubles on
+        # its other rings: transform alone (16 n bytes per element) and draw + transform in one pass (8 n bytes written)
+        for mt, bt in ((2912, 57344), (11648, 14336), (5460, 57344)):
+            tg = CudaTensorReal(mt)
+            dgt = torch.randn(bt, tg.n, 1, dtype=torch.float64, device="cuda", generator=gen)
+            sec_g = f"error m={mt}"
+            rec.add(sec_g, "tensorGaussianDec", timed(lambda: capi.check(tg.plan.op("GaussianDec", dgt.data_ptr(), bt, stream))), 16 * tg.n * bt, bt,
+                    kernel=tg.plan.kernel_name("GaussianDec"))
+            dgt.normal_()
+            rec.add(sec_g, "tGaussianDec", timed(lambda: capi.check(tg.plan.t_gaussian_dec(0.1, 1, 0, dgt.data_ptr(), bt, stream))), 8 * tg.n * bt, bt,
+                    kernel=tg.plan.kernel_name("GaussianDec"))
+            dgt.normal_()
+            rec.add(sec_g, "LDouble", timed(lambda: capi.check(tg.plan.op("LDouble", dgt.data_ptr(), bt, stream))), 16 * tg.n * bt, bt,
+                    kernel=tg.plan.kernel_name("LDouble"))
+            del dgt, tg
+            torch.cuda.empty_cache()
         # complex CRT of the other benchmark rings: the fused_w schedule over complex doubles, the pass engine beside it
         for mt, bt in ((1728, 131072), (2912, 65536), (11648, 16384)):
             tw = CudaTensorComplex(mt)
@@ -637,7 +653,8 @@ def run_gpu_arm(args):
                "tunnel": [[fr(f"tunnel m={mt}/3144961", "CRT"), fr(f"tunnel m={mt}/3144961", "CRTInv")] for mt in (11648, 5824, 2912, 3640, 5460, 4095)],
                "prf_k2": [fr("HomomPRF H1'=F64*F7*F13 ZQ2", "CRT"), fr("HomomPRF H1'=F64*F7*F13 ZQ2", "CRTInv")],
                "prf_k4": [fr("HomomPRF H1'=F64*F7*F13 ZQ4", "CRT"), fr("HomomPRF H1'=F64*F7*F13 ZQ4", "CRTInv")],
-               "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec")}
+               "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec"),
+               "gauss2912": fr("error m=2912", "tensorGaussianDec"), "gauss11648": fr("error m=11648", "tensorGaussianDec")}
     for s, n, ms, _, units, _ in rec.rows:
         if s == "she" and n == "mulAndSwitch":
             summary["she_n"] = round(world * units / (ms * 1e-3))

@@ -119,6 +119,11 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
   if (pl->kind == PLAN_RQ && (!strcmp(op, "L") || !strcmp(op, "LInv") || !strcmp(op, "GPow") || !strcmp(op, "GDec") ||
                               !strcmp(op, "GInvPow") || !strcmp(op, "GInvDec")))
     return fused_stream_line_name(pl);
+  if (pl->kind == PLAN_C) {
+    if (!strcmp(op, "GaussianDec")) return fused_plain_name(pl, true, false);
+    for (const char* nm : {"LR", "LInvR", "GPowR", "GDecR", "LDouble", "LInvDouble"}) if (!strcmp(op, nm)) return fused_plain_name(pl, false, false);
+    for (const char* nm : {"LC", "LInvC", "GPowC", "GDecC", "GInvPowC", "GInvDecC"}) if (!strcmp(op, nm)) return fused_plain_name(pl, false, true);
+  }
   return "generic";
 }
 

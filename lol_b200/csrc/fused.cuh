@@ -28,6 +28,7 @@ int she_knapsack(const lolb_plan* pl, const int64_t* digits, int ell, const int6
 // modulus-free rings (fused_plain.cu); ring = RING_I64 / RING_F64 / RING_C64
 int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t batch, double rscale, cudaStream_t st);
 int fused_plain_gauss(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st);
+const char* fused_plain_name(const lolb_plan* pl, bool gauss, bool cplx);
 // on-device Gaussian source: y[batch][n] i.i.d. N(0, var2 / 2) (pl may be NULL), and tGaussianDec in one pass (draw + transform)
 int fused_plain_real_gaussians(const lolb_plan* pl, double* y, int64_t n, int64_t batch, uint64_t seed, uint64_t first, double var2, cudaStream_t st);
 int fused_plain_gauss_gen(const lolb_plan* pl, double* y, int64_t batch, cudaStream_t st, bool gen, uint64_t seed, uint64_t first, double var2);

@@ -262,6 +262,134 @@ k_gauss_stream(double* __restrict__ y, int64_t batch, const __grid_constant__ Pl
   }
 }
 
+// ------------------------------------------------------------------ the same operators with the ring elements staged in shared memory
+// Indices whose odd primes do not fit a register tile ({7,13}: 72 values, {5,7,13}, {3,5,7,13}: every other ring of the reference's
+// benchmark lists, which time `error` = tGaussianDec and the line operators on each of them): a CTA loads whole ring elements with
+// contiguous 16-byte accesses into a shared-memory tile of ring values, runs one in-place pass per odd-prime axis (a thread per
+// line of p - 1 values) and stores the same way -- one HBM round trip for any number of axes, like k_line_tile over Z_q
+// (fused_stream.cu).  KIND = PASS_GAUSS applies 2 E_p / sqrt(2) per axis (random.cpp:19-50) with the matrices read as constant-bank
+// operands; GEN draws the inputs into the tile instead of loading them (pair p of an element -> coefficients 2p, 2p + 1, the layout
+// of k_real_gaussians, so the one-pass result equals realGaussians followed by the transform bit for bit).
+struct PTileGeom {
+  int32_t n, naxes, epb, threads;  // n: values per element (tupSize folded in); threads: CTA size chosen with epb
+  int32_t p[4], rts[4];
+  uint32_t m_rts[4];               // ceil(2^32 / rts)
+};
+
+struct GaussAll {                  // 2 E_p row-major, one slot per supported prime so that every index is a compile-time constant
+  double m3[4], m5[16], m7[36], m11[100], m13[144];
+};
+
+template <int P>
+__device__ __forceinline__ const double* gauss_slot(const GaussAll& E)
+{
+  if constexpr (P == 3) return E.m3;
+  else if constexpr (P == 5) return E.m5;
+  else if constexpr (P == 7) return E.m7;
+  else if constexpr (P == 11) return E.m11;
+  else return E.m13;
+}
+
+template <class R, int KIND, int P>
+__device__ __forceinline__ void plain_tile_axis(typename R::T* tile, const PTileGeom& G, const int ax, const int units, const GaussAll& E)
+{
+  typedef typename R::T T;
+  constexpr int D = P - 1;
+  const R ring{};
+  const int rts = G.rts[ax];
+  const int total = units * (G.n / D);
+  for (int L = threadIdx.x; L < total; L += blockDim.x) {
+    const int uh = rts == 1 ? L : (int)__umulhi((uint32_t)L, G.m_rts[ax]), lo = L - uh * rts;
+    T* base = tile + (size_t)uh * rts * D + lo;
+    T v[D];
+#pragma unroll
+    for (int a = 0; a < D; a++) v[a] = base[a * rts];
+    if constexpr (KIND == PASS_GAUSS) {
+      const double* M = gauss_slot<P>(E);
+      const double inv_sqrt2 = 0.70710678118654752440;
+      constexpr int RG = D % 4 == 0 ? 4 : 2;           // rows in flight: independent chains for the FP64 pipe at a bounded register count
+#pragma unroll 1
+      for (int r0 = 0; r0 < D; r0 += RG) {             // rolled: the row group is a warp-uniform offset into the constant bank
+        double acc[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) acc[r] = 0.0;
+#pragma unroll
+        for (int col = 0; col < D; col++)
+#pragma unroll
+          for (int r = 0; r < RG; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(M[(r0 + r) * D + col], v[col]));      // order of random.cpp:33-40
+#pragma unroll
+        for (int r = 0; r < RG; r++) base[(r0 + r) * rts] = __dmul_rn(acc[r], inv_sqrt2);
+      }
+    } else {
+      line_ring<KIND, P, R>(ring, v);
+#pragma unroll
+      for (int a = 0; a < D; a++) base[a * rts] = v[a];
+    }
+  }
+}
+
+template <class R, int KIND, bool GEN>
+__global__ void __launch_bounds__(256, KIND == PASS_GAUSS ? 3 : 1)
+k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constant__ PTileGeom G, const __grid_constant__ GaussAll E,
+             double rscale, uint64_t seed, uint64_t first, double var2)
+{
+  typedef typename R::T T;
+  static_assert(sizeof(T) == sizeof(typename R::IO), "the tile holds the values as stored");
+  extern __shared__ __align__(16) unsigned char plain_tile_raw[];
+  T* tile = reinterpret_cast<T*>(plain_tile_raw);
+  double2* tile16 = reinterpret_cast<double2*>(plain_tile_raw);
+  constexpr int PER16 = 16 / (int)sizeof(T);          // values per 16-byte word: 2 (int64, double) or 1 (complex)
+  const int64_t ngroups = (batch + G.epb - 1) / G.epb;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t e0 = g * G.epb;
+    const int cnt = (int)(batch - e0 < G.epb ? batch - e0 : G.epb);
+    double2* src = reinterpret_cast<double2*>(y + (size_t)e0 * G.n);
+    const int words = cnt * G.n / PER16;               // n is even for the 8-byte rings (checked by the host)
+    if constexpr (GEN) {
+      const int half = G.n / 2;
+      for (int i = threadIdx.x; i < words; i += blockDim.x) {
+        const int u = i / half, p = i - u * half;
+        double g0, g1;
+        gauss_pair(seed, first + (uint64_t)(e0 + u), (uint32_t)p, var2, g0, g1);
+        tile16[i] = make_double2(g0, g1);
+      }
+    } else {
+      for (int i0 = threadIdx.x; i0 < words; i0 += 4 * blockDim.x) {      // four 16-byte loads in flight per thread
+        double2 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * blockDim.x;
+          r[u] = i < words ? __ldcs(src + i) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * blockDim.x;
+          if (i < words) tile16[i] = r[u];
+        }
+      }
+    }
+    __syncthreads();
+    for (int ax = 0; ax < G.naxes; ax++) {
+      switch (G.p[ax]) {
+        case 3: plain_tile_axis<R, KIND, 3>(tile, G, ax, cnt, E); break;
+        case 5: plain_tile_axis<R, KIND, 5>(tile, G, ax, cnt, E); break;
+        case 7: plain_tile_axis<R, KIND, 7>(tile, G, ax, cnt, E); break;
+        case 11: plain_tile_axis<R, KIND, 11>(tile, G, ax, cnt, E); break;
+        default: plain_tile_axis<R, KIND, 13>(tile, G, ax, cnt, E); break;
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < words; i += blockDim.x) {
+      double2 v = tile16[i];
+      if constexpr (sizeof(T) == 16) {                 // complex: optional real scale (g.cpp:209-220 intent), as k_line_plain
+        if (rscale != 0.0) v = make_double2(__dmul_rn(v.x, rscale), __dmul_rn(v.y, rscale));
+      }
+      __stcs(src + i, v);
+    }
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ int64_t wsum(int64_t v)
 {
   for (int o = 16; o > 0; o >>= 1) v = (int64_t)((uint64_t)v + (uint64_t)__shfl_down_sync(0xffffffffu, v, o));
@@ -389,6 +517,76 @@ int launched(const char* what)
   return LOLB_OK;
 }
 
+// shared-memory tile kernel: odd primes from {3, 5, 7, 11, 13}, at most four odd axes, one element within the opt-in shared memory
+bool ptile_geom(const lolb_plan* pl, int fold_k, size_t tsize, bool quad, PTileGeom* G, int (&p)[4], int (&ppi)[4], int64_t (&mp)[4])
+{
+  int64_t r[4];
+  const int cnt = odd_axes(pl, p, r, ppi, mp);
+  if (cnt < 1 || cnt > 4) return false;
+  for (int i = 0; i < cnt; i++) if (p[i] != 3 && p[i] != 5 && p[i] != 7 && p[i] != 11 && p[i] != 13) return false;
+  const int64_t n = (int64_t)pl->n * fold_k;
+  if ((tsize == 8 && (n & 1)) || n * (int64_t)tsize > 160 * 1024) return false;
+  // CTA shape: lolb_internal.cuh::choose_tile_shape; LOLB_PLAIN_TILE_BYTES / _EPB / _THREADS override for tuning runs
+  static const int tile_bytes = [] { const char* e = getenv("LOLB_PLAIN_TILE_BYTES"); return e ? atoi(e) : 40960; }();
+  static const int epb_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_EPB"); return e ? atoi(e) : 0; }();
+  static const int thr_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_THREADS"); return e ? atoi(e) : 0; }();
+  TileShape sh = choose_tile_shape(n, p, cnt, tsize, (size_t)tile_bytes, quad);
+  if (epb_env > 0) sh.epb = epb_env;
+  if (thr_env >= 32 && thr_env <= 256) sh.threads = thr_env / 32 * 32;
+  const int64_t epb = sh.epb;
+  G->threads = sh.threads;
+  G->n = (int32_t)n;
+  G->naxes = cnt;
+  G->epb = (int32_t)epb;
+  for (int i = 0; i < cnt; i++) {
+    G->p[i] = p[i];
+    G->rts[i] = (int32_t)(r[i] * fold_k);
+    G->m_rts[i] = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)G->rts[i] - 1) / (uint64_t)G->rts[i]);
+  }
+  return true;
+}
+
+template <class R, int KIND, bool GEN>
+int launch_plain_tile(const lolb_plan* pl, const PTileGeom& G, const GaussAll& E, typename R::IO* y, int64_t batch, double rscale,
+                      uint64_t seed, uint64_t first, double var2, cudaStream_t st)
+{
+  const size_t smem = (size_t)G.epb * G.n * sizeof(typename R::T);
+  const int64_t groups = (batch + G.epb - 1) / G.epb;
+  int per_sm = (int)(200 * 1024 / (smem + 1024));
+  if (per_sm > 2048 / G.threads) per_sm = 2048 / G.threads;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)pl->num_sms * per_sm;
+  if (grid > groups) grid = groups;
+  auto kern = k_plain_tile<R, KIND, GEN>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "k_plain_tile shared memory");
+  }
+  kern<<<(int)grid, G.threads, smem, st>>>(y, batch, G, E, rscale, seed, first, var2);
+  return launched("k_plain_tile");
+}
+
+template <class R>
+int plain_tile_kind(const lolb_plan* pl, int kind, const PTileGeom& G, typename R::IO* y, int64_t batch, double rscale, cudaStream_t st)
+{
+  static const GaussAll none{};
+  switch (kind) {
+    case PASS_L: return launch_plain_tile<R, PASS_L, false>(pl, G, none, y, batch, rscale, 0, 0, 0.0, st);
+    case PASS_LINV: return launch_plain_tile<R, PASS_LINV, false>(pl, G, none, y, batch, rscale, 0, 0, 0.0, st);
+    case PASS_GPOW: return launch_plain_tile<R, PASS_GPOW, false>(pl, G, none, y, batch, rscale, 0, 0, 0.0, st);
+    case PASS_GDEC: return launch_plain_tile<R, PASS_GDEC, false>(pl, G, none, y, batch, rscale, 0, 0, 0.0, st);
+    case PASS_GINVPOW: return launch_plain_tile<R, PASS_GINVPOW, false>(pl, G, none, y, batch, rscale, 0, 0, 0.0, st);
+    case PASS_GINVDEC: return launch_plain_tile<R, PASS_GINVDEC, false>(pl, G, none, y, batch, rscale, 0, 0, 0.0, st);
+    default: return LOLB_FUSED_UNAVAILABLE;
+  }
+}
+
+bool plain_tile_enabled()
+{
+  static const bool on = [] { const char* e = getenv("LOLB_PLAIN_TILE"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
 template <class R, int PA, int PB>
 int line_kind(const lolb_plan* pl, int kind, const PlainGeom& G, typename R::IO* y, int64_t batch, double rscale, cudaStream_t st)
 {
@@ -420,6 +618,19 @@ int line_combo(const lolb_plan* pl, int kind, const PlainGeom& G, int cnt, const
 
 }  // namespace
 
+// which kernel family serves the line operators (gauss = false; tupSize folded) or the Gaussian transform of a plan
+const char* fused_plain_name(const lolb_plan* pl, bool gauss, bool cplx)
+{
+  PlainGeom G{};
+  PTileGeom TG{};
+  int p[4], ppi[4], cnt; int64_t mp[4];
+  if (gauss && pl->k != 1) return "generic";
+  if (make_geom(pl, gauss ? 1 : pl->k, &G, p, ppi, mp, &cnt)) return "plain_stream";
+  if (cnt == 0) return "identity";
+  if (plain_tile_enabled() && ptile_geom(pl, gauss ? 1 : pl->k, cplx ? 16 : 8, gauss, &TG, p, ppi, mp)) return "plain_tile";
+  return "generic";
+}
+
 // ring: RING_I64 / RING_F64 / RING_C64.  GInv on int64 needs the per-element divisibility verdict: generic engine.
 int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t batch, double rscale, cudaStream_t st)
 {
@@ -428,7 +639,18 @@ int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t b
   int p[4], ppi[4], cnt; int64_t mp[4];
   if (!make_geom(pl, pl->k, &G, p, ppi, mp, &cnt)) {
     if (cnt == 0 && !(ring == RING_C64 && rscale != 0.0 && rscale != 1.0)) return LOLB_OK;     // identity for p = 2
-    return LOLB_FUSED_UNAVAILABLE;
+    PTileGeom TG{};
+    if (cnt == 0 || !plain_tile_enabled()) return LOLB_FUSED_UNAVAILABLE;
+    if (ring == RING_I64) {
+      if (kind == PASS_GINVPOW || kind == PASS_GINVDEC || !ptile_geom(pl, pl->k, 8, false, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+      return plain_tile_kind<I64Ring>(pl, kind, TG, (int64_t*)y, batch, 0.0, st);
+    }
+    if (ring == RING_F64) {
+      if (!ptile_geom(pl, pl->k, 8, false, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+      return plain_tile_kind<F64Ring>(pl, kind, TG, (double*)y, batch, 0.0, st);
+    }
+    if (!ptile_geom(pl, pl->k, 16, false, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+    return plain_tile_kind<C64Ring>(pl, kind, TG, (double2*)y, batch, rscale, st);
   }
   if (ring == RING_I64) {
     if (kind == PASS_GINVPOW || kind == PASS_GINVDEC) return LOLB_FUSED_UNAVAILABLE;
@@ -459,7 +681,24 @@ int fused_plain_gauss_gen(const lolb_plan* pl, double* y, int64_t batch, cudaStr
   if (pl->k != 1) return LOLB_FUSED_UNAVAILABLE;
   PlainGeom G{};
   int p[4], ppi[4], cnt; int64_t mp[4];
-  if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) return cnt == 0 ? LOLB_OK : LOLB_FUSED_UNAVAILABLE;
+  if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) {
+    if (cnt == 0) return LOLB_OK;
+    PTileGeom TG{};
+    if (!plain_tile_enabled() || !ptile_geom(pl, 1, 8, true, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+    GaussAll A{};
+    for (int ax = 0; ax < cnt; ax++) {
+      const int P = p[ax];
+      double* M = P == 3 ? A.m3 : P == 5 ? A.m5 : P == 7 ? A.m7 : P == 11 ? A.m11 : A.m13;
+      const std::vector<lolb_complex>& T = pl->cru[ppi[ax]];
+      for (int row = 0; row < P - 1; row++)
+        for (int col = 1; col <= P - 1; col++) {
+          const lolb_complex w = T[(size_t)(((int64_t)row * col) % P) * mp[ax]];
+          M[row * (P - 1) + col - 1] = 2.0 * (col <= (P >> 1) ? w.real : w.imag);
+        }
+    }
+    return gen ? launch_plain_tile<F64Ring, PASS_GAUSS, true>(pl, TG, A, y, batch, 0.0, seed, first, var2, st)
+               : launch_plain_tile<F64Ring, PASS_GAUSS, false>(pl, TG, A, y, batch, 0.0, 0, 0, 0.0, st);
+  }
   // E_p[row][col-1] = Re or Im of ru[(row*col mod p) * p^(e-1)]  (random.cpp:33-40)
   GaussMats E{};
   for (int ax = 0; ax < cnt; ax++) {

@@ -200,7 +200,7 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
 // runs one in-place pass per odd-prime axis (a thread per line of p - 1 words, consecutive threads on consecutive lines) and
 // writes the elements back the same way: one HBM round trip for any number of axes.
 struct TileGeom {
-  int32_t n, naxes, epb;
+  int32_t n, naxes, epb, threads;
   int32_t p[4], rts[4], lines[4];
   uint32_t m_rts[4];              // ceil(2^32 / d): exact floor(x / d) by __umulhi for x d < 2^32
 };
@@ -406,9 +406,18 @@ static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
   G->n = pl->n;
   G->naxes = cnt;
   // measured 2048 / 4096 / 8192 / 16384 words per CTA: m = 2912 L 50 / 60 / 55 / 58 %, m = 5460 38 / 49 / 47 / 46 % of HBM
+  // round 2, last: the CTA shape (threads, elements) that leaves no idle threads in the last round of an axis pass
+  // (lolb_internal.cuh::choose_tile_shape) within `tile_words`; LOLB_LINE_TILE_SHAPE=0 keeps 256 threads x tile_words / n elements
   static const int tile_words = [] { const char* e = getenv("LOLB_LINE_TILE_WORDS"); return e ? atoi(e) : 4096; }();
+  static const bool shaped = [] { const char* e = getenv("LOLB_LINE_TILE_SHAPE"); return !e || atoi(e) != 0; }();
   int64_t epb = tile_words / pl->n;
   if (epb < 1) epb = 1;
+  G->threads = 256;
+  if (shaped) {
+    const TileShape sh = choose_tile_shape(pl->n, p, cnt, sizeof(uint32_t), (size_t)tile_words * sizeof(uint32_t), false);
+    epb = sh.epb;
+    G->threads = sh.threads;
+  }
   G->epb = (int32_t)epb;
   for (int i = 0; i < cnt; i++) {
     G->p[i] = p[i]; G->rts[i] = (int32_t)r[i]; G->lines[i] = pl->n / (p[i] - 1);
@@ -425,14 +434,14 @@ static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqCons
   const size_t smem = (size_t)G.epb * G.n * sizeof(uint32_t);
   const int64_t groups = (batch + G.epb - 1) / G.epb;
   int per_sm = (int)(200 * 1024 / (smem + 1024));
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 2048 / G.threads) per_sm = 2048 / G.threads;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)pl->num_sms * per_sm;
   if (grid > groups) grid = groups;
   cudaError_t e = cudaSuccess;
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) kern<<<(int)grid, 256, smem, st>>>(y, batch, G, zc, scale ? 1 : 0);
+    if (e == cudaSuccess) kern<<<(int)grid, G.threads, smem, st>>>(y, batch, G, zc, scale ? 1 : 0);
   };
   if (narrow) go(k_line_tile<KIND, true>); else go(k_line_tile<KIND, false>);
   if (e != cudaSuccess) return cuda_fail(e, "k_line_tile shared memory");

@@ -146,6 +146,34 @@ struct PerDeviceOnce {
   }
 };
 
+// Shape of a CTA of the shared-memory tile kernels (k_line_tile, k_plain_tile): every axis pass deals epb * n / (p - 1) lines to
+// the CTA's threads, so line counts that are not multiples of the thread count idle most of the CTA in the last round of a
+// pass (n = 1152, three elements, 256 threads: 288 lines of 12 = two rounds for 1.125 rounds of work).  Choose (threads, elements
+// per CTA) with the least idle work -- an axis weighs (p - 1) per line, (p - 1)^2 for dense matrices -- and, within 2 %, the
+// smallest tile (more CTAs per SM overlap one CTA's loads with another's passes), then the larger CTA.
+struct TileShape { int threads, epb; };
+inline TileShape choose_tile_shape(int64_t n, const int* p, int cnt, size_t value_bytes, size_t cap_bytes, bool quad)
+{
+  int64_t cap = (int64_t)(cap_bytes / ((size_t)n * value_bytes));
+  if (cap < 1) cap = 1;
+  if (cap > 64) cap = 64;
+  TileShape best{256, 1};
+  double best_w = 1e30;
+  for (int64_t e = 1; e <= cap; e++)
+    for (int t = 256; t >= 128; t -= 32) {
+      double used = 0.0, work = 0.0;
+      for (int i = 0; i < cnt; i++) {
+        const double w = quad ? (double)(p[i] - 1) * (p[i] - 1) : (double)(p[i] - 1);
+        const int64_t lines = e * (n / (p[i] - 1));
+        used += w * (double)((lines + t - 1) / t * t);
+        work += w * (double)lines;
+      }
+      const double W = used / work;
+      if (W < best_w * 0.98) { best_w = W; best = TileShape{t, (int)e}; }      // e ascending, t descending: ties keep the smaller tile, then the larger CTA
+    }
+  return best;
+}
+
 // plan.cu
 int plan_build_common(lolb_plan* pl, const PrimeExponent* pe, int npe, int k);
 int plan_derive_rq_roots(lolb_plan* pl);              // ZqBasic.hs:144-171 -> pl->ru, ruinv, mhatinv (LOLB_ERR_NO_CRT if none)

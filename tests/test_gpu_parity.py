@@ -560,7 +560,7 @@ def test_complex_crt_fused_w_rings(torch_cuda, gpu_oracle, m, k):
     assert rel_err(t.crtInv(x).cpu().numpy(), g.cpu().numpy()) <= 1e-11
 
 
-@pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89], ids=str)
+@pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89, 91, 77, 33, 728, 2912, 3640, 5460, 4095, 11648], ids=str)
 def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
     """The streaming kernels of the modulus-free rings (one or two small odd primes) against the generic pass
     engine on the same batch: bit-identical for int64, <= 1e-12 for double / complex (same operation order)."""
@@ -929,3 +929,52 @@ def test_line_operators_at_the_arithmetic_mode_thresholds(torch_cuda, gpu_oracle
         got = getattr(t, meth)(x).cpu().numpy()
         for b in range(4):
             assert np.array_equal(got[b], getattr(gpu_oracle, nm)(y[b], pe, [q])[0]), (nm, b)
+
+
+@pytest.mark.parametrize("m,k", [(91, 1), (91, 3), (2912, 2), (5460, 1), (385, 2)], ids=lambda v: str(v))
+def test_plain_tile_kernel_tuples_and_oracle(torch_cuda, gpu_oracle, m, k):
+    """`k_plain_tile` (the modulus-free rings' operators with the element staged in shared memory) on the {7,13}, {5,7,13},
+    {3,5,7,13}, {5,7,11} rings with tupSize folded into the strides, more elements than one CTA's group and a ragged last group:
+    int64 bit for bit against the oracle (l.cpp:28-98, g.cpp:16-58 through tensor.h:39-74), complex within FLOAT_TOL."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorComplex, CudaTensorInt
+    ti, tc = CudaTensorInt(m, k), CudaTensorComplex(m, k)
+    assert ti.plan.kernel_name("LR") == "plain_tile"
+    n, pe, B = ti.n, T.pe_array(m), 61
+    rng = np.random.default_rng(m + k)
+    z = rng.integers(-(2 ** 62), 2 ** 62, size=(B, n, k)).astype(np.int64)
+    c = rng.normal(size=(B, n, k)) + 1j * rng.normal(size=(B, n, k))
+    zx, cx = torch.from_numpy(z).cuda(), torch.from_numpy(c).cuda()
+    for meth, nm in (("l", "tensorLR"), ("lInv", "tensorLInvR"), ("mulGPow", "tensorGPowR"), ("mulGDec", "tensorGDecR")):
+        got = getattr(ti, meth)(zx).cpu().numpy()
+        for b in (0, 1, B // 2, B - 1):
+            assert np.array_equal(got[b], getattr(gpu_oracle, nm)(z[b], pe, k)), (nm, b)
+    for meth, nm in (("l", "tensorLC"), ("lInv", "tensorLInvC"), ("mulGPow", "tensorGPowC"), ("mulGDec", "tensorGDecC")):
+        got = getattr(tc, meth)(cx).cpu().numpy()
+        for b in (0, B - 1):
+            assert rel_err(got[b], getattr(gpu_oracle, nm)(c[b], pe, k)) <= FLOAT_TOL, (nm, b)
+    # round trips on the whole batch
+    assert torch.equal(ti.lInv(ti.l(zx)), zx)
+    small = torch.from_numpy(rng.integers(-8, 9, size=(B, n, k)).astype(np.int64)).cuda()      # no wrap-around: g | g x exactly
+    back, ok = ti.divGPow(ti.mulGPow(small))
+    assert ok.cpu().tolist() == [1] * B and torch.equal(back, small)
+
+
+@pytest.mark.parametrize("m", [91, 2912, 5460, 4095, 11648], ids=str)
+def test_tgaussiandec_one_pass_equals_draw_then_transform(torch_cuda, gpu_oracle, m):
+    """On the rings served by `k_plain_tile` the one-pass tGaussianDec (inputs drawn into the tile) uses the pair layout of
+    realGaussians, so it equals realGaussians followed by tensorGaussianDec bit for bit; the transform itself against the oracle
+    (random.cpp:19-64)."""
+    torch = torch_cuda
+    from lol_b200.factored import radical_fact
+    from lol_b200.tensor import CudaTensorReal
+    t = CudaTensorReal(m)
+    assert t.plan.kernel_name("GaussianDec") == "plain_tile"
+    v, B = 0.37, 23
+    one = t.tGaussianDec(v, B, seed=9, first=5)
+    raw = t.realGaussians(v * (m // radical_fact(m)), B, seed=9, first=5)
+    two = t.gaussianDecTransform(raw)
+    assert torch.isfinite(one).all() and torch.equal(one, two)
+    pe, ruc = T.pe_array(m), T.ru_tables_c(m)
+    for b in (0, B - 1):
+        assert rel_err(two[b].cpu().numpy(), gpu_oracle.tensorGaussianDec(raw[b].cpu().numpy(), pe, ruc)) <= FLOAT_TOL

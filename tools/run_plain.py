@@ -16,7 +16,9 @@ cases = [("CRTC", lambda: tc.plan.op("CRTC", c.data_ptr(), B, st), 32), ("CRTInv
          ("NormSqD", lambda: tr.plan.normsq("D", d.data_ptr(), outd.data_ptr(), B, st), 8),
          ("NormSqR", lambda: ti.plan.normsq("R", z.data_ptr(), outz.data_ptr(), B, st), 8),
          ("LDouble", lambda: tr.plan.op("LDouble", d.data_ptr(), B, st), 16), ("GPowC", lambda: tc.plan.op("GPowC", c.data_ptr(), B, st), 32),
-         ("LR", lambda: ti.plan.op("LR", z.data_ptr(), B, st), 16)]
+         ("LR", lambda: ti.plan.op("LR", z.data_ptr(), B, st), 16),
+         ("tGaussianDec", lambda: tr.plan.t_gaussian_dec(0.1, 1, 0, d.data_ptr(), B, st), 8)]
+print(m, "kernels:", {o: tr.plan.kernel_name(o) for o in ("GaussianDec", "LDouble")}, {o: tc.plan.kernel_name(o) for o in ("CRTC", "GPowC")})
 for name, fn, bpc in cases:
     for _ in range(2): capi.check(fn())
     s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
