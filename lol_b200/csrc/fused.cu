@@ -44,7 +44,7 @@ bool fused_ac_available(const void* slot, bool inverse);
 int fused_ac_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st);
 
 // fused_stream.cu
-const char* fused_stream_line_name(const lolb_plan* pl);
+const char* fused_stream_line_name(const lolb_plan* pl, bool ginv);
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
 int fused_stream_mul(const lolb_plan* pl, int64_t* a, const int64_t* b, int64_t batch, int64_t b_batch, cudaStream_t st);
 
@@ -118,7 +118,7 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
   if (!strcmp(op, "mulRq") || !strcmp(op, "MulGCRT") || !strcmp(op, "DivGCRT")) return ((int64_t)pl->n * pl->k) % 2 == 0 ? "mul_stream" : "generic";
   if (pl->kind == PLAN_RQ && (!strcmp(op, "L") || !strcmp(op, "LInv") || !strcmp(op, "GPow") || !strcmp(op, "GDec") ||
                               !strcmp(op, "GInvPow") || !strcmp(op, "GInvDec")))
-    return fused_stream_line_name(pl);
+    return fused_stream_line_name(pl, !strncmp(op, "GInv", 4));
   if (pl->kind == PLAN_C) {
     if (!strcmp(op, "GaussianDec")) return fused_plain_name(pl, true, false);
     for (const char* nm : {"LR", "LInvR", "GPowR", "GDecR", "LDouble", "LInvDouble"}) if (!strcmp(op, nm)) return fused_plain_name(pl, false, false);

@@ -290,7 +290,9 @@ __device__ __forceinline__ const double* gauss_slot(const GaussAll& E)
   else return E.m13;
 }
 
-template <class R, int KIND, int P>
+// LPT: lines per thread of the Gaussian pass -- 2 when the inputs are loaded (every constant fetched once per two lines, eight chains in
+// flight: 45 % -> 56 % of HBM at m = 2912), 1 when they are drawn in the kernel (the draw wants the registers: 0.80 against 0.97 ms)
+template <class R, int KIND, int P, int LPT>
 __device__ __forceinline__ void plain_tile_axis(typename R::T* tile, const PTileGeom& G, const int ax, const int units, const GaussAll& E)
 {
   typedef typename R::T T;
@@ -298,29 +300,54 @@ __device__ __forceinline__ void plain_tile_axis(typename R::T* tile, const PTile
   const R ring{};
   const int rts = G.rts[ax];
   const int total = units * (G.n / D);
-  for (int L = threadIdx.x; L < total; L += blockDim.x) {
-    const int uh = rts == 1 ? L : (int)__umulhi((uint32_t)L, G.m_rts[ax]), lo = L - uh * rts;
-    T* base = tile + (size_t)uh * rts * D + lo;
-    T v[D];
+  if constexpr (KIND == PASS_GAUSS) {
+    const double* M = gauss_slot<P>(E);
+    const double inv_sqrt2 = 0.70710678118654752440;
+    constexpr int RG = D % 4 == 0 ? 4 : 2;             // rows in flight per line at a bounded register count
+    for (int L0 = threadIdx.x; L0 < total; L0 += LPT * blockDim.x) {
+      T* base[LPT];
+      bool live[LPT];
+      T v[LPT][D];
 #pragma unroll
-    for (int a = 0; a < D; a++) v[a] = base[a * rts];
-    if constexpr (KIND == PASS_GAUSS) {
-      const double* M = gauss_slot<P>(E);
-      const double inv_sqrt2 = 0.70710678118654752440;
-      constexpr int RG = D % 4 == 0 ? 4 : 2;           // rows in flight: independent chains for the FP64 pipe at a bounded register count
+      for (int t = 0; t < LPT; t++) {
+        const int L = L0 + t * blockDim.x;
+        live[t] = L < total;
+        const int Lc = live[t] ? L : L0;
+        const int uh = rts == 1 ? Lc : (int)__umulhi((uint32_t)Lc, G.m_rts[ax]), lo = Lc - uh * rts;
+        base[t] = tile + (size_t)uh * rts * D + lo;
+#pragma unroll
+        for (int a = 0; a < D; a++) v[t][a] = base[t][a * rts];
+      }
 #pragma unroll 1
       for (int r0 = 0; r0 < D; r0 += RG) {             // rolled: the row group is a warp-uniform offset into the constant bank
-        double acc[RG];
+        double acc[LPT][RG];
 #pragma unroll
-        for (int r = 0; r < RG; r++) acc[r] = 0.0;
+        for (int t = 0; t < LPT; t++)
+#pragma unroll
+          for (int r = 0; r < RG; r++) acc[t][r] = 0.0;
 #pragma unroll
         for (int col = 0; col < D; col++)
 #pragma unroll
-          for (int r = 0; r < RG; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(M[(r0 + r) * D + col], v[col]));      // order of random.cpp:33-40
+          for (int r = 0; r < RG; r++) {
+            const double m = M[(r0 + r) * D + col];
 #pragma unroll
-        for (int r = 0; r < RG; r++) base[(r0 + r) * rts] = __dmul_rn(acc[r], inv_sqrt2);
+            for (int t = 0; t < LPT; t++) acc[t][r] = __dadd_rn(acc[t][r], __dmul_rn(m, v[t][col]));      // order of random.cpp:33-40
+          }
+#pragma unroll
+        for (int t = 0; t < LPT; t++)
+          if (live[t]) {
+#pragma unroll
+            for (int r = 0; r < RG; r++) base[t][(r0 + r) * rts] = __dmul_rn(acc[t][r], inv_sqrt2);
+          }
       }
-    } else {
+    }
+  } else {
+    for (int L = threadIdx.x; L < total; L += blockDim.x) {
+      const int uh = rts == 1 ? L : (int)__umulhi((uint32_t)L, G.m_rts[ax]), lo = L - uh * rts;
+      T* base = tile + (size_t)uh * rts * D + lo;
+      T v[D];
+#pragma unroll
+      for (int a = 0; a < D; a++) v[a] = base[a * rts];
       line_ring<KIND, P, R>(ring, v);
 #pragma unroll
       for (int a = 0; a < D; a++) base[a * rts] = v[a];
@@ -328,23 +355,44 @@ __device__ __forceinline__ void plain_tile_axis(typename R::T* tile, const PTile
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Two tile buffers (NBUF = 2, everything but GEN): the next group's elements arrive by cp.async (16-byte, L2-only) while the
+// passes run on the current one, so one CTA overlaps its own HBM reads with its arithmetic instead of relying on co-resident CTAs.
 template <class R, int KIND, bool GEN>
-__global__ void __launch_bounds__(256, KIND == PASS_GAUSS ? 3 : 1)
+__global__ void __launch_bounds__(256, KIND == PASS_GAUSS ? (GEN ? 3 : 2) : 1)
 k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constant__ PTileGeom G, const __grid_constant__ GaussAll E,
              double rscale, uint64_t seed, uint64_t first, double var2)
 {
   typedef typename R::T T;
   static_assert(sizeof(T) == sizeof(typename R::IO), "the tile holds the values as stored");
   extern __shared__ __align__(16) unsigned char plain_tile_raw[];
-  T* tile = reinterpret_cast<T*>(plain_tile_raw);
-  double2* tile16 = reinterpret_cast<double2*>(plain_tile_raw);
   constexpr int PER16 = 16 / (int)sizeof(T);          // values per 16-byte word: 2 (int64, double) or 1 (complex)
+  const int buf_words = G.epb * G.n / PER16;           // 16-byte words per buffer; n is even for the 8-byte rings (checked by the host)
   const int64_t ngroups = (batch + G.epb - 1) / G.epb;
+  auto group_words = [&](int64_t g) { const int64_t e0 = g * G.epb; return (int)(batch - e0 < G.epb ? batch - e0 : G.epb) * (G.n / PER16); };
+  auto prefetch = [&](int64_t g, int buf) {
+    const double2* src = reinterpret_cast<const double2*>(y + (size_t)g * G.epb * G.n);
+    double2* dst = reinterpret_cast<double2*>(plain_tile_raw) + (size_t)buf * buf_words;
+    const int words = group_words(g);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) cp_async16(dst + i, src + i);
+    cp_async_commit();
+  };
+  int cur = 0;
+  if constexpr (!GEN) { if ((int64_t)blockIdx.x < ngroups) prefetch(blockIdx.x, 0); }
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t e0 = g * G.epb;
     const int cnt = (int)(batch - e0 < G.epb ? batch - e0 : G.epb);
-    double2* src = reinterpret_cast<double2*>(y + (size_t)e0 * G.n);
-    const int words = cnt * G.n / PER16;               // n is even for the 8-byte rings (checked by the host)
+    const int words = cnt * (G.n / PER16);
+    double2* tile16 = reinterpret_cast<double2*>(plain_tile_raw) + (size_t)cur * buf_words;
+    T* tile = reinterpret_cast<T*>(tile16);
+    double2* dst = reinterpret_cast<double2*>(y + (size_t)e0 * G.n);
     if constexpr (GEN) {
       const int half = G.n / 2;
       for (int i = threadIdx.x; i < words; i += blockDim.x) {
@@ -353,29 +401,19 @@ k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constan
         gauss_pair(seed, first + (uint64_t)(e0 + u), (uint32_t)p, var2, g0, g1);
         tile16[i] = make_double2(g0, g1);
       }
+      __syncthreads();
     } else {
-      for (int i0 = threadIdx.x; i0 < words; i0 += 4 * blockDim.x) {      // four 16-byte loads in flight per thread
-        double2 r[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u * blockDim.x;
-          r[u] = i < words ? __ldcs(src + i) : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u * blockDim.x;
-          if (i < words) tile16[i] = r[u];
-        }
-      }
+      cp_async_wait_all();
+      __syncthreads();            // the current tile is complete, and every thread is past the previous iteration's reads of the other buffer
+      if (g + gridDim.x < ngroups) prefetch(g + gridDim.x, cur ^ 1);
     }
-    __syncthreads();
     for (int ax = 0; ax < G.naxes; ax++) {
       switch (G.p[ax]) {
-        case 3: plain_tile_axis<R, KIND, 3>(tile, G, ax, cnt, E); break;
-        case 5: plain_tile_axis<R, KIND, 5>(tile, G, ax, cnt, E); break;
-        case 7: plain_tile_axis<R, KIND, 7>(tile, G, ax, cnt, E); break;
-        case 11: plain_tile_axis<R, KIND, 11>(tile, G, ax, cnt, E); break;
-        default: plain_tile_axis<R, KIND, 13>(tile, G, ax, cnt, E); break;
+        case 3: plain_tile_axis<R, KIND, 3, GEN ? 1 : 2>(tile, G, ax, cnt, E); break;
+        case 5: plain_tile_axis<R, KIND, 5, GEN ? 1 : 2>(tile, G, ax, cnt, E); break;
+        case 7: plain_tile_axis<R, KIND, 7, GEN ? 1 : 2>(tile, G, ax, cnt, E); break;
+        case 11: plain_tile_axis<R, KIND, 11, GEN ? 1 : 2>(tile, G, ax, cnt, E); break;
+        default: plain_tile_axis<R, KIND, 13, GEN ? 1 : 2>(tile, G, ax, cnt, E); break;
       }
       __syncthreads();
     }
@@ -384,9 +422,9 @@ k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constan
       if constexpr (sizeof(T) == 16) {                 // complex: optional real scale (g.cpp:209-220 intent), as k_line_plain
         if (rscale != 0.0) v = make_double2(__dmul_rn(v.x, rscale), __dmul_rn(v.y, rscale));
       }
-      __stcs(src + i, v);
+      __stcs(dst + i, v);
     }
-    __syncthreads();
+    if constexpr (GEN) __syncthreads(); else cur ^= 1;
   }
 }
 
@@ -518,19 +556,19 @@ int launched(const char* what)
 }
 
 // shared-memory tile kernel: odd primes from {3, 5, 7, 11, 13}, at most four odd axes, one element within the opt-in shared memory
-bool ptile_geom(const lolb_plan* pl, int fold_k, size_t tsize, bool quad, PTileGeom* G, int (&p)[4], int (&ppi)[4], int64_t (&mp)[4])
+bool ptile_geom(const lolb_plan* pl, int fold_k, size_t tsize, int quad /* 0 line operators, 1 Gaussian drawn in the kernel, 2 Gaussian loaded */, PTileGeom* G, int (&p)[4], int (&ppi)[4], int64_t (&mp)[4])
 {
   int64_t r[4];
   const int cnt = odd_axes(pl, p, r, ppi, mp);
   if (cnt < 1 || cnt > 4) return false;
   for (int i = 0; i < cnt; i++) if (p[i] != 3 && p[i] != 5 && p[i] != 7 && p[i] != 11 && p[i] != 13) return false;
   const int64_t n = (int64_t)pl->n * fold_k;
-  if ((tsize == 8 && (n & 1)) || n * (int64_t)tsize > 160 * 1024) return false;
+  if ((tsize == 8 && (n & 1)) || n * (int64_t)tsize > 100 * 1024) return false;
   // CTA shape: lolb_internal.cuh::choose_tile_shape; LOLB_PLAIN_TILE_BYTES / _EPB / _THREADS override for tuning runs
   static const int tile_bytes = [] { const char* e = getenv("LOLB_PLAIN_TILE_BYTES"); return e ? atoi(e) : 40960; }();
   static const int epb_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_EPB"); return e ? atoi(e) : 0; }();
   static const int thr_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_THREADS"); return e ? atoi(e) : 0; }();
-  TileShape sh = choose_tile_shape(n, p, cnt, tsize, (size_t)tile_bytes, quad);
+  TileShape sh = choose_tile_shape(n, p, cnt, tsize, (size_t)tile_bytes, quad != 0, quad == 2 ? 2 : 1);
   if (epb_env > 0) sh.epb = epb_env;
   if (thr_env >= 32 && thr_env <= 256) sh.threads = thr_env / 32 * 32;
   const int64_t epb = sh.epb;
@@ -550,7 +588,7 @@ template <class R, int KIND, bool GEN>
 int launch_plain_tile(const lolb_plan* pl, const PTileGeom& G, const GaussAll& E, typename R::IO* y, int64_t batch, double rscale,
                       uint64_t seed, uint64_t first, double var2, cudaStream_t st)
 {
-  const size_t smem = (size_t)G.epb * G.n * sizeof(typename R::T);
+  const size_t smem = (size_t)G.epb * G.n * sizeof(typename R::T) * (GEN ? 1 : 2);      // two tile buffers: k_plain_tile prefetches the next group
   const int64_t groups = (batch + G.epb - 1) / G.epb;
   int per_sm = (int)(200 * 1024 / (smem + 1024));
   if (per_sm > 2048 / G.threads) per_sm = 2048 / G.threads;
@@ -627,7 +665,7 @@ const char* fused_plain_name(const lolb_plan* pl, bool gauss, bool cplx)
   if (gauss && pl->k != 1) return "generic";
   if (make_geom(pl, gauss ? 1 : pl->k, &G, p, ppi, mp, &cnt)) return "plain_stream";
   if (cnt == 0) return "identity";
-  if (plain_tile_enabled() && ptile_geom(pl, gauss ? 1 : pl->k, cplx ? 16 : 8, gauss, &TG, p, ppi, mp)) return "plain_tile";
+  if (plain_tile_enabled() && ptile_geom(pl, gauss ? 1 : pl->k, cplx ? 16 : 8, gauss ? 2 : 0, &TG, p, ppi, mp)) return "plain_tile";
   return "generic";
 }
 
@@ -642,14 +680,14 @@ int fused_plain_line(const lolb_plan* pl, int ring, int kind, void* y, int64_t b
     PTileGeom TG{};
     if (cnt == 0 || !plain_tile_enabled()) return LOLB_FUSED_UNAVAILABLE;
     if (ring == RING_I64) {
-      if (kind == PASS_GINVPOW || kind == PASS_GINVDEC || !ptile_geom(pl, pl->k, 8, false, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+      if (kind == PASS_GINVPOW || kind == PASS_GINVDEC || !ptile_geom(pl, pl->k, 8, 0, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
       return plain_tile_kind<I64Ring>(pl, kind, TG, (int64_t*)y, batch, 0.0, st);
     }
     if (ring == RING_F64) {
-      if (!ptile_geom(pl, pl->k, 8, false, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+      if (!ptile_geom(pl, pl->k, 8, 0, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
       return plain_tile_kind<F64Ring>(pl, kind, TG, (double*)y, batch, 0.0, st);
     }
-    if (!ptile_geom(pl, pl->k, 16, false, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+    if (!ptile_geom(pl, pl->k, 16, 0, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
     return plain_tile_kind<C64Ring>(pl, kind, TG, (double2*)y, batch, rscale, st);
   }
   if (ring == RING_I64) {
@@ -684,7 +722,7 @@ int fused_plain_gauss_gen(const lolb_plan* pl, double* y, int64_t batch, cudaStr
   if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) {
     if (cnt == 0) return LOLB_OK;
     PTileGeom TG{};
-    if (!plain_tile_enabled() || !ptile_geom(pl, 1, 8, true, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+    if (!plain_tile_enabled() || !ptile_geom(pl, 1, 8, gen ? 1 : 2, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
     GaussAll A{};
     for (int ax = 0; ax < cnt; ax++) {
       const int P = p[ax];

@@ -200,16 +200,20 @@ k_line_stream(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Li
 // runs one in-place pass per odd-prime axis (a thread per line of p - 1 words, consecutive threads on consecutive lines) and
 // writes the elements back the same way: one HBM round trip for any number of axes.
 struct TileGeom {
-  int32_t n, naxes, epb, threads;
+  int32_t n, naxes, epb, threads;  // n: words per element (tupSize folded in: word w belongs to limb w mod k)
   int32_t p[4], rts[4], lines[4];
   uint32_t m_rts[4];              // ceil(2^32 / d): exact floor(x / d) by __umulhi for x d < 2^32
+  int32_t k;
+  uint32_t m_k;                   // ceil(2^32 / k)
 };
 
 __device__ __forceinline__ int fdiv(uint32_t x, int d, uint32_t magic) { return d == 1 ? (int)x : (int)__umulhi(x, magic); }
 
-template <int KIND, int P, typename I>
+// MULTI (tupSize > 1): the interleaved element is the tensor with one more innermost axis of length k -- strides and n carry the
+// factor k, the limb of a line is its index mod k, and the per-limb constants (Shoup factors in `sps`) are read per line.
+template <int KIND, int P, typename I, bool MULTI>
 __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, const int ax, const int units, const ZqConsts& Z, const bool scale,
-                                          const uint32_t sp)
+                                          const uint32_t* sps)
 {
   constexpr int D = P - 1;
   const int rts = G.rts[ax], lines = G.lines[ax];
@@ -218,8 +222,9 @@ __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, con
     // line L of the CTA's elements: element e, block hi, offset lo -> e n + hi rts D + lo = (L / rts) rts D + lo: one division per line
     const int uh = fdiv((uint32_t)L, rts, G.m_rts[ax]), lo = L - uh * rts;
     uint32_t* base = tile + (size_t)uh * rts * D + lo;
-    const uint32_t q = Z.q[0];
-    const uint64_t mu = Z.mu[0];
+    const int limb = MULTI ? L - fdiv((uint32_t)L, G.k, G.m_k) * G.k : 0;      // rts is a multiple of k
+    const uint32_t q = Z.q[limb];
+    const uint64_t mu = Z.mu[limb];
     I v[D];
 #pragma unroll
     for (int a = 0; a < D; a++) v[a] = (I)base[a * rts];
@@ -228,63 +233,72 @@ __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, con
 #pragma unroll
     for (int a = 0; a < D; a++) {
       uint32_t r = (uint32_t)reduce_biased(v[a], bias, q, mu);
-      if (scale) r = sizeof(I) == 4 ? mul_fixed(r, Z.scale[0], sp, q) : barrett64((uint64_t)r * Z.scale[0], q, mu);
+      if (scale) r = sizeof(I) == 4 ? mul_fixed(r, Z.scale[limb], sps[limb], q) : barrett64((uint64_t)r * Z.scale[limb], q, mu);
       base[a * rts] = r;
     }
   }
 }
 
-template <int KIND, bool NARROW>
+template <int KIND, bool NARROW, bool MULTI>
 __global__ void __launch_bounds__(256)
 k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ TileGeom G, const __grid_constant__ ZqConsts Z, int scale)
 {
   typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
+  // shared memory: the u32 tile of the current group, then a raw int64 staging buffer the NEXT group arrives in by cp.async
+  // (16-byte, L2-only) while the passes run on the current one: a CTA overlaps its own HBM reads with its arithmetic.
   extern __shared__ __align__(16) uint32_t line_tile[];
-  const uint32_t q = Z.q[0];
-  const uint32_t sp = (NARROW && scale) ? (uint32_t)(((uint64_t)Z.scale[0] << 32) / q) : 0u;      // NARROW implies q < 2^31
+  const int tile_words = G.epb * G.n;
+  longlong2* raw = reinterpret_cast<longlong2*>(line_tile + ((tile_words + 3) & ~3));      // 16-byte aligned
+  __shared__ uint32_t sps[kMaxLimbs];                                                            // Shoup factors of rad_odd^-1 per limb
+  if (threadIdx.x < G.k) sps[threadIdx.x] = (NARROW && scale) ? (uint32_t)(((uint64_t)Z.scale[threadIdx.x] << 32) / Z.q[threadIdx.x]) : 0u;      // NARROW implies q < 2^31
   const int64_t ngroups = (batch + G.epb - 1) / G.epb;
+  auto prefetch = [&](int64_t g) {
+    const int64_t e0 = g * G.epb;
+    const int pairs = (int)(batch - e0 < G.epb ? batch - e0 : G.epb) * G.n / 2;      // n is even (checked by the host)
+    const longlong2* src = reinterpret_cast<const longlong2*>(y + (size_t)e0 * G.n);
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(raw + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int64_t)blockIdx.x < ngroups) prefetch(blockIdx.x);
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t e0 = g * G.epb;
     const int cnt = (int)(batch - e0 < G.epb ? batch - e0 : G.epb);
-    longlong2* src = reinterpret_cast<longlong2*>(y + (size_t)e0 * G.n);
-    const int pairs = cnt * G.n / 2;      // n is even (checked by the host)
+    longlong2* dst = reinterpret_cast<longlong2*>(y + (size_t)e0 * G.n);
+    const int pairs = cnt * G.n / 2;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();      // the staged group is complete, and every thread is past the previous iteration's reads of the tile
     // ---- in: word w of the piece -> tile[w]
-    for (int i0 = threadIdx.x; i0 < pairs; i0 += 4 * blockDim.x) {      // four 16-byte loads in flight per thread (ncu: one was 59 % long_scoreboard)
-      longlong2 r[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + u * blockDim.x;
-        r[u] = i < pairs ? __ldcs(src + i) : make_longlong2(0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + u * blockDim.x;
-        if (i >= pairs) break;
-        uint32_t c0 = (uint32_t)r[u].x, c1 = (uint32_t)r[u].y;
-        if ((uint64_t)r[u].x >= (uint64_t)q) { int64_t t = r[u].x % (int64_t)q; c0 = (uint32_t)(t < 0 ? t + q : t); }      // like the reference's c % q
-        if ((uint64_t)r[u].y >= (uint64_t)q) { int64_t t = r[u].y % (int64_t)q; c1 = (uint32_t)(t < 0 ? t + q : t); }
-        *reinterpret_cast<uint2*>(line_tile + 2 * i) = make_uint2(c0, c1);
-      }
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+      const longlong2 r = raw[i];
+      uint32_t c0 = (uint32_t)r.x, c1 = (uint32_t)r.y;
+      const int l0 = MULTI ? 2 * i - fdiv((uint32_t)(2 * i), G.k, G.m_k) * G.k : 0, l1 = MULTI ? (l0 + 1 == G.k ? 0 : l0 + 1) : 0;
+      const uint32_t q0 = Z.q[l0], q1 = Z.q[l1];
+      if ((uint64_t)r.x >= (uint64_t)q0) { int64_t t = r.x % (int64_t)q0; c0 = (uint32_t)(t < 0 ? t + q0 : t); }      // like the reference's c % q
+      if ((uint64_t)r.y >= (uint64_t)q1) { int64_t t = r.y % (int64_t)q1; c1 = (uint32_t)(t < 0 ? t + q1 : t); }
+      *reinterpret_cast<uint2*>(line_tile + 2 * i) = make_uint2(c0, c1);
     }
     __syncthreads();
+    if (g + gridDim.x < ngroups) prefetch(g + gridDim.x);
     // ---- one pass per odd-prime axis, in place
     for (int ax = 0; ax < G.naxes; ax++) {
       const bool sc = scale && ax == G.naxes - 1;
       switch (G.p[ax]) {
-        case 3: tile_axis<KIND, 3, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
-        case 5: tile_axis<KIND, 5, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
-        case 7: tile_axis<KIND, 7, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
-        case 11: tile_axis<KIND, 11, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
-        default: tile_axis<KIND, 13, I>(line_tile, G, ax, cnt, Z, sc, sp); break;
+        case 3: tile_axis<KIND, 3, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 5: tile_axis<KIND, 5, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 7: tile_axis<KIND, 7, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 11: tile_axis<KIND, 11, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        default: tile_axis<KIND, 13, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
       }
       __syncthreads();
     }
     // ---- out
     for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
       const uint2 v = *reinterpret_cast<const uint2*>(line_tile + 2 * i);
-      __stcs(src + i, make_longlong2((int64_t)v.x, (int64_t)v.y));
+      __stcs(dst + i, make_longlong2((int64_t)v.x, (int64_t)v.y));
     }
-    __syncthreads();
   }
 }
 
@@ -400,28 +414,32 @@ static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
 {
   int p[4]; int64_t r[4];
   const int cnt = odd_axes(pl, p, r);
-  if (pl->k != 1 || cnt < 1 || cnt > 4) return false;
+  static const bool multi = [] { const char* e = getenv("LOLB_LINE_TILE_MULTI"); return !e || atoi(e) != 0; }();
+  if ((pl->k != 1 && !multi) || pl->k > kMaxLimbs || cnt < 1 || cnt > 4) return false;
   for (int i = 0; i < cnt; i++) if (p[i] != 3 && p[i] != 5 && p[i] != 7 && p[i] != 11 && p[i] != 13) return false;
-  if ((pl->n & 1) || pl->n > 40960) return false;
-  G->n = pl->n;
+  const int64_t nk = (int64_t)pl->n * pl->k;
+  if ((nk & 1) || nk > 16384) return false;      // 12 bytes of shared memory per word
+  G->n = (int32_t)nk;
+  G->k = pl->k;
+  G->m_k = magic_div((uint32_t)pl->k);
   G->naxes = cnt;
   // measured 2048 / 4096 / 8192 / 16384 words per CTA: m = 2912 L 50 / 60 / 55 / 58 %, m = 5460 38 / 49 / 47 / 46 % of HBM
   // round 2, last: the CTA shape (threads, elements) that leaves no idle threads in the last round of an axis pass
   // (lolb_internal.cuh::choose_tile_shape) within `tile_words`; LOLB_LINE_TILE_SHAPE=0 keeps 256 threads x tile_words / n elements
   static const int tile_words = [] { const char* e = getenv("LOLB_LINE_TILE_WORDS"); return e ? atoi(e) : 4096; }();
   static const bool shaped = [] { const char* e = getenv("LOLB_LINE_TILE_SHAPE"); return !e || atoi(e) != 0; }();
-  int64_t epb = tile_words / pl->n;
+  int64_t epb = tile_words / nk;
   if (epb < 1) epb = 1;
   G->threads = 256;
   if (shaped) {
-    const TileShape sh = choose_tile_shape(pl->n, p, cnt, sizeof(uint32_t), (size_t)tile_words * sizeof(uint32_t), false);
+    const TileShape sh = choose_tile_shape(nk, p, cnt, sizeof(uint32_t), (size_t)tile_words * sizeof(uint32_t), false);
     epb = sh.epb;
     G->threads = sh.threads;
   }
   G->epb = (int32_t)epb;
   for (int i = 0; i < cnt; i++) {
-    G->p[i] = p[i]; G->rts[i] = (int32_t)r[i]; G->lines[i] = pl->n / (p[i] - 1);
-    G->m_rts[i] = magic_div((uint32_t)r[i]);
+    G->p[i] = p[i]; G->rts[i] = (int32_t)(r[i] * pl->k); G->lines[i] = (int32_t)(nk / (p[i] - 1));
+    G->m_rts[i] = magic_div((uint32_t)(r[i] * pl->k));
   }
   return true;
 }
@@ -431,7 +449,7 @@ static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqCons
 {
   bool narrow = true;
   for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * line_mult<KIND>(13) < ((int64_t)1 << 31);
-  const size_t smem = (size_t)G.epb * G.n * sizeof(uint32_t);
+  const size_t smem = (size_t)G.epb * G.n * (sizeof(uint32_t) + sizeof(int64_t)) + 16;      // u32 tile + the raw staging buffer of the next group
   const int64_t groups = (batch + G.epb - 1) / G.epb;
   int per_sm = (int)(200 * 1024 / (smem + 1024));
   if (per_sm > 2048 / G.threads) per_sm = 2048 / G.threads;
@@ -443,7 +461,9 @@ static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqCons
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) kern<<<(int)grid, G.threads, smem, st>>>(y, batch, G, zc, scale ? 1 : 0);
   };
-  if (narrow) go(k_line_tile<KIND, true>); else go(k_line_tile<KIND, false>);
+  if (pl->k == 1) { if (narrow) go(k_line_tile<KIND, true, false>); else go(k_line_tile<KIND, false, false>); }
+  else if (narrow) go(k_line_tile<KIND, true, true>);
+  else return LOLB_FUSED_UNAVAILABLE;      // several limbs in the 64-bit mode: the register-tile launches (fused_stream_line routes them there)
   if (e != cudaSuccess) return cuda_fail(e, "k_line_tile shared memory");
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_line_tile");
@@ -459,16 +479,20 @@ static int line_route(const lolb_plan* pl, LineStep (&st)[4], int* nsteps, TileG
   if (ns == 0) return 0;
   if (ns == 1) return 1;
   static const bool use_tile = [] { const char* e = getenv("LOLB_LINE_TILE"); return !e || atoi(e) != 0; }();
-  if (use_tile && line_tile_geom(pl, G)) return 2;      // tupSize 1 only: with several limbs two register-tile launches measured faster (46 % against 36 % at m = 5824, k = 4)
+  if (use_tile && line_tile_geom(pl, G)) return 2;      // any tupSize (folded into the strides) since the staged, double-buffered version
   return ns > 1 ? 3 : -1;
 }
 
-const char* fused_stream_line_name(const lolb_plan* pl)
+const char* fused_stream_line_name(const lolb_plan* pl, bool ginv)
 {
   LineStep st[4];
   TileGeom G;
   int ns;
-  const int route = line_route(pl, st, &ns, &G);
+  int route = line_route(pl, st, &ns, &G);
+  if (route == 2 && pl->k > 1) {      // several limbs: the tile kernel in its 32-bit mode only (fused_stream_line)
+    const ZqConsts& zc = ginv ? pl->zq_radinv : pl->zq_plain;
+    for (int t = 0; t < pl->k; t++) if ((int64_t)zc.q[t] * (ginv ? 13 * 13 : 13 + 2) >= ((int64_t)1 << 31)) route = 3;
+  }
   return route == 0 ? "identity" : route == 2 ? "line_tile" : route > 0 ? "line_stream" : "generic";
 }
 
@@ -480,7 +504,14 @@ int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool sc
   const int route = line_route(pl, steps, &ns, &TG);
   if (batch <= 0) return LOLB_OK;
   if (route < 0) return LOLB_FUSED_UNAVAILABLE;
-  if (route == 2 && !((uintptr_t)y & 15)) {
+  // several limbs in the tile kernel pay off in its 32-bit mode (m = 5824, tupSize 2 / 4: L 77 % / 52 % against 47 % for the register
+  // tiles); in the 64-bit mode (25-bit moduli under /g) the register-tile launches are as fast or faster (35 % / 29 % against 35 % / 37 %)
+  bool tile_ok = route == 2 && !((uintptr_t)y & 15);
+  if (tile_ok && pl->k > 1 && ns > 1) {
+    const int64_t mult = (kind == PASS_GINVPOW || kind == PASS_GINVDEC) ? 13 * 13 : 13 + 2;      // line_mult<KIND>(13)
+    for (int t = 0; t < pl->k; t++) tile_ok = tile_ok && (int64_t)zc.q[t] * mult < ((int64_t)1 << 31);
+  }
+  if (tile_ok) {
     switch (kind) {
       case PASS_L: return launch_line_tile<PASS_L>(pl, TG, zc, scale, y, batch, st);
       case PASS_LINV: return launch_line_tile<PASS_LINV>(pl, TG, zc, scale, y, batch, st);

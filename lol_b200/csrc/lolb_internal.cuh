@@ -152,7 +152,7 @@ struct PerDeviceOnce {
 // per CTA) with the least idle work -- an axis weighs (p - 1) per line, (p - 1)^2 for dense matrices -- and, within 2 %, the
 // smallest tile (more CTAs per SM overlap one CTA's loads with another's passes), then the larger CTA.
 struct TileShape { int threads, epb; };
-inline TileShape choose_tile_shape(int64_t n, const int* p, int cnt, size_t value_bytes, size_t cap_bytes, bool quad)
+inline TileShape choose_tile_shape(int64_t n, const int* p, int cnt, size_t value_bytes, size_t cap_bytes, bool quad, int lines_per_thread = 1)
 {
   int64_t cap = (int64_t)(cap_bytes / ((size_t)n * value_bytes));
   if (cap < 1) cap = 1;
@@ -165,7 +165,8 @@ inline TileShape choose_tile_shape(int64_t n, const int* p, int cnt, size_t valu
       for (int i = 0; i < cnt; i++) {
         const double w = quad ? (double)(p[i] - 1) * (p[i] - 1) : (double)(p[i] - 1);
         const int64_t lines = e * (n / (p[i] - 1));
-        used += w * (double)((lines + t - 1) / t * t);
+        const int64_t step = (int64_t)t * lines_per_thread;      // lines a CTA takes per round
+        used += w * (double)((lines + step - 1) / step * step);
         work += w * (double)lines;
       }
       const double W = used / work;

@@ -216,6 +216,7 @@ BATCH_PARAMS = [(7, [29]), (33, [67]), (77, [463]), (143, [859]), (448, [3144961
                 (64 * 81, [10369]), (32 * 7 * 13, [8737]), (8 * 7 * 13, [8737]), (8 * 5 * 7 * 13, [14561]), (2016, [2017]),
                 (64 * 27, [3457, 1002241]), (64 * 81, [10031041]), (32 * 7 * 13, [101921]), (8 * 5 * 7 * 13, [1015561, 1026481]),
                 (64 * 7 * 13, [3144961]), (64 * 7 * 13, [23297]),
+                (64 * 7 * 13, [19393921, 18869761]), (32 * 7 * 13, [25159681, 19918081, 19393921]), (64 * 7 * 13, [25159681, 19918081, 19393921, 18869761]),      # HomomPRF chains: line_tile with tupSize folded
                 (128 * 7 * 13, [23297]), (128 * 7 * 13, [3144961]),      # a = 7: two column halves per lane
                 (4 * 3 * 5 * 7 * 13, [3144961]), (9 * 5 * 7 * 13, [3144961]), (4 * 3 * 5 * 7 * 13, [21841]), (9 * 5 * 7 * 13, [8191])]      # four odd prime powers      # lol-apps tunnel ring H1 at its modulus, and the Twace-Embed benchmark modulus (Montgomery class)
 FUSED_W_INDICES = {64 * 27, 64 * 81, 32 * 7 * 13, 8 * 7 * 13, 8 * 5 * 7 * 13, 2016, 64 * 7 * 13, 128 * 7 * 13, 5460, 4095, 448}
@@ -978,3 +979,38 @@ def test_tgaussiandec_one_pass_equals_draw_then_transform(torch_cuda, gpu_oracle
     pe, ruc = T.pe_array(m), T.ru_tables_c(m)
     for b in (0, B - 1):
         assert rel_err(two[b].cpu().numpy(), gpu_oracle.tensorGaussianDec(raw[b].cpu().numpy(), pe, ruc)) <= FLOAT_TOL
+
+
+@pytest.mark.parametrize("m,qs", [(2912, [143165569, 143171393]), (2912, [12655553, 3144961, 12719617]), (5460, [3144961, 21841]), (91, [547, 911, 1093, 2003, 2549])],
+                         ids=lambda v: str(v))
+def test_line_tile_several_limbs(torch_cuda, gpu_oracle, m, qs):
+    """`k_line_tile` with tupSize folded into the strides: limbs on both sides of the int32 / int64 thresholds in one element, an odd
+    tupSize, more elements than one CTA's group, against the oracle (l.cpp:28-98, g.cpp:16-123 through tensor.h:39-74)."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorRq
+    t = CudaTensorRq(m, qs)
+    assert t.plan.kernel_name("L") == "line_tile"
+    n, pe, B = t.n, T.pe_array(m), 45
+    rng = np.random.default_rng(m)
+    y = zq_input(rng, n, qs, batch=B)
+    y[0] = np.array(qs) - 1
+    y[1, ::2] = np.array(qs) - 1
+    x = torch.from_numpy(y).cuda()
+    for meth, nm in (("l", "tensorLRq"), ("lInv", "tensorLInvRq"), ("mulGPow", "tensorGPowRq"), ("mulGDec", "tensorGDecRq")):
+        got = getattr(t, meth)(x).cpu().numpy()
+        for b in (0, 1, 2, 17, B - 1):
+            assert np.array_equal(got[b], getattr(gpu_oracle, nm)(y[b], pe, qs)), (nm, b)
+    for meth, nm in (("divGPow", "tensorGInvPowRq"), ("divGDec", "tensorGInvDecRq")):
+        got = getattr(t, meth)(x).cpu().numpy()
+        for b in (0, 1, 2, 17, B - 1):
+            assert np.array_equal(got[b], getattr(gpu_oracle, nm)(y[b], pe, qs)[0]), (nm, b)
+    # outside the Haskell contract: non-canonical residues are reduced like `c % q` on the way in (every kernel family agrees)
+    z = y.copy()
+    z[2, :7] = z[2, :7] + np.array(qs) * 5
+    z[3, 5:9] = z[3, 5:9] - np.array(qs) * 3
+    xz = torch.from_numpy(z).cuda()
+    t.plan.force_generic(True)
+    ref = t.divGDec(t.l(x))
+    t.plan.force_generic(False)
+    assert torch.equal(t.divGDec(t.l(x)), ref)
+    assert torch.equal(t.mulGPow(xz), t.mulGPow(x))
