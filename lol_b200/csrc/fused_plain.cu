@@ -355,6 +355,9 @@ __device__ __forceinline__ void plain_tile_axis(typename R::T* tile, const PTile
   }
 }
 
+__device__ __forceinline__ int64_t wsum(int64_t v);
+__device__ __forceinline__ double wsum(double v);
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -368,7 +371,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <class R, int KIND, bool GEN>
 __global__ void __launch_bounds__(256, KIND == PASS_GAUSS ? (GEN ? 3 : 2) : 1)
 k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constant__ PTileGeom G, const __grid_constant__ GaussAll E,
-             double rscale, uint64_t seed, uint64_t first, double var2)
+             double rscale, uint64_t seed, uint64_t first, double var2, typename R::IO* __restrict__ out)
 {
   typedef typename R::T T;
   static_assert(sizeof(T) == sizeof(typename R::IO), "the tile holds the values as stored");
@@ -417,12 +420,42 @@ k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constan
       }
       __syncthreads();
     }
-    for (int i = threadIdx.x; i < words; i += blockDim.x) {
-      double2 v = tile16[i];
-      if constexpr (sizeof(T) == 16) {                 // complex: optional real scale (g.cpp:209-220 intent), as k_line_plain
-        if (rscale != 0.0) v = make_double2(__dmul_rn(v.x, rscale), __dmul_rn(v.y, rscale));
+    if constexpr (KIND == PASS_NORMSQ) {
+      // norm.cpp:15-80: out[e] = sum_j y[j] ((x)(I + J) y)[j] -- the tile holds the second factor, the first is re-read (an L2 hit: the
+      // element was fetched by this CTA a few microseconds ago); y is not written
+      if constexpr (sizeof(T) == 8) {
+        __shared__ T part[64 * 8];
+        const R ring{};
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int u = 0; u < cnt; u++) {
+          const T* orig = reinterpret_cast<const T*>(y) + (size_t)(e0 + u) * G.n;
+          const T* second = tile + (size_t)u * G.n;
+          T sacc = ring.zero();
+          for (int j0 = threadIdx.x; j0 < G.n; j0 += 4 * blockDim.x) {      // four re-reads in flight per thread
+            T o[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) { const int j = j0 + w * blockDim.x; o[w] = j < G.n ? __ldg(orig + j) : ring.zero(); }
+#pragma unroll
+            for (int w = 0; w < 4; w++) { const int j = j0 + w * blockDim.x; if (j < G.n) sacc = ring.add(sacc, ring.mul(o[w], second[j])); }
+          }
+          sacc = wsum(sacc);
+          if (lane == 0) part[u * 8 + warp] = sacc;
+        }
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+          T sacc = part[threadIdx.x * 8];
+          for (int w = 1; w < nw; w++) sacc = ring.add(sacc, part[threadIdx.x * 8 + w]);
+          out[e0 + threadIdx.x] = sacc;
+        }
       }
-      __stcs(dst + i, v);
+    } else {
+      for (int i = threadIdx.x; i < words; i += blockDim.x) {
+        double2 v = tile16[i];
+        if constexpr (sizeof(T) == 16) {                 // complex: optional real scale (g.cpp:209-220 intent), as k_line_plain
+          if (rscale != 0.0) v = make_double2(__dmul_rn(v.x, rscale), __dmul_rn(v.y, rscale));
+        }
+        __stcs(dst + i, v);
+      }
     }
     if constexpr (GEN) __syncthreads(); else cur ^= 1;
   }
@@ -586,7 +619,7 @@ bool ptile_geom(const lolb_plan* pl, int fold_k, size_t tsize, int quad /* 0 lin
 
 template <class R, int KIND, bool GEN>
 int launch_plain_tile(const lolb_plan* pl, const PTileGeom& G, const GaussAll& E, typename R::IO* y, int64_t batch, double rscale,
-                      uint64_t seed, uint64_t first, double var2, cudaStream_t st)
+                      uint64_t seed, uint64_t first, double var2, cudaStream_t st, typename R::IO* out = nullptr)
 {
   const size_t smem = (size_t)G.epb * G.n * sizeof(typename R::T) * (GEN ? 1 : 2);      // two tile buffers: k_plain_tile prefetches the next group
   const int64_t groups = (batch + G.epb - 1) / G.epb;
@@ -600,7 +633,7 @@ int launch_plain_tile(const lolb_plan* pl, const PTileGeom& G, const GaussAll& E
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "k_plain_tile shared memory");
   }
-  kern<<<(int)grid, G.threads, smem, st>>>(y, batch, G, E, rscale, seed, first, var2);
+  kern<<<(int)grid, G.threads, smem, st>>>(y, batch, G, E, rscale, seed, first, var2, out);
   return launched("k_plain_tile");
 }
 
@@ -773,7 +806,12 @@ static int normsq_combo(const lolb_plan* pl, const typename R::IO* y, typename R
   if (pl->k != 1) return LOLB_FUSED_UNAVAILABLE;
   PlainGeom G{};
   int p[4], ppi[4], cnt; int64_t mp[4];
-  if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) return LOLB_FUSED_UNAVAILABLE;
+  if (!make_geom(pl, 1, &G, p, ppi, mp, &cnt)) {
+    PTileGeom TG{};
+    static const GaussAll none{};
+    if (cnt == 0 || !plain_tile_enabled() || !ptile_geom(pl, 1, 8, 0, &TG, p, ppi, mp)) return LOLB_FUSED_UNAVAILABLE;
+    return launch_plain_tile<R, PASS_NORMSQ, false>(pl, TG, none, const_cast<typename R::IO*>(y), batch, 0.0, 0, 0, 0.0, st, out);
+  }
   int threads = G.tiles >= 512 ? 512 : ((G.tiles + 31) / 32) * 32;
   for (int c = 512; c >= 128; c -= 32) if (G.tiles % c == 0) { threads = c; break; }
   int64_t grid = (int64_t)pl->num_sms * (2048 / threads);

@@ -23,6 +23,6 @@ for name, fn, bpc in cases:
     for _ in range(2): capi.check(fn())
     s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); s.record()
-    for _ in range(5): capi.check(fn())
-    e.record(); torch.cuda.synchronize(); ms = s.elapsed_time(e) / 5
+    for _ in range(20): capi.check(fn())
+    e.record(); torch.cuda.synchronize(); ms = s.elapsed_time(e) / 20
     print(f"{name:12s} ms {ms:8.3f}  elems/s {B/ms*1e3:12.0f}  frac {bpc*n*B/ms/1e6/6555.8:.4f}")
