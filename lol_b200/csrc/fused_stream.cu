@@ -73,6 +73,20 @@ __device__ __forceinline__ void line_op(I (&v)[P - 1])
 template <int KIND>
 __host__ __device__ constexpr int line_mult(int P) { return (KIND == PASS_GINVPOW || KIND == PASS_GINVDEC) ? P * P : P + 2; }
 
+// Arithmetic mode of the tile kernel for an operator and a set of moduli: 1 = int32 intermediates (line_mult q < 2^31), 2 = the
+// divisions by g with running sums kept reduced (lineop_ginv_red: q max(2 P, P (P - 1) / 2) < 2^32 at P = 13, i.e. q < 55 M -- the
+// 25-bit moduli of the HomomPRF chains), 0 = int64 intermediates
+inline int line_tile_mode(int kind, const ZqConsts& zc, int k)
+{
+  const bool ginv = kind == PASS_GINVPOW || kind == PASS_GINVDEC;
+  bool narrow = true, red = ginv;
+  for (int t = 0; t < k; t++) {
+    narrow = narrow && (int64_t)zc.q[t] * (ginv ? 13 * 13 : 13 + 2) < ((int64_t)1 << 31);
+    red = red && (int64_t)zc.q[t] * 78 < ((int64_t)1 << 32);
+  }
+  return narrow ? 1 : red ? 2 : 0;
+}
+
 struct LineGeom {
   int32_t n, k;
   int32_t RA, RB;        // strides (rts) of the two axes; RB = n when there is no second axis
@@ -209,9 +223,42 @@ struct TileGeom {
 
 __device__ __forceinline__ int fdiv(uint32_t x, int d, uint32_t magic) { return d == 1 ? (int)x : (int)__umulhi(x, magic); }
 
+// The divisions by g on one line with every running value kept in [0, q): the same integers as line_op modulo q (g.cpp:60-123), products
+// bounded by P q instead of P^2 q, so moduli up to 2^32 / 78 stay in 32-bit arithmetic.  v in [0, q) on entry and on exit.
+template <int KIND, int P>
+__device__ __forceinline__ void lineop_ginv_red(uint32_t (&v)[P - 1], const uint32_t q, const uint32_t mu32)
+{
+  constexpr int D = P - 1;
+  if (KIND == PASS_GINVPOW) {                             // v[a] = (P-1-a) lo - (a+1) hi, lo = sum_{i<=a} v, hi = sum_{i>a} v
+    uint32_t sum = 0;
+#pragma unroll
+    for (int a = 0; a < D; a++) sum += v[a];              // <= (P-1) q
+    uint32_t lo = barrett32(sum, q, mu32), hi = 0;
+#pragma unroll
+    for (int a = D - 1; a >= 0; a--) {
+      const uint32_t z = v[a];
+      v[a] = barrett32((uint32_t)(P - 1 - a) * lo + (uint32_t)P * q - (uint32_t)(a + 1) * hi, q, mu32);      // in (0, 2 P q)
+      lo = lo >= z ? lo - z : lo + q - z;
+      hi += z; hi = hi >= q ? hi - q : hi;
+    }
+  } else {                                                // v[D-1] = s = sum (a+1) v[a]; v[a-1] = v[a] - P v_in[a]
+    uint32_t s = 0;
+#pragma unroll
+    for (int a = 0; a < D; a++) s += (uint32_t)(a + 1) * v[a];      // <= P (P-1) / 2 q
+    uint32_t acc = barrett32(s, q, mu32);
+#pragma unroll
+    for (int a = D - 1; a >= 1; a--) {
+      const uint32_t keep = acc;
+      acc = barrett32(acc + (uint32_t)P * q - (uint32_t)P * v[a], q, mu32);      // in (0, (P+1) q)
+      v[a] = keep;
+    }
+    v[0] = acc;
+  }
+}
+
 // MULTI (tupSize > 1): the interleaved element is the tensor with one more innermost axis of length k -- strides and n carry the
 // factor k, the limb of a line is its index mod k, and the per-limb constants (Shoup factors in `sps`) are read per line.
-template <int KIND, int P, typename I, bool MULTI>
+template <int KIND, int P, typename I, bool MULTI, bool RED>
 __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, const int ax, const int units, const ZqConsts& Z, const bool scale,
                                           const uint32_t* sps)
 {
@@ -225,24 +272,34 @@ __device__ __forceinline__ void tile_axis(uint32_t* tile, const TileGeom& G, con
     const int limb = MULTI ? L - fdiv((uint32_t)L, G.k, G.m_k) * G.k : 0;      // rts is a multiple of k
     const uint32_t q = Z.q[limb];
     const uint64_t mu = Z.mu[limb];
-    I v[D];
+    if constexpr (RED) {
+      uint32_t w[D];
 #pragma unroll
-    for (int a = 0; a < D; a++) v[a] = (I)base[a * rts];
-    line_op<KIND, P, I>(v);
-    const int64_t bias = (int64_t)q * line_mult<KIND>(P);
+      for (int a = 0; a < D; a++) w[a] = base[a * rts];
+      lineop_ginv_red<KIND, P>(w, q, (uint32_t)(mu >> 32));
 #pragma unroll
-    for (int a = 0; a < D; a++) {
-      uint32_t r = (uint32_t)reduce_biased(v[a], bias, q, mu);
-      if (scale) r = sizeof(I) == 4 ? mul_fixed(r, Z.scale[limb], sps[limb], q) : barrett64((uint64_t)r * Z.scale[limb], q, mu);
-      base[a * rts] = r;
+      for (int a = 0; a < D; a++) base[a * rts] = scale ? mul_fixed(w[a], Z.scale[limb], sps[limb], q) : w[a];
+    } else {
+      I v[D];
+#pragma unroll
+      for (int a = 0; a < D; a++) v[a] = (I)base[a * rts];
+      line_op<KIND, P, I>(v);
+      const int64_t bias = (int64_t)q * line_mult<KIND>(P);
+#pragma unroll
+      for (int a = 0; a < D; a++) {
+        uint32_t r = (uint32_t)reduce_biased(v[a], bias, q, mu);
+        if (scale) r = sizeof(I) == 4 ? mul_fixed(r, Z.scale[limb], sps[limb], q) : barrett64((uint64_t)r * Z.scale[limb], q, mu);
+        base[a * rts] = r;
+      }
     }
   }
 }
 
-template <int KIND, bool NARROW, bool MULTI>
-__global__ void __launch_bounds__(256)
+template <int KIND, int MODE, bool MULTI>
+__global__ void __launch_bounds__(512)
 k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ TileGeom G, const __grid_constant__ ZqConsts Z, int scale)
 {
+  constexpr bool NARROW = MODE != 0, RED = MODE == 2 && (KIND == PASS_GINVPOW || KIND == PASS_GINVDEC);
   typedef typename std::conditional<NARROW, int32_t, int64_t>::type I;
   // shared memory: the u32 tile of the current group, then a raw int64 staging buffer the NEXT group arrives in by cp.async
   // (16-byte, L2-only) while the passes run on the current one: a CTA overlaps its own HBM reads with its arithmetic.
@@ -286,11 +343,11 @@ k_line_tile(int64_t* __restrict__ y, int64_t batch, const __grid_constant__ Tile
     for (int ax = 0; ax < G.naxes; ax++) {
       const bool sc = scale && ax == G.naxes - 1;
       switch (G.p[ax]) {
-        case 3: tile_axis<KIND, 3, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
-        case 5: tile_axis<KIND, 5, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
-        case 7: tile_axis<KIND, 7, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
-        case 11: tile_axis<KIND, 11, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
-        default: tile_axis<KIND, 13, I, MULTI>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 3: tile_axis<KIND, 3, I, MULTI, RED>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 5: tile_axis<KIND, 5, I, MULTI, RED>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 7: tile_axis<KIND, 7, I, MULTI, RED>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        case 11: tile_axis<KIND, 11, I, MULTI, RED>(line_tile, G, ax, cnt, Z, sc, sps); break;
+        default: tile_axis<KIND, 13, I, MULTI, RED>(line_tile, G, ax, cnt, Z, sc, sps); break;
       }
       __syncthreads();
     }
@@ -437,6 +494,8 @@ static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
     G->threads = sh.threads;
   }
   G->epb = (int32_t)epb;
+  // an element too large for two CTAs per SM (m = 5824, tupSize 4: 110 KB with the staging buffer): twice the threads in the one CTA
+  if ((size_t)epb * nk * 12 > 72 * 1024 && G->threads <= 256) G->threads *= 2;
   for (int i = 0; i < cnt; i++) {
     G->p[i] = p[i]; G->rts[i] = (int32_t)(r[i] * pl->k); G->lines[i] = (int32_t)(nk / (p[i] - 1));
     G->m_rts[i] = magic_div((uint32_t)(r[i] * pl->k));
@@ -447,8 +506,7 @@ static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
 template <int KIND>
 static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st)
 {
-  bool narrow = true;
-  for (int t = 0; t < pl->k; t++) narrow = narrow && (int64_t)zc.q[t] * line_mult<KIND>(13) < ((int64_t)1 << 31);
+  const int mode = line_tile_mode(KIND, zc, pl->k);
   const size_t smem = (size_t)G.epb * G.n * (sizeof(uint32_t) + sizeof(int64_t)) + 16;      // u32 tile + the raw staging buffer of the next group
   const int64_t groups = (batch + G.epb - 1) / G.epb;
   int per_sm = (int)(200 * 1024 / (smem + 1024));
@@ -461,8 +519,13 @@ static int launch_line_tile(const lolb_plan* pl, const TileGeom& G, const ZqCons
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) kern<<<(int)grid, G.threads, smem, st>>>(y, batch, G, zc, scale ? 1 : 0);
   };
-  if (pl->k == 1) { if (narrow) go(k_line_tile<KIND, true, false>); else go(k_line_tile<KIND, false, false>); }
-  else if (narrow) go(k_line_tile<KIND, true, true>);
+  constexpr bool GINV = KIND == PASS_GINVPOW || KIND == PASS_GINVDEC;
+  if (pl->k == 1) {
+    if (mode == 1) go(k_line_tile<KIND, 1, false>);
+    else if (mode == 2) { if constexpr (GINV) go(k_line_tile<KIND, 2, false>); }
+    else go(k_line_tile<KIND, 0, false>);
+  } else if (mode == 1) go(k_line_tile<KIND, 1, true>);
+  else if (mode == 2) { if constexpr (GINV) go(k_line_tile<KIND, 2, true>); }
   else return LOLB_FUSED_UNAVAILABLE;      // several limbs in the 64-bit mode: the register-tile launches (fused_stream_line routes them there)
   if (e != cudaSuccess) return cuda_fail(e, "k_line_tile shared memory");
   e = cudaGetLastError();
@@ -490,8 +553,7 @@ const char* fused_stream_line_name(const lolb_plan* pl, bool ginv)
   int ns;
   int route = line_route(pl, st, &ns, &G);
   if (route == 2 && pl->k > 1) {      // several limbs: the tile kernel in its 32-bit mode only (fused_stream_line)
-    const ZqConsts& zc = ginv ? pl->zq_radinv : pl->zq_plain;
-    for (int t = 0; t < pl->k; t++) if ((int64_t)zc.q[t] * (ginv ? 13 * 13 : 13 + 2) >= ((int64_t)1 << 31)) route = 3;
+    if (line_tile_mode(ginv ? PASS_GINVPOW : PASS_L, ginv ? pl->zq_radinv : pl->zq_plain, pl->k) == 0) route = 3;
   }
   return route == 0 ? "identity" : route == 2 ? "line_tile" : route > 0 ? "line_stream" : "generic";
 }
@@ -507,10 +569,7 @@ int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool sc
   // several limbs in the tile kernel pay off in its 32-bit mode (m = 5824, tupSize 2 / 4: L 77 % / 52 % against 47 % for the register
   // tiles); in the 64-bit mode (25-bit moduli under /g) the register-tile launches are as fast or faster (35 % / 29 % against 35 % / 37 %)
   bool tile_ok = route == 2 && !((uintptr_t)y & 15);
-  if (tile_ok && pl->k > 1 && ns > 1) {
-    const int64_t mult = (kind == PASS_GINVPOW || kind == PASS_GINVDEC) ? 13 * 13 : 13 + 2;      // line_mult<KIND>(13)
-    for (int t = 0; t < pl->k; t++) tile_ok = tile_ok && (int64_t)zc.q[t] * mult < ((int64_t)1 << 31);
-  }
+  if (tile_ok && pl->k > 1 && ns > 1) tile_ok = line_tile_mode(kind, zc, pl->k) != 0;
   if (tile_ok) {
     switch (kind) {
       case PASS_L: return launch_line_tile<PASS_L>(pl, TG, zc, scale, y, batch, st);

@@ -904,7 +904,8 @@ def test_complex_kernels_write_inside_their_batch_only(torch_cuda, m, k):
 
 # moduli on both sides of the thresholds of the line kernels' 32-bit mode: (P + 2) q < 2^31 for L, L^-1, *g and P^2 q < 2^31 for /g
 LINE_MODE_EDGES = [(2912, 143165569), (2912, 143171393), (2912, 12655553), (2912, 12719617), (14400, 306748801), (14400, 306864001),
-                   (14400, 85852801), (14400, 85924801), (1728, 429496129), (1728, 429501313), (1728, 238600513), (1728, 238610881)]
+                   (14400, 85852801), (14400, 85924801), (1728, 429496129), (1728, 429501313), (1728, 238600513), (1728, 238610881),
+                   (2912, 55033889), (2912, 55080481), (5460, 19393921)]      # /g with running sums kept reduced: 78 q < 2^32
 
 
 @pytest.mark.parametrize("m,q", LINE_MODE_EDGES, ids=lambda v: str(v))
@@ -981,7 +982,8 @@ def test_tgaussiandec_one_pass_equals_draw_then_transform(torch_cuda, gpu_oracle
         assert rel_err(two[b].cpu().numpy(), gpu_oracle.tensorGaussianDec(raw[b].cpu().numpy(), pe, ruc)) <= FLOAT_TOL
 
 
-@pytest.mark.parametrize("m,qs", [(2912, [143165569, 143171393]), (2912, [12655553, 3144961, 12719617]), (5460, [3144961, 21841]), (91, [547, 911, 1093, 2003, 2549])],
+@pytest.mark.parametrize("m,qs", [(2912, [143165569, 143171393]), (2912, [12655553, 3144961, 12719617]), (5460, [3144961, 21841]), (91, [547, 911, 1093, 2003, 2549]),
+                                  (5824, [25159681, 19918081, 19393921, 18869761]), (2912, [55033889, 8737])],
                          ids=lambda v: str(v))
 def test_line_tile_several_limbs(torch_cuda, gpu_oracle, m, qs):
     """`k_line_tile` with tupSize folded into the strides: limbs on both sides of the int32 / int64 thresholds in one element, an odd
