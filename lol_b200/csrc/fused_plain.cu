@@ -369,7 +369,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Two tile buffers (NBUF = 2, everything but GEN): the next group's elements arrive by cp.async (16-byte, L2-only) while the
 // passes run on the current one, so one CTA overlaps its own HBM reads with its arithmetic instead of relying on co-resident CTAs.
 template <class R, int KIND, bool GEN>
-__global__ void __launch_bounds__(256, KIND == PASS_GAUSS ? (GEN ? 3 : 2) : 1)
+__global__ void __launch_bounds__((KIND == PASS_GAUSS && !GEN) ? 192 : 256, KIND == PASS_GAUSS ? 3 : 1)      // Gaussian transform: 192-thread CTAs, three per SM (<= 113 registers)
 k_plain_tile(typename R::IO* __restrict__ y, int64_t batch, const __grid_constant__ PTileGeom G, const __grid_constant__ GaussAll E,
              double rscale, uint64_t seed, uint64_t first, double var2, typename R::IO* __restrict__ out)
 {
@@ -601,9 +601,9 @@ bool ptile_geom(const lolb_plan* pl, int fold_k, size_t tsize, int quad /* 0 lin
   static const int tile_bytes = [] { const char* e = getenv("LOLB_PLAIN_TILE_BYTES"); return e ? atoi(e) : 40960; }();
   static const int epb_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_EPB"); return e ? atoi(e) : 0; }();
   static const int thr_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_THREADS"); return e ? atoi(e) : 0; }();
-  TileShape sh = choose_tile_shape(n, p, cnt, tsize, (size_t)tile_bytes, quad != 0, quad == 2 ? 2 : 1);
+  TileShape sh = choose_tile_shape(n, p, cnt, tsize, (size_t)tile_bytes, quad != 0, quad == 2 ? 2 : 1, quad == 2 ? 192 : 256);
   if (epb_env > 0) sh.epb = epb_env;
-  if (thr_env >= 32 && thr_env <= 256) sh.threads = thr_env / 32 * 32;
+  if (thr_env >= 32 && thr_env <= (quad == 2 ? 192 : 256)) sh.threads = thr_env / 32 * 32;
   const int64_t epb = sh.epb;
   G->threads = sh.threads;
   G->n = (int32_t)n;
@@ -623,7 +623,9 @@ int launch_plain_tile(const lolb_plan* pl, const PTileGeom& G, const GaussAll& E
 {
   const size_t smem = (size_t)G.epb * G.n * sizeof(typename R::T) * (GEN ? 1 : 2);      // two tile buffers: k_plain_tile prefetches the next group
   const int64_t groups = (batch + G.epb - 1) / G.epb;
-  int per_sm = (int)(200 * 1024 / (smem + 1024));
+  // CTAs per SM: the Gaussian transform takes everything that fits (228 KB per SM, 1 KB reserved per CTA: three CTAs of two 36 KB
+  // buffers, 56 -> 60 %); the light operators measured faster with one CTA less (L at m = 2912: 86 % against 79 %)
+  int per_sm = (int)((KIND == PASS_GAUSS ? 227 : 200) * 1024 / (smem + 1024));
   if (per_sm > 2048 / G.threads) per_sm = 2048 / G.threads;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)pl->num_sms * per_sm;

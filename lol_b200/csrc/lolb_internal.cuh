@@ -152,15 +152,15 @@ struct PerDeviceOnce {
 // per CTA) with the least idle work -- an axis weighs (p - 1) per line, (p - 1)^2 for dense matrices -- and, within 2 %, the
 // smallest tile (more CTAs per SM overlap one CTA's loads with another's passes), then the larger CTA.
 struct TileShape { int threads, epb; };
-inline TileShape choose_tile_shape(int64_t n, const int* p, int cnt, size_t value_bytes, size_t cap_bytes, bool quad, int lines_per_thread = 1)
+inline TileShape choose_tile_shape(int64_t n, const int* p, int cnt, size_t value_bytes, size_t cap_bytes, bool quad, int lines_per_thread = 1, int max_threads = 256)
 {
   int64_t cap = (int64_t)(cap_bytes / ((size_t)n * value_bytes));
   if (cap < 1) cap = 1;
   if (cap > 64) cap = 64;
-  TileShape best{256, 1};
+  TileShape best{max_threads, 1};
   double best_w = 1e30;
   for (int64_t e = 1; e <= cap; e++)
-    for (int t = 256; t >= 128; t -= 32) {
+    for (int t = max_threads; t >= 128; t -= 32) {
       double used = 0.0, work = 0.0;
       for (int i = 0; i < cnt; i++) {
         const double w = quad ? (double)(p[i] - 1) * (p[i] - 1) : (double)(p[i] - 1);
