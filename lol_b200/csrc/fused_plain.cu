@@ -621,6 +621,7 @@ template <class R, int KIND, bool GEN>
 int launch_plain_tile(const lolb_plan* pl, const PTileGeom& G, const GaussAll& E, typename R::IO* y, int64_t batch, double rscale,
                       uint64_t seed, uint64_t first, double var2, cudaStream_t st, typename R::IO* out = nullptr)
 {
+  if ((uintptr_t)y & 15) return LOLB_FUSED_UNAVAILABLE;      // 16-byte accesses (cp.async, vector stores): an odd word offset goes to the generic engine
   const size_t smem = (size_t)G.epb * G.n * sizeof(typename R::T) * (GEN ? 1 : 2);      // two tile buffers: k_plain_tile prefetches the next group
   const int64_t groups = (batch + G.epb - 1) / G.epb;
   // CTAs per SM: the Gaussian transform takes everything that fits (228 KB per SM, 1 KB reserved per CTA: three CTAs of two 36 KB

@@ -902,6 +902,42 @@ def test_complex_kernels_write_inside_their_batch_only(torch_cuda, m, k):
     assert bool(torch.isfinite(torch.view_as_real(body)).all()) and float(torch.view_as_real(body).abs().max()) < 1e6
 
 
+@pytest.mark.parametrize("m,k", [(2912, 1), (5460, 2), (91, 3), (11648, 1), (4095, 1)], ids=lambda v: str(v))
+@pytest.mark.parametrize("B", [1, 37], ids=lambda v: f"B={v}")
+def test_plain_tile_kernels_write_inside_their_batch_only(torch_cuda, m, k, B):
+    """Guard zones around a ragged batch for `k_plain_tile` (cp.async prefetch of the NEXT group, two tile buffers): the line
+    operators over int64 / double / complex, the Gaussian transform, the one-pass tGaussianDec and the norm (which must not
+    write its input at all)."""
+    torch = torch_cuda
+    from lol_b200 import capi
+    from lol_b200.tensor import CudaTensorComplex, CudaTensorInt, CudaTensorReal
+    st = int(torch.cuda.current_stream().cuda_stream)
+    G = 2048
+    for cls, dtype, sent, names in ((CudaTensorInt, torch.int64, -0x5A5A5A5A5A5A5A5B, ("LR", "LInvR", "GPowR", "GDecR")),
+                                    (CudaTensorReal, torch.float64, -7.25e300, ("LDouble", "LInvDouble")),
+                                    (CudaTensorComplex, torch.complex128, complex(-7.25e300, 3.5e299), ("LC", "GPowC", "GInvDecC"))):
+        t = cls(m, k)
+        n = t.n
+        buf = torch.full((G + B * n * k + G,), sent, dtype=dtype, device="cuda")
+        body = buf[G:G + B * n * k].view(B, n, k)
+        body.copy_(torch.randint(-9, 10, (B, n, k), device="cuda").to(dtype))
+        ptr = buf.data_ptr() + buf.element_size() * G
+        for name in names:
+            capi.check(t.plan.op(name, ptr, B, st))
+        if cls is CudaTensorReal and k == 1:
+            capi.check(t.plan.op("GaussianDec", ptr, B, st))
+            before = body.clone()
+            out = torch.empty(B, 1, dtype=dtype, device="cuda")
+            capi.check(t.plan.normsq("D", ptr, out.data_ptr(), B, st))
+            assert torch.equal(body, before) and bool(torch.isfinite(out).all())
+            capi.check(t.plan.t_gaussian_dec(0.3, 7, 0, ptr, B, st))
+        torch.cuda.synchronize()
+        guard = torch.tensor(sent, dtype=dtype, device="cuda")
+        assert bool((buf[:G] == guard).all()) and bool((buf[G + B * n * k:] == guard).all()), cls.__name__
+        flat = torch.view_as_real(body) if dtype == torch.complex128 else body
+        assert bool((flat != (sent.real if isinstance(sent, complex) else sent)).all())
+
+
 # moduli on both sides of the thresholds of the line kernels' 32-bit mode: (P + 2) q < 2^31 for L, L^-1, *g and P^2 q < 2^31 for /g
 LINE_MODE_EDGES = [(2912, 143165569), (2912, 143171393), (2912, 12655553), (2912, 12719617), (14400, 306748801), (14400, 306864001),
                    (14400, 85852801), (14400, 85924801), (1728, 429496129), (1728, 429501313), (1728, 238600513), (1728, 238610881),
@@ -972,6 +1008,11 @@ def test_tgaussiandec_one_pass_equals_draw_then_transform(torch_cuda, gpu_oracle
     from lol_b200.tensor import CudaTensorReal
     t = CudaTensorReal(m)
     assert t.plan.kernel_name("GaussianDec") == "plain_tile"
+    # a batch that starts at an odd word (8-byte aligned only) takes the generic engine instead of the 16-byte accesses
+    odd = torch.randn(3 * t.n + 1, dtype=torch.float64, device="cuda")
+    view = odd[1:].view(3, t.n, 1)
+    assert view.data_ptr() % 16 == 8
+    assert rel_err(t.gaussianDecTransform(view.clone()).cpu().numpy(), t.gaussianDecTransform(view, inplace=True).cpu().numpy()) <= 1e-12
     v, B = 0.37, 23
     one = t.tGaussianDec(v, B, seed=9, first=5)
     raw = t.realGaussians(v * (m // radical_fact(m)), B, seed=9, first=5)
