@@ -11,4 +11,8 @@ for m, qs in rings:
     print(m, len(qs), {o: t.plan.kernel_name(o) for o in ops})
 for m in (14400, 1728, 2912, 11648, 2048):
     t = CudaTensorComplex(m)
-    print(m, "complex", {o: t.plan.kernel_name(o) for o in ("CRTC", "CRTInvC")})
+    print(m, "complex", {o: t.plan.kernel_name(o) for o in ("CRTC", "CRTInvC", "LC", "GPowC")})
+from lol_b200.tensor import CudaTensorReal
+for m in (14400, 1728, 2912, 3640, 5460, 4095, 11648, 2048):
+    t = CudaTensorReal(m)
+    print(m, "double", {o: t.plan.kernel_name(o) for o in ("GaussianDec", "LDouble")})
