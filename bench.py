@@ -509,7 +509,7 @@ def run_gpu_arm(args):
             del dgt, tg
             torch.cuda.empty_cache()
         # complex CRT of the other benchmark rings: the fused_w schedule over complex doubles, the pass engine beside it
-        for mt, bt in ((1728, 131072), (2912, 65536), (11648, 16384)):
+        for mt, bt in ((1728, 131072), (2912, 65536), (11648, 16384), (2048, 65536)):
             tw = CudaTensorComplex(mt)
             cw = torch.randn(bt, tw.n, 1, dtype=torch.complex128, device="cuda")
             for name in ("CRTC", "CRTInvC"):

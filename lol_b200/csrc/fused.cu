@@ -43,6 +43,12 @@ void fused_ac_release(void* slot);
 bool fused_ac_available(const void* slot, bool inverse);
 int fused_ac_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st);
 
+// fused_pow2c.cu
+int fused_pow2c_select(lolb_plan* pl, void** slot);
+void fused_pow2c_release(void* slot);
+bool fused_pow2c_available(const void* slot, bool inverse);
+int fused_pow2c_crt(const lolb_plan* pl, const void* slot, bool inverse, double2* y, int64_t batch, cudaStream_t st);
+
 // fused_stream.cu
 const char* fused_stream_line_name(const lolb_plan* pl, bool ginv);
 int fused_stream_line(const lolb_plan* pl, int kind, const ZqConsts& zc, bool scale, int64_t* y, int64_t batch, cudaStream_t st);
@@ -56,6 +62,7 @@ struct FusedSet {
   void* pow2_df = nullptr;  // m = 2^e CRT / CRT^-1, dataflow kernel with an L2 exchange ring (13 <= e <= 16)
   void* w = nullptr;        // m = 2^a x odd prime powers (1728, 5184, 2912, 728, 3640, 2016, ...) CRT / CRT^-1
   void* wc = nullptr;       // the same schedule over complex doubles (tensorCRTC / tensorCRTInvC of those indices)
+  void* pow2c = nullptr;    // m = 2^e complex CRT / CRT^-1 (tupSize 1, e <= 14)
 };
 FusedSet* set_of(const lolb_plan* pl) { return (FusedSet*)pl->fused; }
 }  // namespace
@@ -66,6 +73,7 @@ int fused_select(lolb_plan* pl)
     if (!pl->fused) pl->fused = new FusedSet();
     int rc = fused_ac_select(pl, &set_of(pl)->ac);
     if (!rc) rc = fused_wc_select(pl, &set_of(pl)->wc);
+    if (!rc) rc = fused_pow2c_select(pl, &set_of(pl)->pow2c);
     return rc;
   }
   if (pl->kind != PLAN_RQ) return LOLB_OK;
@@ -90,6 +98,7 @@ void fused_release(lolb_plan* pl)
   fused_pow2_release(s->pow2);
   fused_pow2_df_release(s->pow2_df);
   fused_ac_release(s->ac);
+  fused_pow2c_release(s->pow2c);
   delete s;
   pl->fused = nullptr;
 }
@@ -104,6 +113,8 @@ const char* fused_kernel_name(const lolb_plan* pl, const char* op)
     if (!strcmp(op, "CRTInvC") && fused_ac_available(s->ac, true)) return "fused_ac";
     if (!strcmp(op, "CRTC") && fused_wc_available(s->wc, false)) return "fused_w";
     if (!strcmp(op, "CRTInvC") && fused_wc_available(s->wc, true)) return "fused_w";
+    if (!strcmp(op, "CRTC") && fused_pow2c_available(s->pow2c, false)) return "fused_pow2c";
+    if (!strcmp(op, "CRTInvC") && fused_pow2c_available(s->pow2c, true)) return "fused_pow2c";
     if (!strcmp(op, "CRT") && fused_a_available(s->a, false)) return "fused_a";
     if (!strcmp(op, "CRTInv") && fused_a_available(s->a, true)) return "fused_a";
     if (!strcmp(op, "CRT") && fused_w_available(s->w, false)) return "fused_w";
@@ -158,6 +169,7 @@ int fused_crt_c(const lolb_plan* pl, bool inverse, double2* y, int64_t batch, cu
   if (!s) return LOLB_FUSED_UNAVAILABLE;
   int rc = fused_ac_crt(pl, s->ac, inverse, y, batch, st);
   if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_wc_crt(pl, s->wc, inverse, y, batch, st);
+  if (rc == LOLB_FUSED_UNAVAILABLE) rc = fused_pow2c_crt(pl, s->pow2c, inverse, y, batch, st);
   return rc;
 }
 

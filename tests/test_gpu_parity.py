@@ -561,6 +561,43 @@ def test_complex_crt_fused_w_rings(torch_cuda, gpu_oracle, m, k):
     assert rel_err(t.crtInv(x).cpu().numpy(), g.cpu().numpy()) <= 1e-11
 
 
+@pytest.mark.parametrize("e", [3, 4, 5, 6, 8, 10, 11, 12, 13, 14], ids=lambda v: f"m=2^{v}")
+def test_complex_crt_power_of_two(torch_cuda, gpu_oracle, e):
+    """tensorCRTC / tensorCRTInvC for m = 2^e on `k_pow2c` (twist-free Cooley-Tukey rounds over complex doubles, two rounds per
+    pass, e - 1 odd and even, one and several elements per CTA, prefetched and single-buffer sizes): per element against the
+    oracle (crt.cpp:583-598; 1e-9), the ragged batch against the generic pass engine, crtInv . crt = id; guard zones around the batch."""
+    torch = torch_cuda
+    from lol_b200.tensor import CudaTensorComplex
+    m = 1 << e
+    B = 37 if e <= 11 else 5
+    rng = np.random.default_rng(e)
+    pe = T.pe_array(m)
+    t = CudaTensorComplex(m)
+    assert t.plan.kernel_name("CRTC") == "fused_pow2c" and t.plan.kernel_name("CRTInvC") == "fused_pow2c"
+    c = rng.normal(size=(B, t.n, 1)) + 1j * rng.normal(size=(B, t.n, 1))
+    G = 512
+    sent = complex(-7.25e300, 3.5e299)
+    buf = torch.full((G + B * t.n + G,), sent, dtype=torch.complex128, device="cuda")
+    x = buf[G:G + B * t.n].view(B, t.n, 1)
+    x.copy_(torch.from_numpy(c))
+    ruc, ruci = T.ru_tables_c(m), T.ru_tables_c(m, inverse=True)
+    f, g = t.crt(x), t.crtInv(x)
+    for b in (0, B // 2, B - 1):
+        assert rel_err(f[b].cpu().numpy(), gpu_oracle.tensorCRTC(c[b], pe, ruc)) <= FLOAT_TOL
+        assert rel_err(g[b].cpu().numpy(), gpu_oracle.tensorCRTInvC(c[b], pe, ruci, T.mhat_inv_c(m))) <= FLOAT_TOL
+    assert rel_err(t.crtInv(f).cpu().numpy(), c) <= 1e-11
+    t.crt(x, inplace=True)
+    torch.cuda.synchronize()
+    guard = torch.tensor(sent, dtype=torch.complex128, device="cuda")
+    assert bool((buf[:G] == guard).all()) and bool((buf[G + B * t.n:] == guard).all())
+    assert rel_err(x.cpu().numpy(), f.cpu().numpy()) <= 1e-14
+    t.plan.force_generic(True)
+    assert t.plan.kernel_name("CRTC") == "generic"
+    xs = torch.from_numpy(c).cuda()
+    assert rel_err(t.crt(xs).cpu().numpy(), f.cpu().numpy()) <= 1e-11
+    assert rel_err(t.crtInv(xs).cpu().numpy(), g.cpu().numpy()) <= 1e-11
+
+
 @pytest.mark.parametrize("m", [9, 25, 7, 21, 45, 14400, 64 * 27, 89, 91, 77, 33, 728, 2912, 3640, 5460, 4095, 11648], ids=str)
 def test_plain_rings_streaming_equals_generic_engine(torch_cuda, oracle, m):
     """The streaming kernels of the modulus-free rings (one or two small odd primes) against the generic pass
