@@ -7,8 +7,8 @@
 //     inverse   (u, t) -> (u + t, (u - t) T'),  T' = ruinv[(2p+1) n / 2^(r+1)]    rounds descending, then * mhat^-1
 // Over C a different evaluation order changes the rounding only: parity with the reference is to 1e-9 relative (observed 1e-15).
 //
-// Schedule: the elements of a group live in a shared-memory tile of complex doubles; two rounds per pass (a thread owns the four
-// values pos + {0, 1, 2, 3} 2^r: both rounds in registers, one barrier per pass), a last single round when e - 1 is odd; the next
+// Schedule: the elements of a group live in a (padded) shared-memory tile of complex doubles; up to three rounds per pass (a thread owns the
+// 2^S values pos + j 2^r: the rounds in registers, one barrier per pass; passes of three rounds, the remainder in twos); the next
 // group arrives by cp.async while the passes run (two buffers) when two buffers fit, else one buffer with plain loads.  The n - 1
 // twiddles of a direction are one table in global memory (entry 2^r - 1 + p), read through the read-only path.  32 n bytes of HBM
 // traffic per element, one read and one write.  Larger elements than the shared memory holds (n > 8192) and tupSize > 1 stay on the
@@ -29,11 +29,17 @@ struct Pow2C {
 
 struct Pow2CGeom {
   int32_t n, rounds, epb, nbuf;
+  int32_t npass;
+  int8_t pr[8], ps[8];             // pass i of the forward transform: rounds pr[i] .. pr[i] + ps[i] - 1 (ps = 1, 2 or 3); the inverse runs them backwards
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// tile index of value i: one 16-byte slot of padding after every eight values, so that the stride-4 quads of the first pass (a thread
+// owns four consecutive values = 64 bytes) fall in different bank groups for the eight threads of a quarter warp (4-way conflicts before)
+__device__ __host__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
 
 // one round on the pair (u, t)
 template <bool INV>
@@ -50,13 +56,42 @@ __device__ __forceinline__ void bfly(double2& u, double2& t, const double2 T)
   }
 }
 
+// S rounds (r .. r + S - 1) on the 2^S values pos + j 2^r of a thread, bits r .. r + S - 1 of pos clear; value j sits at position
+// pos + j 2^r, so in round r + s its twiddle index is (pos + j 2^r) mod 2^(r+s) = p + (j mod 2^s) 2^r
+template <bool INV, int S>
+__device__ __forceinline__ void pow2c_pass(double2* x, const int vals, const int r, const double2* __restrict__ tw)
+{
+  constexpr int V = 1 << S;
+  const int st = 1 << r;
+  const int groups = vals >> S;
+  for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+    const int p = i & (st - 1);
+    const int pos = ((i >> r) << (r + S)) | p;
+    int ix[V];
+    double2 v[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) { ix[j] = pad8(pos + j * st); v[j] = x[ix[j]]; }
+#pragma unroll
+    for (int ss = 0; ss < S; ss++) {
+      const int s = INV ? S - 1 - ss : ss;
+      const int half = 1 << s;
+      const double2* row = tw + ((st << s) - 1) + p;
+#pragma unroll
+      for (int a = 0; a < V; a++)
+        if (!(a & half)) bfly<INV>(v[a], v[a + half], __ldg(row + (a & (half - 1)) * st));
+    }
+#pragma unroll
+    for (int j = 0; j < V; j++) x[ix[j]] = v[j];
+  }
+}
+
 template <bool INV>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 k_pow2c(double2* __restrict__ y, int64_t batch, const __grid_constant__ Pow2CGeom G, const double2* __restrict__ tw, double2 scale)
 {
   extern __shared__ __align__(16) unsigned char pow2c_raw[];
-  const int n = G.n, R = G.rounds;
-  const int buf_vals = G.epb * n;
+  const int n = G.n;
+  const int buf_vals = pad8(G.epb * n) + 1;      // padded values per buffer
   const int64_t ngroups = (batch + G.epb - 1) / G.epb;
   auto prefetch = [&](int64_t g, int buf) {
     const int64_t e0 = g * G.epb;
@@ -64,7 +99,7 @@ k_pow2c(double2* __restrict__ y, int64_t batch, const __grid_constant__ Pow2CGeo
     const double2* src = y + (size_t)e0 * n;
     double2* dst = reinterpret_cast<double2*>(pow2c_raw) + (size_t)buf * buf_vals;
     for (int i = threadIdx.x; i < vals; i += blockDim.x) {
-      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + pad8(i));
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -87,49 +122,23 @@ k_pow2c(double2* __restrict__ y, int64_t batch, const __grid_constant__ Pow2CGeo
 #pragma unroll
         for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; r[u] = i < vals ? __ldcs(dst + i) : make_double2(0.0, 0.0); }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; if (i < vals) x[i] = r[u]; }
+        for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; if (i < vals) x[pad8(i)] = r[u]; }
       }
       __syncthreads();
     }
-    // ---- passes of two rounds (r, r + 1); forward ascending, inverse descending; a single round is left over when R is odd
-    const int npass = R / 2, odd = R & 1;
-    for (int ps = 0; ps < npass + odd; ps++) {
-      // forward: pairs first (rounds 0-1, 2-3, ...), the single round last; inverse: the mirror image
-      const int idx = INV ? (npass + odd - 1 - ps) : ps;
-      const bool single = odd && idx == npass;
-      const int r = 2 * idx;                                   // the single round is round R - 1 = 2 npass
-      const int st = 1 << r;
-      if (!single) {
-        const int quads = vals >> 2;
-        for (int i = threadIdx.x; i < quads; i += blockDim.x) {
-          const int p = i & (st - 1);
-          const int pos = ((i >> r) << (r + 2)) | p;           // bits r and r + 1 clear
-          double2 v0 = x[pos], v1 = x[pos + st], v2 = x[pos + 2 * st], v3 = x[pos + 3 * st];
-          const double2 Ta = __ldg(tw + (st - 1) + p);                     // round r: p = pos mod 2^r for both pairs
-          const double2 Tb0 = __ldg(tw + (2 * st - 1) + p), Tb1 = __ldg(tw + (2 * st - 1) + p + st);      // round r + 1: pos mod 2^(r+1)
-          if (!INV) {
-            bfly<false>(v0, v1, Ta); bfly<false>(v2, v3, Ta);
-            bfly<false>(v0, v2, Tb0); bfly<false>(v1, v3, Tb1);
-          } else {
-            bfly<true>(v0, v2, Tb0); bfly<true>(v1, v3, Tb1);
-            bfly<true>(v0, v1, Ta); bfly<true>(v2, v3, Ta);
-          }
-          x[pos] = v0; x[pos + st] = v1; x[pos + 2 * st] = v2; x[pos + 3 * st] = v3;
-        }
-      } else {
-        const int pairs = vals >> 1;
-        for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-          const int p = i & (st - 1);
-          const int pos = ((i >> r) << (r + 1)) | p;
-          double2 u = x[pos], t = x[pos + st];
-          bfly<INV>(u, t, __ldg(tw + (st - 1) + p));
-          x[pos] = u; x[pos + st] = t;
-        }
+    // ---- passes of up to three rounds; forward ascending, inverse descending
+    for (int q = 0; q < G.npass; q++) {
+      const int idx = INV ? G.npass - 1 - q : q;
+      const int r = G.pr[idx];
+      switch (G.ps[idx]) {
+        case 3: pow2c_pass<INV, 3>(x, vals, r, tw); break;
+        case 2: pow2c_pass<INV, 2>(x, vals, r, tw); break;
+        default: pow2c_pass<INV, 1>(x, vals, r, tw); break;
       }
       __syncthreads();
     }
     for (int i = threadIdx.x; i < vals; i += blockDim.x) {
-      double2 v = x[i];
+      double2 v = x[pad8(i)];
       if (INV) v = cmul(v, scale);
       __stcs(dst + i, v);
     }
@@ -192,14 +201,24 @@ int fused_pow2c_crt(const lolb_plan* pl, const void* slot, bool inverse, double2
   Pow2CGeom G{};
   G.n = 1 << (F->e - 1);
   G.rounds = F->e - 1;
+  {      // rounds in passes of three, the remainder as passes of two (R = 3a: 3..3; 3a + 2: 3..3 2; 3a + 1: 3..3 2 2; R = 2: 2; R = 4: 2 2)
+    int R = G.rounds, r = 0, np = 0;
+    int threes = R / 3;
+    const int rem = R % 3;
+    if (rem == 1 && threes > 0) threes--;
+    for (int i = 0; i < threes; i++) { G.pr[np] = (int8_t)r; G.ps[np++] = 3; r += 3; }
+    while (R - r >= 2) { G.pr[np] = (int8_t)r; G.ps[np++] = 2; r += 2; }
+    if (R - r == 1) { G.pr[np] = (int8_t)r; G.ps[np++] = 1; r += 1; }
+    G.npass = np;
+  }
   const size_t el = (size_t)G.n * sizeof(double2);
-  G.nbuf = 2 * el <= 96 * 1024 ? 2 : 1;                         // n <= 2048: the next group prefetched into a second buffer
+  G.nbuf = 2 * el <= 80 * 1024 ? 2 : 1;                         // n <= 2048: the next group prefetched into a second buffer
   int64_t epb = (int64_t)(16 * 1024 / el);                      // small rings: several elements per CTA (at least 1024 values)
   if (epb < 1) epb = 1;
   G.epb = (int32_t)epb;
-  const size_t smem = (size_t)G.epb * el * G.nbuf;
+  const size_t smem = (size_t)(pad8((int)(G.epb * G.n)) + 1) * sizeof(double2) * G.nbuf;
   const int64_t groups = (batch + G.epb - 1) / G.epb;
-  const int threads = F->e >= 14 ? 1024 : F->e == 13 ? 512 : 256;      // one or two resident CTAs for the large elements: more threads in each
+  const int threads = F->e >= 13 ? 512 : 256;      // one or two resident CTAs for the large elements: more threads in each
   int per_sm = (int)(200 * 1024 / (smem + 1024));
   if (per_sm > 2048 / threads) per_sm = 2048 / threads;
   if (per_sm < 1) per_sm = 1;
