@@ -602,7 +602,7 @@ bool ptile_geom(const lolb_plan* pl, int fold_k, size_t tsize, int quad /* 0 lin
   static const int epb_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_EPB"); return e ? atoi(e) : 0; }();
   static const int thr_env = [] { const char* e = getenv("LOLB_PLAIN_TILE_THREADS"); return e ? atoi(e) : 0; }();
   TileShape sh = choose_tile_shape(n, p, cnt, tsize, (size_t)tile_bytes, quad != 0, quad == 2 ? 2 : 1, quad == 2 ? 192 : 256);
-  if (epb_env > 0) sh.epb = epb_env;
+  if (epb_env > 0) sh.epb = epb_env < 64 ? epb_env : 64;      // the norm's per-element partial sums are sized for 64 elements
   if (thr_env >= 32 && thr_env <= (quad == 2 ? 192 : 256)) sh.threads = thr_env / 32 * 32;
   const int64_t epb = sh.epb;
   G->threads = sh.threads;

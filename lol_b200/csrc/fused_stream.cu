@@ -471,8 +471,7 @@ static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
 {
   int p[4]; int64_t r[4];
   const int cnt = odd_axes(pl, p, r);
-  static const bool multi = [] { const char* e = getenv("LOLB_LINE_TILE_MULTI"); return !e || atoi(e) != 0; }();
-  if ((pl->k != 1 && !multi) || pl->k > kMaxLimbs || cnt < 1 || cnt > 4) return false;
+  if (pl->k > kMaxLimbs || cnt < 1 || cnt > 4) return false;
   for (int i = 0; i < cnt; i++) if (p[i] != 3 && p[i] != 5 && p[i] != 7 && p[i] != 11 && p[i] != 13) return false;
   const int64_t nk = (int64_t)pl->n * pl->k;
   if ((nk & 1) || nk > 16384) return false;      // 12 bytes of shared memory per word
@@ -481,18 +480,12 @@ static bool line_tile_geom(const lolb_plan* pl, TileGeom* G)
   G->m_k = magic_div((uint32_t)pl->k);
   G->naxes = cnt;
   // measured 2048 / 4096 / 8192 / 16384 words per CTA: m = 2912 L 50 / 60 / 55 / 58 %, m = 5460 38 / 49 / 47 / 46 % of HBM
-  // round 2, last: the CTA shape (threads, elements) that leaves no idle threads in the last round of an axis pass
-  // (lolb_internal.cuh::choose_tile_shape) within `tile_words`; LOLB_LINE_TILE_SHAPE=0 keeps 256 threads x tile_words / n elements
+  // the CTA shape (threads, elements) that leaves no idle threads in the last round of an axis pass
+  // (lolb_internal.cuh::choose_tile_shape) within `tile_words` (LOLB_LINE_TILE_WORDS: tuning runs; 4096 measured best)
   static const int tile_words = [] { const char* e = getenv("LOLB_LINE_TILE_WORDS"); return e ? atoi(e) : 4096; }();
-  static const bool shaped = [] { const char* e = getenv("LOLB_LINE_TILE_SHAPE"); return !e || atoi(e) != 0; }();
-  int64_t epb = tile_words / nk;
-  if (epb < 1) epb = 1;
-  G->threads = 256;
-  if (shaped) {
-    const TileShape sh = choose_tile_shape(nk, p, cnt, sizeof(uint32_t), (size_t)tile_words * sizeof(uint32_t), false);
-    epb = sh.epb;
-    G->threads = sh.threads;
-  }
+  const TileShape sh = choose_tile_shape(nk, p, cnt, sizeof(uint32_t), (size_t)tile_words * sizeof(uint32_t), false);
+  const int64_t epb = sh.epb;
+  G->threads = sh.threads;
   G->epb = (int32_t)epb;
   // an element too large for two CTAs per SM (m = 5824, tupSize 4: 110 KB with the staging buffer): twice the threads in the one CTA
   if ((size_t)epb * nk * 12 > 72 * 1024 && G->threads <= 256) G->threads *= 2;
