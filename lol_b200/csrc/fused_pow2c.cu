@@ -10,7 +10,7 @@
 // Schedule: the elements of a group live in a (padded) shared-memory tile of complex doubles; up to three rounds per pass (a thread owns the
 // 2^S values pos + j 2^r: the rounds in registers, one barrier per pass; passes of three rounds, the remainder in twos); the next
 // group arrives by cp.async while the passes run (two buffers) when two buffers fit, else one buffer with plain loads.  The n - 1
-// twiddles of a direction are one table in global memory (entry 2^r - 1 + p), read through the read-only path.  32 n bytes of HBM
+// twiddles of a direction are one table in global memory (entry 2^r - 1 + p), one read per thread and pass.  32 n bytes of HBM
 // traffic per element, one read and one write.  Larger elements than the shared memory holds (n > 8192) and tupSize > 1 stay on the
 // generic engines.
 #include <vector>
@@ -25,6 +25,7 @@ struct Pow2C {
   bool ok_fwd = false, ok_inv = false;
   int e = 0;                       // m = 2^e, n = 2^(e-1)
   double2* d_tw = nullptr;         // [2][n]: forward table then inverse table, entry (2^r - 1) + p
+  double2 rot1[2], rot2[2];        // per direction: table[n/2] and table[n/4] (root^(n/2) = +-i, root^(n/4))
 };
 
 struct Pow2CGeom {
@@ -57,9 +58,14 @@ __device__ __forceinline__ void bfly(double2& u, double2& t, const double2 T)
 }
 
 // S rounds (r .. r + S - 1) on the 2^S values pos + j 2^r of a thread, bits r .. r + S - 1 of pos clear; value j sits at position
-// pos + j 2^r, so in round r + s its twiddle index is (pos + j 2^r) mod 2^(r+s) = p + (j mod 2^s) 2^r
+// pos + j 2^r, so in round r + s its twiddle index is (pos + j 2^r) mod 2^(r+s) = p + (j mod 2^s) 2^r.
+// One table read per thread and pass: with W = T_{r+S-1}[p] the other twiddles follow from the table's own structure,
+//   T_{rho-1}[p] = T_rho[p]^2   and   T_{r+s}[p + j 2^r] = T_{r+s}[p] * root^(j n / 2^s),
+// where root^(n/2) (`rot1`) and root^(n/4) (`rot2`) are read from the caller's table on the host -- the L1 / shared-memory pipe
+// is this kernel's limiter (ncu: 78 % busy with seven 16-byte table reads per eight values), the FP64 pipe is not (25 %).
 template <bool INV, int S>
-__device__ __forceinline__ void pow2c_pass(double2* x, const int vals, const int r, const double2* __restrict__ tw)
+__device__ __forceinline__ void pow2c_pass(double2* x, const int vals, const int r, const double2* __restrict__ tw, const double2 rot1,
+                                           const double2 rot2)
 {
   constexpr int V = 1 << S;
   const int st = 1 << r;
@@ -71,14 +77,24 @@ __device__ __forceinline__ void pow2c_pass(double2* x, const int vals, const int
     double2 v[V];
 #pragma unroll
     for (int j = 0; j < V; j++) { ix[j] = pad8(pos + j * st); v[j] = x[ix[j]]; }
+    // W[s][j] = T_{r+s}[p + j 2^r], j < 2^s
+    double2 W[S][V / 2];
+    W[S - 1][0] = __ldg(tw + ((st << (S - 1)) - 1) + p);
+#pragma unroll
+    for (int s = S - 2; s >= 0; s--) W[s][0] = cmul(W[s + 1][0], W[s + 1][0]);
+    if constexpr (S >= 2) W[1][1] = cmul(W[1][0], rot1);
+    if constexpr (S >= 3) {
+      W[2][1] = cmul(W[2][0], rot2);
+      W[2][2] = cmul(W[2][0], rot1);
+      W[2][3] = cmul(W[2][1], rot1);
+    }
 #pragma unroll
     for (int ss = 0; ss < S; ss++) {
       const int s = INV ? S - 1 - ss : ss;
       const int half = 1 << s;
-      const double2* row = tw + ((st << s) - 1) + p;
 #pragma unroll
       for (int a = 0; a < V; a++)
-        if (!(a & half)) bfly<INV>(v[a], v[a + half], __ldg(row + (a & (half - 1)) * st));
+        if (!(a & half)) bfly<INV>(v[a], v[a + half], W[s][a & (half - 1)]);
     }
 #pragma unroll
     for (int j = 0; j < V; j++) x[ix[j]] = v[j];
@@ -87,7 +103,8 @@ __device__ __forceinline__ void pow2c_pass(double2* x, const int vals, const int
 
 template <bool INV>
 __global__ void __launch_bounds__(512)
-k_pow2c(double2* __restrict__ y, int64_t batch, const __grid_constant__ Pow2CGeom G, const double2* __restrict__ tw, double2 scale)
+k_pow2c(double2* __restrict__ y, int64_t batch, const __grid_constant__ Pow2CGeom G, const double2* __restrict__ tw, double2 scale,
+        double2 rot1, double2 rot2)
 {
   extern __shared__ __align__(16) unsigned char pow2c_raw[];
   const int n = G.n;
@@ -131,9 +148,9 @@ k_pow2c(double2* __restrict__ y, int64_t batch, const __grid_constant__ Pow2CGeo
       const int idx = INV ? G.npass - 1 - q : q;
       const int r = G.pr[idx];
       switch (G.ps[idx]) {
-        case 3: pow2c_pass<INV, 3>(x, vals, r, tw); break;
-        case 2: pow2c_pass<INV, 2>(x, vals, r, tw); break;
-        default: pow2c_pass<INV, 1>(x, vals, r, tw); break;
+        case 3: pow2c_pass<INV, 3>(x, vals, r, tw, rot1, rot2); break;
+        case 2: pow2c_pass<INV, 2>(x, vals, r, tw, rot1, rot2); break;
+        default: pow2c_pass<INV, 1>(x, vals, r, tw, rot1, rot2); break;
       }
       __syncthreads();
     }
@@ -167,6 +184,8 @@ int fused_pow2c_select(lolb_plan* pl, void** slot)
   for (int dir = 0; dir < 2; dir++) {
     if (!(dir ? F->ok_inv : F->ok_fwd)) continue;
     const std::vector<lolb_complex>& T = dir ? pl->cruinv[0] : pl->cru[0];
+    F->rot1[dir] = make_double2(T[(size_t)n / 2].real, T[(size_t)n / 2].imag);
+    F->rot2[dir] = make_double2(T[(size_t)n / 4].real, T[(size_t)n / 4].imag);
     for (int r = 0; r < e - 1; r++)
       for (int p = 0; p < (1 << r); p++) {
         const lolb_complex w = T[(size_t)(2 * p + 1) * (size_t)(n >> (r + 1))];
@@ -229,7 +248,7 @@ int fused_pow2c_crt(const lolb_plan* pl, const void* slot, bool inverse, double2
   cudaError_t e = cudaSuccess;
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) kern<<<(int)grid, threads, smem, st>>>(y, batch, G, tw, scale);
+    if (e == cudaSuccess) kern<<<(int)grid, threads, smem, st>>>(y, batch, G, tw, scale, F->rot1[inverse ? 1 : 0], F->rot2[inverse ? 1 : 0]);
   };
   if (inverse) go(k_pow2c<true>); else go(k_pow2c<false>);
   if (e != cudaSuccess) return cuda_fail(e, "k_pow2c shared memory");
