@@ -654,7 +654,8 @@ def run_gpu_arm(args):
                "prf_k2": [fr("HomomPRF H1'=F64*F7*F13 ZQ2", "CRT"), fr("HomomPRF H1'=F64*F7*F13 ZQ2", "CRTInv")],
                "prf_k4": [fr("HomomPRF H1'=F64*F7*F13 ZQ4", "CRT"), fr("HomomPRF H1'=F64*F7*F13 ZQ4", "CRTInv")],
                "crtC": [fr("cfg4", "tensorCRTC"), fr("cfg4", "tensorCRTInvC")], "gauss": fr("cfg4", "tensorGaussianDec"),
-               "gauss2912": fr("error m=2912", "tensorGaussianDec"), "gauss11648": fr("error m=11648", "tensorGaussianDec")}
+               "gauss2912": fr("error m=2912", "tensorGaussianDec"), "gauss11648": fr("error m=11648", "tensorGaussianDec"),
+               "crtC2048": [fr("cfg4", "m=2048 tensorCRTC"), fr("cfg4", "m=2048 tensorCRTInvC")]}
     for s, n, ms, _, units, _ in rec.rows:
         if s == "she" and n == "mulAndSwitch":
             summary["she_n"] = round(world * units / (ms * 1e-3))
