@@ -592,16 +592,19 @@ def run_gpu_arm(args):
         full = torch.randint(0, QS[0], (Bn, N_COEFF, 1), dtype=torch.int64, device="cuda", generator=gen) if rank == 0 else None
         loc = scatter_batch(full, Bn, (N_COEFF, 1), torch.int64, torch.device("cuda", local))      # warm-up (NCCL channels)
         gather_batch(loc, Bn)
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        loc = scatter_batch(full, Bn, (N_COEFF, 1), torch.int64, torch.device("cuda", local))
-        torch.cuda.synchronize(); dist.barrier()
-        t1 = time.perf_counter()
-        back = gather_batch(loc, Bn)
-        torch.cuda.synchronize(); dist.barrier()
-        t2 = time.perf_counter()
+        ts, tg = [], []
+        for _ in range(3):      # ~1 ms transfers timed on the host clock: the best of three (an allocation or a late rank costs as much as the copy)
+            torch.cuda.synchronize(); dist.barrier()
+            t0 = time.perf_counter()
+            loc = scatter_batch(full, Bn, (N_COEFF, 1), torch.int64, torch.device("cuda", local))
+            torch.cuda.synchronize(); dist.barrier()
+            t1 = time.perf_counter()
+            back = gather_batch(loc, Bn)
+            torch.cuda.synchronize(); dist.barrier()
+            t2 = time.perf_counter()
+            ts.append(reduce_max(t1 - t0)); tg.append(reduce_max(t2 - t1))
         moved = (Bn - 4096) * N_COEFF * 8
-        shard_io = {"bytes_over_nvlink": moved, "scatter_GB/s": moved / reduce_max(t1 - t0) / 1e9, "gather_GB/s": moved / reduce_max(t2 - t1) / 1e9,
+        shard_io = {"bytes_over_nvlink": moved, "scatter_GB/s": moved / min(ts) / 1e9, "gather_GB/s": moved / min(tg) / 1e9, "samples": 3,
                     "roundtrip_identical": bool(rank != 0 or torch.equal(back, full))}
         del full, loc, back
 
