@@ -136,3 +136,115 @@ def test_twace_crt_chunked_accumulation_never_overflows():
                     assert acc <= M64
                 acc = barrett_u64(acc, q, mu)
             assert acc == sum(x * t for x, t in zip(xs, ts)) % q
+
+
+# ---------------------------------------------------------------- fused_stream.cu: the line operators' 32-bit modes
+M32 = (1 << 32) - 1
+
+
+def barrett32(x, q, mu32):
+    """fused_stream.cu barrett32: x < 2^32, mu32 = floor(2^32 / q) -> x mod q (one conditional subtraction through min)."""
+    assert 0 <= x <= M32
+    r = (x - ((x * mu32) >> 32) * q) & M32
+    assert r < 2 * q
+    return min(r, (r - q) & M32)
+
+
+def ginv_exact(v, p, kind):
+    """line_op over the integers (g.cpp:60-123): GINVPOW / GINVDEC on one line of p - 1 values."""
+    d = p - 1
+    v = list(v)
+    if kind == "pow":
+        lo, hi = sum(v), 0
+        for a in range(d - 1, -1, -1):
+            z = v[a]
+            v[a] = (p - 1 - a) * lo - (a + 1) * hi
+            lo -= z
+            hi += z
+    else:
+        acc = sum((a + 1) * v[a] for a in range(d))
+        for a in range(d - 1, 0, -1):
+            keep = acc
+            acc -= v[a] * p
+            v[a] = keep
+        v[0] = acc
+    return v
+
+
+def ginv_red(v, p, kind, q):
+    """lineop_ginv_red: the same recurrences with every running value kept in [0, q), all arithmetic in wrapping uint32."""
+    d, mu32 = p - 1, (1 << 32) // q
+    v = list(v)
+    if kind == "pow":
+        s = sum(v)
+        assert s <= M32
+        lo, hi = barrett32(s, q, mu32), 0
+        for a in range(d - 1, -1, -1):
+            z = v[a]
+            x = (p - 1 - a) * lo + p * q - (a + 1) * hi
+            assert 0 <= x <= M32
+            v[a] = barrett32(x, q, mu32)
+            lo = lo - z if lo >= z else lo + q - z
+            hi += z
+            hi = hi - q if hi >= q else hi
+            assert 0 <= lo < q and 0 <= hi < q
+    else:
+        s = sum((a + 1) * v[a] for a in range(d))
+        assert s <= M32
+        acc = barrett32(s, q, mu32)
+        for a in range(d - 1, 0, -1):
+            keep = acc
+            x = acc + p * q - p * v[a]
+            assert 0 <= x <= M32
+            acc = barrett32(x, q, mu32)
+            v[a] = keep
+        v[0] = acc
+    return v
+
+
+def test_division_by_g_with_reduced_running_sums_stays_in_32_bits():
+    """The third arithmetic mode of k_line_tile (line_tile_mode == 2): valid for 78 q < 2^32 at p <= 13; extreme and random lines,
+    moduli up to the bound, against the exact integers reduced modulo q."""
+    rnd = random.Random(7)
+    bound = (1 << 32) // 78
+    for q in (3, 8737, 3144961, 12719617, 19393921, 25159681, 55033889, bound):
+        for p in (3, 5, 7, 11, 13):
+            d = p - 1
+            lines = [[q - 1] * d, [0] * d, [q - 1 if a % 2 else 0 for a in range(d)], [0 if a % 2 else q - 1 for a in range(d)]]
+            lines += [[rnd.randrange(q) for _ in range(d)] for _ in range(40)]
+            for v in lines:
+                for kind in ("pow", "dec"):
+                    want = [x % q for x in ginv_exact(v, p, kind)]
+                    assert ginv_red(v, p, kind, q) == want, (q, p, kind, v)
+
+
+def test_line_operator_intermediates_fit_the_32_bit_mode():
+    """line_mult (fused_stream.cu): L, L^-1, *g keep |intermediates| <= (p + 2) q - the bias added before the reduction and the
+    int32 range are sized from it; the divisions by g need p^2 q.  Checked on the extreme lines with exact integers."""
+    for p in (3, 5, 7, 11, 13):
+        d, q = p - 1, 1000003
+        ext = [[q - 1] * d, [q - 1 if a % 2 else 0 for a in range(d)], [0 if a % 2 else q - 1 for a in range(d)]]
+        for v0 in ext:
+            v = list(v0)                                   # L
+            for a in range(1, d):
+                v[a] += v[a - 1]
+            assert max(abs(x) for x in v) <= (p + 2) * q
+            v = list(v0)                                   # L^-1
+            for a in range(d - 1, 0, -1):
+                v[a] -= v[a - 1]
+            assert max(abs(x) for x in v) <= (p + 2) * q
+            v = list(v0)                                   # *g, powerful basis
+            last = v[d - 1]
+            for a in range(d - 1, 0, -1):
+                v[a] += last - v[a - 1]
+            v[0] += last
+            assert max(abs(x) for x in v) <= (p + 2) * q
+            v = list(v0)                                   # *g, decoding basis
+            acc = v[0]
+            for a in range(d - 1, 0, -1):
+                acc += v[a]
+                v[a] -= v[a - 1]
+            v[0] += acc
+            assert max(abs(x) for x in v) <= (p + 2) * q and abs(acc) <= (p + 2) * q
+            for kind in ("pow", "dec"):
+                assert max(abs(x) for x in ginv_exact(v0, p, kind)) <= p * p * q
